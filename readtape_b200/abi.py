@@ -1,0 +1,285 @@
+"""ctypes binding of the C-ABI declared in include/rt_scan.h.
+
+Two shared libraries export that ABI:
+  * readtape_b200/lib/librt_scan_b200.so  -- the product (CUDA, sm_100a)
+  * oracle/_ref/libscan_oracle.so          -- the test-only CPU oracle
+`load_product()` fails loudly when the CUDA library is missing: there is no CPU fallback.
+`load_oracle()` may only be used by tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import tbin as _tbin
+
+RT_MAXTRKS = 19
+RT_HEAD_IGNORE = RT_MAXTRKS - 1
+RT_OK, RT_MISS = 0, 1
+RT_ERR_UNSUPPORTED = -4
+
+RT_F_FIND_ZEROS, RT_F_DIFFERENTIATE, RT_F_INVERT, RT_F_DENSITY_DETECT, RT_F_DESKEWING = 1, 2, 4, 8, 16
+RT_RESET_NONE, RT_RESET_FULL, RT_RESET_WW_PARTIAL, RT_RESET_PEAKSTATE = 0, 1, 2, 3
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT_LIB = os.path.join(_ROOT, "readtape_b200", "lib", "librt_scan_b200.so")
+ORACLE_LIB = os.path.join(_ROOT, "oracle", "_ref", "libscan_oracle.so")
+
+
+class TapeDesc(C.Structure):
+    _fields_ = [("ntrks", C.c_uint32), ("nheads", C.c_uint32), ("head_to_trk", C.c_int32 * RT_MAXTRKS),
+                ("maxvolts", C.c_float), ("tdelta_ns", C.c_uint64), ("tstart_ns", C.c_uint64)]
+
+
+class Parms(C.Structure):
+    _fields_ = [("clk_window", C.c_int32), ("clk_alpha", C.c_float), ("agc_window", C.c_int32),
+                ("agc_alpha", C.c_float), ("min_peak", C.c_float), ("clk_factor", C.c_float),
+                ("pulse_adj", C.c_float), ("pkww_bitfrac", C.c_float), ("pkww_rise", C.c_float),
+                ("z1pt", C.c_float), ("z2pt", C.c_float)]
+
+
+class ScanCfg(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("flags", C.c_uint32), ("bpi", C.c_float), ("ips", C.c_float),
+                ("parms", Parms), ("skew_delaycnt", C.c_int32 * RT_MAXTRKS)]
+
+
+class BulkStats(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("units", C.c_uint64), ("events", C.c_uint64),
+                ("rows_scanned", C.c_uint64), ("track_samples", C.c_uint64),
+                ("ms_preprocess", C.c_double), ("ms_units", C.c_double), ("ms_scan", C.c_double),
+                ("launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+EVENT_DTYPE = np.dtype([("row", "<u8"), ("t_event", "<f8"), ("v_top", "<f4"), ("v_bot", "<f4"),
+                        ("agc_gain", "<f4"), ("trk", "u1"), ("kind", "u1"), ("pad", "u1", (2,))])
+assert EVENT_DTYPE.itemsize == 32
+
+EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_attach_device",
+           "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
+           "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
+           "rt_bulk_scan", "rt_bulk_lookup", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
+           "rt_row_time"]
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rt_scan error {code}: {msg}")
+        self.code = code
+
+
+class Lib:
+    """A loaded implementation of the rt_scan C-ABI."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing -- build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "readtape_b200 has no CPU fallback.")
+        self.path = path
+        L = self.L = C.CDLL(path)
+        vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+        P = C.POINTER
+        L.rt_last_error.restype = C.c_char_p
+        L.rt_backend.restype = C.c_char_p
+        L.rt_abi_version.restype = i32
+        L.rt_open.argtypes = [P(TapeDesc), i32, P(vp)]
+        L.rt_upload.argtypes = [vp, vp, u64]
+        L.rt_attach_device.argtypes = [vp, vp, u64]
+        L.rt_nrows.argtypes = [vp]; L.rt_nrows.restype = u64
+        L.rt_close.argtypes = [vp]; L.rt_close.restype = None
+        L.rt_host_alloc.argtypes = [C.c_size_t]; L.rt_host_alloc.restype = vp
+        L.rt_host_free.argtypes = [vp]; L.rt_host_free.restype = None
+        L.rt_scan_begin.argtypes = [vp, P(ScanCfg), P(vp)]
+        L.rt_scan_reset.argtypes = [vp, i32, u64]
+        L.rt_scan_run.argtypes = [vp, u64, P(vp), P(u64), P(u64)]
+        L.rt_scan_rewind.argtypes = [vp, u64]
+        L.rt_scan_set_avg_height.argtypes = [vp, u32, C.c_float]
+        L.rt_scan_set_cfg.argtypes = [vp, P(ScanCfg)]
+        L.rt_scan_pos.argtypes = [vp]; L.rt_scan_pos.restype = u64
+        L.rt_scan_end.argtypes = [vp]; L.rt_scan_end.restype = None
+        L.rt_bulk_scan.argtypes = [vp, P(ScanCfg), u32, P(vp)]
+        L.rt_bulk_lookup.argtypes = [vp, u32, u64, P(vp), P(u64), P(u64)]
+        L.rt_bulk_get_stats.argtypes = [vp, P(BulkStats)]
+        L.rt_bulk_free.argtypes = [vp]; L.rt_bulk_free.restype = None
+        L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
+        L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
+        for fn in ("rt_open", "rt_upload", "rt_attach_device", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
+                   "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_lookup",
+                   "rt_bulk_get_stats", "rt_pkww_width"):
+            getattr(L, fn).restype = i32
+
+    @property
+    def backend(self) -> str:
+        return self.L.rt_backend().decode()
+
+    def check(self, rc: int) -> int:
+        if rc < 0:
+            raise RtError(rc, self.L.rt_last_error().decode(errors="replace"))
+        return rc
+
+    def open(self, desc: TapeDesc, device: int = 0) -> "Tape":
+        h = C.c_void_p()
+        self.check(self.L.rt_open(C.byref(desc), device, C.byref(h)))
+        return Tape(self, h, desc)
+
+
+def _events_from(ptr: C.c_void_p, n: int) -> np.ndarray:
+    if n == 0 or not ptr.value:
+        return np.zeros(0, dtype=EVENT_DTYPE)
+    buf = (C.c_char * (n * EVENT_DTYPE.itemsize)).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=EVENT_DTYPE, count=n).copy()
+
+
+class Tape:
+    def __init__(self, lib: Lib, handle, desc: TapeDesc):
+        self.lib, self.h, self.desc = lib, handle, desc
+
+    def upload(self, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype="<i2")
+        assert rows.ndim == 2 and rows.shape[1] == self.desc.nheads
+        self.lib.check(self.lib.L.rt_upload(self.h, rows.ctypes.data, rows.shape[0]))
+
+    def attach_device(self, dev_ptr: int, nrows: int) -> None:
+        self.lib.check(self.lib.L.rt_attach_device(self.h, dev_ptr, nrows))
+
+    @property
+    def nrows(self) -> int:
+        return int(self.lib.L.rt_nrows(self.h))
+
+    def scan(self, cfg: ScanCfg) -> "Scan":
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.rt_scan_begin(self.h, C.byref(cfg), C.byref(h)))
+        return Scan(self, h)
+
+    def bulk_scan(self, cfgs) -> "Bulk":
+        arr = (ScanCfg * len(cfgs))(*cfgs)
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.rt_bulk_scan(self.h, arr, len(cfgs), C.byref(h)))
+        return Bulk(self, h)
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.L.rt_close(self.h)
+            self.h = None
+
+
+class Scan:
+    def __init__(self, tape: Tape, handle):
+        self.tape, self.lib, self.h = tape, tape.lib, handle
+
+    def reset(self, kind: int, row: int) -> None:
+        self.lib.check(self.lib.L.rt_scan_reset(self.h, kind, row))
+
+    def run(self, nrows: int):
+        ev, n, done = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self.lib.check(self.lib.L.rt_scan_run(self.h, nrows, C.byref(ev), C.byref(n), C.byref(done)))
+        return _events_from(ev, n.value), int(done.value)
+
+    def rewind(self, row: int) -> None:
+        self.lib.check(self.lib.L.rt_scan_rewind(self.h, row))
+
+    def set_cfg(self, cfg: ScanCfg) -> None:
+        self.lib.check(self.lib.L.rt_scan_set_cfg(self.h, C.byref(cfg)))
+
+    def set_avg_height(self, trk: int, v: float) -> None:
+        self.lib.check(self.lib.L.rt_scan_set_avg_height(self.h, trk, v))
+
+    @property
+    def pos(self) -> int:
+        return int(self.lib.L.rt_scan_pos(self.h))
+
+    def end(self) -> None:
+        if self.h:
+            self.lib.L.rt_scan_end(self.h)
+            self.h = None
+
+
+class Bulk:
+    def __init__(self, tape: Tape, handle):
+        self.tape, self.lib, self.h = tape, tape.lib, handle
+
+    def lookup(self, cfg_index: int, start_row: int):
+        """-> (events, valid_rows) or None on RT_MISS."""
+        ev, n, valid = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        rc = self.lib.check(self.lib.L.rt_bulk_lookup(self.h, cfg_index, start_row, C.byref(ev), C.byref(n),
+                                                      C.byref(valid)))
+        if rc == RT_MISS:
+            return None
+        return _events_from(ev, n.value), int(valid.value)
+
+    def stats(self) -> BulkStats:
+        st = BulkStats()
+        self.lib.check(self.lib.L.rt_bulk_get_stats(self.h, C.byref(st)))
+        return st
+
+    def free(self) -> None:
+        if self.h:
+            self.lib.L.rt_bulk_free(self.h)
+            self.h = None
+
+
+_cache: dict[str, Lib] = {}
+
+
+def load(path: str) -> Lib:
+    if path not in _cache:
+        _cache[path] = Lib(path)
+    return _cache[path]
+
+
+def load_product() -> Lib:
+    """The CUDA library.  Raises if it has not been built -- there is no fallback."""
+    return load(PRODUCT_LIB)
+
+
+def load_oracle() -> Lib:
+    """TEST INFRASTRUCTURE: the CPU oracle (see oracle/scan_oracle.c)."""
+    return load(ORACLE_LIB)
+
+
+# ---- helpers to build the PODs -------------------------------------------------------------
+def make_desc(ntrks: int, maxvolts: float, tdelta_ns: int, tstart_ns: int, nheads: int | None = None,
+              head_to_trk=None) -> TapeDesc:
+    d = TapeDesc()
+    d.ntrks = ntrks
+    d.nheads = nheads if nheads is not None else ntrks
+    h2t = list(head_to_trk) if head_to_trk is not None else list(range(d.nheads))
+    for i in range(RT_MAXTRKS):
+        d.head_to_trk[i] = h2t[i] if i < len(h2t) else RT_HEAD_IGNORE
+    d.maxvolts = maxvolts
+    d.tdelta_ns = tdelta_ns
+    d.tstart_ns = tstart_ns
+    return d
+
+
+def desc_from_header(hdr: _tbin.TbinHeader, ntrks: int | None = None, order: str | None = None) -> TapeDesc:
+    """Mirror of process_file()'s head/track bookkeeping (readtape.c:1646-1648, parse_track_order :877)."""
+    n = ntrks or hdr.ntrks
+    if hdr.mode == _tbin.MODE_WW or (order and any(c in "CLMclmx" for c in order) and not order[0].isdigit()):
+        order = order or hdr.trkorder
+        h2t, nt = [], 0
+        for ch in order:
+            if ch == "x":
+                h2t.append(RT_HEAD_IGNORE)
+            else:
+                h2t.append(nt)
+                nt += 1
+        return make_desc(nt, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns, nheads=len(order), head_to_trk=h2t)
+    h2t = list(range(n))
+    if order and (hdr.flags & _tbin.TBIN_NO_REORDER):   # a permutation given with -order= is only honoured
+        h2t = []                                        # when csvtbin did not already reorder (readtape.c:1646-1648)
+        for ch in order:
+            h2t.append(n - 1 if ch in "pP" else int(ch))
+    return make_desc(n, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns, head_to_trk=h2t)
+
+
+def make_cfg(mode: int, parms: dict, bpi: float, ips: float, flags: int = 0, skew=None) -> ScanCfg:
+    c = ScanCfg()
+    c.mode, c.flags, c.bpi, c.ips = mode, flags, bpi, ips
+    for name, _ in Parms._fields_:
+        setattr(c.parms, name, parms.get(name, 0))
+    for i in range(RT_MAXTRKS):
+        c.skew_delaycnt[i] = int(skew[i]) if skew is not None and i < len(skew) else 0
+    return c
