@@ -1,0 +1,216 @@
+/* readtape_b200/csrc/k_ingest.cu -- K1: TBIN rows -> track-major planes + quiet map.
+ *
+ * Replaces the per-row fread()+convert loop of readblock() (reference src/readtape.c:1405-1425)
+ * for the whole capture at once.  The TBIN payload is row-interleaved: nheads little-endian
+ * int16 per row (18-byte pitch for 9 tracks, csvtbin.h:98-105).  Every later kernel walks ONE
+ * track sequentially, so the first thing done with the bytes is a transpose into track-major
+ * int16 planes (head->track permutation applied, unused Whirlwind heads dropped), together
+ * with the min/max of every 32-row granule per track (the map the unit finder reads) and the
+ * position of the end-of-data marker (-32768 in head 0, readtape.c:1410).
+ *
+ * This is the bandwidth-bound kernel of the pipeline: 2 B read + 2 B written per track-sample.
+ * Layout of the work (sm_100a):
+ *   - persistent CTAs (grid = #SMs x CTAs/SM), each loops over row tiles of TILE_ROWS rows;
+ *   - tiles are staged into shared memory by the TMA engine with 1-D bulk async copies
+ *     (cp.async.bulk ... mbarrier::complete_tx), NSTAGE deep, full/empty mbarrier pairs;
+ *   - each thread owns 8 consecutive rows of the tile = NH x 16 bytes of contiguous shared
+ *     memory, read with NH conflict-free LDS.128, de-interleaved in registers (static
+ *     indexing, NH is a template parameter) and written as one coalesced STG.128 per track;
+ *   - granule min/max: per-thread partials to shared memory, reduced 4:1 after a CTA barrier.
+ * A plain-load kernel (k_ingest_simple) covers odd head counts, unaligned sources and tails.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rt_dev.h"
+#include "kernels.h"
+
+#define ING_THREADS   256
+#define ING_TROWS     (ING_THREADS * 8)      /* 2048 rows per tile */
+#define ING_NSTAGE    4
+
+struct IngestArgs {
+   const int16_t *src;        /* interleaved rows of this upload chunk (device) */
+   uint64_t nrows;            /* rows in this chunk */
+   uint64_t row_base;         /* tape row of src row 0 (multiple of RT_GRAN unless it is the final append) */
+   int16_t *planes; uint64_t plane_stride;
+   int16_t *gmm;              /* [ntrks][ngran_cap][2] */
+   uint64_t ngran_cap;
+   unsigned long long *first_end_row;
+   int32_t trk_of_head[RT_MAXTRKS];   /* -1: dropped */
+};
+
+/* ---- PTX helpers (mbarrier + 1-D bulk TMA) --------------------------------------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+   asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory"); }
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory"); }
+
+/* ---- per-thread de-interleave of 8 rows -------------------------------------------------------- */
+template <int NH>
+__device__ __forceinline__ void deinterleave8(const uint32_t (&w)[NH * 4], const IngestArgs &a, uint64_t row0 /* tape row */,
+                                              uint32_t *part /* smem [NH][ING_THREADS] packed min|max<<16 or null */, int tid) {
+   /* w holds 8 rows x NH halfwords, row-major; element (r,h) is halfword r*NH+h */
+#pragma unroll
+   for (int h = 0; h < NH; ++h) {
+      int k = a.trk_of_head[h];
+      uint32_t o[4];
+      int mn = 32767, mx = -32768;
+#pragma unroll
+      for (int r = 0; r < 8; r += 2) {
+         const int e0 = r * NH + h, e1 = (r + 1) * NH + h;
+         uint32_t lo = (e0 & 1) ? (w[e0 >> 1] >> 16) : (w[e0 >> 1] & 0xffffu);
+         uint32_t hi = (e1 & 1) ? (w[e1 >> 1] >> 16) : (w[e1 >> 1] & 0xffffu);
+         o[r >> 1] = lo | (hi << 16);
+         int s0 = (int)(int16_t)lo, s1 = (int)(int16_t)hi;
+         mn = min(mn, min(s0, s1)); mx = max(mx, max(s0, s1)); }
+      if (h == 0) {                        /* end-of-data marker, readtape.c:1410 */
+#pragma unroll
+         for (int r = 0; r < 8; ++r) {
+            const int e = r * NH;
+            uint32_t v = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+            if (v == 0x8000u) { atomicMin(a.first_end_row, (unsigned long long)(row0 + r)); break; } } }
+      if (k >= 0) {
+         uint4 q = make_uint4(o[0], o[1], o[2], o[3]);
+         *reinterpret_cast<uint4 *>(a.planes + (size_t)k * a.plane_stride + row0) = q;
+         if (part) part[h * ING_THREADS + tid] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); } } }
+
+template <int NH>
+__global__ void __launch_bounds__(ING_THREADS)
+k_ingest_tma(IngestArgs a, uint64_t ntiles) {
+   extern __shared__ __align__(128) unsigned char smem_raw[];
+   constexpr uint32_t TILE_BYTES = ING_TROWS * NH * 2;
+   unsigned char *stage = smem_raw;                                         /* NSTAGE * TILE_BYTES */
+   uint32_t *part = reinterpret_cast<uint32_t *>(smem_raw + ING_NSTAGE * TILE_BYTES);  /* [NH][ING_THREADS] */
+   uint64_t *full = reinterpret_cast<uint64_t *>(part + NH * ING_THREADS);
+   uint64_t *empty = full + ING_NSTAGE;
+   const int tid = threadIdx.x;
+   if (tid == 0) {
+      for (int s = 0; s < ING_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ING_THREADS / 32); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+   __syncthreads();
+
+   const uint64_t first = blockIdx.x, step = gridDim.x;
+   const uint64_t mine = first < ntiles ? (ntiles - first + step - 1) / step : 0;   /* tiles this CTA processes */
+   /* prologue: fill the pipeline */
+   if (tid == 0) {
+      for (uint64_t i = 0; i < mine && i < ING_NSTAGE; ++i) {
+         mbar_expect_tx(&full[i], TILE_BYTES);
+         tma_load_1d(stage + i * TILE_BYTES, reinterpret_cast<const unsigned char *>(a.src) + (first + i * step) * TILE_BYTES,
+                     TILE_BYTES, &full[i]); } }
+   for (uint64_t i = 0; i < mine; ++i) {
+      const int s = (int)(i % ING_NSTAGE);
+      const uint32_t par = (uint32_t)((i / ING_NSTAGE) & 1);
+      mbar_wait(&full[s], par);
+      /* 8 consecutive rows = NH*16 contiguous bytes; lane stride NH*16 B: conflict-free LDS.128 for odd NH */
+      const uint4 *p = reinterpret_cast<const uint4 *>(stage + s * TILE_BYTES + (size_t)tid * NH * 16);
+      uint32_t w[NH * 4];
+#pragma unroll
+      for (int j = 0; j < NH; ++j) { uint4 q = p[j]; w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w; }
+      /* this thread's copy of the stage is in registers: release the slot to the producer early */
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+      if (tid == 0 && i + ING_NSTAGE < mine) {
+         mbar_wait(&empty[s], par);                                       /* all warps have drained stage s */
+         mbar_expect_tx(&full[s], TILE_BYTES);
+         tma_load_1d(stage + s * TILE_BYTES,
+                     reinterpret_cast<const unsigned char *>(a.src) + (first + (i + ING_NSTAGE) * step) * TILE_BYTES,
+                     TILE_BYTES, &full[s]); }
+      const uint64_t tile = first + i * step;
+      const uint64_t row0 = a.row_base + tile * ING_TROWS + (uint64_t)tid * 8;
+      deinterleave8<NH>(w, a, row0, part, tid);
+      __syncthreads();
+      /* granule = 32 rows = 4 threads: reduce the partials, one (head, granule) per thread */
+      for (int o = tid; o < NH * (ING_THREADS / 4); o += ING_THREADS) {
+         const int h = o / (ING_THREADS / 4), g = o % (ING_THREADS / 4);
+         const int k = a.trk_of_head[h];
+         if (k < 0) continue;
+         const uint4 q = *reinterpret_cast<const uint4 *>(&part[h * ING_THREADS + g * 4]);
+         int mn = min(min((int)(int16_t)(q.x & 0xffff), (int)(int16_t)(q.y & 0xffff)),
+                      min((int)(int16_t)(q.z & 0xffff), (int)(int16_t)(q.w & 0xffff)));
+         int mx = max(max((int)(int16_t)(q.x >> 16), (int)(int16_t)(q.y >> 16)),
+                      max((int)(int16_t)(q.z >> 16), (int)(int16_t)(q.w >> 16)));
+         const uint64_t gran = (a.row_base + tile * ING_TROWS) / RT_GRAN + (uint64_t)g;
+         reinterpret_cast<uint32_t *>(a.gmm)[(size_t)k * a.ngran_cap + gran] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); }
+      __syncthreads(); } }
+
+/* ---- plain-load kernel: any head count, any alignment, partial granules -------------------------- */
+__global__ void __launch_bounds__(256)
+k_ingest_simple(IngestArgs a, uint64_t row_from, uint64_t row_to, int nheads) {
+   /* one warp per (granule, all heads): lane = row within the 32-row granule */
+   const int lane = threadIdx.x & 31;
+   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+   const uint64_t g_from = (a.row_base + row_from) / RT_GRAN, g_to = (a.row_base + row_to + RT_GRAN - 1) / RT_GRAN;
+   for (uint64_t g = g_from + warp; g < g_to; g += nwarps) {
+      const uint64_t trow = g * RT_GRAN + lane;                 /* tape row */
+      const bool ok = trow >= a.row_base + row_from && trow < a.row_base + row_to;
+      const int16_t *r = a.src + (trow - a.row_base) * (uint64_t)nheads;
+      for (int h = 0; h < nheads; ++h) {
+         const int k = a.trk_of_head[h];
+         int v = ok ? (int)r[h] : 0;
+         if (h == 0 && ok && v == -32768) atomicMin(a.first_end_row, (unsigned long long)trow);
+         if (k < 0) continue;
+         if (ok) a.planes[(size_t)k * a.plane_stride + trow] = (int16_t)v;
+         int mn = ok ? v : 32767, mx = ok ? v : -32768;
+#pragma unroll
+         for (int d = 16; d > 0; d >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
+         if (lane == 0) {
+            uint32_t *slot = &reinterpret_cast<uint32_t *>(a.gmm)[(size_t)k * a.ngran_cap + g];
+            if (trow < a.row_base + row_from) {                   /* granule partly filled by an earlier append: merge */
+               uint32_t old = *slot;
+               mn = min(mn, (int)(int16_t)(old & 0xffff)); mx = max(mx, (int)(int16_t)(old >> 16)); }
+            *slot = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); } } } }
+
+/* ---- launcher ------------------------------------------------------------------------------------ */
+template <int NH>
+static cudaError_t launch_tma(const IngestArgs &a, uint64_t ntiles, int sms, cudaStream_t st) {
+   const size_t smem = (size_t)ING_NSTAGE * ING_TROWS * NH * 2 + (size_t)NH * ING_THREADS * 4 + 2 * ING_NSTAGE * 8;
+   static bool configured = false;
+   if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_ingest_tma<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = true; }
+   int grid = (int)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
+   k_ingest_tma<NH><<<grid, ING_THREADS, smem, st>>>(a, ntiles);
+   return cudaGetLastError(); }
+
+cudaError_t launch_ingest(const int16_t *src, uint64_t nrows, uint64_t row_base, int nheads, const int32_t *trk_of_head,
+                          int16_t *planes, uint64_t plane_stride, int16_t *gmm, uint64_t ngran_cap,
+                          unsigned long long *first_end_row, int sms, int force_simple, cudaStream_t st, int *launches) {
+   IngestArgs a;
+   a.src = src; a.nrows = nrows; a.row_base = row_base; a.planes = planes; a.plane_stride = plane_stride;
+   a.gmm = gmm; a.ngran_cap = ngran_cap; a.first_end_row = first_end_row;
+   for (int h = 0; h < RT_MAXTRKS; ++h) a.trk_of_head[h] = h < nheads ? trk_of_head[h] : -1;
+   uint64_t done = 0;
+   const bool aligned = ((uintptr_t)src % 16 == 0) && (row_base % ING_TROWS == 0) && ((uintptr_t)planes % 16 == 0) && (plane_stride % 8 == 0);
+   if (!force_simple && aligned && (nheads == 9 || nheads == 7 || nheads == 6)) {
+      uint64_t ntiles = nrows / ING_TROWS;
+      if (ntiles) {
+         cudaError_t e = nheads == 9 ? launch_tma<9>(a, ntiles, sms, st) : nheads == 7 ? launch_tma<7>(a, ntiles, sms, st)
+                         : launch_tma<6>(a, ntiles, sms, st);
+         if (e != cudaSuccess) return e;
+         ++*launches;
+         done = ntiles * ING_TROWS; } }
+   if (done < nrows) {
+      uint64_t grans = (nrows - done + RT_GRAN - 1) / RT_GRAN + 1;
+      uint64_t blocks = (grans + 7) / 8;
+      if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
+      k_ingest_simple<<<(int)blocks, 256, 0, st>>>(a, done, nrows, nheads);
+      ++*launches; }
+   return cudaGetLastError(); }

@@ -1,0 +1,134 @@
+/* readtape_b200/csrc/k_scan.cu -- scan kernels built on the exact generic per-track scan.
+ *
+ *  k_ctx_reset / k_ctx_scan   the stateful exact scan behind rt_scan_* (one thread per track,
+ *                             state lives in device memory between launches; Whirlwind, retries,
+ *                             anything the speculative scan cannot prove)
+ *  k_units_scan               the speculative whole-tape scan: one thread per (unit, track),
+ *                             fresh RT_RESET_FULL at the unit start, events into the chunk pool,
+ *                             plus the per-track data rt_bulk_lookup() needs for its proof
+ */
+#include "scan_generic.cuh"
+#include "kernels.h"
+
+using namespace rtgen;
+
+/* ---- emitters -------------------------------------------------------------------------------- */
+struct FlatEmit {                 /* per-track flat buffer; counts past capacity so the host can regrow */
+   rt_event *buf; uint32_t cap; uint32_t n; uint8_t trk;
+   __device__ void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
+      if (n < cap) {
+         rt_event e;
+         e.row = row; e.t_event = t_ev; e.v_top = v_top; e.v_bot = v_bot; e.agc_gain = agc;
+         e.trk = trk; e.kind = top ? RT_EV_TOP : RT_EV_BOT; e.pad[0] = e.pad[1] = 0;
+         buf[n] = e; }
+      ++n; } };
+
+struct PoolEmit {                 /* chained fixed-size chunks from a global pool */
+   rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
+   uint32_t first_chunk, cur_chunk, n; uint64_t first_row; uint8_t trk;
+   __device__ void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
+      if (n == 0) first_row = row;
+      uint32_t slot = n % RT_EVC;
+      if (slot == 0) {
+         uint32_t c = atomicAdd(cursor, 1u);          /* counts past capacity: the host regrows and reruns */
+         if (c < cap_chunks) {
+            chunk_next[c] = RT_NOCHUNK;
+            if (n == 0) first_chunk = c; else if (cur_chunk != RT_NOCHUNK) chunk_next[cur_chunk] = c;
+            cur_chunk = c; }
+         else cur_chunk = RT_NOCHUNK; }
+      if (cur_chunk != RT_NOCHUNK) {
+         rt_event e;
+         e.row = row; e.t_event = t_ev; e.v_top = v_top; e.v_bot = v_bot; e.agc_gain = agc;
+         e.trk = trk; e.kind = top ? RT_EV_TOP : RT_EV_BOT; e.pad[0] = e.pad[1] = 0;
+         pool[(size_t)cur_chunk * RT_EVC + slot] = e; }
+      ++n; } };
+
+/* ---- stateful context ---------------------------------------------------------------------- */
+__global__ void k_ctx_reset(DevCfg c, TrkState *st, SkewState *sk, int kind, uint64_t row, int time_is_zero) {
+   int trk = threadIdx.x;
+   if (trk >= c.ntrks) return;
+   TrkState &t = st[trk]; SkewState &s = sk[trk];
+   if (kind == RT_RESET_FULL) reset_full(c, t, s, trk, row, time_is_zero != 0);
+   else if (kind == RT_RESET_WW_PARTIAL) {          /* decode_ww.c:42: t_lastpeak = t_prevlastpeak = 0 */
+      t.t_lastpeak = 0;
+      t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u); }
+   else if (kind == RT_RESET_PEAKSTATE) {           /* decoder.c:413-423 */
+      for (int i = 0; i < RT_MAXSKEWSAMP; ++i) s.vdelayed[i] = 0;
+      s.ndx_next = s.slots_filled = 0;
+      t.left = t.right = 0; t.minv = t.maxv = 0; t.countdown = 0; } }
+
+__global__ void k_ctx_set_avg_height(TrkState *st, int trk, float v) {
+   st[trk].avg_height = v; st[trk].avg_height_count = 0; st[trk].avg_height_sum = 0; }
+
+__global__ void k_ctx_scan(DevCfg c, TrkState *st, SkewState *sk, uint64_t row_from, uint64_t row_to,
+                           rt_event *evbuf, uint32_t cap, uint32_t *counts, uint32_t *failed) {
+   int trk = blockIdx.x * blockDim.x + threadIdx.x;
+   if (trk >= c.ntrks) return;
+   TrkState t = st[trk]; SkewState s = sk[trk];
+   const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
+   FlatEmit em{evbuf + (size_t)trk * cap, cap, 0, (uint8_t)trk};
+   float v;
+   for (uint64_t row = row_from; row < row_to; ++row) track_row(c, t, s, trk, plane, row, em, &v);
+   st[trk] = t; sk[trk] = s;
+   counts[trk] = em.n;
+   if (t.failed) atomicMax(failed, (uint32_t)t.failed); }
+
+/* ---- speculative whole-tape scan (generic detector code) -------------------------------------- */
+__global__ void __launch_bounds__(128)
+k_units_scan(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta *meta,
+             rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
+             float quiet_thr, unsigned long long *rows_scanned) {
+   const uint32_t nunits = *nunits_p;
+   const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
+   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (uint64_t)gridDim.x * blockDim.x) {
+      const uint32_t u = (uint32_t)(f / c.ntrks); const int trk = (int)(f % c.ntrks);
+      const UnitDesc ud = units[u];
+      TrkState t; SkewState s;
+      reset_full(c, t, s, trk, ud.row0, row_time(c, ud.row0) == 0.0);
+      const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
+      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+      uint64_t sync_row = RT_NOROW, last_loud = RT_NOROW;
+      float runmin = 0, runmax = 0; bool have_run = false;
+      for (uint64_t row = ud.row0; row < ud.row_end; ++row) {
+         float v_now;
+         unsigned probe = track_row(c, t, s, trk, plane, row, em, &v_now);
+         if (em.n == 0) {                              /* still before the first event: keep the proof data */
+            if (c.det == RT_DET_PEAK) {
+               if (t.init_row == RT_NOROW) {           /* the track has been initialised */
+                  if (!have_run) { runmin = runmax = v_now; have_run = true; }
+                  if (v_now < runmin) runmin = v_now;
+                  if (v_now > runmax) runmax = v_now;
+                  if (runmax - runmin >= quiet_thr) {  /* re-anchor on the current window; loud only if IT is */
+                     float mx = -100, mn = +100;
+                     for (int ndx = t.left;;) {
+                        float v = t.win[ndx];
+                        if (v > mx) mx = v;
+                        if (v < mn) mn = v;
+                        if (ndx == t.right) break;
+                        if (++ndx >= c.width) ndx = 0; }
+                     runmin = mn; runmax = mx;
+                     if (mx - mn >= quiet_thr) last_loud = row; }
+                  if (probe & 2) sync_row = row; } }
+            else {                                      /* zero-crossing detectors: no window to converge */
+               if (v_now > RT_ZEROCROSS_PEAK || v_now < -RT_ZEROCROSS_PEAK) last_loud = row;
+               sync_row = row; } } }
+      TrkMeta m;
+      m.first_event_row = em.first_row; m.sync_row = sync_row; m.last_loud_row = last_loud;
+      m.first_chunk = em.first_chunk; m.nevents = em.n; m.failed = t.failed; m.pad = 0;
+      meta[f] = m;
+      atomicAdd(rows_scanned, (unsigned long long)(ud.row_end - ud.row0)); } }
+
+/* ---- launchers ------------------------------------------------------------------------------ */
+void launch_ctx_reset(const DevCfg &c, TrkState *st, SkewState *sk, int kind, uint64_t row, int tz, cudaStream_t s) {
+   k_ctx_reset<<<1, 32, 0, s>>>(c, st, sk, kind, row, tz); }
+void launch_ctx_set_avg_height(TrkState *st, int trk, float v, cudaStream_t s) {
+   k_ctx_set_avg_height<<<1, 1, 0, s>>>(st, trk, v); }
+void launch_ctx_scan(const DevCfg &c, TrkState *st, SkewState *sk, uint64_t from, uint64_t to, rt_event *ev,
+                     uint32_t cap, uint32_t *counts, uint32_t *failed, cudaStream_t s) {
+   /* one warp per track would waste 31 lanes; tracks are independent, so spread them over blocks of 1 thread
+      each to get them on different SMs (each is a long serial walk) */
+   k_ctx_scan<<<c.ntrks, 1, 0, s>>>(c, st, sk, from, to, ev, cap, counts, failed); }
+void launch_units_scan(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, TrkMeta *meta, rt_event *pool,
+                       uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, float quiet_thr,
+                       unsigned long long *rows_scanned, int grid, cudaStream_t s) {
+   k_units_scan<<<grid, 128, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr, rows_scanned); }

@@ -1,0 +1,36 @@
+/* readtape_b200/csrc/kernels.h -- host-callable launchers of the CUDA kernels. */
+#ifndef RT_KERNELS_H
+#define RT_KERNELS_H
+#include <cuda_runtime.h>
+#include "rt_dev.h"
+
+namespace rtgen { struct SkewState; }
+struct TrkState;
+
+/* k_ingest.cu */
+cudaError_t launch_ingest(const int16_t *src, uint64_t nrows, uint64_t row_base, int nheads, const int32_t *trk_of_head,
+                          int16_t *planes, uint64_t plane_stride, int16_t *gmm, uint64_t ngran_cap,
+                          unsigned long long *first_end_row, int sms, int force_simple, cudaStream_t st, int *launches);
+
+/* k_units.cu */
+struct UnitParams {
+   int32_t det;            /* RT_DET_* */
+   int32_t thr;            /* peak/dzc: a granule is quiet if max-min <= thr ; zc: if max <= thr and min >= -thr (int16 LSBs) */
+   uint32_t min_gap_gran;  /* a gap is >= this many consecutive all-track-quiet granules */
+   uint64_t tail_rows;     /* a unit keeps scanning this many rows into the next unit */
+};
+cudaError_t launch_find_units(const int16_t *gmm, uint64_t ngran_cap, int ntrks, uint64_t nrows, const UnitParams &up,
+                              uint32_t *d_bitmap, uint32_t *d_flags, uint32_t *d_blockcount, UnitDesc *d_units,
+                              uint32_t units_cap, uint32_t *d_nunits, cudaStream_t st, int *launches);
+size_t units_bitmap_words(uint64_t nrows);
+size_t units_blocks(uint64_t nrows);
+
+/* k_scan.cu */
+void launch_ctx_reset(const DevCfg &c, TrkState *st, rtgen::SkewState *sk, int kind, uint64_t row, int tz, cudaStream_t s);
+void launch_ctx_set_avg_height(TrkState *st, int trk, float v, cudaStream_t s);
+void launch_ctx_scan(const DevCfg &c, TrkState *st, rtgen::SkewState *sk, uint64_t from, uint64_t to, rt_event *ev,
+                     uint32_t cap, uint32_t *counts, uint32_t *failed, cudaStream_t s);
+void launch_units_scan(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, TrkMeta *meta, rt_event *pool,
+                       uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, float quiet_thr,
+                       unsigned long long *rows_scanned, int grid, cudaStream_t s);
+#endif

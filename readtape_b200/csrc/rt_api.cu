@@ -1,0 +1,551 @@
+/* readtape_b200/csrc/rt_api.cu -- host side of librt_scan_b200.so: the C-ABI of include/rt_scan.h.
+ *
+ * Plain CUDA runtime, no torch, no CPU compute path: every scan goes through the kernels in
+ * k_ingest.cu / k_units.cu / k_scan.cu / k_fast.cu.  If no CUDA device (or no sm_100a kernel
+ * image) is usable, rt_open() fails with RT_ERR_NODEVICE -- there is no fallback.
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "scan_generic.cuh"
+#include "kernels.h"
+
+using rtgen::SkewState;
+
+/* ---- errors ------------------------------------------------------------------------------------ */
+static thread_local char g_err[512];
+static int set_err(int code, const char *fmt, ...) {
+   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+   return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+      return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char *rt_last_error(void) { return g_err; }
+extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
+extern "C" const char *rt_backend(void) { return "cuda-sm100a"; }
+
+extern "C" double rt_row_time(const rt_tape_desc *d, uint64_t row) {
+   long long ns = (long long)(d->tstart_ns + row * d->tdelta_ns);
+   return (double)ns / 1e9; }
+
+extern "C" int rt_pkww_width(const rt_scan_cfg *cfg, uint64_t tdelta_ns) {
+   /* readtape.c:1453-1457; host code is compiled without FMA contraction (-Xcompiler -ffp-contract=off) */
+   volatile float sample_deltat = (float)(long long)tdelta_ns / 1e9f;
+   if (cfg->bpi == 0 || (cfg->flags & RT_F_DENSITY_DETECT)) return 8;
+   volatile float a = cfg->bpi * cfg->ips;
+   volatile float b = a * sample_deltat;
+   int w = (int)(cfg->parms.pkww_bitfrac / b);
+   return w < RT_PKWW_MAX_WIDTH ? w : RT_PKWW_MAX_WIDTH; }
+
+/* ---- tape ---------------------------------------------------------------------------------------- */
+struct rt_tape {
+   rt_tape_desc desc{};
+   int device = 0, sms = 148;
+   cudaStream_t stream = nullptr;
+   int32_t trk_of_head[RT_MAXTRKS];
+   uint64_t nrows = 0;            /* rows ingested */
+   uint64_t cap_rows = 0;         /* capacity of the planes, rows */
+   int16_t *planes = nullptr; uint64_t plane_stride = 0;
+   int16_t *gmm = nullptr; uint64_t ngran_cap = 0;
+   unsigned long long *d_first_end = nullptr;
+   uint64_t nrows_valid = 0; bool valid_known = false;
+   int16_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t stage_done[2] = {nullptr, nullptr};
+   int force_simple_ingest = 0;
+   int launches = 0;
+   float ms_ingest = 0;
+};
+
+static int tape_reserve(rt_tape *t, uint64_t rows) {
+   if (rows <= t->cap_rows) return RT_OK;
+   cudaSetDevice(t->device);
+   uint64_t newcap = t->cap_rows ? std::max(rows, t->cap_rows * 2) : rows;
+   newcap = (newcap + 2047) / 2048 * 2048 + 2048;                 /* tile multiple + slack for vector reads */
+   uint64_t ngran = newcap / RT_GRAN + 64;
+   int16_t *np = nullptr, *ng = nullptr;
+   const uint32_t nt = t->desc.ntrks;
+   CU(cudaMalloc(&np, (size_t)newcap * nt * sizeof(int16_t)));
+   cudaError_t e = cudaMalloc(&ng, (size_t)ngran * nt * 4);
+   if (e != cudaSuccess) { cudaFree(np); return set_err(RT_ERR_CUDA, "cudaMalloc(gmm) failed: %s", cudaGetErrorString(e)); }
+   if (t->planes) {
+      for (uint32_t k = 0; k < nt; ++k) {
+         CU(cudaMemcpyAsync(np + (size_t)k * newcap, t->planes + (size_t)k * t->plane_stride, (size_t)t->nrows * 2, cudaMemcpyDeviceToDevice, t->stream));
+         CU(cudaMemcpyAsync(reinterpret_cast<char *>(ng) + (size_t)k * ngran * 4, reinterpret_cast<char *>(t->gmm) + (size_t)k * t->ngran_cap * 4,
+                            (size_t)((t->nrows + RT_GRAN - 1) / RT_GRAN) * 4, cudaMemcpyDeviceToDevice, t->stream)); }
+      CU(cudaStreamSynchronize(t->stream));
+      cudaFree(t->planes); cudaFree(t->gmm); }
+   t->planes = np; t->plane_stride = newcap; t->gmm = ng; t->ngran_cap = ngran; t->cap_rows = newcap;
+   return RT_OK; }
+
+extern "C" int rt_open(const rt_tape_desc *desc, int device, rt_tape **out) {
+   if (!desc || !out) return set_err(RT_ERR_ARG, "rt_open: null argument");
+   if (desc->ntrks < 1 || desc->ntrks > RT_MAXTRKS || desc->nheads < desc->ntrks || desc->nheads > RT_MAXTRKS)
+      return set_err(RT_ERR_ARG, "rt_open: bad ntrks/nheads %u/%u", desc->ntrks, desc->nheads);
+   if (!(desc->maxvolts > 0 && desc->maxvolts < 100.0f)) return set_err(RT_ERR_ARG, "rt_open: maxvolts out of range");
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+      return set_err(RT_ERR_NODEVICE, "no CUDA device available (%s); readtape_b200 has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+   if (device < 0 || device >= ndev) return set_err(RT_ERR_ARG, "rt_open: bad device %d (have %d)", device, ndev);
+   CU(cudaSetDevice(device));
+   cudaDeviceProp prop;
+   CU(cudaGetDeviceProperties(&prop, device));
+   if (prop.major != 10)
+      return set_err(RT_ERR_NODEVICE, "device %d is sm_%d%d; this library only carries sm_100a kernels", device, prop.major, prop.minor);
+   rt_tape *t = new (std::nothrow) rt_tape();
+   if (!t) return set_err(RT_ERR_NOMEM, "rt_open: out of memory");
+   t->desc = *desc; t->device = device; t->sms = prop.multiProcessorCount;
+   std::vector<bool> seen(desc->ntrks, false);
+   for (uint32_t h = 0; h < RT_MAXTRKS; ++h) {
+      int k = h < desc->nheads ? desc->head_to_trk[h] : -1;
+      if (k < 0 || k >= (int)desc->ntrks) k = -1;
+      else if (seen[k]) { delete t; return set_err(RT_ERR_ARG, "rt_open: track %d is fed by two heads", k); }
+      else seen[k] = true;
+      t->trk_of_head[h] = k; }
+   for (uint32_t k = 0; k < desc->ntrks; ++k) if (!seen[k]) { delete t; return set_err(RT_ERR_ARG, "rt_open: track %u has no head", k); }
+   const char *fs = getenv("RT_INGEST");
+   t->force_simple_ingest = fs && strcmp(fs, "simple") == 0;
+   CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+   CU(cudaMalloc(&t->d_first_end, sizeof(unsigned long long)));
+   unsigned long long none = ~0ull;
+   CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
+   *out = t; return RT_OK; }
+
+static int tape_ingest(rt_tape *t, const int16_t *d_src, uint64_t nrows) {
+   cudaEvent_t e0, e1;
+   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+   CU(cudaEventRecord(e0, t->stream));
+   cudaError_t e = launch_ingest(d_src, nrows, t->nrows, (int)t->desc.nheads, t->trk_of_head, t->planes, t->plane_stride,
+                                 t->gmm, t->ngran_cap, t->d_first_end, t->sms, t->force_simple_ingest, t->stream, &t->launches);
+   if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "ingest kernel launch failed: %s", cudaGetErrorString(e));
+   CU(cudaEventRecord(e1, t->stream));
+   CU(cudaEventSynchronize(e1));
+   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); t->ms_ingest += ms;
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   t->nrows += nrows; t->valid_known = false;
+   return RT_OK; }
+
+extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
+   if (!t || (!rows && nrows)) return set_err(RT_ERR_ARG, "rt_upload: null argument");
+   if (nrows == 0) return RT_OK;
+   CU(cudaSetDevice(t->device));
+   int rc = tape_reserve(t, t->nrows + nrows);
+   if (rc) return rc;
+   const uint64_t nh = t->desc.nheads;
+   /* stage through two device buffers so the copy of chunk i+1 overlaps the ingest of chunk i */
+   const uint64_t chunk_rows = (uint64_t)2048 * 1024;                       /* 2 Mi rows: 36 MiB for 9 heads */
+   if (!t->d_stage[0]) {
+      size_t need = (size_t)std::min(chunk_rows, nrows + 2048) * nh * 2 + 256;
+      t->stage_bytes = std::max(need, (size_t)1 << 20);
+      for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&t->d_stage[i], t->stage_bytes)); CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); } }
+   const uint64_t stage_rows = (t->stage_bytes - 256) / (nh * 2) / 2048 * 2048;
+   if (t->nrows % 2048 != 0 && !t->force_simple_ingest) { /* appended onto a partial tile: fine, the plain kernel handles it */ }
+   uint64_t done = 0; int buf = 0;
+   while (done < nrows) {
+      uint64_t n = std::min(stage_rows ? stage_rows : nrows - done, nrows - done);
+      CU(cudaEventSynchronize(t->stage_done[buf]));
+      CU(cudaMemcpyAsync(t->d_stage[buf], rows + done * nh, (size_t)n * nh * 2, cudaMemcpyHostToDevice, t->stream));
+      rc = tape_ingest(t, t->d_stage[buf], n);
+      if (rc) return rc;
+      CU(cudaEventRecord(t->stage_done[buf], t->stream));
+      done += n; buf ^= 1; }
+   return RT_OK; }
+
+extern "C" int rt_attach_device(rt_tape *t, const void *rows_dev, uint64_t nrows) {
+   if (!t || (!rows_dev && nrows)) return set_err(RT_ERR_ARG, "rt_attach_device: null argument");
+   if (nrows == 0) return RT_OK;
+   CU(cudaSetDevice(t->device));
+   int rc = tape_reserve(t, t->nrows + nrows);
+   if (rc) return rc;
+   return tape_ingest(t, static_cast<const int16_t *>(rows_dev), nrows); }
+
+static int tape_sync_valid(rt_tape *t) {
+   if (t->valid_known) return RT_OK;
+   unsigned long long fe = ~0ull;
+   CU(cudaSetDevice(t->device));
+   CU(cudaStreamSynchronize(t->stream));
+   CU(cudaMemcpy(&fe, t->d_first_end, sizeof fe, cudaMemcpyDeviceToHost));
+   t->nrows_valid = std::min<uint64_t>(t->nrows, fe);
+   t->valid_known = true;
+   return RT_OK; }
+
+extern "C" uint64_t rt_nrows(const rt_tape *t) {
+   if (!t) return 0;
+   tape_sync_valid(const_cast<rt_tape *>(t));
+   return t->nrows_valid; }
+
+extern "C" void rt_close(rt_tape *t) {
+   if (!t) return;
+   cudaSetDevice(t->device);
+   if (t->stream) cudaStreamSynchronize(t->stream);
+   cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
+   for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); }
+   if (t->stream) cudaStreamDestroy(t->stream);
+   delete t; }
+
+extern "C" void *rt_host_alloc(size_t bytes) {
+   void *p = nullptr;
+   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_err(RT_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+   return p; }
+extern "C" void rt_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* ---- configuration -> device form ------------------------------------------------------------------ */
+static int cfg_check(const rt_tape *t, const rt_scan_cfg *cfg) {
+   if (cfg->mode != RT_MODE_PE && cfg->mode != RT_MODE_NRZI && cfg->mode != RT_MODE_GCR && cfg->mode != RT_MODE_WW)
+      return set_err(RT_ERR_ARG, "bad mode %d", cfg->mode);
+   if ((cfg->flags & RT_F_FIND_ZEROS) && cfg->mode == RT_MODE_PE)
+      return set_err(RT_ERR_UNSUPPORTED, "-zeros with PE needs the PE bit clock in the scan; not supported");
+   if (!(cfg->flags & RT_F_DENSITY_DETECT) && !(cfg->bpi > 0 && cfg->ips > 0))
+      return set_err(RT_ERR_ARG, "bpi/ips must be positive");
+   for (uint32_t k = 0; k < t->desc.ntrks; ++k)
+      if (cfg->skew_delaycnt[k] < 0 || cfg->skew_delaycnt[k] > RT_MAXSKEWSAMP)
+         return set_err(RT_ERR_ARG, "bad skew delay for track %u", k);
+   if (cfg->parms.agc_window < 0 || cfg->parms.agc_window > RT_AGC_MAX_WINDOW || cfg->parms.clk_window < 0 || cfg->parms.clk_window > RT_CLKRATE_WINDOW)
+      return set_err(RT_ERR_ARG, "agc_window/clk_window out of range");
+   if (!(cfg->flags & RT_F_FIND_ZEROS) && rt_pkww_width(cfg, t->desc.tdelta_ns) < 3)
+      return set_err(RT_ERR_UNSUPPORTED, "peak window narrower than 3 samples (%d)", rt_pkww_width(cfg, t->desc.tdelta_ns));
+   return RT_OK; }
+
+static void cfg_to_dev(const rt_tape *t, const rt_scan_cfg *cfg, DevCfg *d) {
+   memset(d, 0, sizeof *d);
+   d->planes = t->planes; d->plane_stride = t->plane_stride; d->nrows = t->nrows_valid;
+   d->tstart_ns = t->desc.tstart_ns; d->tdelta_ns = t->desc.tdelta_ns; d->maxvolts = t->desc.maxvolts;
+   volatile float sd = (float)(long long)t->desc.tdelta_ns / 1e9f;
+   d->sample_deltat = sd;
+   d->bpi = cfg->bpi; d->ips = cfg->ips;
+   d->density = (cfg->flags & RT_F_DENSITY_DETECT) != 0;
+   volatile float bi = cfg->bpi * cfg->ips;
+   d->clk_init = d->density ? 0.0f : 1 / bi;
+   d->ntrks = (int)t->desc.ntrks; d->mode = cfg->mode;
+   d->find_zeros = (cfg->flags & RT_F_FIND_ZEROS) != 0;
+   d->differentiate = (cfg->flags & RT_F_DIFFERENTIATE) != 0;
+   d->invert = (cfg->flags & RT_F_INVERT) != 0;
+   d->det = d->find_zeros ? (d->differentiate ? RT_DET_DZC : RT_DET_ZC) : RT_DET_PEAK;
+   d->width = rt_pkww_width(cfg, t->desc.tdelta_ns);
+   volatile float bid = bi * sd;
+   d->samples_per_bit = cfg->bpi > 0 ? (int)(1 / bid) : 20;
+   d->p = cfg->parms;
+   for (int k = 0; k < RT_MAXTRKS; ++k) d->skew[k] = cfg->skew_delaycnt[k]; }
+
+/* k-way merge of per-track event streams into (row, trk) order */
+struct Cursor { const rt_event *p, *end; };
+
+/* ---- stateful exact scan ----------------------------------------------------------------------- */
+struct rt_scan {
+   rt_tape *tape = nullptr; rt_scan_cfg cfg{}; DevCfg dc{};
+   TrkState *d_st = nullptr, *d_ckst = nullptr; SkewState *d_sk = nullptr, *d_cksk = nullptr;
+   uint64_t pos = 0, ckpt_pos = 0, ckpt_end = 0; bool positioned = false, have_ckpt = false;
+   rt_event *d_ev = nullptr; uint32_t cap = 0; uint32_t *d_counts = nullptr, *d_failed = nullptr;
+   rt_event *h_ev = nullptr; size_t h_ev_cap = 0;       /* pinned staging */
+   std::vector<rt_event> merged;
+};
+
+static int scan_alloc_events(rt_scan *s, uint32_t cap) {
+   const uint32_t nt = s->tape->desc.ntrks;
+   if (s->d_ev) cudaFree(s->d_ev);
+   if (s->h_ev) cudaFreeHost(s->h_ev);
+   s->d_ev = nullptr; s->h_ev = nullptr;
+   CU(cudaMalloc(&s->d_ev, (size_t)cap * nt * sizeof(rt_event)));
+   CU(cudaHostAlloc(&s->h_ev, (size_t)cap * nt * sizeof(rt_event), cudaHostAllocDefault));
+   s->cap = cap; s->h_ev_cap = (size_t)cap * nt;
+   return RT_OK; }
+
+extern "C" int rt_scan_begin(rt_tape *t, const rt_scan_cfg *cfg, rt_scan **out) {
+   if (!t || !cfg || !out) return set_err(RT_ERR_ARG, "rt_scan_begin: null argument");
+   int rc = cfg_check(t, cfg); if (rc) return rc;
+   rc = tape_sync_valid(t); if (rc) return rc;
+   CU(cudaSetDevice(t->device));
+   rt_scan *s = new (std::nothrow) rt_scan();
+   if (!s) return set_err(RT_ERR_NOMEM, "rt_scan_begin: out of memory");
+   s->tape = t; s->cfg = *cfg; cfg_to_dev(t, cfg, &s->dc);
+   const uint32_t nt = t->desc.ntrks;
+   cudaError_t e;
+   if ((e = cudaMalloc(&s->d_st, nt * sizeof(TrkState))) != cudaSuccess || (e = cudaMalloc(&s->d_ckst, nt * sizeof(TrkState))) != cudaSuccess ||
+       (e = cudaMalloc(&s->d_sk, nt * sizeof(SkewState))) != cudaSuccess || (e = cudaMalloc(&s->d_cksk, nt * sizeof(SkewState))) != cudaSuccess ||
+       (e = cudaMalloc(&s->d_counts, (nt + 1) * sizeof(uint32_t))) != cudaSuccess) {
+      rt_scan_end(s); return set_err(RT_ERR_CUDA, "rt_scan_begin: cudaMalloc failed: %s", cudaGetErrorString(e)); }
+   s->d_failed = s->d_counts + nt;
+   cudaMemsetAsync(s->d_st, 0, nt * sizeof(TrkState), t->stream);
+   cudaMemsetAsync(s->d_sk, 0, nt * sizeof(SkewState), t->stream);
+   rc = scan_alloc_events(s, 16384);
+   if (rc) { rt_scan_end(s); return rc; }
+   *out = s; return RT_OK; }
+
+extern "C" int rt_scan_set_cfg(rt_scan *s, const rt_scan_cfg *cfg) {
+   if (!s || !cfg) return set_err(RT_ERR_ARG, "rt_scan_set_cfg: null argument");
+   if (cfg->mode != s->cfg.mode) return set_err(RT_ERR_ARG, "rt_scan_set_cfg: the mode cannot change");
+   int rc = cfg_check(s->tape, cfg); if (rc) return rc;
+   s->cfg = *cfg; cfg_to_dev(s->tape, cfg, &s->dc); s->have_ckpt = false;
+   return RT_OK; }
+
+extern "C" int rt_scan_reset(rt_scan *s, int kind, uint64_t row) {
+   if (!s) return set_err(RT_ERR_ARG, "rt_scan_reset: null");
+   if (kind < RT_RESET_NONE || kind > RT_RESET_PEAKSTATE) return set_err(RT_ERR_ARG, "rt_scan_reset: bad kind %d", kind);
+   rt_tape *t = s->tape;
+   CU(cudaSetDevice(t->device));
+   int rc = tape_sync_valid(t); if (rc) return rc;
+   s->dc.planes = t->planes; s->dc.plane_stride = t->plane_stride; s->dc.nrows = t->nrows_valid;
+   if (kind != RT_RESET_NONE) {
+      int tz = rt_row_time(&t->desc, row) == 0.0;
+      launch_ctx_reset(s->dc, s->d_st, s->d_sk, kind, row, tz, t->stream);
+      CU(cudaGetLastError()); ++t->launches; }
+   s->pos = row; s->positioned = true; s->have_ckpt = false;
+   return RT_OK; }
+
+static int scan_span(rt_scan *s, uint64_t from, uint64_t to, bool want_events) {
+   rt_tape *t = s->tape; const uint32_t nt = t->desc.ntrks;
+   for (;;) {
+      uint32_t zero = 0;
+      CU(cudaMemcpyAsync(s->d_failed, &zero, sizeof zero, cudaMemcpyHostToDevice, t->stream));
+      launch_ctx_scan(s->dc, s->d_st, s->d_sk, from, to, s->d_ev, want_events ? s->cap : 0, s->d_counts, s->d_failed, t->stream);
+      CU(cudaGetLastError()); ++t->launches;
+      uint32_t counts[RT_MAXTRKS + 1];
+      CU(cudaMemcpyAsync(counts, s->d_counts, (nt + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, t->stream));
+      CU(cudaStreamSynchronize(t->stream));
+      if (counts[nt] == 2) return set_err(RT_ERR_STATE, "peak not found in window: the reference would call fatal() here");
+      if (!want_events) return RT_OK;
+      uint32_t mx = 0; for (uint32_t k = 0; k < nt; ++k) mx = std::max(mx, counts[k]);
+      if (mx > s->cap) {           /* event buffers too small: regrow, restore the entry state, rerun */
+         int rc = scan_alloc_events(s, mx + mx / 4 + 1024); if (rc) return rc;
+         CU(cudaMemcpyAsync(s->d_st, s->d_ckst, nt * sizeof(TrkState), cudaMemcpyDeviceToDevice, t->stream));
+         CU(cudaMemcpyAsync(s->d_sk, s->d_cksk, nt * sizeof(SkewState), cudaMemcpyDeviceToDevice, t->stream));
+         continue; }
+      /* fetch and merge */
+      size_t total = 0;
+      for (uint32_t k = 0; k < nt; ++k) {
+         if (counts[k]) CU(cudaMemcpyAsync(s->h_ev + (size_t)k * s->cap, s->d_ev + (size_t)k * s->cap, (size_t)counts[k] * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
+         total += counts[k]; }
+      CU(cudaStreamSynchronize(t->stream));
+      s->merged.clear(); s->merged.reserve(total);
+      Cursor cur[RT_MAXTRKS];
+      for (uint32_t k = 0; k < nt; ++k) { cur[k].p = s->h_ev + (size_t)k * s->cap; cur[k].end = cur[k].p + counts[k]; }
+      for (size_t n = 0; n < total; ++n) {
+         int best = -1; uint64_t brow = ~0ull;
+         for (uint32_t k = 0; k < nt; ++k) if (cur[k].p < cur[k].end && cur[k].p->row < brow) { brow = cur[k].p->row; best = (int)k; }
+         s->merged.push_back(*cur[best].p++); }
+      return RT_OK; } }
+
+extern "C" int rt_scan_run(rt_scan *s, uint64_t nrows, const rt_event **events, uint64_t *nevents, uint64_t *rows_done) {
+   if (!s) return set_err(RT_ERR_ARG, "rt_scan_run: null");
+   if (!s->positioned) return set_err(RT_ERR_STATE, "rt_scan_run before rt_scan_reset");
+   rt_tape *t = s->tape; const uint32_t nt = t->desc.ntrks;
+   CU(cudaSetDevice(t->device));
+   uint64_t end = s->pos + nrows;
+   if (end > t->nrows_valid || end < s->pos) end = t->nrows_valid;
+   if (end < s->pos) end = s->pos;
+   CU(cudaMemcpyAsync(s->d_ckst, s->d_st, nt * sizeof(TrkState), cudaMemcpyDeviceToDevice, t->stream));
+   CU(cudaMemcpyAsync(s->d_cksk, s->d_sk, nt * sizeof(SkewState), cudaMemcpyDeviceToDevice, t->stream));
+   s->ckpt_pos = s->pos; s->ckpt_end = end; s->have_ckpt = true;
+   s->merged.clear();
+   if (end > s->pos) { int rc = scan_span(s, s->pos, end, true); if (rc) return rc; }
+   if (rows_done) *rows_done = end - s->pos;
+   s->pos = end;
+   if (events) *events = s->merged.data();
+   if (nevents) *nevents = s->merged.size();
+   return RT_OK; }
+
+extern "C" int rt_scan_rewind(rt_scan *s, uint64_t row) {
+   if (!s) return set_err(RT_ERR_ARG, "rt_scan_rewind: null");
+   if (!s->have_ckpt || row < s->ckpt_pos || row > s->ckpt_end) return set_err(RT_ERR_STATE, "rt_scan_rewind: row outside the last scanned span");
+   rt_tape *t = s->tape; const uint32_t nt = t->desc.ntrks;
+   CU(cudaSetDevice(t->device));
+   CU(cudaMemcpyAsync(s->d_st, s->d_ckst, nt * sizeof(TrkState), cudaMemcpyDeviceToDevice, t->stream));
+   CU(cudaMemcpyAsync(s->d_sk, s->d_cksk, nt * sizeof(SkewState), cudaMemcpyDeviceToDevice, t->stream));
+   if (row > s->ckpt_pos) { int rc = scan_span(s, s->ckpt_pos, row, false); if (rc) return rc; }
+   s->pos = row; s->merged.clear();
+   return RT_OK; }
+
+extern "C" int rt_scan_set_avg_height(rt_scan *s, uint32_t trk, float v) {
+   if (!s || trk >= s->tape->desc.ntrks) return set_err(RT_ERR_ARG, "rt_scan_set_avg_height: bad argument");
+   CU(cudaSetDevice(s->tape->device));
+   launch_ctx_set_avg_height(s->d_st, (int)trk, v, s->tape->stream);
+   CU(cudaGetLastError()); ++s->tape->launches;
+   return RT_OK; }
+
+extern "C" uint64_t rt_scan_pos(const rt_scan *s) { return s ? s->pos : 0; }
+
+extern "C" void rt_scan_end(rt_scan *s) {
+   if (!s) return;
+   cudaSetDevice(s->tape->device);
+   cudaStreamSynchronize(s->tape->stream);
+   cudaFree(s->d_st); cudaFree(s->d_ckst); cudaFree(s->d_sk); cudaFree(s->d_cksk); cudaFree(s->d_counts); cudaFree(s->d_ev);
+   if (s->h_ev) cudaFreeHost(s->h_ev);
+   delete s; }
+
+/* ---- speculative whole-tape scan ---------------------------------------------------------------- */
+struct BulkCfg {
+   rt_scan_cfg cfg{}; DevCfg dc{};
+   std::vector<UnitDesc> units; std::vector<TrkMeta> meta; std::vector<uint32_t> chunk_next;
+   rt_event *h_pool = nullptr; size_t h_pool_events = 0;      /* pinned */
+   uint32_t chunks_used = 0;
+};
+struct rt_bulk {
+   rt_tape *tape = nullptr; std::vector<BulkCfg> cfgs; rt_bulk_stats stats{};
+   std::vector<rt_event> result;
+};
+
+static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
+   int lead = std::max<int>((int)k + (tz ? 1 : 0), dc.skew[k]);
+   return dc.det == RT_DET_PEAK ? lead + dc.width + 1 : lead + 2; }
+
+extern "C" void rt_bulk_free(rt_bulk *b) {
+   if (!b) return;
+   for (auto &c : b->cfgs) if (c.h_pool) cudaFreeHost(c.h_pool);
+   delete b; }
+
+extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bulk **out) {
+   if (!t || !cfgs || !ncfgs || !out) return set_err(RT_ERR_ARG, "rt_bulk_scan: null argument");
+   int rc = tape_sync_valid(t); if (rc) return rc;
+   CU(cudaSetDevice(t->device));
+   for (uint32_t i = 0; i < ncfgs; ++i) {
+      rc = cfg_check(t, &cfgs[i]); if (rc) return rc;
+      if (cfgs[i].mode == RT_MODE_WW) return set_err(RT_ERR_UNSUPPORTED, "Whirlwind state persists across blocks: use rt_scan_*");
+      if (cfgs[i].flags & RT_F_DENSITY_DETECT) return set_err(RT_ERR_UNSUPPORTED, "density detection is a prefix pass: use rt_scan_*"); }
+   rt_bulk *b = new (std::nothrow) rt_bulk();
+   if (!b) return set_err(RT_ERR_NOMEM, "rt_bulk_scan: out of memory");
+   b->tape = t; b->cfgs.resize(ncfgs);
+   const uint32_t nt = t->desc.ntrks; const uint64_t nrows = t->nrows_valid;
+   int launches0 = t->launches;
+   /* scratch for the unit finder */
+   const size_t words = units_bitmap_words(nrows), nblocks = units_blocks(nrows) + 1;
+   const uint32_t units_cap = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
+   uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units = nullptr;
+   unsigned long long *d_rows_scanned = nullptr; unsigned int *d_cursor = nullptr;
+   TrkMeta *d_meta = nullptr; rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr; uint32_t pool_chunks = 0;
+   cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
+   auto cleanup = [&]() {
+      cudaFree(d_bitmap); cudaFree(d_flags); cudaFree(d_blockcount); cudaFree(d_nunits); cudaFree(d_units);
+      cudaFree(d_rows_scanned); cudaFree(d_cursor); cudaFree(d_meta); cudaFree(d_pool); cudaFree(d_chunk_next);
+      for (auto &e : ev) cudaEventDestroy(e); };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); rt_bulk_free(b); \
+      return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+   CUB(cudaMalloc(&d_bitmap, words * 4)); CUB(cudaMalloc(&d_flags, words * 4)); CUB(cudaMalloc(&d_blockcount, nblocks * 4));
+   CUB(cudaMalloc(&d_nunits, 4)); CUB(cudaMalloc(&d_units, (size_t)units_cap * sizeof(UnitDesc)));
+   CUB(cudaMalloc(&d_rows_scanned, 8)); CUB(cudaMalloc(&d_cursor, 4));
+   b->stats.rows = nrows; b->stats.ms_preprocess = t->ms_ingest;
+   for (uint32_t ci = 0; ci < ncfgs; ++ci) {
+      BulkCfg &bc = b->cfgs[ci];
+      bc.cfg = cfgs[ci]; cfg_to_dev(t, &cfgs[ci], &bc.dc);
+      const DevCfg &dc = bc.dc;
+      /* proposal thresholds (heuristic) and the exact quiet threshold the scan kernel applies */
+      const double lsb = (double)t->desc.maxvolts / 32767.0;
+      const double rows_per_bit = 1.0 / ((double)dc.bpi * dc.ips * dc.sample_deltat);
+      UnitParams up{};
+      up.det = dc.det;
+      float quiet_thr = 0;
+      if (dc.det == RT_DET_PEAK) {
+         quiet_thr = dc.p.pkww_rise * 0.999f;
+         if (dc.p.pkww_rise < 1e-3f) quiet_thr = 0;                      /* nothing can be proven quiet: every lookup misses */
+         up.thr = (int)(0.5 * dc.p.pkww_rise / lsb); }
+      else if (dc.det == RT_DET_ZC) up.thr = (int)(0.9 * RT_ZEROCROSS_PEAK / lsb);
+      else up.thr = (int)(0.9 * std::max(0.05, 0.5 / std::max(1, dc.samples_per_bit)) / lsb);
+      uint64_t gap_rows = (uint64_t)(6.0 * rows_per_bit) + 1;
+      up.min_gap_gran = (uint32_t)std::max<uint64_t>(2, (gap_rows + RT_GRAN - 1) / RT_GRAN + 1);
+      const uint64_t ibg_rows = (uint64_t)(200e-6 / dc.sample_deltat) + 1;      /* *_IBG_SECS, decoder.h:105,113,116 */
+      up.tail_rows = (uint64_t)(16.0 * rows_per_bit) + ibg_rows + 64 + RT_PKWW_MAX_WIDTH + RT_MAXSKEWSAMP;
+      CUB(cudaEventRecord(ev[0], t->stream));
+      cudaError_t e = launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, up, d_bitmap, d_flags, d_blockcount, d_units, units_cap, d_nunits, t->stream, &t->launches);
+      CUB(e);
+      CUB(cudaEventRecord(ev[1], t->stream));
+      uint32_t nunits = 0;
+      CUB(cudaMemcpyAsync(&nunits, d_nunits, 4, cudaMemcpyDeviceToHost, t->stream));
+      CUB(cudaStreamSynchronize(t->stream));
+      if (nunits > units_cap) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "unit table overflow (%u > %u)", nunits, units_cap); }
+      bc.units.resize(nunits); bc.meta.resize((size_t)nunits * nt);
+      cudaFree(d_meta); d_meta = nullptr;
+      if (nunits) CUB(cudaMalloc(&d_meta, (size_t)nunits * nt * sizeof(TrkMeta)));
+      /* event pool: first guess one event per 12 track-samples, regrown on overflow */
+      uint64_t want_chunks = std::max<uint64_t>(4096, nrows * nt / 12 / RT_EVC + (uint64_t)nunits * nt);
+      float ms_scan = 0;
+      for (int attempt = 0; nunits && attempt < 3; ++attempt) {
+         if (want_chunks > pool_chunks) {
+            cudaFree(d_pool); cudaFree(d_chunk_next); d_pool = nullptr; d_chunk_next = nullptr;
+            if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
+            pool_chunks = (uint32_t)want_chunks;
+            CUB(cudaMalloc(&d_pool, (size_t)pool_chunks * RT_EVC * sizeof(rt_event)));
+            CUB(cudaMalloc(&d_chunk_next, (size_t)pool_chunks * 4)); }
+         CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
+         CUB(cudaMemsetAsync(d_rows_scanned, 0, 8, t->stream));
+         CUB(cudaEventRecord(ev[2], t->stream));
+         const uint64_t threads = (uint64_t)nunits * nt;
+         int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * 16);
+         launch_units_scan(dc, d_units, d_nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, quiet_thr, d_rows_scanned, grid, t->stream);
+         CUB(cudaGetLastError()); ++t->launches;
+         CUB(cudaEventRecord(ev[3], t->stream));
+         unsigned int used = 0;
+         CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
+         CUB(cudaStreamSynchronize(t->stream));
+         float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_scan = ms;
+         if (used <= pool_chunks) { bc.chunks_used = used; break; }
+         want_chunks = (uint64_t)used + used / 8 + 1024;
+         if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
+      float ms_units = 0; cudaEventElapsedTime(&ms_units, ev[0], ev[1]);
+      b->stats.ms_units += ms_units; b->stats.ms_scan += ms_scan;
+      /* results to the host */
+      if (nunits) {
+         CUB(cudaMemcpyAsync(bc.units.data(), d_units, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToHost, t->stream));
+         CUB(cudaMemcpyAsync(bc.meta.data(), d_meta, (size_t)nunits * nt * sizeof(TrkMeta), cudaMemcpyDeviceToHost, t->stream));
+         bc.chunk_next.resize(bc.chunks_used);
+         if (bc.chunks_used) {
+            CUB(cudaMemcpyAsync(bc.chunk_next.data(), d_chunk_next, (size_t)bc.chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
+            bc.h_pool_events = (size_t)bc.chunks_used * RT_EVC;
+            CUB(cudaHostAlloc(&bc.h_pool, bc.h_pool_events * sizeof(rt_event), cudaHostAllocDefault));
+            CUB(cudaMemcpyAsync(bc.h_pool, d_pool, bc.h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream)); }
+         unsigned long long rs = 0;
+         CUB(cudaMemcpyAsync(&rs, d_rows_scanned, 8, cudaMemcpyDeviceToHost, t->stream));
+         CUB(cudaStreamSynchronize(t->stream));
+         b->stats.rows_scanned += rs;
+         for (const TrkMeta &m : bc.meta) b->stats.events += m.nevents; }
+      b->stats.units = nunits; }
+   b->stats.track_samples = nrows * nt * ncfgs;
+   b->stats.launches = (uint32_t)(t->launches - launches0);
+   cleanup();
+#undef CUB
+   *out = b; return RT_OK; }
+
+extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
+   if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");
+   *out = b->stats; return RT_OK; }
+
+extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event **events, uint64_t *nevents, uint64_t *valid_rows) {
+   if (!b || ci >= b->cfgs.size()) return set_err(RT_ERR_ARG, "rt_bulk_lookup: bad argument");
+   BulkCfg &bc = b->cfgs[ci];
+   const uint32_t nt = b->tape->desc.ntrks;
+   if (bc.units.empty()) return RT_MISS;
+   /* the last unit that starts at or before start_row */
+   size_t lo = 0, hi = bc.units.size();
+   while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (bc.units[mid].row0 <= start_row) lo = mid; else hi = mid; }
+   const UnitDesc &u = bc.units[lo];
+   if (u.row0 > start_row || start_row >= u.row_end) return RT_MISS;
+   const TrkMeta *m = &bc.meta[lo * nt];
+   const bool tz = rt_row_time(&b->tape->desc, start_row) == 0.0;
+   for (uint32_t k = 0; k < nt; ++k) {
+      if (m[k].failed) return RT_MISS;
+      if (start_row == u.row0) continue;                       /* the very same reset: trivially identical */
+      if (m[k].sync_row == RT_NOROW) return RT_MISS;
+      if (m[k].sync_row < start_row + (uint64_t)fill_of(bc.dc, k, tz)) return RT_MISS;
+      if (bc.dc.det == RT_DET_PEAK) { if (m[k].last_loud_row != RT_NOROW && m[k].last_loud_row >= start_row) return RT_MISS; }
+      else if (m[k].last_loud_row != RT_NOROW) return RT_MISS; }
+   /* merge the per-track chunk chains into (row, trk) order */
+   struct CC { uint32_t chunk, left, slot; } cc[RT_MAXTRKS];
+   size_t total = 0;
+   for (uint32_t k = 0; k < nt; ++k) { cc[k].chunk = m[k].first_chunk; cc[k].left = m[k].nevents; cc[k].slot = 0; total += m[k].nevents; }
+   b->result.clear(); b->result.reserve(total);
+   for (size_t n = 0; n < total; ++n) {
+      int best = -1; uint64_t brow = ~0ull;
+      for (uint32_t k = 0; k < nt; ++k) if (cc[k].left) {
+            const rt_event &e = bc.h_pool[(size_t)cc[k].chunk * RT_EVC + cc[k].slot];
+            if (e.row < brow) { brow = e.row; best = (int)k; } }
+      CC &c = cc[best];
+      b->result.push_back(bc.h_pool[(size_t)c.chunk * RT_EVC + c.slot]);
+      --c.left;
+      if (++c.slot == RT_EVC) { c.slot = 0; c.chunk = c.left ? bc.chunk_next[c.chunk] : RT_NOCHUNK; } }
+   if (events) *events = b->result.data();
+   if (nevents) *nevents = b->result.size();
+   if (valid_rows) *valid_rows = u.row_end - start_row;
+   return RT_OK; }

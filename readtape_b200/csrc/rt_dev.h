@@ -1,0 +1,104 @@
+/* readtape_b200/csrc/rt_dev.h -- structures shared by the CUDA kernels and the host side of
+ * librt_scan_b200.so.  See DESIGN.md for the data layout in HBM.
+ *
+ *  planes   int16 [ntrks][plane_stride]   track-major copy of the TBIN payload, head->track
+ *                                         permutation applied (k_ingest.cu)
+ *  gmm      int16 [ntrks][ngran][2]       min / max of every 32-row granule (k_ingest.cu)
+ *  units    UnitDesc [nunits]             independent scan units cut at all-track quiet gaps
+ *  umeta    TrkMeta  [nunits][ntrks]      per (unit, track) results + equivalence proof data
+ *  evpool   rt_event [pool_chunks][EVC]   events, in fixed-size chunks chained per (unit, track)
+ */
+#ifndef RT_DEV_H
+#define RT_DEV_H
+
+#include <stdint.h>
+#include "rt_scan.h"
+
+#define RT_GRAN            32      /* rows per granule of the quiet map                         */
+#define RT_EVC             32      /* events per pool chunk                                     */
+#define RT_NOCHUNK         0xffffffffu
+#define RT_NOROW           0xffffffffffffffffull
+
+/* compile-time constants of the reference the scan needs (src/decoder.h) */
+#define RT_PKWW_PEAKHEIGHT 4.0f    /* :133 */
+#define RT_DIFF_THRESHOLD  0.05f   /* :135 */
+#define RT_DIFF_SCALE      0.4f    /* :136 */
+#define RT_ZEROCROSS_PEAK  0.2f    /* :138 */
+#define RT_ZEROCROSS_SLOPE 1.5f    /* :139 */
+#define RT_PEAK_THRESHOLD  0.005f  /* :141 */
+#define RT_AGC_MAX_VALUE   2.0f    /* :153 */
+#define RT_AGC_STARTBASE   5       /* :154 */
+#define RT_AGC_ENDBASE     15      /* :155 */
+#define RT_GCR_IDLE_THRESH 6.00    /* :111, a double in the reference */
+#define RT_PE_MIN_PREBITS  70      /* :118 */
+#define RT_GCR_MARK1       0x07    /* decode_gcr.c:422 */
+#define RT_GCR_MARK2       0x1c    /* decode_gcr.c:423 */
+
+/* detector selected by the flags */
+enum { RT_DET_PEAK = 0, RT_DET_ZC = 1, RT_DET_DZC = 2 };
+
+/* Everything a scan kernel needs to know about the tape and the decode configuration. */
+struct DevCfg {
+   const int16_t *planes;         /* [ntrks][plane_stride] */
+   uint64_t plane_stride;         /* elements */
+   uint64_t nrows;                /* valid rows (before the end marker) */
+   uint64_t tstart_ns, tdelta_ns;
+   float    maxvolts;
+   float    sample_deltat;        /* (float)tdelta_ns / 1e9f, readtape.c:1345 */
+   float    bpi, ips;
+   float    clk_init;             /* 1 / (bpi*ips), or 0 while detecting the density */
+   int32_t  ntrks;
+   int32_t  mode;                 /* RT_MODE_* */
+   int32_t  det;                  /* RT_DET_* */
+   int32_t  width;                /* pkww_width */
+   int32_t  samples_per_bit;      /* readtape.c:1402 */
+   int32_t  invert, differentiate, density, find_zeros;
+   rt_parms p;
+   int32_t  skew[RT_MAXTRKS];
+};
+
+/* Per-track detector + feedback state: the device mirror of the parts of struct trkstate_t
+ * (decoder.h:194-255) and struct skew_t (decoder.c:227) that feed back into the detectors. */
+struct TrkState {
+   /* replaces the `t_lastpeak == 0` test + `break` of decoder.c:855-861 (quirk Q2): the row at which
+      this track (re)initialises after a reset; rows before it are skipped; RT_NOROW = done */
+   uint64_t init_row;
+   /* times */
+   double   t_top, t_bot, t_lastpeak, t_firstzero, t_lastzero;
+   /* voltages */
+   float    v_prev, v_top, v_bot, v_lasttop, v_lastbot;
+   /* peak window */
+   float    win[RT_PKWW_MAX_WIDTH];
+   float    minv, maxv;
+   int32_t  left, right, countdown;
+   /* AGC */
+   float    avg_height, avg_height_sum, agc_gain;
+   float    heights[RT_AGC_MAX_WINDOW];
+   int32_t  avg_height_count, heightndx, peakcount;
+   /* PE */
+   float    t_clkwindow;
+   /* GCR clock */
+   float    clk_spacing[RT_CLKRATE_WINDOW];
+   float    clk_avg, t_peakdelta, t_peakdeltaprev, t_pulse_adj;
+   int32_t  clk_ndx, datacount, resync_bitcount;
+   uint8_t  up_pending, dn_pending, datablock, bit1_up, lastbits, bit_m1, bit_m2, failed;
+};
+
+/* One independent scan unit of the speculative whole-tape scan. */
+struct UnitDesc {
+   uint64_t row0;                 /* fresh RT_RESET_FULL happens here                        */
+   uint64_t row_end;              /* scan rows [row0, row_end)                               */
+};
+
+/* Per (unit, track) result. */
+struct TrkMeta {
+   uint64_t first_event_row;      /* RT_NOROW if the track had no event                      */
+   uint64_t sync_row;             /* last row before the first event at which the state became canonical, RT_NOROW if none */
+   uint64_t last_loud_row;        /* last row before sync_row that violates the quiet rule, RT_NOROW if none */
+   uint32_t first_chunk;          /* head of the chunk chain in the event pool               */
+   uint32_t nevents;
+   uint32_t failed;               /* 2: the reference would have called fatal() (peak not found) */
+   uint32_t pad;
+};
+
+#endif

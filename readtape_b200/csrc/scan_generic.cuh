@@ -1,0 +1,311 @@
+/* readtape_b200/csrc/scan_generic.cuh -- the exact, fully general per-track scan (device code).
+ *
+ * One CUDA thread owns one track and walks its sample plane row by row, carrying the complete
+ * per-track state (struct TrkState).  This is the always-correct formulation: every detector
+ * (moving-window peaks, zero crossings, differentiated zero crossings), every mode's feedback
+ * fragment, deskew, invert, differentiate, persistent state (Whirlwind) and all reset kinds.
+ * The speculative whole-tape scan uses the same code for (unit, track) threads; the integer
+ * fast path in scan_fast.cuh is an optimisation of the NRZI/PE/GCR common cases and is tested
+ * against this one.
+ *
+ * Reference semantics followed (file:line in /root/reference/src), type-for-type:
+ *   sample conversion / invert / differentiate   readtape.c:1418-1422, 1383-1388
+ *   deskew FIFO                                  decoder.c:819-831
+ *   first-sample init                            decoder.c:855-861
+ *   lookfor_peak / refine_peak                   decoder.c:751-810 / 700-749
+ *   lookfor_zerocrossing / differentiated        decoder.c:617-649 / 654-683
+ *   process_*_transition glue                    decoder.c:560-609
+ *   adjust_agc, adjust_clock, force_clock        decoder.c:500-558
+ *   NRZI / PE / GCR / WW feedback fragments      decode_nrzi.c:184-230, decode_pe.c:127-201,
+ *                                                decode_gcr.c:731-865, decode_ww.c:167-191
+ *   GCR idle test                                decoder.c:879-882
+ * Compiled with -fmad=false: no FMA contraction, IEEE division, float/double exactly as written
+ * in the reference (built there with FLT_EVAL_METHOD 0).
+ */
+#pragma once
+#include "rt_dev.h"
+
+namespace rtgen {
+
+__device__ __forceinline__ double row_time(const DevCfg &c, uint64_t row) {
+   long long ns = (long long)(c.tstart_ns + row * c.tdelta_ns);
+   return (double)ns / 1e9; }
+
+/* lazily evaluated timenow of the current row */
+struct RowClock {
+   const DevCfg &c; uint64_t row; double t; bool have;
+   __device__ RowClock(const DevCfg &c_, uint64_t r) : c(c_), row(r), t(0), have(false) {}
+   __device__ __forceinline__ double now() { if (!have) { t = row_time(c, row); have = true; } return t; } };
+
+/* ---- clock averaging, decoder.c:533-558 ---------------------------------------------------- */
+__device__ inline void clk_adjust(const DevCfg &c, TrkState &t, float delta) {
+   int win = c.p.clk_window; float alpha = c.p.clk_alpha;
+   if (win > 0) {
+      float old = t.clk_spacing[t.clk_ndx];
+      t.clk_spacing[t.clk_ndx] = delta;
+      if (++t.clk_ndx >= win) t.clk_ndx = 0;
+      t.clk_avg += (delta - old) / win; }
+   else if (alpha > 0) t.clk_avg = alpha * delta + (1 - alpha) * t.clk_avg;
+   else t.clk_avg = (c.mode & (RT_MODE_PE + RT_MODE_WW)) ? 1 / (c.bpi * c.ips) : 0.0f; }
+
+__device__ inline void clk_force(TrkState &t, float v) {
+   for (int i = 0; i < RT_CLKRATE_WINDOW; ++i) t.clk_spacing[i] = v;
+   t.clk_avg = v; }
+
+/* ---- AGC, decoder.c:500-531 ---------------------------------------------------------------- */
+__device__ inline void agc_adjust(const DevCfg &c, TrkState &t) {
+   if (c.find_zeros) return;
+   float gain, lastheight;
+   if (c.p.agc_alpha != 0) {
+      lastheight = t.v_lasttop - t.v_lastbot;
+      if (lastheight > 0) {
+         gain = t.avg_height / lastheight;
+         gain = c.p.agc_alpha * gain + (1 - c.p.agc_alpha) * t.agc_gain;
+         if (gain > RT_AGC_MAX_VALUE) gain = RT_AGC_MAX_VALUE;
+         t.agc_gain = gain; } }
+   if (c.p.agc_window != 0) {
+      lastheight = t.v_lasttop - t.v_lastbot;
+      if (lastheight > 0) {
+         t.heights[t.heightndx] = lastheight;
+         if (++t.heightndx >= c.p.agc_window) t.heightndx = 0;
+         float minheight = 99;
+         for (int i = 0; i < c.p.agc_window; ++i) if (t.heights[i] < minheight) minheight = t.heights[i];
+         gain = t.avg_height / minheight;
+         if (gain > RT_AGC_MAX_VALUE) gain = RT_AGC_MAX_VALUE;
+         t.agc_gain = gain; } } }
+
+__device__ inline void baseline_accumulate(const DevCfg &c, TrkState &t) {
+   t.avg_height_sum += t.v_top - t.v_bot;
+   ++t.avg_height_count;
+   t.heights[t.heightndx] = t.v_top - t.v_bot;
+   if (++t.heightndx >= c.p.agc_window) t.heightndx = 0; }
+
+/* ---- mode feedback fragments ---------------------------------------------------------------- */
+__device__ inline void nrzi_feedback(const DevCfg &c, TrkState &t, bool top) {
+   if (top) {
+      if (t.peakcount >= RT_AGC_STARTBASE && t.peakcount <= RT_AGC_ENDBASE) baseline_accumulate(c, t);
+      else if (t.peakcount > RT_AGC_ENDBASE) {
+         if (t.avg_height_count) {
+            t.avg_height = t.avg_height_sum / t.avg_height_count;
+            t.avg_height_count = 0; }
+         else agc_adjust(c, t); } }
+   else if (t.peakcount > RT_AGC_ENDBASE && t.avg_height_count == 0) agc_adjust(c, t); }
+
+__device__ inline void pe_feedback(const DevCfg &c, TrkState &t, bool top, double t_ev) {
+   if (t.datablock) { agc_adjust(c, t); return; }
+   if (t.peakcount == 1) t.bit1_up = !top;
+   if (t.peakcount > RT_PE_MIN_PREBITS && (t.bit1_up != 0) == top && t_ev - t.t_lastpeak > t.t_clkwindow) {
+      t.datablock = 1;
+      t.avg_height = t.avg_height_sum / t.avg_height_count; }
+   else if (t.peakcount >= RT_AGC_STARTBASE && t.peakcount <= RT_AGC_ENDBASE && t.v_top > t.v_bot)
+      baseline_accumulate(c, t); }
+
+__device__ inline void gcr_addbit(TrkState &t, int bit) {
+   t.datablock = 1;
+   if (t.datacount < RT_MAXBLOCK) { t.bit_m2 = t.bit_m1; t.bit_m1 = (uint8_t)bit; ++t.datacount; }
+   t.lastbits = (uint8_t)((t.lastbits << 1) | bit);
+   if (t.datacount % 5 == 0) {
+      if ((t.lastbits & 0x1f) == RT_GCR_MARK2) t.resync_bitcount = 1;
+      if ((t.lastbits & 0x1f) == RT_GCR_MARK1 && t.resync_bitcount > 0) t.resync_bitcount = 0; }
+   if (t.resync_bitcount > 0) {
+      if (t.resync_bitcount == 5) clk_force(t, t.t_peakdelta);
+      ++t.resync_bitcount; } }
+
+__device__ inline void gcr_feedback(const DevCfg &c, TrkState &t, bool top, double t_ev) {
+   float delta = (float)(t_ev - t.t_lastpeak);
+   int numbits = 1;
+   if (t.datablock) {
+      t.t_peakdeltaprev = t.t_peakdelta;
+      t.t_peakdelta = delta;
+      if (delta - t.t_pulse_adj > c.p.z1pt * t.clk_avg) {
+         ++numbits; gcr_addbit(t, 0);
+         if (delta - t.t_pulse_adj > c.p.z2pt * t.clk_avg) { ++numbits; gcr_addbit(t, 0); } }
+      if (t.datacount > 3 && numbits == 1 && t.bit_m2) clk_adjust(c, t, t.t_peakdeltaprev);
+      t.t_pulse_adj = c.p.pulse_adj * (numbits * t.clk_avg - delta); }
+   gcr_addbit(t, 1);
+   nrzi_feedback(c, t, top); }
+
+/* ---- per-event glue, decoder.c:560-609 ------------------------------------------------------ */
+template <class Emit>
+__device__ inline void transition(const DevCfg &c, TrkState &t, bool top, uint64_t row, Emit &em) {
+   double t_ev = top ? t.t_top : t.t_bot;
+   float v_top_seen = t.v_top, v_bot_seen = t.v_bot;
+   ++t.peakcount;
+   if (!c.density) {
+      if (c.mode == RT_MODE_NRZI) nrzi_feedback(c, t, top);
+      else if (c.mode == RT_MODE_PE) pe_feedback(c, t, top, t_ev);
+      else if (c.mode == RT_MODE_GCR) gcr_feedback(c, t, top, t_ev);
+      else agc_adjust(c, t); }
+   if (top) t.v_lasttop = t.v_top; else t.v_lastbot = t.v_bot;
+   t.t_lastpeak = t_ev;
+   em.emit(row, t_ev, v_top_seen, v_bot_seen, t.agc_gain, top); }
+
+/* ---- moving-window peak detector, decoder.c:700-810 ------------------------------------------ */
+__device__ inline double refine(const DevCfg &c, TrkState &t, float val, bool top, double timenow) {
+   const int w = c.width;
+   int left_distance = 1, prev = -1;
+   float adj = 0;
+   for (int ndx = t.left;;) {
+      if (t.win[ndx] == val) {
+         if (left_distance >= w || prev == -1) { t.failed = 2; return 0; }
+         int next = ndx + 1; if (next >= w) next = 0;
+         if (top) {
+            float edge = val - RT_PEAK_THRESHOLD / t.agc_gain;
+            if (t.win[prev] > edge && t.win[next] < edge) adj = -0.5f;
+            else if (t.win[next] > edge && t.win[prev] < edge) adj = +0.5f; }
+         else {
+            float edge = val + RT_PEAK_THRESHOLD / t.agc_gain;
+            if (t.win[prev] < edge && t.win[next] > edge) adj = -0.5f;
+            else if (t.win[next] < edge && t.win[prev] > edge) adj = +0.5f; }
+         double time = timenow - (double)(((float)(w - left_distance) - adj) * c.sample_deltat);
+         t.countdown = left_distance;
+         return time; }
+      ++left_distance;
+      if (ndx == t.right) break;
+      prev = ndx;
+      if (++ndx >= w) ndx = 0; }
+   t.failed = 2;
+   return 0; }
+
+/* `probe` (out): bit 0 = the window was full (a sample left it), bit 1 = the rescan was triggered by
+ * the running maximum leaving a full window -- the state-independent event at which two scans of
+ * the same samples that were reset at different rows provably become identical. */
+template <class Emit>
+__device__ inline void peak_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em, unsigned &probe) {
+   const int w = c.width;
+   float leaving = 0;
+   probe = 0;
+   if (++t.right >= w) t.right = 0;
+   if (t.right == t.left) {
+      leaving = t.win[t.left];
+      probe = 1;
+      if (++t.left >= w) t.left = 0; }
+   t.win[t.right] = v_now;
+   if (v_now > t.maxv) t.maxv = v_now;
+   if (probe && leaving == t.maxv) probe |= 2;
+   if (leaving == t.maxv || leaving == t.minv) {      /* (Q1) the minimum is only refreshed here */
+      float mx = -100, mn = +100;
+      for (int ndx = t.left;;) {
+         float v = t.win[ndx];
+         if (v > mx) mx = v;
+         if (v < mn) mn = v;
+         if (ndx == t.right) break;
+         if (++ndx >= w) ndx = 0; }
+      t.maxv = mx; t.minv = mn; }
+   if (t.countdown) { --t.countdown; return; }
+   float rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+   float reqmin = c.p.min_peak * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+   float vl = t.win[t.left], vr = t.win[t.right];
+   if (t.maxv > vl + rise && t.maxv > vr + rise && (reqmin == 0 || t.maxv > reqmin)) {
+      t.v_top = t.maxv;
+      t.t_top = refine(c, t, t.maxv, true, clk.now());
+      transition(c, t, true, clk.row, em); }
+   else if (t.minv < vl - rise && t.minv < vr - rise && (reqmin == 0 || t.minv < -reqmin)) {
+      t.v_bot = t.minv;
+      t.t_bot = refine(c, t, t.minv, false, clk.now());
+      transition(c, t, false, clk.row, em); } }
+
+/* ---- zero-crossing detectors, decoder.c:617-683 ---------------------------------------------- */
+template <class Emit>
+__device__ inline void zc_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em) {
+   if (v_now > 0) {
+      t.dn_pending = 0;
+      if (t.v_top < v_now) {
+         t.v_top = v_now;
+         if (t.up_pending && t.v_top > RT_ZEROCROSS_PEAK) {
+            if (t.t_top == 0) t.t_top = clk.now();
+            t.up_pending = 0;
+            t.v_bot = 0;
+            if (clk.now() - t.t_top <= (double)(t.clk_avg * RT_ZEROCROSS_SLOPE)) transition(c, t, true, clk.row, em); } }
+      if (t.v_prev < 0 && t.v_bot < -RT_ZEROCROSS_PEAK) { t.t_top = clk.now(); t.up_pending = 1; } }
+   else if (v_now < 0) {
+      t.up_pending = 0;
+      if (t.v_bot > v_now) {
+         t.v_bot = v_now;
+         if (t.dn_pending && t.v_bot < -RT_ZEROCROSS_PEAK) {
+            if (t.t_bot == 0) t.t_bot = clk.now();
+            t.dn_pending = 0;
+            t.v_top = 0;
+            if (clk.now() - t.t_bot <= (double)(t.clk_avg * RT_ZEROCROSS_SLOPE)) transition(c, t, false, clk.row, em); } }
+      if (t.v_prev > 0 && t.v_top > RT_ZEROCROSS_PEAK) { t.t_bot = clk.now(); t.dn_pending = 1; } }
+   t.v_prev = v_now; }
+
+template <class Emit>
+__device__ inline void dzc_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em) {
+   if (v_now > 0) {
+      if (t.v_top < v_now) t.v_top = v_now;
+      if (t.up_pending) {
+         t.t_top = t.t_firstzero > 0 ? (t.t_firstzero + t.t_lastzero) / 2 : clk.now() - (double)(c.sample_deltat / 2);
+         t.up_pending = 0;
+         t.t_firstzero = 0;
+         transition(c, t, true, clk.row, em); }
+      if (v_now > RT_ZEROCROSS_PEAK) { t.dn_pending = 1; t.t_firstzero = 0; t.v_bot = 0; } }
+   else if (v_now < 0) {
+      if (t.v_bot > v_now) t.v_bot = v_now;
+      if (t.dn_pending) {
+         t.t_bot = t.t_firstzero > 0 ? (t.t_firstzero + t.t_lastzero) / 2 : clk.now() - (double)(c.sample_deltat / 2);
+         t.dn_pending = 0;
+         t.t_firstzero = 0;
+         transition(c, t, false, clk.row, em); }
+      if (v_now < -RT_ZEROCROSS_PEAK) { t.up_pending = 1; t.t_firstzero = 0; t.v_top = 0; } }
+   else {
+      t.t_lastzero = clk.now();
+      if (t.t_firstzero == 0) t.t_firstzero = clk.now(); } }
+
+/* ---- resets (decoder.c:413-455, decode_ww.c:33-49) ------------------------------------------ */
+/* The skew FIFO / differentiator state of the generic path. */
+struct SkewState { float vdelayed[RT_MAXSKEWSAMP]; int32_t ndx_next, slots_filled; float v_last_raw; int32_t pad; };
+
+__device__ inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, int trk, uint64_t row, bool time_is_zero) {
+   /* memset(trkstate,0) + the non-zero members, decoder.c:437-449 */
+   char *p = (char *)&t; for (unsigned i = 0; i < sizeof(TrkState); ++i) p[i] = 0;
+   p = (char *)&s; for (unsigned i = 0; i < sizeof(SkewState); ++i) p[i] = 0;
+   t.agc_gain = 1.0f;
+   t.avg_height = RT_PKWW_PEAKHEIGHT;
+   if (!c.density) { t.clk_avg = c.clk_init; for (int i = 0; i < RT_CLKRATE_WINDOW; ++i) t.clk_spacing[i] = c.clk_init; }
+   t.t_clkwindow = t.clk_avg / 2 * c.p.clk_factor;
+   t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u); }
+
+/* ---- one row of one track ------------------------------------------------------------------- */
+/* returns the probe bits of peak_step (0 for the other detectors / skipped rows); *v_out = v_now */
+template <class Emit>
+__device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane,
+                                     uint64_t row, Emit &em, float *v_out) {
+   /* int16 -> volts, invert, differentiate */
+   float v = (float)plane[row] / 32767 * c.maxvolts;
+   if (c.invert) v = -v;
+   if (c.differentiate) {
+      float delta = v - s.v_last_raw;
+      if (delta < RT_DIFF_THRESHOLD && delta > -RT_DIFF_THRESHOLD) delta = 0;
+      s.v_last_raw = v;
+      v = delta * RT_DIFF_SCALE * c.samples_per_bit; }
+   /* deskew FIFO */
+   float v_now;
+   int delay = c.skew[trk];
+   if (delay == 0) v_now = v;
+   else {
+      if (s.slots_filled < delay) { v_now = v; ++s.slots_filled; }
+      else v_now = s.vdelayed[s.ndx_next];
+      s.vdelayed[s.ndx_next] = v;
+      if (++s.ndx_next >= delay) s.ndx_next = 0; }
+   *v_out = v_now;
+   /* (Q2) rows before this track's (re)initialisation row are not looked at */
+   if (t.init_row != RT_NOROW) {
+      if (row < t.init_row) return 0;
+      if (row == t.init_row) {
+         t.win[0] = v_now;
+         t.maxv = t.minv = v_now;
+         t.t_lastpeak = row_time(c, row);
+         t.init_row = RT_NOROW;
+         return 0; } }
+   RowClock clk(c, row);
+   unsigned probe = 0;
+   if (c.det == RT_DET_PEAK) peak_step(c, t, v_now, clk, em, probe);
+   else if (c.det == RT_DET_ZC) zc_step(c, t, v_now, clk, em);
+   else dzc_step(c, t, v_now, clk, em);
+   if (c.mode == RT_MODE_GCR && t.datablock
+         && clk.now() > t.t_lastpeak + RT_GCR_IDLE_THRESH * (double)t.clk_avg)
+      t.datablock = 0;
+   return probe; }
+
+}  // namespace rtgen

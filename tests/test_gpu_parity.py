@@ -1,0 +1,124 @@
+"""GPU parity: the CUDA library (through the C-ABI) against the reference's events and the oracle.
+
+Bit-exact: rows, polarity, event times (f64), voltages (f32) and AGC gains (f32) are compared as
+bytes (SHA-256 of the canonical records) -- integer/byte work allows no tolerance, and the float
+results are required to be identical too because .tap parity depends on them.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ALL_FIXTURES, load_capture
+from readtape_b200 import abi, evlog
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ALL_FIXTURES)
+def test_exact_scan_reproduces_reference_events(name, cuda_lib):
+    """rt_scan_* driven through the reference's own reset sequence (all modes, all reset kinds)."""
+    doc, segs, heads, rows = load_capture(name)
+    tape = cuda_lib.open(evlog.desc_from_heads(heads))
+    tape.upload(rows)
+    bad = []
+    for seg, got in evlog.replay(tape, segs):
+        if not evlog.matches_fixture(seg, got):
+            bad.append((seg.row, seg.parmset, len(got), seg.nevents))
+    tape.close()
+    assert not bad, f"{len(bad)}/{len(segs)} segments differ from the reference, first: {bad[:3]}"
+
+
+@pytest.mark.parametrize("name", ["Microdata_20blks.nm_tap", "1600bpi_ukn_6s", "sf93_8blks", "analog", "tss_4secs"])
+def test_cuda_equals_oracle_event_for_event(name, cuda_lib, oracle_lib):
+    """Same seeded inputs through both libraries; on a mismatch the first differing event is shown."""
+    doc, segs, heads, rows = load_capture(name)
+    desc = evlog.desc_from_heads(heads)
+    tg, to = cuda_lib.open(desc), oracle_lib.open(desc)
+    tg.upload(rows); to.upload(rows)
+    assert tg.nrows == to.nrows
+    for (seg, a), (_, b) in zip(evlog.replay(tg, segs), evlog.replay(to, segs)):
+        if a.tobytes() != b.tobytes():
+            k = evlog._first_diff(a, b)
+            pytest.fail(f"segment row {seg.row} parmset {seg.parmset}: event #{k}: cuda {a[k] if k < len(a) else None} "
+                        f"oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)} events)")
+    tg.close(); to.close()
+
+
+def test_ingest_tma_equals_plain_kernel(cuda_lib):
+    """K1 with TMA-staged tiles vs the plain-load kernel: identical planes => identical scans."""
+    doc, segs, heads, rows = load_capture("Microdata_20blks.nm_tap")
+    desc = evlog.desc_from_heads(heads)
+    seg = [s for s in segs if s.nevents > 1000][0]
+    out = []
+    for mode in ("tma", "simple"):
+        os.environ["RT_INGEST"] = mode
+        tape = cuda_lib.open(desc)
+        tape.upload(rows)
+        sc = tape.scan(evlog.cfg_for(seg)); sc.reset(abi.RT_RESET_FULL, 0)
+        ev, done = sc.run(tape.nrows)
+        out.append((tape.nrows, done, ev.tobytes()))
+        sc.end(); tape.close()
+    os.environ.pop("RT_INGEST", None)
+    assert out[0] == out[1]
+
+
+def test_chunked_upload_and_end_marker(cuda_lib, oracle_lib):
+    """Appending in odd-sized pieces gives the same tape; the -32768 end marker in head 0 ends it."""
+    doc, segs, heads, rows = load_capture("Microdata_20blks.nm_tap")
+    desc = evlog.desc_from_heads(heads)
+    rows = rows[:150001].copy()
+    rows[140000, 0] = -32768                      # a marker in the middle: everything after it is ignored
+    seg = segs[1]
+    res = []
+    for lib, pieces in ((cuda_lib, [150001]), (cuda_lib, [4096, 10000, 77, 135828]), (oracle_lib, [150001])):
+        tape = lib.open(desc)
+        at = 0
+        for n in pieces:
+            tape.upload(rows[at:at + n]); at += n
+        assert tape.nrows == 140000
+        sc = tape.scan(evlog.cfg_for(seg)); sc.reset(abi.RT_RESET_FULL, 0)
+        ev, done = sc.run(10**9)
+        assert done == 140000
+        res.append(evlog.to_canon(ev).tobytes())
+        sc.end(); tape.close()
+    assert res[0] == res[1] == res[2]
+
+
+@pytest.mark.parametrize("name", ["Microdata_20blks.nm_tap", "PLAGO_beginning.nm_tap", "LJS009_part1_39blks", "1kblks_43blks", "tss_4secs"])
+def test_bulk_scan_lookup_is_exact(name, cuda_lib):
+    """The speculative whole-tape scan: every lookup that HITS must return exactly the events of a
+    fresh reset at the reference's real block start; and it must hit for the bulk of the blocks."""
+    doc, segs, heads, rows = load_capture(name)
+    tape = cuda_lib.open(evlog.desc_from_heads(heads))
+    tape.upload(rows)
+    full = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT)
+            and not (s.flags & abi.RT_F_DESKEWING)]
+    parmsets_used = sorted({s.parmset for s in full})
+    # the deskew pre-pass changes the skew for the main pass: group by (parmset, skew)
+    keys = sorted({(s.parmset, tuple(s.skew)) for s in full})
+    hits = misses = 0
+    for key in keys:
+        group = [s for s in full if (s.parmset, tuple(s.skew)) == key]
+        bulk = tape.bulk_scan([evlog.cfg_for(group[0])])
+        st = bulk.stats()
+        assert st.units >= 1 and st.rows == tape.nrows
+        for seg in group:
+            r = bulk.lookup(0, seg.row)
+            if r is None:
+                misses += 1
+                continue
+            ev, valid = r
+            end = seg.end_row if seg.end_row >= 0 else tape.nrows
+            if seg.row + valid < end:
+                misses += 1          # the unit ends before the reference's block does: caller must use the exact scan
+                continue
+            canon = evlog.to_canon(ev)
+            canon = canon[canon["row"] < end]
+            if seg.stop_row >= 0:
+                canon = canon[canon["row"] <= seg.stop_row]
+            assert evlog.matches_fixture(seg, canon), f"bulk lookup at row {seg.row} parmset {seg.parmset} is not exact"
+            hits += 1
+        bulk.free()
+    tape.close()
+    assert hits > 0 and hits >= 0.7 * (hits + misses), f"only {hits} of {hits + misses} block starts were served by the bulk scan"
