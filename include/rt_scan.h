@@ -189,6 +189,20 @@ int  rt_bulk_scan(rt_tape *tape, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bul
 int  rt_bulk_lookup(rt_bulk *bulk, uint32_t cfg_index, uint64_t start_row,
                     const rt_event **events, uint64_t *nevents, uint64_t *valid_rows);
 
+/* Diagnostics: the unit rt_bulk_lookup() would consult for `start_row` and the per-track proof data
+ * (~0 means "none").  A unit covers start_row iff start_row == row0, or start_row >= row0 - 256 and for every
+ * track  sync_row >= need_sync_row  and  (last_loud_row is none or < start_row), or the same with
+ * (sync_early, loud_early).  rt_bulk_lookup() tries this unit and the next one. */
+typedef struct rt_unit_info {
+   uint64_t unit_index, nunits, row0, row_end;
+   uint32_t ntrks, pad;
+   uint64_t first_event_row[RT_MAXTRKS], sync_row[RT_MAXTRKS], last_loud_row[RT_MAXTRKS], need_sync_row[RT_MAXTRKS];
+   uint64_t sync_early[RT_MAXTRKS], loud_early[RT_MAXTRKS];
+   uint32_t nevents[RT_MAXTRKS];
+   uint32_t pad2;
+} rt_unit_info;
+int  rt_bulk_unit_info(const rt_bulk *bulk, uint32_t cfg_index, uint64_t start_row, rt_unit_info *out);
+
 typedef struct rt_bulk_stats {
    uint64_t rows;            /* rows on the tape                                             */
    uint64_t units;           /* units per cfg                                                */

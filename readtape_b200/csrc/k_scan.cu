@@ -87,33 +87,35 @@ k_units_scan(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta 
       reset_full(c, t, s, trk, ud.row0, row_time(c, ud.row0) == 0.0);
       const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
       PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
-      uint64_t sync_row = RT_NOROW, last_loud = RT_NOROW;
-      float runmin = 0, runmax = 0; bool have_run = false;
+      /* proof data, collected only before the first event (DESIGN.md "unit equivalence"):
+           last_loud     last loud row (QuietTracker) seen so far, starting RT_PRESCAN_ROWS before the unit
+           sync_row      LAST row before the first event at which this scan's state is canonical and the
+                         row is not loud; loud_at_sync = last_loud at that moment
+           sync_first    FIRST such row with nothing loud since the unit start (used to chain units)
+         canonical = a pure function of the samples: for the peak detector the running maximum has just
+         left a FULL window (both scans rescan there, which also refreshes the lazily kept minimum);
+         for the zero-crossing detectors any row once v_prev and the deskew FIFO are warm. */
+      QuietTracker qt; qt.init(c, trk, quiet_thr);
+      const uint64_t pre0 = ud.row0 > RT_PRESCAN_ROWS ? ud.row0 - RT_PRESCAN_ROWS : 0;
+      for (uint64_t j = pre0; j < ud.row0; ++j) qt.feed(c, plane, j, raw_at(c, plane, j));
+      const uint64_t quiet_from = qt.last_loud == RT_NOROW ? pre0 : qt.last_loud + 1;
+      uint64_t sync_row = RT_NOROW, loud_at_sync = RT_NOROW, sync_first = RT_NOROW, sync_early = RT_NOROW, loud_early = RT_NOROW;
+      bool early_frozen = false;
+      const int lead = max(trk + (row_time(c, ud.row0) == 0.0 ? 1 : 0), c.skew[trk]);
+      const uint64_t own_fill = ud.row0 + (uint64_t)(c.det == RT_DET_PEAK ? lead + c.width + 1 : lead + 2);
       for (uint64_t row = ud.row0; row < ud.row_end; ++row) {
-         float v_now;
-         unsigned probe = track_row(c, t, s, trk, plane, row, em, &v_now);
+         float v_raw;
+         unsigned probe = track_row(c, t, s, trk, plane, row, em, &v_raw);
          if (em.n == 0) {                              /* still before the first event: keep the proof data */
-            if (c.det == RT_DET_PEAK) {
-               if (t.init_row == RT_NOROW) {           /* the track has been initialised */
-                  if (!have_run) { runmin = runmax = v_now; have_run = true; }
-                  if (v_now < runmin) runmin = v_now;
-                  if (v_now > runmax) runmax = v_now;
-                  if (runmax - runmin >= quiet_thr) {  /* re-anchor on the current window; loud only if IT is */
-                     float mx = -100, mn = +100;
-                     for (int ndx = t.left;;) {
-                        float v = t.win[ndx];
-                        if (v > mx) mx = v;
-                        if (v < mn) mn = v;
-                        if (ndx == t.right) break;
-                        if (++ndx >= c.width) ndx = 0; }
-                     runmin = mn; runmax = mx;
-                     if (mx - mn >= quiet_thr) last_loud = row; }
-                  if (probe & 2) sync_row = row; } }
-            else {                                      /* zero-crossing detectors: no window to converge */
-               if (v_now > RT_ZEROCROSS_PEAK || v_now < -RT_ZEROCROSS_PEAK) last_loud = row;
-               sync_row = row; } } }
+            qt.feed(c, plane, row, v_raw);
+            const bool canonical = c.det == RT_DET_PEAK ? (probe & 2) != 0 : row >= own_fill;
+            if (sync_early != RT_NOROW && qt.last_loud != loud_early) early_frozen = true;   /* the first quiet stretch is over */
+            if (canonical && (qt.last_loud == RT_NOROW || qt.last_loud < row)) {
+               sync_row = row; loud_at_sync = qt.last_loud;
+               if (!early_frozen) { sync_early = row; loud_early = qt.last_loud; }
+               if (sync_first == RT_NOROW && row >= own_fill && (qt.last_loud == RT_NOROW || qt.last_loud < ud.row0)) sync_first = row; } } }
       TrkMeta m;
-      m.first_event_row = em.first_row; m.sync_row = sync_row; m.last_loud_row = last_loud;
+      m.first_event_row = em.first_row; m.sync_row = sync_row; m.last_loud_row = loud_at_sync; m.sync_first = sync_first; m.quiet_from = quiet_from; m.sync_early = sync_early; m.loud_early = loud_early;
       m.first_chunk = em.first_chunk; m.nevents = em.n; m.failed = t.failed; m.pad = 0;
       meta[f] = m;
       atomicAdd(rows_scanned, (unsigned long long)(ud.row_end - ud.row0)); } }

@@ -441,7 +441,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       if (dc.det == RT_DET_PEAK) {
          quiet_thr = dc.p.pkww_rise * 0.999f;
          if (dc.p.pkww_rise < 1e-3f) quiet_thr = 0;                      /* nothing can be proven quiet: every lookup misses */
-         up.thr = (int)(0.5 * dc.p.pkww_rise / lsb); }
+         up.thr = (int)(0.75 * dc.p.pkww_rise / lsb); }
       else if (dc.det == RT_DET_ZC) up.thr = (int)(0.9 * RT_ZEROCROSS_PEAK / lsb);
       else up.thr = (int)(0.9 * std::max(0.05, 0.5 / std::max(1, dc.samples_per_bit)) / lsb);
       uint64_t gap_rows = (uint64_t)(6.0 * rows_per_bit) + 1;
@@ -512,25 +512,71 @@ extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
    if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");
    *out = b->stats; return RT_OK; }
 
+extern "C" int rt_bulk_unit_info(const rt_bulk *b, uint32_t ci, uint64_t start_row, rt_unit_info *out) {
+   if (!b || ci >= b->cfgs.size() || !out) return set_err(RT_ERR_ARG, "rt_bulk_unit_info: bad argument");
+   const BulkCfg &bc = b->cfgs[ci];
+   const uint32_t nt = b->tape->desc.ntrks;
+   memset(out, 0, sizeof *out);
+   if (bc.units.empty()) return RT_MISS;
+   size_t lo = 0, hi = bc.units.size();
+   while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (bc.units[mid].row0 <= start_row) lo = mid; else hi = mid; }
+   const UnitDesc &u = bc.units[lo];
+   out->unit_index = lo; out->nunits = bc.units.size(); out->row0 = u.row0; out->row_end = u.row_end; out->ntrks = nt;
+   const bool tz = rt_row_time(&b->tape->desc, start_row) == 0.0;
+   for (uint32_t k = 0; k < nt; ++k) {
+      const TrkMeta &m = bc.meta[lo * nt + k];
+      out->first_event_row[k] = m.first_event_row; out->sync_row[k] = m.sync_row; out->last_loud_row[k] = m.last_loud_row;
+      out->sync_early[k] = m.sync_early; out->loud_early[k] = m.loud_early;
+      out->nevents[k] = m.nevents; out->need_sync_row[k] = start_row + (uint64_t)fill_of(bc.dc, k, tz); }
+   return RT_OK; }
+
+/* Can unit `ui` stand in for a fresh RT_RESET_FULL at `start_row`?  (DESIGN.md "unit equivalence") */
+static bool unit_covers(const BulkCfg &bc, const rt_tape_desc &desc, uint32_t nt, size_t ui, uint64_t start_row) {
+   const UnitDesc &u = bc.units[ui];
+   const TrkMeta *m = &bc.meta[ui * nt];
+   if (start_row >= u.row_end) return false;
+   for (uint32_t k = 0; k < nt; ++k) if (m[k].failed) return false;
+   if (start_row == u.row0) return true;                        /* the very same reset: trivially identical */
+   const uint64_t pre0 = u.row0 > RT_PRESCAN_ROWS ? u.row0 - RT_PRESCAN_ROWS : 0;
+   if (start_row < pre0) return false;                          /* quietness before pre0 was never examined */
+   const bool tz = rt_row_time(&desc, start_row) == 0.0;
+   for (uint32_t k = 0; k < nt; ++k) {
+      const uint64_t need = start_row + (uint64_t)fill_of(bc.dc, k, tz);
+      /* two recorded (canonical row, last loud row before it) pairs: the end of the unit's first quiet stretch,
+         and the last one before its first event; either proves the equivalence */
+      const bool late = m[k].sync_row != RT_NOROW && m[k].sync_row >= need && (m[k].last_loud_row == RT_NOROW || m[k].last_loud_row < start_row);
+      const bool early = m[k].sync_early != RT_NOROW && m[k].sync_early >= need && (m[k].loud_early == RT_NOROW || m[k].loud_early < start_row);
+      if (!late && !early) return false; }
+   return true; }
+
 extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event **events, uint64_t *nevents, uint64_t *valid_rows) {
    if (!b || ci >= b->cfgs.size()) return set_err(RT_ERR_ARG, "rt_bulk_lookup: bad argument");
    BulkCfg &bc = b->cfgs[ci];
    const uint32_t nt = b->tape->desc.ntrks;
    if (bc.units.empty()) return RT_MISS;
-   /* the last unit that starts at or before start_row */
+   /* candidates: the last unit that starts at or before start_row, and the one after it (the reference's
+      reset row may lie a little BEFORE the row the unit finder picked) */
    size_t lo = 0, hi = bc.units.size();
    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (bc.units[mid].row0 <= start_row) lo = mid; else hi = mid; }
-   const UnitDesc &u = bc.units[lo];
-   if (u.row0 > start_row || start_row >= u.row_end) return RT_MISS;
+   if (!unit_covers(bc, b->tape->desc, nt, lo, start_row)) {
+      if (lo + 1 < bc.units.size() && unit_covers(bc, b->tape->desc, nt, lo + 1, start_row)) ++lo;
+      else return RT_MISS; }
    const TrkMeta *m = &bc.meta[lo * nt];
-   const bool tz = rt_row_time(&b->tape->desc, start_row) == 0.0;
-   for (uint32_t k = 0; k < nt; ++k) {
-      if (m[k].failed) return RT_MISS;
-      if (start_row == u.row0) continue;                       /* the very same reset: trivially identical */
-      if (m[k].sync_row == RT_NOROW) return RT_MISS;
-      if (m[k].sync_row < start_row + (uint64_t)fill_of(bc.dc, k, tz)) return RT_MISS;
-      if (bc.dc.det == RT_DET_PEAK) { if (m[k].last_loud_row != RT_NOROW && m[k].last_loud_row >= start_row) return RT_MISS; }
-      else if (m[k].last_loud_row != RT_NOROW) return RT_MISS; }
+   /* Chaining: while the unit holds no event at all, the reference's scan passes through it unchanged; it is
+      then identical to the NEXT unit's fresh scan from that unit's first canonical row on, provided that row
+      lies inside the stretch where this unit has already shown the scan to be event-free (the overlap). */
+   while (lo + 1 < bc.units.size()) {
+      bool empty = true;
+      for (uint32_t k = 0; k < nt; ++k) if (m[k].nevents) { empty = false; break; }
+      if (!empty) break;
+      const TrkMeta *mn = &bc.meta[(lo + 1) * nt];
+      const uint64_t known_quiet_end = bc.units[lo].row_end;
+      bool ok = true;
+      for (uint32_t k = 0; k < nt && ok; ++k)
+         ok = !mn[k].failed && mn[k].sync_first != RT_NOROW && mn[k].sync_first < known_quiet_end;
+      if (!ok) break;
+      ++lo; m = mn; }
+   const UnitDesc &ue = bc.units[lo];
    /* merge the per-track chunk chains into (row, trk) order */
    struct CC { uint32_t chunk, left, slot; } cc[RT_MAXTRKS];
    size_t total = 0;
@@ -547,5 +593,5 @@ extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const
       if (++c.slot == RT_EVC) { c.slot = 0; c.chunk = c.left ? bc.chunk_next[c.chunk] : RT_NOCHUNK; } }
    if (events) *events = b->result.data();
    if (nevents) *nevents = b->result.size();
-   if (valid_rows) *valid_rows = u.row_end - start_row;
+   if (valid_rows) *valid_rows = ue.row_end - start_row;
    return RT_OK; }

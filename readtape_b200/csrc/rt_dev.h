@@ -18,6 +18,7 @@
 #define RT_EVC             32      /* events per pool chunk                                     */
 #define RT_NOCHUNK         0xffffffffu
 #define RT_NOROW           0xffffffffffffffffull
+#define RT_PRESCAN_ROWS     256     /* rows before a unit start examined for quietness */
 
 /* compile-time constants of the reference the scan needs (src/decoder.h) */
 #define RT_PKWW_PEAKHEIGHT 4.0f    /* :133 */
@@ -93,8 +94,12 @@ struct UnitDesc {
 /* Per (unit, track) result. */
 struct TrkMeta {
    uint64_t first_event_row;      /* RT_NOROW if the track had no event                      */
-   uint64_t sync_row;             /* last row before the first event at which the state became canonical, RT_NOROW if none */
+   uint64_t sync_row;             /* LAST quiet row before the first event at which the state became canonical, RT_NOROW if none */
    uint64_t last_loud_row;        /* last row before sync_row that violates the quiet rule, RT_NOROW if none */
+   uint64_t sync_early;           /* last canonical quiet row of the FIRST quiet stretch of the unit (frozen at the first loud row after it) */
+   uint64_t loud_early;           /* last loud row before sync_early (from the pre-scan), RT_NOROW if none */
+   uint64_t sync_first;           /* FIRST such row, with the unit quiet from its start up to it (used to chain units), RT_NOROW if none */
+   uint64_t quiet_from;           /* earliest row q <= row0 such that no row in [q, row0] is loud: a reset at any row in [q, row0) is covered too */
    uint32_t first_chunk;          /* head of the chunk chain in the event pool               */
    uint32_t nevents;
    uint32_t failed;               /* 2: the reference would have called fatal() (peak not found) */

@@ -266,8 +266,54 @@ __device__ inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, in
    t.t_clkwindow = t.clk_avg / 2 * c.p.clk_factor;
    t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u); }
 
+/* ---- quiet tracking: the proof data of the speculative scan (DESIGN.md "unit equivalence") ---------
+ * raw_at(j) is the sample of row j as it ENTERS the deskew FIFO.  Any detector window a scan can hold at
+ * row j -- whatever row it was reset at, full or still filling, delayed or not -- only contains raw
+ * samples of rows [j-L+1, j] with L = width + skew delay (peak detector) or 1 + skew delay (zero
+ * crossing).  Row j is "loud" if that span could make ANY such scan in default state fire or arm:
+ *   peak detector : max - min over the span >= 0.999 * pkww_rise   (required_rise at AGC 1, height 4)
+ *   zero crossing : some |v| > ZEROCROSS_PEAK in the span; differentiated: additionally some
+ *                   undifferentiated |v| >= DIFFERENTIATE_THRESHOLD (a reset zeroes v_last_raw, so the
+ *                   first delta after it is the sample itself)
+ * Conservative: "not loud" is a proof, "loud" may be a false alarm. */
+__device__ __forceinline__ float volts_at(const DevCfg &c, const int16_t *plane, uint64_t j) {
+   float v = (float)plane[j] / 32767 * c.maxvolts;
+   return c.invert ? -v : v; }
+
+__device__ inline float raw_at(const DevCfg &c, const int16_t *plane, uint64_t j) {
+   float v = volts_at(c, plane, j);
+   if (c.differentiate) {
+      float prev = j ? volts_at(c, plane, j - 1) : 0.0f;
+      float delta = v - prev;
+      if (delta < RT_DIFF_THRESHOLD && delta > -RT_DIFF_THRESHOLD) delta = 0;
+      v = delta * RT_DIFF_SCALE * c.samples_per_bit; }
+   return v; }
+
+struct QuietTracker {
+   float runmin, runmax, thr; int L; uint64_t last_loud; bool primed;
+   __device__ void init(const DevCfg &c, int trk, float quiet_thr) {
+      L = (c.det == RT_DET_PEAK ? c.width : 1) + c.skew[trk];
+      thr = quiet_thr; last_loud = RT_NOROW; primed = false; runmin = runmax = 0; }
+   /* feed row j (rows must be fed consecutively); v = raw_at(j) */
+   __device__ void feed(const DevCfg &c, const int16_t *plane, uint64_t j, float v) {
+      if (c.det == RT_DET_PEAK) {
+         if (!primed) { runmin = runmax = v; primed = true; }
+         if (v < runmin) runmin = v;
+         if (v > runmax) runmax = v;
+         if (runmax - runmin >= thr) {              /* re-anchor on the exact span; loud only if IT is */
+            float mx = v, mn = v;
+            uint64_t from = j + 1 >= (uint64_t)L ? j + 1 - L : 0;
+            for (uint64_t i = from; i < j; ++i) { float x = raw_at(c, plane, i); if (x > mx) mx = x; if (x < mn) mn = x; }
+            runmin = mn; runmax = mx;
+            if (mx - mn >= thr) last_loud = j; } }
+      else {
+         bool loud = v > RT_ZEROCROSS_PEAK || v < -RT_ZEROCROSS_PEAK;
+         if (c.differentiate) { float u = volts_at(c, plane, j); loud = loud || u >= RT_DIFF_THRESHOLD || u <= -RT_DIFF_THRESHOLD; }
+         if (loud) last_loud = j + (uint64_t)(L - 1); } } };   /* it stays inside every span for L rows */
+
 /* ---- one row of one track ------------------------------------------------------------------- */
-/* returns the probe bits of peak_step (0 for the other detectors / skipped rows); *v_out = v_now */
+/* returns the probe bits of peak_step (0 for the other detectors / skipped rows);
+   *v_out = the sample before the deskew FIFO (after invert/differentiate) */
 template <class Emit>
 __device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane,
                                      uint64_t row, Emit &em, float *v_out) {
@@ -288,7 +334,7 @@ __device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s,
       else v_now = s.vdelayed[s.ndx_next];
       s.vdelayed[s.ndx_next] = v;
       if (++s.ndx_next >= delay) s.ndx_next = 0; }
-   *v_out = v_now;
+   *v_out = v;
    /* (Q2) rows before this track's (re)initialisation row are not looked at */
    if (t.init_row != RT_NOROW) {
       if (row < t.init_row) return 0;

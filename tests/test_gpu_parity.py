@@ -98,6 +98,7 @@ def test_bulk_scan_lookup_is_exact(name, cuda_lib):
     # the deskew pre-pass changes the skew for the main pass: group by (parmset, skew)
     keys = sorted({(s.parmset, tuple(s.skew)) for s in full})
     hits = misses = 0
+    why = []
     for key in keys:
         group = [s for s in full if (s.parmset, tuple(s.skew)) == key]
         bulk = tape.bulk_scan([evlog.cfg_for(group[0])])
@@ -107,11 +108,21 @@ def test_bulk_scan_lookup_is_exact(name, cuda_lib):
             r = bulk.lookup(0, seg.row)
             if r is None:
                 misses += 1
+                ui = bulk.unit_info(0, seg.row)
+                def okpair(s_, l_, need):
+                    return s_ is not None and s_ >= need and (l_ is None or l_ < seg.row)
+                bad = [k for k in range(len(ui["sync_row"]))
+                       if not okpair(ui["sync_row"][k], ui["last_loud_row"][k], ui["need_sync_row"][k])
+                       and not okpair(ui["sync_early"][k], ui["loud_early"][k], ui["need_sync_row"][k])]
+                why.append(f"row {seg.row}: unit [{ui['row0']},{ui['row_end']}) bad tracks {bad}: " + "; ".join(
+                    f"trk{k} first_ev {ui['first_event_row'][k]} sync {ui['sync_row'][k]}/{ui['sync_early'][k]} need {ui['need_sync_row'][k]} "
+                    f"loud {ui['last_loud_row'][k]}/{ui['loud_early'][k]}" for k in bad[:3]))
                 continue
             ev, valid = r
             end = seg.end_row if seg.end_row >= 0 else tape.nrows
             if seg.row + valid < end:
                 misses += 1          # the unit ends before the reference's block does: caller must use the exact scan
+                why.append(f"row {seg.row}: unit ends at {seg.row + valid} before the block does ({end})")
                 continue
             canon = evlog.to_canon(ev)
             canon = canon[canon["row"] < end]
@@ -121,4 +132,8 @@ def test_bulk_scan_lookup_is_exact(name, cuda_lib):
             hits += 1
         bulk.free()
     tape.close()
-    assert hits > 0 and hits >= 0.7 * (hits + misses), f"only {hits} of {hits + misses} block starts were served by the bulk scan"
+    print(f"{name}: bulk hits {hits}, misses {misses}")
+    for w in why[:8]:
+        print("   miss:", w)
+    assert hits > 0 and hits >= 0.7 * (hits + misses), \
+        f"only {hits} of {hits + misses} block starts were served by the bulk scan; " + " | ".join(why[:4])
