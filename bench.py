@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- track-samples/s of the per-track analog scan on synthetic 9-track NRZI TBIN.
+
+Metric (BASELINE.json): track-samples/s = rows x tracks scanned / time, with achieved HBM GB/s
+against the measured roofline.  Workload at N=1: BASELINE.json configs[1] -- "synthetic 9-track
+781 kHz TBIN, 10 Gsample, NRZI, 1 GPU, 1 parmset" = 10e9 track-samples = 1 111 111 111 rows x 9 x
+int16 = 20.0 GB.  N>1: one process per GPU, each scans its own tape of that size
+(time-sharded segments of an N-times longer reel, cut in inter-block gaps): weak scaling, no
+data-path collective; NCCL carries only the barrier, the max-over-ranks time and the result gather
+(per-rank event counts).
+
+A step = one pass of the hot path over the whole tape:
+  value : TBIN rows already resident in HBM -> ingest (de-interleave + quiet map) -> unit table ->
+          scan kernel -> events in HBM                         [rt_attach_device + rt_bulk_scan]
+  e2e   : the same through the C-ABI with HOST buffers: pinned host rows -> H2D -> ... -> events and
+          proof data copied back to pinned host memory         [rt_upload + rt_bulk_scan + rt_bulk_fetch]
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/readtape_ref, the
+unmodified readtape 3.18 binary built by oracle/Makefile) on all host cores, each step a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from readtape_b200 import abi, parmsets, synth, tbin  # noqa: E402
+
+FULL_ROWS = 1_111_111_111          # 10e9 track-samples / 9 tracks
+METRIC = "track-samples/s, 9-track 781 kHz NRZI TBIN scan"
+UNIT = "track-samples/s"
+
+
+def workload_name(rows):
+    return (f"synthetic 9-track 781.25 kHz 800 BPI NRZI TBIN, {rows * 9 / 1e9:.2f}e9 track-samples "
+            f"({rows} rows, {rows * 18 / 1e9:.2f} GB int16), 1 parmset (NRZI #0), per GPU")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.lines, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the reference CPU arm --------------------------------------------------------------------------
+def reference_run(tile, ntiles_per_proc, nproc, steps, warmup, workdir):
+    """nproc independent readtape_ref processes, each decoding its own TBIN of ntiles_per_proc super-tiles."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+    kind = "reference"
+    if not os.path.exists(exe):
+        return None
+    hdr = synth.nrzi_header()
+    path = os.path.join(workdir, "sample.tbin")
+    rows = np.concatenate([tile] * ntiles_per_proc) if ntiles_per_proc > 1 else tile
+    tbin.write_tbin(path, hdr, rows)
+    nrows = rows.shape[0]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([exe, "-q", "-nm", "-nrzi", "-bpi=800", "-ips=50", "-tap", "-nolog", "-nolabels",
+                                   f"-outf={workdir}/out{p}", path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                 for p in range(nproc)]
+        rcs = [p.wait() for p in procs]
+        dt = time.perf_counter() - t0
+        if any(rcs):
+            raise RuntimeError(f"readtape_ref exited {rcs}")
+        if it >= warmup:
+            times.append(dt)
+    tsamp = nrows * 9 * nproc
+    tap = os.path.join(workdir, "out0.tap")
+    return {"value": tsamp * len(times) / sum(times), "ms_per_step": 1e3 * sum(times) / len(times), "kind": kind,
+            "cores": nproc, "rows_per_proc": nrows, "tap_bytes": os.path.getsize(tap) if os.path.exists(tap) else None,
+            "sample": f"{nproc} processes x {ntiles_per_proc} super-tiles ({nrows} rows x 9 tracks each) of the same synthetic "
+                      f"tape, unmodified readtape 3.18 (gcc -O2), whole program incl. file read and .tap write"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("RT_BENCH_ROWS", FULL_ROWS)))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    K = args.steps
+
+    tile = synth.nrzi_tile()
+    nproc = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        work = tempfile.mkdtemp(prefix="rtref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            r = reference_run(tile, 2, nproc, K, W, work)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/readtape_ref not built (run make -C oracle ref in the build container)"}))
+            return
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload_name(args.rows), "note": "each step decodes a bounded sample of that tape"},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    lib = abi.load_product()                      # raises if the CUDA library is missing: no fallback
+    rows = args.rows
+    T = tile.shape[0]
+    hdr = synth.nrzi_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
+
+    # ---- device-resident input: the super-tile repeated (seamless by construction) ----
+    dev = torch.empty((rows, 9), dtype=torch.int16, device="cuda")
+    tile_t = torch.from_numpy(tile).cuda()
+    for at in range(0, rows, T):
+        n = min(T, rows - at)
+        dev[at:at + n] = tile_t[:n]
+    torch.cuda.synchronize()
+    tape = lib.open(desc, device=local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        tape.clear()
+        tape.attach_device(dev.data_ptr(), rows)
+        bulk = tape.bulk_scan([cfg])
+        st = bulk.stats()
+        bulk.free()
+        return st
+
+    for _ in range(W):
+        st = step_resident()
+    sampler = ClockSampler(local_rank); sampler.start()
+    time.sleep(0.25)
+    stats = []
+    barrier(); t0 = time.perf_counter()
+    for _ in range(K):
+        stats.append(step_resident())
+    barrier(); t1 = time.perf_counter()
+    clocks = sampler.stop()
+    elapsed = t1 - t0
+    if dist is not None:
+        tt = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    tsamp = rows * 9
+    value = world * tsamp * K / elapsed
+    ms_scan = float(np.mean([s.ms_scan for s in stats])); ms_units = float(np.mean([s.ms_units for s in stats]))
+    ms_ingest = float(np.mean([s.ms_preprocess for s in stats]))
+    events = int(stats[-1].events); units = int(stats[-1].units)
+    launches_per_step = int(stats[-1].launches) + 2   # + the ingest kernels (TMA tiles + plain tail)
+
+    # ---- e2e: host buffers through the C-ABI ----
+    e2e = None
+    if not args.no_e2e:
+        nbytes = rows * 18
+        hptr = lib.L.rt_host_alloc(nbytes)
+        if not hptr:
+            raise RuntimeError("rt_host_alloc failed for the pinned host tape")
+        hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_int16)), shape=(rows, 9))
+        for at in range(0, rows, T):
+            n = min(T, rows - at)
+            hbuf[at:at + n] = tile[:n]
+
+        def step_e2e():
+            tape.clear()
+            tape.upload_ptr(hptr, rows)
+            bulk = tape.bulk_scan([cfg])
+            bulk.fetch()
+            st = bulk.stats()
+            hit = bulk.lookup(0, 0)                       # the user-facing read of the result
+            assert hit is not None
+            bulk.free()
+            return st
+
+        for _ in range(max(1, W // 2)):
+            step_e2e()
+        ke = max(1, K)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(ke):
+            ste = step_e2e()
+        barrier(); t1 = time.perf_counter()
+        el = t1 - t0
+        if dist is not None:
+            tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = float(tt.item())
+        e2e = {"value": world * tsamp * ke / el, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": int(ste.d2h_bytes), "ms_per_step": 1e3 * el / ke}
+        lib.L.rt_host_free(hptr)
+
+    # ---- result gather over NCCL: per-rank event counts (the only inter-GPU traffic of this path) ----
+    all_events = [events]
+    if dist is not None:
+        g = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([events], dtype=torch.int64, device="cuda"))
+        all_events = [int(x.item()) for x in g]
+
+    # ---- CPU baseline on rank 0, N=1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        work = tempfile.mkdtemp(prefix="rtcpu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            r = reference_run(tile, 2, nproc, 1, 0, work)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = 2.0 * tsamp + 32.0 * events                # 2 B read per track-sample + event bytes
+        achieved = alg_bytes / (ms_scan * 1e-3) / 1e9
+        ingest_bytes = 4.0 * tsamp                              # K1: 2 B read + 2 B written per track-sample
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(rows), "l2": "inputs (rows*18 B per step) are far larger than the 126 MB L2",
+                       "units_per_tape": units, "events_per_tape": events, "super_tile_sha256": synth.tile_sha256(tile)[:16],
+                       "parallelism": f"{world} x independent tapes" if world > 1 else "1 GPU"},
+            "roofline": {"bound": "hbm", "kernel": "k_units_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_scan,
+                         "other_kernels": {"k_ingest_tma": {"ms": ms_ingest, "achieved_GBps": ingest_bytes / (ms_ingest * 1e-3) / 1e9 if ms_ingest else None,
+                                                           "frac": (ingest_bytes / (ms_ingest * 1e-3) / 1e9 / peak) if ms_ingest else None},
+                                           "unit_finder(5 kernels)": {"ms": ms_units}}},
+            "e2e": e2e, "gpu_launches": launches_per_step * K, "clocks": clocks,
+            "cpu_baseline": cpu, "result_gather": {"events_per_rank": all_events},
+        }
+        print(json.dumps(line))
+    tape.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -145,6 +145,8 @@ int  rt_open(const rt_tape_desc *desc, int device, rt_tape **out);
 int  rt_upload(rt_tape *tape, const int16_t *rows, uint64_t nrows);
 /* Same, but `rows_dev` is already a DEVICE pointer (product library only). */
 int  rt_attach_device(rt_tape *tape, const void *rows_dev, uint64_t nrows);
+/* Forget the samples but keep the device buffers (re-use the tape for the next capture of similar size). */
+int  rt_clear(rt_tape *tape);
 uint64_t rt_nrows(const rt_tape *tape);
 void rt_close(rt_tape *tape);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost; malloc/free in the oracle) */
@@ -183,6 +185,9 @@ void rt_scan_end(rt_scan *scan);
  * block start) yields bit-identical events; rt_bulk_lookup() applies that proof.
  * Not for Whirlwind (its state persists across blocks): returns RT_ERR_UNSUPPORTED. */
 int  rt_bulk_scan(rt_tape *tape, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bulk **out);
+/* rt_bulk_scan() leaves its results in device memory; rt_bulk_fetch() copies them to the host (pinned
+ * memory).  The first rt_bulk_lookup()/rt_bulk_unit_info() call does it implicitly. */
+int  rt_bulk_fetch(rt_bulk *bulk);
 /* Events a fresh RT_RESET_FULL scan of configuration `cfg_index` starting at `start_row`
  * would produce, for rows [start_row, start_row + *valid_rows).  RT_MISS if no unit can be
  * proven equivalent (the caller then uses rt_scan_*). */
@@ -214,6 +219,7 @@ typedef struct rt_bulk_stats {
    double   ms_scan;         /* device time: scan kernel                                     */
    uint32_t launches;        /* kernels launched by the call                                 */
    uint32_t pad;
+   uint64_t d2h_bytes;       /* bytes rt_bulk_fetch() copied to the host                     */
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);
 void rt_bulk_free(rt_bulk *bulk);

@@ -49,7 +49,7 @@ class BulkStats(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("units", C.c_uint64), ("events", C.c_uint64),
                 ("rows_scanned", C.c_uint64), ("track_samples", C.c_uint64),
                 ("ms_preprocess", C.c_double), ("ms_units", C.c_double), ("ms_scan", C.c_double),
-                ("launches", C.c_uint32), ("pad", C.c_uint32)]
+                ("launches", C.c_uint32), ("pad", C.c_uint32), ("d2h_bytes", C.c_uint64)]
 
 
 class UnitInfo(C.Structure):
@@ -65,10 +65,10 @@ EVENT_DTYPE = np.dtype([("row", "<u8"), ("t_event", "<f8"), ("v_top", "<f4"), ("
                         ("agc_gain", "<f4"), ("trk", "u1"), ("kind", "u1"), ("pad", "u1", (2,))])
 assert EVENT_DTYPE.itemsize == 32
 
-EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_attach_device",
+EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_attach_device", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
-           "rt_bulk_scan", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
+           "rt_bulk_scan", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
            "rt_row_time"]
 
 
@@ -96,6 +96,8 @@ class Lib:
         L.rt_open.argtypes = [P(TapeDesc), i32, P(vp)]
         L.rt_upload.argtypes = [vp, vp, u64]
         L.rt_attach_device.argtypes = [vp, vp, u64]
+        L.rt_clear.argtypes = [vp]
+        L.rt_bulk_fetch.argtypes = [vp]
         L.rt_nrows.argtypes = [vp]; L.rt_nrows.restype = u64
         L.rt_close.argtypes = [vp]; L.rt_close.restype = None
         L.rt_host_alloc.argtypes = [C.c_size_t]; L.rt_host_alloc.restype = vp
@@ -115,7 +117,7 @@ class Lib:
         L.rt_bulk_free.argtypes = [vp]; L.rt_bulk_free.restype = None
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
         L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
-        for fn in ("rt_open", "rt_upload", "rt_attach_device", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
+        for fn in ("rt_open", "rt_upload", "rt_attach_device", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
                    "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_lookup",
                    "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_pkww_width"):
             getattr(L, fn).restype = i32
@@ -151,8 +153,15 @@ class Tape:
         assert rows.ndim == 2 and rows.shape[1] == self.desc.nheads
         self.lib.check(self.lib.L.rt_upload(self.h, rows.ctypes.data, rows.shape[0]))
 
+    def upload_ptr(self, host_ptr: int, nrows: int) -> None:
+        """rows already laid out in (pinned) host memory at `host_ptr`"""
+        self.lib.check(self.lib.L.rt_upload(self.h, host_ptr, nrows))
+
     def attach_device(self, dev_ptr: int, nrows: int) -> None:
         self.lib.check(self.lib.L.rt_attach_device(self.h, dev_ptr, nrows))
+
+    def clear(self) -> None:
+        self.lib.check(self.lib.L.rt_clear(self.h))
 
     @property
     def nrows(self) -> int:
@@ -218,6 +227,9 @@ class Bulk:
         if rc == RT_MISS:
             return None
         return _events_from(ev, n.value), int(valid.value)
+
+    def fetch(self) -> None:
+        self.lib.check(self.lib.L.rt_bulk_fetch(self.h))
 
     def unit_info(self, cfg_index: int, start_row: int) -> dict:
         ui = UnitInfo()

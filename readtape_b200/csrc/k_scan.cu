@@ -118,7 +118,8 @@ k_units_scan(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta 
       m.first_event_row = em.first_row; m.sync_row = sync_row; m.last_loud_row = loud_at_sync; m.sync_first = sync_first; m.quiet_from = quiet_from; m.sync_early = sync_early; m.loud_early = loud_early;
       m.first_chunk = em.first_chunk; m.nevents = em.n; m.failed = t.failed; m.pad = 0;
       meta[f] = m;
-      atomicAdd(rows_scanned, (unsigned long long)(ud.row_end - ud.row0)); } }
+      atomicAdd(&rows_scanned[0], (unsigned long long)(ud.row_end - ud.row0));
+      if (em.n) atomicAdd(&rows_scanned[1], (unsigned long long)em.n); } }
 
 /* ---- launchers ------------------------------------------------------------------------------ */
 void launch_ctx_reset(const DevCfg &c, TrkState *st, SkewState *sk, int kind, uint64_t row, int tz, cudaStream_t s) {

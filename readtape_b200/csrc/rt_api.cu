@@ -58,6 +58,12 @@ struct rt_tape {
    int force_simple_ingest = 0;
    int launches = 0;
    float ms_ingest = 0;
+   std::vector<cudaEvent_t> ingest_events;
+   uint64_t h2d_bytes = 0;
+   /* grow-only caches re-used by successive rt_bulk_scan()/rt_bulk_fetch() calls (cudaMalloc/cudaHostAlloc of
+      many GB cost far more than the scan itself) */
+   rt_event *pool_cache = nullptr; uint32_t *next_cache = nullptr; uint32_t pool_cache_chunks = 0; bool pool_cache_busy = false;
+   rt_event *pin_cache = nullptr; size_t pin_cache_events = 0; bool pin_cache_busy = false;
 };
 
 static int tape_reserve(rt_tape *t, uint64_t rows) {
@@ -116,6 +122,7 @@ extern "C" int rt_open(const rt_tape_desc *desc, int device, rt_tape **out) {
    CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
    *out = t; return RT_OK; }
 
+/* enqueue the ingest of `nrows` rows at d_src (device) on the tape's stream; does not wait */
 static int tape_ingest(rt_tape *t, const int16_t *d_src, uint64_t nrows) {
    cudaEvent_t e0, e1;
    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
@@ -124,10 +131,17 @@ static int tape_ingest(rt_tape *t, const int16_t *d_src, uint64_t nrows) {
                                  t->gmm, t->ngran_cap, t->d_first_end, t->sms, t->force_simple_ingest, t->stream, &t->launches);
    if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "ingest kernel launch failed: %s", cudaGetErrorString(e));
    CU(cudaEventRecord(e1, t->stream));
-   CU(cudaEventSynchronize(e1));
-   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); t->ms_ingest += ms;
-   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   t->ingest_events.push_back(e0); t->ingest_events.push_back(e1);
    t->nrows += nrows; t->valid_known = false;
+   return RT_OK; }
+
+/* wait for everything enqueued on the tape's stream; fold the ingest kernel times into ms_ingest */
+static int tape_drain(rt_tape *t) {
+   CU(cudaStreamSynchronize(t->stream));
+   for (size_t i = 0; i + 1 < t->ingest_events.size(); i += 2) {
+      float ms = 0; cudaEventElapsedTime(&ms, t->ingest_events[i], t->ingest_events[i + 1]); t->ms_ingest += ms;
+      cudaEventDestroy(t->ingest_events[i]); cudaEventDestroy(t->ingest_events[i + 1]); }
+   t->ingest_events.clear();
    return RT_OK; }
 
 extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
@@ -145,16 +159,18 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
       for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&t->d_stage[i], t->stage_bytes)); CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); } }
    const uint64_t stage_rows = (t->stage_bytes - 256) / (nh * 2) / 2048 * 2048;
    if (t->nrows % 2048 != 0 && !t->force_simple_ingest) { /* appended onto a partial tile: fine, the plain kernel handles it */ }
+   /* copy and ingest are enqueued back to back on one stream (the ingest kernel is ~100x shorter than the
+      PCIe copy of its chunk, so there is nothing to gain from a second stream); the two staging buffers only
+      exist so that a later revision can overlap them.  One synchronisation at the end. */
    uint64_t done = 0; int buf = 0;
    while (done < nrows) {
       uint64_t n = std::min(stage_rows ? stage_rows : nrows - done, nrows - done);
-      CU(cudaEventSynchronize(t->stage_done[buf]));
       CU(cudaMemcpyAsync(t->d_stage[buf], rows + done * nh, (size_t)n * nh * 2, cudaMemcpyHostToDevice, t->stream));
       rc = tape_ingest(t, t->d_stage[buf], n);
       if (rc) return rc;
-      CU(cudaEventRecord(t->stage_done[buf], t->stream));
       done += n; buf ^= 1; }
-   return RT_OK; }
+   t->h2d_bytes += nrows * nh * 2;
+   return tape_drain(t); }
 
 extern "C" int rt_attach_device(rt_tape *t, const void *rows_dev, uint64_t nrows) {
    if (!t || (!rows_dev && nrows)) return set_err(RT_ERR_ARG, "rt_attach_device: null argument");
@@ -162,13 +178,24 @@ extern "C" int rt_attach_device(rt_tape *t, const void *rows_dev, uint64_t nrows
    CU(cudaSetDevice(t->device));
    int rc = tape_reserve(t, t->nrows + nrows);
    if (rc) return rc;
-   return tape_ingest(t, static_cast<const int16_t *>(rows_dev), nrows); }
+   rc = tape_ingest(t, static_cast<const int16_t *>(rows_dev), nrows);
+   if (rc) return rc;
+   return tape_drain(t); }
+
+extern "C" int rt_clear(rt_tape *t) {
+   if (!t) return set_err(RT_ERR_ARG, "rt_clear: null");
+   CU(cudaSetDevice(t->device));
+   int rc = tape_drain(t); if (rc) return rc;
+   unsigned long long none = ~0ull;
+   CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
+   t->nrows = 0; t->nrows_valid = 0; t->valid_known = false; t->ms_ingest = 0; t->h2d_bytes = 0;
+   return RT_OK; }
 
 static int tape_sync_valid(rt_tape *t) {
    if (t->valid_known) return RT_OK;
    unsigned long long fe = ~0ull;
    CU(cudaSetDevice(t->device));
-   CU(cudaStreamSynchronize(t->stream));
+   { int rc = tape_drain(t); if (rc) return rc; }
    CU(cudaMemcpy(&fe, t->d_first_end, sizeof fe, cudaMemcpyDeviceToHost));
    t->nrows_valid = std::min<uint64_t>(t->nrows, fe);
    t->valid_known = true;
@@ -184,6 +211,7 @@ extern "C" void rt_close(rt_tape *t) {
    cudaSetDevice(t->device);
    if (t->stream) cudaStreamSynchronize(t->stream);
    cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
+   cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); }
    if (t->stream) cudaStreamDestroy(t->stream);
    delete t; }
@@ -380,12 +408,17 @@ extern "C" void rt_scan_end(rt_scan *s) {
 /* ---- speculative whole-tape scan ---------------------------------------------------------------- */
 struct BulkCfg {
    rt_scan_cfg cfg{}; DevCfg dc{};
+   /* device-resident results of the scan */
+   UnitDesc *d_units = nullptr; TrkMeta *d_meta = nullptr; rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr;
+   uint32_t nunits = 0, pool_chunks = 0, chunks_used = 0;
+   bool pool_from_cache = false, pin_from_cache = false;
+   /* host copies, filled by rt_bulk_fetch() */
    std::vector<UnitDesc> units; std::vector<TrkMeta> meta; std::vector<uint32_t> chunk_next;
    rt_event *h_pool = nullptr; size_t h_pool_events = 0;      /* pinned */
-   uint32_t chunks_used = 0;
 };
 struct rt_bulk {
    rt_tape *tape = nullptr; std::vector<BulkCfg> cfgs; rt_bulk_stats stats{};
+   bool fetched = false;
    std::vector<rt_event> result;
 };
 
@@ -395,7 +428,11 @@ static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
 
 extern "C" void rt_bulk_free(rt_bulk *b) {
    if (!b) return;
-   for (auto &c : b->cfgs) if (c.h_pool) cudaFreeHost(c.h_pool);
+   cudaSetDevice(b->tape->device);
+   for (auto &c : b->cfgs) {
+      if (c.pin_from_cache) b->tape->pin_cache_busy = false; else if (c.h_pool) cudaFreeHost(c.h_pool);
+      if (c.pool_from_cache) b->tape->pool_cache_busy = false; else { cudaFree(c.d_pool); cudaFree(c.d_chunk_next); }
+      cudaFree(c.d_units); cudaFree(c.d_meta); }
    delete b; }
 
 extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bulk **out) {
@@ -414,19 +451,18 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    /* scratch for the unit finder */
    const size_t words = units_bitmap_words(nrows), nblocks = units_blocks(nrows) + 1;
    const uint32_t units_cap = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
-   uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units = nullptr;
-   unsigned long long *d_rows_scanned = nullptr; unsigned int *d_cursor = nullptr;
-   TrkMeta *d_meta = nullptr; rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr; uint32_t pool_chunks = 0;
+   uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
+   unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr;
    cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
    auto cleanup = [&]() {
-      cudaFree(d_bitmap); cudaFree(d_flags); cudaFree(d_blockcount); cudaFree(d_nunits); cudaFree(d_units);
-      cudaFree(d_rows_scanned); cudaFree(d_cursor); cudaFree(d_meta); cudaFree(d_pool); cudaFree(d_chunk_next);
+      cudaFree(d_bitmap); cudaFree(d_flags); cudaFree(d_blockcount); cudaFree(d_nunits); cudaFree(d_units_tmp);
+      cudaFree(d_counters); cudaFree(d_cursor);
       for (auto &e : ev) cudaEventDestroy(e); };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); rt_bulk_free(b); \
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
    CUB(cudaMalloc(&d_bitmap, words * 4)); CUB(cudaMalloc(&d_flags, words * 4)); CUB(cudaMalloc(&d_blockcount, nblocks * 4));
-   CUB(cudaMalloc(&d_nunits, 4)); CUB(cudaMalloc(&d_units, (size_t)units_cap * sizeof(UnitDesc)));
-   CUB(cudaMalloc(&d_rows_scanned, 8)); CUB(cudaMalloc(&d_cursor, 4));
+   CUB(cudaMalloc(&d_nunits, 4)); CUB(cudaMalloc(&d_units_tmp, (size_t)units_cap * sizeof(UnitDesc)));
+   CUB(cudaMalloc(&d_counters, 16)); CUB(cudaMalloc(&d_cursor, 4));
    b->stats.rows = nrows; b->stats.ms_preprocess = t->ms_ingest;
    for (uint32_t ci = 0; ci < ncfgs; ++ci) {
       BulkCfg &bc = b->cfgs[ci];
@@ -449,58 +485,57 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       const uint64_t ibg_rows = (uint64_t)(200e-6 / dc.sample_deltat) + 1;      /* *_IBG_SECS, decoder.h:105,113,116 */
       up.tail_rows = (uint64_t)(16.0 * rows_per_bit) + ibg_rows + 64 + RT_PKWW_MAX_WIDTH + RT_MAXSKEWSAMP;
       CUB(cudaEventRecord(ev[0], t->stream));
-      cudaError_t e = launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, up, d_bitmap, d_flags, d_blockcount, d_units, units_cap, d_nunits, t->stream, &t->launches);
+      cudaError_t e = launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap, d_nunits, t->stream, &t->launches);
       CUB(e);
       CUB(cudaEventRecord(ev[1], t->stream));
       uint32_t nunits = 0;
       CUB(cudaMemcpyAsync(&nunits, d_nunits, 4, cudaMemcpyDeviceToHost, t->stream));
       CUB(cudaStreamSynchronize(t->stream));
       if (nunits > units_cap) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "unit table overflow (%u > %u)", nunits, units_cap); }
-      bc.units.resize(nunits); bc.meta.resize((size_t)nunits * nt);
-      cudaFree(d_meta); d_meta = nullptr;
-      if (nunits) CUB(cudaMalloc(&d_meta, (size_t)nunits * nt * sizeof(TrkMeta)));
-      /* event pool: first guess one event per 12 track-samples, regrown on overflow */
-      uint64_t want_chunks = std::max<uint64_t>(4096, nrows * nt / 12 / RT_EVC + (uint64_t)nunits * nt);
+      bc.nunits = nunits;
       float ms_scan = 0;
-      for (int attempt = 0; nunits && attempt < 3; ++attempt) {
-         if (want_chunks > pool_chunks) {
-            cudaFree(d_pool); cudaFree(d_chunk_next); d_pool = nullptr; d_chunk_next = nullptr;
-            if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
-            pool_chunks = (uint32_t)want_chunks;
-            CUB(cudaMalloc(&d_pool, (size_t)pool_chunks * RT_EVC * sizeof(rt_event)));
-            CUB(cudaMalloc(&d_chunk_next, (size_t)pool_chunks * 4)); }
-         CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
-         CUB(cudaMemsetAsync(d_rows_scanned, 0, 8, t->stream));
-         CUB(cudaEventRecord(ev[2], t->stream));
-         const uint64_t threads = (uint64_t)nunits * nt;
-         int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * 16);
-         launch_units_scan(dc, d_units, d_nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, quiet_thr, d_rows_scanned, grid, t->stream);
-         CUB(cudaGetLastError()); ++t->launches;
-         CUB(cudaEventRecord(ev[3], t->stream));
-         unsigned int used = 0;
-         CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
-         CUB(cudaStreamSynchronize(t->stream));
-         float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_scan = ms;
-         if (used <= pool_chunks) { bc.chunks_used = used; break; }
-         want_chunks = (uint64_t)used + used / 8 + 1024;
-         if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
+      if (nunits) {
+         CUB(cudaMalloc(&bc.d_units, (size_t)nunits * sizeof(UnitDesc)));
+         CUB(cudaMemcpyAsync(bc.d_units, d_units_tmp, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToDevice, t->stream));
+         CUB(cudaMalloc(&bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta)));
+         /* event pool: first guess one event per 16 track-samples, regrown on overflow */
+         uint64_t want_chunks = std::max<uint64_t>(4096, nrows * nt / 16 / RT_EVC + (uint64_t)nunits * nt);
+         for (int attempt = 0; attempt < 3; ++attempt) {
+            if (want_chunks > bc.pool_chunks) {
+               if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
+               if (bc.pool_from_cache || (!bc.d_pool && !t->pool_cache_busy)) {       /* use / grow the tape's cached pool */
+                  if (want_chunks > t->pool_cache_chunks) {
+                     cudaFree(t->pool_cache); cudaFree(t->next_cache); t->pool_cache = nullptr; t->next_cache = nullptr; t->pool_cache_chunks = 0;
+                     CUB(cudaMalloc(&t->pool_cache, (size_t)want_chunks * RT_EVC * sizeof(rt_event)));
+                     CUB(cudaMalloc(&t->next_cache, (size_t)want_chunks * 4));
+                     t->pool_cache_chunks = (uint32_t)want_chunks; }
+                  bc.d_pool = t->pool_cache; bc.d_chunk_next = t->next_cache; bc.pool_chunks = t->pool_cache_chunks;
+                  bc.pool_from_cache = true; t->pool_cache_busy = true; }
+               else {
+                  cudaFree(bc.d_pool); cudaFree(bc.d_chunk_next); bc.d_pool = nullptr; bc.d_chunk_next = nullptr;
+                  bc.pool_chunks = (uint32_t)want_chunks;
+                  CUB(cudaMalloc(&bc.d_pool, (size_t)bc.pool_chunks * RT_EVC * sizeof(rt_event)));
+                  CUB(cudaMalloc(&bc.d_chunk_next, (size_t)bc.pool_chunks * 4)); } }
+            CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
+            CUB(cudaMemsetAsync(d_counters, 0, 16, t->stream));
+            CUB(cudaEventRecord(ev[2], t->stream));
+            const uint64_t threads = (uint64_t)nunits * nt;
+            int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * 16);
+            launch_units_scan(dc, bc.d_units, d_nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks, quiet_thr, d_counters, grid, t->stream);
+            CUB(cudaGetLastError()); ++t->launches;
+            CUB(cudaEventRecord(ev[3], t->stream));
+            unsigned int used = 0;
+            CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
+            CUB(cudaStreamSynchronize(t->stream));
+            float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_scan = ms;
+            if (used <= bc.pool_chunks) { bc.chunks_used = used; break; }
+            want_chunks = (uint64_t)used + used / 8 + 1024;
+            if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
+         unsigned long long counters[2] = {0, 0};
+         CUB(cudaMemcpy(counters, d_counters, 16, cudaMemcpyDeviceToHost));
+         b->stats.rows_scanned += counters[0]; b->stats.events += counters[1]; }
       float ms_units = 0; cudaEventElapsedTime(&ms_units, ev[0], ev[1]);
       b->stats.ms_units += ms_units; b->stats.ms_scan += ms_scan;
-      /* results to the host */
-      if (nunits) {
-         CUB(cudaMemcpyAsync(bc.units.data(), d_units, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToHost, t->stream));
-         CUB(cudaMemcpyAsync(bc.meta.data(), d_meta, (size_t)nunits * nt * sizeof(TrkMeta), cudaMemcpyDeviceToHost, t->stream));
-         bc.chunk_next.resize(bc.chunks_used);
-         if (bc.chunks_used) {
-            CUB(cudaMemcpyAsync(bc.chunk_next.data(), d_chunk_next, (size_t)bc.chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
-            bc.h_pool_events = (size_t)bc.chunks_used * RT_EVC;
-            CUB(cudaHostAlloc(&bc.h_pool, bc.h_pool_events * sizeof(rt_event), cudaHostAllocDefault));
-            CUB(cudaMemcpyAsync(bc.h_pool, d_pool, bc.h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream)); }
-         unsigned long long rs = 0;
-         CUB(cudaMemcpyAsync(&rs, d_rows_scanned, 8, cudaMemcpyDeviceToHost, t->stream));
-         CUB(cudaStreamSynchronize(t->stream));
-         b->stats.rows_scanned += rs;
-         for (const TrkMeta &m : bc.meta) b->stats.events += m.nevents; }
       b->stats.units = nunits; }
    b->stats.track_samples = nrows * nt * ncfgs;
    b->stats.launches = (uint32_t)(t->launches - launches0);
@@ -508,12 +543,50 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
 #undef CUB
    *out = b; return RT_OK; }
 
+/* Bring the results of rt_bulk_scan() to the host (unit table, proof data, events).  Called by the first
+ * rt_bulk_lookup(); separate so that a caller can overlap it or time it. */
+extern "C" int rt_bulk_fetch(rt_bulk *b) {
+   if (!b) return set_err(RT_ERR_ARG, "rt_bulk_fetch: null");
+   if (b->fetched) return RT_OK;
+   rt_tape *t = b->tape; const uint32_t nt = t->desc.ntrks;
+   CU(cudaSetDevice(t->device));
+   for (BulkCfg &bc : b->cfgs) {
+      const uint32_t nunits = bc.nunits;
+      bc.units.resize(nunits); bc.meta.resize((size_t)nunits * nt); bc.chunk_next.resize(bc.chunks_used);
+      if (!nunits) continue;
+      CU(cudaMemcpyAsync(bc.units.data(), bc.d_units, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToHost, t->stream));
+      CU(cudaMemcpyAsync(bc.meta.data(), bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta), cudaMemcpyDeviceToHost, t->stream));
+      if (bc.chunks_used) {
+         CU(cudaMemcpyAsync(bc.chunk_next.data(), bc.d_chunk_next, (size_t)bc.chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
+         bc.h_pool_events = (size_t)bc.chunks_used * RT_EVC;
+         if (!t->pin_cache_busy) {                                  /* use / grow the tape's cached pinned buffer */
+            if (bc.h_pool_events > t->pin_cache_events) {
+               if (t->pin_cache) cudaFreeHost(t->pin_cache);
+               t->pin_cache = nullptr; t->pin_cache_events = 0;
+               size_t want = bc.h_pool_events + bc.h_pool_events / 16;
+               CU(cudaHostAlloc(&t->pin_cache, want * sizeof(rt_event), cudaHostAllocDefault));
+               t->pin_cache_events = want; }
+            bc.h_pool = t->pin_cache; bc.pin_from_cache = true; t->pin_cache_busy = true; }
+         else CU(cudaHostAlloc(&bc.h_pool, bc.h_pool_events * sizeof(rt_event), cudaHostAllocDefault));
+         CU(cudaMemcpyAsync(bc.h_pool, bc.d_pool, bc.h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
+         b->stats.d2h_bytes += bc.h_pool_events * sizeof(rt_event) + (uint64_t)bc.chunks_used * 4; }
+      b->stats.d2h_bytes += (uint64_t)nunits * (sizeof(UnitDesc) + nt * sizeof(TrkMeta)); }
+   CU(cudaStreamSynchronize(t->stream));
+   /* the device copies are no longer needed */
+   for (BulkCfg &bc : b->cfgs) {
+      cudaFree(bc.d_units); cudaFree(bc.d_meta);
+      if (bc.pool_from_cache) { t->pool_cache_busy = false; bc.pool_from_cache = false; } else { cudaFree(bc.d_pool); cudaFree(bc.d_chunk_next); }
+      bc.d_units = nullptr; bc.d_meta = nullptr; bc.d_pool = nullptr; bc.d_chunk_next = nullptr; }
+   b->fetched = true;
+   return RT_OK; }
+
 extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
    if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");
    *out = b->stats; return RT_OK; }
 
 extern "C" int rt_bulk_unit_info(const rt_bulk *b, uint32_t ci, uint64_t start_row, rt_unit_info *out) {
    if (!b || ci >= b->cfgs.size() || !out) return set_err(RT_ERR_ARG, "rt_bulk_unit_info: bad argument");
+   if (!b->fetched) { int rc = rt_bulk_fetch(const_cast<rt_bulk *>(b)); if (rc) return rc; }
    const BulkCfg &bc = b->cfgs[ci];
    const uint32_t nt = b->tape->desc.ntrks;
    memset(out, 0, sizeof *out);
@@ -551,6 +624,7 @@ static bool unit_covers(const BulkCfg &bc, const rt_tape_desc &desc, uint32_t nt
 
 extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event **events, uint64_t *nevents, uint64_t *valid_rows) {
    if (!b || ci >= b->cfgs.size()) return set_err(RT_ERR_ARG, "rt_bulk_lookup: bad argument");
+   if (!b->fetched) { int rc = rt_bulk_fetch(b); if (rc) return rc; }
    BulkCfg &bc = b->cfgs[ci];
    const uint32_t nt = b->tape->desc.ntrks;
    if (bc.units.empty()) return RT_MISS;
