@@ -1,0 +1,405 @@
+/* readtape_b200/host/readblock_b200.c -- the host side of the drop-in: a replacement for
+ *
+ *        bool readblock(bool retry)                 reference src/readtape.c:1396-1517
+ *
+ * that obtains flux-transition EVENTS from the rt_scan C-ABI (include/rt_scan.h: the CUDA library)
+ * instead of reading rows and calling process_sample() (src/decoder.c:817) once per sample.
+ * Everything above it (process_file, options, parmsets.c, got_datablock, the .tap/.bin/.log
+ * writers) and everything in decode_*.c stays the reference's own unchanged C.
+ *
+ * It is written against the reference's own header (decoder.h) and is meant to be compiled
+ * into readtape by a maintainer.  Nothing of the reference is copied here:
+ * the row loop and process_sample()'s per-row dispatcher are re-formulated event-driven:
+ *
+ *   per block decode:   events = scan(start_row, PARM, globals)          <- GPU
+ *   then, in row order: * the rows at which process_sample() would do something without a
+ *                         detection are computed exactly from the same inequalities it
+ *                         evaluates every row:
+ *                           NRZI  timenow > nrzi.t_lastclock + 2*bitspaceavg  -> nrzi_zerocheck()  (decoder.c:844)
+ *                           PE    timenow - t_lastpeak > bitspaceavg*2.5f      -> idle / pe_end_of_block (:868-877)
+ *                           GCR   timenow > t_lastpeak + 6.00*bitspaceavg      -> idle / gcr_end_of_block (:879-888)
+ *                           WW    timenow - t_lastclkpulseend > avg*1.5f       -> ww_end_of_block (:892-894)
+ *                           the per-track first-sample initialisation rows      (:855-861)
+ *                           interblock_counter expiry                           (:841, :900-903)
+ *                       * each event is handed to the reference's process_up_transition() /
+ *                         process_down_transition() (decoder.c:574/592) exactly as lookfor_peak /
+ *                         lookfor_*zerocrossing would: t->v_top/t_top (or v_bot/t_bot) and the
+ *                         global timenow are set first.
+ * The handlers re-compute AGC themselves; the gain the GPU mirrored is compared after every
+ * event (a free parity self-check): a mismatch is a fatal() error, never silently ignored.
+ *
+ * Link-time glue (no reference source is modified; see readtape_b200/host/Makefile):
+ *   objcopy --weaken-symbol=readblock readtape.o          our readblock() wins
+ *   -Wl,--wrap=init_trackstate,--wrap=ww_init_blockstate,--wrap=init_trackpeak_state,
+ *       --wrap=compute_avg_height                         so we know which reset preceded a call
+ */
+#include "decoder.h"
+#include "rt_scan.h"
+
+/* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
+extern FILE *inf;
+extern bool tbin_file, invert_data, do_differentiate, find_zeros, doing_density_detection, doing_deskew;
+extern struct tbin_hdr_t tbin_hdr;
+extern struct tbin_dat_t tbin_dat;
+extern int nheads, samples_per_bit, subsample, head_to_trk[MAXTRKS];
+extern long long lines_in, numsamples;
+extern double torigin;
+void force_end_of_block(void);                         /* readtape.c:1378 */
+void process_up_transition(struct trkstate_t *t);      /* decoder.c:574 */
+void process_down_transition(struct trkstate_t *t);    /* decoder.c:592 */
+
+/* ---- state ------------------------------------------------------------------------------------- */
+static struct {
+   int opened;
+   rt_tape *tape;
+   rt_tape_desc desc;
+   long long base_pos;              /* file offset of row 0 */
+   uint64_t nrows;                  /* rows before the end marker */
+   int16_t *rows; size_t rows_bytes;/* pinned copy of the payload */
+   /* the pending reset, noted by the wrapped reset functions */
+   int pending_reset;               /* RT_RESET_*; RT_RESET_NONE if none since the last readblock() */
+   /* stateful exact context (Whirlwind, and the fallback for everything else) */
+   rt_scan *ctx; rt_scan_cfg ctx_cfg; int ctx_valid;
+   /* speculative whole-tape scans, one per parameter set on demand */
+   struct { rt_bulk *bulk; rt_scan_cfg cfg; int valid; } bulk[MAXPARMSETS];
+   int use_bulk;
+   /* statistics */
+   long long n_bulk_hits, n_bulk_miss, n_exact_spans, n_events, n_restarts;
+   int said_config;
+} S;
+
+#define EXACT_SPAN_ROWS  (1u << 17)
+
+static void rtfatal(const char *what, int rc) {
+   fatal("B200 scan: %s failed (%d): %s", what, rc, rt_last_error()); }
+
+static double rowtime(uint64_t row) {                  /* readtape.c:1423 */
+   return (double)(int64_t)(S.desc.tstart_ns + row * S.desc.tdelta_ns) / 1e9; }
+
+/* ---- resets: remember what the host did before calling readblock() ------------------------------- */
+void __real_init_trackstate(void);
+void __wrap_init_trackstate(void) { __real_init_trackstate(); S.pending_reset = RT_RESET_FULL; }
+void __real_ww_init_blockstate(void);
+void __wrap_ww_init_blockstate(void) {
+   __real_ww_init_blockstate();
+   if (S.pending_reset != RT_RESET_FULL && S.pending_reset != RT_RESET_PEAKSTATE) S.pending_reset = RT_RESET_WW_PARTIAL;
+   else S.pending_reset |= 0x100; /* a partial reset stacked on a pending full/peakstate one */ }
+void __real_init_trackpeak_state(void);
+void __wrap_init_trackpeak_state(void) { __real_init_trackpeak_state(); S.pending_reset = RT_RESET_PEAKSTATE; }
+void __real_compute_avg_height(struct trkstate_t *t);
+void __wrap_compute_avg_height(struct trkstate_t *t) {
+   __real_compute_avg_height(t);
+   if (S.ctx) { int rc = rt_scan_set_avg_height(S.ctx, (uint32_t)t->trknum, t->v_avg_height); if (rc) rtfatal("rt_scan_set_avg_height", rc); } }
+
+/* ---- configuration ------------------------------------------------------------------------------ */
+static void make_cfg(rt_scan_cfg *c) {
+   memset(c, 0, sizeof *c);
+   c->mode = (int32_t)mode;
+   c->flags = (find_zeros ? RT_F_FIND_ZEROS : 0) | (do_differentiate ? RT_F_DIFFERENTIATE : 0) | (invert_data ? RT_F_INVERT : 0)
+              | (doing_density_detection ? RT_F_DENSITY_DETECT : 0) | (doing_deskew ? RT_F_DESKEWING : 0);
+   c->bpi = bpi; c->ips = ips;
+   c->parms.clk_window = PARM.clk_window; c->parms.clk_alpha = PARM.clk_alpha;
+   c->parms.agc_window = PARM.agc_window; c->parms.agc_alpha = PARM.agc_alpha;
+   c->parms.min_peak = PARM.min_peak; c->parms.clk_factor = PARM.clk_factor; c->parms.pulse_adj = PARM.pulse_adj;
+   c->parms.pkww_bitfrac = PARM.pkww_bitfrac; c->parms.pkww_rise = PARM.pkww_rise;
+   c->parms.z1pt = PARM.z1pt; c->parms.z2pt = PARM.z2pt;
+   for (int k = 0; k < MAXTRKS; ++k) c->skew_delaycnt[k] = skew_delaycnt[k]; }
+
+static void open_tape(void) {
+   assert(tbin_file, "the B200 scan reads .tbin captures only (convert CSV with csvtbin first)");
+   assert(subsample == 1, "the B200 scan does not support -subsample");
+   assert(sizeof(int16_t) == 2 && nheads >= ntrks && nheads <= MAXTRKS, "bad head count %d", nheads);
+   memset(&S.desc, 0, sizeof S.desc);
+   S.desc.ntrks = (uint32_t)ntrks; S.desc.nheads = (uint32_t)nheads;
+   for (int h = 0; h < MAXTRKS; ++h) S.desc.head_to_trk[h] = h < nheads ? head_to_trk[h] : RT_HEAD_IGNORE;
+   S.desc.maxvolts = tbin_hdr.u.s.maxvolts;
+   S.desc.tdelta_ns = (uint64_t)sample_deltat_ns;
+   S.desc.tstart_ns = (uint64_t)timenow_ns;              /* time of the row at the current file position */
+   S.base_pos = ftello(inf);
+   assert(S.base_pos >= 0, "ftell failed");
+   assert(fseeko(inf, 0, SEEK_END) == 0, "fseek failed");
+   long long end = ftello(inf);
+   assert(fseeko(inf, S.base_pos, SEEK_SET) == 0, "fseek failed");
+   uint64_t rowbytes = (uint64_t)nheads * 2;
+   uint64_t nrows_file = (uint64_t)(end - S.base_pos) / rowbytes;
+   int rc = rt_open(&S.desc, getenv("RT_DEVICE") ? atoi(getenv("RT_DEVICE")) : 0, &S.tape);
+   if (rc) rtfatal("rt_open", rc);
+   S.rows_bytes = (size_t)(nrows_file * rowbytes);
+   S.rows = rt_host_alloc(S.rows_bytes + 16);
+   assert(S.rows != NULLP, "cannot allocate %lld bytes of pinned memory", (long long)S.rows_bytes);
+   assert(fread(S.rows, 1, S.rows_bytes, inf) == S.rows_bytes, "cannot read the .tbin payload");
+   assert(fseeko(inf, S.base_pos, SEEK_SET) == 0, "fseek failed");
+   rc = rt_upload(S.tape, S.rows, nrows_file);
+   if (rc) rtfatal("rt_upload", rc);
+   S.nrows = rt_nrows(S.tape);
+   S.use_bulk = !(getenv("RT_NO_BULK") && atoi(getenv("RT_NO_BULK")));
+   S.opened = 1;
+   if (!quiet) rlog("  B200 scan: %s rows x %d heads resident on the GPU (%s)\n", longlongcommas((long long)S.nrows), nheads, rt_backend()); }
+
+/* ---- event sources ------------------------------------------------------------------------------ */
+struct evsrc {
+   const rt_event *ev; uint64_t n, at;      /* current batch */
+   uint64_t valid_end;                      /* rows < valid_end are covered by what we hold */
+   int exact;                               /* 1: S.ctx is running and can be continued */
+};
+
+static void ctx_prepare(const rt_scan_cfg *cfg) {
+   int rc;
+   if (!S.ctx) {
+      rc = rt_scan_begin(S.tape, cfg, &S.ctx); if (rc) rtfatal("rt_scan_begin", rc);
+      S.ctx_cfg = *cfg; }
+   else if (memcmp(&S.ctx_cfg, cfg, sizeof *cfg) != 0) {
+      rc = rt_scan_set_cfg(S.ctx, cfg); if (rc) rtfatal("rt_scan_set_cfg", rc);
+      S.ctx_cfg = *cfg; } }
+
+static void exact_more(struct evsrc *src) {  /* continue the exact scan by one span */
+   uint64_t done = 0;
+   int rc = rt_scan_run(S.ctx, EXACT_SPAN_ROWS, &src->ev, &src->n, &done);
+   if (rc) rtfatal("rt_scan_run", rc);
+   src->at = 0; src->valid_end = rt_scan_pos(S.ctx); ++S.n_exact_spans;
+   if (done == 0) src->valid_end = UINT64_MAX; /* end of tape: nothing more will ever come */ }
+
+static void exact_start(struct evsrc *src, const rt_scan_cfg *cfg, int reset_kind, uint64_t row) {
+   ctx_prepare(cfg);
+   int kind = reset_kind & 0xff;
+   int rc = rt_scan_reset(S.ctx, kind, row); if (rc) rtfatal("rt_scan_reset", rc);
+   if (reset_kind & 0x100) { rc = rt_scan_reset(S.ctx, RT_RESET_WW_PARTIAL, row); if (rc) rtfatal("rt_scan_reset", rc); }
+   memset(src, 0, sizeof *src); src->exact = 1;
+   exact_more(src); }
+
+static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
+   int ps = block.parmset;
+   if (!S.use_bulk || mode == WW || doing_density_detection || doing_deskew) return 0;   /* prefix passes: exact scan */
+   if (S.bulk[ps].valid && memcmp(&S.bulk[ps].cfg, cfg, sizeof *cfg) != 0) {    /* e.g. the skew changed after the pre-pass */
+      rt_bulk_free(S.bulk[ps].bulk); S.bulk[ps].valid = 0; }
+   if (!S.bulk[ps].valid) {
+      int rc = rt_bulk_scan(S.tape, cfg, 1, &S.bulk[ps].bulk);
+      if (rc == RT_ERR_UNSUPPORTED) { S.use_bulk = 0; return 0; }
+      if (rc) rtfatal("rt_bulk_scan", rc);
+      S.bulk[ps].cfg = *cfg; S.bulk[ps].valid = 1; }
+   uint64_t valid = 0;
+   memset(src, 0, sizeof *src);
+   int rc = rt_bulk_lookup(S.bulk[ps].bulk, 0, row, &src->ev, &src->n, &valid);
+   if (rc == RT_MISS) { ++S.n_bulk_miss; return 0; }
+   if (rc) rtfatal("rt_bulk_lookup", rc);
+   src->valid_end = row + valid;
+   if (src->valid_end >= S.nrows) src->valid_end = UINT64_MAX;
+   ++S.n_bulk_hits;
+   return 1; }
+
+/* the next event, or NULL if none is known below row `limit` (then rows < limit hold no event) */
+static const rt_event *peek_event(struct evsrc *src, uint64_t limit, int *need_restart) {
+   for (;;) {
+      if (src->at < src->n) return src->ev[src->at].row < limit ? &src->ev[src->at] : NULLP;
+      if (src->valid_end == UINT64_MAX || src->valid_end >= limit) return NULLP;
+      if (src->exact) exact_more(src);
+      else { *need_restart = 1; return NULLP; } } }
+
+/* ---- exact "first row at which process_sample() sees the condition" searches ----------------------- */
+/* smallest row r >= lo with  rowtime(r) > x  (monotone in r) */
+static uint64_t first_row_time_gt(double x, uint64_t lo) {
+   if (!(x == x) || lo >= S.nrows) return UINT64_MAX;                        /* NaN, or past the end */
+   double est = (x * 1e9 - (double)S.desc.tstart_ns) / (double)S.desc.tdelta_ns;
+   if (est >= (double)S.nrows + 4) return UINT64_MAX;                         /* never before the end marker */
+   uint64_t r = est <= (double)lo ? lo : (uint64_t)est;
+   if (r > lo + 2) r -= 2; else r = lo;
+   while (r > lo && rowtime(r - 1) > x) --r;
+   while (r < S.nrows && !(rowtime(r) > x)) ++r;
+   return r < S.nrows ? r : UINT64_MAX; }
+/* smallest row r >= lo with  rowtime(r) - t0 > thr   (the subtraction is done in double, as in the reference) */
+static uint64_t first_row_delta_gt(double t0, double thr, uint64_t lo) {
+   if (lo >= S.nrows) return UINT64_MAX;
+   uint64_t r = first_row_time_gt(t0 + thr, lo);
+   if (r == UINT64_MAX) r = S.nrows - 1;
+   if (r > lo + 2) r -= 2; else r = lo;
+   while (r > lo && rowtime(r - 1) - t0 > thr) --r;
+   while (r < S.nrows && !(rowtime(r) - t0 > thr)) ++r;
+   return r < S.nrows ? r : UINT64_MAX; }
+
+/* ---- the block decode ------------------------------------------------------------------------------ */
+struct rowstate { uint64_t init_row[MAXTRKS]; };
+
+static void say_configuration(void) {
+   if (quiet || S.said_config) return;
+   S.said_config = 1;
+   rlog("\nexecution-time configuration:\n");
+   rlog("  %d track %s encoding, %s parity, %d BPI at %d IPS", ntrks, modename(),
+        mode == WW ? "no" : expected_parity ? "odd" : "even", (int)bpi, (int)ips);
+   if (bpi != 0) rlog(" (%.2f usec/bit)", 1e6f / (bpi * ips));
+   rlog("\n  first sample is at time %.8lf seconds on the tape\n", timenow);
+   rlog("  sampling rate is %s Hz (%.2f usec)", intcommas((int)(1.0 / sample_deltat)), sample_deltat * 1e6);
+   if (bpi != 0) rlog(", or about %d samples per bit", (int)(1 / (bpi * ips * sample_deltat)));
+   rlog("\n");
+   if (find_zeros) rlog("  will look for zero crossings, not peaks\n");
+   else rlog("  peak detection window width is %d samples (%.2f usec)\n", pkww_width, pkww_width * sample_deltat * 1e6);
+   rlog("  per-sample scan: %s through the rt_scan C-ABI\n\n", rt_backend()); }
+
+/* returns the last row consumed (the row after which the reference's readblock() returns); *endfile set at EOF */
+static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, struct evsrc *src, uint64_t *last_row, bool *endfile) {
+   struct rowstate rs;
+   int need_restart = 0;
+   const uint64_t nrows = S.nrows;
+   const int tz = rowtime(row0) == 0.0;
+   /* (Q2) decoder.c:855-861: after a reset the tracks initialise one per row */
+   for (int k = 0; k < ntrks; ++k) rs.init_row[k] = UINT64_MAX;
+   if ((reset_kind & 0xff) == RT_RESET_FULL || (reset_kind & 0xff) == RT_RESET_WW_PARTIAL || (reset_kind & 0x100))
+      for (int k = 0; k < ntrks; ++k) rs.init_row[k] = row0 + (uint64_t)k + (tz ? 1u : 0u);
+   else for (int k = 0; k < ntrks; ++k) if (trkstate[k].t_lastpeak == 0) rs.init_row[k] = row0 + (uint64_t)k;   /* defensive */
+
+   uint64_t row = row0;                 /* next row to be "processed" */
+   uint64_t pe_idle_row[MAXTRKS], gcr_idle_row[MAXTRKS];
+   for (int k = 0; k < ntrks; ++k) pe_idle_row[k] = gcr_idle_row[k] = UINT64_MAX;
+   uint64_t zerocheck_row = UINT64_MAX, ww_stop_row = UINT64_MAX;
+   int dirty = 1;                       /* timers must be recomputed */
+   *endfile = false;
+
+   for (;;) {
+      /* ---- timers: the first row >= `row` at which each per-row condition of process_sample() holds ---- */
+      if (dirty) {
+         zerocheck_row = ww_stop_row = UINT64_MAX;
+         if (mode == NRZI && nrzi.datablock)
+            zerocheck_row = first_row_time_gt(nrzi.t_lastclock + 2 * nrzi.clkavg.t_bitspaceavg, row);
+         for (int k = 0; k < ntrks; ++k) {
+            struct trkstate_t *t = &trkstate[k];
+            pe_idle_row[k] = gcr_idle_row[k] = UINT64_MAX;
+            uint64_t lo = row;
+            if (rs.init_row[k] != UINT64_MAX && rs.init_row[k] + 1 > lo) lo = rs.init_row[k] + 1;   /* not looked at before that */
+            if (rs.init_row[k] != UINT64_MAX) continue;             /* t_lastpeak == 0: the reference does not look at it yet */
+            if (mode == PE && !t->idle && t->t_lastpeak != 0)
+               pe_idle_row[k] = first_row_delta_gt(t->t_lastpeak, t->clkavg.t_bitspaceavg * PE_IDLE_FACTOR, lo);
+            if (mode == GCR && t->datablock)
+               gcr_idle_row[k] = first_row_time_gt(t->t_lastpeak + GCR_IDLE_THRESH * t->clkavg.t_bitspaceavg, lo); }
+         if (mode == WW && ww.datablock && ww.t_lastclkpulseend > 0)
+            ww_stop_row = first_row_delta_gt(ww.t_lastclkpulseend, ww.clkavg.t_bitspaceavg * WW_CLKSTOP_BITS, row);
+         dirty = 0; }
+
+      /* ---- the next row at which anything happens ---- */
+      uint64_t next = nrows;               /* the end marker */
+      if (zerocheck_row < next) next = zerocheck_row;
+      if (ww_stop_row < next) next = ww_stop_row;
+      for (int k = 0; k < ntrks; ++k) {
+         if (rs.init_row[k] != UINT64_MAX && rs.init_row[k] >= row && rs.init_row[k] < next) next = rs.init_row[k];
+         if (pe_idle_row[k] < next) next = pe_idle_row[k];
+         if (gcr_idle_row[k] < next) next = gcr_idle_row[k]; }
+      const rt_event *e = peek_event(src, next + 1, &need_restart);
+      if (need_restart) return 1;
+      if (e && e->row < next) next = e->row;
+      if (next >= nrows) {                /* readtape.c:1410-1413: the end marker */
+         timenow = nrows ? rowtime(nrows - 1) : timenow;
+         if (nrows > row0) force_end_of_block();
+         *endfile = true;
+         *last_row = nrows;               /* file position: at the marker */
+         return 0; }
+
+      /* ---- process row `next` in the order process_sample() does ---- */
+      row = next;
+      timenow = rowtime(row);
+      if (mode == NRZI && nrzi.datablock && zerocheck_row == row) { nrzi_zerocheck(); dirty = 1; }
+      int stop_tracks = 0;
+      for (int k = 0; k < ntrks && !stop_tracks; ++k) {
+         struct trkstate_t *t = &trkstate[k];
+         if (rs.init_row[k] != UINT64_MAX) {
+            if (row < rs.init_row[k]) break;                       /* the reference's `break`: later tracks are not reached either */
+            if (row == rs.init_row[k]) {                           /* decoder.c:855-861 */
+               t->t_lastpeak = timenow;
+               rs.init_row[k] = UINT64_MAX;
+               dirty = 1;
+               break; } }
+         e = peek_event(src, row + 1, &need_restart);
+         if (need_restart) return 1;
+         if (e && e->row == row && e->trk == k) {
+            ++src->at; ++S.n_events;
+            t->v_top = e->v_top; t->v_bot = e->v_bot;
+            if (e->kind == RT_EV_TOP) { t->t_top = e->t_event; process_up_transition(t); }
+            else { t->t_bot = e->t_event; process_down_transition(t); }
+            if (t->agc_gain != e->agc_gain)
+               fatal("B200 scan diverged from the host on track %d at row %llu: AGC %.9g (scan) vs %.9g (host)",
+                     k, (unsigned long long)row, e->agc_gain, t->agc_gain);
+            dirty = 1; }
+         else if (e && e->row == row && e->trk < k)
+            fatal("B200 scan: event order violated at row %llu", (unsigned long long)row);
+         if (mode == PE && !t->idle && t->t_lastpeak != 0 && timenow - t->t_lastpeak > t->clkavg.t_bitspaceavg * PE_IDLE_FACTOR) {
+            t->v_lastpeak = t->v_now;                              /* decoder.c:868-877 */
+            t->idle = true;
+            dirty = 1;
+            if (++num_trks_idle >= ntrks) pe_end_of_block(); }
+         if (mode == GCR && t->datablock && timenow > t->t_lastpeak + GCR_IDLE_THRESH * t->clkavg.t_bitspaceavg) {
+            t->datablock = false;                                  /* decoder.c:879-888 */
+            t->idle = true;
+            dirty = 1;
+            if (++num_trks_idle >= ntrks) { gcr_end_of_block(); stop_tracks = 1; } } }
+      if (!stop_tracks && mode == WW && ww.datablock && ww.t_lastclkpulseend > 0
+            && timenow - ww.t_lastclkpulseend > ww.clkavg.t_bitspaceavg * WW_CLKSTOP_BITS) {
+         ww_end_of_block(); dirty = 1; }
+      /* events of this row on tracks the reference did not reach (its `break` / `goto exit`) are dropped */
+      for (;;) {
+         e = peek_event(src, row + 1, &need_restart);
+         if (need_restart) return 1;
+         if (!e || e->row != row) break;
+         ++src->at; }
+
+      /* ---- exit logic, decoder.c:900-904 ---- */
+      if (interblock_counter) {
+         /* rows row .. row+interblock_counter-1 are swallowed; the block is returned after the last of them */
+         uint64_t ret = row + (uint64_t)interblock_counter - 1;
+         if (ret >= nrows) {               /* the end marker comes first */
+            timenow = rowtime(nrows - 1);
+            force_end_of_block();
+            *endfile = true; *last_row = nrows;
+            return 0; }
+         interblock_counter = 0;
+         timenow = rowtime(ret);
+         *last_row = ret + 1;
+         return 0; }
+      if (block.results[block.parmset].blktype != BS_NONE) { *last_row = row + 1; return 0; }
+      ++row; } }
+
+bool readblock(bool retry) {
+   if (!S.opened) open_tape();
+   long long pos = ftello(inf);
+   assert(pos >= S.base_pos && (pos - S.base_pos) % (nheads * 2) == 0, "B200 scan: unexpected file position %lld", pos);
+   uint64_t row0 = (uint64_t)(pos - S.base_pos) / (uint64_t)(nheads * 2);
+   int reset_kind = S.pending_reset; S.pending_reset = RT_RESET_NONE;
+   samples_per_bit = bpi > 0 ? (int)(1 / (bpi * ips * sample_deltat)) : 20;     /* readtape.c:1402 */
+   rt_scan_cfg cfg; make_cfg(&cfg);
+   if (!block.window_set) {                                                   /* readtape.c:1453-1501 */
+      pkww_width = rt_pkww_width(&cfg, (uint64_t)sample_deltat_ns);
+      if (row0 < S.nrows) timenow = rowtime(row0);
+      if (torigin == 0) torigin = timenow;
+      say_configuration();
+      block.window_set = true; }
+
+   struct evsrc src;
+   uint64_t last_row = row0; bool endfile = false;
+   int persistent = mode == WW || reset_kind != RT_RESET_FULL;   /* Whirlwind: the scan state carries over from block to block */
+   int from_bulk = !persistent && bulk_start(&src, &cfg, row0);
+   if (!from_bulk) exact_start(&src, &cfg, reset_kind, row0);
+   if (decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile)) {
+      /* the speculative unit ended before the block did: start over with the exact scan */
+      assert(from_bulk, "B200 scan: exact scan asked for a restart");
+      ++S.n_restarts;
+      interblock_counter = 0;
+      init_trackstate();                                           /* the reference's own reset, again */
+      S.pending_reset = RT_RESET_NONE;
+      block.window_set = true;
+      exact_start(&src, &cfg, RT_RESET_FULL, row0);
+      assert(!decode_from(row0, RT_RESET_FULL, &cfg, &src, &last_row, &endfile), "B200 scan: restart failed"); }
+   if (src.exact && persistent && !endfile) {   /* Whirlwind continues from here: leave the scan state exactly where the host stopped */
+      int rc = rt_scan_rewind(S.ctx, last_row); if (rc) rtfatal("rt_scan_rewind", rc); }
+
+   /* bookkeeping the reference's loop does per row (readtape.c:1404,1424,1449-1451) */
+   uint64_t consumed = last_row - row0;
+   numsamples += (long long)consumed;
+   if (!retry) lines_in += (long long)consumed + (endfile ? 1 : 0);
+   timenow_ns = (int64_t)(S.desc.tstart_ns + last_row * S.desc.tdelta_ns);
+   assert(fseeko(inf, S.base_pos + (long long)last_row * nheads * 2 + (endfile ? 2 : 0), SEEK_SET) == 0, "fseek failed");
+
+   struct results_t *result = &block.results[block.parmset];                 /* readtape.c:1509-1515 */
+   result->errcount = result->track_mismatch + result->vparity_errs + result->ecc_errs + result->crc_errs + result->lrc_errs
+                      + result->gcr_bad_sequence + result->ww_bad_length + result->ww_speed_err;
+   result->warncount = result->missed_midbits + result->corrected_bits + result->gcr_bad_dgroups
+                       + result->ww_leading_clock + result->ww_missing_onebit + result->ww_missing_clock;
+   if (endfile && !quiet && getenv("RT_STATS"))
+      rlog("  B200 scan: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n",
+           S.n_events, S.n_bulk_hits, S.n_bulk_miss, S.n_restarts, S.n_exact_spans);
+   return !endfile; }
