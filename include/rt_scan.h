@@ -203,10 +203,13 @@ typedef struct rt_unit_info {
    uint32_t ntrks, pad;
    uint64_t first_event_row[RT_MAXTRKS], sync_row[RT_MAXTRKS], last_loud_row[RT_MAXTRKS], need_sync_row[RT_MAXTRKS];
    uint64_t sync_early[RT_MAXTRKS], loud_early[RT_MAXTRKS];
+   uint64_t sync_first[RT_MAXTRKS], quiet_from[RT_MAXTRKS];
    uint32_t nevents[RT_MAXTRKS];
-   uint32_t pad2;
+   uint32_t failed[RT_MAXTRKS];
 } rt_unit_info;
 int  rt_bulk_unit_info(const rt_bulk *bulk, uint32_t cfg_index, uint64_t start_row, rt_unit_info *out);
+/* The same for unit number `unit_index` (0 .. nunits-1), with start_row = its own first row; RT_MISS past the end. */
+int  rt_bulk_unit_at(const rt_bulk *bulk, uint32_t cfg_index, uint64_t unit_index, rt_unit_info *out);
 
 typedef struct rt_bulk_stats {
    uint64_t rows;            /* rows on the tape                                             */

@@ -58,7 +58,8 @@ class UnitInfo(C.Structure):
                 ("first_event_row", C.c_uint64 * RT_MAXTRKS), ("sync_row", C.c_uint64 * RT_MAXTRKS),
                 ("last_loud_row", C.c_uint64 * RT_MAXTRKS), ("need_sync_row", C.c_uint64 * RT_MAXTRKS),
                 ("sync_early", C.c_uint64 * RT_MAXTRKS), ("loud_early", C.c_uint64 * RT_MAXTRKS),
-                ("nevents", C.c_uint32 * RT_MAXTRKS), ("pad2", C.c_uint32)]
+                ("sync_first", C.c_uint64 * RT_MAXTRKS), ("quiet_from", C.c_uint64 * RT_MAXTRKS),
+                ("nevents", C.c_uint32 * RT_MAXTRKS), ("failed", C.c_uint32 * RT_MAXTRKS)]
 
 
 EVENT_DTYPE = np.dtype([("row", "<u8"), ("t_event", "<f8"), ("v_top", "<f4"), ("v_bot", "<f4"),
@@ -68,7 +69,7 @@ assert EVENT_DTYPE.itemsize == 32
 EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_attach_device", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
-           "rt_bulk_scan", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
+           "rt_bulk_scan", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
            "rt_row_time"]
 
 
@@ -114,12 +115,13 @@ class Lib:
         L.rt_bulk_lookup.argtypes = [vp, u32, u64, P(vp), P(u64), P(u64)]
         L.rt_bulk_get_stats.argtypes = [vp, P(BulkStats)]
         L.rt_bulk_unit_info.argtypes = [vp, u32, u64, P(UnitInfo)]
+        L.rt_bulk_unit_at.argtypes = [vp, u32, u64, P(UnitInfo)]
         L.rt_bulk_free.argtypes = [vp]; L.rt_bulk_free.restype = None
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
         L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
         for fn in ("rt_open", "rt_upload", "rt_attach_device", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
                    "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_lookup",
-                   "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_pkww_width"):
+                   "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_pkww_width"):
             getattr(L, fn).restype = i32
 
     @property
@@ -231,15 +233,27 @@ class Bulk:
     def fetch(self) -> None:
         self.lib.check(self.lib.L.rt_bulk_fetch(self.h))
 
-    def unit_info(self, cfg_index: int, start_row: int) -> dict:
-        ui = UnitInfo()
-        self.lib.check(self.lib.L.rt_bulk_unit_info(self.h, cfg_index, start_row, C.byref(ui)))
+    @staticmethod
+    def _unit_dict(ui: UnitInfo) -> dict:
         n = ui.ntrks
         none = (1 << 64) - 1
         f = lambda a: [None if a[i] == none else int(a[i]) for i in range(n)]
         return {"unit_index": int(ui.unit_index), "nunits": int(ui.nunits), "row0": int(ui.row0), "row_end": int(ui.row_end),
                 "first_event_row": f(ui.first_event_row), "sync_row": f(ui.sync_row), "last_loud_row": f(ui.last_loud_row),
-                "need_sync_row": f(ui.need_sync_row), "sync_early": f(ui.sync_early), "loud_early": f(ui.loud_early), "nevents": [int(ui.nevents[i]) for i in range(n)]}
+                "need_sync_row": f(ui.need_sync_row), "sync_early": f(ui.sync_early), "loud_early": f(ui.loud_early),
+                "sync_first": f(ui.sync_first), "quiet_from": f(ui.quiet_from),
+                "nevents": [int(ui.nevents[i]) for i in range(n)], "failed": [int(ui.failed[i]) for i in range(n)]}
+
+    def unit_info(self, cfg_index: int, start_row: int) -> dict:
+        ui = UnitInfo()
+        self.lib.check(self.lib.L.rt_bulk_unit_info(self.h, cfg_index, start_row, C.byref(ui)))
+        return self._unit_dict(ui)
+
+    def unit_at(self, cfg_index: int, unit_index: int):
+        """proof data of unit number `unit_index`, or None past the last unit"""
+        ui = UnitInfo()
+        rc = self.lib.check(self.lib.L.rt_bulk_unit_at(self.h, cfg_index, unit_index, C.byref(ui)))
+        return None if rc == RT_MISS else self._unit_dict(ui)
 
     def stats(self) -> BulkStats:
         st = BulkStats()

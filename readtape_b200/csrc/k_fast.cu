@@ -1,0 +1,87 @@
+/* readtape_b200/csrc/k_fast.cu -- K3b: the speculative whole-tape scan, int16 fast path (scan_fast.cuh).
+ *
+ * One thread per (unit, track), grid-stride over the unit table; every thread owns a lane-private
+ * scratch area in shared memory laid out [entry][thread] so that every access of a warp hits 32
+ * different banks whatever the lanes' ring positions are.  The 32 lanes of a warp are kept converged by
+ * warp votes (rtfast::drive): search together, handle candidate rows together, change blocks together.
+ * Same outputs as k_units_scan (k_scan.cu): events into the chunk pool, TrkMeta with the
+ * unit-equivalence proof data.
+ */
+#include "scan_fast.cuh"
+#include "kernels.h"
+#include "emit.cuh"
+
+#define FAST_THREADS 128
+
+using namespace rtfast;
+
+struct DevJobs {
+   const DevCfg &c; const UnitDesc *units; TrkMeta *meta; rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
+   int quiet_thr_lsb; unsigned long long *rows_scanned; uint64_t f, total, stride; uint64_t cur;
+   template <class Scan>
+   __device__ bool next(Scan &us) {
+      for (;;) {
+         if (f >= total) return false;
+         cur = f; f += stride;
+         const uint32_t u = (uint32_t)(cur / c.ntrks); const int trk = (int)(cur % c.ntrks);
+         const UnitDesc ud = units[u];
+         if (ud.row_end - ud.row0 > (1ull << 30)) {         /* offsets are 32-bit: leave such a unit to the exact scan */
+            TrkMeta m;
+            m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
+            m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
+            meta[cur] = m;
+            continue; }
+         PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+         us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
+         return true; } }
+   template <class Scan>
+   __device__ void done(Scan &us) {
+      TrkMeta m; us.finish(m); meta[cur] = m;
+      atomicAdd(&rows_scanned[0], (unsigned long long)us.end);
+      if (us.em.n) atomicAdd(&rows_scanned[1], (unsigned long long)us.em.n); } };
+
+struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p) != 0; } };
+
+__global__ void __launch_bounds__(FAST_THREADS, 6)
+k_units_fast(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta *meta,
+             rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
+             int quiet_thr_lsb, unsigned long long *rows_scanned, uint32_t ring) {
+   extern __shared__ __align__(16) uint32_t fast_smem[];
+   /* [entry][thread] layout; the 8-byte PH pairs come first: the lane's pair k sits at byte (k*FAST_THREADS + tid)*8 */
+   LaneMem<FAST_THREADS> mem;
+   mem.ph = reinterpret_cast<pair32 *>(fast_smem) + threadIdx.x;
+   mem.x = fast_smem + (size_t)2 * (c.width + 1) * FAST_THREADS + threadIdx.x;
+   mem.ht = mem.x + (size_t)ring * FAST_THREADS; mem.mask = ring - 1;
+   const uint64_t total = (uint64_t)(*nunits_p) * (uint64_t)c.ntrks;
+   DevJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned,
+                (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, total, (uint64_t)gridDim.x * blockDim.x, 0};
+   UnitScan<FAST_THREADS, PoolEmit> us(c, mem);
+   drive(us, jobs, WarpAny()); }
+
+bool fast_scan_eligible(const DevCfg &c) {
+   return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
+          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH; }
+
+cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, uint32_t nunits_host, TrkMeta *meta, rt_event *pool,
+                              uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
+                              unsigned long long *rows_scanned, int sms, cudaStream_t s) {
+   const uint32_t ring = ring_size(c.width);
+   const size_t smem = (size_t)scratch_words(c.width) * FAST_THREADS * sizeof(uint32_t);
+   static size_t cfg_smem = 0; static int cfg_per_sm = 0;          /* function attributes: set once per shared-memory size */
+   cudaError_t e;
+   if (cfg_smem != smem) {
+      e = cudaFuncSetAttribute(k_units_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(k_units_fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm, k_units_fast, FAST_THREADS, smem);
+      if (e != cudaSuccess) return e;
+      cfg_smem = smem; }
+   int per_sm = cfg_per_sm < 1 ? 1 : cfg_per_sm;
+   const uint64_t threads = (uint64_t)nunits_host * (uint64_t)c.ntrks;
+   uint64_t grid = (threads + FAST_THREADS - 1) / FAST_THREADS;
+   const uint64_t resident = (uint64_t)sms * (uint64_t)per_sm;
+   if (grid > resident) grid = resident;
+   if (grid < 1) grid = 1;
+   k_units_fast<<<(unsigned)grid, FAST_THREADS, smem, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned, ring);
+   return cudaGetLastError(); }

@@ -9,39 +9,9 @@
  */
 #include "scan_generic.cuh"
 #include "kernels.h"
+#include "emit.cuh"
 
 using namespace rtgen;
-
-/* ---- emitters -------------------------------------------------------------------------------- */
-struct FlatEmit {                 /* per-track flat buffer; counts past capacity so the host can regrow */
-   rt_event *buf; uint32_t cap; uint32_t n; uint8_t trk;
-   __device__ void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
-      if (n < cap) {
-         rt_event e;
-         e.row = row; e.t_event = t_ev; e.v_top = v_top; e.v_bot = v_bot; e.agc_gain = agc;
-         e.trk = trk; e.kind = top ? RT_EV_TOP : RT_EV_BOT; e.pad[0] = e.pad[1] = 0;
-         buf[n] = e; }
-      ++n; } };
-
-struct PoolEmit {                 /* chained fixed-size chunks from a global pool */
-   rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
-   uint32_t first_chunk, cur_chunk, n; uint64_t first_row; uint8_t trk;
-   __device__ void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
-      if (n == 0) first_row = row;
-      uint32_t slot = n % RT_EVC;
-      if (slot == 0) {
-         uint32_t c = atomicAdd(cursor, 1u);          /* counts past capacity: the host regrows and reruns */
-         if (c < cap_chunks) {
-            chunk_next[c] = RT_NOCHUNK;
-            if (n == 0) first_chunk = c; else if (cur_chunk != RT_NOCHUNK) chunk_next[cur_chunk] = c;
-            cur_chunk = c; }
-         else cur_chunk = RT_NOCHUNK; }
-      if (cur_chunk != RT_NOCHUNK) {
-         rt_event e;
-         e.row = row; e.t_event = t_ev; e.v_top = v_top; e.v_bot = v_bot; e.agc_gain = agc;
-         e.trk = trk; e.kind = top ? RT_EV_TOP : RT_EV_BOT; e.pad[0] = e.pad[1] = 0;
-         pool[(size_t)cur_chunk * RT_EVC + slot] = e; }
-      ++n; } };
 
 /* ---- stateful context ---------------------------------------------------------------------- */
 __global__ void k_ctx_reset(DevCfg c, TrkState *st, SkewState *sk, int kind, uint64_t row, int time_is_zero) {
@@ -77,7 +47,7 @@ __global__ void k_ctx_scan(DevCfg c, TrkState *st, SkewState *sk, uint64_t row_f
 __global__ void __launch_bounds__(128)
 k_units_scan(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta *meta,
              rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
-             float quiet_thr, unsigned long long *rows_scanned) {
+             float quiet_thr, int quiet_thr_lsb, unsigned long long *rows_scanned) {
    const uint32_t nunits = *nunits_p;
    const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (uint64_t)gridDim.x * blockDim.x) {
@@ -95,7 +65,7 @@ k_units_scan(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta 
          canonical = a pure function of the samples: for the peak detector the running maximum has just
          left a FULL window (both scans rescan there, which also refreshes the lazily kept minimum);
          for the zero-crossing detectors any row once v_prev and the deskew FIFO are warm. */
-      QuietTracker qt; qt.init(c, trk, quiet_thr);
+      QuietTracker qt; qt.init(c, trk, quiet_thr, quiet_thr_lsb);
       const uint64_t pre0 = ud.row0 > RT_PRESCAN_ROWS ? ud.row0 - RT_PRESCAN_ROWS : 0;
       for (uint64_t j = pre0; j < ud.row0; ++j) qt.feed(c, plane, j, raw_at(c, plane, j));
       const uint64_t quiet_from = qt.last_loud == RT_NOROW ? pre0 : qt.last_loud + 1;
@@ -132,6 +102,6 @@ void launch_ctx_scan(const DevCfg &c, TrkState *st, SkewState *sk, uint64_t from
       each to get them on different SMs (each is a long serial walk) */
    k_ctx_scan<<<c.ntrks, 1, 0, s>>>(c, st, sk, from, to, ev, cap, counts, failed); }
 void launch_units_scan(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, TrkMeta *meta, rt_event *pool,
-                       uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, float quiet_thr,
+                       uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, float quiet_thr, int quiet_thr_lsb,
                        unsigned long long *rows_scanned, int grid, cudaStream_t s) {
-   k_units_scan<<<grid, 128, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr, rows_scanned); }
+   k_units_scan<<<grid, 128, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr, quiet_thr_lsb, rows_scanned); }

@@ -12,8 +12,10 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <chrono>
 #include "scan_generic.cuh"
 #include "kernels.h"
+#include "cfg_host.h"
 
 using rtgen::SkewState;
 
@@ -33,14 +35,7 @@ extern "C" double rt_row_time(const rt_tape_desc *d, uint64_t row) {
    long long ns = (long long)(d->tstart_ns + row * d->tdelta_ns);
    return (double)ns / 1e9; }
 
-extern "C" int rt_pkww_width(const rt_scan_cfg *cfg, uint64_t tdelta_ns) {
-   /* readtape.c:1453-1457; host code is compiled without FMA contraction (-Xcompiler -ffp-contract=off) */
-   volatile float sample_deltat = (float)(long long)tdelta_ns / 1e9f;
-   if (cfg->bpi == 0 || (cfg->flags & RT_F_DENSITY_DETECT)) return 8;
-   volatile float a = cfg->bpi * cfg->ips;
-   volatile float b = a * sample_deltat;
-   int w = (int)(cfg->parms.pkww_bitfrac / b);
-   return w < RT_PKWW_MAX_WIDTH ? w : RT_PKWW_MAX_WIDTH; }
+extern "C" int rt_pkww_width(const rt_scan_cfg *cfg, uint64_t tdelta_ns) { return rtcfg::pkww_width(cfg, tdelta_ns); }
 
 /* ---- tape ---------------------------------------------------------------------------------------- */
 struct rt_tape {
@@ -117,6 +112,9 @@ extern "C" int rt_open(const rt_tape_desc *desc, int device, rt_tape **out) {
    const char *fs = getenv("RT_INGEST");
    t->force_simple_ingest = fs && strcmp(fs, "simple") == 0;
    CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+   {  /* the bulk scan allocates its scratch and result tables with the stream-ordered allocator: keep freed memory cached */
+      cudaMemPool_t pool; unsigned long long keep = ~0ull;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
    CU(cudaMalloc(&t->d_first_end, sizeof(unsigned long long)));
    unsigned long long none = ~0ull;
    CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
@@ -240,25 +238,7 @@ static int cfg_check(const rt_tape *t, const rt_scan_cfg *cfg) {
    return RT_OK; }
 
 static void cfg_to_dev(const rt_tape *t, const rt_scan_cfg *cfg, DevCfg *d) {
-   memset(d, 0, sizeof *d);
-   d->planes = t->planes; d->plane_stride = t->plane_stride; d->nrows = t->nrows_valid;
-   d->tstart_ns = t->desc.tstart_ns; d->tdelta_ns = t->desc.tdelta_ns; d->maxvolts = t->desc.maxvolts;
-   volatile float sd = (float)(long long)t->desc.tdelta_ns / 1e9f;
-   d->sample_deltat = sd;
-   d->bpi = cfg->bpi; d->ips = cfg->ips;
-   d->density = (cfg->flags & RT_F_DENSITY_DETECT) != 0;
-   volatile float bi = cfg->bpi * cfg->ips;
-   d->clk_init = d->density ? 0.0f : 1 / bi;
-   d->ntrks = (int)t->desc.ntrks; d->mode = cfg->mode;
-   d->find_zeros = (cfg->flags & RT_F_FIND_ZEROS) != 0;
-   d->differentiate = (cfg->flags & RT_F_DIFFERENTIATE) != 0;
-   d->invert = (cfg->flags & RT_F_INVERT) != 0;
-   d->det = d->find_zeros ? (d->differentiate ? RT_DET_DZC : RT_DET_ZC) : RT_DET_PEAK;
-   d->width = rt_pkww_width(cfg, t->desc.tdelta_ns);
-   volatile float bid = bi * sd;
-   d->samples_per_bit = cfg->bpi > 0 ? (int)(1 / bid) : 20;
-   d->p = cfg->parms;
-   for (int k = 0; k < RT_MAXTRKS; ++k) d->skew[k] = cfg->skew_delaycnt[k]; }
+   rtcfg::to_dev(t->desc, t->planes, t->plane_stride, t->nrows_valid, cfg, d); }
 
 /* k-way merge of per-track event streams into (row, trk) order */
 struct Cursor { const rt_event *p, *end; };
@@ -411,7 +391,7 @@ struct BulkCfg {
    /* device-resident results of the scan */
    UnitDesc *d_units = nullptr; TrkMeta *d_meta = nullptr; rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr;
    uint32_t nunits = 0, pool_chunks = 0, chunks_used = 0;
-   bool pool_from_cache = false, pin_from_cache = false;
+   bool pool_from_cache = false, pin_from_cache = false, fast = false;
    /* host copies, filled by rt_bulk_fetch() */
    std::vector<UnitDesc> units; std::vector<TrkMeta> meta; std::vector<uint32_t> chunk_next;
    rt_event *h_pool = nullptr; size_t h_pool_events = 0;      /* pinned */
@@ -432,7 +412,7 @@ extern "C" void rt_bulk_free(rt_bulk *b) {
    for (auto &c : b->cfgs) {
       if (c.pin_from_cache) b->tape->pin_cache_busy = false; else if (c.h_pool) cudaFreeHost(c.h_pool);
       if (c.pool_from_cache) b->tape->pool_cache_busy = false; else { cudaFree(c.d_pool); cudaFree(c.d_chunk_next); }
-      cudaFree(c.d_units); cudaFree(c.d_meta); }
+      if (c.d_units) cudaFreeAsync(c.d_units, b->tape->stream); if (c.d_meta) cudaFreeAsync(c.d_meta, b->tape->stream); }
    delete b; }
 
 extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bulk **out) {
@@ -443,6 +423,13 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       rc = cfg_check(t, &cfgs[i]); if (rc) return rc;
       if (cfgs[i].mode == RT_MODE_WW) return set_err(RT_ERR_UNSUPPORTED, "Whirlwind state persists across blocks: use rt_scan_*");
       if (cfgs[i].flags & RT_F_DENSITY_DETECT) return set_err(RT_ERR_UNSUPPORTED, "density detection is a prefix pass: use rt_scan_*"); }
+   const bool trace = getenv("RT_TRACE") != nullptr;
+   auto wall0 = std::chrono::steady_clock::now();
+   auto lap = [&](const char *what) {
+      if (!trace) return;
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[rt_bulk_scan] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - wall0).count());
+      wall0 = now; };
    rt_bulk *b = new (std::nothrow) rt_bulk();
    if (!b) return set_err(RT_ERR_NOMEM, "rt_bulk_scan: out of memory");
    b->tape = t; b->cfgs.resize(ncfgs);
@@ -455,14 +442,15 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr;
    cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
    auto cleanup = [&]() {
-      cudaFree(d_bitmap); cudaFree(d_flags); cudaFree(d_blockcount); cudaFree(d_nunits); cudaFree(d_units_tmp);
-      cudaFree(d_counters); cudaFree(d_cursor);
+      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor};
+      for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
       for (auto &e : ev) cudaEventDestroy(e); };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); rt_bulk_free(b); \
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
-   CUB(cudaMalloc(&d_bitmap, words * 4)); CUB(cudaMalloc(&d_flags, words * 4)); CUB(cudaMalloc(&d_blockcount, nblocks * 4));
-   CUB(cudaMalloc(&d_nunits, 4)); CUB(cudaMalloc(&d_units_tmp, (size_t)units_cap * sizeof(UnitDesc)));
-   CUB(cudaMalloc(&d_counters, 16)); CUB(cudaMalloc(&d_cursor, 4));
+   CUB(cudaMallocAsync(&d_bitmap, words * 4, t->stream)); CUB(cudaMallocAsync(&d_flags, words * 4, t->stream)); CUB(cudaMallocAsync(&d_blockcount, nblocks * 4, t->stream));
+   CUB(cudaMallocAsync(&d_nunits, 4, t->stream)); CUB(cudaMallocAsync(&d_units_tmp, (size_t)units_cap * sizeof(UnitDesc), t->stream));
+   CUB(cudaMallocAsync(&d_counters, 16, t->stream)); CUB(cudaMallocAsync(&d_cursor, 4, t->stream));
+   lap("scratch alloc");
    b->stats.rows = nrows; b->stats.ms_preprocess = t->ms_ingest;
    for (uint32_t ci = 0; ci < ncfgs; ++ci) {
       BulkCfg &bc = b->cfgs[ci];
@@ -474,6 +462,11 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       UnitParams up{};
       up.det = dc.det;
       float quiet_thr = 0;
+      const int quiet_thr_lsb = rtcfg::quiet_thr_lsb(dc);
+      /* K3b (int16 fast path) for the peak detector of NRZI / PE; RT_SCAN=generic forces the exact generic kernel (tests) */
+      const char *force = getenv("RT_SCAN");
+      const bool use_fast = fast_scan_eligible(dc) && !(force && strcmp(force, "generic") == 0);
+      bc.fast = use_fast;
       if (dc.det == RT_DET_PEAK) {
          quiet_thr = dc.p.pkww_rise * 0.999f;
          if (dc.p.pkww_rise < 1e-3f) quiet_thr = 0;                      /* nothing can be proven quiet: every lookup misses */
@@ -491,13 +484,14 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       uint32_t nunits = 0;
       CUB(cudaMemcpyAsync(&nunits, d_nunits, 4, cudaMemcpyDeviceToHost, t->stream));
       CUB(cudaStreamSynchronize(t->stream));
+      lap("unit finder + sync");
       if (nunits > units_cap) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "unit table overflow (%u > %u)", nunits, units_cap); }
       bc.nunits = nunits;
       float ms_scan = 0;
       if (nunits) {
-         CUB(cudaMalloc(&bc.d_units, (size_t)nunits * sizeof(UnitDesc)));
+         CUB(cudaMallocAsync(&bc.d_units, (size_t)nunits * sizeof(UnitDesc), t->stream));
          CUB(cudaMemcpyAsync(bc.d_units, d_units_tmp, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToDevice, t->stream));
-         CUB(cudaMalloc(&bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta)));
+         CUB(cudaMallocAsync(&bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta), t->stream));
          /* event pool: first guess one event per 16 track-samples, regrown on overflow */
          uint64_t want_chunks = std::max<uint64_t>(4096, nrows * nt / 16 / RT_EVC + (uint64_t)nunits * nt);
          for (int attempt = 0; attempt < 3; ++attempt) {
@@ -520,14 +514,19 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
             CUB(cudaMemsetAsync(d_counters, 0, 16, t->stream));
             CUB(cudaEventRecord(ev[2], t->stream));
             const uint64_t threads = (uint64_t)nunits * nt;
-            int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * 16);
-            launch_units_scan(dc, bc.d_units, d_nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks, quiet_thr, d_counters, grid, t->stream);
-            CUB(cudaGetLastError()); ++t->launches;
+            if (use_fast) CUB(launch_units_fast(dc, bc.d_units, d_nunits, nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks,
+                                                quiet_thr_lsb, d_counters, t->sms, t->stream));
+            else {
+               int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * 16);
+               launch_units_scan(dc, bc.d_units, d_nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks, quiet_thr, quiet_thr_lsb, d_counters, grid, t->stream);
+               CUB(cudaGetLastError()); }
+            ++t->launches;
             CUB(cudaEventRecord(ev[3], t->stream));
             unsigned int used = 0;
             CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
             CUB(cudaStreamSynchronize(t->stream));
             float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_scan = ms;
+            lap("scan kernel + sync");
             if (used <= bc.pool_chunks) { bc.chunks_used = used; break; }
             want_chunks = (uint64_t)used + used / 8 + 1024;
             if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
@@ -537,6 +536,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       float ms_units = 0; cudaEventElapsedTime(&ms_units, ev[0], ev[1]);
       b->stats.ms_units += ms_units; b->stats.ms_scan += ms_scan;
       b->stats.units = nunits; }
+   lap("counters");
    b->stats.track_samples = nrows * nt * ncfgs;
    b->stats.launches = (uint32_t)(t->launches - launches0);
    cleanup();
@@ -574,7 +574,7 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
    CU(cudaStreamSynchronize(t->stream));
    /* the device copies are no longer needed */
    for (BulkCfg &bc : b->cfgs) {
-      cudaFree(bc.d_units); cudaFree(bc.d_meta);
+      if (bc.d_units) cudaFreeAsync(bc.d_units, t->stream); if (bc.d_meta) cudaFreeAsync(bc.d_meta, t->stream);
       if (bc.pool_from_cache) { t->pool_cache_busy = false; bc.pool_from_cache = false; } else { cudaFree(bc.d_pool); cudaFree(bc.d_chunk_next); }
       bc.d_units = nullptr; bc.d_meta = nullptr; bc.d_pool = nullptr; bc.d_chunk_next = nullptr; }
    b->fetched = true;
@@ -584,15 +584,9 @@ extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
    if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");
    *out = b->stats; return RT_OK; }
 
-extern "C" int rt_bulk_unit_info(const rt_bulk *b, uint32_t ci, uint64_t start_row, rt_unit_info *out) {
-   if (!b || ci >= b->cfgs.size() || !out) return set_err(RT_ERR_ARG, "rt_bulk_unit_info: bad argument");
-   if (!b->fetched) { int rc = rt_bulk_fetch(const_cast<rt_bulk *>(b)); if (rc) return rc; }
-   const BulkCfg &bc = b->cfgs[ci];
+static void fill_unit_info(const rt_bulk *b, const BulkCfg &bc, size_t lo, uint64_t start_row, rt_unit_info *out) {
    const uint32_t nt = b->tape->desc.ntrks;
    memset(out, 0, sizeof *out);
-   if (bc.units.empty()) return RT_MISS;
-   size_t lo = 0, hi = bc.units.size();
-   while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (bc.units[mid].row0 <= start_row) lo = mid; else hi = mid; }
    const UnitDesc &u = bc.units[lo];
    out->unit_index = lo; out->nunits = bc.units.size(); out->row0 = u.row0; out->row_end = u.row_end; out->ntrks = nt;
    const bool tz = rt_row_time(&b->tape->desc, start_row) == 0.0;
@@ -600,7 +594,27 @@ extern "C" int rt_bulk_unit_info(const rt_bulk *b, uint32_t ci, uint64_t start_r
       const TrkMeta &m = bc.meta[lo * nt + k];
       out->first_event_row[k] = m.first_event_row; out->sync_row[k] = m.sync_row; out->last_loud_row[k] = m.last_loud_row;
       out->sync_early[k] = m.sync_early; out->loud_early[k] = m.loud_early;
-      out->nevents[k] = m.nevents; out->need_sync_row[k] = start_row + (uint64_t)fill_of(bc.dc, k, tz); }
+      out->sync_first[k] = m.sync_first; out->quiet_from[k] = m.quiet_from; out->failed[k] = m.failed;
+      out->nevents[k] = m.nevents; out->need_sync_row[k] = start_row + (uint64_t)fill_of(bc.dc, k, tz); } }
+
+extern "C" int rt_bulk_unit_info(const rt_bulk *b, uint32_t ci, uint64_t start_row, rt_unit_info *out) {
+   if (!b || ci >= b->cfgs.size() || !out) return set_err(RT_ERR_ARG, "rt_bulk_unit_info: bad argument");
+   if (!b->fetched) { int rc = rt_bulk_fetch(const_cast<rt_bulk *>(b)); if (rc) return rc; }
+   const BulkCfg &bc = b->cfgs[ci];
+   memset(out, 0, sizeof *out);
+   if (bc.units.empty()) return RT_MISS;
+   size_t lo = 0, hi = bc.units.size();
+   while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (bc.units[mid].row0 <= start_row) lo = mid; else hi = mid; }
+   fill_unit_info(b, bc, lo, start_row, out);
+   return RT_OK; }
+
+extern "C" int rt_bulk_unit_at(const rt_bulk *b, uint32_t ci, uint64_t unit_index, rt_unit_info *out) {
+   if (!b || ci >= b->cfgs.size() || !out) return set_err(RT_ERR_ARG, "rt_bulk_unit_at: bad argument");
+   if (!b->fetched) { int rc = rt_bulk_fetch(const_cast<rt_bulk *>(b)); if (rc) return rc; }
+   const BulkCfg &bc = b->cfgs[ci];
+   memset(out, 0, sizeof *out);
+   if (unit_index >= bc.units.size()) return RT_MISS;
+   fill_unit_info(b, bc, (size_t)unit_index, bc.units[unit_index].row0, out);
    return RT_OK; }
 
 /* Can unit `ui` stand in for a fresh RT_RESET_FULL at `start_row`?  (DESIGN.md "unit equivalence") */

@@ -1,0 +1,398 @@
+/* readtape_b200/csrc/scan_fast.cuh -- int16-domain fast path of the moving-window peak detector.
+ *
+ * Same contract as the (unit, track) scan of k_units_scan (k_scan.cu): one thread scans one track of
+ * one unit from a fresh RT_RESET_FULL, produces the identical events and the identical proof data.
+ * It exists because the exact generic code spends ~230 instruction slots per track-sample; this
+ * formulation needs ~25.  NRZI and PE with the peak detector, no -invert / -differentiate; anything
+ * else stays on the generic kernel.  Host + device code: the CPU tests run the very same functions
+ * (tests/host_fast) against the oracle.
+ *
+ * Reference semantics reproduced (file:line in /root/reference/src):
+ *   lookfor_peak   decoder.c:751-810      refine_peak  decoder.c:700-749
+ *   first-sample init / staggered start    decoder.c:855-861      deskew FIFO  decoder.c:819-831
+ *   process_*_transition glue              decoder.c:560-609      feedback: feedback.cuh
+ *
+ * How it differs from a transliteration:
+ *  1. int16 domain.  v = (float)i/32767*maxvolts (readtape.c:1420) is strictly monotone in i, so the
+ *     max / min / == of lookfor_peak are evaluated on the raw samples; floats are formed only at
+ *     candidate rows, with the reference's exact expressions.
+ *  2. O(1) sliding max and min (van Herk / Gil-Werman): rows are cut into blocks of `width` rows from
+ *     the track's first sample; g = running max inside the current block, H[k] = suffix max of the
+ *     previous block from position k; window max = max(g, H[j+1]).  Samples are held as packed int16x2
+ *     words (x, ~x): one signed 16x2 max yields the max of x and (complemented) the min of x.
+ *  3. The reference's lazily refreshed minimum (decoder.c:765 never updates pkww_minv; only the rescan at
+ *     :767-775 does) is the recurrence  m <- Wmin(r)  iff  leaving >= S(r)  or  leaving == m,
+ *     where S / Wmin are the exact window max / min: `leaving == max(S(r-1), v_now)` <=> leaving >= S(r).
+ *     While the window is still filling, `leaving` is the constant 0.0f of decoder.c:754.
+ *  4. Integer pre-filter: a row can only fire if S - max(left,right) >= T or min(left,right) - m >= T with
+ *     T a conservative integer bound of required_rise (recomputed after every event, the only place
+ *     AGC gain / average height change).  The exact float tests of decoder.c:790-803 run at those rows.
+ *  5. Stop-and-handle loop: lanes search for their next candidate row in a tight loop and handle events
+ *     together afterwards, so that a warp is not serialised on 32 different event times.
+ *
+ * Per-lane scratch (device: lane-interleaved shared memory, bank = lane for every access):
+ *   X[RING]  ring of packed samples indexed by stream offset,  RING = pow2 >= 2*width+6
+ *   H[width] suffix maxima of the previous block
+ */
+#pragma once
+#include <string.h>
+#include "rt_dev.h"
+#include "feedback.cuh"
+#include "quiet.cuh"
+
+#define RT_FHD __host__ __device__ __forceinline__
+
+namespace rtfast {
+
+constexpr uint32_t PK_NEG = 0x80008000u;                 /* identity of vmax2 */
+constexpr int32_t  OFF_NONE = INT32_MIN;                 /* "no row" for offsets relative to the unit start */
+
+RT_FHD uint32_t pk(int x) { return ((uint32_t)x << 16) | ((uint32_t)(~x) & 0xffffu); }
+RT_FHD int pk_hi(uint32_t w) { return (int)w >> 16; }                               /* x, or a max of x          */
+RT_FHD int pk_min(uint32_t w) { return ~(int)(int16_t)(uint16_t)(w & 0xffffu); }     /* min of x (from max of ~x) */
+RT_FHD uint32_t vmax2(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+   return __vmaxs2(a, b);
+#else
+   int ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16), al = (int16_t)(a & 0xffff), bl = (int16_t)(b & 0xffff);
+   int h = ah > bh ? ah : bh, l = al > bl ? al : bl;
+   return ((uint32_t)h << 16) | ((uint32_t)l & 0xffffu);
+#endif
+}
+
+RT_FHD double row_time(const DevCfg &c, uint64_t row) {                              /* readtape.c:1423 */
+   long long ns = (long long)(c.tstart_ns + row * c.tdelta_ns);
+   return (double)ns / 1e9; }
+
+RT_FHD float volts(const DevCfg &c, int x) { return (float)x / 32767 * c.maxvolts; }   /* readtape.c:1420 */
+
+/* ring size for a window width */
+RT_FHD uint32_t ring_size(int w) { uint32_t r = 32; while (r < (uint32_t)(2 * w + 6)) r <<= 1; return r; }
+
+/* lane-private scratch; STRIDE = distance (in elements) between consecutive entries of one lane.
+ *   PH[k], k = 1..w : .x = sample k of the PREVIOUS block (PH[w].x = sample 0 of the current block),
+ *                     .y = max over samples k..w-1 of the previous block (PH[w].y = identity)
+ *                     -> row j of a block reads PH[j+1]: its window's left edge and the suffix max, one 64-bit load
+ *   X[RING]         : ring of packed samples indexed by stream offset (the loader's target; refine_peak walks it)
+ *   HT[10]          : AGC height history (v_heights[], decoder.h:226) -- indexed dynamically, so not in registers */
+struct pair32 { uint32_t x, y; };
+template <int STRIDE>
+struct LaneMem {
+   pair32 *ph; uint32_t *x, *ht; uint32_t mask;
+   RT_FHD uint32_t &X(uint32_t o) const { return x[(size_t)(o & mask) * STRIDE]; }
+   RT_FHD pair32 PH(int k) const {
+#ifdef __CUDA_ARCH__
+      const uint2 v = *reinterpret_cast<const uint2 *>(ph + (size_t)k * STRIDE); return pair32{v.x, v.y};
+#else
+      return ph[(size_t)k * STRIDE];
+#endif
+   }
+   RT_FHD void setPH(int k, uint32_t p, uint32_t h) const {
+#ifdef __CUDA_ARCH__
+      *reinterpret_cast<uint2 *>(ph + (size_t)k * STRIDE) = make_uint2(p, h);
+#else
+      ph[(size_t)k * STRIDE] = pair32{p, h};
+#endif
+   } };
+
+template <int STRIDE>
+struct HeightsRef {
+   uint32_t *p;
+   RT_FHD float &operator[](int i) const { return reinterpret_cast<float *>(p)[(size_t)i * STRIDE]; } };
+
+/* The feedback state of one track: the members of TrkState (rt_dev.h) the peak detector path uses. */
+template <int STRIDE>
+struct FastState {
+   double  t_top, t_bot, t_lastpeak;
+   float   v_top, v_bot, v_lasttop, v_lastbot;
+   float   avg_height, avg_height_sum, agc_gain;
+   HeightsRef<STRIDE> heights;
+   int32_t avg_height_count, heightndx, peakcount;
+   float   t_clkwindow;
+   uint8_t datablock, bit1_up, failed;
+};
+
+/* words of scratch one lane needs; the PH pairs come first (8-byte aligned), then the ring, then the heights */
+RT_FHD uint32_t scratch_words(int w) { return 2u * (uint32_t)(w + 1) + ring_size(w) + RT_AGC_MAX_WINDOW; }
+/* One lane's scan of one (unit, track), written as a resumable state machine so that the 32 lanes of a warp can
+ * be driven in lock step:  begin() -> { search() [-> handle()] }* until the block is done -> advance() -> ... -> finish().
+ * A "block" is `width` consecutive rows counted from the track's first sample (the van Herk blocks). */
+template <int STRIDE, class Emit>
+struct UnitScan {
+   const DevCfg &c; const int16_t *plane; uint64_t row0; uint32_t end; int trk, w, delay; uint32_t io;
+   LaneMem<STRIDE> mem; Emit em; FastState<STRIDE> t;
+   /* detector state */
+   int m, T, blind; uint32_t lvw; float inv_lsb, rise, reqmin;
+   /* position: block [b, b+n), next row b+j, g = running packed max of the block, fillblk = window still filling */
+   uint32_t b, g; int n, j; bool fillblk, done, cand, candA;
+   /* loader */
+   uint32_t ld;
+   /* proof data, kept lazily (offsets relative to row0; OFF_NONE = none): see track() */
+   int qmin, qmax, qthr, qL; int32_t ll, last_canon;
+   int32_t sync_row, loud_at_sync, sync_first, sync_early, loud_early; bool early_frozen; uint32_t sf_from; uint64_t quiet_from;
+
+   RT_FHD UnitScan(const DevCfg &c_, LaneMem<STRIDE> mem_) : c(c_), w(c_.width), mem(mem_) { done = true; cand = false; n = j = 0; }
+
+   /* the sample the detector sees at stream offset o (deskew FIFO, decoder.c:819-831) */
+   RT_FHD int sample(uint32_t o) const { return (int)plane[row0 + (o >= (uint32_t)delay ? o - (uint32_t)delay : o)]; }
+
+   /* make ring entries of offsets < upto available */
+   RT_FHD void ensure(uint32_t upto) {
+      while (ld < upto) {
+         if (ld < (uint32_t)delay) { mem.X(ld) = pk(sample(ld)); ++ld; }
+         else {
+            const int16_t *p = plane + row0 + (ld - (uint32_t)delay);          /* 16-byte aligned: row0 % 32 == 0, (ld-delay) % 8 == 0 */
+#ifdef __CUDA_ARCH__
+            const uint4 q = *reinterpret_cast<const uint4 *>(p);
+            const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#else
+            uint32_t wds[4]; memcpy(wds, p, 16);
+#endif
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+               const uint32_t v = wds[i], nv = ~v;
+               mem.X(ld + 2 * i) = (v << 16) | (nv & 0xffffu);
+               mem.X(ld + 2 * i + 1) = (v & 0xffff0000u) | (nv >> 16); }
+            ld += 8; } } }
+
+   /* required_rise / required_min (decoder.c:785-786) only change at events: cached, with the integer bound T */
+   RT_FHD void thresholds() {
+      rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+      reqmin = c.p.min_peak * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+      /* a top needs S_f > X_f + rise and |volts(i) - i*lsb| <= 2^-22 * 32768 * lsb, so S - X >= rise/lsb*(1-1e-3) - 2 */
+      float q = rise * inv_lsb * 0.999f - 2.0f;
+      T = !(q > 0) ? 0 : (q > 70000.0f ? 70000 : (int)q); }
+
+   /* ---- proof data of the unit-equivalence test, collected before the first event ------------------
+    * k_units_scan (k_scan.cu) evaluates, on every row: loudness (quiet.cuh), then
+    *     if (sync_early set && last_loud != loud_early) early_frozen = true;
+    *     if (canonical && last_loud < row) { sync_row = row; loud_at_sync = last_loud; if (!early_frozen) {sync_early = row; loud_early = last_loud;}
+    *                                         if (sync_first unset && row >= own_fill && last_loud < row0) sync_first = row; }
+    * last_loud only changes on loud rows, which are rare, so the same values are obtained by remembering the last
+    * canonical quiet row (one predicated move per row) and committing it whenever last_loud is about to change. */
+   RT_FHD void commit() {
+      if (last_canon != OFF_NONE && last_canon != sync_row) {        /* a canonical row newer than the committed one */
+         sync_row = last_canon; loud_at_sync = ll;
+         if (!early_frozen) { sync_early = last_canon; loud_early = ll; } } }
+   RT_FHD void loud_row(int32_t o) {
+      commit();
+      if (sync_early != OFF_NONE) early_frozen = true;
+      ll = o;
+      if (o >= 0) sf_from = 0xffffffffu; }
+   /* loudness of the row at offset o (negative: the pre-scan) whose raw (undelayed) sample is `raw` */
+   RT_FHD void feed(int32_t o, int raw) {
+      if (raw < qmin) qmin = raw;
+      if (raw > qmax) qmax = raw;
+      if (qmax - qmin >= qthr) {                   /* re-anchor on the exact span; loud only if IT is */
+         int mx = raw, mn = raw;
+         int64_t from = (int64_t)row0 + o - qL + 1; if (from < 0) from = 0;
+         for (int64_t i = from; i < (int64_t)row0 + o; ++i) { int y = plane[i]; if (y > mx) mx = y; if (y < mn) mn = y; }
+         qmin = mn; qmax = mx;
+         if (mx - mn >= qthr) loud_row(o); } }
+   RT_FHD void track(uint32_t o, int xraw_stream, bool canonical) {
+      feed((int32_t)o, delay ? (int)plane[row0 + o] : xraw_stream);
+      if (canonical && ll != (int32_t)o) {
+         last_canon = (int32_t)o;
+         if (o >= sf_from) { sync_first = (int32_t)o; sf_from = 0xffffffffu; } } }
+
+   /* refine_peak, decoder.c:700-749: window = stream offsets [wstart, o] */
+   RT_FHD double refine(int val, bool top, uint32_t wstart, uint32_t o) {
+      int left_distance = 1;
+      for (uint32_t i = wstart;; ++i) {
+         if (pk_hi(mem.X(i)) == val) {
+            if (left_distance >= w || i == wstart) { t.failed = 2; return 0; }
+            const float vprev = volts(c, pk_hi(mem.X(i - 1)));
+            const float vnext = i < o ? volts(c, pk_hi(mem.X(i + 1))) : 0.0f;     /* i == o: only in a filling window, the unwritten slot */
+            const float v = volts(c, val);
+            float adj = 0;
+            if (top) {
+               float edge = v - RT_PEAK_THRESHOLD / t.agc_gain;
+               if (vprev > edge && vnext < edge) adj = -0.5f;
+               else if (vnext > edge && vprev < edge) adj = +0.5f; }
+            else {
+               float edge = v + RT_PEAK_THRESHOLD / t.agc_gain;
+               if (vprev < edge && vnext > edge) adj = -0.5f;
+               else if (vnext < edge && vprev > edge) adj = +0.5f; }
+            const double timenow = row_time(c, row0 + o);
+            const double time = timenow - (double)(((float)(w - left_distance) - adj) * c.sample_deltat);
+            blind = left_distance;
+            return time; }
+         ++left_distance;
+         if (i == o) break; }
+      t.failed = 2;
+      return 0; }
+
+   /* process_*_transition, decoder.c:560-609 */
+   RT_FHD void transition(bool top, uint32_t o) {
+      const double t_ev = top ? t.t_top : t.t_bot;
+      const float v_top_seen = t.v_top, v_bot_seen = t.v_bot;
+      ++t.peakcount;
+      if (c.mode == RT_MODE_NRZI) rtfb::nrzi_feedback(c, t, top);
+      else if (c.mode == RT_MODE_PE) rtfb::pe_feedback(c, t, top, t_ev);
+      else rtfb::agc_adjust(c, t);
+      if (top) t.v_lasttop = t.v_top; else t.v_lastbot = t.v_bot;
+      t.t_lastpeak = t_ev;
+      em.emit(row0 + o, t_ev, v_top_seen, v_bot_seen, t.agc_gain, top);
+      thresholds(); }
+
+   /* start the scan of unit rows [row0_, row_end) of track trk_ from a fresh RT_RESET_FULL */
+   RT_FHD void begin(const int16_t *plane_, uint64_t row0_, uint64_t row_end, int trk_, Emit em_, int quiet_thr_lsb) {
+      plane = plane_; row0 = row0_; end = (uint32_t)(row_end - row0_); trk = trk_; delay = c.skew[trk_]; em = em_;
+      const bool tz = row_time(c, row0) == 0.0;
+      io = (uint32_t)trk + (tz ? 1u : 0u);
+      /* reset_full (scan_generic.cuh) restricted to the members of FastState */
+      t.t_top = t.t_bot = t.t_lastpeak = 0; t.v_top = t.v_bot = t.v_lasttop = t.v_lastbot = 0; t.avg_height_sum = 0;
+      t.avg_height_count = t.heightndx = t.peakcount = 0; t.datablock = t.bit1_up = t.failed = 0;
+      t.heights.p = mem.ht;
+      for (int i = 0; i < RT_AGC_MAX_WINDOW; ++i) t.heights[i] = 0.0f;
+      t.agc_gain = 1.0f; t.avg_height = RT_PKWW_PEAKHEIGHT;
+      t.t_clkwindow = c.clk_init / 2 * c.p.clk_factor;
+      inv_lsb = 32767.0f / c.maxvolts;
+      thresholds(); blind = 0; m = 0; lvw = 0;
+      /* proof data: quiet pre-scan of the rows before the unit, then the rows up to the track's first sample */
+      qthr = quiet_thr_lsb; qL = w + delay; qmin = 32767; qmax = -32768; ll = last_canon = OFF_NONE;
+      sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false;
+      const int lead = (int)io > delay ? (int)io : delay;
+      sf_from = (uint32_t)(lead + w + 1);
+      const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
+      for (int32_t o = -npre; o < 0; ++o) feed(o, (int)plane[(int64_t)row0 + o]);
+      quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
+      for (uint32_t o = 0; o <= io && o < end; ++o) track(o, sample(o), false);      /* decoder.c:855-861: not looked at yet */
+      cand = false; j = 0; n = 0; g = PK_NEG; fillblk = true; b = io + 1;
+      done = b >= end;
+      if (!done) {
+         const int x0 = sample(io);
+         m = x0; lvw = pk(x0);
+         t.t_lastpeak = row_time(c, row0 + io);
+         mem.X(io) = pk(x0);
+         ld = b < (uint32_t)delay ? b : (b - (uint32_t)delay) / 8 * 8 + (uint32_t)delay;
+         n = end - b < (uint32_t)w ? (int)(end - b) : w;
+         ensure(b + (uint32_t)n);
+         mem.X(io) = pk(x0);                                       /* the loader may have written offsets below b */
+         /* the window of the filling phase always starts at the first sample: with that sample as "previous block"
+            the steady-state expressions yield max(x0, g) and left = x0 */
+         for (int k = 1; k < w; ++k) mem.setPH(k, pk(x0), pk(x0));
+         mem.setPH(w, mem.X(b), PK_NEG); } }
+
+/* the window update shared by all row loops: new sample in, exact max S, lazily refreshed minimum m (decoder.c:753-775) */
+#define RT_ROW_CORE(o_)                                                                             \
+         const uint32_t xw = mem.X(o_);                                                              \
+         const pair32 ph = mem.PH(j + 1);                                                            \
+         g = vmax2(g, xw);                                                                           \
+         const uint32_t sw = vmax2(g, ph.y);                                                         \
+         const int S = pk_hi(sw);
+
+   /* rows of the current block from j on, until a candidate row (cand = true, j stays on it) or the block is done */
+   RT_FHD void search() {
+      cand = false;
+      if (fillblk) { search_fill(); return; }
+      const uint32_t b_ = b;
+      for (; blind && j < n; ++j, --blind) {                      /* decoder.c:778: blind until the last peak has left the window */
+         RT_ROW_CORE(b_ + (uint32_t)j)
+         const int lv = pk_hi(lvw);
+         if (lv >= S || lv == m) m = pk_min(sw);
+         lvw = ph.x; }
+      if (em.n != 0) {
+         for (; j < n; ++j) {
+            RT_ROW_CORE(b_ + (uint32_t)j)
+            const int lv = pk_hi(lvw);
+            if (lv >= S || lv == m) m = pk_min(sw);               /* the rescan of decoder.c:767-775 */
+            lvw = ph.x;
+            const uint32_t xy = vmax2(ph.x, xw);                  /* (max(left,right), ~min(left,right)) */
+            if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { cand = true; return; } } }
+      else {
+         for (; j < n; ++j) {
+            RT_ROW_CORE(b_ + (uint32_t)j)
+            const int lv = pk_hi(lvw);
+            const bool A = lv >= S;
+            if (A || lv == m) m = pk_min(sw);
+            lvw = ph.x;
+            const uint32_t xy = vmax2(ph.x, xw);
+            if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { cand = true; candA = A; return; }
+            track(b_ + (uint32_t)j, pk_hi(xw), A); } } }
+
+   /* the same for the block right after the track's first sample, whose window is still filling for j < w-1 */
+   RT_FHD void search_fill() {
+      for (; j < n; ++j) {
+         const uint32_t o = b + (uint32_t)j;
+         RT_ROW_CORE(o)
+         const bool full = j == w - 1;
+         const int lv = full ? pk_hi(lvw) : 0;                    /* decoder.c:754: old_left stays 0 until the window is full */
+         const bool A = full ? lv >= S : S == 0;
+         if (A || lv == m) m = pk_min(sw);
+         lvw = ph.x;
+         if (blind) { --blind; continue; }
+         const uint32_t xy = vmax2(ph.x, xw);
+         if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { cand = true; candA = full && A; return; }
+         if (em.n == 0) track(o, pk_hi(xw), full && A); } }
+
+   /* the exact tests of decoder.c:790-803 at the candidate row b+j */
+   RT_FHD void handle() {
+      const uint32_t o = b + (uint32_t)j;
+      const uint32_t xw = mem.X(o);
+      const pair32 ph = mem.PH(j + 1);
+      const uint32_t sw = vmax2(g, ph.y);
+      const int S = pk_hi(sw);
+      const bool full = !fillblk || j == w - 1;
+      const uint32_t wstart = full ? o - (uint32_t)w + 1u : io;
+      const float vl = volts(c, pk_hi(ph.x)), vr = volts(c, pk_hi(xw));
+      const float maxv = volts(c, S), minv = volts(c, m);
+      bool fired = false;
+      if (maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin)) {
+         if (em.n == 0) commit();
+         t.v_top = maxv;
+         t.t_top = refine(S, true, wstart, o);
+         transition(true, o);
+         fired = true; }
+      else if (minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin)) {
+         if (em.n == 0) commit();
+         t.v_bot = minv;
+         t.t_bot = refine(m, false, wstart, o);
+         transition(false, o);
+         fired = true; }
+      if (!fired && em.n == 0) track(o, pk_hi(xw), candA);
+      cand = false; ++j; }
+
+   /* the current block is done: prepare the next one, or finish the unit */
+   RT_FHD void advance() {
+      if (n == w) {                                               /* this block becomes the "previous block" */
+         uint32_t h = PK_NEG;
+         for (int k = w - 1; k >= 1; --k) { const uint32_t x = mem.X(b + (uint32_t)k); h = vmax2(h, x); mem.setPH(k, x, h); } }
+      b += (uint32_t)w; fillblk = false; j = 0; g = PK_NEG;
+      if (b >= end) { done = true; n = 0; return; }
+      n = end - b < (uint32_t)w ? (int)(end - b) : w;
+      ensure(b + (uint32_t)n);
+      mem.setPH(w, mem.X(b), PK_NEG); }
+
+   RT_FHD void finish(TrkMeta &meta) {
+      if (em.n == 0) commit();
+      meta.first_event_row = em.first_row;
+      meta.sync_row = sync_row == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_row;
+      meta.last_loud_row = loud_at_sync == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_at_sync);
+      meta.sync_first = sync_first == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_first;
+      meta.quiet_from = quiet_from;
+      meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
+      meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
+      meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = 0; } };
+#undef RT_ROW_CORE
+
+/* Drive one lane (host) or the 32 lanes of a warp (device) through a list of (unit, track) jobs.  `Jobs` provides
+ *   bool next(UnitScan&)   start the lane's next job, false if there is none
+ *   void done(UnitScan&)   the lane's job is finished (store its TrkMeta)
+ * and `any(pred)` is the warp vote (identity on the host).  The votes keep the lanes converged: all lanes search,
+ * then the lanes that stopped on a candidate row handle it TOGETHER, then all lanes move to their next block together. */
+template <class Scan, class Jobs, class Vote>
+RT_FHD void drive(Scan &us, Jobs &jobs, Vote any) {
+   bool active = jobs.next(us);
+   while (any(active)) {
+      const bool more = active && !us.done && us.j < us.n;
+      if (any(more)) {
+         if (more) us.search();
+         const bool cnd = more && us.cand;
+         if (any(cnd)) { if (cnd) us.handle(); }
+         continue; }
+      if (active) {
+         if (!us.done) us.advance();
+         if (us.done) { jobs.done(us); active = jobs.next(us); } } } }
+
+}  // namespace rtfast

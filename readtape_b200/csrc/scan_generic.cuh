@@ -24,6 +24,8 @@
  */
 #pragma once
 #include "rt_dev.h"
+#include "feedback.cuh"
+#include "quiet.cuh"
 
 namespace rtgen {
 
@@ -52,53 +54,11 @@ __device__ inline void clk_force(TrkState &t, float v) {
    for (int i = 0; i < RT_CLKRATE_WINDOW; ++i) t.clk_spacing[i] = v;
    t.clk_avg = v; }
 
-/* ---- AGC, decoder.c:500-531 ---------------------------------------------------------------- */
-__device__ inline void agc_adjust(const DevCfg &c, TrkState &t) {
-   if (c.find_zeros) return;
-   float gain, lastheight;
-   if (c.p.agc_alpha != 0) {
-      lastheight = t.v_lasttop - t.v_lastbot;
-      if (lastheight > 0) {
-         gain = t.avg_height / lastheight;
-         gain = c.p.agc_alpha * gain + (1 - c.p.agc_alpha) * t.agc_gain;
-         if (gain > RT_AGC_MAX_VALUE) gain = RT_AGC_MAX_VALUE;
-         t.agc_gain = gain; } }
-   if (c.p.agc_window != 0) {
-      lastheight = t.v_lasttop - t.v_lastbot;
-      if (lastheight > 0) {
-         t.heights[t.heightndx] = lastheight;
-         if (++t.heightndx >= c.p.agc_window) t.heightndx = 0;
-         float minheight = 99;
-         for (int i = 0; i < c.p.agc_window; ++i) if (t.heights[i] < minheight) minheight = t.heights[i];
-         gain = t.avg_height / minheight;
-         if (gain > RT_AGC_MAX_VALUE) gain = RT_AGC_MAX_VALUE;
-         t.agc_gain = gain; } } }
-
-__device__ inline void baseline_accumulate(const DevCfg &c, TrkState &t) {
-   t.avg_height_sum += t.v_top - t.v_bot;
-   ++t.avg_height_count;
-   t.heights[t.heightndx] = t.v_top - t.v_bot;
-   if (++t.heightndx >= c.p.agc_window) t.heightndx = 0; }
-
-/* ---- mode feedback fragments ---------------------------------------------------------------- */
-__device__ inline void nrzi_feedback(const DevCfg &c, TrkState &t, bool top) {
-   if (top) {
-      if (t.peakcount >= RT_AGC_STARTBASE && t.peakcount <= RT_AGC_ENDBASE) baseline_accumulate(c, t);
-      else if (t.peakcount > RT_AGC_ENDBASE) {
-         if (t.avg_height_count) {
-            t.avg_height = t.avg_height_sum / t.avg_height_count;
-            t.avg_height_count = 0; }
-         else agc_adjust(c, t); } }
-   else if (t.peakcount > RT_AGC_ENDBASE && t.avg_height_count == 0) agc_adjust(c, t); }
-
-__device__ inline void pe_feedback(const DevCfg &c, TrkState &t, bool top, double t_ev) {
-   if (t.datablock) { agc_adjust(c, t); return; }
-   if (t.peakcount == 1) t.bit1_up = !top;
-   if (t.peakcount > RT_PE_MIN_PREBITS && (t.bit1_up != 0) == top && t_ev - t.t_lastpeak > t.t_clkwindow) {
-      t.datablock = 1;
-      t.avg_height = t.avg_height_sum / t.avg_height_count; }
-   else if (t.peakcount >= RT_AGC_STARTBASE && t.peakcount <= RT_AGC_ENDBASE && t.v_top > t.v_bot)
-      baseline_accumulate(c, t); }
+/* ---- AGC and the NRZI / PE feedback fragments: shared with the fast path (feedback.cuh) ------ */
+using rtfb::agc_adjust;
+using rtfb::baseline_accumulate;
+using rtfb::nrzi_feedback;
+using rtfb::pe_feedback;
 
 __device__ inline void gcr_addbit(TrkState &t, int bit) {
    t.datablock = 1;
@@ -290,12 +250,15 @@ __device__ inline float raw_at(const DevCfg &c, const int16_t *plane, uint64_t j
    return v; }
 
 struct QuietTracker {
-   float runmin, runmax, thr; int L; uint64_t last_loud; bool primed;
-   __device__ void init(const DevCfg &c, int trk, float quiet_thr) {
+   float runmin, runmax, thr; int L; uint64_t last_loud; bool primed, use_int; QuietInt qi;
+   __device__ void init(const DevCfg &c, int trk, float quiet_thr, int quiet_thr_lsb) {
       L = (c.det == RT_DET_PEAK ? c.width : 1) + c.skew[trk];
-      thr = quiet_thr; last_loud = RT_NOROW; primed = false; runmin = runmax = 0; }
+      thr = quiet_thr; last_loud = RT_NOROW; primed = false; runmin = runmax = 0;
+      use_int = c.det == RT_DET_PEAK && !c.differentiate;          /* quiet.cuh: the int16-domain test both scan kernels share */
+      qi.init(L, quiet_thr_lsb); }
    /* feed row j (rows must be fed consecutively); v = raw_at(j) */
    __device__ void feed(const DevCfg &c, const int16_t *plane, uint64_t j, float v) {
+      if (use_int) { qi.feed(plane, j, (int)plane[j]); last_loud = qi.last_loud; return; }
       if (c.det == RT_DET_PEAK) {
          if (!primed) { runmin = runmax = v; primed = true; }
          if (v < runmin) runmin = v;
