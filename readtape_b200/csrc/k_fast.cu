@@ -40,23 +40,19 @@ struct DevJobs {
       atomicAdd(&rows_scanned[0], (unsigned long long)us.end);
       if (us.em.n) atomicAdd(&rows_scanned[1], (unsigned long long)us.em.n); } };
 
-struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p) != 0; } };
+struct WarpCount { __device__ int operator()(bool p) const { return __popc(__ballot_sync(0xffffffffu, p)); } };
 
-__global__ void __launch_bounds__(FAST_THREADS, 6)
+__global__ void __launch_bounds__(FAST_THREADS, 4)
 k_units_fast(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta *meta,
              rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
              int quiet_thr_lsb, unsigned long long *rows_scanned, uint32_t ring) {
    extern __shared__ __align__(16) uint32_t fast_smem[];
-   /* [entry][thread] layout; the 8-byte PH pairs come first: the lane's pair k sits at byte (k*FAST_THREADS + tid)*8 */
-   LaneMem<FAST_THREADS> mem;
-   mem.ph = reinterpret_cast<pair32 *>(fast_smem) + threadIdx.x;
-   mem.x = fast_smem + (size_t)2 * (c.width + 1) * FAST_THREADS + threadIdx.x;
-   mem.ht = mem.x + (size_t)ring * FAST_THREADS; mem.mask = ring - 1;
+   LaneMem<FAST_THREADS> mem = lane_mem<FAST_THREADS>(fast_smem + threadIdx.x, c.width);      /* [entry][thread] layout */
    const uint64_t total = (uint64_t)(*nunits_p) * (uint64_t)c.ntrks;
    DevJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned,
                 (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, total, (uint64_t)gridDim.x * blockDim.x, 0};
    UnitScan<FAST_THREADS, PoolEmit> us(c, mem);
-   drive(us, jobs, WarpAny()); }
+   drive(us, jobs, WarpCount()); }
 
 bool fast_scan_eligible(const DevCfg &c) {
    return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate

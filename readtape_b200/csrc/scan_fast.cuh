@@ -66,34 +66,32 @@ RT_FHD double row_time(const DevCfg &c, uint64_t row) {                         
 
 RT_FHD float volts(const DevCfg &c, int x) { return (float)x / 32767 * c.maxvolts; }   /* readtape.c:1420 */
 
-/* ring size for a window width */
-RT_FHD uint32_t ring_size(int w) { uint32_t r = 32; while (r < (uint32_t)(2 * w + 6)) r <<= 1; return r; }
+/* Lanes run FAST_K rows between two maintenance points (loader, job switch); a lane that meets a candidate row waits
+   for the handler, which runs when FAST_NPEND lanes of the warp are waiting or at the maintenance point. */
+#define FAST_K      16
+#define FAST_NPEND  8
 
-/* lane-private scratch; STRIDE = distance (in elements) between consecutive entries of one lane.
- *   PH[k], k = 1..w : .x = sample k of the PREVIOUS block (PH[w].x = sample 0 of the current block),
- *                     .y = max over samples k..w-1 of the previous block (PH[w].y = identity)
- *                     -> row j of a block reads PH[j+1]: its window's left edge and the suffix max, one 64-bit load
- *   X[RING]         : ring of packed samples indexed by stream offset (the loader's target; refine_peak walks it)
- *   HT[10]          : AGC height history (v_heights[], decoder.h:226) -- indexed dynamically, so not in registers */
-struct pair32 { uint32_t x, y; };
+/* ring size for a window width: holds offsets [o-w+1, o+FAST_K+w+7] */
+RT_FHD uint32_t ring_size(int w) { uint32_t r = 32; while (r < (uint32_t)(2 * w + FAST_K + 8)) r <<= 1; return r; }
+
+/* lane-private scratch; STRIDE = distance (in words) between consecutive entries of one lane.
+ *   X[RING]      : ring of packed samples indexed by stream offset (the loader's target)
+ *   H[2][w+1]    : suffix maxima of the previous block (read by the forward step: row j reads H[prev][j+1], entry w is
+ *                  the identity) and of the current block (written by the backward step, one entry per row)
+ *   HT[10]       : AGC height history (v_heights[], decoder.h:226) -- indexed dynamically, so not in registers */
 template <int STRIDE>
 struct LaneMem {
-   pair32 *ph; uint32_t *x, *ht; uint32_t mask;
+   uint32_t *x, *h, *ht; uint32_t mask;
    RT_FHD uint32_t &X(uint32_t o) const { return x[(size_t)(o & mask) * STRIDE]; }
-   RT_FHD pair32 PH(int k) const {
-#ifdef __CUDA_ARCH__
-      const uint2 v = *reinterpret_cast<const uint2 *>(ph + (size_t)k * STRIDE); return pair32{v.x, v.y};
-#else
-      return ph[(size_t)k * STRIDE];
-#endif
-   }
-   RT_FHD void setPH(int k, uint32_t p, uint32_t h) const {
-#ifdef __CUDA_ARCH__
-      *reinterpret_cast<uint2 *>(ph + (size_t)k * STRIDE) = make_uint2(p, h);
-#else
-      ph[(size_t)k * STRIDE] = pair32{p, h};
-#endif
-   } };
+   RT_FHD uint32_t &H(int k) const { return h[(size_t)k * STRIDE]; } };
+
+/* exact min / max of plane[from .. to) and x: the rare re-anchoring step of the loudness test.  Kept out of line so that
+   its address arithmetic is not hoisted into the row loop. */
+struct minmax { int mn, mx; };
+__host__ __device__ __noinline__ static minmax span_minmax(const int16_t *plane, int64_t from, int64_t to, int x) {
+   minmax r{x, x};
+   for (int64_t i = from; i < to; ++i) { const int y = plane[i]; if (y > r.mx) r.mx = y; if (y < r.mn) r.mn = y; }
+   return r; }
 
 template <int STRIDE>
 struct HeightsRef {
@@ -112,26 +110,36 @@ struct FastState {
    uint8_t datablock, bit1_up, failed;
 };
 
-/* words of scratch one lane needs; the PH pairs come first (8-byte aligned), then the ring, then the heights */
-RT_FHD uint32_t scratch_words(int w) { return 2u * (uint32_t)(w + 1) + ring_size(w) + RT_AGC_MAX_WINDOW; }
-/* One lane's scan of one (unit, track), written as a resumable state machine so that the 32 lanes of a warp can
- * be driven in lock step:  begin() -> { search() [-> handle()] }* until the block is done -> advance() -> ... -> finish().
+/* words of scratch one lane needs: ring, the two H arrays, the heights */
+RT_FHD uint32_t scratch_words(int w) { return ring_size(w) + 2u * (uint32_t)(w + 1) + RT_AGC_MAX_WINDOW; }
+template <int STRIDE>
+RT_FHD LaneMem<STRIDE> lane_mem(uint32_t *lane_base /* first word of this lane in a [scratch_words][STRIDE] array */, int w) {
+   LaneMem<STRIDE> m;
+   m.x = lane_base; m.mask = ring_size(w) - 1;
+   m.h = m.x + (size_t)ring_size(w) * STRIDE; m.ht = m.h + (size_t)2 * (w + 1) * STRIDE;
+   return m; }
+/* One lane's scan of one (unit, track) as a resumable state machine, so that the 32 lanes of a warp can be driven
+ * together (drive()):  begin() -> { step() | handle() }* -> finish().   step() processes exactly one row: forward step of the
+ * sliding max/min, one backward step of the current block's suffix maxima, lazy-minimum update, pre-filter.  A row that
+ * passes the pre-filter leaves the lane waiting (pend) for handle(), which runs the exact tests for all waiting lanes at once.
  * A "block" is `width` consecutive rows counted from the track's first sample (the van Herk blocks). */
+enum { ST_RUN = 0, ST_PEND = 1, ST_DONE = 2 };          /* scanning | stopped on a candidate row, waiting for handle() | unit finished */
 template <int STRIDE, class Emit>
 struct UnitScan {
    const DevCfg &c; const int16_t *plane; uint64_t row0; uint32_t end; int trk, w, delay; uint32_t io;
    LaneMem<STRIDE> mem; Emit em; FastState<STRIDE> t;
    /* detector state */
    int m, T, blind; uint32_t lvw; float inv_lsb, rise, reqmin;
-   /* position: block [b, b+n), next row b+j, g = running packed max of the block, fillblk = window still filling */
-   uint32_t b, g; int n, j; bool fillblk, done, cand, candA;
+   /* position: next row o = b + j; g = running packed max of block [b, b+w) up to j, hbk = running max of its backward pass;
+      hp / hc = first entries of the previous / current block's H array; fillblk = the window is still filling */
+   uint32_t o, b, g, hbk; int j, hp, hc, st, fillblk, candA, pre;
    /* loader */
    uint32_t ld;
    /* proof data, kept lazily (offsets relative to row0; OFF_NONE = none): see track() */
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
    int32_t sync_row, loud_at_sync, sync_first, sync_early, loud_early; bool early_frozen; uint32_t sf_from; uint64_t quiet_from;
 
-   RT_FHD UnitScan(const DevCfg &c_, LaneMem<STRIDE> mem_) : c(c_), w(c_.width), mem(mem_) { done = true; cand = false; n = j = 0; }
+   RT_FHD UnitScan(const DevCfg &c_, LaneMem<STRIDE> mem_) : c(c_), w(c_.width), mem(mem_) { st = ST_DONE; j = 0; o = end = 0; }
 
    /* the sample the detector sees at stream offset o (deskew FIFO, decoder.c:819-831) */
    RT_FHD int sample(uint32_t o) const { return (int)plane[row0 + (o >= (uint32_t)delay ? o - (uint32_t)delay : o)]; }
@@ -184,43 +192,35 @@ struct UnitScan {
       if (raw < qmin) qmin = raw;
       if (raw > qmax) qmax = raw;
       if (qmax - qmin >= qthr) {                   /* re-anchor on the exact span; loud only if IT is */
-         int mx = raw, mn = raw;
-         int64_t from = (int64_t)row0 + o - qL + 1; if (from < 0) from = 0;
-         for (int64_t i = from; i < (int64_t)row0 + o; ++i) { int y = plane[i]; if (y > mx) mx = y; if (y < mn) mn = y; }
-         qmin = mn; qmax = mx;
-         if (mx - mn >= qthr) loud_row(o); } }
+         const int64_t to = (int64_t)row0 + o, from = to - qL + 1;
+         const minmax r = span_minmax(plane, from < 0 ? 0 : from, to, raw);
+         qmin = r.mn; qmax = r.mx;
+         if (r.mx - r.mn >= qthr) loud_row(o); } }
    RT_FHD void track(uint32_t o, int xraw_stream, bool canonical) {
       feed((int32_t)o, delay ? (int)plane[row0 + o] : xraw_stream);
       if (canonical && ll != (int32_t)o) {
          last_canon = (int32_t)o;
          if (o >= sf_from) { sync_first = (int32_t)o; sf_from = 0xffffffffu; } } }
 
-   /* refine_peak, decoder.c:700-749: window = stream offsets [wstart, o] */
-   RT_FHD double refine(int val, bool top, uint32_t wstart, uint32_t o) {
-      int left_distance = 1;
-      for (uint32_t i = wstart;; ++i) {
-         if (pk_hi(mem.X(i)) == val) {
-            if (left_distance >= w || i == wstart) { t.failed = 2; return 0; }
-            const float vprev = volts(c, pk_hi(mem.X(i - 1)));
-            const float vnext = i < o ? volts(c, pk_hi(mem.X(i + 1))) : 0.0f;     /* i == o: only in a filling window, the unwritten slot */
-            const float v = volts(c, val);
-            float adj = 0;
-            if (top) {
-               float edge = v - RT_PEAK_THRESHOLD / t.agc_gain;
-               if (vprev > edge && vnext < edge) adj = -0.5f;
-               else if (vnext > edge && vprev < edge) adj = +0.5f; }
-            else {
-               float edge = v + RT_PEAK_THRESHOLD / t.agc_gain;
-               if (vprev < edge && vnext > edge) adj = -0.5f;
-               else if (vnext < edge && vprev > edge) adj = +0.5f; }
-            const double timenow = row_time(c, row0 + o);
-            const double time = timenow - (double)(((float)(w - left_distance) - adj) * c.sample_deltat);
-            blind = left_distance;
-            return time; }
-         ++left_distance;
-         if (i == o) break; }
-      t.failed = 2;
-      return 0; }
+   /* refine_peak, decoder.c:700-749: window = stream offsets [wstart, o]; v = volts(val).
+      Written for lanes in lock step: a fixed-trip search for the FIRST sample equal to val (no early exit), and one code
+      path for both polarities -- a bottom peak is a top peak of the negated signal (float negation is exact and rounding
+      is symmetric, so  a < b + e  <=>  -a > -b - e  bit for bit). */
+   RT_FHD double refine(int val, float v, bool top, uint32_t wstart, uint32_t o) {
+      uint32_t pos = 0xffffffffu;
+      for (uint32_t i = o + 1; i-- > wstart;) if (pk_hi(mem.X(i)) == val) pos = i;          /* ends on the leftmost match */
+      const int left_distance = (int)(pos - wstart) + 1;
+      if (pos == 0xffffffffu || left_distance >= w || pos == wstart) { t.failed = 2; return 0; }   /* the reference would fatal() */
+      const float sg = top ? 1.0f : -1.0f;
+      const float vprev = sg * volts(c, pk_hi(mem.X(pos - 1)));
+      const float vnext = pos < o ? sg * volts(c, pk_hi(mem.X(pos + 1))) : 0.0f;     /* pos == o: only in a filling window, the unwritten slot */
+      const float edge = sg * v - RT_PEAK_THRESHOLD / t.agc_gain;
+      float adj = 0;
+      if (vprev > edge && vnext < edge) adj = -0.5f;
+      else if (vnext > edge && vprev < edge) adj = +0.5f;
+      const double timenow = row_time(c, row0 + o);
+      blind = left_distance;
+      return timenow - (double)(((float)(w - left_distance) - adj) * c.sample_deltat); }
 
    /* process_*_transition, decoder.c:560-609 */
    RT_FHD void transition(bool top, uint32_t o) {
@@ -258,114 +258,91 @@ struct UnitScan {
       for (int32_t o = -npre; o < 0; ++o) feed(o, (int)plane[(int64_t)row0 + o]);
       quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
       for (uint32_t o = 0; o <= io && o < end; ++o) track(o, sample(o), false);      /* decoder.c:855-861: not looked at yet */
-      cand = false; j = 0; n = 0; g = PK_NEG; fillblk = true; b = io + 1;
-      done = b >= end;
-      if (!done) {
+      j = 0; g = hbk = PK_NEG; fillblk = true; pre = true; o = b = io + 1; hp = 0; hc = w + 1;
+      st = b >= end ? ST_DONE : ST_RUN;
+      if (st == ST_RUN) {
          const int x0 = sample(io);
          m = x0; lvw = pk(x0);
          t.t_lastpeak = row_time(c, row0 + io);
-         mem.X(io) = pk(x0);
          ld = b < (uint32_t)delay ? b : (b - (uint32_t)delay) / 8 * 8 + (uint32_t)delay;
-         n = end - b < (uint32_t)w ? (int)(end - b) : w;
-         ensure(b + (uint32_t)n);
-         mem.X(io) = pk(x0);                                       /* the loader may have written offsets below b */
-         /* the window of the filling phase always starts at the first sample: with that sample as "previous block"
-            the steady-state expressions yield max(x0, g) and left = x0 */
-         for (int k = 1; k < w; ++k) mem.setPH(k, pk(x0), pk(x0));
-         mem.setPH(w, mem.X(b), PK_NEG); } }
+         ensure(o + FAST_K + (uint32_t)w);
+         mem.X(io) = pk(x0);                                       /* the loader starts at b (or at the chunk that holds it) */
+         /* the window of the filling phase always starts at the first sample: with that sample as the "previous block"
+            the steady-state expression yields max(x0, g); entry w is the identity (row w-1's window is the block itself) */
+         for (int k = 1; k < w; ++k) mem.H(hp + k) = pk(x0);
+         mem.H(hp + w) = PK_NEG; mem.H(hc + w) = PK_NEG;
+         /* the first block (window still filling) is walked here, once per job, so that step() does not carry its cases */
+         while (fillblk && st != ST_DONE) { step_fill(); if (st == ST_PEND) handle(); }
+         if (st == ST_RUN) ensure(o + FAST_K + (uint32_t)w); } }
 
-/* the window update shared by all row loops: new sample in, exact max S, lazily refreshed minimum m (decoder.c:753-775) */
-#define RT_ROW_CORE(o_)                                                                             \
-         const uint32_t xw = mem.X(o_);                                                              \
-         const pair32 ph = mem.PH(j + 1);                                                            \
-         g = vmax2(g, xw);                                                                           \
-         const uint32_t sw = vmax2(g, ph.y);                                                         \
-         const int S = pk_hi(sw);
+   /* move to the next row; at a block boundary the block just finished becomes the "previous block" */
+   RT_FHD void step_pos() {
+      ++o;
+      if (++j == w) { j = 0; b += (uint32_t)w; g = hbk = PK_NEG; const int x = hp; hp = hc; hc = x; fillblk = false; }
+      if (o >= end) st = ST_DONE; }
 
-   /* rows of the current block from j on, until a candidate row (cand = true, j stays on it) or the block is done */
-   RT_FHD void search() {
-      cand = false;
-      if (fillblk) { search_fill(); return; }
-      const uint32_t b_ = b;
-      for (; blind && j < n; ++j, --blind) {                      /* decoder.c:778: blind until the last peak has left the window */
-         RT_ROW_CORE(b_ + (uint32_t)j)
-         const int lv = pk_hi(lvw);
-         if (lv >= S || lv == m) m = pk_min(sw);
-         lvw = ph.x; }
-      if (em.n != 0) {
-         for (; j < n; ++j) {
-            RT_ROW_CORE(b_ + (uint32_t)j)
-            const int lv = pk_hi(lvw);
-            if (lv >= S || lv == m) m = pk_min(sw);               /* the rescan of decoder.c:767-775 */
-            lvw = ph.x;
-            const uint32_t xy = vmax2(ph.x, xw);                  /* (max(left,right), ~min(left,right)) */
-            if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { cand = true; return; } } }
-      else {
-         for (; j < n; ++j) {
-            RT_ROW_CORE(b_ + (uint32_t)j)
-            const int lv = pk_hi(lvw);
-            const bool A = lv >= S;
-            if (A || lv == m) m = pk_min(sw);
-            lvw = ph.x;
-            const uint32_t xy = vmax2(ph.x, xw);
-            if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { cand = true; candA = A; return; }
-            track(b_ + (uint32_t)j, pk_hi(xw), A); } } }
+   /* one row.  decoder.c:753-775 (window update, exact max S, lazily refreshed minimum m), :778 (blind countdown), and the
+      integer pre-filter of the shape tests :790-803 */
+   RT_FHD void step() {
+      const uint32_t xw = mem.X(o);
+      const uint32_t xlw = mem.X(o - (uint32_t)w + 1u);           /* the window's left edge */
+      g = vmax2(g, xw);
+      const uint32_t sw = vmax2(g, mem.H(hp + j + 1));
+      const int S = pk_hi(sw);
+      const int lv = pk_hi(lvw);
+      const bool A = lv >= S;                                     /* leaving == max(maxv, v_now)  <=>  leaving >= S */
+      if (A || lv == m) m = pk_min(sw);                           /* the rescan of decoder.c:767-775 */
+      lvw = xlw;
+      const int kb = w - 1 - j;                                   /* backward pass of this block, one position per row */
+      if (kb >= 1) { hbk = vmax2(hbk, mem.X(o + (uint32_t)(kb - j))); mem.H(hc + kb) = hbk; }   /* block start + kb */
+      if (blind) { --blind; step_pos(); return; }
+      const uint32_t xy = vmax2(xlw, xw);                         /* (max(left,right), ~min(left,right)) */
+      if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { st = ST_PEND; candA = A; return; }
+      if (pre) track(o, pk_hi(xw), A);
+      step_pos(); }
 
    /* the same for the block right after the track's first sample, whose window is still filling for j < w-1 */
-   RT_FHD void search_fill() {
-      for (; j < n; ++j) {
-         const uint32_t o = b + (uint32_t)j;
-         RT_ROW_CORE(o)
-         const bool full = j == w - 1;
-         const int lv = full ? pk_hi(lvw) : 0;                    /* decoder.c:754: old_left stays 0 until the window is full */
-         const bool A = full ? lv >= S : S == 0;
-         if (A || lv == m) m = pk_min(sw);
-         lvw = ph.x;
-         if (blind) { --blind; continue; }
-         const uint32_t xy = vmax2(ph.x, xw);
-         if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { cand = true; candA = full && A; return; }
-         if (em.n == 0) track(o, pk_hi(xw), full && A); } }
-
-   /* the exact tests of decoder.c:790-803 at the candidate row b+j */
-   RT_FHD void handle() {
-      const uint32_t o = b + (uint32_t)j;
+   RT_FHD void step_fill() {
       const uint32_t xw = mem.X(o);
-      const pair32 ph = mem.PH(j + 1);
-      const uint32_t sw = vmax2(g, ph.y);
+      const bool full = j == w - 1;                               /* the window holds `width` samples */
+      const uint32_t xlw = mem.X(full ? o - (uint32_t)w + 1u : io);
+      g = vmax2(g, xw);
+      const uint32_t sw = vmax2(g, mem.H(hp + j + 1));
       const int S = pk_hi(sw);
+      const int lv = full ? pk_hi(lvw) : 0;                       /* decoder.c:754: old_left stays 0 until the window is full */
+      const bool A = full ? lv >= S : S == 0;
+      if (A || lv == m) m = pk_min(sw);
+      lvw = xlw;
+      const int kb = w - 1 - j;
+      if (kb >= 1) { hbk = vmax2(hbk, mem.X(b + (uint32_t)kb)); mem.H(hc + kb) = hbk; }
+      if (blind) { --blind; step_pos(); return; }
+      const uint32_t xy = vmax2(xlw, xw);
+      if (S - pk_hi(xy) >= T || pk_min(xy) - m >= T) { st = ST_PEND; candA = full && A; return; }
+      if (pre) track(o, pk_hi(xw), full && A);
+      step_pos(); }
+
+   /* the exact tests of decoder.c:790-803 at the candidate row o, then move on */
+   RT_FHD void handle() {
+      const uint32_t xw = mem.X(o);
       const bool full = !fillblk || j == w - 1;
       const uint32_t wstart = full ? o - (uint32_t)w + 1u : io;
-      const float vl = volts(c, pk_hi(ph.x)), vr = volts(c, pk_hi(xw));
+      const uint32_t xlw = mem.X(wstart);
+      const int S = pk_hi(vmax2(g, mem.H(hp + j + 1)));
+      const float vl = volts(c, pk_hi(xlw)), vr = volts(c, pk_hi(xw));
       const float maxv = volts(c, S), minv = volts(c, m);
-      bool fired = false;
-      if (maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin)) {
-         if (em.n == 0) commit();
-         t.v_top = maxv;
-         t.t_top = refine(S, true, wstart, o);
-         transition(true, o);
-         fired = true; }
-      else if (minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin)) {
-         if (em.n == 0) commit();
-         t.v_bot = minv;
-         t.t_bot = refine(m, false, wstart, o);
-         transition(false, o);
-         fired = true; }
-      if (!fired && em.n == 0) track(o, pk_hi(xw), candA);
-      cand = false; ++j; }
-
-   /* the current block is done: prepare the next one, or finish the unit */
-   RT_FHD void advance() {
-      if (n == w) {                                               /* this block becomes the "previous block" */
-         uint32_t h = PK_NEG;
-         for (int k = w - 1; k >= 1; --k) { const uint32_t x = mem.X(b + (uint32_t)k); h = vmax2(h, x); mem.setPH(k, x, h); } }
-      b += (uint32_t)w; fillblk = false; j = 0; g = PK_NEG;
-      if (b >= end) { done = true; n = 0; return; }
-      n = end - b < (uint32_t)w ? (int)(end - b) : w;
-      ensure(b + (uint32_t)n);
-      mem.setPH(w, mem.X(b), PK_NEG); }
+      const bool top = maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
+      const bool bot = !top && minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
+      if (top || bot) {
+         if (pre) { commit(); pre = false; }
+         const double tp = refine(top ? S : m, top ? maxv : minv, top, wstart, o);
+         if (top) { t.v_top = maxv; t.t_top = tp; } else { t.v_bot = minv; t.t_bot = tp; }
+         transition(top, o); }
+      else if (pre) track(o, pk_hi(xw), candA);
+      st = ST_RUN;
+      step_pos(); }
 
    RT_FHD void finish(TrkMeta &meta) {
-      if (em.n == 0) commit();
+      if (pre) commit();
       meta.first_event_row = em.first_row;
       meta.sync_row = sync_row == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_row;
       meta.last_loud_row = loud_at_sync == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_at_sync);
@@ -374,25 +351,22 @@ struct UnitScan {
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
       meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = 0; } };
-#undef RT_ROW_CORE
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through a list of (unit, track) jobs.  `Jobs` provides
  *   bool next(UnitScan&)   start the lane's next job, false if there is none
  *   void done(UnitScan&)   the lane's job is finished (store its TrkMeta)
- * and `any(pred)` is the warp vote (identity on the host).  The votes keep the lanes converged: all lanes search,
- * then the lanes that stopped on a candidate row handle it TOGETHER, then all lanes move to their next block together. */
+ * and `count(pred)` is the warp vote popc(ballot(pred)) (0/1 on the host).  Between two votes every running lane walks up
+ * to FAST_K rows of ITS job; a lane that stops on a candidate row waits for the end of the batch, then all waiting lanes run
+ * the exact tests TOGETHER (tests + refine_peak + AGC + event store cost ~10 row steps, so they must not run for one lane
+ * at a time); then finished lanes pick their next job and every lane refills its sample ring. */
 template <class Scan, class Jobs, class Vote>
-RT_FHD void drive(Scan &us, Jobs &jobs, Vote any) {
+RT_FHD void drive(Scan &us, Jobs &jobs, Vote count) {
    bool active = jobs.next(us);
-   while (any(active)) {
-      const bool more = active && !us.done && us.j < us.n;
-      if (any(more)) {
-         if (more) us.search();
-         const bool cnd = more && us.cand;
-         if (any(cnd)) { if (cnd) us.handle(); }
-         continue; }
-      if (active) {
-         if (!us.done) us.advance();
-         if (us.done) { jobs.done(us); active = jobs.next(us); } } } }
+   while (count(active)) {
+      if (active && us.st == ST_RUN)
+         for (int k = 0; k < FAST_K; ++k) { us.step(); if (us.st != ST_RUN) break; }
+      if (count(active && us.st == ST_PEND)) { if (active && us.st == ST_PEND) us.handle(); }
+      if (active && us.st == ST_DONE) { jobs.done(us); active = jobs.next(us); }
+      if (active && us.st == ST_RUN) us.ensure(us.o + FAST_K + (uint32_t)us.w); } }
 
 }  // namespace rtfast

@@ -31,7 +31,7 @@ struct HostJobs {
       us.begin(planes + (size_t)k * plane_stride, row0, row_end, k, em, thr);
       return true; }
    template <class Scan> void done(Scan &us) { us.finish(meta[k]); counts[k] = us.em.n; ++k; } };
-struct HostAny { bool operator()(bool p) const { return p; } };
+struct HostCount { int operator()(bool p) const { return p ? 1 : 0; } };
 
 /* planes: [ntrks][plane_stride] int16 (track-major, >= 16 readable rows past row_end).  Scans every track of the
  * unit [row0, row_end) from a fresh RT_RESET_FULL; events of track k go to out[k*cap ...], counts[k] = events produced
@@ -44,14 +44,11 @@ extern "C" int fast_host_scan_unit(const int16_t *planes, uint64_t plane_stride,
    const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE) && !dc.invert && !dc.differentiate
                          && !dc.density && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
    if (!eligible) return RT_ERR_UNSUPPORTED;
-   const uint32_t ring = rtfast::ring_size(dc.width);
-   std::vector<uint32_t> scratch(rtfast::scratch_words(dc.width), 0xdeadbeefu);
-   rtfast::LaneMem<1> mem;
-   mem.ph = reinterpret_cast<rtfast::pair32 *>(scratch.data()); mem.x = scratch.data() + 2 * (dc.width + 1);
-   mem.ht = mem.x + ring; mem.mask = ring - 1;
+   std::vector<uint32_t> scratch(rtfast::scratch_words(dc.width), 0x7fff8000u);   /* poison: the largest sample and the smallest complement */
+   rtfast::LaneMem<1> mem = rtfast::lane_mem<1>(scratch.data(), dc.width);
    HostJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0};
    rtfast::UnitScan<1, HostEmit> us(dc, mem);
-   rtfast::drive(us, jobs, HostAny());
+   rtfast::drive(us, jobs, HostCount());
    return RT_OK; }
 
 extern "C" int fast_host_meta_size(void) { return (int)sizeof(TrkMeta); }
