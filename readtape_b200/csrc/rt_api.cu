@@ -238,7 +238,9 @@ static int cfg_check(const rt_tape *t, const rt_scan_cfg *cfg) {
    return RT_OK; }
 
 static void cfg_to_dev(const rt_tape *t, const rt_scan_cfg *cfg, DevCfg *d) {
-   rtcfg::to_dev(t->desc, t->planes, t->plane_stride, t->nrows_valid, cfg, d); }
+   rtcfg::to_dev(t->desc, t->planes, t->plane_stride, t->nrows_valid, cfg, d);
+   const char *skip = getenv("RT_FAST_SKIP");                       /* RT_FAST_SKIP=0: the fast path walks every row (tests) */
+   if (!(skip && skip[0] == '0')) { d->gmm = reinterpret_cast<const uint32_t *>(t->gmm); d->ngran_cap = t->ngran_cap; } }
 
 /* k-way merge of per-track event streams into (row, trk) order */
 struct Cursor { const rt_event *p, *end; };

@@ -56,6 +56,8 @@ struct DevCfg {
    int32_t  invert, differentiate, density, find_zeros;
    rt_parms p;
    int32_t  skew[RT_MAXTRKS];
+   const uint32_t *gmm;           /* [ntrks][ngran_cap] packed (min | max<<16) of every 32-row granule; null: no gap skipping */
+   uint64_t ngran_cap;
 };
 
 /* Per-track detector + feedback state: the device mirror of the parts of struct trkstate_t

@@ -69,7 +69,9 @@ RT_FHD float volts(const DevCfg &c, int x) { return (float)x / 32767 * c.maxvolt
 /* Lanes run FAST_K rows between two maintenance points (loader, job switch); a lane that meets a candidate row waits
    for the handler, which runs when FAST_NPEND lanes of the warp are waiting or at the maintenance point. */
 #define FAST_K      16
-#define FAST_NPEND  8
+/* gap skipping (try_skip): granules examined per attempt, and the quiet rows left in front of the first loud granule */
+#define FAST_SKIP_LOOKAHEAD 512
+#define FAST_M_UNKNOWN      (1 << 20)
 
 /* ring size for a window width: holds offsets [o-w+1, o+FAST_K+w+7] */
 RT_FHD uint32_t ring_size(int w) { uint32_t r = 32; while (r < (uint32_t)(2 * w + FAST_K + 8)) r <<= 1; return r; }
@@ -135,6 +137,9 @@ struct UnitScan {
    uint32_t o, b, g, hbk; int j, hp, hc, st, fillblk, candA, pre;
    /* loader */
    uint32_t ld;
+   /* gap skipping: this track's granule min/max map (null = off), next offset at which an attempt is worthwhile, and the
+      offset by which the lazily kept minimum must have been re-established after a jump (0 = not pending) */
+   const uint32_t *gm; uint32_t next_try, munk_until, nskipped;
    /* proof data, kept lazily (offsets relative to row0; OFF_NONE = none): see track() */
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
    int32_t sync_row, loud_at_sync, sync_first, sync_early, loud_early; bool early_frozen; uint32_t sf_from; uint64_t quiet_from;
@@ -238,6 +243,7 @@ struct UnitScan {
    /* start the scan of unit rows [row0_, row_end) of track trk_ from a fresh RT_RESET_FULL */
    RT_FHD void begin(const int16_t *plane_, uint64_t row0_, uint64_t row_end, int trk_, Emit em_, int quiet_thr_lsb) {
       plane = plane_; row0 = row0_; end = (uint32_t)(row_end - row0_); trk = trk_; delay = c.skew[trk_]; em = em_;
+      gm = c.gmm ? c.gmm + (size_t)trk_ * c.ngran_cap : nullptr; next_try = 0; munk_until = 0; nskipped = 0;
       const bool tz = row_time(c, row0) == 0.0;
       io = (uint32_t)trk + (tz ? 1u : 0u);
       /* reset_full (scan_generic.cuh) restricted to the members of FastState */
@@ -341,6 +347,55 @@ struct UnitScan {
       st = ST_RUN;
       step_pos(); }
 
+   /* Gap skipping, called between two batches.  Let thr be the integer bound T of required_rise (and, before the first
+      event, also the loudness threshold of the proof).  If the raw samples of rows [A, B) span less than thr, no row whose
+      window lies inside [A, B) can pass the pre-filter:  S - max(l,r) <= max - min  and  min(l,r) - m <= max - min  because
+      the lazily kept minimum m is always the value of a sample inside the window.  Such rows change nothing but the window
+      state, so the lane jumps over them: it restarts its block structure `width` rows before the target (one warm-up block
+      with the tests off rebuilds ring, g and the suffix maxima), and marks m unknown; m is exact again at the first row
+      where the window maximum leaves (A-row) -- the jump stops early enough for that to happen inside the quiet stretch,
+      and a unit whose m is still unknown after the margin is flagged failed (the host then uses the exact scan).
+      The span test uses the 32-row granule min/max map of k_ingest.cu. */
+   RT_FHD void try_skip() {
+      if (!gm || o < next_try || o < (uint32_t)(delay + w) || fillblk) return;
+      if (pre && sf_from != 0xffffffffu) return;                  /* sync_first (unit chaining) wants the FIRST canonical row: find it first */
+      if (munk_until) {
+         if (m != FAST_M_UNKNOWN) munk_until = 0;
+         else if (o >= munk_until) { t.failed = 4; munk_until = 0; }
+         else return; }
+      const int thr = pre && qthr < T ? qthr : T;
+      const int margin = 12 * w + 32;
+      next_try = o + 64;
+      if (thr < 8) return;
+      const uint64_t first_raw = row0 + o - (uint32_t)delay - (uint32_t)(w - 1);    /* earliest raw row in the window of row o */
+      const uint64_t gi = first_raw / RT_GRAN, gend = (row0 + end - (uint32_t)delay + RT_GRAN - 1) / RT_GRAN;
+      const uint64_t gmax = gi + FAST_SKIP_LOOKAHEAD < gend ? gi + FAST_SKIP_LOOKAHEAD : gend;
+      int mn = 32767, mx = -32768;
+      uint64_t gq = gi;
+      for (; gq < gmax; ++gq) {
+         const uint32_t v = gm[gq];
+         const int a = (int)(int16_t)(uint16_t)(v & 0xffffu), bb = (int)(int16_t)(uint16_t)(v >> 16);
+         const int nmn = a < mn ? a : mn, nmx = bb > mx ? bb : mx;
+         if (nmx - nmn >= thr) break;
+         mn = nmn; mx = nmx; }
+      /* raw rows [32*gi, 32*gq) are quiet: stream rows < oq cannot fire */
+      int64_t oq = (int64_t)(gq * RT_GRAN) - (int64_t)row0 + delay;
+      const bool to_end = oq >= (int64_t)end;
+      if (to_end) oq = end;
+      const int64_t target = to_end ? oq : oq - margin;
+      if (target < (int64_t)o + w + 32) return;
+      const uint32_t jump = (uint32_t)target - o;
+      const int blind_after = (uint32_t)blind > jump ? blind - (int)jump : 0;
+      if (pre) { if (mn < qmin) qmin = mn; if (mx > qmax) qmax = mx; }      /* the loudness tracker stays conservative */
+      nskipped += jump - (to_end ? 0u : (uint32_t)w);
+      if (to_end) { o = end; st = ST_DONE; return; }
+      o = b = (uint32_t)target - (uint32_t)w; j = 0; g = hbk = PK_NEG;
+      ld = (o - (uint32_t)delay) / 8 * 8 + (uint32_t)delay;
+      ensure(o + FAST_K + 2u * (uint32_t)w);
+      blind = w;
+      for (int i = 0; i < w; ++i) step();                         /* warm-up block: tests off */
+      blind = blind_after; m = FAST_M_UNKNOWN; munk_until = (uint32_t)target + (uint32_t)margin; next_try = o; }
+
    RT_FHD void finish(TrkMeta &meta) {
       if (pre) commit();
       meta.first_event_row = em.first_row;
@@ -350,7 +405,7 @@ struct UnitScan {
       meta.quiet_from = quiet_from;
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
-      meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = 0; } };
+      meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = nskipped; } };   /* pad: rows jumped over (diagnostics) */
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through a list of (unit, track) jobs.  `Jobs` provides
  *   bool next(UnitScan&)   start the lane's next job, false if there is none
@@ -366,6 +421,7 @@ RT_FHD void drive(Scan &us, Jobs &jobs, Vote count) {
       if (active && us.st == ST_RUN)
          for (int k = 0; k < FAST_K; ++k) { us.step(); if (us.st != ST_RUN) break; }
       if (count(active && us.st == ST_PEND)) { if (active && us.st == ST_PEND) us.handle(); }
+      if (active && us.st == ST_RUN) us.try_skip();
       if (active && us.st == ST_DONE) { jobs.done(us); active = jobs.next(us); }
       if (active && us.st == ST_RUN) us.ensure(us.o + FAST_K + (uint32_t)us.w); } }
 

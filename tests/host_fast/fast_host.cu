@@ -38,9 +38,19 @@ struct HostCount { int operator()(bool p) const { return p ? 1 : 0; } };
  * (may exceed cap), meta[k] = proof data.  Returns 0, or -4 if the configuration is not eligible for the fast path. */
 extern "C" int fast_host_scan_unit(const int16_t *planes, uint64_t plane_stride, uint64_t nrows, const rt_tape_desc *desc,
                                    const rt_scan_cfg *cfg, uint64_t row0, uint64_t row_end, rt_event *out, uint32_t cap,
-                                   uint32_t *counts, TrkMeta *meta) {
+                                   uint32_t *counts, TrkMeta *meta, int skip_gaps) {
    DevCfg dc;
    rtcfg::to_dev(*desc, planes, plane_stride, nrows, cfg, &dc);
+   std::vector<uint32_t> gmm;                                      /* the granule min/max map k_ingest.cu builds on the device */
+   if (skip_gaps) {
+      const uint64_t ngran = (nrows + RT_GRAN - 1) / RT_GRAN + 1;
+      gmm.assign((size_t)ngran * dc.ntrks, 0);
+      for (int k = 0; k < dc.ntrks; ++k)
+         for (uint64_t g = 0; g * RT_GRAN < nrows; ++g) {
+            int mn = 32767, mx = -32768;
+            for (uint64_t r = g * RT_GRAN; r < (g + 1) * RT_GRAN && r < nrows; ++r) { int v = planes[(size_t)k * plane_stride + r]; if (v < mn) mn = v; if (v > mx) mx = v; }
+            gmm[(size_t)k * ngran + g] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); }
+      dc.gmm = gmm.data(); dc.ngran_cap = ngran; }
    const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE) && !dc.invert && !dc.differentiate
                          && !dc.density && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
    if (!eligible) return RT_ERR_UNSUPPORTED;

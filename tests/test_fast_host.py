@@ -25,7 +25,7 @@ def fast_host():
     L = C.CDLL(HOST_LIB)
     L.fast_host_scan_unit.restype = C.c_int
     L.fast_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg),
-                                      C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+                                      C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
     return L
 
 
@@ -41,18 +41,20 @@ def make_planes(rows, desc):
     return planes, stride
 
 
-def fast_scan(L, planes, stride, nrows, desc, cfg, row0, row_end, cap=1 << 16):
+def fast_scan(L, planes, stride, nrows, desc, cfg, row0, row_end, cap=1 << 16, skip=1):
     nt = desc.ntrks
     out = np.zeros((nt, cap), dtype=abi.EVENT_DTYPE)
     counts = np.zeros(nt, dtype=np.uint32)
     meta = np.zeros((nt, L.fast_host_meta_size()), dtype=np.uint8)
     rc = L.fast_host_scan_unit(planes.ctypes.data, stride, nrows, C.byref(desc), C.byref(cfg), row0, row_end,
-                               out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data)
+                               out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, skip)
     if rc != 0:
         return None
     assert counts.max(initial=0) <= cap
     ev = np.concatenate([out[k, :counts[k]] for k in range(nt)])
     order = np.lexsort((ev["trk"], ev["row"]))
+    fast_scan.failed = [int(np.frombuffer(meta[k].tobytes(), dtype='<u4')[-2]) for k in range(nt)]
+    fast_scan.skipped = [int(np.frombuffer(meta[k].tobytes(), dtype='<u4')[-1]) for k in range(nt)]
     return ev[order]
 
 
@@ -69,7 +71,7 @@ def test_fast_path_reproduces_reference_events(name, fast_host):
     if len(end):
         nrows = int(end[0])
     planes, stride = make_planes(rows[:nrows], desc)
-    done = 0
+    done = skipped = walked = 0
     for seg in segs:
         if seg.reset_kind != abi.RT_RESET_FULL or (seg.flags & abi.RT_F_DENSITY_DETECT):
             continue
@@ -83,8 +85,14 @@ def test_fast_path_reproduces_reference_events(name, fast_host):
             canon = canon[canon["row"] <= seg.stop_row]
         assert evlog.matches_fixture(seg, canon), \
             f"{name}: segment at row {seg.row} parmset {seg.parmset}: {len(canon)} events, reference {seg.nevents}"
+        assert not any(fast_scan.failed), f"{name}: segment at row {seg.row}: failed flags {fast_scan.failed}"
+        skipped += sum(fast_scan.skipped); walked += (min(stop, nrows) - seg.row) * desc.ntrks
+        # and with gap skipping off: the same events
+        ev2 = fast_scan(fast_host, planes, stride, nrows, desc, cfg, seg.row, min(stop, nrows), skip=0)
+        assert ev2.tobytes() == ev.tobytes() and not any(fast_scan.skipped)
         done += 1
     assert done > 0
+    print(f"{name}: {done} segments, {skipped} of {walked} track-rows jumped over ({100.0 * skipped / max(walked, 1):.1f} %)")
 
 
 def test_fast_path_equals_oracle_on_synthetic(fast_host, oracle_lib):
@@ -100,6 +108,7 @@ def test_fast_path_equals_oracle_on_synthetic(fast_host, oracle_lib):
                 sc = tape.scan(cfg); sc.reset(abi.RT_RESET_FULL, row0)
                 want, _ = sc.run(rows.shape[0]); sc.end()
                 got = fast_scan(fast_host, planes, stride, rows.shape[0], desc, cfg, row0, rows.shape[0])
+                assert not any(fast_scan.failed) and sum(fast_scan.skipped) > 0.3 * rows.shape[0] * 9, (fast_scan.failed, fast_scan.skipped)
                 a, b = evlog.to_canon(got), evlog.to_canon(want)
                 if a.tobytes() != b.tobytes():
                     k = evlog._first_diff(a, b)

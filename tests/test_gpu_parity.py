@@ -161,7 +161,8 @@ def test_fast_kernel_equals_generic_kernel_on_every_unit(name, cuda_lib):
     for key in keys:
         cfg = evlog.cfg_for([s for s in full if (s.parmset, tuple(s.skew)) == key][0])
         res = []
-        for force in ("generic", None):
+        for force, skip in (("generic", "1"), (None, "0"), (None, "1")):
+            os.environ["RT_FAST_SKIP"] = skip
             if force:
                 os.environ["RT_SCAN"] = force
             else:
@@ -174,12 +175,20 @@ def test_fast_kernel_equals_generic_kernel_on_every_unit(name, cuda_lib):
                 evs.append(None if r is None else (r[0].tobytes(), r[1]))
             res.append((units, evs, bulk.stats().events))
             bulk.free()
-        os.environ.pop("RT_SCAN", None)
-        (ug, eg, ng), (uf, ef, nf) = res
-        assert len(ug) == len(uf) and ng == nf, (len(ug), len(uf), ng, nf)
-        for a, b, x, y in zip(ug, uf, eg, ef):
+        os.environ.pop("RT_SCAN", None); os.environ.pop("RT_FAST_SKIP", None)
+        (ug, eg, ng), (uf, ef, nf), (us, es, ns) = res
+        assert len(ug) == len(uf) == len(us) and ng == nf == ns, (len(ug), len(uf), len(us), ng, nf, ns)
+        for a, b, x, y in zip(ug, uf, eg, ef):                     # walking every row: identical in everything
             assert a == b, f"proof data differ for unit {a['unit_index']} [{a['row0']},{a['row_end']}): generic {a} fast {b}"
             assert x == y, f"events differ for unit {a['unit_index']} [{a['row0']},{a['row_end']})"
+        for a, b in zip(ug, us):                                   # jumping over quiet stretches: same events, sound proof data
+            assert not any(b["failed"]), f"unit {b['unit_index']}: failed flags {b['failed']}"
+            for key in ("row0", "row_end", "first_event_row", "nevents", "quiet_from"):
+                assert a[key] == b[key], (key, a, b)
+        n_same = sum(1 for x, y in zip(eg, es) if x == y)
+        assert n_same >= 0.9 * len(eg), f"only {n_same} of {len(eg)} unit lookups agree with gap skipping on"
+        for x, y in zip(eg, es):
+            assert y is None or x is None or x == y, "a lookup that hits must return the same events"
         nunits += len(ug)
     tape.close()
     assert nunits > 0
