@@ -17,28 +17,32 @@ using namespace rtfast;
 
 struct DevJobs {
    const DevCfg &c; const UnitDesc *units; TrkMeta *meta; rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
-   int quiet_thr_lsb; unsigned long long *rows_scanned; uint64_t f, total, stride; uint64_t cur;
+   int quiet_thr_lsb; unsigned long long *counters /* [0] rows, [1] events, [2] next job group */; uint64_t total; uint64_t cur; bool exhausted;
    template <class Scan>
-   __device__ bool next(Scan &us) {
-      for (;;) {
-         if (f >= total) return false;
-         cur = f; f += stride;
-         const uint32_t u = (uint32_t)(cur / c.ntrks); const int trk = (int)(cur % c.ntrks);
-         const UnitDesc ud = units[u];
-         if (ud.row_end - ud.row0 > (1ull << 30)) {         /* offsets are 32-bit: leave such a unit to the exact scan */
-            TrkMeta m;
-            m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
-            m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
-            meta[cur] = m;
-            continue; }
-         PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
-         us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
-         return true; } }
+   __device__ bool next(Scan &us) {                           /* warp-collective: groups of 32 consecutive jobs, fetched dynamically */
+      const int lane = threadIdx.x & 31;
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&counters[2], 32ull);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      exhausted = base >= total;
+      cur = base + (unsigned)lane;
+      if (cur >= total) return false;
+      const uint32_t u = (uint32_t)(cur / c.ntrks); const int trk = (int)(cur % c.ntrks);
+      const UnitDesc ud = units[u];
+      if (ud.row_end - ud.row0 > (1ull << 30)) {            /* offsets are 32-bit: leave such a unit to the exact scan */
+         TrkMeta m;
+         m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
+         m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
+         meta[cur] = m;
+         return false; }
+      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+      us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
+      return true; }
    template <class Scan>
    __device__ void done(Scan &us) {
       TrkMeta m; us.finish(m); meta[cur] = m;
-      atomicAdd(&rows_scanned[0], (unsigned long long)us.end);
-      if (us.em.n) atomicAdd(&rows_scanned[1], (unsigned long long)us.em.n); } };
+      atomicAdd(&counters[0], (unsigned long long)us.end);
+      if (us.em.n) atomicAdd(&counters[1], (unsigned long long)us.em.n); } };
 
 struct WarpCount { __device__ int operator()(bool p) const { return __popc(__ballot_sync(0xffffffffu, p)); } };
 
@@ -49,8 +53,7 @@ k_units_fast(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta 
    extern __shared__ __align__(16) uint32_t fast_smem[];
    LaneMem<FAST_THREADS> mem = lane_mem<FAST_THREADS>(fast_smem + threadIdx.x, c.width);      /* [entry][thread] layout */
    const uint64_t total = (uint64_t)(*nunits_p) * (uint64_t)c.ntrks;
-   DevJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned,
-                (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, total, (uint64_t)gridDim.x * blockDim.x, 0};
+   DevJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned, total, 0, false};
    UnitScan<FAST_THREADS, PoolEmit> us(c, mem);
    drive(us, jobs, WarpCount()); }
 

@@ -451,7 +451,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
    CUB(cudaMallocAsync(&d_bitmap, words * 4, t->stream)); CUB(cudaMallocAsync(&d_flags, words * 4, t->stream)); CUB(cudaMallocAsync(&d_blockcount, nblocks * 4, t->stream));
    CUB(cudaMallocAsync(&d_nunits, 4, t->stream)); CUB(cudaMallocAsync(&d_units_tmp, (size_t)units_cap * sizeof(UnitDesc), t->stream));
-   CUB(cudaMallocAsync(&d_counters, 16, t->stream)); CUB(cudaMallocAsync(&d_cursor, 4, t->stream));
+   CUB(cudaMallocAsync(&d_counters, 32, t->stream)); CUB(cudaMallocAsync(&d_cursor, 4, t->stream));
    lap("scratch alloc");
    b->stats.rows = nrows; b->stats.ms_preprocess = t->ms_ingest;
    for (uint32_t ci = 0; ci < ncfgs; ++ci) {
@@ -513,7 +513,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
                   CUB(cudaMalloc(&bc.d_pool, (size_t)bc.pool_chunks * RT_EVC * sizeof(rt_event)));
                   CUB(cudaMalloc(&bc.d_chunk_next, (size_t)bc.pool_chunks * 4)); } }
             CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
-            CUB(cudaMemsetAsync(d_counters, 0, 16, t->stream));
+            CUB(cudaMemsetAsync(d_counters, 0, 32, t->stream));
             CUB(cudaEventRecord(ev[2], t->stream));
             const uint64_t threads = (uint64_t)nunits * nt;
             if (use_fast) CUB(launch_units_fast(dc, bc.d_units, d_nunits, nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks,

@@ -408,7 +408,8 @@ struct UnitScan {
       meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = nskipped; } };   /* pad: rows jumped over (diagnostics) */
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through a list of (unit, track) jobs.  `Jobs` provides
- *   bool next(UnitScan&)   start the lane's next job, false if there is none
+ *   bool next(UnitScan&)   start the lane's next job, false if there is none (called by all lanes of the warp together)
+ *   bool exhausted         set by next() when the job list has run out (the same for all lanes)
  *   void done(UnitScan&)   the lane's job is finished (store its TrkMeta)
  * and `count(pred)` is the warp vote popc(ballot(pred)) (0/1 on the host).  Between two votes every running lane walks up
  * to FAST_K rows of ITS job; a lane that stops on a candidate row waits for the end of the batch, then all waiting lanes run
@@ -416,13 +417,17 @@ struct UnitScan {
  * at a time); then finished lanes pick their next job and every lane refills its sample ring. */
 template <class Scan, class Jobs, class Vote>
 RT_FHD void drive(Scan &us, Jobs &jobs, Vote count) {
-   bool active = jobs.next(us);
-   while (count(active)) {
-      if (active && us.st == ST_RUN)
-         for (int k = 0; k < FAST_K; ++k) { us.step(); if (us.st != ST_RUN) break; }
-      if (count(active && us.st == ST_PEND)) { if (active && us.st == ST_PEND) us.handle(); }
-      if (active && us.st == ST_RUN) us.try_skip();
-      if (active && us.st == ST_DONE) { jobs.done(us); active = jobs.next(us); }
-      if (active && us.st == ST_RUN) us.ensure(us.o + FAST_K + (uint32_t)us.w); } }
+   for (;;) {
+      /* the warp takes its next GROUP of jobs (32 consecutive (unit, track) pairs = the tracks of 3-4 neighbouring units) only when
+         all its lanes are idle: the lanes then meet blocks and gaps together -- large handler batches, converged jumps */
+      bool active = jobs.next(us);
+      if (jobs.exhausted) return;
+      while (count(active)) {
+         if (active && us.st == ST_RUN)
+            for (int k = 0; k < FAST_K; ++k) { us.step(); if (us.st != ST_RUN) break; }
+         if (count(active && us.st == ST_PEND)) { if (active && us.st == ST_PEND) us.handle(); }
+         if (active && us.st == ST_RUN) us.try_skip();
+         if (active && us.st == ST_DONE) { jobs.done(us); active = false; }
+         if (active && us.st == ST_RUN) us.ensure(us.o + FAST_K + (uint32_t)us.w); } } }
 
 }  // namespace rtfast

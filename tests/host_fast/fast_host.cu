@@ -24,9 +24,10 @@ struct HostEmit {
 /* the job list of one lane: the tracks of one unit, one after the other */
 struct HostJobs {
    const DevCfg &dc; const int16_t *planes; uint64_t plane_stride, row0, row_end; rt_event *out; uint32_t cap; uint32_t *counts; TrkMeta *meta;
-   int thr, k;
+   int thr, k; bool exhausted;
    template <class Scan> bool next(Scan &us) {
-      if (k >= dc.ntrks) return false;
+      exhausted = k >= dc.ntrks;
+      if (exhausted) return false;
       HostEmit em{out + (size_t)k * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)k};
       us.begin(planes + (size_t)k * plane_stride, row0, row_end, k, em, thr);
       return true; }
@@ -56,7 +57,7 @@ extern "C" int fast_host_scan_unit(const int16_t *planes, uint64_t plane_stride,
    if (!eligible) return RT_ERR_UNSUPPORTED;
    std::vector<uint32_t> scratch(rtfast::scratch_words(dc.width), 0x7fff8000u);   /* poison: the largest sample and the smallest complement */
    rtfast::LaneMem<1> mem = rtfast::lane_mem<1>(scratch.data(), dc.width);
-   HostJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0};
+   HostJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0, false};
    rtfast::UnitScan<1, HostEmit> us(dc, mem);
    rtfast::drive(us, jobs, HostCount());
    return RT_OK; }
