@@ -276,6 +276,14 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         scan_kernel = "k_units_scan (generic)" if os.environ.get("RT_SCAN") == "generic" else "k_units_fast"
+        traffic = None                                            # DRAM bytes of that kernel per launch, from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "summary_r01.json")) as fh:
+                prof = json.load(fh).get(scan_kernel)
+            if prof and prof["rows"] == rows:
+                traffic = prof["dram_read_bytes"] + prof["dram_write_bytes"]
+        except Exception:
+            pass
         alg_bytes = 2.0 * tsamp + 32.0 * events                # 2 B read per track-sample + event bytes
         achieved = alg_bytes / (ms_scan * 1e-3) / 1e9
         ingest_bytes = 4.0 * tsamp                              # K1: 2 B read + 2 B written per track-sample
@@ -287,7 +295,7 @@ def main():
                        "units_per_tape": units, "events_per_tape": events, "super_tile_sha256": synth.tile_sha256(tile)[:16],
                        "parallelism": f"{world} x independent tapes" if world > 1 else "1 GPU"},
             "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_scan,
                          "other_kernels": {"k_ingest_tma": {"ms": ms_ingest, "achieved_GBps": ingest_bytes / (ms_ingest * 1e-3) / 1e9 if ms_ingest else None,
                                                            "frac": (ingest_bytes / (ms_ingest * 1e-3) / 1e9 / peak) if ms_ingest else None},
