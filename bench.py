@@ -13,7 +13,7 @@ A step = one pass of the hot path over the whole tape:
   value : TBIN rows already resident in HBM -> ingest (de-interleave + quiet map) -> unit table ->
           scan kernel -> events in HBM                         [rt_attach_device + rt_bulk_scan]
   e2e   : the same through the C-ABI with HOST buffers: pinned host rows -> H2D -> ... -> events and
-          proof data copied back to pinned host memory         [rt_upload + rt_bulk_scan + rt_bulk_fetch]
+          proof data copied back to pinned host memory         [rt_bulk_scan_host: the three stages overlapped]
 `--impl reference` times the reference's own CPU implementation (oracle/_ref/readtape_ref, the
 unmodified readtape 3.18 binary built by oracle/Makefile) on all host cores, each step a bounded
 sample of the same workload.
@@ -229,10 +229,7 @@ def main():
             hbuf[at:at + n] = tile[:n]
 
         def step_e2e():
-            tape.clear()
-            tape.upload_ptr(hptr, rows)
-            bulk = tape.bulk_scan([cfg])
-            bulk.fetch()
+            bulk = tape.bulk_scan_host(hptr, rows, cfg)           # clear + H2D + ingest + scan + D2H, overlapped
             st = bulk.stats()
             hit = bulk.lookup(0, 0)                       # the user-facing read of the result
             assert hit is not None
@@ -252,7 +249,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             el = float(tt.item())
         e2e = {"value": world * tsamp * ke / el, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-               "d2h_bytes_per_step": int(ste.d2h_bytes), "ms_per_step": 1e3 * el / ke}
+               "d2h_bytes_per_step": int(ste.d2h_bytes), "ms_per_step": 1e3 * el / ke, "segments_streamed": int(ste.pad),
+               "api": "rt_bulk_scan_host (pinned host rows -> events + proof data in pinned host memory) + rt_bulk_lookup"}
         lib.L.rt_host_free(hptr)
 
     # ---- result gather over NCCL: per-rank event counts (the only inter-GPU traffic of this path) ----

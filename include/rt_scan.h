@@ -188,6 +188,10 @@ int  rt_bulk_scan(rt_tape *tape, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bul
 /* rt_bulk_scan() leaves its results in device memory; rt_bulk_fetch() copies them to the host (pinned
  * memory).  The first rt_bulk_lookup()/rt_bulk_unit_info() call does it implicitly. */
 int  rt_bulk_fetch(rt_bulk *bulk);
+/* rt_clear() + rt_upload(rows) + rt_bulk_scan(cfg) + rt_bulk_fetch() in one call with the three stages overlapped: the tape is
+ * scanned segment by segment while it is still being copied (PCIe is the slow stage), and the events of each segment travel
+ * back while the next one arrives.  `rows` should be pinned (rt_host_alloc).  Same results as the separate calls. */
+int  rt_bulk_scan_host(rt_tape *tape, const int16_t *rows, uint64_t nrows, const rt_scan_cfg *cfg, rt_bulk **out);
 /* Events a fresh RT_RESET_FULL scan of configuration `cfg_index` starting at `start_row`
  * would produce, for rows [start_row, start_row + *valid_rows).  RT_MISS if no unit can be
  * proven equivalent (the caller then uses rt_scan_*). */
@@ -221,7 +225,7 @@ typedef struct rt_bulk_stats {
    double   ms_units;        /* device time: unit table construction                         */
    double   ms_scan;         /* device time: scan kernel                                     */
    uint32_t launches;        /* kernels launched by the call                                 */
-   uint32_t pad;
+   uint32_t pad;             /* rt_bulk_scan_host: number of segments streamed, 0 = plain sequence    */
    uint64_t d2h_bytes;       /* bytes rt_bulk_fetch() copied to the host                     */
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);

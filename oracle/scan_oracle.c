@@ -531,6 +531,7 @@ int rt_bulk_lookup(rt_bulk *b, uint32_t c, uint64_t r, const rt_event **e, uint6
 int rt_clear(rt_tape *t) { if (!t) return RT_ERR_ARG; t->nrows = 0; t->cap = 0; return RT_OK; }
 int rt_bulk_fetch(rt_bulk *b) { (void)b; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_unit_info(const rt_bulk *b, uint32_t c, uint64_t r, rt_unit_info *o) { (void)b; (void)c; (void)r; (void)o; return RT_ERR_UNSUPPORTED; }
+int rt_bulk_scan_host(rt_tape *t, const int16_t *r, uint64_t n, const rt_scan_cfg *c, rt_bulk **o) { (void)t; (void)r; (void)n; (void)c; (void)o; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_unit_at(const rt_bulk *b, uint32_t c, uint64_t r, rt_unit_info *o) { (void)b; (void)c; (void)r; (void)o; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *o) { (void)b; (void)o; return RT_ERR_UNSUPPORTED; }
 void rt_bulk_free(rt_bulk *b) { (void)b; }

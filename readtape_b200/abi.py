@@ -69,7 +69,7 @@ assert EVENT_DTYPE.itemsize == 32
 EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_attach_device", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
-           "rt_bulk_scan", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
+           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
            "rt_row_time"]
 
 
@@ -112,6 +112,7 @@ class Lib:
         L.rt_scan_pos.argtypes = [vp]; L.rt_scan_pos.restype = u64
         L.rt_scan_end.argtypes = [vp]; L.rt_scan_end.restype = None
         L.rt_bulk_scan.argtypes = [vp, P(ScanCfg), u32, P(vp)]
+        L.rt_bulk_scan_host.argtypes = [vp, vp, u64, P(ScanCfg), P(vp)]
         L.rt_bulk_lookup.argtypes = [vp, u32, u64, P(vp), P(u64), P(u64)]
         L.rt_bulk_get_stats.argtypes = [vp, P(BulkStats)]
         L.rt_bulk_unit_info.argtypes = [vp, u32, u64, P(UnitInfo)]
@@ -120,7 +121,7 @@ class Lib:
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
         L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
         for fn in ("rt_open", "rt_upload", "rt_attach_device", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
-                   "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_lookup",
+                   "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_lookup",
                    "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_pkww_width"):
             getattr(L, fn).restype = i32
 
@@ -178,6 +179,12 @@ class Tape:
         arr = (ScanCfg * len(cfgs))(*cfgs)
         h = C.c_void_p()
         self.lib.check(self.lib.L.rt_bulk_scan(self.h, arr, len(cfgs), C.byref(h)))
+        return Bulk(self, h)
+
+    def bulk_scan_host(self, host_ptr: int, nrows: int, cfg: ScanCfg) -> "Bulk":
+        """clear + upload + whole-tape scan + fetch, overlapped (rows at `host_ptr`, ideally pinned)"""
+        h = C.c_void_p()
+        self.lib.check(self.lib.L.rt_bulk_scan_host(self.h, host_ptr, nrows, C.byref(cfg), C.byref(h)))
         return Bulk(self, h)
 
     def close(self) -> None:

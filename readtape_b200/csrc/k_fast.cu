@@ -47,12 +47,12 @@ struct DevJobs {
 struct WarpCount { __device__ int operator()(bool p) const { return __popc(__ballot_sync(0xffffffffu, p)); } };
 
 __global__ void __launch_bounds__(FAST_THREADS, 4)
-k_units_fast(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta *meta,
+k_units_fast(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
              rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
              int quiet_thr_lsb, unsigned long long *rows_scanned, uint32_t ring) {
    extern __shared__ __align__(16) uint32_t fast_smem[];
    LaneMem<FAST_THREADS> mem = lane_mem<FAST_THREADS>(fast_smem + threadIdx.x, c.width);      /* [entry][thread] layout */
-   const uint64_t total = (uint64_t)(*nunits_p) * (uint64_t)c.ntrks;
+   const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
    DevJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned, total, 0, false};
    UnitScan<FAST_THREADS, PoolEmit> us(c, mem);
    drive(us, jobs, WarpCount()); }
@@ -61,9 +61,9 @@ bool fast_scan_eligible(const DevCfg &c) {
    return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
           && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH; }
 
-cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, uint32_t nunits_host, TrkMeta *meta, rt_event *pool,
+cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                               uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
-                              unsigned long long *rows_scanned, int sms, cudaStream_t s) {
+                              unsigned long long *rows_scanned, int sms, int max_ctas_per_sm, cudaStream_t s) {
    const uint32_t ring = ring_size(c.width);
    const size_t smem = (size_t)scratch_words(c.width) * FAST_THREADS * sizeof(uint32_t);
    static size_t cfg_smem = 0; static int cfg_per_sm = 0;          /* function attributes: set once per shared-memory size */
@@ -77,10 +77,13 @@ cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, const uint
       if (e != cudaSuccess) return e;
       cfg_smem = smem; }
    int per_sm = cfg_per_sm < 1 ? 1 : cfg_per_sm;
-   const uint64_t threads = (uint64_t)nunits_host * (uint64_t)c.ntrks;
+   if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;       /* leave room for concurrent ingest kernels */
+   const uint64_t threads = (uint64_t)nunits * (uint64_t)c.ntrks;
    uint64_t grid = (threads + FAST_THREADS - 1) / FAST_THREADS;
    const uint64_t resident = (uint64_t)sms * (uint64_t)per_sm;
    if (grid > resident) grid = resident;
    if (grid < 1) grid = 1;
+   e = cudaMemsetAsync(rows_scanned + 2, 0, sizeof(unsigned long long), s);       /* the job-group counter of this launch */
+   if (e != cudaSuccess) return e;
    k_units_fast<<<(unsigned)grid, FAST_THREADS, smem, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, rows_scanned, ring);
    return cudaGetLastError(); }

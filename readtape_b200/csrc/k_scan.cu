@@ -45,10 +45,9 @@ __global__ void k_ctx_scan(DevCfg c, TrkState *st, SkewState *sk, uint64_t row_f
 
 /* ---- speculative whole-tape scan (generic detector code) -------------------------------------- */
 __global__ void __launch_bounds__(128)
-k_units_scan(DevCfg c, const UnitDesc *units, const uint32_t *nunits_p, TrkMeta *meta,
+k_units_scan(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
              rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
              float quiet_thr, int quiet_thr_lsb, unsigned long long *rows_scanned) {
-   const uint32_t nunits = *nunits_p;
    const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
    for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (uint64_t)gridDim.x * blockDim.x) {
       const uint32_t u = (uint32_t)(f / c.ntrks); const int trk = (int)(f % c.ntrks);
@@ -101,7 +100,7 @@ void launch_ctx_scan(const DevCfg &c, TrkState *st, SkewState *sk, uint64_t from
    /* one warp per track would waste 31 lanes; tracks are independent, so spread them over blocks of 1 thread
       each to get them on different SMs (each is a long serial walk) */
    k_ctx_scan<<<c.ntrks, 1, 0, s>>>(c, st, sk, from, to, ev, cap, counts, failed); }
-void launch_units_scan(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, TrkMeta *meta, rt_event *pool,
+void launch_units_scan(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                        uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, float quiet_thr, int quiet_thr_lsb,
                        unsigned long long *rows_scanned, int grid, cudaStream_t s) {
    k_units_scan<<<grid, 128, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr, quiet_thr_lsb, rows_scanned); }

@@ -30,12 +30,12 @@ void launch_ctx_reset(const DevCfg &c, TrkState *st, rtgen::SkewState *sk, int k
 void launch_ctx_set_avg_height(TrkState *st, int trk, float v, cudaStream_t s);
 void launch_ctx_scan(const DevCfg &c, TrkState *st, rtgen::SkewState *sk, uint64_t from, uint64_t to, rt_event *ev,
                      uint32_t cap, uint32_t *counts, uint32_t *failed, cudaStream_t s);
-void launch_units_scan(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, TrkMeta *meta, rt_event *pool,
+void launch_units_scan(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                        uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, float quiet_thr, int quiet_thr_lsb,
                        unsigned long long *rows_scanned, int grid, cudaStream_t s);
 /* k_fast.cu: the int16-domain fast path of the moving-window peak detector (same contract as launch_units_scan) */
 bool fast_scan_eligible(const DevCfg &c);
-cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, const uint32_t *nunits, uint32_t nunits_host, TrkMeta *meta, rt_event *pool,
+cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                               uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
-                              unsigned long long *rows_scanned, int sms, cudaStream_t s);
+                              unsigned long long *rows_scanned, int sms, int max_ctas_per_sm, cudaStream_t s);
 #endif

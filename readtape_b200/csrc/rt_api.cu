@@ -59,6 +59,9 @@ struct rt_tape {
       many GB cost far more than the scan itself) */
    rt_event *pool_cache = nullptr; uint32_t *next_cache = nullptr; uint32_t pool_cache_chunks = 0; bool pool_cache_busy = false;
    rt_event *pin_cache = nullptr; size_t pin_cache_events = 0; bool pin_cache_busy = false;
+   /* rt_bulk_scan_host(): extra streams, and the sizes the last whole-tape scan needed (capacity planning of the streamed scan) */
+   cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[2] = {nullptr, nullptr};
+   uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
 };
 
 static int tape_reserve(rt_tape *t, uint64_t rows) {
@@ -142,6 +145,32 @@ static int tape_drain(rt_tape *t) {
    t->ingest_events.clear();
    return RT_OK; }
 
+/* two device staging buffers for the chunked host->device copy; *stage_rows = rows per chunk */
+static int stage_prepare(rt_tape *t, uint64_t nrows, uint64_t *stage_rows) {
+   const uint64_t nh = t->desc.nheads;
+   const uint64_t chunk_rows = (uint64_t)2048 * 1024;                       /* 2 Mi rows: 36 MiB for 9 heads */
+   if (!t->d_stage[0]) {
+      size_t need = (size_t)std::min(chunk_rows, nrows + 2048) * nh * 2 + 256;
+      t->stage_bytes = std::max(need, (size_t)1 << 20);
+      CU(cudaStreamCreateWithFlags(&t->s_copy, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+         CU(cudaMalloc(&t->d_stage[i], t->stage_bytes));
+         CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming)); } }
+   *stage_rows = (t->stage_bytes - 256) / (nh * 2) / 2048 * 2048;
+   return RT_OK; }
+
+/* one chunk: host->device copy on the copy stream, ingest kernel on the tape's stream; the copy engine never waits for a
+   kernel launch (the copy into a staging buffer only waits for the ingest that last read that buffer, two chunks earlier) */
+static int enqueue_chunk(rt_tape *t, const int16_t *src, uint64_t n, int buf) {
+   CU(cudaStreamWaitEvent(t->s_copy, t->stage_done[buf], 0));
+   CU(cudaMemcpyAsync(t->d_stage[buf], src, (size_t)n * t->desc.nheads * 2, cudaMemcpyHostToDevice, t->s_copy));
+   CU(cudaEventRecord(t->stage_copied[buf], t->s_copy));
+   CU(cudaStreamWaitEvent(t->stream, t->stage_copied[buf], 0));
+   int rc = tape_ingest(t, t->d_stage[buf], n);
+   if (rc) return rc;
+   CU(cudaEventRecord(t->stage_done[buf], t->stream));
+   return RT_OK; }
+
 extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
    if (!t || (!rows && nrows)) return set_err(RT_ERR_ARG, "rt_upload: null argument");
    if (nrows == 0) return RT_OK;
@@ -149,22 +178,14 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
    int rc = tape_reserve(t, t->nrows + nrows);
    if (rc) return rc;
    const uint64_t nh = t->desc.nheads;
-   /* stage through two device buffers so the copy of chunk i+1 overlaps the ingest of chunk i */
-   const uint64_t chunk_rows = (uint64_t)2048 * 1024;                       /* 2 Mi rows: 36 MiB for 9 heads */
-   if (!t->d_stage[0]) {
-      size_t need = (size_t)std::min(chunk_rows, nrows + 2048) * nh * 2 + 256;
-      t->stage_bytes = std::max(need, (size_t)1 << 20);
-      for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&t->d_stage[i], t->stage_bytes)); CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); } }
-   const uint64_t stage_rows = (t->stage_bytes - 256) / (nh * 2) / 2048 * 2048;
+   uint64_t stage_rows = 0;
+   rc = stage_prepare(t, nrows, &stage_rows); if (rc) return rc;
    if (t->nrows % 2048 != 0 && !t->force_simple_ingest) { /* appended onto a partial tile: fine, the plain kernel handles it */ }
-   /* copy and ingest are enqueued back to back on one stream (the ingest kernel is ~100x shorter than the
-      PCIe copy of its chunk, so there is nothing to gain from a second stream); the two staging buffers only
-      exist so that a later revision can overlap them.  One synchronisation at the end. */
+   /* copies on the copy stream, ingest kernels on the tape's stream, two staging buffers; one synchronisation at the end */
    uint64_t done = 0; int buf = 0;
    while (done < nrows) {
       uint64_t n = std::min(stage_rows ? stage_rows : nrows - done, nrows - done);
-      CU(cudaMemcpyAsync(t->d_stage[buf], rows + done * nh, (size_t)n * nh * 2, cudaMemcpyHostToDevice, t->stream));
-      rc = tape_ingest(t, t->d_stage[buf], n);
+      rc = enqueue_chunk(t, rows + done * nh, n, buf);
       if (rc) return rc;
       done += n; buf ^= 1; }
    t->h2d_bytes += nrows * nh * 2;
@@ -210,8 +231,11 @@ extern "C" void rt_close(rt_tape *t) {
    if (t->stream) cudaStreamSynchronize(t->stream);
    cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
    cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
-   for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); }
+   for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
+   if (t->s_copy) cudaStreamDestroy(t->s_copy);
    if (t->stream) cudaStreamDestroy(t->stream);
+   if (t->s_scan) cudaStreamDestroy(t->s_scan);
+   if (t->s_out) cudaStreamDestroy(t->s_out);
    delete t; }
 
 extern "C" void *rt_host_alloc(size_t bytes) {
@@ -408,6 +432,42 @@ static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
    int lead = std::max<int>((int)k + (tz ? 1 : 0), dc.skew[k]);
    return dc.det == RT_DET_PEAK ? lead + dc.width + 1 : lead + 2; }
 
+/* Everything derived from one configuration that the unit finder and the scan kernels need. */
+struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; };
+static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
+   cfg_to_dev(t, cfg, &pl->dc);
+   const DevCfg &dc = pl->dc;
+   /* proposal thresholds (heuristic) and the exact quiet threshold the scan kernel applies */
+   const double lsb = (double)t->desc.maxvolts / 32767.0;
+   const double rows_per_bit = 1.0 / ((double)dc.bpi * dc.ips * dc.sample_deltat);
+   pl->up = UnitParams{};
+   pl->up.det = dc.det;
+   pl->quiet_thr = 0;
+   pl->quiet_thr_lsb = rtcfg::quiet_thr_lsb(dc);
+   /* K3b (int16 fast path) for the peak detector of NRZI / PE; RT_SCAN=generic forces the exact generic kernel (tests) */
+   const char *force = getenv("RT_SCAN");
+   pl->use_fast = fast_scan_eligible(dc) && !(force && strcmp(force, "generic") == 0);
+   if (dc.det == RT_DET_PEAK) {
+      pl->quiet_thr = dc.p.pkww_rise * 0.999f;
+      if (dc.p.pkww_rise < 1e-3f) pl->quiet_thr = 0;                  /* nothing can be proven quiet: every lookup misses */
+      pl->up.thr = (int)(0.75 * dc.p.pkww_rise / lsb); }
+   else if (dc.det == RT_DET_ZC) pl->up.thr = (int)(0.9 * RT_ZEROCROSS_PEAK / lsb);
+   else pl->up.thr = (int)(0.9 * std::max(0.05, 0.5 / std::max(1, dc.samples_per_bit)) / lsb);
+   uint64_t gap_rows = (uint64_t)(6.0 * rows_per_bit) + 1;
+   pl->up.min_gap_gran = (uint32_t)std::max<uint64_t>(2, (gap_rows + RT_GRAN - 1) / RT_GRAN + 1);
+   const uint64_t ibg_rows = (uint64_t)(200e-6 / dc.sample_deltat) + 1;      /* *_IBG_SECS, decoder.h:105,113,116 */
+   pl->up.tail_rows = (uint64_t)(16.0 * rows_per_bit) + ibg_rows + 64 + RT_PKWW_MAX_WIDTH + RT_MAXSKEWSAMP; }
+
+static cudaError_t launch_scan(const rt_tape *t, const ScanPlan &pl, const UnitDesc *d_units, uint32_t nunits, TrkMeta *d_meta, rt_event *d_pool,
+                               uint32_t *d_chunk_next, unsigned int *d_cursor, uint32_t pool_chunks, unsigned long long *d_counters,
+                               int max_ctas_per_sm, cudaStream_t st) {
+   if (pl.use_fast) return launch_units_fast(pl.dc, d_units, nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, pl.quiet_thr_lsb, d_counters,
+                                             t->sms, max_ctas_per_sm, st);
+   const uint64_t threads = (uint64_t)nunits * t->desc.ntrks;
+   int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * (max_ctas_per_sm > 0 ? 4 : 16));
+   launch_units_scan(pl.dc, d_units, nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, pl.quiet_thr, pl.quiet_thr_lsb, d_counters, grid, st);
+   return cudaGetLastError(); }
+
 extern "C" void rt_bulk_free(rt_bulk *b) {
    if (!b) return;
    cudaSetDevice(b->tape->device);
@@ -456,29 +516,9 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    b->stats.rows = nrows; b->stats.ms_preprocess = t->ms_ingest;
    for (uint32_t ci = 0; ci < ncfgs; ++ci) {
       BulkCfg &bc = b->cfgs[ci];
-      bc.cfg = cfgs[ci]; cfg_to_dev(t, &cfgs[ci], &bc.dc);
-      const DevCfg &dc = bc.dc;
-      /* proposal thresholds (heuristic) and the exact quiet threshold the scan kernel applies */
-      const double lsb = (double)t->desc.maxvolts / 32767.0;
-      const double rows_per_bit = 1.0 / ((double)dc.bpi * dc.ips * dc.sample_deltat);
-      UnitParams up{};
-      up.det = dc.det;
-      float quiet_thr = 0;
-      const int quiet_thr_lsb = rtcfg::quiet_thr_lsb(dc);
-      /* K3b (int16 fast path) for the peak detector of NRZI / PE; RT_SCAN=generic forces the exact generic kernel (tests) */
-      const char *force = getenv("RT_SCAN");
-      const bool use_fast = fast_scan_eligible(dc) && !(force && strcmp(force, "generic") == 0);
-      bc.fast = use_fast;
-      if (dc.det == RT_DET_PEAK) {
-         quiet_thr = dc.p.pkww_rise * 0.999f;
-         if (dc.p.pkww_rise < 1e-3f) quiet_thr = 0;                      /* nothing can be proven quiet: every lookup misses */
-         up.thr = (int)(0.75 * dc.p.pkww_rise / lsb); }
-      else if (dc.det == RT_DET_ZC) up.thr = (int)(0.9 * RT_ZEROCROSS_PEAK / lsb);
-      else up.thr = (int)(0.9 * std::max(0.05, 0.5 / std::max(1, dc.samples_per_bit)) / lsb);
-      uint64_t gap_rows = (uint64_t)(6.0 * rows_per_bit) + 1;
-      up.min_gap_gran = (uint32_t)std::max<uint64_t>(2, (gap_rows + RT_GRAN - 1) / RT_GRAN + 1);
-      const uint64_t ibg_rows = (uint64_t)(200e-6 / dc.sample_deltat) + 1;      /* *_IBG_SECS, decoder.h:105,113,116 */
-      up.tail_rows = (uint64_t)(16.0 * rows_per_bit) + ibg_rows + 64 + RT_PKWW_MAX_WIDTH + RT_MAXSKEWSAMP;
+      ScanPlan pl; make_plan(t, &cfgs[ci], &pl);
+      bc.cfg = cfgs[ci]; bc.dc = pl.dc; bc.fast = pl.use_fast;
+      const UnitParams &up = pl.up;
       CUB(cudaEventRecord(ev[0], t->stream));
       cudaError_t e = launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap, d_nunits, t->stream, &t->launches);
       CUB(e);
@@ -515,13 +555,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
             CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
             CUB(cudaMemsetAsync(d_counters, 0, 32, t->stream));
             CUB(cudaEventRecord(ev[2], t->stream));
-            const uint64_t threads = (uint64_t)nunits * nt;
-            if (use_fast) CUB(launch_units_fast(dc, bc.d_units, d_nunits, nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks,
-                                                quiet_thr_lsb, d_counters, t->sms, t->stream));
-            else {
-               int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * 16);
-               launch_units_scan(dc, bc.d_units, d_nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks, quiet_thr, quiet_thr_lsb, d_counters, grid, t->stream);
-               CUB(cudaGetLastError()); }
+            CUB(launch_scan(t, pl, bc.d_units, nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks, d_counters, 0, t->stream));
             ++t->launches;
             CUB(cudaEventRecord(ev[3], t->stream));
             unsigned int used = 0;
@@ -541,6 +575,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    lap("counters");
    b->stats.track_samples = nrows * nt * ncfgs;
    b->stats.launches = (uint32_t)(t->launches - launches0);
+   if (ncfgs == 1) { t->hist_rows = nrows; t->hist_units = b->cfgs[0].nunits; t->hist_chunks = b->cfgs[0].chunks_used; }   /* sizes the streamed scan */
    cleanup();
 #undef CUB
    *out = b; return RT_OK; }
@@ -581,6 +616,145 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
       bc.d_units = nullptr; bc.d_meta = nullptr; bc.d_pool = nullptr; bc.d_chunk_next = nullptr; }
    b->fetched = true;
    return RT_OK; }
+
+/* Upload + whole-tape scan + fetch in one call, overlapped.  Replaces  rt_clear(); rt_upload(); rt_bulk_scan(cfg); rt_bulk_fetch().
+ * The host->device copy of a 20 GB capture takes ~7x longer than scanning it, so the tape is processed in segments while it
+ * arrives: all copies + ingest kernels are enqueued on the tape's stream; after each segment the unit finder runs on the
+ * prefix ingested so far (stream s_scan), the units that are already complete are scanned (with at most 2 CTAs per SM, so
+ * that the ingest kernels of the following chunks still find room), and their events, proof data and chunk links go back
+ * to the host on a third stream while the next segment is being copied.  Buffer capacities come from the previous
+ * whole-tape scan of this tape object; without such history (or when they do not suffice) the plain sequence is used. */
+extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows, const rt_scan_cfg *cfg, rt_bulk **out) {
+   if (!t || !rows || !cfg || !out) return set_err(RT_ERR_ARG, "rt_bulk_scan_host: null argument");
+   CU(cudaSetDevice(t->device));
+   int rc = rt_clear(t); if (rc) return rc;
+   const uint32_t nt = t->desc.ntrks; const uint64_t nh = t->desc.nheads;
+   const char *env = getenv("RT_STREAM");
+   const bool trace = getenv("RT_TRACE") != nullptr;
+   bool stream_ok = !(env && env[0] == '0') && t->hist_rows && nrows <= t->hist_rows + t->hist_rows / 20 && nrows >= (16u << 20)
+                    && cfg->mode != RT_MODE_WW && !(cfg->flags & RT_F_DENSITY_DETECT) && !t->pool_cache_busy && !t->pin_cache_busy
+                    && t->pool_cache && t->pin_cache && t->pool_cache_chunks >= t->hist_chunks + t->hist_chunks / 32
+                    && t->pin_cache_events / RT_EVC >= (size_t)t->hist_chunks + t->hist_chunks / 32;
+   if (stream_ok) { rc = tape_reserve(t, nrows); if (rc) return rc; rc = cfg_check(t, cfg); if (rc) return rc; }
+   if (!stream_ok) {
+      rc = rt_upload(t, rows, nrows); if (rc) return rc;
+      rc = rt_bulk_scan(t, cfg, 1, out); if (rc) return rc;
+      return rt_bulk_fetch(*out); }
+
+   uint64_t stage_rows = 0;
+   rc = stage_prepare(t, nrows, &stage_rows); if (rc) return rc;
+   if (!t->s_scan) { CU(cudaStreamCreateWithFlags(&t->s_scan, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking)); }
+   ScanPlan pl; make_plan(t, cfg, &pl); pl.dc.nrows = nrows;
+   const uint32_t cap_units = t->hist_units + t->hist_units / 8 + 1024;
+   const uint32_t cap_chunks = (uint32_t)std::min<size_t>(t->pool_cache_chunks, t->pin_cache_events / RT_EVC);
+   const size_t words = units_bitmap_words(nrows), nblocks = units_blocks(nrows) + 1;
+   const uint32_t units_cap_tmp = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
+   uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
+   unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr; TrkMeta *d_meta = nullptr;
+   std::vector<cudaEvent_t> seg_ev; std::vector<uint64_t> seg_rows_done;
+   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+   rt_bulk *b = new (std::nothrow) rt_bulk();
+   if (!b) return set_err(RT_ERR_NOMEM, "rt_bulk_scan_host: out of memory");
+   b->tape = t; b->cfgs.resize(1);
+   BulkCfg &bc = b->cfgs[0];
+   bc.cfg = *cfg; bc.dc = pl.dc; bc.fast = pl.use_fast;
+   bool failed = false; const char *why = "";
+   auto release = [&]() {
+      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta};
+      for (void *p : scr) if (p) cudaFreeAsync(p, t->s_scan);
+      for (auto e : seg_ev) cudaEventDestroy(e);
+      if (ev_a) cudaEventDestroy(ev_a); if (ev_b) cudaEventDestroy(ev_b); };
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); release(); t->pool_cache_busy = t->pin_cache_busy = false; delete b; \
+      return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+   CUS(cudaMallocAsync(&d_bitmap, words * 4, t->s_scan)); CUS(cudaMallocAsync(&d_flags, words * 4, t->s_scan)); CUS(cudaMallocAsync(&d_blockcount, nblocks * 4, t->s_scan));
+   CUS(cudaMallocAsync(&d_nunits, 4, t->s_scan)); CUS(cudaMallocAsync(&d_units_tmp, (size_t)units_cap_tmp * sizeof(UnitDesc), t->s_scan));
+   CUS(cudaMallocAsync(&d_counters, 32, t->s_scan)); CUS(cudaMallocAsync(&d_cursor, 4, t->s_scan));
+   CUS(cudaMallocAsync(&d_meta, (size_t)cap_units * nt * sizeof(TrkMeta), t->s_scan));
+   CUS(cudaMemsetAsync(d_cursor, 0, 4, t->s_scan)); CUS(cudaMemsetAsync(d_counters, 0, 32, t->s_scan));
+   CUS(cudaEventCreate(&ev_a)); CUS(cudaEventCreate(&ev_b));
+   t->pool_cache_busy = t->pin_cache_busy = true;
+   rt_event *d_pool = t->pool_cache; uint32_t *d_chunk_next = t->next_cache; rt_event *h_pool = t->pin_cache;
+   const int launches0 = t->launches;
+
+   /* 1. everything that moves samples: enqueued once, runs by itself */
+   {  const uint64_t seg_target = std::max<uint64_t>(stage_rows * 4, (nrows / 16 + stage_rows - 1) / stage_rows * stage_rows);
+      uint64_t done = 0, next_mark = seg_target; int buf = 0;
+      while (done < nrows) {
+         const uint64_t n = std::min(stage_rows, nrows - done);
+         rc = enqueue_chunk(t, rows + done * nh, n, buf);
+         if (rc) { cudaDeviceSynchronize(); release(); t->pool_cache_busy = t->pin_cache_busy = false; delete b; return rc; }
+         done += n; buf ^= 1;
+         if (done >= next_mark || done == nrows) {
+            cudaEvent_t e; CUS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); CUS(cudaEventRecord(e, t->stream));
+            seg_ev.push_back(e); seg_rows_done.push_back(done); next_mark = done + seg_target; } }
+      t->h2d_bytes += nrows * nh * 2; }
+
+   /* 2. per segment: units of the prefix, scan the complete ones, send their results home */
+   uint32_t u_done = 0, c_done = 0, nun = 0; double ms_scan = 0, ms_units = 0;
+   for (size_t k = 0; k < seg_ev.size() && !failed; ++k) {
+      const bool last = k + 1 == seg_ev.size();
+      const uint64_t R = seg_rows_done[k];
+      CUS(cudaStreamWaitEvent(t->s_scan, seg_ev[k], 0));
+      CUS(cudaEventRecord(ev_a, t->s_scan));
+      CUS(launch_find_units(t->gmm, t->ngran_cap, (int)nt, R, pl.up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap_tmp, d_nunits, t->s_scan, &t->launches));
+      CUS(cudaEventRecord(ev_b, t->s_scan));
+      uint32_t nunits = 0;
+      CUS(cudaMemcpyAsync(&nunits, d_nunits, 4, cudaMemcpyDeviceToHost, t->s_scan));
+      CUS(cudaStreamSynchronize(t->s_scan));
+      { float ms = 0; cudaEventElapsedTime(&ms, ev_a, ev_b); ms_units += ms; }
+      if (nunits > cap_units || nunits > units_cap_tmp) { failed = true; why = "more units than the previous scan"; break; }
+      nun = nunits;
+      bc.units.resize(nun);
+      if (nun > u_done) CUS(cudaMemcpy(bc.units.data() + u_done, d_units_tmp + u_done, (size_t)(nun - u_done) * sizeof(UnitDesc), cudaMemcpyDeviceToHost));
+      uint32_t u_final = u_done;
+      if (last) {
+         rc = tape_sync_valid(t);
+         if (rc || t->nrows_valid != nrows) { failed = true; why = "end-of-data marker inside the capture"; break; }
+         u_final = nun; }
+      else while (u_final + 1 < nun && bc.units[u_final + 1].row0 + pl.up.tail_rows + 4096 <= R) ++u_final;    /* row_end can no longer change */
+      if (u_final == u_done) continue;
+      CUS(cudaEventRecord(ev_a, t->s_scan));
+      CUS(launch_scan(t, pl, d_units_tmp + u_done, u_final - u_done, d_meta + (size_t)u_done * nt, d_pool, d_chunk_next, d_cursor, cap_chunks, d_counters,
+                      last ? 0 : 2, t->s_scan));
+      ++t->launches;
+      CUS(cudaEventRecord(ev_b, t->s_scan));
+      unsigned int used = 0;
+      CUS(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->s_scan));
+      CUS(cudaStreamSynchronize(t->s_scan));
+      { float ms = 0; cudaEventElapsedTime(&ms, ev_a, ev_b); ms_scan += ms; }
+      if (trace) fprintf(stderr, "[rt_bulk_scan_host] segment %zu: rows %llu, units %u..%u, chunks %u..%u\n", k, (unsigned long long)R, u_done, u_final, c_done, used);
+      if (used > cap_chunks) { failed = true; why = "more events than the previous scan"; break; }
+      bc.meta.resize((size_t)u_final * nt); bc.chunk_next.resize(used);
+      CUS(cudaMemcpy(bc.meta.data() + (size_t)u_done * nt, d_meta + (size_t)u_done * nt, (size_t)(u_final - u_done) * nt * sizeof(TrkMeta), cudaMemcpyDeviceToHost));
+      if (used > c_done) {
+         CUS(cudaMemcpy(bc.chunk_next.data() + c_done, d_chunk_next + c_done, (size_t)(used - c_done) * 4, cudaMemcpyDeviceToHost));
+         CUS(cudaMemcpyAsync(h_pool + (size_t)c_done * RT_EVC, d_pool + (size_t)c_done * RT_EVC, (size_t)(used - c_done) * RT_EVC * sizeof(rt_event),
+                             cudaMemcpyDeviceToHost, t->s_out)); }
+      b->stats.d2h_bytes += (uint64_t)(used - c_done) * (RT_EVC * sizeof(rt_event) + 4) + (uint64_t)(u_final - u_done) * (sizeof(UnitDesc) + nt * sizeof(TrkMeta));
+      u_done = u_final; c_done = used; }
+   CUS(cudaStreamSynchronize(t->s_out));
+   rc = tape_drain(t);
+   if (failed || rc) {                                           /* the samples are resident by now: plain scan + fetch */
+      cudaDeviceSynchronize(); release(); t->pool_cache_busy = t->pin_cache_busy = false; delete b;
+      if (rc) return rc;
+      if (trace) fprintf(stderr, "[rt_bulk_scan_host] streamed scan abandoned (%s): plain scan\n", why);
+      rc = tape_sync_valid(t); if (rc) return rc;
+      rc = rt_bulk_scan(t, cfg, 1, out); if (rc) return rc;
+      return rt_bulk_fetch(*out); }
+   unsigned long long counters[2] = {0, 0};
+   CUS(cudaMemcpy(counters, d_counters, 16, cudaMemcpyDeviceToHost));
+   bc.nunits = nun; bc.chunks_used = c_done; bc.pool_chunks = cap_chunks;
+   bc.h_pool = h_pool; bc.h_pool_events = (size_t)c_done * RT_EVC; bc.pin_from_cache = true;
+   t->pool_cache_busy = false;                                    /* the device pool is free again; the pinned copy belongs to the bulk */
+   b->fetched = true;
+   b->stats.rows = nrows; b->stats.units = nun; b->stats.events = counters[1]; b->stats.rows_scanned = counters[0];
+   b->stats.track_samples = nrows * nt; b->stats.ms_preprocess = t->ms_ingest; b->stats.ms_units = ms_units; b->stats.ms_scan = ms_scan;
+   b->stats.launches = (uint32_t)(t->launches - launches0);
+   b->stats.pad = (uint32_t)seg_ev.size();                        /* segments streamed (0: the plain sequence was used) */
+   t->hist_rows = nrows; t->hist_units = nun; t->hist_chunks = c_done;
+   release();
+#undef CUS
+   *out = b; return RT_OK; }
 
 extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
    if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");

@@ -219,3 +219,43 @@ def test_fast_kernel_on_synthetic_tape_equals_oracle(cuda_lib, oracle_lib):
             assert a.tobytes() == b.tobytes(), f"unit {ui['unit_index']} parmset {pi}: {len(a)} vs {len(b)} events, first diff {evlog._first_diff(a, b)}"
         sc.end(); bulk.free()
     tg.close(); to.close()
+
+
+def test_streamed_host_scan_equals_plain_sequence(cuda_lib):
+    """rt_bulk_scan_host(): the first call on a tape object has no capacity history and runs upload + scan + fetch one after
+    the other; the second one streams (scans segment by segment while the copy is still running).  Both must give the
+    same units, proof data and events as the separate calls."""
+    import ctypes
+    from readtape_b200 import parmsets, synth, tbin
+    tile = synth.nrzi_tile()
+    reps = 14                                                       # 17.5 M rows: above the streaming threshold
+    n = tile.shape[0] * reps
+    hdr = synth.nrzi_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
+    L = cuda_lib.L
+    hptr = L.rt_host_alloc(n * 18)
+    assert hptr
+    hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_int16)), shape=(n, 9))
+    for i in range(reps):
+        hbuf[i * tile.shape[0]:(i + 1) * tile.shape[0]] = tile
+    tape = cuda_lib.open(desc)
+
+    def snapshot(bulk):
+        units = _all_units(bulk)
+        sample = units[::max(1, len(units) // 40)]
+        evs = [bulk.lookup(0, u["row0"]) for u in sample]
+        return units, [(e[0].tobytes(), e[1]) for e in evs], bulk.stats()
+
+    tape.upload_ptr(hptr, n)
+    ref = tape.bulk_scan([cfg]); ref.fetch()
+    u0, e0, s0 = snapshot(ref); ref.free()
+    b1 = tape.bulk_scan_host(hptr, n, cfg)
+    u1, e1, s1 = snapshot(b1); b1.free()
+    b2 = tape.bulk_scan_host(hptr, n, cfg)
+    u2, e2, s2 = snapshot(b2); b2.free()
+    tape.close(); L.rt_host_free(hptr)
+    assert s2.pad >= 2, f"the second call did not stream (segments {s2.pad})"
+    assert s0.events == s1.events == s2.events and s0.units == s1.units == s2.units
+    assert u0 == u1 == u2
+    assert e0 == e1 == e2
