@@ -219,6 +219,14 @@ def main():
     # ---- e2e: host buffers through the C-ABI ----
     e2e = None
     if not args.no_e2e:
+        # the pinned host copy of the tape is per rank: never ask for more than a share of what the box has free
+        try:
+            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+        except Exception:
+            avail = None
+        rows_full = rows
+        if avail is not None and rows * 18 * 1.15 > 0.6 * avail / world:
+            rows = max(T, int(0.6 * avail / world / 1.15 / 18) // T * T)      # a shorter host tape (whole super-tiles) rather than an OOM
         nbytes = rows * 18
         hptr = lib.L.rt_host_alloc(nbytes)
         if not hptr:
@@ -248,10 +256,11 @@ def main():
             tt = torch.tensor([el], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             el = float(tt.item())
-        e2e = {"value": world * tsamp * ke / el, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+        e2e = {"value": world * rows * 9 * ke / el, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "rows_per_gpu": int(rows),
                "d2h_bytes_per_step": int(ste.d2h_bytes), "ms_per_step": 1e3 * el / ke, "segments_streamed": int(ste.pad),
                "api": "rt_bulk_scan_host (pinned host rows -> events + proof data in pinned host memory) + rt_bulk_lookup"}
         lib.L.rt_host_free(hptr)
+        rows = rows_full
 
     # ---- result gather over NCCL: per-rank event counts (the only inter-GPU traffic of this path) ----
     all_events = [events]

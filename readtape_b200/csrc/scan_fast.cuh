@@ -135,7 +135,7 @@ struct UnitScan {
    /* position: next row o = b + j; g = running packed max of block [b, b+w) up to j, hbk = running max of its backward pass;
       hp / hc = first entries of the previous / current block's H array; fillblk = the window is still filling */
    uint32_t o, b, g, hbk; int j, hp, hc, st, fillblk, candA, pre;
-   /* loader */
+   /* loader: offsets < ld are in the ring */
    uint32_t ld;
    /* gap skipping: this track's granule min/max map (null = off), next offset at which an attempt is worthwhile, and the
       offset by which the lazily kept minimum must have been re-established after a jump (0 = not pending) */
@@ -144,29 +144,45 @@ struct UnitScan {
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
    int32_t sync_row, loud_at_sync, sync_first, sync_early, loud_early; bool early_frozen; uint32_t sf_from; uint64_t quiet_from;
 
-   RT_FHD UnitScan(const DevCfg &c_, LaneMem<STRIDE> mem_) : c(c_), w(c_.width), mem(mem_) { st = ST_DONE; j = 0; o = end = 0; }
+   RT_FHD UnitScan(const DevCfg &c_, LaneMem<STRIDE> mem_) : c(c_), w(c_.width), mem(mem_) { st = ST_DONE; j = 0; o = end = 0; ld = 0; pf_at = 0xffffffffu; }
 
    /* the sample the detector sees at stream offset o (deskew FIFO, decoder.c:819-831) */
    RT_FHD int sample(uint32_t o) const { return (int)plane[row0 + (o >= (uint32_t)delay ? o - (uint32_t)delay : o)]; }
 
+   /* ---- loader: 16-byte chunks of 8 samples -> packed ring entries --------------------------------------------------
+      The chunks the next batch of rows will need are requested one batch ahead (prefetch) and stored when they are due
+      (ensure), so that no lane ever waits for DRAM inside the row loop. */
+   struct chunk8 { uint32_t w[4]; };
+   RT_FHD chunk8 load_chunk(uint32_t at) const {                  /* samples of stream offsets [at, at+8), at >= delay */
+      const int16_t *p = plane + row0 + (at - (uint32_t)delay);    /* 16-byte aligned: row0 % 32 == 0, (at-delay) % 8 == 0 */
+      chunk8 q;
+#ifdef __CUDA_ARCH__
+      const uint4 v = *reinterpret_cast<const uint4 *>(p);
+      q.w[0] = v.x; q.w[1] = v.y; q.w[2] = v.z; q.w[3] = v.w;
+#else
+      memcpy(q.w, p, 16);
+#endif
+      return q; }
+   RT_FHD void store_chunk(uint32_t at, const chunk8 &q) const {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+         const uint32_t v = q.w[i], nv = ~v;
+         mem.X(at + 2 * i) = (v << 16) | (nv & 0xffffu);
+         mem.X(at + 2 * i + 1) = (v & 0xffff0000u) | (nv >> 16); } }
+   chunk8 pf0, pf1; uint32_t pf_at;                               /* two chunks in flight for offsets pf_at, pf_at+8; pf_at = ~0: none */
+   RT_FHD void prefetch() {
+      pf_at = 0xffffffffu;
+      if (ld < (uint32_t)delay || ld >= end + 16u) return;
+      pf_at = ld; pf0 = load_chunk(ld); pf1 = load_chunk(ld + 8); }
    /* make ring entries of offsets < upto available */
    RT_FHD void ensure(uint32_t upto) {
+      if (pf_at == ld) {                                          /* the prefetched chunks are the next ones due */
+         if (ld < upto) { store_chunk(ld, pf0); ld += 8; }
+         if (ld < upto && ld == pf_at + 8) { store_chunk(ld, pf1); ld += 8; } }
+      pf_at = 0xffffffffu;
       while (ld < upto) {
          if (ld < (uint32_t)delay) { mem.X(ld) = pk(sample(ld)); ++ld; }
-         else {
-            const int16_t *p = plane + row0 + (ld - (uint32_t)delay);          /* 16-byte aligned: row0 % 32 == 0, (ld-delay) % 8 == 0 */
-#ifdef __CUDA_ARCH__
-            const uint4 q = *reinterpret_cast<const uint4 *>(p);
-            const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-#else
-            uint32_t wds[4]; memcpy(wds, p, 16);
-#endif
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-               const uint32_t v = wds[i], nv = ~v;
-               mem.X(ld + 2 * i) = (v << 16) | (nv & 0xffffu);
-               mem.X(ld + 2 * i + 1) = (v & 0xffff0000u) | (nv >> 16); }
-            ld += 8; } } }
+         else { store_chunk(ld, load_chunk(ld)); ld += 8; } } }
 
    /* required_rise / required_min (decoder.c:785-786) only change at events: cached, with the integer bound T */
    RT_FHD void thresholds() {
@@ -270,7 +286,7 @@ struct UnitScan {
          const int x0 = sample(io);
          m = x0; lvw = pk(x0);
          t.t_lastpeak = row_time(c, row0 + io);
-         ld = b < (uint32_t)delay ? b : (b - (uint32_t)delay) / 8 * 8 + (uint32_t)delay;
+         ld = b < (uint32_t)delay ? b : (b - (uint32_t)delay) / 8 * 8 + (uint32_t)delay; pf_at = 0xffffffffu;
          ensure(o + FAST_K + (uint32_t)w);
          mem.X(io) = pk(x0);                                       /* the loader starts at b (or at the chunk that holds it) */
          /* the window of the filling phase always starts at the first sample: with that sample as the "previous block"
@@ -372,12 +388,26 @@ struct UnitScan {
       const uint64_t gmax = gi + FAST_SKIP_LOOKAHEAD < gend ? gi + FAST_SKIP_LOOKAHEAD : gend;
       int mn = 32767, mx = -32768;
       uint64_t gq = gi;
-      for (; gq < gmax; ++gq) {
-         const uint32_t v = gm[gq];
-         const int a = (int)(int16_t)(uint16_t)(v & 0xffffu), bb = (int)(int16_t)(uint16_t)(v >> 16);
-         const int nmn = a < mn ? a : mn, nmx = bb > mx ? bb : mx;
-         if (nmx - nmn >= thr) break;
-         mn = nmn; mx = nmx; }
+      bool open_run = true;
+      while (open_run && gq < gmax) {
+         /* eight granules per round trip (two 16-byte loads) where alignment and range allow, else one */
+         uint32_t v[8]; int nv = 1;
+         if ((gq & 3) == 0 && gq + 8 <= gmax) {
+#ifdef __CUDA_ARCH__
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(gm + gq), q1 = *reinterpret_cast<const uint4 *>(gm + gq + 4);
+            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+#else
+            memcpy(v, gm + gq, 32);
+#endif
+            nv = 8; }
+         else v[0] = gm[gq];
+#pragma unroll
+         for (int i = 0; i < 8; ++i) {
+            if (i < nv && open_run) {
+               const int a = (int)(int16_t)(uint16_t)(v[i] & 0xffffu), bb = (int)(int16_t)(uint16_t)(v[i] >> 16);
+               const int nmn = a < mn ? a : mn, nmx = bb > mx ? bb : mx;
+               if (nmx - nmn >= thr) open_run = false;
+               else { mn = nmn; mx = nmx; ++gq; } } } }
       /* raw rows [32*gi, 32*gq) are quiet: stream rows < oq cannot fire */
       int64_t oq = (int64_t)(gq * RT_GRAN) - (int64_t)row0 + delay;
       const bool to_end = oq >= (int64_t)end;
@@ -390,7 +420,7 @@ struct UnitScan {
       nskipped += jump - (to_end ? 0u : (uint32_t)w);
       if (to_end) { o = end; st = ST_DONE; return; }
       o = b = (uint32_t)target - (uint32_t)w; j = 0; g = hbk = PK_NEG;
-      ld = (o - (uint32_t)delay) / 8 * 8 + (uint32_t)delay;
+      ld = (o - (uint32_t)delay) / 8 * 8 + (uint32_t)delay; pf_at = 0xffffffffu;
       ensure(o + FAST_K + 2u * (uint32_t)w);
       blind = w;
       for (int i = 0; i < w; ++i) step();                         /* warm-up block: tests off */
@@ -423,8 +453,9 @@ RT_FHD void drive(Scan &us, Jobs &jobs, Vote count) {
       bool active = jobs.next(us);
       if (jobs.exhausted) return;
       while (count(active)) {
-         if (active && us.st == ST_RUN)
-            for (int k = 0; k < FAST_K; ++k) { us.step(); if (us.st != ST_RUN) break; }
+         if (active && us.st == ST_RUN) {
+            us.prefetch();                                         /* the chunks due at the end of this batch: requested now */
+            for (int k = 0; k < FAST_K; ++k) { us.step(); if (us.st != ST_RUN) break; } }
          if (count(active && us.st == ST_PEND)) { if (active && us.st == ST_PEND) us.handle(); }
          if (active && us.st == ST_RUN) us.try_skip();
          if (active && us.st == ST_DONE) { jobs.done(us); active = false; }

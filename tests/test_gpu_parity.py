@@ -259,3 +259,39 @@ def test_streamed_host_scan_equals_plain_sequence(cuda_lib):
     assert s0.events == s1.events == s2.events and s0.units == s1.units == s2.units
     assert u0 == u1 == u2
     assert e0 == e1 == e2
+
+
+@pytest.mark.parametrize("name", ["1600bpi_ukn_6s", "LJS009_part1_39blks"])
+def test_pe_parmset_fanout_on_one_gpu(name, cuda_lib, oracle_lib):
+    """BASELINE config 3: all 8 built-in PE parameter sets (parmsets.c:80-87) scanned in ONE rt_bulk_scan call; every lookup
+    at a block start of the reference must equal the oracle's exact scan from a fresh reset there, for every parameter set."""
+    from readtape_b200 import parmsets
+    doc, segs, heads, rows = load_capture(name)
+    desc = evlog.desc_from_heads(heads)
+    tg, to = cuda_lib.open(desc), oracle_lib.open(desc)
+    tg.upload(rows); to.upload(rows)
+    base = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT) and s.parmset == 0]
+    assert base
+    cfgs = [abi.make_cfg(base[0].mode, parmsets.PE[p], base[0].bpi, base[0].ips, flags=base[0].flags, skew=base[0].skew) for p in range(8)]
+    bulk = tg.bulk_scan(cfgs)
+    st = bulk.stats()
+    assert st.track_samples == tg.nrows * desc.ntrks * 8
+    hits = total = 0
+    for p, cfg in enumerate(cfgs):
+        sc = to.scan(cfg)
+        for seg in base[:12]:
+            total += 1
+            r = bulk.lookup(p, seg.row)
+            if r is None:
+                continue
+            ev, valid = r
+            end = seg.end_row if seg.end_row >= 0 else tg.nrows
+            span = min(valid, end - seg.row)
+            sc.reset(abi.RT_RESET_FULL, seg.row)
+            want, _ = sc.run(span)
+            got = evlog.to_canon(ev); got = got[got["row"] < seg.row + span]
+            assert got.tobytes() == evlog.to_canon(want).tobytes(), f"parmset {p} block at row {seg.row}: lookup differs from the oracle"
+            hits += 1
+        sc.end()
+    bulk.free(); tg.close(); to.close()
+    assert hits >= 0.7 * total, f"only {hits} of {total} (parmset, block) lookups were served by the bulk scan"
