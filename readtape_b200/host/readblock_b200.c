@@ -35,6 +35,7 @@
  */
 #include "decoder.h"
 #include "rt_scan.h"
+#include <time.h>
 
 /* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
 extern FILE *inf;
@@ -65,8 +66,11 @@ static struct {
    int use_bulk;
    /* statistics */
    long long n_bulk_hits, n_bulk_miss, n_exact_spans, n_events, n_restarts;
+   double s_scan, s_replay, s_open;  /* wall seconds: inside the rt_scan library / replaying events into the handlers / opening */
    int said_config;
 } S;
+
+static double wall(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 #define EXACT_SPAN_ROWS  (1u << 17)
 
@@ -355,7 +359,8 @@ static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, st
       ++row; } }
 
 bool readblock(bool retry) {
-   if (!S.opened) open_tape();
+   double w0 = wall();
+   if (!S.opened) { open_tape(); S.s_open += wall() - w0; w0 = wall(); }
    long long pos = ftello(inf);
    assert(pos >= S.base_pos && (pos - S.base_pos) % (nheads * 2) == 0, "B200 scan: unexpected file position %lld", pos);
    uint64_t row0 = (uint64_t)(pos - S.base_pos) / (uint64_t)(nheads * 2);
@@ -374,6 +379,7 @@ bool readblock(bool retry) {
    int persistent = mode == WW || reset_kind != RT_RESET_FULL;   /* Whirlwind: the scan state carries over from block to block */
    int from_bulk = !persistent && bulk_start(&src, &cfg, row0);
    if (!from_bulk) exact_start(&src, &cfg, reset_kind, row0);
+   S.s_scan += wall() - w0; w0 = wall();
    if (decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile)) {
       /* the speculative unit ended before the block did: start over with the exact scan */
       assert(from_bulk, "B200 scan: exact scan asked for a restart");
@@ -399,7 +405,9 @@ bool readblock(bool retry) {
                       + result->gcr_bad_sequence + result->ww_bad_length + result->ww_speed_err;
    result->warncount = result->missed_midbits + result->corrected_bits + result->gcr_bad_dgroups
                        + result->ww_leading_clock + result->ww_missing_onebit + result->ww_missing_clock;
-   if (endfile && !quiet && getenv("RT_STATS"))
+   S.s_replay += wall() - w0;
+   if (endfile && getenv("RT_STATS")) {
       rlog("  B200 scan: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n",
            S.n_events, S.n_bulk_hits, S.n_bulk_miss, S.n_restarts, S.n_exact_spans);
+      rlog("  B200 scan: %.3f s opening + upload, %.3f s in the scan library, %.3f s replaying events into the handlers\n", S.s_open, S.s_scan, S.s_replay); }
    return !endfile; }

@@ -115,3 +115,30 @@ def test_fast_path_equals_oracle_on_synthetic(fast_host, oracle_lib):
                     pytest.fail(f"skew {skew} parmset {pi} row0 {row0}: event #{k}: fast {a[k] if k < len(a) else None} oracle {b[k] if k < len(b) else None} "
                                 f"({len(a)} vs {len(b)})")
             tape.close()
+
+
+@pytest.mark.parametrize("bpi,pi,mode", [(1600, 0, "nrzi"), (556, 1, "nrzi"), (300, 4, "nrzi"), (200, 0, "nrzi"), (800, 0, "pe"), (400, 2, "pe"), (1100, 6, "pe")])
+def test_fast_path_other_window_widths(bpi, pi, mode, fast_host, oracle_lib):
+    """window widths 3..50 (ring sizes 64 and 128, windows longer than a batch of rows), PE feedback, odd skews: the same
+    synthetic samples scanned under other densities -- not a meaningful decode, but every event must match the oracle"""
+    hdr, rows = synth.nrzi_tape(nblocks=4, seed=5)
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    planes, stride = make_planes(rows, desc)
+    m = tbin.MODE_NRZI if mode == "nrzi" else tbin.MODE_PE
+    table = parmsets.NRZI if mode == "nrzi" else parmsets.PE
+    cfg = abi.make_cfg(m, table[pi], float(bpi), hdr.ips, skew=[1, 0, 5, 2, 0, 9, 3, 0, 17])
+    tape = oracle_lib.open(desc); tape.upload(rows)
+    w = oracle_lib.L.rt_pkww_width(C.byref(cfg), hdr.tdelta_ns)
+    assert 3 <= w <= 50
+    for row0 in (0, 32 * 211):
+        sc = tape.scan(cfg); sc.reset(abi.RT_RESET_FULL, row0)
+        want, _ = sc.run(rows.shape[0]); sc.end()
+        for skip in (1, 0):
+            got = fast_scan(fast_host, planes, stride, rows.shape[0], desc, cfg, row0, rows.shape[0], skip=skip)
+            assert got is not None and not any(fast_scan.failed), fast_scan.failed
+            a, b = evlog.to_canon(got), evlog.to_canon(want)
+            if a.tobytes() != b.tobytes():
+                k = evlog._first_diff(a, b)
+                pytest.fail(f"bpi {bpi} width {w} parmset {pi} row0 {row0} skip {skip}: event #{k}: fast {a[k] if k < len(a) else None} "
+                            f"oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)})")
+    tape.close()

@@ -202,11 +202,13 @@ def test_fast_kernel_on_synthetic_tape_equals_oracle(cuda_lib, oracle_lib):
     desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
     tg, to = cuda_lib.open(desc), oracle_lib.open(desc)
     tg.upload(rows); to.upload(rows)
-    for pi in (0, 5):
-        cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[pi], hdr.bpi, hdr.ips)
+    for pi, bpi, mode, skew in ((0, hdr.bpi, tbin.MODE_NRZI, None), (5, hdr.bpi, tbin.MODE_NRZI, None), (1, 556.0, tbin.MODE_NRZI, [1, 0, 5, 2, 0, 9, 3, 0, 17]),
+                                (0, 200.0, tbin.MODE_NRZI, None), (2, 400.0, tbin.MODE_PE, [0, 3, 0, 0, 7, 0, 0, 1, 0]), (0, 1600.0, tbin.MODE_PE, None)):
+        table = parmsets.NRZI if mode == tbin.MODE_NRZI else parmsets.PE
+        cfg = abi.make_cfg(mode, table[pi], bpi, hdr.ips, skew=skew)       # other densities: window widths 6..50, ring sizes 64 / 128
         bulk = tg.bulk_scan([cfg])
         units = _all_units(bulk)
-        assert len(units) >= 20
+        assert len(units) >= 1
         sc = to.scan(cfg)
         for ui in units:
             r = bulk.lookup(0, ui["row0"])
