@@ -75,3 +75,17 @@ def gather(obj, dist=None, dst: int = 0):
     out = [None] * dist.get_world_size() if dist.get_rank() == dst else None
     dist.gather_object(obj, out, dst=dst)
     return out
+
+
+def assign_units(nparmsets: int, nshards: int, world: int):
+    """(parameter set, time shard) scan units -> ranks (BASELINE config 4: tracks x parmsets sharded over the GPUs of a box).
+
+    A parameter-set retry is a full independent re-scan of the same rows (readtape.c:1755-1795), so the unit of work is
+    (parmset p, time shard s).  Units are dealt round-robin in shard-major order: consecutive ranks take the parameter sets
+    of the SAME shard, so that a rank needs as few different shards (= host->device copies) as possible, and the load
+    differs by at most one unit.  -> list over ranks of [(p, s), ...]"""
+    units = [(p, s) for s in range(nshards) for p in range(nparmsets)]
+    out = [[] for _ in range(world)]
+    for i, u in enumerate(units):
+        out[i * world // len(units) if len(units) >= world else i].append(u)
+    return out

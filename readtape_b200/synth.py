@@ -139,3 +139,56 @@ def nrzi_tape(nblocks: int = 8, seed: int = 7, **kw):
 
 def tile_sha256(tile: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(tile).tobytes()).hexdigest()
+
+
+# ---- GCR-density workload (BASELINE config 4) ----------------------------------------------------------------------
+GCR_TDELTA_NS = 160                                  # 6.25 MHz
+GCR_ROWS_PER_BIT = 1.0 / (9042 * 50 * 160e-9)        # 13.82
+
+
+def gcr_like_tile(seed: int = 0xC0FFEE, nblocks: int = 4, bits_per_block: int = 45_000, gap_rows: int = 37_500,
+                  ntrks: int = 9, noise_mv: float = 4.0) -> np.ndarray:
+    """A tape tile at GCR 6250 density (9042 flux cells per inch, 50 IPS, 6.25 MHz sampling, maxvolts 3.2): every track carries
+    an independent random run-length-limited bit stream (at most two 0 cells between 1 cells, as 5-bit GCR groups guarantee),
+    one flux reversal per 1 cell, alternating polarity raised-cosine pulses, 0.3-inch gaps.  It has the transition density,
+    amplitudes and block/gap proportions of a 6250 BPI reel, which is what the scan cost depends on; it is NOT a decodable
+    GCR block (no sync marks / ECC), so it is a throughput workload only -- parity for GCR uses the reference's captures."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    period = int(bits_per_block * GCR_ROWS_PER_BIT) + gap_rows
+    period = (period + 2047) // 2048 * 2048                       # whole ingest tiles per block period
+    nrows = period * nblocks
+    volts = np.zeros((ntrks, nrows + 64), dtype=np.float64)
+    hw = 0.55 * GCR_ROWS_PER_BIT
+    k = np.arange(-9, 10)
+    for b in range(nblocks):
+        start = b * period + gap_rows // 2
+        for trk in range(ntrks):
+            bits = rng.random(bits_per_block) < 0.62
+            run = 0
+            for i in range(bits_per_block):                        # enforce the (0,2) run-length limit
+                if bits[i]:
+                    run = 0
+                else:
+                    run += 1
+                    if run > 2:
+                        bits[i] = True; run = 0
+            cells = np.flatnonzero(bits)
+            times = start + (cells + 0.5) * GCR_ROWS_PER_BIT * (1.0 + 0.004 * np.sin(2 * np.pi * cells / 9000.0)) + 0.37 * trk
+            sign = np.where(np.arange(len(times)) % 2 == 0, 1.0, -1.0)
+            amp = 1.6 + 0.05 * trk
+            centre = np.floor(times).astype(np.int64)
+            idx = centre[:, None] + k[None, :]
+            dt = idx - times[:, None]
+            pulse = np.where(np.abs(dt) < hw, 0.5 * (1.0 + np.cos(np.pi * dt / hw)), 0.0)
+            np.add.at(volts[trk], idx.ravel(), (pulse * (amp * sign)[:, None]).ravel())
+    volts = volts[:, :nrows]
+    volts += rng.normal(0.0, noise_mv * 1e-3, size=volts.shape)
+    q = np.rint(volts / 3.2 * 32767.0)
+    np.clip(q, -32767, 32767, out=q)
+    return np.ascontiguousarray(q.T.astype("<i2"))
+
+
+def gcr_header(tstart_ns: int = 1_000_000_000) -> TbinHeader:
+    from .tbin import MODE_GCR
+    return TbinHeader(descr="synthetic GCR-density flux pattern (readtape_b200.synth)", flags=0, ntrks=9, tdelta_ns=GCR_TDELTA_NS,
+                      maxvolts=3.2, mode=MODE_GCR, bpi=9042.0, ips=50.0, tstart_ns=tstart_ns)

@@ -92,3 +92,18 @@ def test_plan_cuts_only_in_gaps():
             if b < rows.shape[0]:
                 assert any(s < b < e for s, e in gaps), (world, sh)
                 assert b % shard.GRAN == 0
+
+
+@pytest.mark.parametrize("nparm,nshards,world", [(5, 8, 8), (5, 1, 8), (8, 2, 4), (1, 8, 8), (5, 3, 2), (2, 1, 1)])
+def test_parmset_by_shard_units_are_dealt_evenly(nparm, nshards, world):
+    """config 4: 5 GCR parameter sets x time shards over 8 GPUs -- every unit exactly once, loads within one unit,
+    and a rank touches as few different shards as possible"""
+    per_rank = shard.assign_units(nparm, nshards, world)
+    flat = [u for r in per_rank for u in r]
+    assert sorted(flat) == sorted((p, s) for p in range(nparm) for s in range(nshards))
+    loads = [len(r) for r in per_rank]
+    if nparm * nshards >= world:
+        assert max(loads) - min(loads) <= 1, loads
+    for r in per_rank:
+        shards_touched = {s for _, s in r}
+        assert len(shards_touched) <= (len(r) + nparm - 1) // nparm + 1

@@ -15,6 +15,9 @@ for exe, env in (("readtape_b200/bin/readtape_b200", {"RT_STATS": "1"}), ("readt
     r = subprocess.run([exe, "-q", "-nm", "-nrzi", "-bpi=800", "-ips=50", "-tap", "-nolog", "-nolabels", f"-outf={d}/out_{os.path.basename(exe)}", path],
                        capture_output=True, text=True, env=dict(os.environ, **env))
     dt = time.time() - t0
-    print(os.path.basename(exe), f"rc={r.returncode} {dt:.2f}s  {nrows*9/dt/1e6:.1f} M track-samples/s", (r.stdout.strip().splitlines() or [""])[-1][:160])
+    print(os.path.basename(exe), f"rc={r.returncode} {dt:.2f}s  {nrows*9/dt/1e6:.1f} M track-samples/s")
+    for l in r.stdout.splitlines():
+        if "B200 scan:" in l:
+            print("   ", l.strip())
 a = open(f"{d}/out_readtape_b200.tap", "rb").read(); b = open(f"{d}/out_readtape_ref.tap", "rb").read()
 print("tap identical:", a == b, len(a))
