@@ -60,6 +60,7 @@ struct rt_tape {
    rt_event *pool_cache = nullptr; uint32_t *next_cache = nullptr; uint32_t pool_cache_chunks = 0; bool pool_cache_busy = false;
    rt_event *pin_cache = nullptr; size_t pin_cache_events = 0; bool pin_cache_busy = false;
    /* rt_bulk_scan_host(): extra streams, and the sizes the last whole-tape scan needed (capacity planning of the streamed scan) */
+   std::vector<cudaStream_t> s_par;                               /* rt_bulk_scan with several configurations: their kernels run side by side */
    cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[2] = {nullptr, nullptr};
    uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
 };
@@ -234,6 +235,7 @@ extern "C" void rt_close(rt_tape *t) {
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
    if (t->s_copy) cudaStreamDestroy(t->s_copy);
    if (t->stream) cudaStreamDestroy(t->stream);
+   for (auto st : t->s_par) cudaStreamDestroy(st);
    if (t->s_scan) cudaStreamDestroy(t->s_scan);
    if (t->s_out) cudaStreamDestroy(t->s_out);
    delete t; }
@@ -414,17 +416,19 @@ extern "C" void rt_scan_end(rt_scan *s) {
 /* ---- speculative whole-tape scan ---------------------------------------------------------------- */
 struct BulkCfg {
    rt_scan_cfg cfg{}; DevCfg dc{};
-   /* device-resident results of the scan */
-   UnitDesc *d_units = nullptr; TrkMeta *d_meta = nullptr; rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr;
-   uint32_t nunits = 0, pool_chunks = 0, chunks_used = 0;
-   bool pool_from_cache = false, pin_from_cache = false, fast = false;
-   /* host copies, filled by rt_bulk_fetch() */
-   std::vector<UnitDesc> units; std::vector<TrkMeta> meta; std::vector<uint32_t> chunk_next;
-   rt_event *h_pool = nullptr; size_t h_pool_events = 0;      /* pinned */
+   UnitDesc *d_units = nullptr; TrkMeta *d_meta = nullptr;       /* device-resident results of the scan */
+   uint32_t nunits = 0;
+   bool fast = false;
+   std::vector<UnitDesc> units; std::vector<TrkMeta> meta;        /* host copies, filled by rt_bulk_fetch() */
 };
 struct rt_bulk {
    rt_tape *tape = nullptr; std::vector<BulkCfg> cfgs; rt_bulk_stats stats{};
    bool fetched = false;
+   /* ONE event pool for all configurations of a scan: their kernels run concurrently and take chunks from the same cursor */
+   rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr; uint32_t pool_chunks = 0, chunks_used = 0;
+   bool pool_from_cache = false, pin_from_cache = false;
+   rt_event *h_pool = nullptr; size_t h_pool_events = 0;          /* pinned */
+   std::vector<uint32_t> chunk_next;
    std::vector<rt_event> result;
 };
 
@@ -470,11 +474,11 @@ static cudaError_t launch_scan(const rt_tape *t, const ScanPlan &pl, const UnitD
 
 extern "C" void rt_bulk_free(rt_bulk *b) {
    if (!b) return;
-   cudaSetDevice(b->tape->device);
-   for (auto &c : b->cfgs) {
-      if (c.pin_from_cache) b->tape->pin_cache_busy = false; else if (c.h_pool) cudaFreeHost(c.h_pool);
-      if (c.pool_from_cache) b->tape->pool_cache_busy = false; else { cudaFree(c.d_pool); cudaFree(c.d_chunk_next); }
-      if (c.d_units) cudaFreeAsync(c.d_units, b->tape->stream); if (c.d_meta) cudaFreeAsync(c.d_meta, b->tape->stream); }
+   rt_tape *t = b->tape;
+   cudaSetDevice(t->device);
+   if (b->pin_from_cache) t->pin_cache_busy = false; else if (b->h_pool) cudaFreeHost(b->h_pool);
+   if (b->pool_from_cache) t->pool_cache_busy = false; else { cudaFree(b->d_pool); cudaFree(b->d_chunk_next); }
+   for (auto &c : b->cfgs) { if (c.d_units) cudaFreeAsync(c.d_units, t->stream); if (c.d_meta) cudaFreeAsync(c.d_meta, t->stream); }
    delete b; }
 
 extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bulk **out) {
@@ -497,90 +501,105 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    b->tape = t; b->cfgs.resize(ncfgs);
    const uint32_t nt = t->desc.ntrks; const uint64_t nrows = t->nrows_valid;
    int launches0 = t->launches;
-   /* scratch for the unit finder */
+   /* scratch for the unit finder; one set of counters per configuration */
    const size_t words = units_bitmap_words(nrows), nblocks = units_blocks(nrows) + 1;
    const uint32_t units_cap = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
    uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr;
    cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
+   std::vector<cudaEvent_t> done_ev(ncfgs, nullptr);
    auto cleanup = [&]() {
       void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
-      for (auto &e : ev) cudaEventDestroy(e); };
-#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); rt_bulk_free(b); \
+      for (auto &e : ev) cudaEventDestroy(e);
+      for (auto e : done_ev) if (e) cudaEventDestroy(e); };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); rt_bulk_free(b); \
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
    CUB(cudaMallocAsync(&d_bitmap, words * 4, t->stream)); CUB(cudaMallocAsync(&d_flags, words * 4, t->stream)); CUB(cudaMallocAsync(&d_blockcount, nblocks * 4, t->stream));
    CUB(cudaMallocAsync(&d_nunits, 4, t->stream)); CUB(cudaMallocAsync(&d_units_tmp, (size_t)units_cap * sizeof(UnitDesc), t->stream));
-   CUB(cudaMallocAsync(&d_counters, 32, t->stream)); CUB(cudaMallocAsync(&d_cursor, 4, t->stream));
+   CUB(cudaMallocAsync(&d_counters, 32 * (size_t)ncfgs, t->stream)); CUB(cudaMallocAsync(&d_cursor, 4, t->stream));
+   if (ncfgs > 1 && t->s_par.empty()) {                           /* streams for the configurations' scan kernels */
+      t->s_par.resize(4);
+      for (auto &st : t->s_par) CUB(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); }
    lap("scratch alloc");
    b->stats.rows = nrows; b->stats.ms_preprocess = t->ms_ingest;
+
+   /* 1. unit tables, one per configuration (the proposal thresholds depend on it) */
+   std::vector<ScanPlan> plans(ncfgs);
+   uint64_t total_units = 0;
    for (uint32_t ci = 0; ci < ncfgs; ++ci) {
       BulkCfg &bc = b->cfgs[ci];
-      ScanPlan pl; make_plan(t, &cfgs[ci], &pl);
+      ScanPlan &pl = plans[ci]; make_plan(t, &cfgs[ci], &pl);
       bc.cfg = cfgs[ci]; bc.dc = pl.dc; bc.fast = pl.use_fast;
-      const UnitParams &up = pl.up;
       CUB(cudaEventRecord(ev[0], t->stream));
-      cudaError_t e = launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap, d_nunits, t->stream, &t->launches);
-      CUB(e);
+      CUB(launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, pl.up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap, d_nunits, t->stream, &t->launches));
       CUB(cudaEventRecord(ev[1], t->stream));
       uint32_t nunits = 0;
       CUB(cudaMemcpyAsync(&nunits, d_nunits, 4, cudaMemcpyDeviceToHost, t->stream));
       CUB(cudaStreamSynchronize(t->stream));
-      lap("unit finder + sync");
       if (nunits > units_cap) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "unit table overflow (%u > %u)", nunits, units_cap); }
-      bc.nunits = nunits;
-      float ms_scan = 0;
+      bc.nunits = nunits; total_units += nunits;
+      float ms_units = 0; cudaEventElapsedTime(&ms_units, ev[0], ev[1]); b->stats.ms_units += ms_units;
       if (nunits) {
          CUB(cudaMallocAsync(&bc.d_units, (size_t)nunits * sizeof(UnitDesc), t->stream));
          CUB(cudaMemcpyAsync(bc.d_units, d_units_tmp, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToDevice, t->stream));
-         CUB(cudaMallocAsync(&bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta), t->stream));
-         /* event pool: first guess one event per 16 track-samples, regrown on overflow */
-         uint64_t want_chunks = std::max<uint64_t>(4096, nrows * nt / 16 / RT_EVC + (uint64_t)nunits * nt);
-         for (int attempt = 0; attempt < 3; ++attempt) {
-            if (want_chunks > bc.pool_chunks) {
-               if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
-               if (bc.pool_from_cache || (!bc.d_pool && !t->pool_cache_busy)) {       /* use / grow the tape's cached pool */
-                  if (want_chunks > t->pool_cache_chunks) {
-                     cudaFree(t->pool_cache); cudaFree(t->next_cache); t->pool_cache = nullptr; t->next_cache = nullptr; t->pool_cache_chunks = 0;
-                     CUB(cudaMalloc(&t->pool_cache, (size_t)want_chunks * RT_EVC * sizeof(rt_event)));
-                     CUB(cudaMalloc(&t->next_cache, (size_t)want_chunks * 4));
-                     t->pool_cache_chunks = (uint32_t)want_chunks; }
-                  bc.d_pool = t->pool_cache; bc.d_chunk_next = t->next_cache; bc.pool_chunks = t->pool_cache_chunks;
-                  bc.pool_from_cache = true; t->pool_cache_busy = true; }
-               else {
-                  cudaFree(bc.d_pool); cudaFree(bc.d_chunk_next); bc.d_pool = nullptr; bc.d_chunk_next = nullptr;
-                  bc.pool_chunks = (uint32_t)want_chunks;
-                  CUB(cudaMalloc(&bc.d_pool, (size_t)bc.pool_chunks * RT_EVC * sizeof(rt_event)));
-                  CUB(cudaMalloc(&bc.d_chunk_next, (size_t)bc.pool_chunks * 4)); } }
-            CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
-            CUB(cudaMemsetAsync(d_counters, 0, 32, t->stream));
-            CUB(cudaEventRecord(ev[2], t->stream));
-            CUB(launch_scan(t, pl, bc.d_units, nunits, bc.d_meta, bc.d_pool, bc.d_chunk_next, d_cursor, bc.pool_chunks, d_counters, 0, t->stream));
+         CUB(cudaMallocAsync(&bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta), t->stream)); } }
+   b->stats.units = b->cfgs[ncfgs - 1].nunits;
+   lap("unit finder + sync");
+
+   /* 2. all scan kernels, concurrently, into one event pool: first guess one event per 16 track-samples, regrown on overflow */
+   if (total_units) {
+      uint64_t want_chunks = std::max<uint64_t>(4096, (uint64_t)ncfgs * (nrows * nt / 16 / RT_EVC) + total_units * nt);
+      for (int attempt = 0; attempt < 3; ++attempt) {
+         if (want_chunks > b->pool_chunks) {
+            if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
+            if (b->pool_from_cache || (!b->d_pool && !t->pool_cache_busy)) {          /* use / grow the tape's cached pool */
+               if (want_chunks > t->pool_cache_chunks) {
+                  cudaFree(t->pool_cache); cudaFree(t->next_cache); t->pool_cache = nullptr; t->next_cache = nullptr; t->pool_cache_chunks = 0;
+                  CUB(cudaMalloc(&t->pool_cache, (size_t)want_chunks * RT_EVC * sizeof(rt_event)));
+                  CUB(cudaMalloc(&t->next_cache, (size_t)want_chunks * 4));
+                  t->pool_cache_chunks = (uint32_t)want_chunks; }
+               b->d_pool = t->pool_cache; b->d_chunk_next = t->next_cache; b->pool_chunks = t->pool_cache_chunks;
+               b->pool_from_cache = true; t->pool_cache_busy = true; }
+            else {
+               cudaFree(b->d_pool); cudaFree(b->d_chunk_next); b->d_pool = nullptr; b->d_chunk_next = nullptr;
+               b->pool_chunks = (uint32_t)want_chunks;
+               CUB(cudaMalloc(&b->d_pool, (size_t)b->pool_chunks * RT_EVC * sizeof(rt_event)));
+               CUB(cudaMalloc(&b->d_chunk_next, (size_t)b->pool_chunks * 4)); } }
+         CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
+         CUB(cudaMemsetAsync(d_counters, 0, 32 * (size_t)ncfgs, t->stream));
+         CUB(cudaEventRecord(ev[2], t->stream));
+         for (uint32_t ci = 0; ci < ncfgs; ++ci) {
+            BulkCfg &bc = b->cfgs[ci];
+            if (!bc.nunits) continue;
+            cudaStream_t st = ncfgs > 1 ? t->s_par[ci % t->s_par.size()] : t->stream;
+            if (st != t->stream) CUB(cudaStreamWaitEvent(st, ev[2], 0));
+            CUB(launch_scan(t, plans[ci], bc.d_units, bc.nunits, bc.d_meta, b->d_pool, b->d_chunk_next, d_cursor, b->pool_chunks, d_counters + 4 * ci, 0, st));
             ++t->launches;
-            CUB(cudaEventRecord(ev[3], t->stream));
-            unsigned int used = 0;
-            CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
-            CUB(cudaStreamSynchronize(t->stream));
-            float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_scan = ms;
-            lap("scan kernel + sync");
-            if (used <= bc.pool_chunks) { bc.chunks_used = used; break; }
-            want_chunks = (uint64_t)used + used / 8 + 1024;
-            if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
-         unsigned long long counters[2] = {0, 0};
-         CUB(cudaMemcpy(counters, d_counters, 16, cudaMemcpyDeviceToHost));
-         b->stats.rows_scanned += counters[0]; b->stats.events += counters[1]; }
-      float ms_units = 0; cudaEventElapsedTime(&ms_units, ev[0], ev[1]);
-      b->stats.ms_units += ms_units; b->stats.ms_scan += ms_scan;
-      b->stats.units = nunits; }
+            if (st != t->stream) {
+               if (!done_ev[ci]) CUB(cudaEventCreateWithFlags(&done_ev[ci], cudaEventDisableTiming));
+               CUB(cudaEventRecord(done_ev[ci], st)); CUB(cudaStreamWaitEvent(t->stream, done_ev[ci], 0)); } }
+         CUB(cudaEventRecord(ev[3], t->stream));
+         unsigned int used = 0;
+         CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
+         CUB(cudaStreamSynchronize(t->stream));
+         float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); b->stats.ms_scan = ms;
+         lap("scan kernel(s) + sync");
+         if (used <= b->pool_chunks) { b->chunks_used = used; break; }
+         want_chunks = (uint64_t)used + used / 8 + 1024;
+         if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
+      std::vector<unsigned long long> counters(4 * (size_t)ncfgs, 0);
+      CUB(cudaMemcpy(counters.data(), d_counters, 32 * (size_t)ncfgs, cudaMemcpyDeviceToHost));
+      for (uint32_t ci = 0; ci < ncfgs; ++ci) { b->stats.rows_scanned += counters[4 * ci]; b->stats.events += counters[4 * ci + 1]; } }
    lap("counters");
    b->stats.track_samples = nrows * nt * ncfgs;
    b->stats.launches = (uint32_t)(t->launches - launches0);
-   if (ncfgs == 1) { t->hist_rows = nrows; t->hist_units = b->cfgs[0].nunits; t->hist_chunks = b->cfgs[0].chunks_used; }   /* sizes the streamed scan */
+   if (ncfgs == 1) { t->hist_rows = nrows; t->hist_units = b->cfgs[0].nunits; t->hist_chunks = b->chunks_used; }   /* sizes the streamed scan */
    cleanup();
 #undef CUB
    *out = b; return RT_OK; }
 
-/* Bring the results of rt_bulk_scan() to the host (unit table, proof data, events).  Called by the first
+/* Bring the results of rt_bulk_scan() to the host (unit tables, proof data, events).  Called by the first
  * rt_bulk_lookup(); separate so that a caller can overlap it or time it. */
 extern "C" int rt_bulk_fetch(rt_bulk *b) {
    if (!b) return set_err(RT_ERR_ARG, "rt_bulk_fetch: null");
@@ -589,31 +608,33 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
    CU(cudaSetDevice(t->device));
    for (BulkCfg &bc : b->cfgs) {
       const uint32_t nunits = bc.nunits;
-      bc.units.resize(nunits); bc.meta.resize((size_t)nunits * nt); bc.chunk_next.resize(bc.chunks_used);
+      bc.units.resize(nunits); bc.meta.resize((size_t)nunits * nt);
       if (!nunits) continue;
       CU(cudaMemcpyAsync(bc.units.data(), bc.d_units, (size_t)nunits * sizeof(UnitDesc), cudaMemcpyDeviceToHost, t->stream));
       CU(cudaMemcpyAsync(bc.meta.data(), bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta), cudaMemcpyDeviceToHost, t->stream));
-      if (bc.chunks_used) {
-         CU(cudaMemcpyAsync(bc.chunk_next.data(), bc.d_chunk_next, (size_t)bc.chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
-         bc.h_pool_events = (size_t)bc.chunks_used * RT_EVC;
-         if (!t->pin_cache_busy) {                                  /* use / grow the tape's cached pinned buffer */
-            if (bc.h_pool_events > t->pin_cache_events) {
-               if (t->pin_cache) cudaFreeHost(t->pin_cache);
-               t->pin_cache = nullptr; t->pin_cache_events = 0;
-               size_t want = bc.h_pool_events + bc.h_pool_events / 16;
-               CU(cudaHostAlloc(&t->pin_cache, want * sizeof(rt_event), cudaHostAllocDefault));
-               t->pin_cache_events = want; }
-            bc.h_pool = t->pin_cache; bc.pin_from_cache = true; t->pin_cache_busy = true; }
-         else CU(cudaHostAlloc(&bc.h_pool, bc.h_pool_events * sizeof(rt_event), cudaHostAllocDefault));
-         CU(cudaMemcpyAsync(bc.h_pool, bc.d_pool, bc.h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
-         b->stats.d2h_bytes += bc.h_pool_events * sizeof(rt_event) + (uint64_t)bc.chunks_used * 4; }
       b->stats.d2h_bytes += (uint64_t)nunits * (sizeof(UnitDesc) + nt * sizeof(TrkMeta)); }
+   b->chunk_next.resize(b->chunks_used);
+   if (b->chunks_used) {
+      CU(cudaMemcpyAsync(b->chunk_next.data(), b->d_chunk_next, (size_t)b->chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
+      b->h_pool_events = (size_t)b->chunks_used * RT_EVC;
+      if (!t->pin_cache_busy) {                                  /* use / grow the tape's cached pinned buffer */
+         if (b->h_pool_events > t->pin_cache_events) {
+            if (t->pin_cache) cudaFreeHost(t->pin_cache);
+            t->pin_cache = nullptr; t->pin_cache_events = 0;
+            size_t want = b->h_pool_events + b->h_pool_events / 16;
+            CU(cudaHostAlloc(&t->pin_cache, want * sizeof(rt_event), cudaHostAllocDefault));
+            t->pin_cache_events = want; }
+         b->h_pool = t->pin_cache; b->pin_from_cache = true; t->pin_cache_busy = true; }
+      else CU(cudaHostAlloc(&b->h_pool, b->h_pool_events * sizeof(rt_event), cudaHostAllocDefault));
+      CU(cudaMemcpyAsync(b->h_pool, b->d_pool, b->h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
+      b->stats.d2h_bytes += b->h_pool_events * sizeof(rt_event) + (uint64_t)b->chunks_used * 4; }
    CU(cudaStreamSynchronize(t->stream));
    /* the device copies are no longer needed */
    for (BulkCfg &bc : b->cfgs) {
       if (bc.d_units) cudaFreeAsync(bc.d_units, t->stream); if (bc.d_meta) cudaFreeAsync(bc.d_meta, t->stream);
-      if (bc.pool_from_cache) { t->pool_cache_busy = false; bc.pool_from_cache = false; } else { cudaFree(bc.d_pool); cudaFree(bc.d_chunk_next); }
-      bc.d_units = nullptr; bc.d_meta = nullptr; bc.d_pool = nullptr; bc.d_chunk_next = nullptr; }
+      bc.d_units = nullptr; bc.d_meta = nullptr; }
+   if (b->pool_from_cache) { t->pool_cache_busy = false; b->pool_from_cache = false; } else { cudaFree(b->d_pool); cudaFree(b->d_chunk_next); }
+   b->d_pool = nullptr; b->d_chunk_next = nullptr;
    b->fetched = true;
    return RT_OK; }
 
@@ -724,10 +745,10 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
       { float ms = 0; cudaEventElapsedTime(&ms, ev_a, ev_b); ms_scan += ms; }
       if (trace) fprintf(stderr, "[rt_bulk_scan_host] segment %zu: rows %llu, units %u..%u, chunks %u..%u\n", k, (unsigned long long)R, u_done, u_final, c_done, used);
       if (used > cap_chunks) { failed = true; why = "more events than the previous scan"; break; }
-      bc.meta.resize((size_t)u_final * nt); bc.chunk_next.resize(used);
+      bc.meta.resize((size_t)u_final * nt); b->chunk_next.resize(used);
       CUS(cudaMemcpy(bc.meta.data() + (size_t)u_done * nt, d_meta + (size_t)u_done * nt, (size_t)(u_final - u_done) * nt * sizeof(TrkMeta), cudaMemcpyDeviceToHost));
       if (used > c_done) {
-         CUS(cudaMemcpy(bc.chunk_next.data() + c_done, d_chunk_next + c_done, (size_t)(used - c_done) * 4, cudaMemcpyDeviceToHost));
+         CUS(cudaMemcpy(b->chunk_next.data() + c_done, d_chunk_next + c_done, (size_t)(used - c_done) * 4, cudaMemcpyDeviceToHost));
          CUS(cudaMemcpyAsync(h_pool + (size_t)c_done * RT_EVC, d_pool + (size_t)c_done * RT_EVC, (size_t)(used - c_done) * RT_EVC * sizeof(rt_event),
                              cudaMemcpyDeviceToHost, t->s_out)); }
       b->stats.d2h_bytes += (uint64_t)(used - c_done) * (RT_EVC * sizeof(rt_event) + 4) + (uint64_t)(u_final - u_done) * (sizeof(UnitDesc) + nt * sizeof(TrkMeta));
@@ -743,8 +764,8 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
       return rt_bulk_fetch(*out); }
    unsigned long long counters[2] = {0, 0};
    CUS(cudaMemcpy(counters, d_counters, 16, cudaMemcpyDeviceToHost));
-   bc.nunits = nun; bc.chunks_used = c_done; bc.pool_chunks = cap_chunks;
-   bc.h_pool = h_pool; bc.h_pool_events = (size_t)c_done * RT_EVC; bc.pin_from_cache = true;
+   bc.nunits = nun; b->chunks_used = c_done; b->pool_chunks = cap_chunks;
+   b->h_pool = h_pool; b->h_pool_events = (size_t)c_done * RT_EVC; b->pin_from_cache = true;
    t->pool_cache_busy = false;                                    /* the device pool is free again; the pinned copy belongs to the bulk */
    b->fetched = true;
    b->stats.rows = nrows; b->stats.units = nun; b->stats.events = counters[1]; b->stats.rows_scanned = counters[0];
@@ -849,12 +870,12 @@ extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const
    for (size_t n = 0; n < total; ++n) {
       int best = -1; uint64_t brow = ~0ull;
       for (uint32_t k = 0; k < nt; ++k) if (cc[k].left) {
-            const rt_event &e = bc.h_pool[(size_t)cc[k].chunk * RT_EVC + cc[k].slot];
+            const rt_event &e = b->h_pool[(size_t)cc[k].chunk * RT_EVC + cc[k].slot];
             if (e.row < brow) { brow = e.row; best = (int)k; } }
       CC &c = cc[best];
-      b->result.push_back(bc.h_pool[(size_t)c.chunk * RT_EVC + c.slot]);
+      b->result.push_back(b->h_pool[(size_t)c.chunk * RT_EVC + c.slot]);
       --c.left;
-      if (++c.slot == RT_EVC) { c.slot = 0; c.chunk = c.left ? bc.chunk_next[c.chunk] : RT_NOCHUNK; } }
+      if (++c.slot == RT_EVC) { c.slot = 0; c.chunk = c.left ? b->chunk_next[c.chunk] : RT_NOCHUNK; } }
    if (events) *events = b->result.data();
    if (nevents) *nevents = b->result.size();
    if (valid_rows) *valid_rows = ue.row_end - start_row;
