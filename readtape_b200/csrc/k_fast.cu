@@ -8,6 +8,7 @@
  * unit-equivalence proof data.
  */
 #include "scan_fast.cuh"
+#include "scan_zc.cuh"
 #include "kernels.h"
 #include "emit.cuh"
 
@@ -57,13 +58,42 @@ k_units_fast(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
    UnitScan<FAST_THREADS, PoolEmit> us(c, mem);
    drive(us, jobs, WarpCount()); }
 
+/* the zero-crossing fast path for GCR (scan_zc.cuh): same driver, same job groups */
+__global__ void __launch_bounds__(FAST_THREADS, 4)
+k_units_zc(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
+           rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, unsigned long long *rows_scanned) {
+   extern __shared__ __align__(16) uint32_t fast_smem[];
+   ZcMem<FAST_THREADS> mem = zc_mem<FAST_THREADS>(fast_smem + threadIdx.x);
+   const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
+   DevJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, 0, rows_scanned, total, 0, false};
+   ZcScan<FAST_THREADS, PoolEmit> us(c, mem);
+   drive(us, jobs, WarpCount()); }
+
 bool fast_scan_eligible(const DevCfg &c) {
+   if (zc_scan_eligible(c)) return true;
    return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
           && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH; }
 
 cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                               uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                               unsigned long long *rows_scanned, int sms, int max_ctas_per_sm, cudaStream_t s) {
+   if (zc_scan_eligible(c)) {
+      const size_t zsmem = (size_t)zc_scratch_words(c) * FAST_THREADS * sizeof(uint32_t);
+      static size_t zcfg_smem = 0; static int zcfg_per_sm = 0;
+      cudaError_t ze;
+      if (zcfg_smem != zsmem) {
+         ze = cudaFuncSetAttribute(k_units_zc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem); if (ze != cudaSuccess) return ze;
+         ze = cudaFuncSetAttribute(k_units_zc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); if (ze != cudaSuccess) return ze;
+         ze = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zcfg_per_sm, k_units_zc, FAST_THREADS, zsmem); if (ze != cudaSuccess) return ze;
+         zcfg_smem = zsmem; }
+      int zper = zcfg_per_sm < 1 ? 1 : zcfg_per_sm;
+      if (max_ctas_per_sm > 0 && zper > max_ctas_per_sm) zper = max_ctas_per_sm;
+      uint64_t zgrid = ((uint64_t)nunits * (uint64_t)c.ntrks + FAST_THREADS - 1) / FAST_THREADS;
+      if (zgrid > (uint64_t)sms * (uint64_t)zper) zgrid = (uint64_t)sms * (uint64_t)zper;
+      if (zgrid < 1) zgrid = 1;
+      ze = cudaMemsetAsync(rows_scanned + 2, 0, sizeof(unsigned long long), s); if (ze != cudaSuccess) return ze;
+      k_units_zc<<<(unsigned)zgrid, FAST_THREADS, zsmem, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, rows_scanned);
+      return cudaGetLastError(); }
    const uint32_t ring = ring_size(c.width);
    const size_t smem = (size_t)scratch_words(c.width) * FAST_THREADS * sizeof(uint32_t);
    static size_t cfg_smem = 0; static int cfg_per_sm = 0;          /* function attributes: set once per shared-memory size */

@@ -8,6 +8,7 @@
 #include <vector>
 #include <cstdint>
 #include "scan_fast.cuh"
+#include "scan_zc.cuh"
 #include "cfg_host.h"
 
 struct HostEmit {
@@ -52,6 +53,13 @@ extern "C" int fast_host_scan_unit(const int16_t *planes, uint64_t plane_stride,
             for (uint64_t r = g * RT_GRAN; r < (g + 1) * RT_GRAN && r < nrows; ++r) { int v = planes[(size_t)k * plane_stride + r]; if (v < mn) mn = v; if (v > mx) mx = v; }
             gmm[(size_t)k * ngran + g] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); }
       dc.gmm = gmm.data(); dc.ngran_cap = ngran; }
+   if (rtfast::zc_scan_eligible(dc)) {                             /* the zero-crossing fast path (GCR -zeros) */
+      std::vector<uint32_t> zs(rtfast::zc_scratch_words(dc), 0x7fff8000u);
+      rtfast::ZcMem<1> zm = rtfast::zc_mem<1>(zs.data());
+      HostJobs zjobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, 0, 0, false};
+      rtfast::ZcScan<1, HostEmit> zus(dc, zm);
+      rtfast::drive(zus, zjobs, HostCount());
+      return RT_OK; }
    const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE) && !dc.invert && !dc.differentiate
                          && !dc.density && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
    if (!eligible) return RT_ERR_UNSUPPORTED;

@@ -58,7 +58,7 @@ def fast_scan(L, planes, stride, nrows, desc, cfg, row0, row_end, cap=1 << 16, s
     return ev[order]
 
 
-ELIGIBLE = ["Microdata_20blks.nm_tap", "Microdata_20blks", "PLAGO_beginning.nm_tap", "PLAGO_beginning", "1600bpi_ukn_6s",
+ELIGIBLE = ["sf93_8blks", "1kblks_43blks", "Microdata_20blks.nm_tap", "Microdata_20blks", "PLAGO_beginning.nm_tap", "PLAGO_beginning", "1600bpi_ukn_6s",
             "LJS009_part1_39blks", "SRI_SDS_102715028_4secs", "tss_4secs"]
 
 
@@ -141,4 +141,27 @@ def test_fast_path_other_window_widths(bpi, pi, mode, fast_host, oracle_lib):
                 k = evlog._first_diff(a, b)
                 pytest.fail(f"bpi {bpi} width {w} parmset {pi} row0 {row0} skip {skip}: event #{k}: fast {a[k] if k < len(a) else None} "
                             f"oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)})")
+    tape.close()
+
+
+def test_zero_crossing_fast_path_all_gcr_parmsets(fast_host, oracle_lib):
+    """the 5 built-in GCR parameter sets (EWMA and moving-window clocks, resync) with -zeros on the GCR-density synthetic tile,
+    with and without skew: event-for-event against the oracle"""
+    rows = synth.gcr_like_tile(nblocks=2, bits_per_block=6000, gap_rows=9000)
+    hdr = synth.gcr_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    planes, stride = make_planes(rows, desc)
+    tape = oracle_lib.open(desc); tape.upload(rows)
+    for skew in (None, [0, 2, 1, 0, 11, 3, 0, 5, 1]):
+        for pi in range(5):
+            cfg = abi.make_cfg(tbin.MODE_GCR, parmsets.GCR[pi], hdr.bpi, hdr.ips, flags=abi.RT_F_FIND_ZEROS, skew=skew)
+            for row0 in (0, 32 * 100):
+                sc = tape.scan(cfg); sc.reset(abi.RT_RESET_FULL, row0)
+                want, _ = sc.run(rows.shape[0]); sc.end()
+                got = fast_scan(fast_host, planes, stride, rows.shape[0], desc, cfg, row0, rows.shape[0])
+                assert got is not None and len(got) > 10000
+                a, b = evlog.to_canon(got), evlog.to_canon(want)
+                if a.tobytes() != b.tobytes():
+                    k = evlog._first_diff(a, b)
+                    pytest.fail(f"skew {skew} parmset {pi} row0 {row0}: event #{k}: fast {a[k] if k < len(a) else None} oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)})")
     tape.close()

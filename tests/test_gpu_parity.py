@@ -148,7 +148,7 @@ def _all_units(bulk):
         out.append(ui); i += 1
 
 
-@pytest.mark.parametrize("name", ["Microdata_20blks.nm_tap", "PLAGO_beginning", "LJS009_part1_39blks", "1600bpi_ukn_6s", "tss_4secs"])
+@pytest.mark.parametrize("name", ["Microdata_20blks.nm_tap", "PLAGO_beginning", "LJS009_part1_39blks", "1600bpi_ukn_6s", "tss_4secs", "sf93_8blks", "1kblks_43blks"])
 def test_fast_kernel_equals_generic_kernel_on_every_unit(name, cuda_lib):
     """K3b (int16 fast path) against K3a (exact generic scan): same unit table, and for EVERY unit the same
     events (bit-exact) and the same unit-equivalence proof data, for every parameter set / skew the reference used."""
