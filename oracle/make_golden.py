@@ -14,7 +14,7 @@ Runs only in the build container (needs /root/reference and oracle/_ref built by
      (tests/golden/<name>.tap) -- these pin both the CPU oracle and the CUDA path,
   4. replays every segment through the CPU oracle and fails if any event differs.
 
-Usage: python oracle/make_golden.py [--skip-oracle-check]
+Usage: python oracle/make_golden.py [--skip-oracle-check] [--stage-only]
 """
 from __future__ import annotations
 
@@ -99,7 +99,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-oracle-check", action="store_true")
     ap.add_argument("--only", default=None)
+    ap.add_argument("--stage-only", action="store_true",
+                    help="only (re)create oracle/_ref/examples/ (what build() does in a fresh container)")
     args = ap.parse_args()
+    if args.stage_only:
+        for name, directory, _opts, rows in EXAMPLES:
+            dst = os.path.join(OUT, "examples", name + ".tbin")
+            if not os.path.exists(dst):
+                stage(name, directory, rows)
+        print("staged", len(EXAMPLES), "captures under", os.path.join(OUT, "examples"))
+        return
     os.makedirs(GOLD, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="rtgold_")
     ref_status = {}
