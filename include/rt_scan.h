@@ -227,9 +227,22 @@ typedef struct rt_bulk_stats {
    uint32_t launches;        /* kernels launched by the call                                 */
    uint32_t pad;             /* rt_bulk_scan_host: number of segments streamed, 0 = plain sequence    */
    uint64_t d2h_bytes;       /* bytes rt_bulk_fetch() copied to the host                     */
+   double   ms_masks;        /* device time: candidate-mask pass of the two-pass peak scan (a part of ms_scan; 0 if not used) */
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);
 void rt_bulk_free(rt_bulk *bulk);
+
+/* Diagnostics / tests: the two bit planes the two-pass peak scan derives from the samples (pure functions of the window of
+ * lookfor_peak, decoder.c:751-775, width = rt_pkww_width(cfg)):  bit (row % 32) of word (row / 32) of track k, for rows
+ * [0, rt_nrows), in cand[k * words_per_track ...] / acan[...]:
+ *    cand: max(window) - max(left edge, right edge) >= T0  or  min(left edge, right edge) - min(window) >= T0
+ *    acan: the sample that left the window at this row was >= max(window)      (the rescan condition of decoder.c:767)
+ * T0 = (int)(t0_frac * T), T = the integer bound of required_rise (decoder.c:785) with AGC gain 1 and average height 4 V;
+ * it is returned in *t0.  Rows whose window would reach before row 0 have both bits clear.  The oracle computes the
+ * definition; the product library runs its mask kernel.  RT_ERR_UNSUPPORTED if the configuration does not use the peak
+ * detector or T0 < 16. */
+int  rt_peak_masks(rt_tape *tape, const rt_scan_cfg *cfg, float t0_frac, uint32_t *cand, uint32_t *acan,
+                   uint64_t words_per_track, int32_t *t0);
 
 /* ---- helpers shared by both libraries ------------------------------------------------- */
 /* pkww_width exactly as readtape.c:1453-1457 computes it (float arithmetic, truncation). */

@@ -530,6 +530,38 @@ int rt_bulk_lookup(rt_bulk *b, uint32_t c, uint64_t r, const rt_event **e, uint6
    return set_err(RT_ERR_UNSUPPORTED, "the oracle only implements the exact scan"); }
 int rt_clear(rt_tape *t) { if (!t) return RT_ERR_ARG; t->nrows = 0; t->cap = 0; return RT_OK; }
 int rt_bulk_fetch(rt_bulk *b) { (void)b; return RT_ERR_UNSUPPORTED; }
+
+/* The two bit planes of the product's two-pass peak scan, by definition (include/rt_scan.h: rt_peak_masks).  The window of
+   lookfor_peak (decoder.c:751-775) at row p holds samples p-w+1 .. p of the track; int16 -> volts (readtape.c:1420) is strictly
+   monotone, so max / min / comparisons are taken on the raw samples. */
+int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, uint32_t *cand, uint32_t *acan, uint64_t wpt, int32_t *t0) {
+   if (!t || !cfg || !cand || !acan) return set_err(RT_ERR_ARG, "rt_peak_masks: null argument");
+   if ((cfg->flags & (RT_F_FIND_ZEROS | RT_F_DENSITY_DETECT | RT_F_INVERT | RT_F_DIFFERENTIATE)) || wpt * 32 < t->nrows)
+      return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: not the plain peak detector, or buffer too small");
+   const int w = rt_pkww_width(cfg, t->desc.tdelta_ns);
+   const float inv_lsb = 32767.0f / t->desc.maxvolts;
+   const float q = cfg->parms.pkww_rise * inv_lsb * 0.999f - 2.0f;
+   if (!(q > 0) || w < 3) return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: no usable threshold");
+   const int T = q > 70000.0f ? 70000 : (int)q;
+   int T0 = (int)((float)T * t0_frac);
+   if (T0 > 65535) T0 = 65535;
+   if (T0 < 16) return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: T0 < 16");
+   if (t0) *t0 = T0;
+   const uint32_t nh = t->desc.nheads;
+   for (uint32_t k = 0; k < t->desc.ntrks; ++k) {
+      memset(cand + (size_t)k * wpt, 0, (size_t)wpt * 4); memset(acan + (size_t)k * wpt, 0, (size_t)wpt * 4); }
+   for (uint32_t h = 0; h < nh; ++h) {
+      const int k = t->desc.head_to_trk[h];
+      if (k < 0 || k >= (int)t->desc.ntrks) continue;
+      uint32_t *c = cand + (size_t)k * wpt, *a = acan + (size_t)k * wpt;
+      for (uint64_t p = (uint64_t)w; p < t->nrows; ++p) {
+         int S = -32768, mn = 32767;
+         for (uint64_t r = p - w + 1; r <= p; ++r) { int v = t->rows[r * nh + h]; if (v > S) S = v; if (v < mn) mn = v; }
+         const int l = t->rows[(p - w + 1) * nh + h], r_ = t->rows[p * nh + h], lv = t->rows[(p - w) * nh + h];
+         const int mx = l > r_ ? l : r_, mi = l < r_ ? l : r_;
+         if (S - mx >= T0 || mi - mn >= T0) c[p >> 5] |= 1u << (p & 31);
+         if (lv >= S) a[p >> 5] |= 1u << (p & 31); } }
+   return RT_OK; }
 int rt_bulk_unit_info(const rt_bulk *b, uint32_t c, uint64_t r, rt_unit_info *o) { (void)b; (void)c; (void)r; (void)o; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_scan_host(rt_tape *t, const int16_t *r, uint64_t n, const rt_scan_cfg *c, rt_bulk **o) { (void)t; (void)r; (void)n; (void)c; (void)o; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_unit_at(const rt_bulk *b, uint32_t c, uint64_t r, rt_unit_info *o) { (void)b; (void)c; (void)r; (void)o; return RT_ERR_UNSUPPORTED; }

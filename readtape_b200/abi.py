@@ -49,7 +49,7 @@ class BulkStats(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("units", C.c_uint64), ("events", C.c_uint64),
                 ("rows_scanned", C.c_uint64), ("track_samples", C.c_uint64),
                 ("ms_preprocess", C.c_double), ("ms_units", C.c_double), ("ms_scan", C.c_double),
-                ("launches", C.c_uint32), ("pad", C.c_uint32), ("d2h_bytes", C.c_uint64)]
+                ("launches", C.c_uint32), ("pad", C.c_uint32), ("d2h_bytes", C.c_uint64), ("ms_masks", C.c_double)]
 
 
 class UnitInfo(C.Structure):
@@ -69,7 +69,7 @@ assert EVENT_DTYPE.itemsize == 32
 EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_attach_device", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
-           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_pkww_width",
+           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_peak_masks", "rt_pkww_width",
            "rt_row_time"]
 
 
@@ -118,11 +118,12 @@ class Lib:
         L.rt_bulk_unit_info.argtypes = [vp, u32, u64, P(UnitInfo)]
         L.rt_bulk_unit_at.argtypes = [vp, u32, u64, P(UnitInfo)]
         L.rt_bulk_free.argtypes = [vp]; L.rt_bulk_free.restype = None
+        L.rt_peak_masks.argtypes = [vp, P(ScanCfg), C.c_float, vp, vp, u64, P(C.c_int32)]
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
         L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
         for fn in ("rt_open", "rt_upload", "rt_attach_device", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
                    "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_lookup",
-                   "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_pkww_width"):
+                   "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_pkww_width", "rt_peak_masks"):
             getattr(L, fn).restype = i32
 
     @property
@@ -180,6 +181,16 @@ class Tape:
         h = C.c_void_p()
         self.lib.check(self.lib.L.rt_bulk_scan(self.h, arr, len(cfgs), C.byref(h)))
         return Bulk(self, h)
+
+    def peak_masks(self, cfg: ScanCfg, t0_frac: float = 0.25):
+        """(cand, acan, T0): the bit planes of the two-pass peak scan, uint32 [ntrks][ceil(nrows/32)] (rt_peak_masks)"""
+        import numpy as np
+        nt = self.desc.ntrks
+        wpt = (self.nrows + 31) // 32 + 1
+        cand = np.zeros((nt, wpt), dtype=np.uint32); acan = np.zeros((nt, wpt), dtype=np.uint32)
+        t0 = C.c_int32(0)
+        self.lib.check(self.lib.L.rt_peak_masks(self.h, C.byref(cfg), t0_frac, cand.ctypes.data, acan.ctypes.data, wpt, C.byref(t0)))
+        return cand, acan, int(t0.value)
 
     def bulk_scan_host(self, host_ptr: int, nrows: int, cfg: ScanCfg) -> "Bulk":
         """clear + upload + whole-tape scan + fetch, overlapped (rows at `host_ptr`, ideally pinned)"""

@@ -1,0 +1,130 @@
+/* readtape_b200/csrc/k_sparse.cu -- K3c: the speculative whole-tape scan of the moving-window peak detector in two passes.
+ *
+ *  k_peak_masks<W>   phase A (scan_masks.cuh): one thread per run of 64 rows of one track; int16x2 SIMD sliding max / min by
+ *                    doubling in registers; writes the `cand` and `acan` bit planes (2 bits per track-sample).  HBM-bound:
+ *                    2 B read + 0.25 B written per track-sample, no divergence, no shared memory.
+ *  k_units_sparse    phase B (scan_sparse.cuh): one lane per (unit, track) job, fetched dynamically; visits candidate rows only.
+ *                    Same outputs as k_units_fast / k_units_scan: events into the chunk pool, TrkMeta with the proof data.
+ */
+#include "scan_sparse.cuh"
+#include "kernels.h"
+#include "emit.cuh"
+
+#define MASK_THREADS   128
+#define SPARSE_THREADS 128
+
+using namespace rtsparse;
+
+/* grid: x = groups of MASK_THREADS runs, y = track.  Runs whose halo would reach in front of the plane use the scalar path. */
+template <int W>
+__global__ void __launch_bounds__(MASK_THREADS)
+k_peak_masks(const int16_t *planes, uint64_t plane_stride, uint64_t run_lo, uint64_t nruns, uint32_t T0,
+             uint32_t *cand, uint32_t *acan, uint64_t mask_stride) {
+   const uint64_t r = (uint64_t)blockIdx.x * MASK_THREADS + threadIdx.x;
+   if (r >= nruns) return;
+   const int trk = blockIdx.y;
+   const int16_t *plane = planes + (size_t)trk * plane_stride;
+   const int64_t p0 = (int64_t)(run_lo + r) * rtmask::MASK_RUN;
+   uint32_t cw[2], aw[2];
+   if (p0 >= rtmask::RunMasks<W>::HALO) rtmask::RunMasks<W>::run(plane, p0, T0, cw, aw);
+   else {
+      rtmask::word_masks_scalar(plane, p0 / 32, W, (int)T0, &cw[0], &aw[0]);
+      rtmask::word_masks_scalar(plane, p0 / 32 + 1, W, (int)T0, &cw[1], &aw[1]); }
+   const size_t wi = (size_t)trk * mask_stride + (size_t)(p0 / 32);
+   *reinterpret_cast<uint2 *>(cand + wi) = make_uint2(cw[0], cw[1]);
+   *reinterpret_cast<uint2 *>(acan + wi) = make_uint2(aw[0], aw[1]); }
+
+template <int W>
+static cudaError_t launch_masks_w(const DevCfg &c, uint64_t run_lo, uint64_t nruns, uint32_t *cand, uint32_t *acan, cudaStream_t s) {
+   dim3 grid((unsigned)((nruns + MASK_THREADS - 1) / MASK_THREADS), (unsigned)c.ntrks);
+   k_peak_masks<W><<<grid, MASK_THREADS, 0, s>>>(c.planes, c.plane_stride, run_lo, nruns, (uint32_t)c.T0, cand, acan, c.mask_stride);
+   return cudaGetLastError(); }
+
+/* phase A over plane rows [row_lo, row_hi) (rounded outwards to whole runs; row_hi <= plane_stride) */
+cudaError_t launch_peak_masks(const DevCfg &c, uint64_t row_lo, uint64_t row_hi, cudaStream_t s) {
+   if (row_hi <= row_lo) return cudaSuccess;
+   const uint64_t run_lo = row_lo / rtmask::MASK_RUN, run_hi = (row_hi + rtmask::MASK_RUN - 1) / rtmask::MASK_RUN;
+   const uint64_t nruns = run_hi - run_lo;
+   uint32_t *cand = const_cast<uint32_t *>(c.m_cand), *acan = const_cast<uint32_t *>(c.m_acan);
+   switch (c.width) {
+#define MW(W) case W: return launch_masks_w<W>(c, run_lo, nruns, cand, acan, s);
+      MW(3) MW(4) MW(5) MW(6) MW(7) MW(8) MW(9) MW(10) MW(11) MW(12) MW(13) MW(14) MW(15) MW(16) MW(17) MW(18) MW(19) MW(20)
+      MW(21) MW(22) MW(23) MW(24) MW(25) MW(26) MW(27) MW(28) MW(29) MW(30) MW(31) MW(32) MW(33) MW(34) MW(35) MW(36) MW(37) MW(38)
+      MW(39) MW(40) MW(41) MW(42) MW(43) MW(44) MW(45) MW(46) MW(47) MW(48) MW(49) MW(50)
+#undef MW
+      default: return cudaErrorInvalidValue; } }
+
+/* words per track of a mask plane for a plane of `plane_stride` rows (+ slack for unaligned 32-bit reads) */
+uint64_t peak_mask_stride(uint64_t plane_stride) { return (plane_stride + 31) / 32 + 4; }
+
+/* the integer threshold the masks are built for: a fraction of the default-state bound (AGC gain 1, average height 4 V).
+   0 = the two-pass scan is not worthwhile / not applicable for this configuration */
+int peak_mask_T0(const DevCfg &c, float frac) {
+   const float inv_lsb = 32767.0f / c.maxvolts;
+   const float q = c.p.pkww_rise * inv_lsb * 0.999f - 2.0f;
+   if (!(q > 0)) return 0;
+   const int T = q > 70000.0f ? 70000 : (int)q;
+   const int T0 = (int)((float)T * frac);
+   return T0 < 16 ? 0 : (T0 > 65535 ? 65535 : T0); }
+
+struct SparseJobs {
+   const DevCfg &c; const UnitDesc *units; TrkMeta *meta; rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
+   int quiet_thr_lsb; unsigned long long *counters /* [0] rows, [1] events, [2] next job */; uint64_t total; uint64_t cur;
+   template <class Scan>
+   __device__ bool next(Scan &us) {                           /* per lane: one (unit, track) job at a time */
+      for (;;) {
+         cur = atomicAdd(&counters[2], 1ull);
+         if (cur >= total) return false;
+         const uint32_t u = (uint32_t)(cur / c.ntrks); const int trk = (int)(cur % c.ntrks);
+         const UnitDesc ud = units[u];
+         if (ud.row_end - ud.row0 > (1ull << 30)) {            /* offsets are 32-bit: leave such a unit to the exact scan */
+            TrkMeta m;
+            m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
+            m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
+            meta[cur] = m;
+            continue; }
+         PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+         us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
+         return true; } }
+   template <class Scan>
+   __device__ void done(Scan &us) {
+      TrkMeta m; us.finish(m); meta[cur] = m;
+      atomicAdd(&counters[0], (unsigned long long)us.end);
+      if (us.em.n) atomicAdd(&counters[1], (unsigned long long)us.em.n); } };
+
+struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };
+
+__global__ void __launch_bounds__(SPARSE_THREADS)
+k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
+               rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
+               int quiet_thr_lsb, unsigned long long *counters) {
+   __shared__ uint32_t heights[RT_AGC_MAX_WINDOW * SPARSE_THREADS];      /* v_heights[] of every lane, [entry][thread] */
+   const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
+   SparseJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters, total, 0};
+   SparseScan<SPARSE_THREADS, PoolEmit> us(c, heights + threadIdx.x);
+   drive_sparse(us, jobs, WarpAny()); }
+
+bool sparse_scan_eligible(const DevCfg &c) {
+   return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
+          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.T0 > 0 && c.m_cand && c.m_acan; }
+
+/* phase B only: the masks of rows [0, max row_end) must have been built (launch_peak_masks) on the same stream */
+cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
+                                uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
+                                unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s) {
+   static int per_sm_cached = 0;
+   cudaError_t e;
+   if (!per_sm_cached) {
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse, SPARSE_THREADS, 0);
+      if (e != cudaSuccess) return e;
+      if (per_sm_cached < 1) per_sm_cached = 1; }
+   int per_sm = per_sm_cached;
+   if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
+   const uint64_t jobs = (uint64_t)nunits * (uint64_t)c.ntrks;
+   uint64_t grid = (jobs + SPARSE_THREADS - 1) / SPARSE_THREADS;
+   if (grid > (uint64_t)sms * (uint64_t)per_sm) grid = (uint64_t)sms * (uint64_t)per_sm;
+   if (grid < 1) grid = 1;
+   e = cudaMemsetAsync(counters + 2, 0, sizeof(unsigned long long), s);
+   if (e != cudaSuccess) return e;
+   k_units_sparse<<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   return cudaGetLastError(); }

@@ -38,4 +38,13 @@ bool fast_scan_eligible(const DevCfg &c);
 cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                               uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                               unsigned long long *rows_scanned, int sms, int max_ctas_per_sm, cudaStream_t s);
+/* k_sparse.cu: the two-pass scan of the moving-window peak detector (K3c): phase A writes the candidate / canonical bit planes
+   DevCfg::m_cand / m_acan for plane rows [row_lo, row_hi), phase B scans the units (same contract as launch_units_fast) */
+uint64_t peak_mask_stride(uint64_t plane_stride);
+int peak_mask_T0(const DevCfg &c, float frac);
+bool sparse_scan_eligible(const DevCfg &c);
+cudaError_t launch_peak_masks(const DevCfg &c, uint64_t row_lo, uint64_t row_hi, cudaStream_t s);
+cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
+                                uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
+                                unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s);
 #endif

@@ -437,7 +437,7 @@ static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
    return dc.det == RT_DET_PEAK ? lead + dc.width + 1 : lead + 2; }
 
 /* Everything derived from one configuration that the unit finder and the scan kernels need. */
-struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; };
+struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; bool use_sparse; };
 static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
    cfg_to_dev(t, cfg, &pl->dc);
    const DevCfg &dc = pl->dc;
@@ -451,6 +451,14 @@ static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
    /* K3b (int16 fast path) for the peak detector of NRZI / PE; RT_SCAN=generic forces the exact generic kernel (tests) */
    const char *force = getenv("RT_SCAN");
    pl->use_fast = fast_scan_eligible(dc) && !(force && strcmp(force, "generic") == 0);
+   /* K3c (two passes: candidate masks + sparse scan) where the peak-detector fast path applies; RT_SCAN=fast keeps the one-pass
+      kernel K3b (tests), RT_SPARSE_T0 = mask threshold as a fraction of the default-state bound (default 0.25) */
+   const char *t0env = getenv("RT_SPARSE_T0");
+   pl->dc.T0 = 0; pl->dc.m_cand = pl->dc.m_acan = nullptr; pl->dc.mask_stride = 0;
+   pl->use_sparse = false;
+   if (pl->use_fast && dc.det == RT_DET_PEAK && !(force && strcmp(force, "fast") == 0)) {
+      pl->dc.T0 = peak_mask_T0(dc, t0env ? (float)atof(t0env) : 0.25f);
+      pl->use_sparse = pl->dc.T0 > 0; }
    if (dc.det == RT_DET_PEAK) {
       pl->quiet_thr = dc.p.pkww_rise * 0.999f;
       if (dc.p.pkww_rise < 1e-3f) pl->quiet_thr = 0;                  /* nothing can be proven quiet: every lookup misses */
@@ -465,6 +473,8 @@ static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
 static cudaError_t launch_scan(const rt_tape *t, const ScanPlan &pl, const UnitDesc *d_units, uint32_t nunits, TrkMeta *d_meta, rt_event *d_pool,
                                uint32_t *d_chunk_next, unsigned int *d_cursor, uint32_t pool_chunks, unsigned long long *d_counters,
                                int max_ctas_per_sm, cudaStream_t st) {
+   if (pl.use_sparse) return launch_units_sparse(pl.dc, d_units, nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, pl.quiet_thr_lsb, d_counters,
+                                                 t->sms, max_ctas_per_sm, st);
    if (pl.use_fast) return launch_units_fast(pl.dc, d_units, nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, pl.quiet_thr_lsb, d_counters,
                                              t->sms, max_ctas_per_sm, st);
    const uint64_t threads = (uint64_t)nunits * t->desc.ntrks;
@@ -506,11 +516,16 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    const uint32_t units_cap = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
    uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr;
-   cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
+   cudaEvent_t ev[5]; for (auto &e : ev) cudaEventCreate(&e);
    std::vector<cudaEvent_t> done_ev(ncfgs, nullptr);
+   /* K3c: candidate / canonical bit planes, one set per distinct (window width, T0) -- parameter sets that only differ in
+      clock / AGC constants share them */
+   struct MaskSet { int width, T0; uint32_t *mc, *ma; uint32_t first_cfg; };
+   std::vector<MaskSet> msets;
    auto cleanup = [&]() {
       void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
+      for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream); }
       for (auto &e : ev) cudaEventDestroy(e);
       for (auto e : done_ev) if (e) cudaEventDestroy(e); };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); rt_bulk_free(b); \
@@ -546,6 +561,18 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          CUB(cudaMallocAsync(&bc.d_meta, (size_t)nunits * nt * sizeof(TrkMeta), t->stream)); } }
    b->stats.units = b->cfgs[ncfgs - 1].nunits;
    lap("unit finder + sync");
+   {  const uint64_t mstride = peak_mask_stride(t->plane_stride);
+      for (uint32_t ci = 0; ci < ncfgs; ++ci) {
+         ScanPlan &pl = plans[ci];
+         if (!pl.use_sparse || !b->cfgs[ci].nunits) continue;
+         size_t k = 0;
+         while (k < msets.size() && !(msets[k].width == pl.dc.width && msets[k].T0 == pl.dc.T0)) ++k;
+         if (k == msets.size()) {
+            MaskSet m{pl.dc.width, pl.dc.T0, nullptr, nullptr, ci};
+            msets.push_back(m);
+            CUB(cudaMallocAsync(&msets[k].mc, (size_t)mstride * nt * 4, t->stream));
+            CUB(cudaMallocAsync(&msets[k].ma, (size_t)mstride * nt * 4, t->stream)); }
+         pl.dc.m_cand = msets[k].mc; pl.dc.m_acan = msets[k].ma; pl.dc.mask_stride = mstride; } }
 
    /* 2. all scan kernels, concurrently, into one event pool: first guess one event per 16 track-samples, regrown on overflow */
    if (total_units) {
@@ -569,11 +596,14 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          CUB(cudaMemsetAsync(d_cursor, 0, 4, t->stream));
          CUB(cudaMemsetAsync(d_counters, 0, 32 * (size_t)ncfgs, t->stream));
          CUB(cudaEventRecord(ev[2], t->stream));
+         if (attempt == 0) {                                      /* phase A of the two-pass scan: once per mask set */
+            for (auto &m : msets) { CUB(launch_peak_masks(plans[m.first_cfg].dc, 0, nrows, t->stream)); ++t->launches; } }
+         CUB(cudaEventRecord(ev[4], t->stream));
          for (uint32_t ci = 0; ci < ncfgs; ++ci) {
             BulkCfg &bc = b->cfgs[ci];
             if (!bc.nunits) continue;
             cudaStream_t st = ncfgs > 1 ? t->s_par[ci % t->s_par.size()] : t->stream;
-            if (st != t->stream) CUB(cudaStreamWaitEvent(st, ev[2], 0));
+            if (st != t->stream) CUB(cudaStreamWaitEvent(st, ev[4], 0));
             CUB(launch_scan(t, plans[ci], bc.d_units, bc.nunits, bc.d_meta, b->d_pool, b->d_chunk_next, d_cursor, b->pool_chunks, d_counters + 4 * ci, 0, st));
             ++t->launches;
             if (st != t->stream) {
@@ -583,7 +613,8 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          unsigned int used = 0;
          CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
          CUB(cudaStreamSynchronize(t->stream));
-         float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); b->stats.ms_scan = ms;
+         float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); b->stats.ms_scan = attempt == 0 ? ms : b->stats.ms_scan + ms;
+         if (attempt == 0 && !msets.empty()) { cudaEventElapsedTime(&ms, ev[2], ev[4]); b->stats.ms_masks = ms; }
          lap("scan kernel(s) + sync");
          if (used <= b->pool_chunks) { b->chunks_used = used; break; }
          want_chunks = (uint64_t)used + used / 8 + 1024;
@@ -672,6 +703,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    const uint32_t units_cap_tmp = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
    uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr; TrkMeta *d_meta = nullptr;
+   uint32_t *d_mc = nullptr, *d_ma = nullptr; uint64_t masks_done = 0; double ms_masks = 0;   /* K3c bit planes, built segment by segment */
    std::vector<cudaEvent_t> seg_ev; std::vector<uint64_t> seg_rows_done;
    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
    rt_bulk *b = new (std::nothrow) rt_bulk();
@@ -681,16 +713,22 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    bc.cfg = *cfg; bc.dc = pl.dc; bc.fast = pl.use_fast;
    bool failed = false; const char *why = "";
    auto release = [&]() {
-      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta};
+      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta, d_mc, d_ma};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->s_scan);
       for (auto e : seg_ev) cudaEventDestroy(e);
       if (ev_a) cudaEventDestroy(ev_a); if (ev_b) cudaEventDestroy(ev_b); };
+   struct EvGuard { cudaEvent_t *e; ~EvGuard() { if (*e) cudaEventDestroy(*e); } };
 #define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); release(); t->pool_cache_busy = t->pin_cache_busy = false; delete b; \
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
    CUS(cudaMallocAsync(&d_bitmap, words * 4, t->s_scan)); CUS(cudaMallocAsync(&d_flags, words * 4, t->s_scan)); CUS(cudaMallocAsync(&d_blockcount, nblocks * 4, t->s_scan));
    CUS(cudaMallocAsync(&d_nunits, 4, t->s_scan)); CUS(cudaMallocAsync(&d_units_tmp, (size_t)units_cap_tmp * sizeof(UnitDesc), t->s_scan));
    CUS(cudaMallocAsync(&d_counters, 32, t->s_scan)); CUS(cudaMallocAsync(&d_cursor, 4, t->s_scan));
    CUS(cudaMallocAsync(&d_meta, (size_t)cap_units * nt * sizeof(TrkMeta), t->s_scan));
+   if (pl.use_sparse) {
+      const uint64_t mstride = peak_mask_stride(t->plane_stride);
+      CUS(cudaMallocAsync(&d_mc, (size_t)mstride * nt * 4, t->s_scan)); CUS(cudaMallocAsync(&d_ma, (size_t)mstride * nt * 4, t->s_scan));
+      pl.dc.m_cand = d_mc; pl.dc.m_acan = d_ma; pl.dc.mask_stride = mstride; }
+   cudaEvent_t ev_m = nullptr; EvGuard ev_m_guard{&ev_m};
    CUS(cudaMemsetAsync(d_cursor, 0, 4, t->s_scan)); CUS(cudaMemsetAsync(d_counters, 0, 32, t->s_scan));
    CUS(cudaEventCreate(&ev_a)); CUS(cudaEventCreate(&ev_b));
    t->pool_cache_busy = t->pin_cache_busy = true;
@@ -735,6 +773,11 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
       else while (u_final + 1 < nun && bc.units[u_final + 1].row0 + pl.up.tail_rows + 4096 <= R) ++u_final;    /* row_end can no longer change */
       if (u_final == u_done) continue;
       CUS(cudaEventRecord(ev_a, t->s_scan));
+      if (pl.use_sparse) {                                       /* phase A for the rows that arrived since the last segment */
+         if (!ev_m) CUS(cudaEventCreate(&ev_m));
+         CUS(launch_peak_masks(pl.dc, masks_done, R, t->s_scan)); ++t->launches;
+         masks_done = R / 64 * 64;                               /* the run that holds row R is redone when it is complete */
+         CUS(cudaEventRecord(ev_m, t->s_scan)); }
       CUS(launch_scan(t, pl, d_units_tmp + u_done, u_final - u_done, d_meta + (size_t)u_done * nt, d_pool, d_chunk_next, d_cursor, cap_chunks, d_counters,
                       last ? 0 : 2, t->s_scan));
       ++t->launches;
@@ -742,7 +785,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
       unsigned int used = 0;
       CUS(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->s_scan));
       CUS(cudaStreamSynchronize(t->s_scan));
-      { float ms = 0; cudaEventElapsedTime(&ms, ev_a, ev_b); ms_scan += ms; }
+      { float ms = 0; cudaEventElapsedTime(&ms, ev_a, ev_b); ms_scan += ms; if (ev_m) { cudaEventElapsedTime(&ms, ev_a, ev_m); ms_masks += ms; } }
       if (trace) fprintf(stderr, "[rt_bulk_scan_host] segment %zu: rows %llu, units %u..%u, chunks %u..%u\n", k, (unsigned long long)R, u_done, u_final, c_done, used);
       if (used > cap_chunks) { failed = true; why = "more events than the previous scan"; break; }
       bc.meta.resize((size_t)u_final * nt); b->chunk_next.resize(used);
@@ -769,13 +812,46 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    t->pool_cache_busy = false;                                    /* the device pool is free again; the pinned copy belongs to the bulk */
    b->fetched = true;
    b->stats.rows = nrows; b->stats.units = nun; b->stats.events = counters[1]; b->stats.rows_scanned = counters[0];
-   b->stats.track_samples = nrows * nt; b->stats.ms_preprocess = t->ms_ingest; b->stats.ms_units = ms_units; b->stats.ms_scan = ms_scan;
+   b->stats.track_samples = nrows * nt; b->stats.ms_preprocess = t->ms_ingest; b->stats.ms_units = ms_units; b->stats.ms_scan = ms_scan; b->stats.ms_masks = ms_masks;
    b->stats.launches = (uint32_t)(t->launches - launches0);
    b->stats.pad = (uint32_t)seg_ev.size();                        /* segments streamed (0: the plain sequence was used) */
    t->hist_rows = nrows; t->hist_units = nun; t->hist_chunks = c_done;
    release();
 #undef CUS
    *out = b; return RT_OK; }
+
+/* diagnostics / tests: run phase A of the two-pass peak scan and hand the bit planes to the host */
+extern "C" int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, uint32_t *cand, uint32_t *acan, uint64_t wpt, int32_t *t0) {
+   if (!t || !cfg || !cand || !acan) return set_err(RT_ERR_ARG, "rt_peak_masks: null argument");
+   int rc = tape_sync_valid(t); if (rc) return rc;
+   rc = cfg_check(t, cfg); if (rc) return rc;
+   CU(cudaSetDevice(t->device));
+   DevCfg dc; cfg_to_dev(t, cfg, &dc);
+   const uint64_t nrows = t->nrows_valid;
+   if (dc.det != RT_DET_PEAK || dc.invert || dc.differentiate || dc.density || wpt * 32 < nrows)
+      return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: not the plain peak detector, or buffer too small");
+   dc.T0 = peak_mask_T0(dc, t0_frac);
+   if (dc.T0 <= 0) return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: T0 < 16");
+   if (t0) *t0 = dc.T0;
+   const uint64_t ms = peak_mask_stride(t->plane_stride); const uint32_t nt = t->desc.ntrks;
+   uint32_t *d_mc = nullptr, *d_ma = nullptr;
+   CU(cudaMalloc(&d_mc, (size_t)ms * nt * 4));
+   cudaError_t e = cudaMalloc(&d_ma, (size_t)ms * nt * 4);
+   if (e == cudaSuccess) {
+      dc.m_cand = d_mc; dc.m_acan = d_ma; dc.mask_stride = ms;
+      e = launch_peak_masks(dc, 0, nrows, t->stream); ++t->launches;
+      const uint64_t nw = (nrows + 31) / 32;
+      for (uint32_t k = 0; k < nt && e == cudaSuccess; ++k) {
+         memset(cand + (size_t)k * wpt, 0, (size_t)wpt * 4); memset(acan + (size_t)k * wpt, 0, (size_t)wpt * 4);
+         e = cudaMemcpyAsync(cand + (size_t)k * wpt, d_mc + (size_t)k * ms, (size_t)nw * 4, cudaMemcpyDeviceToHost, t->stream);
+         if (e == cudaSuccess) e = cudaMemcpyAsync(acan + (size_t)k * wpt, d_ma + (size_t)k * ms, (size_t)nw * 4, cudaMemcpyDeviceToHost, t->stream); }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+      if (e == cudaSuccess && (nrows & 31)) {                    /* rows past the end of the data: not defined, cleared */
+         const uint32_t keep = (1u << (nrows & 31)) - 1u;
+         for (uint32_t k = 0; k < nt; ++k) { cand[(size_t)k * wpt + nw - 1] &= keep; acan[(size_t)k * wpt + nw - 1] &= keep; } } }
+   cudaFree(d_mc); cudaFree(d_ma);
+   if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "rt_peak_masks: %s", cudaGetErrorString(e));
+   return RT_OK; }
 
 extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
    if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");

@@ -1,0 +1,319 @@
+/* readtape_b200/csrc/scan_sparse.cuh -- K3c phase B: the sequential part of the moving-window peak detector,
+ * visiting candidate rows only.
+ *
+ * Same contract as UnitScan (scan_fast.cuh) and the (unit, track) scan of k_units_scan (k_scan.cu): one lane scans
+ * one track of one unit from a fresh RT_RESET_FULL and produces the identical events and proof data.  Phase A
+ * (scan_masks.cuh) has already evaluated the pure, row-parallel part of lookfor_peak (decoder.c:751-810) for every
+ * row of the plane and left two bit planes: `cand` (rows that can pass the shape tests for any threshold >= T0) and
+ * `acan` (rows where the window maximum left the window, i.e. where the reference rescans: decoder.c:767).  What is
+ * left is sequential but sparse -- the AGC-dependent threshold (decoder.c:785), the blind countdown (:778), the lazily
+ * refreshed minimum (:765) -- and is only needed AT candidate rows:
+ *
+ *   sparse mode   next set bit of `cand` at or after the end of the blind stretch -> window maximum, edges and the
+ *                 position of the peak straight from the plane (w samples) -> exact float tests of decoder.c:790-803.
+ *                 Only if the top test fails is the lazy minimum needed: m(p) = Wmin(a) at the last `acan` row a <= p,
+ *                 then the recurrence  m <- Wmin(q) iff raw[q-w] == m  over (a, p]  (scan_fast.cuh, note 3).
+ *   dense mode    a plain row-by-row restatement (window rescanned on every row).  Used for the first rows of a unit
+ *                 -- while the window fills, while the deskew FIFO fills, and until the first `acan` row makes the
+ *                 lazy minimum a pure function of the samples -- and whenever the current threshold bound T drops
+ *                 below T0 (AGC gain high / low average height), until it is back.  Correctness therefore never
+ *                 depends on T0; only speed does.
+ *
+ * The proof data of the unit-equivalence test concerns the rows before the first event: loud rows and
+ * canonical (= acan) non-loud rows.  In sparse mode they are derived granule-wise when the first event is found
+ * (advance_pre): 32 rows whose granule min/max keep the running span below the threshold cannot contain a loud row,
+ * and their canonical rows are the bits of `acan`.
+ *
+ * Reference semantics (file:line in /root/reference/src): lookfor_peak decoder.c:751-810, refine_peak :700-749,
+ * first-sample init :855-861, deskew FIFO :819-831, process_*_transition :560-609; feedback: feedback.cuh.
+ * Host + device code: tests/host_fast runs the same functions on the CPU against the oracle.
+ */
+#pragma once
+#include "scan_fast.cuh"
+#include "scan_masks.cuh"
+
+namespace rtsparse {
+
+using rtfast::FastState; using rtfast::OFF_NONE; using rtfast::minmax; using rtfast::span_minmax;
+using rtfast::row_time; using rtfast::volts;
+
+enum { SP_DENSE = 0, SP_SPARSE = 1, SP_DONE = 2 };
+constexpr uint32_t NO_ROW32 = 0xffffffffu;
+#define SPARSE_SEARCH_WORDS 4          /* mask words examined per step while looking for the next candidate */
+
+/* 32 mask bits starting at bit position p (any alignment); the arrays have slack words behind the last row */
+RT_FHD uint32_t bits_at(const uint32_t *mk, uint64_t p) {
+   const uint64_t wi = p >> 5; const int sh = (int)(p & 31);
+   const uint32_t lo = mk[wi];
+   if (sh == 0) return lo;
+   return (lo >> sh) | (mk[wi + 1] << (32 - sh)); }
+RT_FHD int ctz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+   return __ffs((int)v) - 1;
+#else
+   return __builtin_ctz(v);
+#endif
+}
+RT_FHD int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+   return __clz((int)v);
+#else
+   return __builtin_clz(v);
+#endif
+}
+
+template <int STRIDE, class Emit>
+struct SparseScan {
+   const DevCfg &c; const int16_t *plane; const uint32_t *mc, *ma; const uint32_t *gm;
+   uint64_t row0; uint32_t end; int trk, w, delay; uint32_t io, o_pure;
+   Emit em; FastState<STRIDE> t; uint32_t *ht;
+   /* detector state: o = next row; tests are off for rows < resume (blind countdown, decoder.c:778); m = the lazy minimum,
+      exact for row mq (dense mode: for row o - 1) */
+   uint32_t o, resume, mq; int m, T, st; float inv_lsb, rise, reqmin;
+   uint32_t ndense;                                             /* rows walked in dense mode (diagnostics) */
+   /* proof data (offsets relative to row0; OFF_NONE = none), as in UnitScan */
+   bool pre; uint32_t pre_pos;
+   int qmin, qmax, qthr, qL; int32_t ll, last_canon;
+   int32_t sync_row, loud_at_sync, sync_first, sync_early, loud_early; bool early_frozen; uint32_t sf_from; uint64_t quiet_from;
+
+   RT_FHD SparseScan(const DevCfg &c_, uint32_t *heights) : c(c_), w(c_.width), ht(heights) { st = SP_DONE; o = end = 0; }
+
+   /* the sample the detector sees at stream offset o (deskew FIFO, decoder.c:819-831) */
+   RT_FHD int sample(uint32_t oo) const { return (int)plane[row0 + (oo >= (uint32_t)delay ? oo - (uint32_t)delay : oo)]; }
+   /* plane row of stream offset o, for o >= delay */
+   RT_FHD uint64_t prow(uint32_t oo) const { return row0 + oo - (uint32_t)delay; }
+
+   RT_FHD void thresholds() {                                   /* decoder.c:785-786; T: see UnitScan::thresholds */
+      rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+      reqmin = c.p.min_peak * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+      float q = rise * inv_lsb * 0.999f - 2.0f;
+      T = !(q > 0) ? 0 : (q > 70000.0f ? 70000 : (int)q); }
+
+   /* ---- proof data: identical bookkeeping to UnitScan (scan_fast.cuh) ---- */
+   RT_FHD void commit() {
+      if (last_canon != OFF_NONE && last_canon != sync_row) {
+         sync_row = last_canon; loud_at_sync = ll;
+         if (!early_frozen) { sync_early = last_canon; loud_early = ll; } } }
+   RT_FHD void loud_row(int32_t oo) {
+      commit();
+      if (sync_early != OFF_NONE) early_frozen = true;
+      ll = oo;
+      if (oo >= 0) sf_from = NO_ROW32; }
+   RT_FHD void feed(int32_t oo, int raw) {
+      if (raw < qmin) qmin = raw;
+      if (raw > qmax) qmax = raw;
+      if (qmax - qmin >= qthr) {
+         const int64_t to = (int64_t)row0 + oo, from = to - qL + 1;
+         const minmax r = span_minmax(plane, from < 0 ? 0 : from, to, raw);
+         qmin = r.mn; qmax = r.mx;
+         if (r.mx - r.mn >= qthr) loud_row(oo); } }
+   RT_FHD void track(uint32_t oo, bool canonical) {
+      feed((int32_t)oo, (int)plane[row0 + oo]);
+      if (canonical && ll != (int32_t)oo) {
+         last_canon = (int32_t)oo;
+         if (oo >= sf_from) { sync_first = (int32_t)oo; sf_from = NO_ROW32; } } }
+   /* rows [pre_pos, upto) of the sparse stretch: none of them had an event; canonical rows are the acan bits */
+   RT_FHD void advance_pre(uint32_t upto) {
+      while (pre_pos < upto) {
+         if (gm && ((row0 + pre_pos) & (RT_GRAN - 1)) == 0 && pre_pos + RT_GRAN <= upto) {
+            const uint32_t g = gm[(row0 + pre_pos) / RT_GRAN];
+            const int gmn = (int)(int16_t)(uint16_t)(g & 0xffffu), gmx = (int)(int16_t)(uint16_t)(g >> 16);
+            const int nmn = gmn < qmin ? gmn : qmin, nmx = gmx > qmax ? gmx : qmax;
+            if (nmx - nmn < qthr) {                              /* no row of this granule can be loud */
+               qmin = nmn; qmax = nmx;
+               const uint32_t bits = bits_at(ma, prow(pre_pos));
+               if (bits) {
+                  if (sf_from != NO_ROW32) {
+                     const uint32_t b2 = sf_from <= pre_pos ? bits : (sf_from - pre_pos < 32 ? bits >> (sf_from - pre_pos) << (sf_from - pre_pos) : 0u);
+                     if (b2) { sync_first = (int32_t)(pre_pos + (uint32_t)ctz32(b2)); sf_from = NO_ROW32; } }
+                  last_canon = (int32_t)(pre_pos + 31u - (uint32_t)clz32(bits)); }
+               pre_pos += RT_GRAN; continue; } }
+         const uint64_t p = prow(pre_pos);
+         track(pre_pos, (ma[p >> 5] >> (p & 31)) & 1u);
+         ++pre_pos; } }
+
+   /* process_*_transition, decoder.c:560-609 */
+   RT_FHD void transition(bool top, uint32_t oo) {
+      const double t_ev = top ? t.t_top : t.t_bot;
+      const float v_top_seen = t.v_top, v_bot_seen = t.v_bot;
+      ++t.peakcount;
+      if (c.mode == RT_MODE_NRZI) rtfb::nrzi_feedback(c, t, top);
+      else if (c.mode == RT_MODE_PE) rtfb::pe_feedback(c, t, top, t_ev);
+      else rtfb::agc_adjust(c, t);
+      if (top) t.v_lasttop = t.v_top; else t.v_lastbot = t.v_bot;
+      t.t_lastpeak = t_ev;
+      em.emit(row0 + oo, t_ev, v_top_seen, v_bot_seen, t.agc_gain, top);
+      thresholds(); }
+
+   /* the event at row oo: peak value `val` (int16 domain), float value v; the peak is the sample at window position
+      `pos` (stream offset / plane row arithmetic is the caller's), ld = its 1-based distance from the left edge, prev / next
+      its neighbours.  refine_peak, decoder.c:700-749, one code path for both polarities (see UnitScan::refine). */
+   RT_FHD void fire(bool top, float v, int ld, bool found, int xprev, int xnext, uint32_t oo) {
+      if (pre) { commit(); pre = false; }
+      if (!found || ld >= w || ld <= 1) { t.failed = 2; resume = oo + 1; return; }        /* the reference would fatal() */
+      const float sg = top ? 1.0f : -1.0f;
+      const float vprev = sg * volts(c, xprev), vnext = sg * volts(c, xnext);
+      const float edge = sg * v - RT_PEAK_THRESHOLD / t.agc_gain;
+      float adj = 0;
+      if (vprev > edge && vnext < edge) adj = -0.5f;
+      else if (vnext > edge && vprev < edge) adj = +0.5f;
+      const double timenow = row_time(c, row0 + oo);
+      const double tp = timenow - (double)(((float)(w - ld) - adj) * c.sample_deltat);
+      resume = oo + (uint32_t)ld + 1u;                           /* pkww_countdown = left_distance */
+      if (top) { t.v_top = v; t.t_top = tp; } else { t.v_bot = v; t.t_bot = tp; }
+      transition(top, oo); }
+
+   /* start the scan of unit rows [row0_, row_end) of track trk_ from a fresh RT_RESET_FULL */
+   RT_FHD void begin(const int16_t *plane_, uint64_t row0_, uint64_t row_end, int trk_, Emit em_, int quiet_thr_lsb) {
+      plane = plane_; row0 = row0_; end = (uint32_t)(row_end - row0_); trk = trk_; delay = c.skew[trk_]; em = em_;
+      mc = c.m_cand + (size_t)trk_ * c.mask_stride; ma = c.m_acan + (size_t)trk_ * c.mask_stride;
+      gm = c.gmm ? c.gmm + (size_t)trk_ * c.ngran_cap : nullptr;
+      const bool tz = row_time(c, row0) == 0.0;
+      io = (uint32_t)trk + (tz ? 1u : 0u);
+      o_pure = ((uint32_t)delay > io ? (uint32_t)delay : io) + (uint32_t)w;
+      t.t_top = t.t_bot = t.t_lastpeak = 0; t.v_top = t.v_bot = t.v_lasttop = t.v_lastbot = 0; t.avg_height_sum = 0;
+      t.avg_height_count = t.heightndx = t.peakcount = 0; t.datablock = t.bit1_up = t.failed = 0;
+      t.heights.p = ht;
+      for (int i = 0; i < RT_AGC_MAX_WINDOW; ++i) t.heights[i] = 0.0f;
+      t.agc_gain = 1.0f; t.avg_height = RT_PKWW_PEAKHEIGHT;
+      t.t_clkwindow = c.clk_init / 2 * c.p.clk_factor;
+      inv_lsb = 32767.0f / c.maxvolts;
+      thresholds(); resume = 0; m = 0; mq = 0; ndense = 0;
+      qthr = quiet_thr_lsb; qL = w + delay; qmin = 32767; qmax = -32768; ll = last_canon = OFF_NONE;
+      sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false; pre = true;
+      const int lead = (int)io > delay ? (int)io : delay;
+      sf_from = (uint32_t)(lead + w + 1);
+      const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
+      for (int32_t oo = -npre; oo < 0; ++oo) feed(oo, (int)plane[(int64_t)row0 + oo]);
+      quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
+      for (uint32_t oo = 0; oo <= io && oo < end; ++oo) track(oo, false);              /* decoder.c:855-861: not looked at yet */
+      o = io + 1; pre_pos = o;
+      st = o >= end ? SP_DONE : SP_DENSE;
+      if (st == SP_DENSE) { m = sample(io); t.t_lastpeak = row_time(c, row0 + io); } }
+
+   /* ---- dense mode: one row, by definition ---- */
+   RT_FHD void dense_step() {
+      const bool had_w = o >= io + (uint32_t)w;                 /* the window was full: its oldest sample leaves (decoder.c:755) */
+      const uint32_t ws = had_w ? o - (uint32_t)w + 1u : io;
+      int S = -32768, mn = 32767;
+      for (uint32_t i = ws; i <= o; ++i) { const int v = sample(i); if (v > S) S = v; if (v < mn) mn = v; }
+      const int lv = had_w ? sample(o - (uint32_t)w) : 0;        /* decoder.c:754: old_left stays 0 until the window is full */
+      const bool A = had_w ? lv >= S : S == 0;
+      if (A || lv == m) m = mn;                                  /* the rescan of decoder.c:767-775 */
+      const bool canonical = had_w && A;
+      ++ndense;
+      bool fired = false;
+      if (o >= resume) {
+         const int xl = sample(ws), xr = sample(o);
+         const float vl = volts(c, xl), vr = volts(c, xr), maxv = volts(c, S), minv = volts(c, m);
+         const bool top = maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
+         const bool bot = !top && minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
+         if (top || bot) {
+            const int val = top ? S : m;
+            uint32_t pos = NO_ROW32;
+            for (uint32_t i = o + 1; i-- > ws;) if (sample(i) == val) pos = i;         /* leftmost match */
+            const bool found = pos != NO_ROW32;
+            const int ld = found ? (int)(pos - ws) + 1 : 0;
+            const int xprev = found && pos > ws ? sample(pos - 1) : 0, xnext = found && pos < o ? sample(pos + 1) : 0;
+            fire(top, top ? maxv : minv, ld, found, xprev, xnext, o);
+            fired = true; } }
+      if (pre && !fired) track(o, canonical);
+      const uint32_t cur = o;
+      ++o; pre_pos = o;
+      if (o >= end) { st = SP_DONE; return; }
+      /* from a canonical row of the pure regime on, the state is what the masks describe */
+      if (canonical && cur >= o_pure && T >= c.T0 && c.T0 > 0) { st = SP_SPARSE; mq = cur; } }
+
+   /* ---- sparse mode ---- */
+   RT_FHD int window_min(uint64_t p) const {
+      int mn = 32767;
+      const int16_t *q = plane + (p - (uint32_t)w + 1u);
+      for (int i = 0; i < w; ++i) { const int v = q[i]; if (v < mn) mn = v; }
+      return mn; }
+   /* the lazy minimum at stream offset oo (plane row p), from its last exactly known value (row mq) */
+   RT_FHD void lazy_min(uint32_t oo) {
+      if (mq == oo) return;
+      const uint64_t p = prow(oo), pm = prow(mq);
+      /* last acan row in (pm, p] */
+      uint64_t a = pm; bool have = false;
+      {
+         uint64_t wi = p >> 5;
+         uint32_t bits = ma[wi] & (0xffffffffu >> (31 - (int)(p & 31)));
+         for (;;) {
+            const uint64_t base = wi << 5;
+            if (base + 31 <= pm) break;                                                   /* the whole word is at or before pm */
+            if (base <= pm) bits &= (pm - base) >= 31 ? 0u : (0xffffffffu << ((int)(pm - base) + 1));
+            if (bits) { a = base + 31u - (uint32_t)clz32(bits); have = true; break; }
+            if (base <= pm || wi == 0) break;
+            --wi; bits = ma[wi]; } }
+      uint64_t q = pm;
+      if (have) { m = window_min(a); q = a; }
+      for (++q; q <= p; ++q) if ((int)plane[q - (uint32_t)w] == m) m = window_min(q);
+      mq = oo; }
+
+   RT_FHD void sparse_step() {
+      /* next candidate row at or after the end of the blind stretch */
+      uint32_t from = o > resume ? o : resume;
+      if (from >= end) { o = end; st = SP_DONE; return; }
+      uint64_t p = prow(from);
+      const uint64_t pend = prow(end);
+      uint32_t bits = bits_at(mc, p);
+      int nw = 1;
+      while (!bits && nw < SPARSE_SEARCH_WORDS && p + 32 < pend) { p += 32; bits = bits_at(mc, p); ++nw; }
+      if (!bits) { p += 32; o = p >= pend ? end : (uint32_t)(p - row0) + (uint32_t)delay; if (o >= end) st = SP_DONE; return; }
+      p += (uint32_t)ctz32(bits);
+      if (p >= pend) { o = end; st = SP_DONE; return; }
+      const uint32_t oc = (uint32_t)(p - row0) + (uint32_t)delay;
+      /* window maximum, its leftmost position, the edges */
+      const int16_t *win = plane + (p - (uint32_t)w + 1u);
+      int S = -32768, pos = 0;
+      for (int i = 0; i < w; ++i) { const int v = win[i]; if (v > S) { S = v; pos = i; } }
+      const int xl = win[0], xr = win[w - 1];
+      const float vl = volts(c, xl), vr = volts(c, xr), maxv = volts(c, S);
+      const bool top = maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
+      bool bot = false; float minv = 0;
+      if (!top) {
+         lazy_min(oc);
+         minv = volts(c, m);
+         bot = minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
+         if (bot) { pos = -1; for (int i = w; i-- > 0;) if ((int)win[i] == m) pos = i; } }
+      o = oc + 1;
+      if (top || bot) {
+         if (pre) advance_pre(oc);
+         const bool found = pos >= 0;
+         const int xprev = found && pos > 0 ? win[pos - 1] : 0, xnext = found && pos < w - 1 ? win[pos + 1] : 0;
+         fire(top, top ? maxv : minv, pos + 1, found, xprev, xnext, oc);
+         if (T < c.T0) { lazy_min(oc); st = SP_DENSE; } }           /* the masks no longer cover the threshold: walk rows */
+      if (o >= end) st = SP_DONE; }
+
+   RT_FHD void step() { if (st == SP_DENSE) dense_step(); else if (st == SP_SPARSE) sparse_step(); }
+
+   RT_FHD void finish(TrkMeta &meta) {
+      if (pre) { advance_pre(end); commit(); }        /* dense mode keeps pre_pos == o: nothing left then */
+      meta.first_event_row = em.first_row;
+      meta.sync_row = sync_row == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_row;
+      meta.last_loud_row = loud_at_sync == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_at_sync);
+      meta.sync_first = sync_first == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_first;
+      meta.quiet_from = quiet_from;
+      meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
+      meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
+      meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = end > ndense ? end - ndense : 0; } };   /* pad: rows not walked (diagnostics) */
+
+/* Drive one lane (host) or the 32 lanes of a warp (device) through (unit, track) jobs.  `Jobs` provides
+ *   bool next(Scan&)   start the lane's next job, false if there is none
+ *   void done(Scan&)   the lane's job is finished (store its TrkMeta)
+ * `any(pred)` is the warp vote (identity on the host).  Lanes fetch jobs independently: a lane in a gap costs a few
+ * mask words per step, so there is nothing to gain from keeping the lanes of a warp on neighbouring rows. */
+template <class Scan, class Jobs, class Vote>
+RT_FHD void drive_sparse(Scan &us, Jobs &jobs, Vote any) {
+   bool have = false;
+   for (;;) {
+      if (!have || us.st == SP_DONE) {
+         if (have) jobs.done(us);
+         have = jobs.next(us); }
+      if (!any(have)) return;
+      if (have) {
+#pragma unroll 1
+         for (int k = 0; k < 4 && us.st != SP_DONE; ++k) us.step(); } } }
+
+}  // namespace rtsparse

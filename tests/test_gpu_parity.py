@@ -4,6 +4,7 @@ Bit-exact: rows, polarity, event times (f64), voltages (f32) and AGC gains (f32)
 bytes (SHA-256 of the canonical records) -- integer/byte work allows no tolerance, and the float
 results are required to be identical too because .tap parity depends on them.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -149,24 +150,28 @@ def _all_units(bulk):
 
 
 @pytest.mark.parametrize("name", ["Microdata_20blks.nm_tap", "PLAGO_beginning", "LJS009_part1_39blks", "1600bpi_ukn_6s", "tss_4secs", "sf93_8blks", "1kblks_43blks"])
-def test_fast_kernel_equals_generic_kernel_on_every_unit(name, cuda_lib):
-    """K3b (int16 fast path) against K3a (exact generic scan): same unit table, and for EVERY unit the same
-    events (bit-exact) and the same unit-equivalence proof data, for every parameter set / skew the reference used."""
+def test_fast_kernels_equal_generic_kernel_on_every_unit(name, cuda_lib):
+    """K3c (two passes: candidate masks + sparse scan, the default) and K3b (one-pass int16 fast path, RT_SCAN=fast) against
+    K3a (exact generic scan, RT_SCAN=generic): same unit table, and for EVERY unit the same events (bit-exact) and the same
+    unit-equivalence proof data, for every parameter set / skew the reference used.  K3c also with a mask threshold so high
+    that it keeps falling back to its row-by-row mode (RT_SPARSE_T0=1.0) and without the granule map (RT_FAST_SKIP=0)."""
     doc, segs, heads, rows = load_capture(name)
     tape = cuda_lib.open(evlog.desc_from_heads(heads))
     tape.upload(rows)
     full = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT)]
     keys = sorted({(s.parmset, tuple(s.skew)) for s in full})
     nunits = 0
+    variants = (("generic", "1", None), ("fast", "0", None), ("fast", "1", None), (None, "1", None), (None, "0", None), (None, "1", "1.0"))
     for key in keys:
         cfg = evlog.cfg_for([s for s in full if (s.parmset, tuple(s.skew)) == key][0])
         res = []
-        for force, skip in (("generic", "1"), (None, "0"), (None, "1")):
+        for force, skip, t0 in variants:
             os.environ["RT_FAST_SKIP"] = skip
-            if force:
-                os.environ["RT_SCAN"] = force
-            else:
-                os.environ.pop("RT_SCAN", None)
+            for k, v in (("RT_SCAN", force), ("RT_SPARSE_T0", t0)):
+                if v:
+                    os.environ[k] = v
+                else:
+                    os.environ.pop(k, None)
             bulk = tape.bulk_scan([cfg])
             units = _all_units(bulk)
             evs = []
@@ -175,13 +180,18 @@ def test_fast_kernel_equals_generic_kernel_on_every_unit(name, cuda_lib):
                 evs.append(None if r is None else (r[0].tobytes(), r[1]))
             res.append((units, evs, bulk.stats().events))
             bulk.free()
-        os.environ.pop("RT_SCAN", None); os.environ.pop("RT_FAST_SKIP", None)
-        (ug, eg, ng), (uf, ef, nf), (us, es, ns) = res
-        assert len(ug) == len(uf) == len(us) and ng == nf == ns, (len(ug), len(uf), len(us), ng, nf, ns)
-        for a, b, x, y in zip(ug, uf, eg, ef):                     # walking every row: identical in everything
-            assert a == b, f"proof data differ for unit {a['unit_index']} [{a['row0']},{a['row_end']}): generic {a} fast {b}"
-            assert x == y, f"events differ for unit {a['unit_index']} [{a['row0']},{a['row_end']})"
-        for a, b in zip(ug, us):                                   # jumping over quiet stretches: same events, sound proof data
+        for k in ("RT_SCAN", "RT_FAST_SKIP", "RT_SPARSE_T0"):
+            os.environ.pop(k, None)
+        (ug, eg, ng) = res[0]
+        for vi in (1, 3, 4, 5):                                    # walking / deriving every row: identical in everything
+            (uf, ef, nf) = res[vi]
+            assert len(ug) == len(uf) and ng == nf, (variants[vi], len(ug), len(uf), ng, nf)
+            for a, b, x, y in zip(ug, uf, eg, ef):
+                assert a == b, f"{variants[vi]}: proof data differ for unit {a['unit_index']} [{a['row0']},{a['row_end']}): generic {a} other {b}"
+                assert x == y, f"{variants[vi]}: events differ for unit {a['unit_index']} [{a['row0']},{a['row_end']})"
+        (us, es, ns) = res[2]
+        assert len(ug) == len(us) and ng == ns
+        for a, b in zip(ug, us):                                   # K3b jumping over quiet stretches: same events, sound proof data
             assert not any(b["failed"]), f"unit {b['unit_index']}: failed flags {b['failed']}"
             for key in ("row0", "row_end", "first_event_row", "nevents", "quiet_from"):
                 assert a[key] == b[key], (key, a, b)
@@ -192,6 +202,35 @@ def test_fast_kernel_equals_generic_kernel_on_every_unit(name, cuda_lib):
         nunits += len(ug)
     tape.close()
     assert nunits > 0
+
+
+@pytest.mark.parametrize("name", ["Microdata_20blks", "LJS009_part1_39blks", "tss_4secs"])
+def test_peak_mask_kernel_equals_definition(name, cuda_lib, oracle_lib):
+    """phase A of the two-pass scan (int16x2 SIMD in registers) against the oracle's brute-force definition of the two bit planes,
+    on real captures, for the window widths of every built-in parameter set and a few odd ones"""
+    from readtape_b200 import parmsets
+    doc, segs, heads, rows = load_capture(name)
+    desc = evlog.desc_from_heads(heads)
+    tg, to = cuda_lib.open(desc), oracle_lib.open(desc)
+    tg.upload(rows); to.upload(rows)
+    base = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT)][0]
+    table = parmsets.BUILTIN[base.mode]
+    widths = set()
+    for pi, scale in [(p, 1.0) for p in range(len(table))] + [(0, 0.3), (0, 0.45), (0, 2.2), (0, 3.9)]:
+        cfg = abi.make_cfg(base.mode, table[pi], base.bpi * scale, base.ips, flags=base.flags, skew=base.skew)
+        w = cuda_lib.L.rt_pkww_width(C.byref(cfg), desc.tdelta_ns)
+        if w < 3 or (w, table[pi]["pkww_rise"]) in widths:
+            continue
+        widths.add((w, table[pi]["pkww_rise"]))
+        for frac in (0.25, 1.0):
+            cg, ag, t0g = tg.peak_masks(cfg, frac)
+            co, ao, t0o = to.peak_masks(cfg, frac)
+            assert t0g == t0o and t0g >= 16
+            assert np.array_equal(cg, co), f"cand differs: width {w} T0 {t0g}"
+            assert np.array_equal(ag, ao), f"acan differs: width {w} T0 {t0g}"
+            assert co.any() and ao.any()
+    tg.close(); to.close()
+    assert len(widths) >= 4, widths
 
 
 def test_fast_kernel_on_synthetic_tape_equals_oracle(cuda_lib, oracle_lib):

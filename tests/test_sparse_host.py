@@ -1,0 +1,205 @@
+"""The two-pass scan K3c (readtape_b200/csrc/scan_masks.cuh + scan_sparse.cuh) built for the HOST, against the reference.
+
+Phase A (candidate / canonical bit planes, int16x2 SIMD by doubling) is checked against its brute-force definition for
+every window width; phase B (the sparse sequential scan) must reproduce the reference's events on every eligible decode
+segment of the bundled captures (committed digests), for thresholds T0 that make the masks dense, normal and so high
+that the scan keeps falling back to its row-by-row mode, and must produce the same proof data as the one-pass fast
+path.  The CUDA kernels instantiate the same __host__ __device__ code; the GPU tests check kernel == this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_capture
+from readtape_b200 import abi, evlog, parmsets, synth, tbin
+from test_fast_host import HOST_LIB, fast_scan, make_planes
+
+META_WORDS_NO_PAD = slice(0, -1)          # TrkMeta as u32 words without the trailing diagnostics word
+
+
+@pytest.fixture(scope="session")
+def host_lib():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host_fast")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    L = C.CDLL(HOST_LIB)
+    L.fast_host_scan_unit.restype = C.c_int
+    L.fast_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg),
+                                      C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    L.sparse_host_scan_unit.restype = C.c_int
+    L.sparse_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg),
+                                        C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+    L.masks_host_build.restype = C.c_int
+    L.masks_host_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    return L
+
+
+def sparse_scan(L, planes, stride, nrows, desc, cfg, row0, row_end, frac=0.25, gmm=1, cap=1 << 16):
+    nt = desc.ntrks
+    out = np.zeros((nt, cap), dtype=abi.EVENT_DTYPE)
+    counts = np.zeros(nt, dtype=np.uint32)
+    meta = np.zeros((nt, L.fast_host_meta_size()), dtype=np.uint8)
+    rc = L.sparse_host_scan_unit(planes.ctypes.data, stride, nrows, C.byref(desc), C.byref(cfg), row0, row_end,
+                                 out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, frac, gmm)
+    if rc != 0:
+        return None, None
+    assert counts.max(initial=0) <= cap
+    ev = np.concatenate([out[k, :counts[k]] for k in range(nt)])
+    order = np.lexsort((ev["trk"], ev["row"]))
+    return ev[order], meta.view("<u4")
+
+
+def fast_meta(L, planes, stride, nrows, desc, cfg, row0, row_end, cap=1 << 16):
+    nt = desc.ntrks
+    out = np.zeros((nt, cap), dtype=abi.EVENT_DTYPE)
+    counts = np.zeros(nt, dtype=np.uint32)
+    meta = np.zeros((nt, L.fast_host_meta_size()), dtype=np.uint8)
+    rc = L.fast_host_scan_unit(planes.ctypes.data, stride, nrows, C.byref(desc), C.byref(cfg), row0, row_end,
+                               out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, 0)   # gap skipping off: every row tracked
+    assert rc == 0
+    return meta.view("<u4")
+
+
+@pytest.mark.parametrize("w", list(range(3, 51)))
+def test_masks_simd_equals_definition(w, host_lib):
+    """phase A, every window width: random walk + plateaus + full-scale steps, two thresholds"""
+    rng = np.random.default_rng(1000 + w)
+    n = 64 * 40
+    a = np.cumsum(rng.integers(-900, 901, size=(3, n)), axis=1)
+    a[1] = (a[1] // 700) * 700                                   # plateaus: many equal samples
+    a[2, ::97] = 32767; a[2, 5::131] = -32768                    # extreme values
+    planes = np.clip(a, -32768, 32767).astype("<i2")
+    planes = np.ascontiguousarray(planes)
+    stride = n
+    ms = 2 * (n // 64) + 4
+    for T0 in (1, 57, 3000, 65535):
+        got = [np.zeros((3, ms), dtype=np.uint32) for _ in range(2)]
+        want = [np.zeros((3, ms), dtype=np.uint32) for _ in range(2)]
+        assert host_lib.masks_host_build(planes.ctypes.data, stride, 3, n // 64, w, T0, got[0].ctypes.data, got[1].ctypes.data, ms, 1) == 0
+        assert host_lib.masks_host_build(planes.ctypes.data, stride, 3, n // 64, w, T0, want[0].ctypes.data, want[1].ctypes.data, ms, 0) == 0
+        assert np.array_equal(got[0], want[0]), f"cand differs, w={w} T0={T0}"
+        assert np.array_equal(got[1], want[1]), f"acan differs, w={w} T0={T0}"
+        assert want[1].any() and (T0 > 3000 or want[0].any())
+
+
+ELIGIBLE = ["Microdata_20blks.nm_tap", "Microdata_20blks", "PLAGO_beginning.nm_tap", "PLAGO_beginning", "1600bpi_ukn_6s",
+            "LJS009_part1_39blks", "SRI_SDS_102715028_4secs", "tss_4secs"]
+
+
+@pytest.mark.parametrize("name", ELIGIBLE)
+def test_sparse_scan_reproduces_reference_events(name, host_lib):
+    doc, segs, heads, rows = load_capture(name)
+    desc = evlog.desc_from_heads(heads)
+    nrows = rows.shape[0]
+    end = np.nonzero(rows[:, 0] == -32768)[0]
+    if len(end):
+        nrows = int(end[0])
+    planes, stride = make_planes(rows[:nrows], desc)
+    done = 0; skipped = walked = 0
+    for seg in segs:
+        if seg.reset_kind != abi.RT_RESET_FULL or (seg.flags & abi.RT_F_DENSITY_DETECT):
+            continue
+        cfg = evlog.cfg_for(seg)
+        stop = min(seg.end_row if seg.end_row >= 0 else nrows, nrows)
+        ref_meta = None
+        for frac, gmm in ((0.25, 1), (1.0, 1), (0.03, 0)):
+            ev, meta = sparse_scan(host_lib, planes, stride, nrows, desc, cfg, seg.row, stop, frac, gmm)
+            if ev is None:
+                break
+            canon = evlog.to_canon(ev)
+            if seg.stop_row >= 0:
+                canon = canon[canon["row"] <= seg.stop_row]
+            assert evlog.matches_fixture(seg, canon), \
+                f"{name}: segment at row {seg.row} parmset {seg.parmset} T0 frac {frac}: {len(canon)} events, reference {seg.nevents}"
+            assert not meta[:, -2].any(), f"{name}: segment at row {seg.row}: failed flags {meta[:, -2]}"
+            if ref_meta is None:
+                ref_meta = fast_meta(host_lib, planes, stride, nrows, desc, cfg, seg.row, stop)
+            assert np.array_equal(meta[:, META_WORDS_NO_PAD], ref_meta[:, META_WORDS_NO_PAD]), \
+                f"{name}: segment at row {seg.row} frac {frac}: proof data differs from the one-pass fast path"
+            if frac == 0.25:
+                skipped += int(meta[:, -1].sum()); walked += (stop - seg.row) * desc.ntrks
+        else:
+            done += 1
+    assert done > 0
+    print(f"{name}: {done} segments, {100.0 * skipped / max(walked, 1):.1f} % of the track-rows not walked row by row")
+
+
+def test_sparse_scan_equals_oracle_on_synthetic(host_lib, oracle_lib):
+    """whole synthetic tape as ONE unit, with and without a per-track skew, from several start rows"""
+    hdr, rows = synth.nrzi_tape(nblocks=8, seed=11)
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    planes, stride = make_planes(rows, desc)
+    n = rows.shape[0]
+    for skew in (None, [0, 3, 1, 7, 2, 0, 12, 5, 50]):
+        for pi in (0, 4):
+            cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[pi], hdr.bpi, hdr.ips, skew=skew)
+            tape = oracle_lib.open(desc); tape.upload(rows)
+            for row0 in (0, 4096, 64 * 137):
+                sc = tape.scan(cfg); sc.reset(abi.RT_RESET_FULL, row0)
+                want, _ = sc.run(n); sc.end()
+                ref_meta = fast_meta(host_lib, planes, stride, n, desc, cfg, row0, n)
+                for frac in (0.25, 0.9):
+                    got, meta = sparse_scan(host_lib, planes, stride, n, desc, cfg, row0, n, frac)
+                    assert got is not None and not meta[:, -2].any()
+                    a, b = evlog.to_canon(got), evlog.to_canon(want)
+                    if a.tobytes() != b.tobytes():
+                        k = evlog._first_diff(a, b)
+                        pytest.fail(f"skew {skew} parmset {pi} row0 {row0} frac {frac}: event #{k}: sparse {a[k] if k < len(a) else None} "
+                                    f"oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)})")
+                    assert np.array_equal(meta[:, META_WORDS_NO_PAD], ref_meta[:, META_WORDS_NO_PAD])
+                    if frac == 0.25:
+                        assert meta[:, -1].sum() > 0.9 * (n - row0) * 9        # nearly all rows are never walked
+            tape.close()
+
+
+@pytest.mark.parametrize("bpi,pi,mode", [(1600, 0, "nrzi"), (556, 1, "nrzi"), (300, 4, "nrzi"), (200, 0, "nrzi"), (800, 0, "pe"), (400, 2, "pe"), (1100, 6, "pe")])
+def test_sparse_scan_other_window_widths(bpi, pi, mode, host_lib, oracle_lib):
+    """window widths 3..50, PE feedback, odd skews: the same synthetic samples scanned under other densities"""
+    hdr, rows = synth.nrzi_tape(nblocks=4, seed=5)
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    planes, stride = make_planes(rows, desc)
+    n = rows.shape[0]
+    m = tbin.MODE_NRZI if mode == "nrzi" else tbin.MODE_PE
+    table = parmsets.NRZI if mode == "nrzi" else parmsets.PE
+    cfg = abi.make_cfg(m, table[pi], float(bpi), hdr.ips, skew=[1, 0, 5, 2, 0, 9, 3, 0, 17])
+    tape = oracle_lib.open(desc); tape.upload(rows)
+    for row0 in (0, 32 * 211):
+        sc = tape.scan(cfg); sc.reset(abi.RT_RESET_FULL, row0)
+        want, _ = sc.run(n); sc.end()
+        ref_meta = fast_meta(host_lib, planes, stride, n, desc, cfg, row0, n)
+        for frac, gmm in ((0.25, 1), (0.6, 0)):
+            got, meta = sparse_scan(host_lib, planes, stride, n, desc, cfg, row0, n, frac, gmm)
+            assert got is not None and not meta[:, -2].any()
+            a, b = evlog.to_canon(got), evlog.to_canon(want)
+            if a.tobytes() != b.tobytes():
+                k = evlog._first_diff(a, b)
+                pytest.fail(f"bpi {bpi} parmset {pi} row0 {row0} frac {frac}: event #{k}: sparse {a[k] if k < len(a) else None} "
+                            f"oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)})")
+            assert np.array_equal(meta[:, META_WORDS_NO_PAD], ref_meta[:, META_WORDS_NO_PAD])
+    tape.close()
+
+
+def test_oracle_mask_definition_equals_host_build(host_lib, oracle_lib):
+    """rt_peak_masks of the oracle (what the GPU mask kernel is compared with) == the host build of the SIMD code"""
+    doc, segs, heads, rows = load_capture("Microdata_20blks")
+    desc = evlog.desc_from_heads(heads)
+    nrows = int(np.nonzero(rows[:, 0] == -32768)[0][0]) if (rows[:, 0] == -32768).any() else rows.shape[0]
+    planes, stride = make_planes(rows[:nrows], desc)
+    tape = oracle_lib.open(desc); tape.upload(rows)
+    assert tape.nrows == nrows
+    seg = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT)][0]
+    cfg = evlog.cfg_for(seg)
+    co, ao, t0 = tape.peak_masks(cfg, 0.25)
+    w = oracle_lib.L.rt_pkww_width(C.byref(cfg), desc.tdelta_ns)
+    nruns = (nrows + 63) // 64
+    ms = 2 * nruns + 4
+    cg = np.zeros((desc.ntrks, ms), dtype=np.uint32); ag = np.zeros((desc.ntrks, ms), dtype=np.uint32)
+    assert host_lib.masks_host_build(planes.ctypes.data, stride, desc.ntrks, nruns, w, t0, cg.ctypes.data, ag.ctypes.data, ms, 1) == 0
+    nw = (nrows + 31) // 32
+    if nrows & 31:
+        keep = np.uint32((1 << (nrows & 31)) - 1)
+        cg[:, nw - 1] &= keep; ag[:, nw - 1] &= keep
+    assert np.array_equal(cg[:, :nw], co[:, :nw]) and np.array_equal(ag[:, :nw], ao[:, :nw])
+    assert co.any() and ao.any()
+    tape.close()
