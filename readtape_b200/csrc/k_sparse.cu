@@ -6,6 +6,7 @@
  *  k_units_sparse    phase B (scan_sparse.cuh): one lane per (unit, track) job, fetched dynamically; visits candidate rows only.
  *                    Same outputs as k_units_fast / k_units_scan: events into the chunk pool, TrkMeta with the proof data.
  */
+#include <stdlib.h>
 #include "scan_sparse.cuh"
 #include "kernels.h"
 #include "emit.cuh"
@@ -69,23 +70,27 @@ int peak_mask_T0(const DevCfg &c, float frac) {
 
 struct SparseJobs {
    const DevCfg &c; const UnitDesc *units; TrkMeta *meta; rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
-   int quiet_thr_lsb; unsigned long long *counters /* [0] rows, [1] events, [2] next job */; uint64_t total; uint64_t cur;
+   int quiet_thr_lsb; unsigned long long *counters /* [0] rows, [1] events, [2] next job group */; uint64_t total; uint64_t cur; bool exhausted;
    template <class Scan>
-   __device__ bool next(Scan &us) {                           /* per lane: one (unit, track) job at a time */
-      for (;;) {
-         cur = atomicAdd(&counters[2], 1ull);
-         if (cur >= total) return false;
-         const uint32_t u = (uint32_t)(cur / c.ntrks); const int trk = (int)(cur % c.ntrks);
-         const UnitDesc ud = units[u];
-         if (ud.row_end - ud.row0 > (1ull << 30)) {            /* offsets are 32-bit: leave such a unit to the exact scan */
-            TrkMeta m;
-            m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
-            m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
-            meta[cur] = m;
-            continue; }
-         PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
-         us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
-         return true; } }
+   __device__ bool next(Scan &us) {                           /* warp-collective: groups of 32 consecutive jobs, fetched dynamically */
+      const int lane = threadIdx.x & 31;
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&counters[2], 32ull);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      exhausted = base >= total;
+      cur = base + (unsigned)lane;
+      if (cur >= total) return false;
+      const uint32_t u = (uint32_t)(cur / c.ntrks); const int trk = (int)(cur % c.ntrks);
+      const UnitDesc ud = units[u];
+      if (ud.row_end - ud.row0 > (1ull << 30)) {            /* offsets are 32-bit: leave such a unit to the exact scan */
+         TrkMeta m;
+         m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
+         m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
+         meta[cur] = m;
+         return false; }
+      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+      us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
+      return true; }
    template <class Scan>
    __device__ void done(Scan &us) {
       TrkMeta m; us.finish(m); meta[cur] = m;
@@ -94,13 +99,16 @@ struct SparseJobs {
 
 struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };
 
-__global__ void __launch_bounds__(SPARSE_THREADS)
+/* MINB = CTAs per SM the register allocation aims at (the lane state is large: 4 -> 128 registers, 6 -> 80 with some cold
+   state spilled); which one is faster is a latency-hiding question, decided by measurement (RT_SPARSE_OCC) */
+template <int MINB>
+__global__ void __launch_bounds__(SPARSE_THREADS, MINB)
 k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
                rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
                int quiet_thr_lsb, unsigned long long *counters) {
    __shared__ uint32_t heights[RT_AGC_MAX_WINDOW * SPARSE_THREADS];      /* v_heights[] of every lane, [entry][thread] */
    const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
-   SparseJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters, total, 0};
+   SparseJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters, total, 0, false};
    SparseScan<SPARSE_THREADS, PoolEmit> us(c, heights + threadIdx.x);
    drive_sparse(us, jobs, WarpAny()); }
 
@@ -112,11 +120,16 @@ bool sparse_scan_eligible(const DevCfg &c) {
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s) {
-   static int per_sm_cached = 0;
+   static int occ = 0, per_sm_cached = 0;
    cudaError_t e;
-   if (!per_sm_cached) {
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse, SPARSE_THREADS, 0);
-      if (e != cudaSuccess) return e;
+   if (!occ) {
+      const char *env = getenv("RT_SPARSE_OCC");
+      occ = env ? atoi(env) : 4;
+      if (occ != 6 && occ != 8) occ = 4;
+      e = occ == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<4>, SPARSE_THREADS, 0)
+        : occ == 6 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<6>, SPARSE_THREADS, 0)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<8>, SPARSE_THREADS, 0);
+      if (e != cudaSuccess) { occ = 0; return e; }
       if (per_sm_cached < 1) per_sm_cached = 1; }
    int per_sm = per_sm_cached;
    if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
@@ -126,5 +139,7 @@ cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t
    if (grid < 1) grid = 1;
    e = cudaMemsetAsync(counters + 2, 0, sizeof(unsigned long long), s);
    if (e != cudaSuccess) return e;
-   k_units_sparse<<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   if (occ == 4) k_units_sparse<4><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   else if (occ == 6) k_units_sparse<6><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   else k_units_sparse<8><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
    return cudaGetLastError(); }

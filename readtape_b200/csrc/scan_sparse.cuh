@@ -34,6 +34,16 @@
 
 namespace rtsparse {
 
+#if defined(RT_SPARSE_STATS)
+struct Stats { unsigned long long steps, cands, evals, tops, bcalls, shortcut, lazy, hops, acanfound, events, dense; };
+inline Stats &stats() { static Stats s{}; return s; }
+#endif
+#if defined(RT_SPARSE_STATS) && !defined(__CUDA_ARCH__)
+#define SP_STAT(f, n) (stats().f += (n))
+#else
+#define SP_STAT(f, n) ((void)0)
+#endif
+
 using rtfast::FastState; using rtfast::OFF_NONE; using rtfast::minmax; using rtfast::span_minmax;
 using rtfast::row_time; using rtfast::volts;
 
@@ -72,7 +82,7 @@ struct SparseScan {
    uint32_t o, resume, mq; int m, T, st; float inv_lsb, rise, reqmin;
    uint32_t ndense;                                             /* rows walked in dense mode (diagnostics) */
    /* proof data (offsets relative to row0; OFF_NONE = none), as in UnitScan */
-   bool pre; uint32_t pre_pos;
+   bool pre; uint32_t pre_pos, pre_end;                         /* pre_end: the row of the first event once it is known */
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
    int32_t sync_row, loud_at_sync, sync_first, sync_early, loud_early; bool early_frozen; uint32_t sf_from; uint64_t quiet_from;
 
@@ -149,7 +159,7 @@ struct SparseScan {
       `pos` (stream offset / plane row arithmetic is the caller's), ld = its 1-based distance from the left edge, prev / next
       its neighbours.  refine_peak, decoder.c:700-749, one code path for both polarities (see UnitScan::refine). */
    RT_FHD void fire(bool top, float v, int ld, bool found, int xprev, int xnext, uint32_t oo) {
-      if (pre) { commit(); pre = false; }
+      if (pre) { pre = false; pre_end = oo; }                    /* the proof data of rows < oo is completed in finish() */
       if (!found || ld >= w || ld <= 1) { t.failed = 2; resume = oo + 1; return; }        /* the reference would fatal() */
       const float sg = top ? 1.0f : -1.0f;
       const float vprev = sg * volts(c, xprev), vnext = sg * volts(c, xnext);
@@ -180,7 +190,7 @@ struct SparseScan {
       inv_lsb = 32767.0f / c.maxvolts;
       thresholds(); resume = 0; m = 0; mq = 0; ndense = 0;
       qthr = quiet_thr_lsb; qL = w + delay; qmin = 32767; qmax = -32768; ll = last_canon = OFF_NONE;
-      sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false; pre = true;
+      sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false; pre = true; pre_end = 0;
       const int lead = (int)io > delay ? (int)io : delay;
       sf_from = (uint32_t)(lead + w + 1);
       const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
@@ -201,7 +211,7 @@ struct SparseScan {
       const bool A = had_w ? lv >= S : S == 0;
       if (A || lv == m) m = mn;                                  /* the rescan of decoder.c:767-775 */
       const bool canonical = had_w && A;
-      ++ndense;
+      ++ndense; SP_STAT(dense, 1);
       bool fired = false;
       if (o >= resume) {
          const int xl = sample(ws), xr = sample(o);
@@ -219,18 +229,56 @@ struct SparseScan {
             fired = true; } }
       if (pre && !fired) track(o, canonical);
       const uint32_t cur = o;
-      ++o; pre_pos = o;
+      ++o; if (pre) pre_pos = o;
       if (o >= end) { st = SP_DONE; return; }
       /* from a canonical row of the pure regime on, the state is what the masks describe */
       if (canonical && cur >= o_pure && T >= c.T0 && c.T0 > 0) { st = SP_SPARSE; mq = cur; } }
 
    /* ---- sparse mode ---- */
-   RT_FHD int window_min(uint64_t p) const {
-      int mn = 32767;
-      const int16_t *q = plane + (p - (uint32_t)w + 1u);
-      for (int i = 0; i < w; ++i) { const int v = q[i]; if (v < mn) mn = v; }
-      return mn; }
-   /* the lazy minimum at stream offset oo (plane row p), from its last exactly known value (row mq) */
+   /* One pass over the w samples at win[0 .. w): packed keys carry value and position through a single min / max,
+         kmax = max_i ((v_i + 32768) << 6 | 63 - i)  ->  maximum and its LEFTMOST position
+         kmin = min_i ((v_i + 32768) << 6 | i)       ->  minimum and its LEFTMOST position
+         keq  = min_i (v_i == val ? i : 64)          ->  leftmost position of a sample equal to val (64: none)       (EQ only)
+      (w <= 50 < 64).  Windows of up to 16 samples -- every built-in parameter set at the usual 10..20 samples per bit -- are
+      read with 16 independent predicated loads, so that the lane waits for memory once, not once per sample. */
+   struct WinKeys { uint32_t kmax, kmin, keq; };
+   static RT_FHD int key_val(uint32_t k) { return (int)(k >> 6) - 32768; }
+   static RT_FHD int kmax_pos(uint32_t k) { return 63 - (int)(k & 63u); }
+   static RT_FHD int kmin_pos(uint32_t k) { return (int)(k & 63u); }
+   template <bool MAXK, bool EQ>
+   RT_FHD WinKeys scan_window(const int16_t *win, int val) const {
+      WinKeys r{0u, 0xffffffffu, 64u};
+      if (w <= 16) {
+         int v[16];
+#pragma unroll
+         for (int i = 0; i < 16; ++i) v[i] = i < w ? (int)win[i] : 0;
+#pragma unroll
+         for (int i = 0; i < 16; ++i) {
+            if (i < w) {
+               const uint32_t kb = ((uint32_t)(v[i] + 32768) << 6) + (uint32_t)i;
+               if (kb < r.kmin) r.kmin = kb;
+               if (MAXK) { const uint32_t kt = kb + (uint32_t)(63 - 2 * i); if (kt > r.kmax) r.kmax = kt; }
+               if (EQ) { if (v[i] == val && (uint32_t)i < r.keq) r.keq = (uint32_t)i; } } } }
+      else {
+         for (int i = 0; i < w; ++i) {
+            const int vi = (int)win[i];
+            const uint32_t kb = ((uint32_t)(vi + 32768) << 6) + (uint32_t)i;
+            if (kb < r.kmin) r.kmin = kb;
+            if (MAXK) { const uint32_t kt = kb + (uint32_t)(63 - 2 * i); if (kt > r.kmax) r.kmax = kt; }
+            if (EQ) { if (vi == val && (uint32_t)i < r.keq) r.keq = (uint32_t)i; } } }
+      return r; }
+   /* is there an acan row in plane rows [lo, hi]  (hi - lo < 64) */
+   RT_FHD bool acan_in(uint64_t lo, uint64_t hi) const {
+      const uint32_t n = (uint32_t)(hi - lo) + 1u;
+      uint32_t b = bits_at(ma, lo);
+      if (n < 32) return (b & ((1u << n) - 1u)) != 0;
+      if (b) return true;
+      b = bits_at(ma, lo + 32);
+      return (n >= 64 ? b : (b & ((1u << (n - 32)) - 1u))) != 0; }
+   /* The lazy minimum at stream offset oo (plane row p), from its last exactly known value (row mq).  m only changes at
+      refresh rows: acan rows, and rows where the sample that leaves equals m (decoder.c:767).  After a refresh at row r the value
+      is Wmin(r) and the next refresh of the second kind happens when the LEFTMOST sample with that value leaves, at row
+      (its position) + w -- so the walk hops from refresh to refresh instead of visiting every row. */
    RT_FHD void lazy_min(uint32_t oo) {
       if (mq == oo) return;
       const uint64_t p = prow(oo), pm = prow(mq);
@@ -246,9 +294,20 @@ struct SparseScan {
             if (bits) { a = base + 31u - (uint32_t)clz32(bits); have = true; break; }
             if (base <= pm || wi == 0) break;
             --wi; bits = ma[wi]; } }
-      uint64_t q = pm;
-      if (have) { m = window_min(a); q = a; }
-      for (++q; q <= p; ++q) if ((int)plane[q - (uint32_t)w] == m) m = window_min(q);
+      SP_STAT(lazy, 1); SP_STAT(acanfound, have ? 1 : 0);
+      /* one loop for both starts -- from the acan row a (m = its window minimum) or from row pm (m as it is: find the sample that
+         carries it) -- and for the hops, so that the lanes of a warp that need this run the same code */
+      uint64_t r = have ? a : pm;
+      bool keep = !have;
+      for (;;) {
+         const uint64_t ws = r - (uint32_t)w + 1u;
+         const WinKeys k = scan_window<false, true>(plane + ws, m);
+         uint64_t at;
+         if (keep && k.keq < 64u) at = ws + k.keq;
+         else { m = key_val(k.kmin); at = ws + (uint32_t)kmin_pos(k.kmin); }
+         keep = false;
+         if (at + (uint32_t)w > p) break;
+         r = at + (uint32_t)w; SP_STAT(hops, 1); }
       mq = oo; }
 
    RT_FHD void sparse_step() {
@@ -264,22 +323,31 @@ struct SparseScan {
       p += (uint32_t)ctz32(bits);
       if (p >= pend) { o = end; st = SP_DONE; return; }
       const uint32_t oc = (uint32_t)(p - row0) + (uint32_t)delay;
-      /* window maximum, its leftmost position, the edges */
+      /* window maximum (leftmost position) and minimum, the edges; then the integer pre-filter for the CURRENT threshold bound T:
+         the top test can only pass if S - max(l, r) >= T, the bottom test only if min(l, r) - m >= T, and m >= Wmin */
       const int16_t *win = plane + (p - (uint32_t)w + 1u);
-      int S = -32768, pos = 0;
-      for (int i = 0; i < w; ++i) { const int v = win[i]; if (v > S) { S = v; pos = i; } }
+      const WinKeys wk = scan_window<true, false>(win, 0);
+      const int S = key_val(wk.kmax), mn = key_val(wk.kmin), posm = kmin_pos(wk.kmin);
+      int pos = kmax_pos(wk.kmax);
       const int xl = win[0], xr = win[w - 1];
+      const bool tcand = S - (xl > xr ? xl : xr) >= T, bcand = (xl < xr ? xl : xr) - mn >= T;
+      o = oc + 1;
+      SP_STAT(cands, 1);
+      if (!tcand && !bcand) { if (o >= end) st = SP_DONE; return; }
+      SP_STAT(evals, 1);
       const float vl = volts(c, xl), vr = volts(c, xr), maxv = volts(c, S);
-      const bool top = maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
+      const bool top = tcand && maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
       bool bot = false; float minv = 0;
-      if (!top) {
-         lazy_min(oc);
+      if (!top && bcand) {
+         /* a refresh at or after the row at which the window's (leftmost) minimum entered makes m that minimum */
+         SP_STAT(bcalls, 1);
+         if (acan_in(p - (uint32_t)w + 1u + (uint32_t)posm, p)) { m = mn; mq = oc; SP_STAT(shortcut, 1); }
+         else lazy_min(oc);
          minv = volts(c, m);
          bot = minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
-         if (bot) { pos = -1; for (int i = w; i-- > 0;) if ((int)win[i] == m) pos = i; } }
-      o = oc + 1;
+         if (bot) { pos = posm; if (m != mn) { pos = -1; for (int i = w; i-- > 0;) if ((int)win[i] == m) pos = i; } } }
       if (top || bot) {
-         if (pre) advance_pre(oc);
+         SP_STAT(events, 1); SP_STAT(tops, top ? 1 : 0);
          const bool found = pos >= 0;
          const int xprev = found && pos > 0 ? win[pos - 1] : 0, xnext = found && pos < w - 1 ? win[pos + 1] : 0;
          fire(top, top ? maxv : minv, pos + 1, found, xprev, xnext, oc);
@@ -289,7 +357,9 @@ struct SparseScan {
    RT_FHD void step() { if (st == SP_DENSE) dense_step(); else if (st == SP_SPARSE) sparse_step(); }
 
    RT_FHD void finish(TrkMeta &meta) {
-      if (pre) { advance_pre(end); commit(); }        /* dense mode keeps pre_pos == o: nothing left then */
+      /* rows before the first event (or the whole unit) that the sparse mode has not tracked yet: done here, for all lanes of
+         the warp together (dense mode keeps pre_pos == o: nothing is left then) */
+      advance_pre(pre ? end : pre_end); commit();
       meta.first_event_row = em.first_row;
       meta.sync_row = sync_row == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_row;
       meta.last_loud_row = loud_at_sync == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_at_sync);
@@ -300,20 +370,21 @@ struct SparseScan {
       meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = end > ndense ? end - ndense : 0; } };   /* pad: rows not walked (diagnostics) */
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through (unit, track) jobs.  `Jobs` provides
- *   bool next(Scan&)   start the lane's next job, false if there is none
+ *   bool next(Scan&)   start the lane's next job, false if there is none (called by all lanes of the warp together)
+ *   bool exhausted     set by next() when the job list has run out (the same for all lanes)
  *   void done(Scan&)   the lane's job is finished (store its TrkMeta)
- * `any(pred)` is the warp vote (identity on the host).  Lanes fetch jobs independently: a lane in a gap costs a few
- * mask words per step, so there is nothing to gain from keeping the lanes of a warp on neighbouring rows. */
+ * `any(pred)` is the warp vote (identity on the host).  The warp takes 32 consecutive jobs (the tracks of 3-4 neighbouring units)
+ * at a time, so that the per-job work -- quiet pre-scan, window fill, the walk to the first event, proof data -- runs for all lanes
+ * together instead of one lane at a time while the other 31 wait. */
 template <class Scan, class Jobs, class Vote>
 RT_FHD void drive_sparse(Scan &us, Jobs &jobs, Vote any) {
-   bool have = false;
    for (;;) {
-      if (!have || us.st == SP_DONE) {
-         if (have) jobs.done(us);
-         have = jobs.next(us); }
-      if (!any(have)) return;
-      if (have) {
+      const bool have = jobs.next(us);
+      if (jobs.exhausted) return;
+      while (any(have && us.st != SP_DONE)) {
+         if (have && us.st != SP_DONE) {
 #pragma unroll 1
-         for (int k = 0; k < 4 && us.st != SP_DONE; ++k) us.step(); } } }
+            for (int k = 0; k < 4 && us.st != SP_DONE; ++k) us.step(); } }
+      if (have) jobs.done(us); } }
 
 }  // namespace rtsparse

@@ -102,9 +102,10 @@ extern "C" int masks_host_build(const int16_t *planes, uint64_t plane_stride, in
 
 struct HostSparseJobs {
    const DevCfg &dc; const int16_t *planes; uint64_t plane_stride, row0, row_end; rt_event *out; uint32_t cap; uint32_t *counts; TrkMeta *meta;
-   int thr, k;
+   int thr, k; bool exhausted;
    template <class Scan> bool next(Scan &us) {
-      if (k >= dc.ntrks) return false;
+      exhausted = k >= dc.ntrks;
+      if (exhausted) return false;
       HostEmit em{out + (size_t)k * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)k};
       us.begin(planes + (size_t)k * plane_stride, row0, row_end, k, em, thr);
       return true; }
@@ -151,9 +152,17 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
    dc.m_cand = cc.cand.data(); dc.m_acan = cc.acan.data(); dc.mask_stride = cc.mask_stride; dc.T0 = T0;
    if (use_gmm) { dc.gmm = cc.gmm.data(); dc.ngran_cap = cc.ngran; }
    uint32_t heights[RT_AGC_MAX_WINDOW];
-   HostSparseJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0};
+   HostSparseJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0, false};
    rtsparse::SparseScan<1, HostEmit> us(dc, heights);
    rtsparse::drive_sparse(us, jobs, HostAny());
    return RT_OK; }
+
+#ifdef RT_SPARSE_STATS
+extern "C" void sparse_host_stats(unsigned long long *out) { memcpy(out, &rtsparse::stats(), sizeof(rtsparse::Stats)); memset(&rtsparse::stats(), 0, sizeof(rtsparse::Stats)); }
+#endif
+/* volts() of the scan code for every int16 value (exhaustive check of the division-free formulation) */
+extern "C" void volts_host_all(float maxvolts, float *out /* [65536], index x + 32768 */) {
+   DevCfg dc; memset(&dc, 0, sizeof dc); dc.maxvolts = maxvolts;
+   for (int x = -32768; x <= 32767; ++x) out[x + 32768] = rtfast::volts(dc, x); }
 
 extern "C" int fast_host_meta_size(void) { return (int)sizeof(TrkMeta); }

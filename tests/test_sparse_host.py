@@ -203,3 +203,13 @@ def test_oracle_mask_definition_equals_host_build(host_lib, oracle_lib):
     assert np.array_equal(cg[:, :nw], co[:, :nw]) and np.array_equal(ag[:, :nw], ao[:, :nw])
     assert co.any() and ao.any()
     tape.close()
+
+
+def test_volts_without_division_is_exact(host_lib):
+    """readtape.c:1420 v = (float)i16 / 32767 * maxvolts: the scan code's FMA formulation of the division, for every int16 value"""
+    x = np.arange(-32768, 32768, dtype=np.float32)
+    for mv in (4.4, 3.2, 1.0, 0.7071, 12.5, 7.3):
+        out = np.zeros(65536, dtype=np.float32)
+        host_lib.volts_host_all(C.c_float(mv), out.ctypes.data)
+        want = (x / np.float32(32767)) * np.float32(mv)
+        assert want.dtype == np.float32 and np.array_equal(out.view(np.uint32), want.view(np.uint32)), mv
