@@ -17,13 +17,16 @@
 using namespace rtsparse;
 
 /* grid: x = groups of MASK_THREADS runs, y = track.  Runs whose halo would reach in front of the plane use the scalar path. */
+struct TrackT0 { int32_t v[RT_MAXTRKS]; };                      /* per-track mask threshold, passed by value */
+
 template <int W>
 __global__ void __launch_bounds__(MASK_THREADS)
-k_peak_masks(const int16_t *planes, uint64_t plane_stride, uint64_t run_lo, uint64_t nruns, uint32_t T0,
+k_peak_masks(const int16_t *planes, uint64_t plane_stride, uint64_t run_lo, uint64_t nruns, const __grid_constant__ TrackT0 t0s,
              uint32_t *cand, uint32_t *acan, uint64_t mask_stride) {
    const uint64_t r = (uint64_t)blockIdx.x * MASK_THREADS + threadIdx.x;
    if (r >= nruns) return;
    const int trk = blockIdx.y;
+   const uint32_t T0 = (uint32_t)t0s.v[trk];
    const int16_t *plane = planes + (size_t)trk * plane_stride;
    const int64_t p0 = (int64_t)(run_lo + r) * rtmask::MASK_RUN;
    uint32_t cw[2], aw[2];
@@ -38,7 +41,9 @@ k_peak_masks(const int16_t *planes, uint64_t plane_stride, uint64_t run_lo, uint
 template <int W>
 static cudaError_t launch_masks_w(const DevCfg &c, uint64_t run_lo, uint64_t nruns, uint32_t *cand, uint32_t *acan, cudaStream_t s) {
    dim3 grid((unsigned)((nruns + MASK_THREADS - 1) / MASK_THREADS), (unsigned)c.ntrks);
-   k_peak_masks<W><<<grid, MASK_THREADS, 0, s>>>(c.planes, c.plane_stride, run_lo, nruns, (uint32_t)c.T0, cand, acan, c.mask_stride);
+   TrackT0 t0s;
+   for (int k = 0; k < RT_MAXTRKS; ++k) t0s.v[k] = c.T0[k] > 0 ? c.T0[k] : 65535;
+   k_peak_masks<W><<<grid, MASK_THREADS, 0, s>>>(c.planes, c.plane_stride, run_lo, nruns, t0s, cand, acan, c.mask_stride);
    return cudaGetLastError(); }
 
 /* phase A over plane rows [row_lo, row_hi) (rounded outwards to whole runs; row_hi <= plane_stride) */
@@ -113,9 +118,70 @@ k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
    drive_sparse(us, jobs, WarpAny()); }
 
 bool sparse_scan_eligible(const DevCfg &c) {
+   for (int k = 0; k < c.ntrks; ++k) if (c.T0[k] <= 0) return false;
    return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
-          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.T0 > 0 && c.m_cand && c.m_acan; }
+          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.m_cand && c.m_acan; }
 
+/* ---- choosing T0 from the data ----------------------------------------------------------------------------------------------
+ * required_rise (decoder.c:785) follows the signal: pkww_rise * (average peak-to-peak height / 4 V) / AGC gain.  A mask threshold
+ * above the bound T of the moment sends the sparse scan into its slow row-by-row mode; one far below it floods it with candidates.
+ * k_span_hist builds, per track, a histogram of the peak-to-peak span (max - min) of a sample of 128-row stretches (4 granules of
+ * the quiet map: several bit cells, so that both polarities are inside); the host (peak_mask_auto_T0) takes the full-scale height A
+ * (99.8th percentile), calls everything above A/4 signal and uses the 10th percentile of that as the smallest height to expect,
+ * halved once more because the AGC gain may reach 2.  Only speed depends on the choice, never a result. */
+#define HIST_BINS 1024                                          /* 64 LSB per bin */
+__global__ void __launch_bounds__(256)
+k_span_hist(const uint32_t *gmm, uint64_t ngran_cap, uint64_t ngroups, uint32_t nsamples, uint32_t *hist) {
+   __shared__ uint32_t h[HIST_BINS];
+   for (int i = threadIdx.x; i < HIST_BINS; i += 256) h[i] = 0;
+   __syncthreads();
+   const uint32_t *g = gmm + (size_t)blockIdx.x * ngran_cap;
+   const uint64_t stride = ngroups / nsamples > 0 ? ngroups / nsamples : 1;
+   for (uint32_t i = threadIdx.x; i < nsamples; i += 256) {
+      const uint64_t gi = (uint64_t)i * stride;
+      if (gi >= ngroups) break;
+      int mn = 32767, mx = -32768;
+      for (int k = 0; k < 4; ++k) {
+         const uint32_t v = g[4 * gi + k];
+         const int a = (int)(int16_t)(uint16_t)(v & 0xffffu), b = (int)(int16_t)(uint16_t)(v >> 16);
+         if (a < mn) mn = a; if (b > mx) mx = b; }
+      atomicAdd(&h[min(HIST_BINS - 1, max(mx - mn, 0) >> 6)], 1u); }
+   __syncthreads();
+   for (int i = threadIdx.x; i < HIST_BINS; i += 256) hist[(size_t)blockIdx.x * HIST_BINS + i] = h[i]; }
+
+uint32_t span_hist_words(int ntrks) { return (uint32_t)ntrks * HIST_BINS; }
+cudaError_t launch_span_hist(const uint32_t *gmm, uint64_t ngran_cap, uint64_t nrows, int ntrks, uint32_t *d_hist, cudaStream_t s) {
+   const uint64_t ngroups = nrows / (4 * RT_GRAN);
+   if (!ngroups) return cudaMemsetAsync(d_hist, 0, (size_t)span_hist_words(ntrks) * 4, s);
+   const uint32_t nsamples = (uint32_t)(ngroups < 65536 ? ngroups : 65536);
+   k_span_hist<<<ntrks, 256, 0, s>>>(gmm, ngran_cap, ngroups, nsamples, d_hist);
+   return cudaGetLastError(); }
+
+/* T0 of every track from the host copy of the histograms: min(0.75 * default-state bound, 0.5 * bound for the smallest signal height
+   to expect), at least 5 % of the default-state bound.  Returns false if the two-pass scan does not apply. */
+bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist) {
+   const int Tdef = peak_mask_T0(c, 1.0f);
+   if (Tdef <= 0) return false;
+   for (int k = 0; k < c.ntrks; ++k) {
+      const uint32_t *h = hist + (size_t)k * HIST_BINS;
+      unsigned long long total = 0, acc = 0;
+      for (int b = 0; b < HIST_BINS; ++b) total += h[b];
+      int T0 = (int)(0.75f * (float)Tdef);
+      if (total >= 64) {
+         int bA = 0;                                            /* full-scale height: 99.8th percentile of all stretches */
+         for (; bA < HIST_BINS; ++bA) { acc += h[bA]; if (acc * 1000 >= total * 998) break; }
+         const int b0 = bA / 4 > 1 ? bA / 4 : 1;               /* signal: at least a quarter of that */
+         unsigned long long sig = 0;
+         for (int b = b0; b < HIST_BINS; ++b) sig += h[b];
+         if (sig >= 16) {
+            acc = 0; int b = b0;
+            for (; b < HIST_BINS; ++b) { acc += h[b]; if (acc * 10 >= sig) break; }
+            const float alow = (float)(b << 6);
+            const int Test = (int)(0.5f * (c.p.pkww_rise * alow / RT_PKWW_PEAKHEIGHT * 0.999f - 2.0f));
+            if (Test < T0) T0 = Test; } }
+      const int floor_ = Tdef / 20 > 16 ? Tdef / 20 : 16;
+      c.T0[k] = T0 < floor_ ? floor_ : (T0 > 65535 ? 65535 : T0); }
+   return true; }
 /* phase B only: the masks of rows [0, max row_end) must have been built (launch_peak_masks) on the same stream */
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,

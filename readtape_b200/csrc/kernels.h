@@ -43,6 +43,9 @@ cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t n
 uint64_t peak_mask_stride(uint64_t plane_stride);
 int peak_mask_T0(const DevCfg &c, float frac);
 bool sparse_scan_eligible(const DevCfg &c);
+uint32_t span_hist_words(int ntrks);
+cudaError_t launch_span_hist(const uint32_t *gmm, uint64_t ngran_cap, uint64_t nrows, int ntrks, uint32_t *d_hist, cudaStream_t s);
+bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist);
 cudaError_t launch_peak_masks(const DevCfg &c, uint64_t row_lo, uint64_t row_hi, cudaStream_t s);
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,

@@ -437,7 +437,7 @@ static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
    return dc.det == RT_DET_PEAK ? lead + dc.width + 1 : lead + 2; }
 
 /* Everything derived from one configuration that the unit finder and the scan kernels need. */
-struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; bool use_sparse; };
+struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; bool use_sparse; bool t0_auto; };
 static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
    cfg_to_dev(t, cfg, &pl->dc);
    const DevCfg &dc = pl->dc;
@@ -452,13 +452,18 @@ static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
    const char *force = getenv("RT_SCAN");
    pl->use_fast = fast_scan_eligible(dc) && !(force && strcmp(force, "generic") == 0);
    /* K3c (two passes: candidate masks + sparse scan) where the peak-detector fast path applies; RT_SCAN=fast keeps the one-pass
-      kernel K3b (tests), RT_SPARSE_T0 = mask threshold as a fraction of the default-state bound (default 0.25) */
+      kernel K3b (tests).  The mask threshold T0 is chosen per track from the data (plan_auto_t0) unless RT_SPARSE_T0 fixes it as a
+      fraction of the default-state bound (tests). */
    const char *t0env = getenv("RT_SPARSE_T0");
-   pl->dc.T0 = 0; pl->dc.m_cand = pl->dc.m_acan = nullptr; pl->dc.mask_stride = 0;
-   pl->use_sparse = false;
+   for (int k = 0; k < RT_MAXTRKS; ++k) pl->dc.T0[k] = 0;
+   pl->dc.m_cand = pl->dc.m_acan = nullptr; pl->dc.mask_stride = 0;
+   pl->use_sparse = pl->t0_auto = false;
    if (pl->use_fast && dc.det == RT_DET_PEAK && !(force && strcmp(force, "fast") == 0)) {
-      pl->dc.T0 = peak_mask_T0(dc, t0env ? (float)atof(t0env) : 0.25f);
-      pl->use_sparse = pl->dc.T0 > 0; }
+      if (t0env) {
+         const int T0 = peak_mask_T0(dc, (float)atof(t0env));
+         for (int k = 0; k < dc.ntrks; ++k) pl->dc.T0[k] = T0;
+         pl->use_sparse = T0 > 0; }
+      else { pl->use_sparse = peak_mask_T0(dc, 1.0f) > 0; pl->t0_auto = pl->use_sparse; } }
    if (dc.det == RT_DET_PEAK) {
       pl->quiet_thr = dc.p.pkww_rise * 0.999f;
       if (dc.p.pkww_rise < 1e-3f) pl->quiet_thr = 0;                  /* nothing can be proven quiet: every lookup misses */
@@ -481,6 +486,21 @@ static cudaError_t launch_scan(const rt_tape *t, const ScanPlan &pl, const UnitD
    int grid = (int)std::min<uint64_t>((threads + 127) / 128, (uint64_t)t->sms * (max_ctas_per_sm > 0 ? 4 : 16));
    launch_units_scan(pl.dc, d_units, nunits, d_meta, d_pool, d_chunk_next, d_cursor, pool_chunks, pl.quiet_thr, pl.quiet_thr_lsb, d_counters, grid, st);
    return cudaGetLastError(); }
+
+/* per-track mask thresholds of the two-pass scan from the span histogram of the rows ingested so far (one small kernel + 36 KB D2H) */
+static cudaError_t plan_auto_t0(const rt_tape *t, ScanPlan *pl, uint64_t rows_avail, uint32_t *d_hist, std::vector<uint32_t> &h_hist, bool &have_hist, cudaStream_t st) {
+   if (!pl->t0_auto) return cudaSuccess;
+   const int nt = (int)t->desc.ntrks;
+   if (!have_hist) {
+      cudaError_t e = launch_span_hist(reinterpret_cast<const uint32_t *>(t->gmm), t->ngran_cap, rows_avail, nt, d_hist, st);
+      if (e != cudaSuccess) return e;
+      h_hist.resize(span_hist_words(nt));
+      e = cudaMemcpyAsync(h_hist.data(), d_hist, h_hist.size() * 4, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) return e;
+      e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e;
+      have_hist = true; }
+   if (!peak_mask_auto_T0(pl->dc, h_hist.data())) pl->use_sparse = false;
+   if (getenv("RT_TRACE")) { fprintf(stderr, "[two-pass scan] T0 per track:"); for (int k = 0; k < nt; ++k) fprintf(stderr, " %d", pl->dc.T0[k]); fprintf(stderr, "\n"); }
+   return cudaSuccess; }
 
 extern "C" void rt_bulk_free(rt_bulk *b) {
    if (!b) return;
@@ -520,10 +540,11 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    std::vector<cudaEvent_t> done_ev(ncfgs, nullptr);
    /* K3c: candidate / canonical bit planes, one set per distinct (window width, T0) -- parameter sets that only differ in
       clock / AGC constants share them */
-   struct MaskSet { int width, T0; uint32_t *mc, *ma; uint32_t first_cfg; };
+   struct MaskSet { int width; int32_t T0[RT_MAXTRKS]; uint32_t *mc, *ma; uint32_t first_cfg; };
+   uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have_hist = false;
    std::vector<MaskSet> msets;
    auto cleanup = [&]() {
-      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor};
+      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_hist};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
       for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream); }
       for (auto &e : ev) cudaEventDestroy(e);
@@ -565,14 +586,19 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       for (uint32_t ci = 0; ci < ncfgs; ++ci) {
          ScanPlan &pl = plans[ci];
          if (!pl.use_sparse || !b->cfgs[ci].nunits) continue;
+         if (pl.t0_auto) {
+            if (!d_hist) { CUB(cudaMallocAsync(&d_hist, (size_t)span_hist_words((int)nt) * 4, t->stream)); ++t->launches; }
+            CUB(plan_auto_t0(t, &pl, nrows, d_hist, h_hist, have_hist, t->stream));
+            if (!pl.use_sparse) continue; }
          size_t k = 0;
-         while (k < msets.size() && !(msets[k].width == pl.dc.width && msets[k].T0 == pl.dc.T0)) ++k;
+         while (k < msets.size() && !(msets[k].width == pl.dc.width && memcmp(msets[k].T0, pl.dc.T0, sizeof pl.dc.T0) == 0)) ++k;
          if (k == msets.size()) {
-            MaskSet m{pl.dc.width, pl.dc.T0, nullptr, nullptr, ci};
+            MaskSet m{}; m.width = pl.dc.width; memcpy(m.T0, pl.dc.T0, sizeof m.T0); m.first_cfg = ci;
             msets.push_back(m);
             CUB(cudaMallocAsync(&msets[k].mc, (size_t)mstride * nt * 4, t->stream));
             CUB(cudaMallocAsync(&msets[k].ma, (size_t)mstride * nt * 4, t->stream)); }
          pl.dc.m_cand = msets[k].mc; pl.dc.m_acan = msets[k].ma; pl.dc.mask_stride = mstride; } }
+   lap("mask thresholds");
 
    /* 2. all scan kernels, concurrently, into one event pool: first guess one event per 16 track-samples, regrown on overflow */
    if (total_units) {
@@ -704,6 +730,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr; TrkMeta *d_meta = nullptr;
    uint32_t *d_mc = nullptr, *d_ma = nullptr; uint64_t masks_done = 0; double ms_masks = 0;   /* K3c bit planes, built segment by segment */
+   uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have_hist = false;
    std::vector<cudaEvent_t> seg_ev; std::vector<uint64_t> seg_rows_done;
    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
    rt_bulk *b = new (std::nothrow) rt_bulk();
@@ -713,7 +740,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    bc.cfg = *cfg; bc.dc = pl.dc; bc.fast = pl.use_fast;
    bool failed = false; const char *why = "";
    auto release = [&]() {
-      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta, d_mc, d_ma};
+      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta, d_mc, d_ma, d_hist};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->s_scan);
       for (auto e : seg_ev) cudaEventDestroy(e);
       if (ev_a) cudaEventDestroy(ev_a); if (ev_b) cudaEventDestroy(ev_b); };
@@ -727,6 +754,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    if (pl.use_sparse) {
       const uint64_t mstride = peak_mask_stride(t->plane_stride);
       CUS(cudaMallocAsync(&d_mc, (size_t)mstride * nt * 4, t->s_scan)); CUS(cudaMallocAsync(&d_ma, (size_t)mstride * nt * 4, t->s_scan));
+      if (pl.t0_auto) CUS(cudaMallocAsync(&d_hist, (size_t)span_hist_words((int)nt) * 4, t->s_scan));
       pl.dc.m_cand = d_mc; pl.dc.m_acan = d_ma; pl.dc.mask_stride = mstride; }
    cudaEvent_t ev_m = nullptr; EvGuard ev_m_guard{&ev_m};
    CUS(cudaMemsetAsync(d_cursor, 0, 4, t->s_scan)); CUS(cudaMemsetAsync(d_counters, 0, 32, t->s_scan));
@@ -754,6 +782,9 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
       const bool last = k + 1 == seg_ev.size();
       const uint64_t R = seg_rows_done[k];
       CUS(cudaStreamWaitEvent(t->s_scan, seg_ev[k], 0));
+      if (pl.use_sparse && pl.t0_auto && !have_hist) {            /* mask thresholds from the first segment of the tape */
+         CUS(plan_auto_t0(t, &pl, R, d_hist, h_hist, have_hist, t->s_scan)); ++t->launches;
+         bc.dc = pl.dc; }
       CUS(cudaEventRecord(ev_a, t->s_scan));
       CUS(launch_find_units(t->gmm, t->ngran_cap, (int)nt, R, pl.up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap_tmp, d_nunits, t->s_scan, &t->launches));
       CUS(cudaEventRecord(ev_b, t->s_scan));
@@ -830,9 +861,10 @@ extern "C" int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, 
    const uint64_t nrows = t->nrows_valid;
    if (dc.det != RT_DET_PEAK || dc.invert || dc.differentiate || dc.density || wpt * 32 < nrows)
       return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: not the plain peak detector, or buffer too small");
-   dc.T0 = peak_mask_T0(dc, t0_frac);
-   if (dc.T0 <= 0) return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: T0 < 16");
-   if (t0) *t0 = dc.T0;
+   const int T0 = peak_mask_T0(dc, t0_frac);
+   if (T0 <= 0) return set_err(RT_ERR_UNSUPPORTED, "rt_peak_masks: T0 < 16");
+   for (int k = 0; k < RT_MAXTRKS; ++k) dc.T0[k] = T0;
+   if (t0) *t0 = T0;
    const uint64_t ms = peak_mask_stride(t->plane_stride); const uint32_t nt = t->desc.ntrks;
    uint32_t *d_mc = nullptr, *d_ma = nullptr;
    CU(cudaMalloc(&d_mc, (size_t)ms * nt * 4));

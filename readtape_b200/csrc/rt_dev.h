@@ -59,10 +59,10 @@ struct DevCfg {
    const uint32_t *gmm;           /* [ntrks][ngran_cap] packed (min | max<<16) of every 32-row granule; null: no gap skipping */
    uint64_t ngran_cap;
    /* K3c (scan_masks.cuh / scan_sparse.cuh): bit planes of phase A, [ntrks][mask_stride] words, bit p%32 of word p/32 = plane row p;
-      T0 = the integer threshold they were built for (0: not built) */
+      T0[k] = the integer threshold the planes of track k were built for (0: not built) */
    const uint32_t *m_cand, *m_acan;
    uint64_t mask_stride;
-   int32_t  T0;
+   int32_t  T0[RT_MAXTRKS];
 };
 
 /* Per-track detector + feedback state: the device mirror of the parts of struct trkstate_t

@@ -50,6 +50,8 @@ using rtfast::row_time; using rtfast::volts;
 enum { SP_DENSE = 0, SP_SPARSE = 1, SP_DONE = 2 };
 constexpr uint32_t NO_ROW32 = 0xffffffffu;
 #define SPARSE_SEARCH_WORDS 4          /* mask words examined per step while looking for the next candidate */
+#define SPARSE_TRIES 1                 /* candidates a lane may reject with the integer pre-filter within one step (measured: retrying
+                                          inside the step costs more in divergence than it saves in expensive-part utilisation) */
 
 /* 32 mask bits starting at bit position p (any alignment); the arrays have slack words behind the last row */
 RT_FHD uint32_t bits_at(const uint32_t *mk, uint64_t p) {
@@ -79,8 +81,9 @@ struct SparseScan {
    Emit em; FastState<STRIDE> t; uint32_t *ht;
    /* detector state: o = next row; tests are off for rows < resume (blind countdown, decoder.c:778); m = the lazy minimum,
       exact for row mq (dense mode: for row o - 1) */
-   uint32_t o, resume, mq; int m, T, st; float inv_lsb, rise, reqmin;
+   uint32_t o, resume, mq; int m, T, T0t, st; float inv_lsb, rise, reqmin;
    uint32_t ndense;                                             /* rows walked in dense mode (diagnostics) */
+   uint32_t cb, cb_o;                                           /* the 32 candidate bits of rows [cb_o, cb_o + 32) (cb_o = NO_ROW32: none held) */
    /* proof data (offsets relative to row0; OFF_NONE = none), as in UnitScan */
    bool pre; uint32_t pre_pos, pre_end;                         /* pre_end: the row of the first event once it is known */
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
@@ -142,6 +145,41 @@ struct SparseScan {
          track(pre_pos, (ma[p >> 5] >> (p & 31)) & 1u);
          ++pre_pos; } }
 
+   /* The quiet pre-scan of rows [-npre, -1] (UnitScan feeds them one by one).  Only two things survive it: the last loud row, and a
+      (min, max) pair that covers at least the last qL rows.  A unit starts right behind the previous block, so walking the rows
+      forwards means an exact span for nearly every one of them; instead the rows are visited BACKWARDS until the first loud one:
+      for a row whose whole span [row - qL + 1, row] has been fed, "loud" is exactly "that span >= qthr" (quiet.cuh), whatever the
+      tracker's running pair was, and a pair over a SUPERSET of the tracker's rows decides every later row the same way.  Whole
+      quiet granules are skipped with the granule map.  Only if no such row is loud are the first qL - 1 rows -- whose verdict
+      depends on where feeding started -- fed the original way. */
+   RT_FHD void prescan(int32_t npre) {
+      const int32_t pure_lo = -npre + qL - 1;
+      int smn = 32767, smx = -32768;
+      int32_t oo = -1;
+      while (oo >= pure_lo) {
+         const int64_t to = (int64_t)row0 + oo;
+         if (gm && (to & (RT_GRAN - 1)) == RT_GRAN - 1 && oo - (RT_GRAN - 1) >= pure_lo) {
+            int64_t gfirst = (to - (RT_GRAN - 1) - qL + 1); gfirst = gfirst < 0 ? 0 : gfirst / RT_GRAN;
+            const int64_t glast = to / RT_GRAN;
+            int gmn = 32767, gmx = -32768, lmn = 0, lmx = 0;
+            for (int64_t g = gfirst; g <= glast; ++g) {
+               const uint32_t v = gm[g];
+               lmn = (int)(int16_t)(uint16_t)(v & 0xffffu); lmx = (int)(int16_t)(uint16_t)(v >> 16);
+               if (lmn < gmn) gmn = lmn; if (lmx > gmx) gmx = lmx; }
+            if (gmx - gmn < qthr) {                              /* no row of granule glast can be loud */
+               if (lmn < smn) smn = lmn; if (lmx > smx) smx = lmx;
+               oo -= RT_GRAN; continue; } }
+         const int64_t from = to - qL + 1;
+         const int x = (int)plane[to];
+         const minmax r = span_minmax(plane, from < 0 ? 0 : from, to, x);
+         if (r.mx - r.mn >= qthr) {
+            ll = oo; qmin = r.mn < smn ? r.mn : smn; qmax = r.mx > smx ? r.mx : smx;
+            return; }
+         if (x < smn) smn = x; if (x > smx) smx = x;
+         --oo; }
+      for (int32_t q = -npre; q < pure_lo && q < 0; ++q) feed(q, (int)plane[(int64_t)row0 + q]);
+      if (smn < qmin) qmin = smn; if (smx > qmax) qmax = smx; }
+
    /* process_*_transition, decoder.c:560-609 */
    RT_FHD void transition(bool top, uint32_t oo) {
       const double t_ev = top ? t.t_top : t.t_bot;
@@ -177,7 +215,7 @@ struct SparseScan {
    RT_FHD void begin(const int16_t *plane_, uint64_t row0_, uint64_t row_end, int trk_, Emit em_, int quiet_thr_lsb) {
       plane = plane_; row0 = row0_; end = (uint32_t)(row_end - row0_); trk = trk_; delay = c.skew[trk_]; em = em_;
       mc = c.m_cand + (size_t)trk_ * c.mask_stride; ma = c.m_acan + (size_t)trk_ * c.mask_stride;
-      gm = c.gmm ? c.gmm + (size_t)trk_ * c.ngran_cap : nullptr;
+      gm = c.gmm ? c.gmm + (size_t)trk_ * c.ngran_cap : nullptr; T0t = c.T0[trk_];
       const bool tz = row_time(c, row0) == 0.0;
       io = (uint32_t)trk + (tz ? 1u : 0u);
       o_pure = ((uint32_t)delay > io ? (uint32_t)delay : io) + (uint32_t)w;
@@ -188,13 +226,13 @@ struct SparseScan {
       t.agc_gain = 1.0f; t.avg_height = RT_PKWW_PEAKHEIGHT;
       t.t_clkwindow = c.clk_init / 2 * c.p.clk_factor;
       inv_lsb = 32767.0f / c.maxvolts;
-      thresholds(); resume = 0; m = 0; mq = 0; ndense = 0;
+      thresholds(); resume = 0; m = 0; mq = 0; ndense = 0; cb = 0; cb_o = NO_ROW32;
       qthr = quiet_thr_lsb; qL = w + delay; qmin = 32767; qmax = -32768; ll = last_canon = OFF_NONE;
       sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false; pre = true; pre_end = 0;
       const int lead = (int)io > delay ? (int)io : delay;
       sf_from = (uint32_t)(lead + w + 1);
       const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
-      for (int32_t oo = -npre; oo < 0; ++oo) feed(oo, (int)plane[(int64_t)row0 + oo]);
+      prescan(npre);
       quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
       for (uint32_t oo = 0; oo <= io && oo < end; ++oo) track(oo, false);              /* decoder.c:855-861: not looked at yet */
       o = io + 1; pre_pos = o;
@@ -232,7 +270,7 @@ struct SparseScan {
       ++o; if (pre) pre_pos = o;
       if (o >= end) { st = SP_DONE; return; }
       /* from a canonical row of the pure regime on, the state is what the masks describe */
-      if (canonical && cur >= o_pure && T >= c.T0 && c.T0 > 0) { st = SP_SPARSE; mq = cur; } }
+      if (canonical && cur >= o_pure && T >= T0t && T0t > 0) { st = SP_SPARSE; mq = cur; } }
 
    /* ---- sparse mode ---- */
    /* One pass over the w samples at win[0 .. w): packed keys carry value and position through a single min / max,
@@ -311,29 +349,39 @@ struct SparseScan {
       mq = oo; }
 
    RT_FHD void sparse_step() {
-      /* next candidate row at or after the end of the blind stretch */
-      uint32_t from = o > resume ? o : resume;
-      if (from >= end) { o = end; st = SP_DONE; return; }
-      uint64_t p = prow(from);
+      /* The cheap part -- next candidate row at or after the end of the blind stretch, its window, the integer pre-filter for the
+         CURRENT threshold bound T (the top test can only pass if S - max(l, r) >= T, the bottom test only if min(l, r) - m >= T, and
+         m >= Wmin) -- is repeated up to SPARSE_TRIES times, so that when the warp goes on to the expensive part most of its lanes
+         bring a row that has a real chance of being an event. */
+      uint64_t p = 0; uint32_t oc = 0; const int16_t *win = plane;
+      int S = 0, mn = 0, posm = 0, pos = 0, xl = 0, xr = 0; bool tcand = false, bcand = false;
       const uint64_t pend = prow(end);
-      uint32_t bits = bits_at(mc, p);
-      int nw = 1;
-      while (!bits && nw < SPARSE_SEARCH_WORDS && p + 32 < pend) { p += 32; bits = bits_at(mc, p); ++nw; }
-      if (!bits) { p += 32; o = p >= pend ? end : (uint32_t)(p - row0) + (uint32_t)delay; if (o >= end) st = SP_DONE; return; }
-      p += (uint32_t)ctz32(bits);
-      if (p >= pend) { o = end; st = SP_DONE; return; }
-      const uint32_t oc = (uint32_t)(p - row0) + (uint32_t)delay;
-      /* window maximum (leftmost position) and minimum, the edges; then the integer pre-filter for the CURRENT threshold bound T:
-         the top test can only pass if S - max(l, r) >= T, the bottom test only if min(l, r) - m >= T, and m >= Wmin */
-      const int16_t *win = plane + (p - (uint32_t)w + 1u);
-      const WinKeys wk = scan_window<true, false>(win, 0);
-      const int S = key_val(wk.kmax), mn = key_val(wk.kmin), posm = kmin_pos(wk.kmin);
-      int pos = kmax_pos(wk.kmax);
-      const int xl = win[0], xr = win[w - 1];
-      const bool tcand = S - (xl > xr ? xl : xr) >= T, bcand = (xl < xr ? xl : xr) - mn >= T;
-      o = oc + 1;
-      SP_STAT(cands, 1);
-      if (!tcand && !bcand) { if (o >= end) st = SP_DONE; return; }
+#pragma unroll 1
+      for (int tries = 0; tries < SPARSE_TRIES; ++tries) {
+         const uint32_t from = o > resume ? o : resume;
+         if (from >= end) { o = end; st = SP_DONE; return; }
+         p = prow(from);
+         /* the candidate bits of 32 rows stay in a register from step to step: successive candidates mostly share them */
+         uint32_t bits; uint32_t nv = 32;
+         if (cb_o != NO_ROW32 && from >= cb_o && from - cb_o < 32u) { bits = cb >> (from - cb_o); nv = 32u - (from - cb_o); }
+         else { bits = bits_at(mc, p); cb = bits; cb_o = from; }
+         int nw = 1;
+         while (!bits && nw < SPARSE_SEARCH_WORDS && p + nv < pend) {
+            p += nv; nv = 32; bits = bits_at(mc, p); cb = bits; cb_o = (uint32_t)(p - row0) + (uint32_t)delay; ++nw; }
+         if (!bits) { p += nv; o = p >= pend ? end : (uint32_t)(p - row0) + (uint32_t)delay; if (o >= end) st = SP_DONE; return; }
+         p += (uint32_t)ctz32(bits);
+         if (p >= pend) { o = end; st = SP_DONE; return; }
+         oc = (uint32_t)(p - row0) + (uint32_t)delay;
+         win = plane + (p - (uint32_t)w + 1u);
+         const WinKeys wk = scan_window<true, false>(win, 0);
+         S = key_val(wk.kmax); mn = key_val(wk.kmin); posm = kmin_pos(wk.kmin); pos = kmax_pos(wk.kmax);
+         xl = win[0]; xr = win[w - 1];
+         tcand = S - (xl > xr ? xl : xr) >= T; bcand = (xl < xr ? xl : xr) - mn >= T;
+         o = oc + 1;
+         SP_STAT(cands, 1);
+         if (tcand || bcand) break;
+         if (o >= end) { st = SP_DONE; return; } }
+      if (!tcand && !bcand) return;
       SP_STAT(evals, 1);
       const float vl = volts(c, xl), vr = volts(c, xr), maxv = volts(c, S);
       const bool top = tcand && maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
@@ -351,7 +399,7 @@ struct SparseScan {
          const bool found = pos >= 0;
          const int xprev = found && pos > 0 ? win[pos - 1] : 0, xnext = found && pos < w - 1 ? win[pos + 1] : 0;
          fire(top, top ? maxv : minv, pos + 1, found, xprev, xnext, oc);
-         if (T < c.T0) { lazy_min(oc); st = SP_DENSE; } }           /* the masks no longer cover the threshold: walk rows */
+         if (T < T0t) { lazy_min(oc); st = SP_DENSE; } }           /* the masks no longer cover the threshold: walk rows */
       if (o >= end) st = SP_DONE; }
 
    RT_FHD void step() { if (st == SP_DENSE) dense_step(); else if (st == SP_SPARSE) sparse_step(); }

@@ -149,7 +149,8 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
             cc.gmm[(size_t)k * cc.ngran + g] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); }
       it = cache.emplace(key, std::move(cc)).first; }
    Cache &cc = it->second;
-   dc.m_cand = cc.cand.data(); dc.m_acan = cc.acan.data(); dc.mask_stride = cc.mask_stride; dc.T0 = T0;
+   dc.m_cand = cc.cand.data(); dc.m_acan = cc.acan.data(); dc.mask_stride = cc.mask_stride;
+   for (int k = 0; k < RT_MAXTRKS; ++k) dc.T0[k] = T0;
    if (use_gmm) { dc.gmm = cc.gmm.data(); dc.ngran_cap = cc.ngran; }
    uint32_t heights[RT_AGC_MAX_WINDOW];
    HostSparseJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0, false};
