@@ -354,7 +354,7 @@ struct SparseScan {
          m >= Wmin) -- is repeated up to SPARSE_TRIES times, so that when the warp goes on to the expensive part most of its lanes
          bring a row that has a real chance of being an event. */
       uint64_t p = 0; uint32_t oc = 0; const int16_t *win = plane;
-      int S = 0, mn = 0, posm = 0, pos = 0, xl = 0, xr = 0; bool tcand = false, bcand = false;
+      int S = 0, mn = 0, posm = 0, pos = 0, xl = 0, xr = 0; bool tcand = false, bcand = false; uint32_t abits = 0;
       const uint64_t pend = prow(end);
 #pragma unroll 1
       for (int tries = 0; tries < SPARSE_TRIES; ++tries) {
@@ -373,6 +373,7 @@ struct SparseScan {
          if (p >= pend) { o = end; st = SP_DONE; return; }
          oc = (uint32_t)(p - row0) + (uint32_t)delay;
          win = plane + (p - (uint32_t)w + 1u);
+         if (w <= 32) abits = bits_at(ma, p - (uint32_t)w + 1u);      /* acan bits of the window's rows: requested together with the samples */
          const WinKeys wk = scan_window<true, false>(win, 0);
          S = key_val(wk.kmax); mn = key_val(wk.kmin); posm = kmin_pos(wk.kmin); pos = kmax_pos(wk.kmax);
          xl = win[0]; xr = win[w - 1];
@@ -389,7 +390,9 @@ struct SparseScan {
       if (!top && bcand) {
          /* a refresh at or after the row at which the window's (leftmost) minimum entered makes m that minimum */
          SP_STAT(bcalls, 1);
-         if (acan_in(p - (uint32_t)w + 1u + (uint32_t)posm, p)) { m = mn; mq = oc; SP_STAT(shortcut, 1); }
+         const bool fresh = w <= 32 ? ((abits >> posm) & (w >= 32 ? 0xffffffffu : ((1u << (w - posm)) - 1u))) != 0
+                                    : acan_in(p - (uint32_t)w + 1u + (uint32_t)posm, p);
+         if (fresh) { m = mn; mq = oc; SP_STAT(shortcut, 1); }
          else lazy_min(oc);
          minv = volts(c, m);
          bot = minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
