@@ -22,28 +22,29 @@ struct TrackT0 { int32_t v[RT_MAXTRKS]; };                      /* per-track mas
 template <int W>
 __global__ void __launch_bounds__(MASK_THREADS)
 k_peak_masks(const int16_t *planes, uint64_t plane_stride, uint64_t run_lo, uint64_t nruns, const __grid_constant__ TrackT0 t0s,
-             uint32_t *cand, uint32_t *acan, uint64_t mask_stride) {
+             const __grid_constant__ TrackT0 t1s, uint32_t *cand, uint32_t *cand2, uint32_t *acan, uint64_t mask_stride) {
    const uint64_t r = (uint64_t)blockIdx.x * MASK_THREADS + threadIdx.x;
    if (r >= nruns) return;
    const int trk = blockIdx.y;
-   const uint32_t T0 = (uint32_t)t0s.v[trk];
+   const uint32_t T0 = (uint32_t)t0s.v[trk], T1 = (uint32_t)t1s.v[trk];
    const int16_t *plane = planes + (size_t)trk * plane_stride;
    const int64_t p0 = (int64_t)(run_lo + r) * rtmask::MASK_RUN;
-   uint32_t cw[2], aw[2];
-   if (p0 >= rtmask::RunMasks<W>::HALO) rtmask::RunMasks<W>::run(plane, p0, T0, cw, aw);
+   uint32_t cw[2], dw[2], aw[2];
+   if (p0 >= rtmask::RunMasks<W>::HALO) rtmask::RunMasks<W>::run(plane, p0, T0, T1, cw, dw, aw);
    else {
-      rtmask::word_masks_scalar(plane, p0 / 32, W, (int)T0, &cw[0], &aw[0]);
-      rtmask::word_masks_scalar(plane, p0 / 32 + 1, W, (int)T0, &cw[1], &aw[1]); }
+      rtmask::word_masks_scalar(plane, p0 / 32, W, (int)T0, (int)T1, &cw[0], &dw[0], &aw[0]);
+      rtmask::word_masks_scalar(plane, p0 / 32 + 1, W, (int)T0, (int)T1, &cw[1], &dw[1], &aw[1]); }
    const size_t wi = (size_t)trk * mask_stride + (size_t)(p0 / 32);
    *reinterpret_cast<uint2 *>(cand + wi) = make_uint2(cw[0], cw[1]);
+   *reinterpret_cast<uint2 *>(cand2 + wi) = make_uint2(dw[0], dw[1]);
    *reinterpret_cast<uint2 *>(acan + wi) = make_uint2(aw[0], aw[1]); }
 
 template <int W>
-static cudaError_t launch_masks_w(const DevCfg &c, uint64_t run_lo, uint64_t nruns, uint32_t *cand, uint32_t *acan, cudaStream_t s) {
+static cudaError_t launch_masks_w(const DevCfg &c, uint64_t run_lo, uint64_t nruns, uint32_t *cand, uint32_t *cand2, uint32_t *acan, cudaStream_t s) {
    dim3 grid((unsigned)((nruns + MASK_THREADS - 1) / MASK_THREADS), (unsigned)c.ntrks);
-   TrackT0 t0s;
-   for (int k = 0; k < RT_MAXTRKS; ++k) t0s.v[k] = c.T0[k] > 0 ? c.T0[k] : 65535;
-   k_peak_masks<W><<<grid, MASK_THREADS, 0, s>>>(c.planes, c.plane_stride, run_lo, nruns, t0s, cand, acan, c.mask_stride);
+   TrackT0 t0s, t1s;
+   for (int k = 0; k < RT_MAXTRKS; ++k) { t0s.v[k] = c.T0[k] > 0 ? c.T0[k] : 65535; t1s.v[k] = c.T1[k] > 0 ? c.T1[k] : 65535; }
+   k_peak_masks<W><<<grid, MASK_THREADS, 0, s>>>(c.planes, c.plane_stride, run_lo, nruns, t0s, t1s, cand, cand2, acan, c.mask_stride);
    return cudaGetLastError(); }
 
 /* phase A over plane rows [row_lo, row_hi) (rounded outwards to whole runs; row_hi <= plane_stride) */
@@ -51,9 +52,9 @@ cudaError_t launch_peak_masks(const DevCfg &c, uint64_t row_lo, uint64_t row_hi,
    if (row_hi <= row_lo) return cudaSuccess;
    const uint64_t run_lo = row_lo / rtmask::MASK_RUN, run_hi = (row_hi + rtmask::MASK_RUN - 1) / rtmask::MASK_RUN;
    const uint64_t nruns = run_hi - run_lo;
-   uint32_t *cand = const_cast<uint32_t *>(c.m_cand), *acan = const_cast<uint32_t *>(c.m_acan);
+   uint32_t *cand = const_cast<uint32_t *>(c.m_cand), *cand2 = const_cast<uint32_t *>(c.m_cand2), *acan = const_cast<uint32_t *>(c.m_acan);
    switch (c.width) {
-#define MW(W) case W: return launch_masks_w<W>(c, run_lo, nruns, cand, acan, s);
+#define MW(W) case W: return launch_masks_w<W>(c, run_lo, nruns, cand, cand2, acan, s);
       MW(3) MW(4) MW(5) MW(6) MW(7) MW(8) MW(9) MW(10) MW(11) MW(12) MW(13) MW(14) MW(15) MW(16) MW(17) MW(18) MW(19) MW(20)
       MW(21) MW(22) MW(23) MW(24) MW(25) MW(26) MW(27) MW(28) MW(29) MW(30) MW(31) MW(32) MW(33) MW(34) MW(35) MW(36) MW(37) MW(38)
       MW(39) MW(40) MW(41) MW(42) MW(43) MW(44) MW(45) MW(46) MW(47) MW(48) MW(49) MW(50)
@@ -120,7 +121,7 @@ k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
 bool sparse_scan_eligible(const DevCfg &c) {
    for (int k = 0; k < c.ntrks; ++k) if (c.T0[k] <= 0) return false;
    return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
-          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.m_cand && c.m_acan; }
+          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.m_cand && c.m_cand2 && c.m_acan; }
 
 /* ---- choosing T0 from the data ----------------------------------------------------------------------------------------------
  * required_rise (decoder.c:785) follows the signal: pkww_rise * (average peak-to-peak height / 4 V) / AGC gain.  A mask threshold
@@ -166,7 +167,7 @@ bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist) {
       const uint32_t *h = hist + (size_t)k * HIST_BINS;
       unsigned long long total = 0, acc = 0;
       for (int b = 0; b < HIST_BINS; ++b) total += h[b];
-      int T0 = (int)(0.75f * (float)Tdef);
+      int T0 = (int)(0.75f * (float)Tdef), T1 = 0;
       if (total >= 64) {
          int bA = 0;                                            /* full-scale height: 99.8th percentile of all stretches */
          for (; bA < HIST_BINS; ++bA) { acc += h[bA]; if (acc * 1000 >= total * 998) break; }
@@ -178,9 +179,12 @@ bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist) {
             for (; b < HIST_BINS; ++b) { acc += h[b]; if (acc * 10 >= sig) break; }
             const float alow = (float)(b << 6);
             const int Test = (int)(0.5f * (c.p.pkww_rise * alow / RT_PKWW_PEAKHEIGHT * 0.999f - 2.0f));
-            if (Test < T0) T0 = Test; } }
+            if (Test < T0) T0 = Test;
+            for (; b < HIST_BINS; ++b) { if (acc * 2 >= sig) break; acc += h[b + 1 < HIST_BINS ? b + 1 : b]; }   /* median signal height */
+            T1 = (int)(0.8f * (c.p.pkww_rise * (float)(b << 6) / RT_PKWW_PEAKHEIGHT * 0.999f - 2.0f)); } }
       const int floor_ = Tdef / 20 > 16 ? Tdef / 20 : 16;
-      c.T0[k] = T0 < floor_ ? floor_ : (T0 > 65535 ? 65535 : T0); }
+      c.T0[k] = T0 < floor_ ? floor_ : (T0 > 65535 ? 65535 : T0);
+      c.T1[k] = T1 > c.T0[k] + c.T0[k] / 8 ? (T1 > 65535 ? 65535 : T1) : 0; }
    return true; }
 /* phase B only: the masks of rows [0, max row_end) must have been built (launch_peak_masks) on the same stream */
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
@@ -191,8 +195,9 @@ cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t
    if (!occ) {
       const char *env = getenv("RT_SPARSE_OCC");
       occ = env ? atoi(env) : 4;
-      if (occ != 6 && occ != 8) occ = 4;
+      if (occ != 5 && occ != 6 && occ != 8) occ = 4;
       e = occ == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<4>, SPARSE_THREADS, 0)
+        : occ == 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<5>, SPARSE_THREADS, 0)
         : occ == 6 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<6>, SPARSE_THREADS, 0)
                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<8>, SPARSE_THREADS, 0);
       if (e != cudaSuccess) { occ = 0; return e; }
@@ -206,6 +211,7 @@ cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t
    e = cudaMemsetAsync(counters + 2, 0, sizeof(unsigned long long), s);
    if (e != cudaSuccess) return e;
    if (occ == 4) k_units_sparse<4><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   else if (occ == 5) k_units_sparse<5><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
    else if (occ == 6) k_units_sparse<6><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
    else k_units_sparse<8><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
    return cudaGetLastError(); }

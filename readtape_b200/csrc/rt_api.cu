@@ -455,13 +455,13 @@ static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
       kernel K3b (tests).  The mask threshold T0 is chosen per track from the data (plan_auto_t0) unless RT_SPARSE_T0 fixes it as a
       fraction of the default-state bound (tests). */
    const char *t0env = getenv("RT_SPARSE_T0");
-   for (int k = 0; k < RT_MAXTRKS; ++k) pl->dc.T0[k] = 0;
-   pl->dc.m_cand = pl->dc.m_acan = nullptr; pl->dc.mask_stride = 0;
+   for (int k = 0; k < RT_MAXTRKS; ++k) pl->dc.T0[k] = pl->dc.T1[k] = 0;
+   pl->dc.m_cand = pl->dc.m_cand2 = pl->dc.m_acan = nullptr; pl->dc.mask_stride = 0;
    pl->use_sparse = pl->t0_auto = false;
    if (pl->use_fast && dc.det == RT_DET_PEAK && !(force && strcmp(force, "fast") == 0)) {
       if (t0env) {
          const int T0 = peak_mask_T0(dc, (float)atof(t0env));
-         for (int k = 0; k < dc.ntrks; ++k) pl->dc.T0[k] = T0;
+         for (int k = 0; k < dc.ntrks; ++k) { pl->dc.T0[k] = T0; pl->dc.T1[k] = T0 > 0 && T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 0; }
          pl->use_sparse = T0 > 0; }
       else { pl->use_sparse = peak_mask_T0(dc, 1.0f) > 0; pl->t0_auto = pl->use_sparse; } }
    if (dc.det == RT_DET_PEAK) {
@@ -499,7 +499,7 @@ static cudaError_t plan_auto_t0(const rt_tape *t, ScanPlan *pl, uint64_t rows_av
       e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e;
       have_hist = true; }
    if (!peak_mask_auto_T0(pl->dc, h_hist.data())) pl->use_sparse = false;
-   if (getenv("RT_TRACE")) { fprintf(stderr, "[two-pass scan] T0 per track:"); for (int k = 0; k < nt; ++k) fprintf(stderr, " %d", pl->dc.T0[k]); fprintf(stderr, "\n"); }
+   if (getenv("RT_TRACE")) { fprintf(stderr, "[two-pass scan] T0/T1 per track:"); for (int k = 0; k < nt; ++k) fprintf(stderr, " %d/%d", pl->dc.T0[k], pl->dc.T1[k]); fprintf(stderr, "\n"); }
    return cudaSuccess; }
 
 extern "C" void rt_bulk_free(rt_bulk *b) {
@@ -540,13 +540,13 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    std::vector<cudaEvent_t> done_ev(ncfgs, nullptr);
    /* K3c: candidate / canonical bit planes, one set per distinct (window width, T0) -- parameter sets that only differ in
       clock / AGC constants share them */
-   struct MaskSet { int width; int32_t T0[RT_MAXTRKS]; uint32_t *mc, *ma; uint32_t first_cfg; };
+   struct MaskSet { int width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; uint32_t *mc, *md, *ma; uint32_t first_cfg; };
    uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have_hist = false;
    std::vector<MaskSet> msets;
    auto cleanup = [&]() {
       void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_hist};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
-      for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream); }
+      for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.md) cudaFreeAsync(m.md, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream); }
       for (auto &e : ev) cudaEventDestroy(e);
       for (auto e : done_ev) if (e) cudaEventDestroy(e); };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); rt_bulk_free(b); \
@@ -591,13 +591,15 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
             CUB(plan_auto_t0(t, &pl, nrows, d_hist, h_hist, have_hist, t->stream));
             if (!pl.use_sparse) continue; }
          size_t k = 0;
-         while (k < msets.size() && !(msets[k].width == pl.dc.width && memcmp(msets[k].T0, pl.dc.T0, sizeof pl.dc.T0) == 0)) ++k;
+         while (k < msets.size() && !(msets[k].width == pl.dc.width && memcmp(msets[k].T0, pl.dc.T0, sizeof pl.dc.T0) == 0
+                                      && memcmp(msets[k].T1, pl.dc.T1, sizeof pl.dc.T1) == 0)) ++k;
          if (k == msets.size()) {
-            MaskSet m{}; m.width = pl.dc.width; memcpy(m.T0, pl.dc.T0, sizeof m.T0); m.first_cfg = ci;
+            MaskSet m{}; m.width = pl.dc.width; memcpy(m.T0, pl.dc.T0, sizeof m.T0); memcpy(m.T1, pl.dc.T1, sizeof m.T1); m.first_cfg = ci;
             msets.push_back(m);
             CUB(cudaMallocAsync(&msets[k].mc, (size_t)mstride * nt * 4, t->stream));
+            CUB(cudaMallocAsync(&msets[k].md, (size_t)mstride * nt * 4, t->stream));
             CUB(cudaMallocAsync(&msets[k].ma, (size_t)mstride * nt * 4, t->stream)); }
-         pl.dc.m_cand = msets[k].mc; pl.dc.m_acan = msets[k].ma; pl.dc.mask_stride = mstride; } }
+         pl.dc.m_cand = msets[k].mc; pl.dc.m_cand2 = msets[k].md; pl.dc.m_acan = msets[k].ma; pl.dc.mask_stride = mstride; } }
    lap("mask thresholds");
 
    /* 2. all scan kernels, concurrently, into one event pool: first guess one event per 16 track-samples, regrown on overflow */
@@ -729,7 +731,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    const uint32_t units_cap_tmp = (uint32_t)std::min<uint64_t>(nrows / RT_GRAN + 2, 0x7fffffffu);
    uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr; TrkMeta *d_meta = nullptr;
-   uint32_t *d_mc = nullptr, *d_ma = nullptr; uint64_t masks_done = 0; double ms_masks = 0;   /* K3c bit planes, built segment by segment */
+   uint32_t *d_mc = nullptr, *d_md = nullptr, *d_ma = nullptr; uint64_t masks_done = 0; double ms_masks = 0;   /* K3c bit planes, built segment by segment */
    uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have_hist = false;
    std::vector<cudaEvent_t> seg_ev; std::vector<uint64_t> seg_rows_done;
    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -740,7 +742,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    bc.cfg = *cfg; bc.dc = pl.dc; bc.fast = pl.use_fast;
    bool failed = false; const char *why = "";
    auto release = [&]() {
-      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta, d_mc, d_ma, d_hist};
+      void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_meta, d_mc, d_md, d_ma, d_hist};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->s_scan);
       for (auto e : seg_ev) cudaEventDestroy(e);
       if (ev_a) cudaEventDestroy(ev_a); if (ev_b) cudaEventDestroy(ev_b); };
@@ -753,9 +755,10 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    CUS(cudaMallocAsync(&d_meta, (size_t)cap_units * nt * sizeof(TrkMeta), t->s_scan));
    if (pl.use_sparse) {
       const uint64_t mstride = peak_mask_stride(t->plane_stride);
-      CUS(cudaMallocAsync(&d_mc, (size_t)mstride * nt * 4, t->s_scan)); CUS(cudaMallocAsync(&d_ma, (size_t)mstride * nt * 4, t->s_scan));
+      CUS(cudaMallocAsync(&d_mc, (size_t)mstride * nt * 4, t->s_scan)); CUS(cudaMallocAsync(&d_md, (size_t)mstride * nt * 4, t->s_scan));
+      CUS(cudaMallocAsync(&d_ma, (size_t)mstride * nt * 4, t->s_scan));
       if (pl.t0_auto) CUS(cudaMallocAsync(&d_hist, (size_t)span_hist_words((int)nt) * 4, t->s_scan));
-      pl.dc.m_cand = d_mc; pl.dc.m_acan = d_ma; pl.dc.mask_stride = mstride; }
+      pl.dc.m_cand = d_mc; pl.dc.m_cand2 = d_md; pl.dc.m_acan = d_ma; pl.dc.mask_stride = mstride; }
    cudaEvent_t ev_m = nullptr; EvGuard ev_m_guard{&ev_m};
    CUS(cudaMemsetAsync(d_cursor, 0, 4, t->s_scan)); CUS(cudaMemsetAsync(d_counters, 0, 32, t->s_scan));
    CUS(cudaEventCreate(&ev_a)); CUS(cudaEventCreate(&ev_b));
@@ -866,11 +869,12 @@ extern "C" int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, 
    for (int k = 0; k < RT_MAXTRKS; ++k) dc.T0[k] = T0;
    if (t0) *t0 = T0;
    const uint64_t ms = peak_mask_stride(t->plane_stride); const uint32_t nt = t->desc.ntrks;
-   uint32_t *d_mc = nullptr, *d_ma = nullptr;
+   uint32_t *d_mc = nullptr, *d_md = nullptr, *d_ma = nullptr;
    CU(cudaMalloc(&d_mc, (size_t)ms * nt * 4));
    cudaError_t e = cudaMalloc(&d_ma, (size_t)ms * nt * 4);
+   if (e == cudaSuccess) e = cudaMalloc(&d_md, (size_t)ms * nt * 4);
    if (e == cudaSuccess) {
-      dc.m_cand = d_mc; dc.m_acan = d_ma; dc.mask_stride = ms;
+      dc.m_cand = d_mc; dc.m_cand2 = d_md; dc.m_acan = d_ma; dc.mask_stride = ms;
       e = launch_peak_masks(dc, 0, nrows, t->stream); ++t->launches;
       const uint64_t nw = (nrows + 31) / 32;
       for (uint32_t k = 0; k < nt && e == cudaSuccess; ++k) {
@@ -881,7 +885,7 @@ extern "C" int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, 
       if (e == cudaSuccess && (nrows & 31)) {                    /* rows past the end of the data: not defined, cleared */
          const uint32_t keep = (1u << (nrows & 31)) - 1u;
          for (uint32_t k = 0; k < nt; ++k) { cand[(size_t)k * wpt + nw - 1] &= keep; acan[(size_t)k * wpt + nw - 1] &= keep; } } }
-   cudaFree(d_mc); cudaFree(d_ma);
+   cudaFree(d_mc); cudaFree(d_md); cudaFree(d_ma);
    if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "rt_peak_masks: %s", cudaGetErrorString(e));
    return RT_OK; }
 

@@ -63,6 +63,10 @@ struct DevCfg {
    const uint32_t *m_cand, *m_acan;
    uint64_t mask_stride;
    int32_t  T0[RT_MAXTRKS];
+   /* a second candidate plane for a higher threshold T1[k] >= T0[k] (0: none): once the AGC has settled, required_rise is usually
+      well above its default-state value, and the sparse scan then follows the plane with fewer candidates */
+   const uint32_t *m_cand2;
+   int32_t  T1[RT_MAXTRKS];
 };
 
 /* Per-track detector + feedback state: the device mirror of the parts of struct trkstate_t

@@ -74,7 +74,7 @@ RT_FHD uint32_t shifted(const uint32_t (&a)[N], int i) {
 template <int W> struct Pow2 { static constexpr int value = W >= 32 ? 32 : W >= 16 ? 16 : W >= 8 ? 8 : W >= 4 ? 4 : W >= 2 ? 2 : 1; };
 
 /* One run: rows [p0, p0 + MASK_RUN) of `plane`, p0 a multiple of 32 and p0 >= HALO (the caller uses the scalar path
-   below near the start of a plane).  1 <= T0 <= 65535.  Results: two mask words each. */
+   below near the start of a plane).  1 <= T0 <= T1 <= 65535 (T1 = 65535: second plane practically empty).  Results: two mask words each. */
 template <int W>
 struct RunMasks {
    static constexpr int HALO = (W + 7) / 8 * 8;               /* rows read in front of the run (needs raw[p - W]) */
@@ -111,7 +111,7 @@ struct RunMasks {
       const uint32_t n1 = (g_hi & 0x5555u) | ((g_hi >> 15) & 0xaaaau);
       return n0 | (n1 << 16); }
 
-   static RT_FHD void run(const int16_t *plane, int64_t p0, uint32_t T0, uint32_t (&cand)[2], uint32_t (&acan)[2]) {
+   static RT_FHD void run(const int16_t *plane, int64_t p0, uint32_t T0, uint32_t T1, uint32_t (&cand)[2], uint32_t (&cand2)[2], uint32_t (&acan)[2]) {
       uint32_t x[NW], P[NW], Dt[MASK_RUN / 2];
       const int16_t *src = plane + (p0 - HALO);                /* 16-byte aligned: p0 % 32 == 0, HALO % 8 == 0, planes 16-byte aligned */
 #pragma unroll
@@ -124,8 +124,8 @@ struct RunMasks {
          for (int k = 0; k < 4; ++k) x[4 * cch + k] ^= BIAS2;
 #endif
       }
-      const uint32_t one2 = 0x00010001u, t0m1 = (T0 - 1u) | ((T0 - 1u) << 16);
-      uint32_t gc[4] = {0, 0, 0, 0}, gn[4] = {0, 0, 0, 0};
+      const uint32_t one2 = 0x00010001u, t0m1 = (T0 - 1u) | ((T0 - 1u) << 16), t1m1 = (T1 - 1u) | ((T1 - 1u) << 16);
+      uint32_t gc[4] = {0, 0, 0, 0}, gd[4] = {0, 0, 0, 0}, gn[4] = {0, 0, 0, 0};
       /* pass 1: window maximum -> top-side margin S - max(l, r), and "the leaving sample is below the maximum" (not acan) */
 #pragma unroll
       for (int i = 0; i < NW; ++i) P[i] = x[i];
@@ -149,15 +149,18 @@ struct RunMasks {
          const uint32_t l = shifted<W - 1>(x, i), r = x[i];
          const uint32_t Dm = v_maxu2(Dt[j], v_minu2(l, r) - Wm);
          const uint32_t hit = v_minu2(v_maxu2(Dm, t0m1) - t0m1, one2);        /* 1 where the margin >= T0 */
-         gc[j >> 3] += hit << (2 * (j & 7)); }
+         const uint32_t hit2 = v_minu2(v_maxu2(Dm, t1m1) - t1m1, one2);       /* 1 where the margin >= T1 */
+         gc[j >> 3] += hit << (2 * (j & 7));
+         gd[j >> 3] += hit2 << (2 * (j & 7)); }
       cand[0] = fold(gc[0], gc[1]); cand[1] = fold(gc[2], gc[3]);
+      cand2[0] = fold(gd[0], gd[1]); cand2[1] = fold(gd[2], gd[3]);
       acan[0] = ~fold(gn[0], gn[1]); acan[1] = ~fold(gn[2], gn[3]); } };
 
 /* The same bits by definition, one row at a time: rows [p_from, p_to) (any alignment inside one mask word range is the
    caller's business: this returns the bits of ONE 32-row word `wi`).  Rows whose window would reach before row 0 get
    cand = acan = 0 (the sparse scan never looks at them).  Used near the start of a plane and by the tests. */
-__host__ __device__ inline void word_masks_scalar(const int16_t *plane, int64_t wi, int w, int T0, uint32_t *cand, uint32_t *acan) {
-   uint32_t cb = 0, ab = 0;
+__host__ __device__ inline void word_masks_scalar(const int16_t *plane, int64_t wi, int w, int T0, int T1, uint32_t *cand, uint32_t *cand2, uint32_t *acan) {
+   uint32_t cb = 0, db = 0, ab = 0;
    for (int b = 0; b < 32; ++b) {
       const int64_t p = wi * 32 + b;
       if (p < w) continue;
@@ -166,7 +169,8 @@ __host__ __device__ inline void word_masks_scalar(const int16_t *plane, int64_t 
       const int l = plane[p - w + 1], r = plane[p], lv = plane[p - w];
       const int mxlr = l > r ? l : r, mnlr = l < r ? l : r;
       if (S - mxlr >= T0 || mnlr - mn >= T0) cb |= 1u << b;
+      if (S - mxlr >= T1 || mnlr - mn >= T1) db |= 1u << b;
       if (lv >= S) ab |= 1u << b; }
-   *cand = cb; *acan = ab; }
+   *cand = cb; *cand2 = db; *acan = ab; }
 
 }  // namespace rtmask

@@ -76,12 +76,12 @@ RT_FHD int clz32(uint32_t v) {
 
 template <int STRIDE, class Emit>
 struct SparseScan {
-   const DevCfg &c; const int16_t *plane; const uint32_t *mc, *ma; const uint32_t *gm;
+   const DevCfg &c; const int16_t *plane; const uint32_t *mc, *mc_lo, *mc_hi, *ma; const uint32_t *gm;
    uint64_t row0; uint32_t end; int trk, w, delay; uint32_t io, o_pure;
    Emit em; FastState<STRIDE> t; uint32_t *ht;
    /* detector state: o = next row; tests are off for rows < resume (blind countdown, decoder.c:778); m = the lazy minimum,
       exact for row mq (dense mode: for row o - 1) */
-   uint32_t o, resume, mq; int m, T, T0t, st; float inv_lsb, rise, reqmin;
+   uint32_t o, resume, mq; int m, T, T0t, T1t, st; float inv_lsb, rise, reqmin;
    uint32_t ndense;                                             /* rows walked in dense mode (diagnostics) */
    uint32_t cb, cb_o;                                           /* the 32 candidate bits of rows [cb_o, cb_o + 32) (cb_o = NO_ROW32: none held) */
    /* proof data (offsets relative to row0; OFF_NONE = none), as in UnitScan */
@@ -100,7 +100,10 @@ struct SparseScan {
       rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
       reqmin = c.p.min_peak * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
       float q = rise * inv_lsb * 0.999f - 2.0f;
-      T = !(q > 0) ? 0 : (q > 70000.0f ? 70000 : (int)q); }
+      T = !(q > 0) ? 0 : (q > 70000.0f ? 70000 : (int)q);
+      /* follow the candidate plane with the highest threshold that T still covers */
+      const uint32_t *want = T1t > 0 && T >= T1t ? mc_hi : mc_lo;
+      if (want != mc) { mc = want; cb_o = NO_ROW32; } }
 
    /* ---- proof data: identical bookkeeping to UnitScan (scan_fast.cuh) ---- */
    RT_FHD void commit() {
@@ -214,7 +217,8 @@ struct SparseScan {
    /* start the scan of unit rows [row0_, row_end) of track trk_ from a fresh RT_RESET_FULL */
    RT_FHD void begin(const int16_t *plane_, uint64_t row0_, uint64_t row_end, int trk_, Emit em_, int quiet_thr_lsb) {
       plane = plane_; row0 = row0_; end = (uint32_t)(row_end - row0_); trk = trk_; delay = c.skew[trk_]; em = em_;
-      mc = c.m_cand + (size_t)trk_ * c.mask_stride; ma = c.m_acan + (size_t)trk_ * c.mask_stride;
+      mc_lo = c.m_cand + (size_t)trk_ * c.mask_stride; mc_hi = c.m_cand2 + (size_t)trk_ * c.mask_stride; mc = mc_lo;
+      ma = c.m_acan + (size_t)trk_ * c.mask_stride; T1t = c.T1[trk_]; cb = 0; cb_o = NO_ROW32;
       gm = c.gmm ? c.gmm + (size_t)trk_ * c.ngran_cap : nullptr; T0t = c.T0[trk_];
       const bool tz = row_time(c, row0) == 0.0;
       io = (uint32_t)trk + (tz ? 1u : 0u);

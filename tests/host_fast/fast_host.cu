@@ -75,24 +75,24 @@ extern "C" int fast_host_scan_unit(const int16_t *planes, uint64_t plane_stride,
 
 /* ---- K3c: phase A masks + sparse scan (scan_masks.cuh / scan_sparse.cuh), host build ---------------------------------- */
 template <int W>
-static void host_masks_w(const int16_t *plane, uint64_t nruns, uint32_t T0, uint32_t *cand, uint32_t *acan) {
+static void host_masks_w(const int16_t *plane, uint64_t nruns, uint32_t T0, uint32_t T1, uint32_t *cand, uint32_t *cand2, uint32_t *acan) {
    for (uint64_t r = 0; r < nruns; ++r) {
       const int64_t p0 = (int64_t)r * rtmask::MASK_RUN;
-      uint32_t cw[2], aw[2];
-      if (p0 >= rtmask::RunMasks<W>::HALO) rtmask::RunMasks<W>::run(plane, p0, T0, cw, aw);
-      else { rtmask::word_masks_scalar(plane, p0 / 32, W, (int)T0, &cw[0], &aw[0]); rtmask::word_masks_scalar(plane, p0 / 32 + 1, W, (int)T0, &cw[1], &aw[1]); }
-      cand[2 * r] = cw[0]; cand[2 * r + 1] = cw[1]; acan[2 * r] = aw[0]; acan[2 * r + 1] = aw[1]; } }
+      uint32_t cw[2], dw[2], aw[2];
+      if (p0 >= rtmask::RunMasks<W>::HALO) rtmask::RunMasks<W>::run(plane, p0, T0, T1, cw, dw, aw);
+      else { rtmask::word_masks_scalar(plane, p0 / 32, W, (int)T0, (int)T1, &cw[0], &dw[0], &aw[0]); rtmask::word_masks_scalar(plane, p0 / 32 + 1, W, (int)T0, (int)T1, &cw[1], &dw[1], &aw[1]); }
+      cand[2 * r] = cw[0]; cand[2 * r + 1] = cw[1]; cand2[2 * r] = dw[0]; cand2[2 * r + 1] = dw[1]; acan[2 * r] = aw[0]; acan[2 * r + 1] = aw[1]; } }
 
 /* masks of rows [0, nruns*64) of every track (plane_stride >= nruns*64); simd=0: the brute-force definition instead */
-extern "C" int masks_host_build(const int16_t *planes, uint64_t plane_stride, int ntrks, uint64_t nruns, int w, int T0,
-                                uint32_t *cand, uint32_t *acan, uint64_t mask_stride, int simd) {
-   if (w < 3 || w > RT_PKWW_MAX_WIDTH || T0 < 1 || T0 > 65535) return RT_ERR_ARG;
+extern "C" int masks_host_build(const int16_t *planes, uint64_t plane_stride, int ntrks, uint64_t nruns, int w, int T0, int T1,
+                                uint32_t *cand, uint32_t *cand2, uint32_t *acan, uint64_t mask_stride, int simd) {
+   if (w < 3 || w > RT_PKWW_MAX_WIDTH || T0 < 1 || T0 > 65535 || T1 < T0 || T1 > 65535) return RT_ERR_ARG;
    for (int k = 0; k < ntrks; ++k) {
       const int16_t *plane = planes + (size_t)k * plane_stride;
-      uint32_t *c = cand + (size_t)k * mask_stride, *a = acan + (size_t)k * mask_stride;
-      if (!simd) { for (uint64_t wi = 0; wi < 2 * nruns; ++wi) rtmask::word_masks_scalar(plane, (int64_t)wi, w, T0, &c[wi], &a[wi]); continue; }
+      uint32_t *c = cand + (size_t)k * mask_stride, *d = cand2 + (size_t)k * mask_stride, *a = acan + (size_t)k * mask_stride;
+      if (!simd) { for (uint64_t wi = 0; wi < 2 * nruns; ++wi) rtmask::word_masks_scalar(plane, (int64_t)wi, w, T0, T1, &c[wi], &d[wi], &a[wi]); continue; }
       switch (w) {
-#define MW(W) case W: host_masks_w<W>(plane, nruns, (uint32_t)T0, c, a); break;
+#define MW(W) case W: host_masks_w<W>(plane, nruns, (uint32_t)T0, (uint32_t)T1, c, d, a); break;
          MW(3) MW(4) MW(5) MW(6) MW(7) MW(8) MW(9) MW(10) MW(11) MW(12) MW(13) MW(14) MW(15) MW(16) MW(17) MW(18) MW(19) MW(20)
          MW(21) MW(22) MW(23) MW(24) MW(25) MW(26) MW(27) MW(28) MW(29) MW(30) MW(31) MW(32) MW(33) MW(34) MW(35) MW(36) MW(37) MW(38)
          MW(39) MW(40) MW(41) MW(42) MW(43) MW(44) MW(45) MW(46) MW(47) MW(48) MW(49) MW(50)
@@ -128,7 +128,8 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
    int T0 = q > 0 ? (int)((q > 70000.0f ? 70000.0f : (float)(int)q) * t0_frac) : 0;
    if (T0 > 65535) T0 = 65535;
    if (T0 < 1) return RT_ERR_UNSUPPORTED;
-   struct Cache { std::vector<uint32_t> cand, acan, gmm; uint64_t mask_stride, ngran; };
+   struct Cache { std::vector<uint32_t> cand, cand2, acan, gmm; uint64_t mask_stride, ngran; };
+   const int T1 = T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 65535;      /* a second plane at 1.6 x T0, as the library does for a fixed RT_SPARSE_T0 */
    static std::map<std::tuple<const int16_t *, uint64_t, int, int, int>, Cache> cache;
    auto key = std::make_tuple(planes, nrows, dc.ntrks, dc.width, T0);
    auto it = cache.find(key);
@@ -138,8 +139,8 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
       const uint64_t nruns = (nrows + rtmask::MASK_RUN - 1) / rtmask::MASK_RUN;
       if (nruns * rtmask::MASK_RUN > plane_stride) return RT_ERR_ARG;
       cc.mask_stride = 2 * nruns + 4;
-      cc.cand.assign((size_t)cc.mask_stride * dc.ntrks, 0); cc.acan.assign((size_t)cc.mask_stride * dc.ntrks, 0);
-      masks_host_build(planes, plane_stride, dc.ntrks, nruns, dc.width, T0, cc.cand.data(), cc.acan.data(), cc.mask_stride, 1);
+      cc.cand.assign((size_t)cc.mask_stride * dc.ntrks, 0); cc.cand2.assign((size_t)cc.mask_stride * dc.ntrks, 0); cc.acan.assign((size_t)cc.mask_stride * dc.ntrks, 0);
+      masks_host_build(planes, plane_stride, dc.ntrks, nruns, dc.width, T0, T1, cc.cand.data(), cc.cand2.data(), cc.acan.data(), cc.mask_stride, 1);
       cc.ngran = (nrows + RT_GRAN - 1) / RT_GRAN + 1;
       cc.gmm.assign((size_t)cc.ngran * dc.ntrks, 0);
       for (int k = 0; k < dc.ntrks; ++k)
@@ -149,8 +150,8 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
             cc.gmm[(size_t)k * cc.ngran + g] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); }
       it = cache.emplace(key, std::move(cc)).first; }
    Cache &cc = it->second;
-   dc.m_cand = cc.cand.data(); dc.m_acan = cc.acan.data(); dc.mask_stride = cc.mask_stride;
-   for (int k = 0; k < RT_MAXTRKS; ++k) dc.T0[k] = T0;
+   dc.m_cand = cc.cand.data(); dc.m_cand2 = cc.cand2.data(); dc.m_acan = cc.acan.data(); dc.mask_stride = cc.mask_stride;
+   for (int k = 0; k < RT_MAXTRKS; ++k) { dc.T0[k] = T0; dc.T1[k] = T1; }
    if (use_gmm) { dc.gmm = cc.gmm.data(); dc.ngran_cap = cc.ngran; }
    uint32_t heights[RT_AGC_MAX_WINDOW];
    HostSparseJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0, false};

@@ -31,7 +31,7 @@ def host_lib():
     L.sparse_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg),
                                         C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
     L.masks_host_build.restype = C.c_int
-    L.masks_host_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    L.masks_host_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     return L
 
 
@@ -74,12 +74,15 @@ def test_masks_simd_equals_definition(w, host_lib):
     stride = n
     ms = 2 * (n // 64) + 4
     for T0 in (1, 57, 3000, 65535):
-        got = [np.zeros((3, ms), dtype=np.uint32) for _ in range(2)]
-        want = [np.zeros((3, ms), dtype=np.uint32) for _ in range(2)]
-        assert host_lib.masks_host_build(planes.ctypes.data, stride, 3, n // 64, w, T0, got[0].ctypes.data, got[1].ctypes.data, ms, 1) == 0
-        assert host_lib.masks_host_build(planes.ctypes.data, stride, 3, n // 64, w, T0, want[0].ctypes.data, want[1].ctypes.data, ms, 0) == 0
+        T1 = min(65535, T0 * 3 + 11)
+        got = [np.zeros((3, ms), dtype=np.uint32) for _ in range(3)]
+        want = [np.zeros((3, ms), dtype=np.uint32) for _ in range(3)]
+        assert host_lib.masks_host_build(planes.ctypes.data, stride, 3, n // 64, w, T0, T1, got[0].ctypes.data, got[2].ctypes.data, got[1].ctypes.data, ms, 1) == 0
+        assert host_lib.masks_host_build(planes.ctypes.data, stride, 3, n // 64, w, T0, T1, want[0].ctypes.data, want[2].ctypes.data, want[1].ctypes.data, ms, 0) == 0
         assert np.array_equal(got[0], want[0]), f"cand differs, w={w} T0={T0}"
+        assert np.array_equal(got[2], want[2]), f"cand2 differs, w={w} T1={T1}"
         assert np.array_equal(got[1], want[1]), f"acan differs, w={w} T0={T0}"
+        assert not (want[2] & ~want[0]).any()                       # the higher threshold selects a subset
         assert want[1].any() and (T0 > 3000 or want[0].any())
 
 
@@ -194,8 +197,8 @@ def test_oracle_mask_definition_equals_host_build(host_lib, oracle_lib):
     w = oracle_lib.L.rt_pkww_width(C.byref(cfg), desc.tdelta_ns)
     nruns = (nrows + 63) // 64
     ms = 2 * nruns + 4
-    cg = np.zeros((desc.ntrks, ms), dtype=np.uint32); ag = np.zeros((desc.ntrks, ms), dtype=np.uint32)
-    assert host_lib.masks_host_build(planes.ctypes.data, stride, desc.ntrks, nruns, w, t0, cg.ctypes.data, ag.ctypes.data, ms, 1) == 0
+    cg = np.zeros((desc.ntrks, ms), dtype=np.uint32); ag = np.zeros((desc.ntrks, ms), dtype=np.uint32); dg = np.zeros((desc.ntrks, ms), dtype=np.uint32)
+    assert host_lib.masks_host_build(planes.ctypes.data, stride, desc.ntrks, nruns, w, t0, 65535, cg.ctypes.data, dg.ctypes.data, ag.ctypes.data, ms, 1) == 0
     nw = (nrows + 31) // 32
     if nrows & 31:
         keep = np.uint32((1 << (nrows & 31)) - 1)
