@@ -138,24 +138,27 @@ k_span_hist(const uint32_t *gmm, uint64_t ngran_cap, uint64_t ngroups, uint32_t 
    __syncthreads();
    const uint32_t *g = gmm + (size_t)blockIdx.x * ngran_cap;
    const uint64_t stride = ngroups / nsamples > 0 ? ngroups / nsamples : 1;
-   for (uint32_t i = threadIdx.x; i < nsamples; i += 256) {
+   for (uint32_t i = blockIdx.y * 256 + threadIdx.x; i < nsamples; i += gridDim.y * 256) {
       const uint64_t gi = (uint64_t)i * stride;
       if (gi >= ngroups) break;
+      const uint4 q = *reinterpret_cast<const uint4 *>(g + 4 * gi);            /* 4 granules: 16-byte aligned */
+      const uint32_t v[4] = {q.x, q.y, q.z, q.w};
       int mn = 32767, mx = -32768;
       for (int k = 0; k < 4; ++k) {
-         const uint32_t v = g[4 * gi + k];
-         const int a = (int)(int16_t)(uint16_t)(v & 0xffffu), b = (int)(int16_t)(uint16_t)(v >> 16);
+         const int a = (int)(int16_t)(uint16_t)(v[k] & 0xffffu), b = (int)(int16_t)(uint16_t)(v[k] >> 16);
          if (a < mn) mn = a; if (b > mx) mx = b; }
       atomicAdd(&h[min(HIST_BINS - 1, max(mx - mn, 0) >> 6)], 1u); }
    __syncthreads();
-   for (int i = threadIdx.x; i < HIST_BINS; i += 256) hist[(size_t)blockIdx.x * HIST_BINS + i] = h[i]; }
+   for (int i = threadIdx.x; i < HIST_BINS; i += 256) if (h[i]) atomicAdd(&hist[(size_t)blockIdx.x * HIST_BINS + i], h[i]); }
 
 uint32_t span_hist_words(int ntrks) { return (uint32_t)ntrks * HIST_BINS; }
 cudaError_t launch_span_hist(const uint32_t *gmm, uint64_t ngran_cap, uint64_t nrows, int ntrks, uint32_t *d_hist, cudaStream_t s) {
    const uint64_t ngroups = nrows / (4 * RT_GRAN);
    if (!ngroups) return cudaMemsetAsync(d_hist, 0, (size_t)span_hist_words(ntrks) * 4, s);
    const uint32_t nsamples = (uint32_t)(ngroups < 65536 ? ngroups : 65536);
-   k_span_hist<<<ntrks, 256, 0, s>>>(gmm, ngran_cap, ngroups, nsamples, d_hist);
+   cudaError_t e = cudaMemsetAsync(d_hist, 0, (size_t)span_hist_words(ntrks) * 4, s);
+   if (e != cudaSuccess) return e;
+   k_span_hist<<<dim3((unsigned)ntrks, 16), 256, 0, s>>>(gmm, ngran_cap, ngroups, nsamples, d_hist);
    return cudaGetLastError(); }
 
 /* T0 of every track from the host copy of the histograms: min(0.75 * default-state bound, 0.5 * bound for the smallest signal height
