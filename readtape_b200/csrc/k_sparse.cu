@@ -184,7 +184,7 @@ bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist) {
             const int Test = (int)(0.5f * (c.p.pkww_rise * alow / RT_PKWW_PEAKHEIGHT * 0.999f - 2.0f));
             if (Test < T0) T0 = Test;
             for (; b < HIST_BINS; ++b) { if (acc * 2 >= sig) break; acc += h[b + 1 < HIST_BINS ? b + 1 : b]; }   /* median signal height */
-            T1 = (int)(0.8f * (c.p.pkww_rise * (float)(b << 6) / RT_PKWW_PEAKHEIGHT * 0.999f - 2.0f)); } }
+            T1 = (int)(0.9f * (c.p.pkww_rise * (float)(b << 6) / RT_PKWW_PEAKHEIGHT * 0.999f - 2.0f)); } }   /* below it the scan simply follows the T0 plane */
       const int floor_ = Tdef / 20 > 16 ? Tdef / 20 : 16;
       c.T0[k] = T0 < floor_ ? floor_ : (T0 > 65535 ? 65535 : T0);
       c.T1[k] = T1 > c.T0[k] + c.T0[k] / 8 ? (T1 > 65535 ? 65535 : T1) : 0; }

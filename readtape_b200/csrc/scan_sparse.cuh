@@ -377,8 +377,13 @@ struct SparseScan {
          if (p >= pend) { o = end; st = SP_DONE; return; }
          oc = (uint32_t)(p - row0) + (uint32_t)delay;
          win = plane + (p - (uint32_t)w + 1u);
-         if (w <= 32) abits = bits_at(ma, p - (uint32_t)w + 1u);      /* acan bits of the window's rows: requested together with the samples */
+         /* acan bits of the window's rows: the two words are requested together with the samples and only combined afterwards (an
+            instruction that needs them in front of the sample loads would hold those back) */
+         const uint64_t aw = (p - (uint32_t)w + 1u) >> 5; const int ash = (int)((p - (uint32_t)w + 1u) & 31);
+         uint32_t a_lo = 0, a_hi = 0;
+         if (w <= 32) { a_lo = ma[aw]; a_hi = ma[aw + 1]; }
          const WinKeys wk = scan_window<true, false>(win, 0);
+         abits = ash ? (a_lo >> ash) | (a_hi << (32 - ash)) : a_lo;
          S = key_val(wk.kmax); mn = key_val(wk.kmin); posm = kmin_pos(wk.kmin); pos = kmax_pos(wk.kmax);
          xl = win[0]; xr = win[w - 1];
          tcand = S - (xl > xr ? xl : xr) >= T; bcand = (xl < xr ? xl : xr) - mn >= T;
