@@ -321,14 +321,24 @@ struct SparseScan {
       refresh rows: acan rows, and rows where the sample that leaves equals m (decoder.c:767).  After a refresh at row r the value
       is Wmin(r) and the next refresh of the second kind happens when the LEFTMOST sample with that value leaves, at row
       (its position) + w -- so the walk hops from refresh to refresh instead of visiting every row. */
-   RT_FHD void lazy_min(uint32_t oo) {
+   /* hint: the acan bits of the rows of the window that ends at oo, if the caller holds them (hint_rows = w, else 0): the last
+      acan row is then found without touching the bit plane again, unless it lies in front of the window */
+   RT_FHD void lazy_min(uint32_t oo, uint32_t hint_bits = 0, int hint_rows = 0) {
       if (mq == oo) return;
       const uint64_t p = prow(oo), pm = prow(mq);
       /* last acan row in (pm, p] */
       uint64_t a = pm; bool have = false;
-      {
-         uint64_t wi = p >> 5;
-         uint32_t bits = ma[wi] & (0xffffffffu >> (31 - (int)(p & 31)));
+      uint64_t top = p;                                           /* rows above `top` are known to hold no acan row */
+      bool search = true;
+      if (hint_rows) {
+         const uint64_t ws = p - (uint32_t)hint_rows + 1u;
+         const uint32_t hb = hint_rows >= 32 ? hint_bits : hint_bits & ((1u << hint_rows) - 1u);
+         if (hb) { const uint64_t ah = ws + 31u - (uint32_t)clz32(hb); search = false; if (ah > pm) { a = ah; have = true; } }
+         else if (ws <= pm + 1) search = false;                   /* the window covers (pm, p]: none */
+         else top = ws - 1; }
+      if (search) {
+         uint64_t wi = top >> 5;
+         uint32_t bits = ma[wi] & (0xffffffffu >> (31 - (int)(top & 31)));
          for (;;) {
             const uint64_t base = wi << 5;
             if (base + 31 <= pm) break;                                                   /* the whole word is at or before pm */
@@ -382,10 +392,11 @@ struct SparseScan {
          const uint64_t aw = (p - (uint32_t)w + 1u) >> 5; const int ash = (int)((p - (uint32_t)w + 1u) & 31);
          uint32_t a_lo = 0, a_hi = 0;
          if (w <= 32) { a_lo = ma[aw]; a_hi = ma[aw + 1]; }
+         xr = win[w - 1];
          const WinKeys wk = scan_window<true, false>(win, 0);
          abits = ash ? (a_lo >> ash) | (a_hi << (32 - ash)) : a_lo;
          S = key_val(wk.kmax); mn = key_val(wk.kmin); posm = kmin_pos(wk.kmin); pos = kmax_pos(wk.kmax);
-         xl = win[0]; xr = win[w - 1];
+         xl = win[0];
          tcand = S - (xl > xr ? xl : xr) >= T; bcand = (xl < xr ? xl : xr) - mn >= T;
          o = oc + 1;
          SP_STAT(cands, 1);
@@ -402,7 +413,7 @@ struct SparseScan {
          const bool fresh = w <= 32 ? ((abits >> posm) & (w >= 32 ? 0xffffffffu : ((1u << (w - posm)) - 1u))) != 0
                                     : acan_in(p - (uint32_t)w + 1u + (uint32_t)posm, p);
          if (fresh) { m = mn; mq = oc; SP_STAT(shortcut, 1); }
-         else lazy_min(oc);
+         else lazy_min(oc, abits, w <= 32 ? w : 0);
          minv = volts(c, m);
          bot = minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
          if (bot) { pos = posm; if (m != mn) { pos = -1; for (int i = w; i-- > 0;) if ((int)win[i] == m) pos = i; } } }
