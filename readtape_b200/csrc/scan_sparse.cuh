@@ -59,6 +59,12 @@ RT_FHD uint32_t bits_at(const uint32_t *mk, uint64_t p) {
    const uint32_t lo = mk[wi];
    if (sh == 0) return lo;
    return (lo >> sh) | (mk[wi + 1] << (32 - sh)); }
+/* 64 mask bits starting at bit position p */
+RT_FHD uint64_t bits64_at(const uint32_t *mk, uint64_t p) {
+   const uint64_t wi = p >> 5; const int sh = (int)(p & 31);
+   const uint32_t w0 = mk[wi], w1 = mk[wi + 1], w2 = mk[wi + 2];
+   const uint32_t lo = sh ? (w0 >> sh) | (w1 << (32 - sh)) : w0, hi = sh ? (w1 >> sh) | (w2 << (32 - sh)) : w1;
+   return (uint64_t)lo | ((uint64_t)hi << 32); }
 RT_FHD int ctz32(uint32_t v) {
 #ifdef __CUDA_ARCH__
    return __ffs((int)v) - 1;
@@ -83,7 +89,7 @@ struct SparseScan {
       exact for row mq (dense mode: for row o - 1) */
    uint32_t o, resume, mq; int m, T, T0t, T1t, st; float inv_lsb, rise, reqmin;
    uint32_t ndense;                                             /* rows walked in dense mode (diagnostics) */
-   uint32_t cb, cb_o;                                           /* the 32 candidate bits of rows [cb_o, cb_o + 32) (cb_o = NO_ROW32: none held) */
+   uint64_t cb; uint32_t cb_o;                                  /* the 64 candidate bits of rows [cb_o, cb_o + 64) (cb_o = NO_ROW32: none held) */
    /* proof data (offsets relative to row0; OFF_NONE = none), as in UnitScan */
    bool pre; uint32_t pre_pos, pre_end;                         /* pre_end: the row of the first event once it is known */
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
@@ -375,15 +381,16 @@ struct SparseScan {
          const uint32_t from = o > resume ? o : resume;
          if (from >= end) { o = end; st = SP_DONE; return; }
          p = prow(from);
-         /* the candidate bits of 32 rows stay in a register from step to step: successive candidates mostly share them */
-         uint32_t bits; uint32_t nv = 32;
-         if (cb_o != NO_ROW32 && from >= cb_o && from - cb_o < 32u) { bits = cb >> (from - cb_o); nv = 32u - (from - cb_o); }
-         else { bits = bits_at(mc, p); cb = bits; cb_o = from; }
+         /* the candidate bits of 64 rows stay in registers from step to step: successive candidates mostly share them, and the second
+            half has arrived long before it is needed */
+         uint64_t bits; uint32_t nv = 64;
+         if (cb_o != NO_ROW32 && from >= cb_o && from - cb_o < 64u) { bits = cb >> (from - cb_o); nv = 64u - (from - cb_o); }
+         else { bits = bits64_at(mc, p); cb = bits; cb_o = from; }
          int nw = 1;
-         while (!bits && nw < SPARSE_SEARCH_WORDS && p + nv < pend) {
-            p += nv; nv = 32; bits = bits_at(mc, p); cb = bits; cb_o = (uint32_t)(p - row0) + (uint32_t)delay; ++nw; }
+         while (!bits && nw < SPARSE_SEARCH_WORDS / 2 && p + nv < pend) {
+            p += nv; nv = 64; bits = bits64_at(mc, p); cb = bits; cb_o = (uint32_t)(p - row0) + (uint32_t)delay; ++nw; }
          if (!bits) { p += nv; o = p >= pend ? end : (uint32_t)(p - row0) + (uint32_t)delay; if (o >= end) st = SP_DONE; return; }
-         p += (uint32_t)ctz32(bits);
+         { const uint32_t blo = (uint32_t)bits; p += blo ? (uint32_t)ctz32(blo) : 32u + (uint32_t)ctz32((uint32_t)(bits >> 32)); }
          if (p >= pend) { o = end; st = SP_DONE; return; }
          oc = (uint32_t)(p - row0) + (uint32_t)delay;
          win = plane + (p - (uint32_t)w + 1u);
