@@ -373,12 +373,12 @@ def main():
         two_pass = ms_masks > 0
         alg_bytes = 2.0 * tsamp + 32.0 * events                # 2 B read per track-sample + event bytes
         ingest_bytes = 4.0 * tsamp                              # K1: 2 B read + 2 B written per track-sample
-        # per-kernel algorithmic bytes: phase A reads every sample once and writes 2 bits per track-sample;
-        # phase B reads those 2 bits and writes the events
+        # per-kernel algorithmic bytes: phase A reads every sample once and writes 3 bits per track-sample;
+        # phase B reads those 3 bits and writes the events
         kernels = {"k_ingest_tma": (ms_ingest, ingest_bytes)}
         if two_pass:
-            kernels["k_peak_masks"] = (ms_masks, 2.25 * tsamp)
-            kernels["k_units_sparse"] = (ms_scan - ms_masks, 0.25 * tsamp + 32.0 * events)
+            kernels["k_peak_masks"] = (ms_masks, 2.375 * tsamp)
+            kernels["k_units_sparse"] = (ms_scan - ms_masks, 0.375 * tsamp + 32.0 * events)
         else:
             kernels["k_units_scan (generic)" if force == "generic" else "k_units_fast"] = (ms_scan, alg_bytes)
         scan_kernel = max((k for k in kernels if k != "k_ingest_tma"), key=lambda k: kernels[k][0])

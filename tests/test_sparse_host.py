@@ -216,3 +216,46 @@ def test_volts_without_division_is_exact(host_lib):
         host_lib.volts_host_all(C.c_float(mv), out.ctypes.data)
         want = (x / np.float32(32767)) * np.float32(mv)
         assert want.dtype == np.float32 and np.array_equal(out.view(np.uint32), want.view(np.uint32)), mv
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_sparse_scan_on_adversarial_signals(seed, host_lib, oracle_lib):
+    """signals built to stress what real captures rarely do: coarsely quantised levels (long runs of EQUAL samples: every
+    leftmost-position and equality rule of lookfor_peak / refine_peak / the lazy minimum is hit), clipping at +-full scale,
+    amplitude steps (AGC swings, T crossing T0 / T1 in both directions), DC drift; one unit = the whole signal; compared event
+    for event with the oracle, and the proof data with the one-pass path"""
+    rng = np.random.default_rng(seed)
+    n = 64 * 600
+    t = np.arange(n)
+    rows = np.zeros((n, 9), dtype=np.int64)
+    for k in range(9):
+        period = rng.uniform(14, 40)
+        amp = rng.uniform(2000, 30000) * (1 + 0.8 * np.sign(np.sin(2 * np.pi * t / rng.uniform(3000, 9000))))     # amplitude steps
+        sig = amp * np.sin(2 * np.pi * t / period + rng.uniform(0, 6)) * (rng.random(n).cumsum() % 2000 > 600)     # bursts and gaps
+        sig += 1500 * np.sin(2 * np.pi * t / 5000.0) + rng.normal(0, rng.uniform(5, 120), n)
+        q = int(rng.choice([1, 64, 512, 2048]))
+        rows[:, k] = np.clip(np.round(sig / q) * q, -32768, 32767)
+    rows = rows.astype("<i2")
+    rows[rows[:, 0] == -32768, 0] = -32767                          # head 0 == -32768 is the TBIN end marker
+    desc = abi.make_desc(9, 4.4, 1280, 1_000_000_000)
+    planes, stride = make_planes(rows, desc)
+    tape = oracle_lib.open(desc); tape.upload(rows)
+    cases = [(tbin.MODE_NRZI, parmsets.NRZI[0], 800.0, None), (tbin.MODE_NRZI, parmsets.NRZI[4], 800.0, [0, 4, 1, 9, 2, 0, 30, 5, 50]),
+             (tbin.MODE_PE, parmsets.PE[0], 1600.0, [3, 0, 0, 1, 0, 7, 0, 0, 2]), (tbin.MODE_NRZI, parmsets.NRZI[1], 300.0, None)]
+    mode, parm, bpi, skew = cases[seed % len(cases)]
+    cfg = abi.make_cfg(mode, parm, bpi, 50.0, skew=skew)
+    for row0 in (0, 64 * 50):
+        sc = tape.scan(cfg); sc.reset(abi.RT_RESET_FULL, row0)
+        want, _ = sc.run(n); sc.end()
+        ref_meta = fast_meta(host_lib, planes, stride, n, desc, cfg, row0, n, cap=1 << 17)
+        for frac, gmm in ((0.25, 1), (0.7, 1), (0.06, 0)):
+            got, meta = sparse_scan(host_lib, planes, stride, n, desc, cfg, row0, n, frac, gmm, cap=1 << 17)
+            assert got is not None
+            a, b = evlog.to_canon(got), evlog.to_canon(want)
+            if a.tobytes() != b.tobytes():
+                k = evlog._first_diff(a, b)
+                pytest.fail(f"seed {seed} row0 {row0} frac {frac}: event #{k}: sparse {a[k] if k < len(a) else None} "
+                            f"oracle {b[k] if k < len(b) else None} ({len(a)} vs {len(b)})")
+            assert len(b) > 500
+            assert np.array_equal(meta[:, META_WORDS_NO_PAD], ref_meta[:, META_WORDS_NO_PAD]), f"seed {seed} row0 {row0} frac {frac}: proof data"
+    tape.close()
