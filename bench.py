@@ -193,7 +193,7 @@ def bench_gcr(args, rank, world, local_rank, W, K):
                 "config": {"workload": f"synthetic 9-track GCR-density (9042 fci, 50 IPS, 6.25 MHz) TBIN, {rows} rows ({rows * 18 / 1e9:.1f} GB) per time shard, "
                                        f"{world} shard(s) x {len(cfgs)} parameter sets = {npass} scan passes dealt over {world} GPU(s), -zeros",
                            "l2": "inputs far larger than the 126 MB L2", "units_of_rank0": mine},
-                "roofline": {"bound": "hbm", "kernel": "k_units_scan (generic, zero-crossing detector)", "achieved": alg / (ms_scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "k_units_zc (zero-crossing fast path, one lane per (unit, track))", "achieved": alg / (ms_scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / (ms_scan * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_scan / max(1, len(mine))},
                 "e2e": None, "gpu_launches": sum(int(s.launches) for s in sts) * K + 2 * K * len(shards), "clocks": clocks, "cpu_baseline": None,
                 "result_gather": {"passes": npass, "events": int(events.item())}}
