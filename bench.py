@@ -406,7 +406,8 @@ def main():
             "device_ms_per_step": ms_ingest + ms_units + ms_scan,      # CUDA events on the library's own stream, summed over the step's kernels "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(rows), "l2": "inputs (rows*18 B per step) are far larger than the 126 MB L2",
-                       "units_per_tape": units, "events_per_tape": events, "super_tile_sha256": synth.tile_sha256(tile)[:16],
+                       "units_per_tape": units, "events_per_tape": events,
+                       "rows_walked_one_by_one_frac": int(stats[-1].rows_scanned) / float(tsamp), "super_tile_sha256": synth.tile_sha256(tile)[:16],
                        "parallelism": f"{world} x independent tapes" if world > 1 else "1 GPU"},
             "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -219,7 +219,8 @@ typedef struct rt_bulk_stats {
    uint64_t rows;            /* rows on the tape                                             */
    uint64_t units;           /* units per cfg                                                */
    uint64_t events;          /* total events over all cfgs                                   */
-   uint64_t rows_scanned;    /* sum over (unit,cfg) of rows the detector actually walked      */
+   uint64_t rows_scanned;    /* sum over (unit,track,cfg) of the rows a lane walked one by one: all of them for the one-pass kernels,
+                                only the dense-mode rows (window fill, threshold below the mask threshold) for the two-pass scan */
    uint64_t track_samples;   /* rows * ntrks * ncfgs: the metric's numerator                 */
    double   ms_preprocess;   /* device time: de-interleave + gap map (0 if done at upload)   */
    double   ms_units;        /* device time: unit table construction                         */

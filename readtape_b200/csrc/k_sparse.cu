@@ -100,7 +100,7 @@ struct SparseJobs {
    template <class Scan>
    __device__ void done(Scan &us) {
       TrkMeta m; us.finish(m); meta[cur] = m;
-      atomicAdd(&counters[0], (unsigned long long)us.end);
+      if (us.ndense) atomicAdd(&counters[0], (unsigned long long)us.ndense);      /* rows walked one by one (dense mode) */
       if (us.em.n) atomicAdd(&counters[1], (unsigned long long)us.em.n); } };
 
 struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };

@@ -204,6 +204,31 @@ def test_fast_kernels_equal_generic_kernel_on_every_unit(name, cuda_lib):
     assert nunits > 0
 
 
+@pytest.mark.parametrize("name", ["Microdata_20blks.nm_tap", "PLAGO_beginning.nm_tap", "LJS009_part1_39blks", "1600bpi_ukn_6s", "tss_4secs"])
+def test_data_driven_mask_thresholds_keep_the_scan_sparse(name, cuda_lib):
+    """the per-track mask thresholds chosen from the span histogram: on real captures (NRZI and PE, 0.5 .. 4 V peak to peak) the
+    two-pass scan must stay out of its row-by-row mode for all but a few percent of the rows (a fixed fraction of the default-state
+    threshold puts 38 % of LJS009 there), whereas a threshold above every bound (RT_SPARSE_T0=8) walks nearly everything"""
+    doc, segs, heads, rows = load_capture(name)
+    tape = cuda_lib.open(evlog.desc_from_heads(heads))
+    tape.upload(rows)
+    seg = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT)][0]
+    cfg = evlog.cfg_for(seg)
+    bulk = tape.bulk_scan([cfg]); st = bulk.stats(); bulk.free()
+    assert st.ms_masks > 0, "the two-pass scan was not used"
+    dense = st.rows_scanned / float(st.track_samples)
+    os.environ["RT_SPARSE_T0"] = "8"
+    try:
+        bulk = tape.bulk_scan([cfg]); st2 = bulk.stats(); bulk.free()
+    finally:
+        os.environ.pop("RT_SPARSE_T0", None)
+    tape.close()
+    print(f"{name}: dense-mode rows {100 * dense:.2f} %, with an unreachable threshold {100 * st2.rows_scanned / float(st2.track_samples):.1f} %")
+    assert st2.events == st.events
+    assert dense < 0.03, f"{100 * dense:.1f} % of the track-rows were walked one by one"
+    assert st2.rows_scanned > 10 * max(st.rows_scanned, 1) or st2.rows_scanned > 0.3 * st2.track_samples
+
+
 @pytest.mark.parametrize("name", ["Microdata_20blks", "LJS009_part1_39blks", "tss_4secs"])
 def test_peak_mask_kernel_equals_definition(name, cuda_lib, oracle_lib):
     """phase A of the two-pass scan (int16x2 SIMD in registers) against the oracle's brute-force definition of the two bit planes,
