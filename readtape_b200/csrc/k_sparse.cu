@@ -37,7 +37,9 @@ k_peak_masks(const int16_t *planes, uint64_t plane_stride, uint64_t run_lo, uint
    const size_t wi = (size_t)trk * mask_stride + (size_t)(p0 / 32);
    *reinterpret_cast<uint2 *>(cand + wi) = make_uint2(cw[0], cw[1]);
    *reinterpret_cast<uint2 *>(cand2 + wi) = make_uint2(dw[0], dw[1]);
-   *reinterpret_cast<uint2 *>(acan + wi) = make_uint2(aw[0], aw[1]); }
+   *reinterpret_cast<uint2 *>(acan + wi) = make_uint2(aw[0], aw[1]);
+   if (r == nruns - 1) {                                       /* the slack words behind the last run: readers fetch up to 64 bits past a row */
+      for (int k = 2; k < 6 && (size_t)(p0 / 32) + k < mask_stride; ++k) cand[wi + k] = cand2[wi + k] = acan[wi + k] = 0u; } }
 
 template <int W>
 static cudaError_t launch_masks_w(const DevCfg &c, uint64_t run_lo, uint64_t nruns, uint32_t *cand, uint32_t *cand2, uint32_t *acan, cudaStream_t s) {

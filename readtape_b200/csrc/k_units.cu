@@ -36,7 +36,7 @@ k_quiet_bitmap(const uint32_t *gmm, uint64_t ngran_cap, int ntrks, uint64_t ngra
          if (up.det == RT_DET_ZC) { if (mx > up.thr || mn < -up.thr) quiet = false; }
          else if (mx - mn > up.thr) quiet = false; } }
    uint32_t word = __ballot_sync(0xffffffffu, quiet);
-   if ((threadIdx.x & 31) == 0) bitmap[g >> 5] = word; }
+   if ((threadIdx.x & 31) == 0 && (g >> 5) < (ngran + 31) / 32) bitmap[g >> 5] = word; }     /* the grid is rounded up to whole CTAs */
 
 __device__ __forceinline__ bool quiet_at(const uint32_t *bitmap, uint64_t g) { return (bitmap[g >> 5] >> (g & 31)) & 1u; }
 

@@ -1,0 +1,8 @@
+#!/bin/bash
+# tools/memcheck.sh -- compute-sanitizer memcheck over the smoke test and a cross-section of the GPU parity tests (B200 box).
+# Round 1: found one out-of-bounds write (k_quiet_bitmap wrote up to 3 words past the quiet bitmap when the granule count was
+# not a multiple of 256; fixed), 0 errors since.
+set -e
+compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()"
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q \
+   -k "bulk_scan_lookup and Microdata or data_driven and LJS009 or peak_mask and tss or fanout and 1600"
