@@ -329,8 +329,10 @@ struct SparseScan {
       (its position) + w -- so the walk hops from refresh to refresh instead of visiting every row. */
    /* hint: the acan bits of the rows of the window that ends at oo, if the caller holds them (hint_rows = w, else 0): the last
       acan row is then found without touching the bit plane again, unless it lies in front of the window */
-   RT_FHD void lazy_min(uint32_t oo, uint32_t hint_bits = 0, int hint_rows = 0) {
-      if (mq == oo) return;
+   /* returns the plane row of the LEFTMOST sample of the window that ends at oo which carries m (~0: not determined): the carrier
+      found by the walk has not left yet (else there would have been another refresh), and no equal sample lies left of it */
+   RT_FHD uint64_t lazy_min(uint32_t oo, uint32_t hint_bits = 0, int hint_rows = 0) {
+      if (mq == oo) return ~0ull;
       const uint64_t p = prow(oo), pm = prow(mq);
       /* last acan row in (pm, p] */
       uint64_t a = pm; bool have = false;
@@ -357,16 +359,17 @@ struct SparseScan {
          carries it) -- and for the hops, so that the lanes of a warp that need this run the same code */
       uint64_t r = have ? a : pm;
       bool keep = !have;
+      uint64_t at;
       for (;;) {
          const uint64_t ws = r - (uint32_t)w + 1u;
          const WinKeys k = scan_window<false, true>(plane + ws, m);
-         uint64_t at;
          if (keep && k.keq < 64u) at = ws + k.keq;
          else { m = key_val(k.kmin); at = ws + (uint32_t)kmin_pos(k.kmin); }
          keep = false;
          if (at + (uint32_t)w > p) break;
          r = at + (uint32_t)w; SP_STAT(hops, 1); }
-      mq = oo; }
+      mq = oo;
+      return at; }
 
    RT_FHD void sparse_step() {
       /* The cheap part -- next candidate row at or after the end of the blind stretch, its window, the integer pre-filter for the
@@ -419,11 +422,14 @@ struct SparseScan {
          SP_STAT(bcalls, 1);
          const bool fresh = w <= 32 ? ((abits >> posm) & (w >= 32 ? 0xffffffffu : ((1u << (w - posm)) - 1u))) != 0
                                     : acan_in(p - (uint32_t)w + 1u + (uint32_t)posm, p);
+         uint64_t m_at = p - (uint32_t)w + 1u + (uint32_t)posm;
          if (fresh) { m = mn; mq = oc; SP_STAT(shortcut, 1); }
-         else lazy_min(oc, abits, w <= 32 ? w : 0);
+         else m_at = lazy_min(oc, abits, w <= 32 ? w : 0);
          minv = volts(c, m);
          bot = minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin);
-         if (bot) { pos = posm; if (m != mn) { pos = -1; for (int i = w; i-- > 0;) if ((int)win[i] == m) pos = i; } } }
+         if (bot) {
+            pos = m_at != ~0ull ? (int)(m_at - (p - (uint32_t)w + 1u)) : -1;
+            if (pos < 0 || pos >= w || (int)win[pos] != m) { pos = -1; for (int i = w; i-- > 0;) if ((int)win[i] == m) pos = i; } } }   /* (never taken in practice) */
       if (top || bot) {
          SP_STAT(events, 1); SP_STAT(tops, top ? 1 : 0);
          const bool found = pos >= 0;
