@@ -37,19 +37,8 @@ REF = os.environ.get("RT_REFERENCE", "/root/reference")
 OUT = os.path.join(ROOT, "oracle", "_ref")
 GOLD = os.path.join(ROOT, "tests", "golden")
 
-# name, directory, Makefile options (examples/*/Makefile), rows to stage (None = whole file)
-EXAMPLES = [
-    ("Microdata_20blks", "9trk_NRZI", "-v -m -nrzi -hex -ascii", None),
-    ("PLAGO_beginning", "9trk_NRZI", "-v -m -nrzi -ips=50 -deskew -ebcdic -linefeed", 700_000),
-    ("1600bpi_ukn_6s", "9trk_PE", "-v -m -ntrks=9 -pe -bpi=1600 -ips=50 -order=01234576p -tap -ascii -linefeed", 600_000),
-    ("LJS009_part1_39blks", "9trk_PE", "-v -m -ntrks=9 -pe -bpi=1600 -ips=50 -tap -ebcdic -linesize=137", 600_000),
-    ("1kblks_43blks", "9trk_GCR", "-v -m -gcr -ips=50 -order=76543210p -zeros -correct -tap -ascii -linefeed", 600_000),
-    ("sf93_8blks", "9trk_GCR", "-v -m -gcr -ips=50 -zeros -correct -tap -ascii -linefeed", 600_000),
-    ("analog", "9trk_GCR", "-v -gcr -ips=125 -differentiate -zeros -tap -ascii", None),
-    ("SRI_SDS_102715028_4secs", "7trk_NRZI", "-v -m -nrzi -ntrks=7 -order=543210p -tap -SDS -linesize=144", 700_000),
-    ("tss_4secs", "7trk_NRZI", "-v -m -nrzi -ntrks=7 -tap", 700_000),
-    ("132_pt1", "6trk_Whirlwind", "-whirlwind -v3 -fluxdir=auto -tap -deskew -octal2 -flexo", None),
-]
+from oracle.captures import EXAMPLES, stage_xz, staged_path, full_path  # noqa: E402  (the capture table lives there)
+
 # extra command lines on the staged captures: BASELINE.json config 1 ("-nm -nrzi -tap", one parmset)
 EXTRA = [
     ("Microdata_20blks", "nm_tap", "-nm -nrzi -tap"),
@@ -77,22 +66,38 @@ def run(binary, opts, src, outbase, evdump=None):
 
 
 def stage(name, directory, rows):
-    src = os.path.join(REF, "examples", directory, name + ".tbin")
-    dst = os.path.join(OUT, "examples", name + ".tbin")
-    os.makedirs(os.path.dirname(dst), exist_ok=True)
-    if rows is None:
-        if not os.path.exists(dst) or os.path.getsize(dst) != os.path.getsize(src):
-            shutil.copyfile(src, dst)
-        return dst
-    hdr, allrows = tbin.read_tbin(src)
-    with open(src, "rb") as fh:
-        head = fh.read(hdr.payload_offset)
-    keep = np.array(allrows[:rows])
-    with open(dst, "wb") as fh:
-        fh.write(head)
-        keep.tofile(fh)
-        fh.write(np.array([tbin.END_MARK], dtype="<i2").tobytes())
-    return dst
+    """-> path of the capture the segment fixtures are generated from (whole file or prefix + end marker)"""
+    stage_xz(name)
+    return staged_path(name)
+
+
+def full_outputs():
+    """The reference on the WHOLE captures, with the example's own Makefile command line and the EXTRA ones: SHA-256 (and size) of
+    every .tap/.bin it writes -> tests/golden/full_outputs.json.  For the Makefile command lines these are the reference-held
+    goldens of examples/*/expected_results (checked here byte for byte)."""
+    tmp = tempfile.mkdtemp(prefix="rtfull_")
+    doc = {}
+    for name, directory, opts, _rows in EXAMPLES:
+        src = os.path.join(REF, "examples", directory, name + ".tbin")
+        exp_dir = os.path.join(REF, "examples", directory, "expected_results")
+        for tag, o in [("", opts)] + [(tag, o) for (n, tag, o) in EXTRA if n == name]:
+            label = name + ("." + tag if tag else "")
+            wd = os.path.join(tmp, label); os.makedirs(wd)
+            run("readtape_ref", o, src, os.path.join(wd, name))
+            outs = {}
+            for f in sorted(os.listdir(wd)):
+                if f.endswith(".tap") or f.endswith(".bin"):
+                    made = os.path.join(wd, f)
+                    held = os.path.join(exp_dir, f)
+                    is_held = (not tag) and os.path.exists(held)
+                    if is_held and open(made, "rb").read() != open(held, "rb").read():
+                        raise SystemExit(f"reference output {f} differs from the reference-held golden")
+                    outs[f] = {"sha256": sha256_file(made), "bytes": os.path.getsize(made), "reference_held_golden": bool(is_held)}
+            doc[label] = {"capture": name, "options": o, "outputs": outs}
+            print(f"  {label}: " + ", ".join(f"{k} ({v['bytes']} B{', golden' if v['reference_held_golden'] else ''})" for k, v in outs.items()))
+    with open(os.path.join(GOLD, "full_outputs.json"), "w") as fh:
+        json.dump(doc, fh, indent=1, sort_keys=True); fh.write("\n")
+    shutil.rmtree(tmp, ignore_errors=True)
 
 
 def main():
@@ -101,13 +106,17 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--stage-only", action="store_true",
                     help="only (re)create oracle/_ref/examples/ (what build() does in a fresh container)")
+    ap.add_argument("--full-only", action="store_true",
+                    help="only regenerate tests/golden/full_outputs.json (the reference's outputs on the WHOLE captures)")
     args = ap.parse_args()
+    if args.full_only:
+        full_outputs()
+        return
     if args.stage_only:
         for name, directory, _opts, rows in EXAMPLES:
-            dst = os.path.join(OUT, "examples", name + ".tbin")
-            if not os.path.exists(dst):
-                stage(name, directory, rows)
-        print("staged", len(EXAMPLES), "captures under", os.path.join(OUT, "examples"))
+            stage(name, directory, rows)
+            full_path(name)
+        print("staged", len(EXAMPLES), "captures under", os.path.join(OUT, "examples_full"), "(xz) and", os.path.join(OUT, "examples"))
         return
     os.makedirs(GOLD, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="rtgold_")

@@ -4,7 +4,8 @@
 host-side logic, and the C-ABI export check.  `-m gpu` runs on a B200 and compares the CUDA
 library with the reference goldens and with the CPU oracle through the same C-ABI.
 Nothing under tests/ reads /root/reference: reference-derived inputs are the committed fixtures
-in tests/golden/ and the staged captures in oracle/_ref/examples/ (see oracle/make_golden.py).
+in tests/golden/ and the staged captures (oracle/captures.py: xz files under oracle/_ref/examples_full/
+that travel to the GPU box; the .tbin files the tests read are derived from them on first use).
 """
 import os
 import sys
@@ -45,13 +46,21 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+def capture_path(capture_file, full=False):
+    """path of a staged capture (`<name>.tbin`): the prefix the segment fixtures were made from, or the whole file"""
+    from oracle import captures
+    name = capture_file[:-5] if capture_file.endswith(".tbin") else capture_file
+    path = captures.full_path(name) if full else captures.staged_path(name)
+    if path is None:
+        pytest.skip(f"capture {name} was never staged (run `python oracle/make_golden.py --stage-only` in the build container)")
+    return path
+
+
 def load_capture(fixture_name):
     """-> (doc, segments, heads, rows) for a committed fixture; skips if the staged capture is absent."""
     from readtape_b200 import evlog, tbin
     doc, segs = evlog.load_fixture(os.path.join(GOLDEN, fixture_name + ".segments.json"))
-    path = os.path.join(EXAMPLES, doc["capture"])
-    if not os.path.exists(path):
-        pytest.skip(f"staged capture {path} missing (run `make -C oracle` + oracle/make_golden.py in the build container)")
+    path = capture_path(doc["capture"])
     heads = doc["heads"]
     _, rows = tbin.read_tbin(path, nheads=heads["nheads"])
     return doc, segs, heads, np.asarray(rows)

@@ -5,37 +5,73 @@ shim (readtape_b200/host/readblock_b200.c) must write byte-identical .tap/.bin f
     (oracle/_ref/readtape_shim_oracle, test infrastructure).
   * GPU: the shim linked against the CUDA library (readtape_b200/bin/readtape_b200): the product,
     with the speculative whole-tape scan and with the exact scan only (RT_NO_BULK=1).
-Expected outputs are the reference's own (tests/golden/*.tap, and SHA-256 of its .bin files recorded in
-the fixtures by oracle/make_golden.py).  Both binaries are built in the build container from the
-reference sources where they lie; the tests skip if they were not built.
+Expected outputs:
+  * WHOLE captures: the reference-held goldens of examples/*/expected_results (every .tap/.bin, SHA-256 in
+    tests/golden/full_outputs.json, verified byte for byte against the reference's files when that table was
+    generated), plus the reference's own output for BASELINE config 1's "-nm -nrzi -tap" command line;
+  * prefix captures (the per-segment event fixtures): the reference run on the prefix (tests/golden/*.tap and the
+    SHA-256 of its .bin files recorded in the fixtures by oracle/make_golden.py).
+Both binaries are built in the build container from the reference sources where they lie; the tests skip if they
+were not built.
 """
 import hashlib
 import json
 import os
+import re
 import subprocess
 
 import pytest
 
-from conftest import ALL_FIXTURES, EXAMPLES, GOLDEN, ROOT
+from conftest import ALL_FIXTURES, GOLDEN, ROOT, capture_path
 
 ORACLE_SHIM = os.path.join(ROOT, "oracle", "_ref", "readtape_shim_oracle")
 CUDA_SHIM = os.path.join(ROOT, "readtape_b200", "bin", "readtape_b200")
+FULL = json.load(open(os.path.join(GOLDEN, "full_outputs.json")))
+MIN_HIT_RATE = 0.95          # block decodes served by the speculative whole-tape scan ((hits - restarts) / (hits + misses))
+
+
+def shim_stats(stdout):
+    """the RT_STATS=1 line of the shim -> dict"""
+    m = re.search(r"B200 scan: (\d+) events, (\d+) speculative hits, (\d+) misses, (\d+) restarts, (\d+) exact spans", stdout)
+    if not m:
+        return None
+    ev, hits, miss, restarts, spans = map(int, m.groups())
+    return {"events": ev, "hits": hits, "misses": miss, "restarts": restarts, "exact_spans": spans}
+
+
+def record_stats(label, st):
+    """hit / miss / restart counts per fixture: printed (pytest -s / -rP) and kept in gpurun_out/hitrates.json"""
+    print(f"[hit-rate] {label}: {st}")
+    out = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(out):
+        return
+    path = os.path.join(out, "hitrates.json")
+    try:
+        doc = json.load(open(path))
+    except Exception:
+        doc = {}
+    doc[label] = st
+    with open(path, "w") as fh:
+        json.dump(doc, fh, indent=1, sort_keys=True)
+
+
+def run_binary(exe, opts, capture, outbase, tmp_path, env_extra=None):
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (make -C readtape_b200/host in the build container)")
+    env = dict(os.environ, RT_STATS="1")
+    env.update(env_extra or {})
+    opts = [o for o in opts.split() if o not in ("-v", "-v3")] + ["-v"]
+    r = subprocess.run([exe] + opts + [f"-outf={outbase}", capture], capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "FATAL" not in r.stdout
+    return r.stdout
 
 
 def run_shim(exe, name, tmp_path, env_extra=None):
     doc = json.load(open(os.path.join(GOLDEN, name + ".segments.json")))
-    capture = os.path.join(EXAMPLES, doc["capture"])
-    if not os.path.exists(exe):
-        pytest.skip(f"{exe} not built (make -C readtape_b200/host in the build container)")
-    if not os.path.exists(capture):
-        pytest.skip(f"staged capture {capture} missing")
+    capture = capture_path(doc["capture"])
     out = os.path.join(str(tmp_path), name)
-    env = dict(os.environ, RT_STATS="1")
-    env.update(env_extra or {})
-    opts = [o for o in doc["options"].split() if o not in ("-v", "-v3")] + ["-v"]
-    r = subprocess.run([exe] + opts + [f"-outf={out}", capture], capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "FATAL" not in r.stdout
+    stdout = run_binary(exe, doc["options"], capture, out, tmp_path, env_extra)
     for fname, sha in doc["reference_outputs"].items():
         made = os.path.join(str(tmp_path), fname)
         assert os.path.exists(made), f"{fname} was not written"
@@ -44,7 +80,23 @@ def run_shim(exe, name, tmp_path, env_extra=None):
         gold = os.path.join(GOLDEN, fname)
         if os.path.exists(gold):
             assert data == open(gold, "rb").read()
-    return r.stdout
+    return stdout
+
+
+def run_full(exe, label, tmp_path, env_extra=None):
+    """the WHOLE capture with the command line of full_outputs.json[label]; every .tap/.bin must have the recorded SHA-256"""
+    doc = FULL[label]
+    capture = capture_path(doc["capture"], full=True)
+    out = os.path.join(str(tmp_path), doc["capture"])
+    stdout = run_binary(exe, doc["options"], capture, out, tmp_path, env_extra)
+    assert doc["outputs"]
+    for fname, want in doc["outputs"].items():
+        made = os.path.join(str(tmp_path), fname)
+        assert os.path.exists(made), f"{fname} was not written"
+        data = open(made, "rb").read()
+        assert len(data) == want["bytes"] and hashlib.sha256(data).hexdigest() == want["sha256"], \
+            f"{fname} differs from the reference{'-held golden' if want['reference_held_golden'] else ''} ({len(data)} vs {want['bytes']} bytes)"
+    return stdout
 
 
 @pytest.mark.parametrize("name", ALL_FIXTURES)
@@ -52,11 +104,35 @@ def test_shim_on_oracle_backend_writes_reference_output(name, tmp_path):
     run_shim(ORACLE_SHIM, name, tmp_path)
 
 
+@pytest.mark.parametrize("label", sorted(FULL))
+def test_shim_on_oracle_backend_whole_capture_matches_reference_golden(label, tmp_path):
+    """the replay logic on the WHOLE captures (later blocks, later AGC states, the real end of tape), CPU oracle behind the C-ABI"""
+    run_full(ORACLE_SHIM, label, tmp_path)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ALL_FIXTURES)
 def test_readtape_b200_writes_reference_output(name, tmp_path):
     out = run_shim(CUDA_SHIM, name, tmp_path)
     assert "cuda-sm100a" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("label", sorted(FULL))
+def test_readtape_b200_whole_capture_matches_reference_golden(label, tmp_path):
+    """the product on the WHOLE bundled captures against the reference-held goldens (all 12 .tap/.bin of
+    examples/*/expected_results) and BASELINE config 1's command line; also records how many block decodes the
+    speculative whole-tape scan served"""
+    out = run_full(CUDA_SHIM, label, tmp_path)
+    assert "cuda-sm100a" in out
+    st = shim_stats(out)
+    assert st is not None, out[-1500:]
+    record_stats(label, st)
+    doc = FULL[label]
+    if "-whirlwind" in doc["options"]:
+        return                               # Whirlwind: the detector state persists across blocks, no speculative units
+    decodes = st["hits"] + st["misses"]          # a restart is a hit whose unit ended before the block did
+    assert decodes > 0 and st["hits"] - st["restarts"] >= MIN_HIT_RATE * decodes, f"{label}: {st}"
 
 
 @pytest.mark.gpu
@@ -68,7 +144,5 @@ def test_readtape_b200_exact_scan_only(name, tmp_path):
 @pytest.mark.gpu
 def test_readtape_b200_uses_the_speculative_scan(tmp_path):
     out = run_shim(CUDA_SHIM, "Microdata_20blks.nm_tap", tmp_path)
-    line = [l for l in out.splitlines() if "speculative hits" in l]
-    assert line, out[-1500:]
-    hits = int(line[-1].split("events,")[1].split("speculative hits")[0])
-    assert hits >= 15, line[-1]
+    st = shim_stats(out)
+    assert st is not None and st["hits"] >= 15, out[-1500:]
