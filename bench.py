@@ -403,7 +403,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * elapsed / K,
-            "device_ms_per_step": ms_ingest + ms_units + ms_scan,      # CUDA events on the library's own stream, summed over the step's kernels "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "device_ms_per_step": ms_ingest + ms_units + ms_scan,      # CUDA events on the library's own stream, summed over the step's kernels
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(rows), "l2": "inputs (rows*18 B per step) are far larger than the 126 MB L2",
                        "units_per_tape": units, "events_per_tape": events,
