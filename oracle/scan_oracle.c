@@ -8,9 +8,9 @@
  *
  * PARITY PINS: this restatement is checked event-for-event (row, track, polarity, t_event,
  * v_top, v_bot, agc_gain -- bit-exact) against logs dumped from the unmodified reference by
- * oracle/evdump_shim.c on the reference's bundled examples (tests/test_oracle_pins.py, and the
+ * oracle/evdump_shim.c on the reference's bundled examples (tests/test_oracle_golden.py, and the
  * committed digests in tests/golden/).  The reference itself reproduces all of its golden
- * .tap/.bin files here (tests/golden/README.md).
+ * .tap/.bin files here (tests/golden/reference_goldens.json, tests/golden/full_outputs.json).
  *
  * What is restated, and where it lives in the reference:
  *   int16 -> volts, invert, differentiate     readtape.c:1418-1422, 1383-1394

@@ -42,7 +42,10 @@ extern FILE *inf;
 extern bool tbin_file, invert_data, do_differentiate, find_zeros, doing_density_detection, doing_deskew;
 extern struct tbin_hdr_t tbin_hdr;
 extern struct tbin_dat_t tbin_dat;
-extern int nheads, samples_per_bit, subsample, head_to_trk[MAXTRKS];
+extern int nheads, samples_per_bit, subsample, head_to_trk[MAXTRKS], trk_to_head[MAXTRKS];
+extern bool set_ntrks_from_order;
+extern char track_order_string[MAXTRKS + 1];
+extern char *wwtracktype_names[WWTRK_NUMTYPES];
 extern long long lines_in, numsamples;
 extern double torigin;
 void force_end_of_block(void);                         /* readtape.c:1378 */
@@ -138,7 +141,8 @@ static void open_tape(void) {
    S.nrows = rt_nrows(S.tape);
    S.use_bulk = !(getenv("RT_NO_BULK") && atoi(getenv("RT_NO_BULK")));
    S.opened = 1;
-   if (!quiet) rlog("  B200 scan: %s rows x %d heads resident on the GPU (%s)\n", longlongcommas((long long)S.nrows), nheads, rt_backend()); }
+   /* extra log lines only on request: without RT_STATS the .log is line for line the reference's */
+   if (!quiet && getenv("RT_STATS")) rlog("  B200 scan: %s rows x %d heads resident on the GPU (%s)\n", longlongcommas((long long)S.nrows), nheads, rt_backend()); }
 
 /* ---- event sources ------------------------------------------------------------------------------ */
 struct evsrc {
@@ -171,6 +175,20 @@ static void exact_start(struct evsrc *src, const rt_scan_cfg *cfg, int reset_kin
    memset(src, 0, sizeof *src); src->exact = 1;
    exact_more(src); }
 
+/* diagnostics (RT_STATS=2): why no speculative unit could be proven equivalent to a fresh reset at `row` */
+static void say_miss(rt_bulk *bulk, uint64_t row) {
+   static rt_unit_info ui;
+   if (rt_bulk_unit_info(bulk, 0, row, &ui) != RT_OK) { rlog("  B200 scan: miss at row %llu: no unit\n", (unsigned long long)row); return; }
+   rlog("  B200 scan: miss at row %llu: unit %llu of %llu [%llu, %llu)\n", (unsigned long long)row, (unsigned long long)ui.unit_index,
+        (unsigned long long)ui.nunits, (unsigned long long)ui.row0, (unsigned long long)ui.row_end);
+   for (uint32_t k = 0; k < ui.ntrks; ++k) {
+      const int late = ui.sync_row[k] != UINT64_MAX && ui.sync_row[k] >= ui.need_sync_row[k] && (ui.last_loud_row[k] == UINT64_MAX || ui.last_loud_row[k] < row);
+      const int early = ui.sync_early[k] != UINT64_MAX && ui.sync_early[k] >= ui.need_sync_row[k] && (ui.loud_early[k] == UINT64_MAX || ui.loud_early[k] < row);
+      if (late || early) continue;
+      rlog("     trk %u: first event %lld, sync %lld (loud %lld), early sync %lld (loud %lld), need %lld, failed %u, events %u\n", k,
+           (long long)ui.first_event_row[k], (long long)ui.sync_row[k], (long long)ui.last_loud_row[k], (long long)ui.sync_early[k],
+           (long long)ui.loud_early[k], (long long)ui.need_sync_row[k], ui.failed[k], ui.nevents[k]); } }
+
 static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    int ps = block.parmset;
    if (!S.use_bulk || mode == WW || doing_density_detection || doing_deskew) return 0;   /* prefix passes: exact scan */
@@ -184,7 +202,10 @@ static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    uint64_t valid = 0;
    memset(src, 0, sizeof *src);
    int rc = rt_bulk_lookup(S.bulk[ps].bulk, 0, row, &src->ev, &src->n, &valid);
-   if (rc == RT_MISS) { ++S.n_bulk_miss; return 0; }
+   if (rc == RT_MISS) {
+      ++S.n_bulk_miss;
+      if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2) say_miss(S.bulk[ps].bulk, row);
+      return 0; }
    if (rc) rtfatal("rt_bulk_lookup", rc);
    src->valid_end = row + valid;
    if (src->valid_end >= S.nrows) src->valid_end = UINT64_MAX;
@@ -223,20 +244,48 @@ static uint64_t first_row_delta_gt(double t0, double thr, uint64_t lo) {
 /* ---- the block decode ------------------------------------------------------------------------------ */
 struct rowstate { uint64_t init_row[MAXTRKS]; };
 
+/* the "execution-time configuration" block the reference logs before its first sample (readtape.c:1460-1499): the log must not
+   drift, so every line it prints is printed here too, from the same globals, in the same order */
 static void say_configuration(void) {
    if (quiet || S.said_config) return;
    S.said_config = 1;
+   const int spb = bpi != 0 ? (int)(1 / (bpi * ips * sample_deltat)) : 0;
    rlog("\nexecution-time configuration:\n");
+   if (set_ntrks_from_order) rlog("  we set ntrks=%d as implied by the -order string \"%s\"\n", ntrks, track_order_string);
    rlog("  %d track %s encoding, %s parity, %d BPI at %d IPS", ntrks, modename(),
         mode == WW ? "no" : expected_parity ? "odd" : "even", (int)bpi, (int)ips);
    if (bpi != 0) rlog(" (%.2f usec/bit)", 1e6f / (bpi * ips));
    rlog("\n  first sample is at time %.8lf seconds on the tape\n", timenow);
+   if (subsample > 1) rlog("  subsampling every %d samples\n", subsample);
+   if (invert_data) rlog("  inverting the data polarity\n");
+   if (reverse_tape) rlog("  reversing the bit pairs in each word, and the words in each block\n");
    rlog("  sampling rate is %s Hz (%.2f usec)", intcommas((int)(1.0 / sample_deltat)), sample_deltat * 1e6);
-   if (bpi != 0) rlog(", or about %d samples per bit", (int)(1 / (bpi * ips * sample_deltat)));
+   if (bpi != 0) rlog(", or about %d samples per bit", spb);
    rlog("\n");
+   if (bpi != 0 && spb > 100) rlog("  ---> Warning: excessive samples per bit; consider using the -subsample option\n");
    if (find_zeros) rlog("  will look for zero crossings, not peaks\n");
    else rlog("  peak detection window width is %d samples (%.2f usec)\n", pkww_width, pkww_width * sample_deltat * 1e6);
-   rlog("  per-sample scan: %s through the rt_scan C-ABI\n\n", rt_backend()); }
+   if (mode == WW) {
+      rlog("  Whirlwind data has %d tracks from %d data heads assigned as follows:\n", ntrks, nheads);
+      for (int ty = 0; ty < WWTRK_NUMTYPES; ++ty) {
+         const int trk = ww_type_to_trk[ty];
+         if (trk == -1) rlog("              there is no  ");
+         else rlog("    track %d, head %d is the ", trk, trk_to_head[trk]);
+         rlog(" %s, '%c'\n", wwtracktype_names[ty], WWTRKTYPE_SYMBOLS[ty]); }
+      for (int h = 0; h < nheads; ++h) if (head_to_trk[h] == WWHEAD_IGNORE) rlog("             head %d is unused\n", h);
+      const char *dir = flux_direction_requested == FLUX_AUTO ? "will be automatically determined for each block"
+                        : flux_direction_requested == FLUX_POS ? "is expected to be positive"
+                        : flux_direction_requested == FLUX_NEG ? "is expected to be negative" : "--- internal error  ---";
+      rlog("  the initial peak polarity for each flux change %s\n", dir); }
+   else {
+      rlog("  input data order: ");
+      for (int i = 0; i < ntrks; ++i) {
+         const int k = head_to_trk[i];
+         if (k == ntrks - 1) rlog("p"); else rlog("%d", k);
+         if (k == 0) rlog("(msb)");
+         if (k == ntrks - 2) rlog("(lsb)"); }
+      rlog("\n"); }
+   rlog("\n"); }
 
 /* returns the last row consumed (the row after which the reference's readblock() returns); *endfile set at EOF */
 static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, struct evsrc *src, uint64_t *last_row, bool *endfile) {
@@ -384,6 +433,8 @@ bool readblock(bool retry) {
       /* the speculative unit ended before the block did: start over with the exact scan */
       assert(from_bulk, "B200 scan: exact scan asked for a restart");
       ++S.n_restarts;
+      if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2)
+         rlog("  B200 scan: restart: the unit found for row %llu ends at row %llu, inside the block\n", (unsigned long long)row0, (unsigned long long)src.valid_end);
       interblock_counter = 0;
       init_trackstate();                                           /* the reference's own reset, again */
       S.pending_reset = RT_RESET_NONE;
