@@ -35,7 +35,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-from readtape_b200 import abi, parmsets, synth, tbin  # noqa: E402
+from readtape_b200 import abi, parmsets, synth, tbin, verify  # noqa: E402
 
 FULL_ROWS = 1_111_111_111          # 10e9 track-samples / 9 tracks
 METRIC = "track-samples/s, 9-track 781 kHz NRZI TBIN scan"
@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--workload", default="nrzi", choices=["nrzi", "gcr"],
                     help="nrzi: BASELINE config 2 (the headline line); gcr: config 4, GCR-density tape x 5 parameter sets sharded over the GPUs")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-scale check of the scan's events against the oracle (outside the timed regions)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -348,6 +349,22 @@ def main():
         lib.L.rt_host_free(hptr)
         rows = rows_full
 
+    # ---- full-scale verification (outside the timed regions): every tile of the periodic tape must carry the same events, every
+    #      event time must be the reference's expression bit for bit, and one tile must equal the CPU oracle's events ----
+    verified = None
+    if not args.no_verify:
+        tape.clear()
+        tape.attach_device(dev.data_ptr(), rows)
+        bulk = tape.bulk_scan([cfg])
+        verified = verify.verify_periodic(abi.load_oracle(), bulk, desc, cfg, tile, rows)
+        bulk.free()
+        if not verified["ok"]:
+            print(f"rank {rank}: VERIFICATION FAILED: {verified}", file=sys.stderr)
+        if dist is not None:
+            okt = torch.tensor([1 if verified["ok"] else 0], dtype=torch.int64, device="cuda")
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            verified["ok_all_ranks"] = bool(okt.item())
+
     # ---- result gather over NCCL: per-rank event counts (the only inter-GPU traffic of this path) ----
     all_events = [events]
     if dist is not None:
@@ -409,7 +426,7 @@ def main():
             "config": {"workload": workload_name(rows), "l2": "inputs (rows*18 B per step) are far larger than the 126 MB L2",
                        "units_per_tape": units, "events_per_tape": events,
                        "rows_walked_one_by_one_frac": int(stats[-1].rows_scanned) / float(tsamp), "super_tile_sha256": synth.tile_sha256(tile)[:16],
-                       "parallelism": f"{world} x independent tapes" if world > 1 else "1 GPU"},
+                       "parallelism": f"{world} x independent tapes" if world > 1 else "1 GPU", "verified": verified},
             "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms, "other_kernels": others},
@@ -420,6 +437,8 @@ def main():
     tape.close()
     if dist is not None:
         dist.destroy_process_group()
+    if verified is not None and not verified.get("ok_all_ranks", verified["ok"]):
+        sys.exit(1)                                   # a fast scan whose events differ from the reference's is not a result
 
 
 if __name__ == "__main__":

@@ -199,7 +199,8 @@ int  rt_bulk_lookup(rt_bulk *bulk, uint32_t cfg_index, uint64_t start_row,
                     const rt_event **events, uint64_t *nevents, uint64_t *valid_rows);
 
 /* Diagnostics: the unit rt_bulk_lookup() would consult for `start_row` and the per-track proof data
- * (~0 means "none").  A unit covers start_row iff start_row == row0, or start_row >= row0 - 256 and for every
+ * (~0 means "none").  A unit covers start_row iff start_row == row0, or start_row >= row0 - P (P = the quiet pre-scan
+ * length, 256 .. 4096 rows depending on the sample rate and density) and for every
  * track  sync_row >= need_sync_row  and  (last_loud_row is none or < start_row), or the same with
  * (sync_early, loud_early).  rt_bulk_lookup() tries this unit and the next one. */
 typedef struct rt_unit_info {
@@ -231,6 +232,19 @@ typedef struct rt_bulk_stats {
    double   ms_masks;        /* device time: candidate-mask pass of the two-pass peak scan (a part of ms_scan; 0 if not used) */
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);
+
+/* Verification at scale (product library only; must be called BEFORE rt_bulk_fetch()/rt_bulk_lookup(), while the results are
+ * still in device memory).  For a tape that repeats every `period_rows` rows, every block decode starts from a fresh reset, so
+ * the events of tile k are those of tile 0 shifted by k * period_rows rows.  For tile i < ntiles: events[i] = number of events
+ * with i * period_rows <= row < (i+1) * period_rows (each counted once, by the unit that owns its row), digest[i] = the sum
+ * (mod 2^64) over those events of
+ *      mix(mix(mix(k0) ^ k1) ^ k2),   mix = the splitmix64 finaliser,
+ *      k0 = (row - i*period_rows) | trk << 40 | kind << 48 | (hs & 0xfff) << 52,  k1 = bits(v_top) | bits(v_bot) << 32,  k2 = bits(agc_gain),
+ *      hs = round((row time - t_event) / (sample period / 2)).
+ * *bad_times = events whose double-precision t_event is not bit-identical to the reference's expression for (row, hs):
+ * decoder.c:732 for the peak detector, the row time of row - hs/2 for the zero-crossing detector. */
+int  rt_bulk_tile_digest(rt_bulk *bulk, uint32_t cfg_index, uint64_t period_rows, uint64_t ntiles,
+                         uint64_t *events, uint64_t *digest, uint64_t *bad_times);
 void rt_bulk_free(rt_bulk *bulk);
 
 /* Diagnostics / tests: the two bit planes the two-pass peak scan derives from the samples (pure functions of the window of

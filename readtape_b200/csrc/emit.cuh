@@ -19,9 +19,10 @@ struct FlatEmit {                 /* per-track flat buffer; counts past capacity
 
 struct PoolEmit {                 /* chained fixed-size chunks from a global pool */
    rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
-   uint32_t first_chunk, cur_chunk, n; uint64_t first_row; uint8_t trk;
+   uint32_t first_chunk, cur_chunk, n; uint64_t first_row; uint8_t trk; uint64_t last_row;
    __device__ void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
       if (n == 0) first_row = row;
+      last_row = row;
       uint32_t slot = n % RT_EVC;
       if (slot == 0) {
          uint32_t c = atomicAdd(cursor, 1u);          /* counts past capacity: the host regrows and reruns */

@@ -55,9 +55,9 @@ k_units_scan(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
       TrkState t; SkewState s;
       reset_full(c, t, s, trk, ud.row0, row_time(c, ud.row0) == 0.0);
       const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
-      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk, RT_NOROW};
       /* proof data, collected only before the first event (DESIGN.md "unit equivalence"):
-           last_loud     last loud row (QuietTracker) seen so far, starting RT_PRESCAN_ROWS before the unit
+           last_loud     last loud row (QuietTracker) seen so far, starting DevCfg::prescan_rows before the unit
            sync_row      LAST row before the first event at which this scan's state is canonical and the
                          row is not loud; loud_at_sync = last_loud at that moment
            sync_first    FIRST such row with nothing loud since the unit start (used to chain units)
@@ -65,7 +65,7 @@ k_units_scan(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
          left a FULL window (both scans rescan there, which also refreshes the lazily kept minimum);
          for the zero-crossing detectors any row once v_prev and the deskew FIFO are warm. */
       QuietTracker qt; qt.init(c, trk, quiet_thr, quiet_thr_lsb);
-      const uint64_t pre0 = ud.row0 > RT_PRESCAN_ROWS ? ud.row0 - RT_PRESCAN_ROWS : 0;
+      const uint64_t pre0 = ud.row0 > (uint64_t)c.prescan_rows ? ud.row0 - (uint64_t)c.prescan_rows : 0;
       for (uint64_t j = pre0; j < ud.row0; ++j) qt.feed(c, plane, j, raw_at(c, plane, j));
       const uint64_t quiet_from = qt.last_loud == RT_NOROW ? pre0 : qt.last_loud + 1;
       uint64_t sync_row = RT_NOROW, loud_at_sync = RT_NOROW, sync_first = RT_NOROW, sync_early = RT_NOROW, loud_early = RT_NOROW;
@@ -86,6 +86,7 @@ k_units_scan(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
       TrkMeta m;
       m.first_event_row = em.first_row; m.sync_row = sync_row; m.last_loud_row = loud_at_sync; m.sync_first = sync_first; m.quiet_from = quiet_from; m.sync_early = sync_early; m.loud_early = loud_early;
       m.first_chunk = em.first_chunk; m.nevents = em.n; m.failed = t.failed; m.pad = 0;
+      m.last_event_row = em.last_row; m.quiet_tail_from = RT_NOROW;
       meta[f] = m;
       atomicAdd(&rows_scanned[0], (unsigned long long)(ud.row_end - ud.row0));
       if (em.n) atomicAdd(&rows_scanned[1], (unsigned long long)em.n); } }

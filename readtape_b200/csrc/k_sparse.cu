@@ -94,9 +94,10 @@ struct SparseJobs {
          TrkMeta m;
          m.first_event_row = m.sync_row = m.last_loud_row = m.sync_early = m.loud_early = m.sync_first = RT_NOROW;
          m.quiet_from = ud.row0; m.first_chunk = RT_NOCHUNK; m.nevents = 0; m.failed = 3; m.pad = 0;
+         m.last_event_row = m.quiet_tail_from = RT_NOROW;
          meta[cur] = m;
          return false; }
-      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk};
+      PoolEmit em{pool, chunk_next, cursor, cap_chunks, RT_NOCHUNK, RT_NOCHUNK, 0, RT_NOROW, (uint8_t)trk, RT_NOROW};
       us.begin(c.planes + (size_t)trk * c.plane_stride, ud.row0, ud.row_end, trk, em, quiet_thr_lsb);
       return true; }
    template <class Scan>

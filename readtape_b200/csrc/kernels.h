@@ -50,4 +50,8 @@ cudaError_t launch_peak_masks(const DevCfg &c, uint64_t row_lo, uint64_t row_hi,
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s);
+/* k_digest.cu: per-tile event counts and order-independent digests of a finished whole-tape scan (verification at scale) */
+cudaError_t launch_tile_digest(const DevCfg &c, const UnitDesc *units, uint32_t nunits, const TrkMeta *meta, const rt_event *pool,
+                               const uint32_t *chunk_next, uint64_t period, uint64_t ntiles, unsigned long long *counts,
+                               unsigned long long *digests, unsigned long long *bad, int sms, cudaStream_t s);
 #endif

@@ -889,6 +889,28 @@ extern "C" int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, 
    if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "rt_peak_masks: %s", cudaGetErrorString(e));
    return RT_OK; }
 
+extern "C" int rt_bulk_tile_digest(rt_bulk *b, uint32_t ci, uint64_t period, uint64_t ntiles, uint64_t *events, uint64_t *digest, uint64_t *bad_times) {
+   if (!b || ci >= b->cfgs.size() || !period || !ntiles || !events || !digest) return set_err(RT_ERR_ARG, "rt_bulk_tile_digest: bad argument");
+   if (b->fetched || !b->d_pool) return set_err(RT_ERR_STATE, "rt_bulk_tile_digest: the results have left the device (call it before rt_bulk_fetch / rt_bulk_lookup)");
+   rt_tape *t = b->tape; BulkCfg &bc = b->cfgs[ci];
+   CU(cudaSetDevice(t->device));
+   memset(events, 0, ntiles * 8); memset(digest, 0, ntiles * 8); if (bad_times) *bad_times = 0;
+   if (!bc.nunits) return RT_OK;
+   unsigned long long *d = nullptr;
+   CU(cudaMallocAsync(&d, (2 * ntiles + 1) * 8, t->stream));
+   cudaError_t e = cudaMemsetAsync(d, 0, (2 * ntiles + 1) * 8, t->stream);
+   if (e == cudaSuccess) e = launch_tile_digest(bc.dc, bc.d_units, bc.nunits, bc.d_meta, b->d_pool, b->d_chunk_next, period, ntiles, d, d + ntiles, d + 2 * ntiles, t->sms, t->stream);
+   ++t->launches;
+   unsigned long long bad = 0;
+   if (e == cudaSuccess) e = cudaMemcpyAsync(events, d, ntiles * 8, cudaMemcpyDeviceToHost, t->stream);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(digest, d + ntiles, ntiles * 8, cudaMemcpyDeviceToHost, t->stream);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d + 2 * ntiles, 8, cudaMemcpyDeviceToHost, t->stream);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+   cudaFreeAsync(d, t->stream);
+   if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "rt_bulk_tile_digest: %s", cudaGetErrorString(e));
+   if (bad_times) *bad_times = bad;
+   return RT_OK; }
+
 extern "C" int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *out) {
    if (!b || !out) return set_err(RT_ERR_ARG, "rt_bulk_get_stats: null argument");
    *out = b->stats; return RT_OK; }
@@ -933,7 +955,7 @@ static bool unit_covers(const BulkCfg &bc, const rt_tape_desc &desc, uint32_t nt
    if (start_row >= u.row_end) return false;
    for (uint32_t k = 0; k < nt; ++k) if (m[k].failed) return false;
    if (start_row == u.row0) return true;                        /* the very same reset: trivially identical */
-   const uint64_t pre0 = u.row0 > RT_PRESCAN_ROWS ? u.row0 - RT_PRESCAN_ROWS : 0;
+   const uint64_t pre0 = u.row0 > (uint64_t)bc.dc.prescan_rows ? u.row0 - (uint64_t)bc.dc.prescan_rows : 0;
    if (start_row < pre0) return false;                          /* quietness before pre0 was never examined */
    const bool tz = rt_row_time(&desc, start_row) == 0.0;
    for (uint32_t k = 0; k < nt; ++k) {
@@ -943,6 +965,18 @@ static bool unit_covers(const BulkCfg &bc, const rt_tape_desc &desc, uint32_t nt
       const bool late = m[k].sync_row != RT_NOROW && m[k].sync_row >= need && (m[k].last_loud_row == RT_NOROW || m[k].last_loud_row < start_row);
       const bool early = m[k].sync_early != RT_NOROW && m[k].sync_early >= need && (m[k].loud_early == RT_NOROW || m[k].loud_early < start_row);
       if (!late && !early) return false; }
+   return true; }
+
+/* The tail rule: start_row lies behind every event of unit `ui`, and no row of [start_row, row_end) is loud on any track: a fresh
+   scan from start_row stays in default state (no event, so no feedback) and cannot fire before row_end either. */
+static bool unit_tail_covers(const BulkCfg &bc, uint32_t nt, size_t ui, uint64_t start_row) {
+   const UnitDesc &u = bc.units[ui];
+   const TrkMeta *m = &bc.meta[ui * nt];
+   if (start_row < u.row0 || start_row >= u.row_end) return false;
+   for (uint32_t k = 0; k < nt; ++k) {
+      if (m[k].failed) return false;
+      if (m[k].nevents && m[k].last_event_row >= start_row) return false;
+      if (m[k].quiet_tail_from == RT_NOROW || m[k].quiet_tail_from > start_row) return false; }
    return true; }
 
 extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event **events, uint64_t *nevents, uint64_t *valid_rows) {
@@ -957,6 +991,12 @@ extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const
    while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (bc.units[mid].row0 <= start_row) lo = mid; else hi = mid; }
    if (!unit_covers(bc, b->tape->desc, nt, lo, start_row)) {
       if (lo + 1 < bc.units.size() && unit_covers(bc, b->tape->desc, nt, lo + 1, start_row)) ++lo;
+      else if (unit_tail_covers(bc, nt, lo, start_row)) {        /* nothing up to the end of this unit (typically: the end of the tape) */
+         b->result.clear();
+         if (events) *events = b->result.data();
+         if (nevents) *nevents = 0;
+         if (valid_rows) *valid_rows = bc.units[lo].row_end - start_row;
+         return RT_OK; }
       else return RT_MISS; }
    const TrkMeta *m = &bc.meta[lo * nt];
    /* Chaining: while the unit holds no event at all, the reference's scan passes through it unchanged; it is

@@ -18,7 +18,8 @@
 #define RT_EVC             32      /* events per pool chunk                                     */
 #define RT_NOCHUNK         0xffffffffu
 #define RT_NOROW           0xffffffffffffffffull
-#define RT_PRESCAN_ROWS     256     /* rows before a unit start examined for quietness */
+#define RT_PRESCAN_MIN      256     /* DevCfg::prescan_rows: rows before a unit start examined for quietness (at least / at most) */
+#define RT_PRESCAN_MAX      4096
 
 /* compile-time constants of the reference the scan needs (src/decoder.h) */
 #define RT_PKWW_PEAKHEIGHT 4.0f    /* :133 */
@@ -67,6 +68,10 @@ struct DevCfg {
       well above its default-state value, and the sparse scan then follows the plane with fewer candidates */
    const uint32_t *m_cand2;
    int32_t  T1[RT_MAXTRKS];
+   /* rows in front of a unit's first row that every scan examines for quietness: the reference starts looking for the next block
+      where the previous one ended plus its inter-block skip, which on real tapes lies up to an inter-block-gap time in front of
+      the first all-quiet granule the unit finder cuts at (decaying noise behind a block) */
+   int32_t  prescan_rows;
 };
 
 /* Per-track detector + feedback state: the device mirror of the parts of struct trkstate_t
@@ -111,6 +116,10 @@ struct TrkMeta {
    uint64_t loud_early;           /* last loud row before sync_early (from the pre-scan), RT_NOROW if none */
    uint64_t sync_first;           /* FIRST such row, with the unit quiet from its start up to it (used to chain units), RT_NOROW if none */
    uint64_t quiet_from;           /* earliest row q <= row0 such that no row in [q, row0] is loud: a reset at any row in [q, row0) is covered too */
+   /* the tail rule (rt_bulk_lookup): a fresh reset at a row s behind the unit's last event, with no loud row in [s, row_end),
+      finds nothing up to row_end either (a scan without events stays in default state, and "not loud" proves it cannot fire) */
+   uint64_t last_event_row;       /* RT_NOROW if the track had no event                      */
+   uint64_t quiet_tail_from;      /* earliest row q such that no row in [q, row_end) is loud; RT_NOROW: not examined (then the rule is off) */
    uint32_t first_chunk;          /* head of the chunk chain in the event pool               */
    uint32_t nevents;
    uint32_t failed;               /* 2: the reference would have called fatal() (peak not found) */

@@ -291,7 +291,7 @@ struct UnitScan {
       sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false;
       const int lead = (int)io > delay ? (int)io : delay;
       sf_from = (uint32_t)(lead + w + 1);
-      const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
+      const int32_t npre = row0 > (uint64_t)c.prescan_rows ? c.prescan_rows : (int32_t)row0;
       for (int32_t o = -npre; o < 0; ++o) feed(o, (int)plane[(int64_t)row0 + o]);
       quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
       for (uint32_t o = 0; o <= io && o < end; ++o) track(o, sample(o), false);      /* decoder.c:855-861: not looked at yet */
@@ -450,7 +450,8 @@ struct UnitScan {
       meta.quiet_from = quiet_from;
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
-      meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = nskipped; } };   /* pad: rows jumped over (diagnostics) */
+      meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = nskipped;
+      meta.last_event_row = em.last_row; meta.quiet_tail_from = RT_NOROW; } };   /* pad: rows jumped over (diagnostics) */
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through a list of (unit, track) jobs.  `Jobs` provides
  *   bool next(UnitScan&)   start the lane's next job, false if there is none (called by all lanes of the warp together)

@@ -189,6 +189,28 @@ struct SparseScan {
       for (int32_t q = -npre; q < pure_lo && q < 0; ++q) feed(q, (int)plane[(int64_t)row0 + q]);
       if (smn < qmin) qmin = smn; if (smx > qmax) qmax = smx; }
 
+   /* The tail rule's proof datum (TrkMeta::quiet_tail_from): the earliest row q >= row0 + lo such that no row of [q, row_end) is
+      loud, with loud(j) := the raw samples of rows [j - qL + 1, j] span >= qthr (the definition itself, independent of where any
+      tracker started).  Walks backwards from the unit's end, whole quiet granules at a time, and stops at the first loud row. */
+   RT_FHD uint64_t quiet_tail(uint32_t lo) const {
+      int64_t oo = (int64_t)end - 1;
+      while (oo >= (int64_t)lo) {
+         const int64_t to = (int64_t)row0 + oo;
+         if (gm && (to & (RT_GRAN - 1)) == RT_GRAN - 1 && oo - (RT_GRAN - 1) >= (int64_t)lo) {
+            int64_t gfirst = (to - (RT_GRAN - 1) - qL + 1); gfirst = gfirst < 0 ? 0 : gfirst / RT_GRAN;
+            const int64_t glast = to / RT_GRAN;
+            int gmn = 32767, gmx = -32768;
+            for (int64_t g = gfirst; g <= glast; ++g) {
+               const uint32_t v = gm[g];
+               const int lmn = (int)(int16_t)(uint16_t)(v & 0xffffu), lmx = (int)(int16_t)(uint16_t)(v >> 16);
+               if (lmn < gmn) gmn = lmn; if (lmx > gmx) gmx = lmx; }
+            if (gmx - gmn < qthr) { oo -= RT_GRAN; continue; } }      /* no row of granule glast can be loud */
+         const int64_t from = to - qL + 1;
+         const minmax r = span_minmax(plane, from < 0 ? 0 : from, to, (int)plane[to]);
+         if (r.mx - r.mn >= qthr) return row0 + (uint64_t)oo + 1u;
+         --oo; }
+      return row0 + lo; }
+
    /* process_*_transition, decoder.c:560-609 */
    RT_FHD void transition(bool top, uint32_t oo) {
       const double t_ev = top ? t.t_top : t.t_bot;
@@ -241,7 +263,7 @@ struct SparseScan {
       sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false; pre = true; pre_end = 0;
       const int lead = (int)io > delay ? (int)io : delay;
       sf_from = (uint32_t)(lead + w + 1);
-      const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
+      const int32_t npre = row0 > (uint64_t)c.prescan_rows ? c.prescan_rows : (int32_t)row0;
       prescan(npre);
       quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
       for (uint32_t oo = 0; oo <= io && oo < end; ++oo) track(oo, false);              /* decoder.c:855-861: not looked at yet */
@@ -451,6 +473,8 @@ struct SparseScan {
       meta.quiet_from = quiet_from;
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
+      meta.last_event_row = em.last_row;
+      meta.quiet_tail_from = qthr > 0 ? quiet_tail(end > (uint32_t)c.prescan_rows ? end - (uint32_t)c.prescan_rows : 0u) : RT_NOROW;
       meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = end > ndense ? end - ndense : 0; } };   /* pad: rows not walked (diagnostics) */
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through (unit, track) jobs.  `Jobs` provides

@@ -170,7 +170,7 @@ struct ZcScan {
       sync_row = loud_at_sync = sync_first = sync_early = loud_early = OFF_NONE; early_frozen = false;
       const int lead = (int)io > delay ? (int)io : delay;
       own_fill = (uint32_t)(lead + 2); sf_from = own_fill;
-      const int32_t npre = row0 > RT_PRESCAN_ROWS ? (int32_t)RT_PRESCAN_ROWS : (int32_t)row0;
+      const int32_t npre = row0 > (uint64_t)c.prescan_rows ? c.prescan_rows : (int32_t)row0;
       for (int32_t off = -npre; off < 0; ++off) { const int raw = (int)plane[(int64_t)row0 + off]; if (raw >= izc || raw <= -izc) loud_until(off + qL - 1); }
       quiet_from = ll == OFF_NONE ? row0 - (uint64_t)npre : (uint64_t)((int64_t)row0 + ll + 1);
       for (uint32_t off = 0; off <= io && off < end; ++off) track((int32_t)off, (int)plane[row0 + off]);     /* not looked at yet (decoder.c:855-861) */
@@ -224,6 +224,14 @@ struct ZcScan {
       meta.quiet_from = quiet_from;
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
+      meta.last_event_row = em.last_row;
+      {  /* the tail rule: the last sample beyond ZEROCROSS_PEAK keeps the rows up to qL - 1 behind it loud */
+         const uint32_t lo = end > (uint32_t)c.prescan_rows ? end - (uint32_t)c.prescan_rows : 0u;
+         int64_t scan_lo = (int64_t)lo - (qL - 1); if ((int64_t)row0 + scan_lo < 0) scan_lo = -(int64_t)row0;
+         int64_t r = (int64_t)end - 1;
+         for (; r >= scan_lo; --r) { const int x = (int)plane[(int64_t)row0 + r]; if (x >= izc || x <= -izc) break; }
+         const uint64_t q = r < scan_lo ? row0 + lo : (uint64_t)((int64_t)row0 + r + qL);
+         meta.quiet_tail_from = q > row0 + end ? row0 + end : q; }
       meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = 0; meta.pad = 0; } };
 
 }  // namespace rtfast

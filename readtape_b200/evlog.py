@@ -289,3 +289,33 @@ def load_fixture(path: str):
         s.sha256, s.nevents = sha, nev
         segs.append(s)
     return doc, segs
+
+
+# ---- the tile digest of rt_bulk_tile_digest (include/rt_scan.h), restated with numpy for the checker side ----------------
+def _mix64(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(30); x *= np.uint64(0xbf58476d1ce4e5b9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94d049bb133111eb)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def tile_digest(ev: np.ndarray, tile_index: int, period_rows: int, tstart_ns: int, tdelta_ns: int):
+    """(count, digest) of the events `ev` (abi.EVENT_DTYPE or CANON records) that lie in tile `tile_index`"""
+    lo = tile_index * period_rows
+    e = ev[(ev["row"] >= lo) & (ev["row"] < lo + period_rows)]
+    if len(e) == 0:
+        return 0, 0
+    ns = (np.uint64(tstart_ns) + e["row"].astype(np.uint64) * np.uint64(tdelta_ns)).astype(np.int64)
+    now = ns.astype(np.float64) / 1e9
+    sd = np.float64(np.float32(np.float32(tdelta_ns) / np.float32(1e9)))          # sample_deltat as the reference holds it (a float)
+    hsd = (now - e["t_event"]) / (sd * 0.5)
+    hs = np.where(hsd < 0, hsd - 0.5, hsd + 0.5).astype(np.int64)
+    k0 = (e["row"].astype(np.uint64) - np.uint64(lo)) | (e["trk"].astype(np.uint64) << np.uint64(40)) \
+        | (e["kind"].astype(np.uint64) << np.uint64(48)) | ((hs.astype(np.uint64) & np.uint64(0xfff)) << np.uint64(52))
+    k1 = e["v_top"].view("<u4").astype(np.uint64) | (e["v_bot"].view("<u4").astype(np.uint64) << np.uint64(32))
+    k2 = e["agc_gain"].view("<u4").astype(np.uint64)
+    h = _mix64(_mix64(_mix64(k0) ^ k1) ^ k2)
+    with np.errstate(over="ignore"):
+        return int(len(e)), int(np.sum(h, dtype=np.uint64))

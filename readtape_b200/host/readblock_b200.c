@@ -149,7 +149,11 @@ struct evsrc {
    const rt_event *ev; uint64_t n, at;      /* current batch */
    uint64_t valid_end;                      /* rows < valid_end are covered by what we hold */
    int exact;                               /* 1: S.ctx is running and can be continued */
+   /* what is needed to carry on with the exact scan when a speculative unit ends inside the block */
+   uint64_t row0; const rt_scan_cfg *cfg;
+   uint64_t taken; uint64_t last_row; int last_trk;   /* events handed out so far, and the last of them */
 };
+#define TAKE(src) do { (src)->last_row = (src)->ev[(src)->at].row; (src)->last_trk = (src)->ev[(src)->at].trk; ++(src)->at; ++(src)->taken; } while (0)
 
 static void ctx_prepare(const rt_scan_cfg *cfg) {
    int rc;
@@ -172,8 +176,34 @@ static void exact_start(struct evsrc *src, const rt_scan_cfg *cfg, int reset_kin
    int kind = reset_kind & 0xff;
    int rc = rt_scan_reset(S.ctx, kind, row); if (rc) rtfatal("rt_scan_reset", rc);
    if (reset_kind & 0x100) { rc = rt_scan_reset(S.ctx, RT_RESET_WW_PARTIAL, row); if (rc) rtfatal("rt_scan_reset", rc); }
-   memset(src, 0, sizeof *src); src->exact = 1;
+   memset(src, 0, sizeof *src); src->exact = 1; src->row0 = row; src->cfg = cfg;
    exact_more(src); }
+
+/* The speculative unit ended before the block did.  Its events ARE the events of a fresh reset at the block's first row (that is
+   what rt_bulk_lookup proved), so the exact scan from that row reproduces them one for one: it is started, the events already
+   replayed are skipped, and the replay carries on where it was -- nothing is replayed twice (peak statistics, log lines and the
+   handlers' one-shot warnings stay exactly the reference's). */
+static void continue_exact(struct evsrc *src) {
+   const uint64_t taken = src->taken, last_row = src->last_row; const int last_trk = src->last_trk;
+   const uint64_t row0 = src->row0; const rt_scan_cfg *cfg = src->cfg;
+   ++S.n_restarts;
+   if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2)
+      rlog("  B200 scan: the unit found for row %llu ends at row %llu, inside the block: exact scan from there on\n",
+           (unsigned long long)row0, (unsigned long long)src->valid_end);
+   exact_start(src, cfg, RT_RESET_FULL, row0);
+   uint64_t skip = taken;
+   while (skip) {
+      const uint64_t have = src->n - src->at;
+      if (have >= skip) {
+         src->at += skip; skip = 0;
+         const rt_event *e = &src->ev[src->at - 1];
+         if (e->row != last_row || e->trk != last_trk)
+            fatal("B200 scan: exact scan disagrees with the speculative unit at row %llu", (unsigned long long)last_row); }
+      else {
+         skip -= have; src->at = src->n;
+         if (src->valid_end == UINT64_MAX) fatal("B200 scan: exact scan ended before the speculative unit did");
+         exact_more(src); } }
+   src->taken = taken; src->last_row = last_row; src->last_trk = last_trk; }
 
 /* diagnostics (RT_STATS=2): why no speculative unit could be proven equivalent to a fresh reset at `row` */
 static void say_miss(rt_bulk *bulk, uint64_t row) {
@@ -200,7 +230,7 @@ static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
       if (rc) rtfatal("rt_bulk_scan", rc);
       S.bulk[ps].cfg = *cfg; S.bulk[ps].valid = 1; }
    uint64_t valid = 0;
-   memset(src, 0, sizeof *src);
+   memset(src, 0, sizeof *src); src->row0 = row; src->cfg = cfg;
    int rc = rt_bulk_lookup(S.bulk[ps].bulk, 0, row, &src->ev, &src->n, &valid);
    if (rc == RT_MISS) {
       ++S.n_bulk_miss;
@@ -213,12 +243,12 @@ static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    return 1; }
 
 /* the next event, or NULL if none is known below row `limit` (then rows < limit hold no event) */
-static const rt_event *peek_event(struct evsrc *src, uint64_t limit, int *need_restart) {
+static const rt_event *peek_event(struct evsrc *src, uint64_t limit) {
    for (;;) {
       if (src->at < src->n) return src->ev[src->at].row < limit ? &src->ev[src->at] : NULLP;
       if (src->valid_end == UINT64_MAX || src->valid_end >= limit) return NULLP;
       if (src->exact) exact_more(src);
-      else { *need_restart = 1; return NULLP; } } }
+      else continue_exact(src); } }
 
 /* ---- exact "first row at which process_sample() sees the condition" searches ----------------------- */
 /* smallest row r >= lo with  rowtime(r) > x  (monotone in r) */
@@ -288,9 +318,8 @@ static void say_configuration(void) {
    rlog("\n"); }
 
 /* returns the last row consumed (the row after which the reference's readblock() returns); *endfile set at EOF */
-static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, struct evsrc *src, uint64_t *last_row, bool *endfile) {
+static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, struct evsrc *src, uint64_t *last_row, bool *endfile) {
    struct rowstate rs;
-   int need_restart = 0;
    const uint64_t nrows = S.nrows;
    const int tz = rowtime(row0) == 0.0;
    /* (Q2) decoder.c:855-861: after a reset the tracks initialise one per row */
@@ -334,15 +363,14 @@ static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, st
          if (rs.init_row[k] != UINT64_MAX && rs.init_row[k] >= row && rs.init_row[k] < next) next = rs.init_row[k];
          if (pe_idle_row[k] < next) next = pe_idle_row[k];
          if (gcr_idle_row[k] < next) next = gcr_idle_row[k]; }
-      const rt_event *e = peek_event(src, next + 1, &need_restart);
-      if (need_restart) return 1;
+      const rt_event *e = peek_event(src, next + 1);
       if (e && e->row < next) next = e->row;
       if (next >= nrows) {                /* readtape.c:1410-1413: the end marker */
          timenow = nrows ? rowtime(nrows - 1) : timenow;
          if (nrows > row0) force_end_of_block();
          *endfile = true;
          *last_row = nrows;               /* file position: at the marker */
-         return 0; }
+         return; }
 
       /* ---- process row `next` in the order process_sample() does ---- */
       row = next;
@@ -358,10 +386,9 @@ static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, st
                rs.init_row[k] = UINT64_MAX;
                dirty = 1;
                break; } }
-         e = peek_event(src, row + 1, &need_restart);
-         if (need_restart) return 1;
+         e = peek_event(src, row + 1);
          if (e && e->row == row && e->trk == k) {
-            ++src->at; ++S.n_events;
+            TAKE(src); ++S.n_events;
             t->v_top = e->v_top; t->v_bot = e->v_bot;
             if (e->kind == RT_EV_TOP) { t->t_top = e->t_event; process_up_transition(t); }
             else { t->t_bot = e->t_event; process_down_transition(t); }
@@ -386,10 +413,9 @@ static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, st
          ww_end_of_block(); dirty = 1; }
       /* events of this row on tracks the reference did not reach (its `break` / `goto exit`) are dropped */
       for (;;) {
-         e = peek_event(src, row + 1, &need_restart);
-         if (need_restart) return 1;
+         e = peek_event(src, row + 1);
          if (!e || e->row != row) break;
-         ++src->at; }
+         TAKE(src); }
 
       /* ---- exit logic, decoder.c:900-904 ---- */
       if (interblock_counter) {
@@ -399,12 +425,12 @@ static int decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, st
             timenow = rowtime(nrows - 1);
             force_end_of_block();
             *endfile = true; *last_row = nrows;
-            return 0; }
+            return; }
          interblock_counter = 0;
          timenow = rowtime(ret);
          *last_row = ret + 1;
-         return 0; }
-      if (block.results[block.parmset].blktype != BS_NONE) { *last_row = row + 1; return 0; }
+         return; }
+      if (block.results[block.parmset].blktype != BS_NONE) { *last_row = row + 1; return; }
       ++row; } }
 
 bool readblock(bool retry) {
@@ -429,18 +455,7 @@ bool readblock(bool retry) {
    int from_bulk = !persistent && bulk_start(&src, &cfg, row0);
    if (!from_bulk) exact_start(&src, &cfg, reset_kind, row0);
    S.s_scan += wall() - w0; w0 = wall();
-   if (decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile)) {
-      /* the speculative unit ended before the block did: start over with the exact scan */
-      assert(from_bulk, "B200 scan: exact scan asked for a restart");
-      ++S.n_restarts;
-      if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2)
-         rlog("  B200 scan: restart: the unit found for row %llu ends at row %llu, inside the block\n", (unsigned long long)row0, (unsigned long long)src.valid_end);
-      interblock_counter = 0;
-      init_trackstate();                                           /* the reference's own reset, again */
-      S.pending_reset = RT_RESET_NONE;
-      block.window_set = true;
-      exact_start(&src, &cfg, RT_RESET_FULL, row0);
-      assert(!decode_from(row0, RT_RESET_FULL, &cfg, &src, &last_row, &endfile), "B200 scan: restart failed"); }
+   decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile);
    if (src.exact && persistent && !endfile) {   /* Whirlwind continues from here: leave the scan state exactly where the host stopped */
       int rc = rt_scan_rewind(S.ctx, last_row); if (rc) rtfatal("rt_scan_rewind", rc); }
 

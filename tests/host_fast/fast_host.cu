@@ -15,9 +15,10 @@
 #include "cfg_host.h"
 
 struct HostEmit {
-   rt_event *buf; uint32_t cap, n; uint64_t first_row; uint32_t first_chunk; uint8_t trk;
+   rt_event *buf; uint32_t cap, n; uint64_t first_row; uint32_t first_chunk; uint8_t trk; uint64_t last_row;
    void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
       if (n == 0) first_row = row;
+      last_row = row;
       if (n < cap) {
          rt_event e;
          e.row = row; e.t_event = t_ev; e.v_top = v_top; e.v_bot = v_bot; e.agc_gain = agc;
@@ -32,7 +33,7 @@ struct HostJobs {
    template <class Scan> bool next(Scan &us) {
       exhausted = k >= dc.ntrks;
       if (exhausted) return false;
-      HostEmit em{out + (size_t)k * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)k};
+      HostEmit em{out + (size_t)k * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)k, RT_NOROW};
       us.begin(planes + (size_t)k * plane_stride, row0, row_end, k, em, thr);
       return true; }
    template <class Scan> void done(Scan &us) { us.finish(meta[k]); counts[k] = us.em.n; ++k; } };
@@ -106,7 +107,7 @@ struct HostSparseJobs {
    template <class Scan> bool next(Scan &us) {
       exhausted = k >= dc.ntrks;
       if (exhausted) return false;
-      HostEmit em{out + (size_t)k * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)k};
+      HostEmit em{out + (size_t)k * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)k, RT_NOROW};
       us.begin(planes + (size_t)k * plane_stride, row0, row_end, k, em, thr);
       return true; }
    template <class Scan> void done(Scan &us) { us.finish(meta[k]); counts[k] = us.em.n; ++k; } };

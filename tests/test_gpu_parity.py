@@ -361,3 +361,35 @@ def test_pe_parmset_fanout_on_one_gpu(name, cuda_lib, oracle_lib):
         sc.end()
     bulk.free(); tg.close(); to.close()
     assert hits >= 0.7 * total, f"only {hits} of {total} (parmset, block) lookups were served by the bulk scan"
+
+
+def test_tile_digest_at_scale_equals_oracle(cuda_lib, oracle_lib):
+    """rt_bulk_tile_digest(): on a periodic tape every tile must carry the same events (count + order-independent digest, computed
+    on the device over ALL events), every double-precision event time must be reproduced by the reference's expression, and the
+    digest of one tile must equal the one computed from the CPU oracle's events -- the check bench.py applies to the full-size tape"""
+    from readtape_b200 import parmsets, synth, tbin, verify
+    tile = synth.nrzi_tile()
+    reps = 5
+    hdr = synth.nrzi_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
+    tape = cuda_lib.open(desc)
+    for _ in range(reps):
+        tape.upload(tile)
+    nrows = tile.shape[0] * reps
+    bulk = tape.bulk_scan([cfg])
+    rep = verify.verify_periodic(oracle_lib, bulk, desc, cfg, tile, nrows)
+    st = bulk.stats()
+    bulk.free()
+    print(rep)
+    assert rep["ok"], rep
+    assert rep["events_digested"] == st.events or rep["events_digested"] <= st.events       # overlap events are counted once
+    # a corrupted tape must be noticed: one sample of tile 3 changed
+    bad = tile.copy(); bad[700_000, 4] = 20000
+    tape.clear()
+    for i in range(reps):
+        tape.upload(bad if i == 3 else tile)
+    bulk = tape.bulk_scan([cfg])
+    rep2 = verify.verify_periodic(oracle_lib, bulk, desc, cfg, tile, nrows)
+    bulk.free(); tape.close()
+    assert not rep2["ok"] and rep2["first_differing_tile"] == 3, rep2

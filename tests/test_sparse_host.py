@@ -17,7 +17,9 @@ from conftest import ROOT, load_capture
 from readtape_b200 import abi, evlog, parmsets, synth, tbin
 from test_fast_host import HOST_LIB, fast_scan, make_planes
 
-META_WORDS_NO_PAD = slice(0, -1)          # TrkMeta as u32 words without the trailing diagnostics word
+# TrkMeta as u32 words without quiet_tail_from (words 16-17: only the two-pass scan and the zero-crossing path derive it) and the
+# trailing diagnostics word
+META_WORDS_NO_PAD = list(range(16)) + [18, 19, 20]
 
 
 @pytest.fixture(scope="session")
