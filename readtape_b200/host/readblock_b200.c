@@ -318,6 +318,49 @@ static void say_configuration(void) {
    rlog("\n"); }
 
 /* returns the last row consumed (the row after which the reference's readblock() returns); *endfile set at EOF */
+/* exit logic of process_sample() once a row is done, decoder.c:900-904; returns 1 if the block decode ends here */
+static inline int row_exit(uint64_t row, uint64_t nrows, uint64_t *last_row, bool *endfile) {
+   if (interblock_counter) {
+      /* rows row .. row+interblock_counter-1 are swallowed; the block is returned after the last of them */
+      uint64_t ret = row + (uint64_t)interblock_counter - 1;
+      if (ret >= nrows) {               /* the end marker comes first */
+         timenow = rowtime(nrows - 1);
+         force_end_of_block();
+         *endfile = true; *last_row = nrows;
+         return 1; }
+      interblock_counter = 0;
+      timenow = rowtime(ret);
+      *last_row = ret + 1;
+      return 1; }
+   if (block.results[block.parmset].blktype != BS_NONE) { *last_row = row + 1; return 1; }
+   return 0; }
+
+/* hand one event to the reference's handler exactly as lookfor_peak / lookfor_*zerocrossing would (decoder.c:574/592) */
+static inline void apply_event(struct trkstate_t *t, const rt_event *e, uint64_t row) {
+   ++S.n_events;
+   t->v_top = e->v_top; t->v_bot = e->v_bot;
+   if (e->kind == RT_EV_TOP) { t->t_top = e->t_event; process_up_transition(t); }
+   else { t->t_bot = e->t_event; process_down_transition(t); }
+   if (t->agc_gain != e->agc_gain)
+      fatal("B200 scan diverged from the host on track %d at row %llu: AGC %.9g (scan) vs %.9g (host)",
+            (int)e->trk, (unsigned long long)row, e->agc_gain, t->agc_gain); }
+
+/* Is any of process_sample()'s per-row conditions (decoder.c:844,868,879,892) true at a row whose time is `te`?  They are
+   monotone in the time, so "false at te" means false at every earlier row since the state last changed. */
+static inline int timer_due_at(double te) {
+   if (mode == NRZI) return nrzi.datablock && te > nrzi.t_lastclock + 2 * nrzi.clkavg.t_bitspaceavg;
+   if (mode == PE) {
+      for (int k = 0; k < ntrks; ++k) {
+         const struct trkstate_t *t = &trkstate[k];
+         if (!t->idle && t->t_lastpeak != 0 && te - t->t_lastpeak > t->clkavg.t_bitspaceavg * PE_IDLE_FACTOR) return 1; }
+      return 0; }
+   if (mode == GCR) {
+      for (int k = 0; k < ntrks; ++k) {
+         const struct trkstate_t *t = &trkstate[k];
+         if (t->datablock && te > t->t_lastpeak + GCR_IDLE_THRESH * t->clkavg.t_bitspaceavg) return 1; }
+      return 0; }
+   return ww.datablock && ww.t_lastclkpulseend > 0 && te - ww.t_lastclkpulseend > ww.clkavg.t_bitspaceavg * WW_CLKSTOP_BITS; }
+
 static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, struct evsrc *src, uint64_t *last_row, bool *endfile) {
    struct rowstate rs;
    const uint64_t nrows = S.nrows;
@@ -335,7 +378,37 @@ static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, s
    int dirty = 1;                       /* timers must be recomputed */
    *endfile = false;
 
+   int init_pending = 0;
+   for (int k = 0; k < ntrks; ++k) if (rs.init_row[k] != UINT64_MAX) ++init_pending;
+
    for (;;) {
+      /* ---- the common case, one event at a time: every track is initialised, the next event is at hand, and none of the per-row
+              conditions becomes true at or before its row -- then process_sample() does nothing on the rows in between, and on the
+              event's row only what the events of that row make it do ---- */
+      while (!init_pending && src->at < src->n) {
+         const rt_event *e = &src->ev[src->at];
+         const double te = rowtime(e->row);
+         if (timer_due_at(te)) break;
+         row = e->row; timenow = te;
+         for (;;) {                                             /* the events of this row, in track order */
+            struct trkstate_t *t = &trkstate[e->trk];
+            TAKE(src);
+            apply_event(t, e, row);
+            /* the per-track tests behind the detector call, decoder.c:868-888 (the other tracks: not due, see above) */
+            if (mode == PE && !t->idle && t->t_lastpeak != 0 && timenow - t->t_lastpeak > t->clkavg.t_bitspaceavg * PE_IDLE_FACTOR) {
+               t->v_lastpeak = t->v_now; t->idle = true;
+               if (++num_trks_idle >= ntrks) pe_end_of_block(); }
+            if (mode == GCR && t->datablock && timenow > t->t_lastpeak + GCR_IDLE_THRESH * t->clkavg.t_bitspaceavg) {
+               t->datablock = false; t->idle = true;
+               if (++num_trks_idle >= ntrks) { gcr_end_of_block(); break; } }
+            if (src->at >= src->n || src->ev[src->at].row != row) break;
+            e = &src->ev[src->at]; }
+         dirty = 1;
+         if (mode == WW && timer_due_at(timenow)) ww_end_of_block();
+         while (src->at < src->n && src->ev[src->at].row == row) TAKE(src);      /* behind a `goto exit`: not reached */
+         if (row_exit(row, nrows, last_row, endfile)) return;
+         ++row; }
+
       /* ---- timers: the first row >= `row` at which each per-row condition of process_sample() holds ---- */
       if (dirty) {
          zerocheck_row = ww_stop_row = UINT64_MAX;
@@ -383,18 +456,13 @@ static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, s
             if (row < rs.init_row[k]) break;                       /* the reference's `break`: later tracks are not reached either */
             if (row == rs.init_row[k]) {                           /* decoder.c:855-861 */
                t->t_lastpeak = timenow;
-               rs.init_row[k] = UINT64_MAX;
+               rs.init_row[k] = UINT64_MAX; --init_pending;
                dirty = 1;
                break; } }
          e = peek_event(src, row + 1);
          if (e && e->row == row && e->trk == k) {
-            TAKE(src); ++S.n_events;
-            t->v_top = e->v_top; t->v_bot = e->v_bot;
-            if (e->kind == RT_EV_TOP) { t->t_top = e->t_event; process_up_transition(t); }
-            else { t->t_bot = e->t_event; process_down_transition(t); }
-            if (t->agc_gain != e->agc_gain)
-               fatal("B200 scan diverged from the host on track %d at row %llu: AGC %.9g (scan) vs %.9g (host)",
-                     k, (unsigned long long)row, e->agc_gain, t->agc_gain);
+            TAKE(src);
+            apply_event(t, e, row);
             dirty = 1; }
          else if (e && e->row == row && e->trk < k)
             fatal("B200 scan: event order violated at row %llu", (unsigned long long)row);
@@ -417,20 +485,7 @@ static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, s
          if (!e || e->row != row) break;
          TAKE(src); }
 
-      /* ---- exit logic, decoder.c:900-904 ---- */
-      if (interblock_counter) {
-         /* rows row .. row+interblock_counter-1 are swallowed; the block is returned after the last of them */
-         uint64_t ret = row + (uint64_t)interblock_counter - 1;
-         if (ret >= nrows) {               /* the end marker comes first */
-            timenow = rowtime(nrows - 1);
-            force_end_of_block();
-            *endfile = true; *last_row = nrows;
-            return; }
-         interblock_counter = 0;
-         timenow = rowtime(ret);
-         *last_row = ret + 1;
-         return; }
-      if (block.results[block.parmset].blktype != BS_NONE) { *last_row = row + 1; return; }
+      if (row_exit(row, nrows, last_row, endfile)) return;
       ++row; } }
 
 bool readblock(bool retry) {
