@@ -122,6 +122,79 @@ def reference_run(tile, ntiles_per_proc, nproc, steps, warmup, workdir):
                       f"tape, unmodified readtape 3.18 (gcc -O2), whole program incl. file read and .tap write"}
 
 
+# ---- the product, end to end: TBIN file -> .tap through readtape with the B200 scan -------------------------------------------
+def product_run(tile, workdir, gpus, nproc, reps=889, ref_tiles=56, runs=2):
+    """readtape_b200 (the reference's own host code with readblock() replaced, readtape_b200/host) on a reel of `reps` super-tiles
+    in the page cache, split between `nproc` worker processes (RT_WORKERS) dealt over `gpus` GPUs (RT_DEVICES), wall clock from
+    exec to exit; beside it the unmodified reference doing the same work with all host cores (`nproc` processes x `ref_tiles`
+    super-tiles each, >= the same number of rows); the product's .tap must be the reference's."""
+    exe = os.path.join(ROOT, "readtape_b200", "bin", "readtape_b200")
+    ref = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+    if not (os.path.exists(exe) and os.path.exists(ref)):
+        return {"unavailable": "readtape_b200/bin/readtape_b200 or oracle/_ref/readtape_ref not built"}
+    hdr = tbin.build_header(synth.nrzi_header())
+    end = np.array([tbin.END_MARK], dtype="<i2").tobytes()
+    reel = os.path.join(workdir, "reel.tbin")
+    with open(reel, "wb") as fh:
+        fh.write(hdr)
+        for _ in range(reps):
+            tile.tofile(fh)
+        fh.write(end)
+    opts = ["-q", "-nm", "-nrzi", "-bpi=800", "-ips=50", "-tap", "-nolog", "-nolabels"]
+    env = dict(os.environ, RT_WORKERS=str(nproc), RT_DEVICES=str(gpus), RT_STATS="1")
+    times, out = [], ""
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        r = subprocess.run([exe] + opts + [f"-outf={workdir}/prod", reel], capture_output=True, text=True, env=env)
+        times.append(time.perf_counter() - t0)
+        out = r.stdout
+        if r.returncode != 0:
+            return {"error": f"readtape_b200 exited {r.returncode}: {r.stdout[-400:]} {r.stderr[-400:]}"}
+    phases = {"open_upload_s": 0.0, "scan_s": 0.0, "replay_s": 0.0, "events": 0, "hits": 0, "misses": 0, "restarts": 0}
+    import re
+    for m in re.finditer(r"(\d+) events, (\d+) speculative hits, (\d+) misses, (\d+) restarts", out):
+        for key, v in zip(("events", "hits", "misses", "restarts"), m.groups()):
+            phases[key] += int(v)
+    for m in re.finditer(r"([\d.]+) s opening \+ upload, ([\d.]+) s in the scan library, ([\d.]+) s replaying", out):
+        for key, v in zip(("open_upload_s", "scan_s", "replay_s"), m.groups()):
+            phases[key] = max(phases[key], float(v))             # the slowest worker
+    # the reference, same work, all cores
+    sample = os.path.join(workdir, "ref_sample.tbin")
+    with open(sample, "wb") as fh:
+        fh.write(hdr)
+        for _ in range(ref_tiles):
+            tile.tofile(fh)
+        fh.write(end)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([ref] + opts + [f"-outf={workdir}/ref{p}", sample], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for p in range(nproc)]
+    rcs = [p.wait() for p in procs]
+    t_ref = time.perf_counter() - t0
+    if any(rcs):
+        return {"error": f"readtape_ref exited {rcs}"}
+    # .tap identity: every block decode is independent and the reel is periodic, so the reel's .tap is the per-tile record
+    # sequence repeated; the per-tile sequence comes from the reference's own output
+    body = open(f"{workdir}/ref0.tap", "rb").read()
+    assert body[-4:] == b"\xff" * 4
+    body = body[:-4]
+    per_tile = body[: len(body) // ref_tiles]
+    identical = False
+    if len(body) % ref_tiles == 0 and per_tile * ref_tiles == body:
+        got = open(f"{workdir}/prod.tap", "rb").read()
+        identical = len(got) == len(per_tile) * reps + 4 and got[-4:] == b"\xff" * 4 and all(
+            got[i * len(per_tile):(i + 1) * len(per_tile)] == per_tile for i in range(reps))
+    rows = reps * tile.shape[0]
+    best = min(times)
+    res = {"workload": f"TBIN file in the page cache ({reps} super-tiles, {rows} rows, {rows * 18 / 1e9:.2f} GB) -> .tap, whole program "
+                       f"(readtape's own host code + the B200 scan), {nproc} worker processes on {gpus} GPU(s)",
+           "seconds": best, "seconds_all_runs": times, "value": rows * 9 / best, "unit": UNIT, "tap_bytes": os.path.getsize(f"{workdir}/prod.tap"),
+           "tap_identical_to_reference": bool(identical), "slowest_worker": phases,
+           "reference": {"seconds": t_ref, "value": nproc * ref_tiles * tile.shape[0] * 9 / t_ref, "processes": nproc,
+                         "super_tiles_per_process": ref_tiles, "what": "unmodified readtape 3.18 (gcc -O2), the same command line"},
+           }
+    res["ratio_vs_reference_all_cores"] = res["value"] / res["reference"]["value"]
+    return res
+
+
 def bench_gcr(args, rank, world, local_rank, W, K):
     """BASELINE config 4: 9-track GCR 6250 density at 6.25 MHz with the zero-crossing detector (-zeros, as all reference GCR
     examples), the 5 built-in GCR parameter sets (parmsets.c:106-110) x time shards dealt over the ranks (shard.assign_units).
@@ -215,6 +288,7 @@ def main():
     ap.add_argument("--workload", default="nrzi", choices=["nrzi", "gcr"],
                     help="nrzi: BASELINE config 2 (the headline line); gcr: config 4, GCR-density tape x 5 parameter sets sharded over the GPUs")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-product", action="store_true", help="skip the whole-program run (TBIN file -> .tap through readtape_b200)")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-scale check of the scan's events against the oracle (outside the timed regions)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -372,6 +446,22 @@ def main():
         dist.all_gather(g, torch.tensor([events], dtype=torch.int64, device="cuda"))
         all_events = [int(x.item()) for x in g]
 
+    # ---- the product end to end (rank 0; the reel is split over all N GPUs of the job) ----
+    product = None
+    if not args.no_product and rows == FULL_ROWS:
+        if dist is not None:
+            dist.barrier()
+        if rank == 0:
+            work = tempfile.mkdtemp(prefix="rtprod_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            try:
+                product = product_run(tile, work, world, nproc)
+            except Exception as exc:                                  # the headline numbers above stand on their own
+                product = {"error": repr(exc)}
+            finally:
+                shutil.rmtree(work, ignore_errors=True)
+        if dist is not None:
+            dist.barrier()
+
     # ---- CPU baseline on rank 0, N=1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -431,7 +521,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms, "other_kernels": others},
             "e2e": e2e, "gpu_launches": launches_per_step * K, "clocks": clocks,
-            "cpu_baseline": cpu, "result_gather": {"events_per_rank": all_events},
+            "cpu_baseline": cpu, "result_gather": {"events_per_rank": all_events}, "product": product,
         }
         print(json.dumps(line))
     tape.close()

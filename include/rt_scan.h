@@ -198,6 +198,11 @@ int  rt_bulk_scan_host(rt_tape *tape, const int16_t *rows, uint64_t nrows, const
 int  rt_bulk_lookup(rt_bulk *bulk, uint32_t cfg_index, uint64_t start_row,
                     const rt_event **events, uint64_t *nevents, uint64_t *valid_rows);
 
+/* The unit the last successful rt_bulk_lookup() of configuration `cfg_index` resolved to (before chaining through event-free
+ * units): its first row and end.  Lets a caller that splits one tape between workers prove a hand-over: "a fresh reset at my
+ * current row is equivalent to a fresh reset at a unit that starts at or behind the row where the next worker starts". */
+int  rt_bulk_last_unit(const rt_bulk *bulk, uint32_t cfg_index, uint64_t *row0, uint64_t *row_end);
+
 /* Diagnostics: the unit rt_bulk_lookup() would consult for `start_row` and the per-track proof data
  * (~0 means "none").  A unit covers start_row iff start_row == row0, or start_row >= row0 - P (P = the quiet pre-scan
  * length, 256 .. 4096 rows depending on the sample rate and density) and for every

@@ -419,6 +419,7 @@ struct BulkCfg {
    UnitDesc *d_units = nullptr; TrkMeta *d_meta = nullptr;       /* device-resident results of the scan */
    uint32_t nunits = 0;
    bool fast = false;
+   size_t last_unit = ~(size_t)0;                                 /* rt_bulk_last_unit() */
    std::vector<UnitDesc> units; std::vector<TrkMeta> meta;        /* host copies, filled by rt_bulk_fetch() */
 };
 struct rt_bulk {
@@ -892,6 +893,14 @@ extern "C" int rt_peak_masks(rt_tape *t, const rt_scan_cfg *cfg, float t0_frac, 
    if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "rt_peak_masks: %s", cudaGetErrorString(e));
    return RT_OK; }
 
+extern "C" int rt_bulk_last_unit(const rt_bulk *b, uint32_t ci, uint64_t *row0, uint64_t *row_end) {
+   if (!b || ci >= b->cfgs.size()) return set_err(RT_ERR_ARG, "rt_bulk_last_unit: bad argument");
+   const BulkCfg &bc = b->cfgs[ci];
+   if (bc.last_unit >= bc.units.size()) return set_err(RT_ERR_STATE, "rt_bulk_last_unit: no successful lookup yet");
+   if (row0) *row0 = bc.units[bc.last_unit].row0;
+   if (row_end) *row_end = bc.units[bc.last_unit].row_end;
+   return RT_OK; }
+
 extern "C" int rt_bulk_tile_digest(rt_bulk *b, uint32_t ci, uint64_t period, uint64_t ntiles, uint64_t *events, uint64_t *digest, uint64_t *bad_times) {
    if (!b || ci >= b->cfgs.size() || !period || !ntiles || !events || !digest) return set_err(RT_ERR_ARG, "rt_bulk_tile_digest: bad argument");
    if (b->fetched || !b->d_pool) return set_err(RT_ERR_STATE, "rt_bulk_tile_digest: the results have left the device (call it before rt_bulk_fetch / rt_bulk_lookup)");
@@ -1032,13 +1041,14 @@ extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const
             if (!bridged && br1 != RT_NOROW) { int rc = bridge_holds(b, ci, lo + 1, start_row, br1, &bridged); if (rc) return rc; if (bridged) ++lo; } } }
       if (bridged) { /* covered */ }
       else if (unit_tail_covers(bc, nt, lo, start_row)) {        /* nothing up to the end of this unit (typically: the end of the tape) */
-         b->result.clear();
+         b->result.clear(); bc.last_unit = lo;
          if (events) *events = b->result.data();
          if (nevents) *nevents = 0;
          if (valid_rows) *valid_rows = bc.units[lo].row_end - start_row;
          return RT_OK; }
       else return RT_MISS; }
    const TrkMeta *m = &bc.meta[lo * nt];
+   bc.last_unit = lo;
    /* Chaining: while the unit holds no event at all, the reference's scan passes through it unchanged; it is
       then identical to the NEXT unit's fresh scan from that unit's first canonical row on, provided that row
       lies inside the stretch where this unit has already shown the scan to be event-free (the overlap). */

@@ -36,6 +36,8 @@
 #include "decoder.h"
 #include "rt_scan.h"
 #include <time.h>
+#include <unistd.h>
+#include <sys/wait.h>
 
 /* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
 extern FILE *inf;
@@ -46,8 +48,15 @@ extern int nheads, samples_per_bit, subsample, head_to_trk[MAXTRKS], trk_to_head
 extern bool set_ntrks_from_order;
 extern char track_order_string[MAXTRKS + 1];
 extern char *wwtracktype_names[WWTRK_NUMTYPES];
-extern long long lines_in, numsamples;
+extern long long lines_in, numsamples, numoutbytes;
 extern double torigin;
+extern bool tap_format, do_txtfile, deskew, skew_given;
+extern FILE *outf;
+extern int numblks;
+extern char baseoutfilename[], baseinfilename[];
+void create_datafile(const char *name);                /* readtape.c:1092 */
+void output_tap_marker(uint32_t num);                  /* readtape.c:1077 */
+void close_file(void);                                 /* readtape.c:1085 */
 void force_end_of_block(void);                         /* readtape.c:1378 */
 void process_up_transition(struct trkstate_t *t);      /* decoder.c:574 */
 void process_down_transition(struct trkstate_t *t);    /* decoder.c:592 */
@@ -71,11 +80,24 @@ static struct {
    long long n_bulk_hits, n_bulk_miss, n_exact_spans, n_events, n_restarts;
    double s_scan, s_replay, s_open;  /* wall seconds: inside the rt_scan library / replaying events into the handlers / opening */
    int said_config;
-} S;
+   /* one reel split between worker processes (RT_WORKERS, see run_workers) */
+   int par_checked, nworkers, worker;   /* worker: 0 .. nworkers-1, or -1 for the classic single process */
+   uint64_t file_rows;                  /* rows in the file, counted from the position of the first readblock() */
+   uint64_t nominal_lo, nominal_hi;     /* this worker's share of the reel, file rows (cut points are moved to inter-block gaps) */
+   uint64_t row_off;                    /* file row of tape row 0 (the worker only holds its share plus a margin) */
+   uint64_t stop_row;                   /* tape row of the unit boundary where the next worker starts; UINT64_MAX: run to the end */
+   int worker_ready;                    /* the worker's boundaries are known */
+   int must_seek_start;                 /* worker > 0: the first readblock() call only positions the file at the worker's first row */
+} S = { .worker = -1, .stop_row = UINT64_MAX };
 
 static double wall(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 #define EXACT_SPAN_ROWS  (1u << 17)
+/* rows a worker holds beyond its nominal share on both sides (the cut moves to the next gap), and the smallest share a reel is split
+   into; the environment overrides exist for tests on the small bundled captures */
+#define WORKER_MARGIN_ROWS  (getenv("RT_WORKER_MARGIN_ROWS") ? strtoull(getenv("RT_WORKER_MARGIN_ROWS"), NULLP, 10) : (uint64_t)(4u << 20))
+#define WORKER_MIN_ROWS     (getenv("RT_WORKER_MIN_ROWS") ? strtoull(getenv("RT_WORKER_MIN_ROWS"), NULLP, 10) : (uint64_t)(8u << 20))
+#define WORKER_UNPROVEN     98              /* exit code of a worker whose hand-over could not be proven: the reel is decoded unsplit */
 
 static void rtfatal(const char *what, int rc) {
    fatal("B200 scan: %s failed (%d): %s", what, rc, rt_last_error()); }
@@ -129,13 +151,27 @@ static void open_tape(void) {
    assert(fseeko(inf, S.base_pos, SEEK_SET) == 0, "fseek failed");
    uint64_t rowbytes = (uint64_t)nheads * 2;
    uint64_t nrows_file = (uint64_t)(end - S.base_pos) / rowbytes;
-   int rc = rt_open(&S.desc, getenv("RT_DEVICE") ? atoi(getenv("RT_DEVICE")) : 0, &S.tape);
+   uint64_t first = 0;                                   /* file rows [first, first + nrows_file) go to the GPU */
+   if (S.worker >= 0) {                                  /* a worker holds its share of the reel plus a margin on both sides */
+      uint64_t lo = S.nominal_lo > WORKER_MARGIN_ROWS ? (S.nominal_lo - WORKER_MARGIN_ROWS) / 2048 * 2048 : 0;
+      uint64_t hi = S.worker == S.nworkers - 1 ? nrows_file : S.nominal_hi + WORKER_MARGIN_ROWS;
+      if (hi > nrows_file) hi = nrows_file;
+      first = lo; nrows_file = hi - lo;
+      S.row_off = first;
+      S.base_pos += (long long)(first * rowbytes);        /* from here on, rows are counted from the worker's first row */
+      S.desc.tstart_ns += first * S.desc.tdelta_ns; }
+   int dev = getenv("RT_DEVICE") ? atoi(getenv("RT_DEVICE")) : 0;
+   if (S.worker >= 0 && getenv("RT_DEVICES") && atoi(getenv("RT_DEVICES")) > 1) dev = S.worker % atoi(getenv("RT_DEVICES"));   /* one reel over several GPUs */
+   int rc = rt_open(&S.desc, dev, &S.tape);
    if (rc) rtfatal("rt_open", rc);
    S.rows_bytes = (size_t)(nrows_file * rowbytes);
    S.rows = rt_host_alloc(S.rows_bytes + 16);
    assert(S.rows != NULLP, "cannot allocate %lld bytes of pinned memory", (long long)S.rows_bytes);
-   assert(fread(S.rows, 1, S.rows_bytes, inf) == S.rows_bytes, "cannot read the .tbin payload");
-   assert(fseeko(inf, S.base_pos, SEEK_SET) == 0, "fseek failed");
+   {  size_t got = 0;                                    /* pread: the stdio position of `inf` stays where the host put it */
+      while (got < S.rows_bytes) {
+         ssize_t n = pread(fileno(inf), (char *)S.rows + got, S.rows_bytes - got, (off_t)(S.base_pos + (long long)got));
+         assert(n > 0, "cannot read the .tbin payload");
+         got += (size_t)n; } }
    rc = rt_upload(S.tape, S.rows, nrows_file);
    if (rc) rtfatal("rt_upload", rc);
    S.nrows = rt_nrows(S.tape);
@@ -488,9 +524,143 @@ static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, s
       if (row_exit(row, nrows, last_row, endfile)) return;
       ++row; } }
 
+/* ---- one reel, several worker processes (opt-in: RT_WORKERS=P) ------------------------------------------------------------
+ * The replay of the events through the reference's handlers is single-threaded host work (the reference is not re-entrant), and once
+ * the scan runs on the GPU it is all that is left: ~150 ns per flux transition.  Every block decode starts from init_trackstate(),
+ * so blocks are independent, and the reference's per-block outputs in .tap format simply concatenate.  With RT_WORKERS=P the first
+ * readblock() call forks P workers BEFORE anything touches CUDA; worker i opens its own share of the reel (file rows
+ * [i*N/P, (i+1)*N/P) plus a margin), scans it on the GPU (RT_DEVICES=n deals the workers over n GPUs) and runs the reference's
+ * unchanged process_file() loop on it, writing <out>.partNNN.tap.  Cut points are not the nominal rows but inter-block gaps:
+ *   - worker i > 0 starts at the first unit boundary behind its nominal first row (a unit boundary is the start of an all-track
+ *     quiet stretch, k_units.cu), i.e. with a fresh init_trackstate() there;
+ *   - worker i < P-1 stops at the first block start for which rt_bulk_lookup() PROVES that a fresh reset there is equivalent to a
+ *     fresh reset at a unit that starts at or behind that same boundary -- which it computes from its own copy of the same samples.
+ *     If the proof fails the worker exits with WORKER_UNPROVEN and the parent decodes the reel unsplit.
+ * The parent never initialises CUDA: it waits, concatenates the parts (each without its end-of-medium marker), writes the marker,
+ * and reports like readtape's main() does in quiet mode.  Only what is safe to split is split: .tap output, quiet mode (per-block log
+ * lines carry running block numbers), no text file, no Whirlwind (state persists), no density / deskew pre-pass pending. */
+static void part_name(char *buf, size_t n, int i, const char *ext) { snprintf(buf, n, "%s.part%03d%s", baseoutfilename, i, ext); }
+
+static void run_workers(void) {
+   const char *env = getenv("RT_WORKERS");
+   int P = env ? atoi(env) : 1;
+   if (P <= 1) return;
+   if (!(tbin_file && tap_format && quiet && !do_txtfile && mode != WW && subsample == 1 && bpi != 0 && !doing_density_detection
+         && !doing_deskew && (!deskew || skew_given) && numblks == 0 && outf == NULLP)) return;
+   long long pos = ftello(inf);
+   assert(pos >= 0 && fseeko(inf, 0, SEEK_END) == 0, "fseek failed");
+   long long end = ftello(inf);
+   assert(fseeko(inf, pos, SEEK_SET) == 0, "fseek failed");
+   const uint64_t N = (uint64_t)(end - pos) / ((uint64_t)nheads * 2);
+   if (N / (uint64_t)P < WORKER_MIN_ROWS) P = (int)(N / WORKER_MIN_ROWS);
+   if (P <= 1) return;
+   static char base[MAXPATH + 50];
+   strcpy(base, baseoutfilename);
+   fflush(NULL);
+   pid_t pids[256]; if (P > 256) P = 256;
+   for (int i = 0; i < P; ++i) {
+      pid_t pid = fork();
+      assert(pid >= 0, "fork failed");
+      if (pid == 0) {                                        /* the worker: carries on into open_tape() with its share */
+         char name[MAXPATH + 80];
+         S.worker = i; S.nworkers = P; S.file_rows = N;
+         S.nominal_lo = (uint64_t)i * N / (uint64_t)P / 2048 * 2048;
+         S.nominal_hi = i == P - 1 ? N : (uint64_t)(i + 1) * N / (uint64_t)P / 2048 * 2048;
+         S.must_seek_start = i > 0;
+         part_name(name, sizeof name, i, ".out");
+         assert(freopen(name, "w", stdout) != NULLP, "cannot create %s", name);
+         part_name(name, sizeof name, i, "");
+         assert(strlen(name) < MAXPATH, "output name too long");
+         strcpy(baseoutfilename, name);                      /* create_datafile() -> <out>.partNNN.tap */
+         return; }
+      pids[i] = pid; }
+   /* the parent */
+   int worst = 0;
+   for (int i = 0; i < P; ++i) {
+      int st = 0;
+      assert(waitpid(pids[i], &st, 0) == pids[i], "waitpid failed");
+      int code = WIFEXITED(st) ? WEXITSTATUS(st) : 99;
+      if (code != 0 && (worst == 0 || worst == WORKER_UNPROVEN)) worst = code; }
+   bool all_ok = true;
+   char name[MAXPATH + 80], line[MAXLINE];
+   if (worst == 0) {
+      for (int i = 0; i < P; ++i) {                          /* the parts, in order, without their end-of-medium markers */
+         part_name(name, sizeof name, i, ".tap");
+         FILE *f = fopen(name, "rb");
+         if (!f) continue;
+         if (!outf) create_datafile(NULLP);
+         assert(fseeko(f, 0, SEEK_END) == 0, "fseek failed");
+         long long len = ftello(f);
+         unsigned char tail[4] = {0, 0, 0, 0};
+         if (len >= 4) { assert(fseeko(f, len - 4, SEEK_SET) == 0 && fread(tail, 1, 4, f) == 4, "cannot read %s", name);
+                         if (tail[0] == 0xff && tail[1] == 0xff && tail[2] == 0xff && tail[3] == 0xff) len -= 4; }
+         assert(fseeko(f, 0, SEEK_SET) == 0, "fseek failed");
+         static char buf[1 << 20];
+         for (long long left = len; left > 0;) {
+            size_t want = left > (long long)sizeof buf ? sizeof buf : (size_t)left;
+            assert(fread(buf, 1, want, f) == want && fwrite(buf, 1, want, outf) == want, "cannot copy %s", name);
+            left -= (long long)want; }
+         numoutbytes += len;
+         fclose(f); } }
+   for (int i = 0; i < P; ++i) {                             /* what the workers printed; their verdicts */
+      part_name(name, sizeof name, i, ".out");
+      FILE *f = fopen(name, "r");
+      if (f) {
+         size_t tag = strlen(baseinfilename);
+         while (fgets(line, MAXLINE, f)) {
+            if (strncmp(line, baseinfilename, tag) == 0 && line[tag] == ':') { if (strstr(line + tag, "bad")) all_ok = false; continue; }
+            if (worst != WORKER_UNPROVEN) fputs(line, stdout); }
+         fclose(f); }
+      remove(name);
+      part_name(name, sizeof name, i, ".tap"); remove(name); }
+   if (worst == WORKER_UNPROVEN) {                           /* decode the reel in one piece after all */
+      if (getenv("RT_STATS")) printf("  B200 scan: a worker could not prove its hand-over; decoding the reel unsplit\n");
+      return; }
+   if (worst != 0) exit(worst);
+   /* what process_file() does at the end of the file (readtape.c:1862-1867) and main() in quiet mode (:2014) */
+   if (tap_format && outf) output_tap_marker(0xffffffffl);
+   close_file();
+   printf("%s: %s\n", baseinfilename, all_ok ? "ok" : "bad");
+   fflush(NULL);
+   exit(0); }
+
+/* worker: the unit boundaries that delimit this worker's part, from the unit table of the current parameter set */
+static void worker_boundaries(const rt_scan_cfg *cfg, uint64_t *start_row) {
+   struct evsrc probe;
+   static rt_unit_info ui;
+   *start_row = 0;
+   /* make sure the whole-tape scan of this parameter set exists (a lookup at the tape's first row creates it) */
+   (void)bulk_start(&probe, cfg, 0);
+   int ps = block.parmset;
+   if (!S.bulk[ps].valid) fatal("B200 scan: RT_WORKERS needs the speculative whole-tape scan");
+   for (int which = 0; which < 2; ++which) {
+      const uint64_t nominal = which == 0 ? S.nominal_lo : S.nominal_hi;
+      if ((which == 0 && S.worker == 0) || (which == 1 && S.worker == S.nworkers - 1)) continue;
+      int rc = rt_bulk_unit_info(S.bulk[ps].bulk, 0, nominal - S.row_off, &ui);
+      if (rc == RT_OK) rc = rt_bulk_unit_at(S.bulk[ps].bulk, 0, ui.unit_index + 1, &ui);
+      if (rc != RT_OK) { fflush(NULL); _exit(WORKER_UNPROVEN); }         /* no inter-block gap within the margin */
+      if (which == 0) *start_row = ui.row0; else S.stop_row = ui.row0; } }
+
 bool readblock(bool retry) {
    double w0 = wall();
+   if (!S.par_checked) { S.par_checked = 1; run_workers(); }      /* RT_WORKERS: the parent does not come back from there */
    if (!S.opened) { open_tape(); S.s_open += wall() - w0; w0 = wall(); }
+   if (S.worker >= 0 && !S.worker_ready) {
+      /* a worker's first call: find its boundaries; a worker other than the first only moves to its first row and reports "noise",
+         so that process_file() takes its next block start (blockstart, readtape.c:1722) from there */
+      rt_scan_cfg cfg0; make_cfg(&cfg0);
+      uint64_t start = 0;
+      worker_boundaries(&cfg0, &start);
+      S.worker_ready = 1;
+      if (S.must_seek_start) {
+         S.must_seek_start = 0;
+         timenow_ns = (int64_t)(S.desc.tstart_ns + start * S.desc.tdelta_ns);
+         timenow = rowtime(start);
+         assert(fseeko(inf, S.base_pos + (long long)start * nheads * 2, SEEK_SET) == 0, "fseek failed");
+         block.results[block.parmset].blktype = BS_NOISE;
+         S.pending_reset = RT_RESET_NONE;
+         S.s_scan += wall() - w0;
+         return true; } }
    long long pos = ftello(inf);
    assert(pos >= S.base_pos && (pos - S.base_pos) % (nheads * 2) == 0, "B200 scan: unexpected file position %lld", pos);
    uint64_t row0 = (uint64_t)(pos - S.base_pos) / (uint64_t)(nheads * 2);
@@ -508,6 +678,17 @@ bool readblock(bool retry) {
    uint64_t last_row = row0; bool endfile = false;
    int persistent = mode == WW || reset_kind != RT_RESET_FULL;   /* Whirlwind: the scan state carries over from block to block */
    int from_bulk = !persistent && bulk_start(&src, &cfg, row0);
+   if (S.stop_row != UINT64_MAX && !retry) {                     /* a worker that is not the last: is this block the next worker's? */
+      uint64_t u0 = 0;
+      if (from_bulk && rt_bulk_last_unit(S.bulk[block.parmset].bulk, 0, &u0, NULLP) == RT_OK && u0 >= S.stop_row) {
+         /* proven: a fresh reset here == a fresh reset at a unit at or behind the boundary; the next worker starts exactly there */
+         S.s_scan += wall() - w0;
+         if (getenv("RT_STATS")) {
+            rlog("  B200 scan: worker %d of %d: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n", S.worker, S.nworkers,
+                 S.n_events, S.n_bulk_hits, S.n_bulk_miss, S.n_restarts, S.n_exact_spans);
+            rlog("  B200 scan: worker %d: %.3f s opening + upload, %.3f s in the scan library, %.3f s replaying events into the handlers\n", S.worker, S.s_open, S.s_scan, S.s_replay); }
+         return false; }                                          /* end of this worker's part: block type BS_NONE, "end of file" */
+      if (row0 >= S.stop_row) { fflush(NULL); _exit(WORKER_UNPROVEN); } }
    if (!from_bulk) exact_start(&src, &cfg, reset_kind, row0);
    S.s_scan += wall() - w0; w0 = wall();
    decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile);

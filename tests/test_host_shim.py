@@ -188,3 +188,58 @@ def test_readtape_b200_product_on_64_super_tiles_equals_reference(tmp_path):
         assert st["misses"] == 0 and st["restarts"] == 0 and st["hits"] >= reps * 64, st
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def _reel(d, reps):
+    import numpy as np
+    from readtape_b200 import synth, tbin
+    tile = synth.nrzi_tile()
+    path = os.path.join(d, "reel.tbin")
+    with open(path, "wb") as fh:
+        fh.write(tbin.build_header(synth.nrzi_header()))
+        for _ in range(reps):
+            tile.tofile(fh)
+        fh.write(np.array([tbin.END_MARK], dtype="<i2").tobytes())
+    return path, reps * tile.shape[0]
+
+
+@pytest.mark.gpu
+def test_readtape_b200_split_between_worker_processes_equals_reference(tmp_path):
+    """RT_WORKERS: one reel split between worker processes at inter-block gaps (each worker scans its share on the GPU and replays it
+    through the reference's handlers; the hand-over between neighbours is PROVEN by rt_bulk_lookup or the reel is decoded unsplit).
+    The concatenated .tap must be byte-identical to the unmodified reference's: 40 super-tiles in 5 workers, and real captures
+    (NRZI 9-track, NRZI 7-track, PE, GCR) split in 3 with small shares forced."""
+    import shutil
+    import tempfile
+    import time
+    ref = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+    if not (os.path.exists(ref) and os.path.exists(CUDA_SHIM)):
+        pytest.skip("reference / product binaries not built")
+    d = tempfile.mkdtemp(prefix="rtw_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        path, nrows = _reel(d, 40)
+        jobs = [("synthetic_40_tiles_5_workers", path, "-q -nm -nrzi -bpi=800 -ips=50 -tap -nolog -nolabels", {"RT_WORKERS": "5"}, 5)]
+        for name, opts in (("PLAGO_beginning", "-q -nm -nrzi -ips=50 -tap -nolog"), ("tss_4secs", "-q -m -nrzi -ntrks=7 -tap -nolog"),
+                           ("LJS009_part1_39blks", "-q -m -ntrks=9 -pe -bpi=1600 -ips=50 -tap -nolog"),
+                           ("1kblks_43blks", "-q -m -gcr -ips=50 -order=76543210p -zeros -correct -tap -nolog")):
+            jobs.append((name + "_3_workers", capture_path(name, full=True), opts,
+                         {"RT_WORKERS": "3", "RT_WORKER_MIN_ROWS": "300000", "RT_WORKER_MARGIN_ROWS": "700000"}, 3))
+        for label, cap, opts, env, nw in jobs:
+            r0 = subprocess.run([ref] + opts.split() + [f"-outf={d}/ref_{label}", cap], capture_output=True, text=True, timeout=900)
+            assert r0.returncode == 0, r0.stdout[-1500:]
+            t0 = time.time()
+            r = subprocess.run([CUDA_SHIM] + opts.split() + [f"-outf={d}/new_{label}", cap], capture_output=True, text=True,
+                               env=dict(os.environ, RT_STATS="1", **env), timeout=900)
+            dt = time.time() - t0
+            assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
+            a = open(f"{d}/new_{label}.tap", "rb").read(); b = open(f"{d}/ref_{label}.tap", "rb").read()
+            workers = len([l for l in r.stdout.splitlines() if "B200 scan: worker" in l and "events" in l]) + 1     # the last one reports as usual
+            unsplit = "decoding the reel unsplit" in r.stdout
+            record_stats(label, {"seconds": round(dt, 2), "tap_bytes": len(a), "workers_reported": workers, "unsplit_fallback": unsplit})
+            assert a == b, f"{label}: .tap differs ({len(a)} vs {len(b)} bytes)\n" + r.stdout[-1500:]
+            assert r.stdout.strip().splitlines()[-1] == r0.stdout.strip().splitlines()[-1], (r.stdout[-300:], r0.stdout[-300:])
+            assert not [f for f in os.listdir(d) if ".part" in f], "part files left behind"
+            if label.startswith("synthetic"):
+                assert workers == nw and not unsplit, r.stdout[-1500:]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
