@@ -608,7 +608,10 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
 
    /* 2. all scan kernels, concurrently, into one event pool: first guess one event per 16 track-samples, regrown on overflow */
    if (total_units) {
-      uint64_t want_chunks = std::max<uint64_t>(4096, (uint64_t)ncfgs * (nrows * nt / 16 / RT_EVC) + total_units * nt);
+      /* first guess: one event per 64 track-samples (0.5 B per track-sample; a block of 800 BPI NRZI at 20 samples per bit has one
+         per ~40, half of a reel is gap) plus one partly filled chunk per (unit, track); an overflow costs one regrowth + rescan, after
+         which the tape's cached pool fits */
+      uint64_t want_chunks = std::max<uint64_t>(4096, (uint64_t)ncfgs * (nrows * nt / 64 / RT_EVC) + total_units * nt);
       for (int attempt = 0; attempt < 3; ++attempt) {
          if (want_chunks > b->pool_chunks) {
             if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
