@@ -72,8 +72,8 @@ k_units_zc(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
 
 bool fast_scan_eligible(const DevCfg &c) {
    if (zc_scan_eligible(c)) return true;
-   return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
-          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH; }
+   return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE || c.density) && !c.invert && !c.differentiate
+          && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH; }
 
 cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                               uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,

@@ -123,8 +123,8 @@ k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
 
 bool sparse_scan_eligible(const DevCfg &c) {
    for (int k = 0; k < c.ntrks; ++k) if (c.T0[k] <= 0) return false;
-   return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE) && !c.invert && !c.differentiate
-          && !c.density && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.m_cand && c.m_cand2 && c.m_acan; }
+   return c.det == RT_DET_PEAK && (c.mode == RT_MODE_NRZI || c.mode == RT_MODE_PE || c.density) && !c.invert && !c.differentiate
+          && c.width >= 3 && c.width <= RT_PKWW_MAX_WIDTH && c.m_cand && c.m_cand2 && c.m_acan; }
 
 /* ---- choosing T0 from the data ----------------------------------------------------------------------------------------------
  * required_rise (decoder.c:785) follows the signal: pkww_rise * (average peak-to-peak height / 4 V) / AGC gain.  A mask threshold

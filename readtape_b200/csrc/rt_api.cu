@@ -446,7 +446,9 @@ static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
    const DevCfg &dc = pl->dc;
    /* proposal thresholds (heuristic) and the exact quiet threshold the scan kernel applies */
    const double lsb = (double)t->desc.maxvolts / 32767.0;
-   const double rows_per_bit = 1.0 / ((double)dc.bpi * dc.ips * dc.sample_deltat);
+   /* density detection (bpi == 0): the bit length is what is being looked for; assume a long one (200 BPI at 50 IPS): fewer and
+      longer units, never a cut inside a block */
+   const double rows_per_bit = dc.bpi > 0 && dc.ips > 0 ? 1.0 / ((double)dc.bpi * dc.ips * dc.sample_deltat) : 1.0 / (200.0 * 50.0 * dc.sample_deltat);
    pl->up = UnitParams{};
    pl->up.det = dc.det;
    pl->quiet_thr = 0;
@@ -522,7 +524,8 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    for (uint32_t i = 0; i < ncfgs; ++i) {
       rc = cfg_check(t, &cfgs[i]); if (rc) return rc;
       if (cfgs[i].mode == RT_MODE_WW) return set_err(RT_ERR_UNSUPPORTED, "Whirlwind state persists across blocks: use rt_scan_*");
-      if (cfgs[i].flags & RT_F_DENSITY_DETECT) return set_err(RT_ERR_UNSUPPORTED, "density detection is a prefix pass: use rt_scan_*"); }
+      if ((cfgs[i].flags & RT_F_DENSITY_DETECT) && (cfgs[i].flags & RT_F_FIND_ZEROS))
+         return set_err(RT_ERR_UNSUPPORTED, "density detection with the zero-crossing detector: use rt_scan_*"); }
    const bool trace = getenv("RT_TRACE") != nullptr;
    auto wall0 = std::chrono::steady_clock::now();
    auto lap = [&](const char *what) {

@@ -263,7 +263,8 @@ struct UnitScan {
       const double t_ev = top ? t.t_top : t.t_bot;
       const float v_top_seen = t.v_top, v_bot_seen = t.v_bot;
       ++t.peakcount;
-      if (c.mode == RT_MODE_NRZI) rtfb::nrzi_feedback(c, t, top);
+      if (c.density) { /* doing_density_detection: the mode handlers are bypassed (decoder.c:578), AGC and average height stay put */ }
+      else if (c.mode == RT_MODE_NRZI) rtfb::nrzi_feedback(c, t, top);
       else if (c.mode == RT_MODE_PE) rtfb::pe_feedback(c, t, top, t_ev);
       else rtfb::agc_adjust(c, t);
       if (top) t.v_lasttop = t.v_top; else t.v_lastbot = t.v_bot;

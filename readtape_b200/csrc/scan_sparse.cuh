@@ -216,7 +216,8 @@ struct SparseScan {
       const double t_ev = top ? t.t_top : t.t_bot;
       const float v_top_seen = t.v_top, v_bot_seen = t.v_bot;
       ++t.peakcount;
-      if (c.mode == RT_MODE_NRZI) rtfb::nrzi_feedback(c, t, top);
+      if (c.density) { /* doing_density_detection: the mode handlers are bypassed (decoder.c:578), AGC and average height stay put */ }
+      else if (c.mode == RT_MODE_NRZI) rtfb::nrzi_feedback(c, t, top);
       else if (c.mode == RT_MODE_PE) rtfb::pe_feedback(c, t, top, t_ev);
       else rtfb::agc_adjust(c, t);
       if (top) t.v_lasttop = t.v_top; else t.v_lastbot = t.v_bot;
@@ -474,7 +475,8 @@ struct SparseScan {
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
       meta.last_event_row = em.last_row;
-      meta.quiet_tail_from = qthr > 0 ? quiet_tail(end > (uint32_t)c.prescan_rows ? end - (uint32_t)c.prescan_rows : 0u) : RT_NOROW;
+      /* only the unit that ends the tape needs it: behind every other unit the next one's quiet pre-scan examines the same rows */
+      meta.quiet_tail_from = qthr > 0 && row0 + end >= c.nrows ? quiet_tail(end > (uint32_t)c.prescan_rows ? end - (uint32_t)c.prescan_rows : 0u) : RT_NOROW;
       meta.first_chunk = em.first_chunk; meta.nevents = em.n; meta.failed = t.failed; meta.pad = end > ndense ? end - ndense : 0; } };   /* pad: rows not walked (diagnostics) */
 
 /* Drive one lane (host) or the 32 lanes of a warp (device) through (unit, track) jobs.  `Jobs` provides

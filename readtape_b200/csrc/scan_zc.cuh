@@ -225,7 +225,8 @@ struct ZcScan {
       meta.sync_early = sync_early == OFF_NONE ? RT_NOROW : row0 + (uint64_t)sync_early;
       meta.loud_early = loud_early == OFF_NONE ? RT_NOROW : (uint64_t)((int64_t)row0 + loud_early);
       meta.last_event_row = em.last_row;
-      {  /* the tail rule: the last sample beyond ZEROCROSS_PEAK keeps the rows up to qL - 1 behind it loud */
+      meta.quiet_tail_from = RT_NOROW;
+      if (row0 + end >= c.nrows) {  /* the tail rule (the unit that ends the tape): the last sample beyond ZEROCROSS_PEAK keeps the rows up to qL - 1 behind it loud */
          const uint32_t lo = end > (uint32_t)c.prescan_rows ? end - (uint32_t)c.prescan_rows : 0u;
          int64_t scan_lo = (int64_t)lo - (qL - 1); if ((int64_t)row0 + scan_lo < 0) scan_lo = -(int64_t)row0;
          int64_t r = (int64_t)end - 1;

@@ -38,6 +38,7 @@
 #include <time.h>
 #include <unistd.h>
 #include <sys/wait.h>
+#include <sys/mman.h>
 
 /* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
 extern FILE *inf;
@@ -52,7 +53,7 @@ extern long long lines_in, numsamples, numoutbytes;
 extern double torigin;
 extern bool tap_format, do_txtfile, deskew, skew_given;
 extern FILE *outf;
-extern int numblks;
+extern int numblks, numblks_limit;
 extern char baseoutfilename[], baseinfilename[];
 void create_datafile(const char *name);                /* readtape.c:1092 */
 void output_tap_marker(uint32_t num);                  /* readtape.c:1077 */
@@ -68,7 +69,7 @@ static struct {
    rt_tape_desc desc;
    long long base_pos;              /* file offset of row 0 */
    uint64_t nrows;                  /* rows before the end marker */
-   int16_t *rows; size_t rows_bytes;/* pinned copy of the payload */
+   size_t rows_bytes;               /* payload bytes uploaded */
    /* the pending reset, noted by the wrapped reset functions */
    int pending_reset;               /* RT_RESET_*; RT_RESET_NONE if none since the last readblock() */
    /* stateful exact context (Whirlwind, and the fallback for everything else) */
@@ -162,18 +163,23 @@ static void open_tape(void) {
       S.desc.tstart_ns += first * S.desc.tdelta_ns; }
    int dev = getenv("RT_DEVICE") ? atoi(getenv("RT_DEVICE")) : 0;
    if (S.worker >= 0 && getenv("RT_DEVICES") && atoi(getenv("RT_DEVICES")) > 1) dev = S.worker % atoi(getenv("RT_DEVICES"));   /* one reel over several GPUs */
+   double w1 = wall();
    int rc = rt_open(&S.desc, dev, &S.tape);
    if (rc) rtfatal("rt_open", rc);
+   double w2 = wall();
+   /* the payload goes to the GPU straight from the page cache: the file is mapped, not read into a (pinned) copy */
    S.rows_bytes = (size_t)(nrows_file * rowbytes);
-   S.rows = rt_host_alloc(S.rows_bytes + 16);
-   assert(S.rows != NULLP, "cannot allocate %lld bytes of pinned memory", (long long)S.rows_bytes);
-   {  size_t got = 0;                                    /* pread: the stdio position of `inf` stays where the host put it */
-      while (got < S.rows_bytes) {
-         ssize_t n = pread(fileno(inf), (char *)S.rows + got, S.rows_bytes - got, (off_t)(S.base_pos + (long long)got));
-         assert(n > 0, "cannot read the .tbin payload");
-         got += (size_t)n; } }
-   rc = rt_upload(S.tape, S.rows, nrows_file);
+   const long pg = sysconf(_SC_PAGESIZE);
+   const off_t map_off = (off_t)(S.base_pos / pg * pg);
+   const size_t map_len = S.rows_bytes + (size_t)(S.base_pos - map_off);
+   void *map = map_len ? mmap(NULLP, map_len, PROT_READ, MAP_PRIVATE, fileno(inf), map_off) : NULLP;
+   assert(map_len == 0 || map != MAP_FAILED, "cannot map the .tbin payload");
+   if (map_len) madvise(map, map_len, MADV_SEQUENTIAL);
+   rc = rt_upload(S.tape, (const int16_t *)((const char *)map + (S.base_pos - map_off)), nrows_file);
    if (rc) rtfatal("rt_upload", rc);
+   if (map_len) munmap(map, map_len);
+   if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2)
+      rlog("  B200 scan: rt_open %.3f s, upload of %.2f GB %.3f s\n", w2 - w1, S.rows_bytes / 1e9, wall() - w2);
    S.nrows = rt_nrows(S.tape);
    S.use_bulk = !(getenv("RT_NO_BULK") && atoi(getenv("RT_NO_BULK")));
    S.opened = 1;
@@ -257,7 +263,9 @@ static void say_miss(rt_bulk *bulk, uint64_t row) {
 
 static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    int ps = block.parmset;
-   if (!S.use_bulk || mode == WW || doing_density_detection || doing_deskew) return 0;   /* prefix passes: exact scan */
+   if (!S.use_bulk || mode == WW) return 0;         /* Whirlwind: the detector state persists from block to block */
+   /* the density and deskew pre-passes (readtape.c:1656-1717) reset per block like the main pass: the same speculative scan
+      serves them, with their own configuration (handlers bypassed and width 8 / skew delays still zero) */
    if (S.bulk[ps].valid && memcmp(&S.bulk[ps].cfg, cfg, sizeof *cfg) != 0) {    /* e.g. the skew changed after the pre-pass */
       rt_bulk_free(S.bulk[ps].bulk); S.bulk[ps].valid = 0; }
    if (!S.bulk[ps].valid) {
@@ -546,7 +554,7 @@ static void run_workers(void) {
    int P = env ? atoi(env) : 1;
    if (P <= 1) return;
    if (!(tbin_file && tap_format && quiet && !do_txtfile && mode != WW && subsample == 1 && bpi != 0 && !doing_density_detection
-         && !doing_deskew && (!deskew || skew_given) && numblks == 0 && outf == NULLP)) return;
+         && !doing_deskew && (!deskew || skew_given) && numblks == 0 && numblks_limit == INT_MAX && outf == NULLP)) return;
    long long pos = ftello(inf);
    assert(pos >= 0 && fseeko(inf, 0, SEEK_END) == 0, "fseek failed");
    long long end = ftello(inf);
@@ -567,6 +575,7 @@ static void run_workers(void) {
          S.nominal_lo = (uint64_t)i * N / (uint64_t)P / 2048 * 2048;
          S.nominal_hi = i == P - 1 ? N : (uint64_t)(i + 1) * N / (uint64_t)P / 2048 * 2048;
          S.must_seek_start = i > 0;
+         if (i > 0) numblks = 1 << 20;                         /* "wrote block 1" (readtape.c:1271) is the first worker's line */
          part_name(name, sizeof name, i, ".out");
          assert(freopen(name, "w", stdout) != NULLP, "cannot create %s", name);
          part_name(name, sizeof name, i, "");

@@ -73,7 +73,7 @@ def test_fast_path_reproduces_reference_events(name, fast_host):
     planes, stride = make_planes(rows[:nrows], desc)
     done = skipped = walked = 0
     for seg in segs:
-        if seg.reset_kind != abi.RT_RESET_FULL or (seg.flags & abi.RT_F_DENSITY_DETECT):
+        if seg.reset_kind != abi.RT_RESET_FULL:
             continue
         cfg = evlog.cfg_for(seg)
         stop = seg.end_row if seg.end_row >= 0 else nrows

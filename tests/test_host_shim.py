@@ -233,7 +233,7 @@ def test_readtape_b200_split_between_worker_processes_equals_reference(tmp_path)
             dt = time.time() - t0
             assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
             a = open(f"{d}/new_{label}.tap", "rb").read(); b = open(f"{d}/ref_{label}.tap", "rb").read()
-            workers = len([l for l in r.stdout.splitlines() if "B200 scan: worker" in l and "events" in l]) + 1     # the last one reports as usual
+            workers = len([l for l in r.stdout.splitlines() if "B200 scan: worker" in l and "speculative hits" in l]) + 1     # the last one reports as usual
             unsplit = "decoding the reel unsplit" in r.stdout
             record_stats(label, {"seconds": round(dt, 2), "tap_bytes": len(a), "workers_reported": workers, "unsplit_fallback": unsplit})
             assert a == b, f"{label}: .tap differs ({len(a)} vs {len(b)} bytes)\n" + r.stdout[-1500:]
