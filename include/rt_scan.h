@@ -129,6 +129,12 @@ typedef struct rt_scan rt_scan;   /* a stateful scan context (per-track detector
 typedef struct rt_bulk rt_bulk;   /* result of a whole-tape speculative scan                  */
 
 const char *rt_last_error(void);
+/* Process-wide options.  RT_OPT_SHARED_RESULTS (value 0/1): rt_bulk_fetch() places the events in an anonymous MAP_SHARED mapping
+ * (pinned only while the copy runs) instead of cudaHostAlloc memory, so that worker processes forked AFTER the fetch can read them.
+ * Such children must not call anything of this library that touches the device: only rt_bulk_lookup() with bridge scans off
+ * (environment RT_BRIDGE=0), rt_bulk_last_unit(), rt_bulk_unit_info() / rt_bulk_unit_at(). */
+#define RT_OPT_SHARED_RESULTS 1
+int  rt_set_option(int option, int value);
 int  rt_abi_version(void);
 /* Name of the implementation behind the ABI: "cuda-sm100a" or "oracle-cpu". */
 const char *rt_backend(void);

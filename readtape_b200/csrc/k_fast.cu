@@ -80,13 +80,11 @@ cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t n
                               unsigned long long *rows_scanned, int sms, int max_ctas_per_sm, cudaStream_t s) {
    if (zc_scan_eligible(c)) {
       const size_t zsmem = (size_t)zc_scratch_words(c) * FAST_THREADS * sizeof(uint32_t);
-      static size_t zcfg_smem = 0; static int zcfg_per_sm = 0;
+      int zcfg_per_sm = 0;                                            /* per launch: attributes are per device, not per process */
       cudaError_t ze;
-      if (zcfg_smem != zsmem) {
-         ze = cudaFuncSetAttribute(k_units_zc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem); if (ze != cudaSuccess) return ze;
-         ze = cudaFuncSetAttribute(k_units_zc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); if (ze != cudaSuccess) return ze;
-         ze = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zcfg_per_sm, k_units_zc, FAST_THREADS, zsmem); if (ze != cudaSuccess) return ze;
-         zcfg_smem = zsmem; }
+      ze = cudaFuncSetAttribute(k_units_zc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem); if (ze != cudaSuccess) return ze;
+      ze = cudaFuncSetAttribute(k_units_zc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); if (ze != cudaSuccess) return ze;
+      ze = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zcfg_per_sm, k_units_zc, FAST_THREADS, zsmem); if (ze != cudaSuccess) return ze;
       int zper = zcfg_per_sm < 1 ? 1 : zcfg_per_sm;
       if (max_ctas_per_sm > 0 && zper > max_ctas_per_sm) zper = max_ctas_per_sm;
       uint64_t zgrid = ((uint64_t)nunits * (uint64_t)c.ntrks + FAST_THREADS - 1) / FAST_THREADS;
@@ -97,16 +95,14 @@ cudaError_t launch_units_fast(const DevCfg &c, const UnitDesc *units, uint32_t n
       return cudaGetLastError(); }
    const uint32_t ring = ring_size(c.width);
    const size_t smem = (size_t)scratch_words(c.width) * FAST_THREADS * sizeof(uint32_t);
-   static size_t cfg_smem = 0; static int cfg_per_sm = 0;          /* function attributes: set once per shared-memory size */
+   int cfg_per_sm = 0;                                              /* per launch: attributes are per device, not per process */
    cudaError_t e;
-   if (cfg_smem != smem) {
-      e = cudaFuncSetAttribute(k_units_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_units_fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (e != cudaSuccess) return e;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm, k_units_fast, FAST_THREADS, smem);
-      if (e != cudaSuccess) return e;
-      cfg_smem = smem; }
+   e = cudaFuncSetAttribute(k_units_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+   if (e != cudaSuccess) return e;
+   e = cudaFuncSetAttribute(k_units_fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+   if (e != cudaSuccess) return e;
+   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_per_sm, k_units_fast, FAST_THREADS, smem);
+   if (e != cudaSuccess) return e;
    int per_sm = cfg_per_sm < 1 ? 1 : cfg_per_sm;
    if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;       /* leave room for concurrent ingest kernels */
    const uint64_t threads = (uint64_t)nunits * (uint64_t)c.ntrks;

@@ -181,11 +181,10 @@ k_ingest_simple(IngestArgs a, uint64_t row_from, uint64_t row_to, int nheads) {
 template <int NH>
 static cudaError_t launch_tma(const IngestArgs &a, uint64_t ntiles, int sms, cudaStream_t st) {
    const size_t smem = (size_t)ING_NSTAGE * ING_TROWS * NH * 2 + (size_t)NH * ING_THREADS * 4 + 2 * ING_NSTAGE * 8;
-   static bool configured = false;
-   if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(k_ingest_tma<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = true; }
+   /* function attributes belong to the device / context of the launch: set on every launch (a host-side table look-up), never
+      cached in a process-wide static -- a second device, or a second thread with another tape, must see them too */
+   cudaError_t e = cudaFuncSetAttribute(k_ingest_tma<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+   if (e != cudaSuccess) return e;
    int grid = (int)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
    k_ingest_tma<NH><<<grid, ING_THREADS, smem, st>>>(a, ntiles);
    return cudaGetLastError(); }

@@ -196,9 +196,9 @@ bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist) {
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s) {
-   static int occ = 0, per_sm_cached = 0;
+   int occ = 0, per_sm_cached = 0;                                  /* per launch: the occupancy belongs to the device of the launch */
    cudaError_t e;
-   if (!occ) {
+   {
       const char *env = getenv("RT_SPARSE_OCC");
       occ = env ? atoi(env) : 4;
       if (occ != 5 && occ != 6 && occ != 8) occ = 4;

@@ -5,6 +5,11 @@
  * image) is usable, rt_open() fails with RT_ERR_NODEVICE -- there is no fallback.
  */
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -28,6 +33,12 @@ static int set_err(int code, const char *fmt, ...) {
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 extern "C" const char *rt_last_error(void) { return g_err; }
+
+/* process-wide options (rt_set_option) */
+static int g_opt_shared_results = 0;
+extern "C" int rt_set_option(int option, int value) {
+   if (option == RT_OPT_SHARED_RESULTS) { g_opt_shared_results = value != 0; return RT_OK; }
+   return set_err(RT_ERR_ARG, "rt_set_option: unknown option %d", option); }
 extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
 extern "C" const char *rt_backend(void) { return "cuda-sm100a"; }
 
@@ -63,6 +74,7 @@ struct rt_tape {
    std::vector<cudaStream_t> s_par;                               /* rt_bulk_scan with several configurations: their kernels run side by side */
    cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[2] = {nullptr, nullptr};
    uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
+   int16_t *h_ring = nullptr; cudaEvent_t ring_done[6] = {};       /* pinned ring for uploads from pageable memory */
 };
 
 static int tape_reserve(rt_tape *t, uint64_t rows) {
@@ -172,6 +184,52 @@ static int enqueue_chunk(rt_tape *t, const int16_t *src, uint64_t n, int buf) {
    CU(cudaEventRecord(t->stage_done[buf], t->stream));
    return RT_OK; }
 
+/* Upload from PAGEABLE host memory (a file mapping, a malloc'd buffer): cudaMemcpyAsync would stage such a copy through the driver's
+   own bounce buffer with one thread (~10 GB/s).  Instead a few threads copy chunks into a ring of pinned buffers while the copy
+   engine drains them, which keeps PCIe busy (RT_UPLOAD_THREADS, default 4). */
+static int upload_pageable(rt_tape *t, const int16_t *rows, uint64_t nrows, uint64_t stage_rows) {
+   const uint64_t nh = t->desc.nheads;
+   const int NB = 6;
+   const size_t slot_bytes = (size_t)stage_rows * nh * 2;
+   if (!t->h_ring) {
+      CU(cudaHostAlloc(&t->h_ring, slot_bytes * NB, cudaHostAllocDefault));
+      for (int i = 0; i < NB; ++i) CU(cudaEventCreateWithFlags(&t->ring_done[i], cudaEventDisableTiming)); }
+   const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
+   const char *env = getenv("RT_UPLOAD_THREADS");
+   int nthreads = env ? atoi(env) : 4;
+   nthreads = std::max(1, std::min<int>(nthreads, (int)std::min<uint64_t>(nchunks, 16)));
+   std::mutex mu; std::condition_variable cv;
+   std::vector<char> filled(nchunks, 0);
+   uint64_t released = 0;                                         /* chunks whose ring slot may be overwritten again */
+   std::atomic<uint64_t> next{0};
+   auto producer = [&]() {
+      for (;;) {
+         const uint64_t i = next.fetch_add(1);
+         if (i >= nchunks) return;
+         { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return i < released + NB; }); }
+         const uint64_t r0 = i * stage_rows, n = std::min(stage_rows, nrows - r0);
+         memcpy(reinterpret_cast<char *>(t->h_ring) + (size_t)(i % NB) * slot_bytes, rows + r0 * nh, (size_t)n * nh * 2);
+         { std::lock_guard<std::mutex> lk(mu); filled[i] = 1; }
+         cv.notify_all(); } };
+   std::vector<std::thread> th;
+   for (int k = 0; k < nthreads; ++k) th.emplace_back(producer);
+   int rc = RT_OK;
+   for (uint64_t i = 0; i < nchunks; ++i) {
+      { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return filled[i] != 0; }); }
+      const uint64_t r0 = i * stage_rows, n = std::min(stage_rows, nrows - r0);
+      if (rc == RT_OK) {
+         rc = enqueue_chunk(t, reinterpret_cast<const int16_t *>(reinterpret_cast<char *>(t->h_ring) + (size_t)(i % NB) * slot_bytes), n, (int)(i & 1));
+         if (rc == RT_OK && cudaEventRecord(t->ring_done[i % NB], t->s_copy) != cudaSuccess) rc = set_err(RT_ERR_CUDA, "cudaEventRecord failed"); }
+      if (i + 2 >= (uint64_t)NB) {                                /* keep NB - 2 copies in flight, then free the oldest slot */
+         const uint64_t k = i + 2 - NB;
+         if (rc == RT_OK) cudaEventSynchronize(t->ring_done[k % NB]);
+         { std::lock_guard<std::mutex> lk(mu); released = k + 1; }
+         cv.notify_all(); } }
+   { std::lock_guard<std::mutex> lk(mu); released = nchunks; }
+   cv.notify_all();
+   for (auto &x : th) x.join();
+   return rc; }
+
 extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
    if (!t || (!rows && nrows)) return set_err(RT_ERR_ARG, "rt_upload: null argument");
    if (nrows == 0) return RT_OK;
@@ -181,6 +239,16 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
    const uint64_t nh = t->desc.nheads;
    uint64_t stage_rows = 0;
    rc = stage_prepare(t, nrows, &stage_rows); if (rc) return rc;
+   if (nrows >= 4 * stage_rows && stage_rows) {                   /* a large upload from pageable memory: staged by our own threads */
+      cudaPointerAttributes pa{};
+      const bool pageable = cudaPointerGetAttributes(&pa, rows) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+      cudaGetLastError();
+      const char *env = getenv("RT_UPLOAD_THREADS");
+      if (pageable && !(env && atoi(env) == 0)) {
+         rc = upload_pageable(t, rows, nrows, stage_rows);
+         if (rc) { cudaDeviceSynchronize(); return rc; }
+         t->h2d_bytes += nrows * nh * 2;
+         return tape_drain(t); } }
    if (t->nrows % 2048 != 0 && !t->force_simple_ingest) { /* appended onto a partial tile: fine, the plain kernel handles it */ }
    /* copies on the copy stream, ingest kernels on the tape's stream, two staging buffers; one synchronisation at the end */
    uint64_t done = 0; int buf = 0;
@@ -233,6 +301,7 @@ extern "C" void rt_close(rt_tape *t) {
    cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
    cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
+   if (t->h_ring) { cudaFreeHost(t->h_ring); for (auto e : t->ring_done) if (e) cudaEventDestroy(e); }
    if (t->s_copy) cudaStreamDestroy(t->s_copy);
    if (t->stream) cudaStreamDestroy(t->stream);
    for (auto st : t->s_par) cudaStreamDestroy(st);
@@ -429,6 +498,7 @@ struct rt_bulk {
    rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr; uint32_t pool_chunks = 0, chunks_used = 0;
    bool pool_from_cache = false, pin_from_cache = false;
    rt_event *h_pool = nullptr; size_t h_pool_events = 0;          /* pinned */
+   size_t h_pool_shared_bytes = 0;                                /* != 0: h_pool is an anonymous MAP_SHARED mapping of this size (RT_OPT_SHARED_RESULTS) */
    std::vector<uint32_t> chunk_next;
    std::vector<rt_event> result;
    rt_scan *bridge = nullptr; uint32_t bridge_cfg = ~0u;          /* exact context for bridge scans (rt_bulk_lookup) */
@@ -512,7 +582,8 @@ extern "C" void rt_bulk_free(rt_bulk *b) {
    rt_tape *t = b->tape;
    cudaSetDevice(t->device);
    if (b->bridge) rt_scan_end(b->bridge);
-   if (b->pin_from_cache) t->pin_cache_busy = false; else if (b->h_pool) cudaFreeHost(b->h_pool);
+   if (b->h_pool_shared_bytes) munmap(b->h_pool, b->h_pool_shared_bytes);
+   else if (b->pin_from_cache) t->pin_cache_busy = false; else if (b->h_pool) cudaFreeHost(b->h_pool);
    if (b->pool_from_cache) t->pool_cache_busy = false; else { cudaFree(b->d_pool); cudaFree(b->d_chunk_next); }
    for (auto &c : b->cfgs) { if (c.d_units) cudaFreeAsync(c.d_units, t->stream); if (c.d_meta) cudaFreeAsync(c.d_meta, t->stream); }
    delete b; }
@@ -686,6 +757,19 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
    if (b->chunks_used) {
       CU(cudaMemcpyAsync(b->chunk_next.data(), b->d_chunk_next, (size_t)b->chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
       b->h_pool_events = (size_t)b->chunks_used * RT_EVC;
+      if (g_opt_shared_results) {
+         /* memory that worker processes forked after this call can read: shared anonymous pages, pinned only while the copy runs */
+         const size_t bytes = (b->h_pool_events * sizeof(rt_event) + 4095) / 4096 * 4096;
+         void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_POPULATE, -1, 0);
+         if (p == MAP_FAILED) return set_err(RT_ERR_NOMEM, "rt_bulk_fetch: cannot map %zu bytes of shared memory", bytes);
+         b->h_pool = static_cast<rt_event *>(p); b->h_pool_shared_bytes = bytes;
+         const bool reg = cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess;
+         if (!reg) cudaGetLastError();
+         CU(cudaMemcpyAsync(b->h_pool, b->d_pool, b->h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
+         CU(cudaStreamSynchronize(t->stream));
+         if (reg) cudaHostUnregister(p);
+         b->stats.d2h_bytes += b->h_pool_events * sizeof(rt_event) + (uint64_t)b->chunks_used * 4; }
+      else {
       if (!t->pin_cache_busy) {                                  /* use / grow the tape's cached pinned buffer */
          if (b->h_pool_events > t->pin_cache_events) {
             if (t->pin_cache) cudaFreeHost(t->pin_cache);
@@ -696,7 +780,7 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
          b->h_pool = t->pin_cache; b->pin_from_cache = true; t->pin_cache_busy = true; }
       else CU(cudaHostAlloc(&b->h_pool, b->h_pool_events * sizeof(rt_event), cudaHostAllocDefault));
       CU(cudaMemcpyAsync(b->h_pool, b->d_pool, b->h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
-      b->stats.d2h_bytes += b->h_pool_events * sizeof(rt_event) + (uint64_t)b->chunks_used * 4; }
+      b->stats.d2h_bytes += b->h_pool_events * sizeof(rt_event) + (uint64_t)b->chunks_used * 4; } }
    CU(cudaStreamSynchronize(t->stream));
    /* the device copies are no longer needed */
    for (BulkCfg &bc : b->cfgs) {

@@ -248,18 +248,24 @@ static void continue_exact(struct evsrc *src) {
    src->taken = taken; src->last_row = last_row; src->last_trk = last_trk; }
 
 /* diagnostics (RT_STATS=2): why no speculative unit could be proven equivalent to a fresh reset at `row` */
+static void say_unit(const rt_unit_info *ui, uint64_t row, int all) {
+   rlog("     unit %llu of %llu [%llu, %llu)\n", (unsigned long long)ui->unit_index, (unsigned long long)ui->nunits,
+        (unsigned long long)ui->row0, (unsigned long long)ui->row_end);
+   for (uint32_t k = 0; k < ui->ntrks; ++k) {
+      const int late = ui->sync_row[k] != UINT64_MAX && ui->sync_row[k] >= ui->need_sync_row[k] && (ui->last_loud_row[k] == UINT64_MAX || ui->last_loud_row[k] < row);
+      const int early = ui->sync_early[k] != UINT64_MAX && ui->sync_early[k] >= ui->need_sync_row[k] && (ui->loud_early[k] == UINT64_MAX || ui->loud_early[k] < row);
+      if ((late || early) && !all) continue;
+      rlog("       trk %u%s: first event %lld, sync %lld (loud %lld), early sync %lld (loud %lld), need %lld, failed %u, events %u\n", k, late || early ? " ok" : "",
+           (long long)ui->first_event_row[k], (long long)ui->sync_row[k], (long long)ui->last_loud_row[k], (long long)ui->sync_early[k],
+           (long long)ui->loud_early[k], (long long)ui->need_sync_row[k], ui->failed[k], ui->nevents[k]); } }
 static void say_miss(rt_bulk *bulk, uint64_t row) {
-   static rt_unit_info ui;
+   static rt_unit_info ui, un;
    if (rt_bulk_unit_info(bulk, 0, row, &ui) != RT_OK) { rlog("  B200 scan: miss at row %llu: no unit\n", (unsigned long long)row); return; }
-   rlog("  B200 scan: miss at row %llu: unit %llu of %llu [%llu, %llu)\n", (unsigned long long)row, (unsigned long long)ui.unit_index,
-        (unsigned long long)ui.nunits, (unsigned long long)ui.row0, (unsigned long long)ui.row_end);
-   for (uint32_t k = 0; k < ui.ntrks; ++k) {
-      const int late = ui.sync_row[k] != UINT64_MAX && ui.sync_row[k] >= ui.need_sync_row[k] && (ui.last_loud_row[k] == UINT64_MAX || ui.last_loud_row[k] < row);
-      const int early = ui.sync_early[k] != UINT64_MAX && ui.sync_early[k] >= ui.need_sync_row[k] && (ui.loud_early[k] == UINT64_MAX || ui.loud_early[k] < row);
-      if (late || early) continue;
-      rlog("     trk %u: first event %lld, sync %lld (loud %lld), early sync %lld (loud %lld), need %lld, failed %u, events %u\n", k,
-           (long long)ui.first_event_row[k], (long long)ui.sync_row[k], (long long)ui.last_loud_row[k], (long long)ui.sync_early[k],
-           (long long)ui.loud_early[k], (long long)ui.need_sync_row[k], ui.failed[k], ui.nevents[k]); } }
+   rlog("  B200 scan: miss at row %llu, parmset %d\n", (unsigned long long)row, block.parmset);
+   say_unit(&ui, row, 0);
+   if (rt_bulk_unit_at(bulk, 0, ui.unit_index + 1, &un) == RT_OK) {
+      for (uint32_t k = 0; k < un.ntrks; ++k) un.need_sync_row[k] = ui.need_sync_row[k];       /* as seen from `row` */
+      say_unit(&un, row, 0); } }
 
 static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    int ps = block.parmset;
