@@ -39,6 +39,8 @@
 #include <unistd.h>
 #include <sys/wait.h>
 #include <sys/mman.h>
+#include <sys/socket.h>
+#include <poll.h>
 
 /* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
 extern FILE *inf;
@@ -75,7 +77,7 @@ static struct {
    /* stateful exact context (Whirlwind, and the fallback for everything else) */
    rt_scan *ctx; rt_scan_cfg ctx_cfg; int ctx_valid;
    /* speculative whole-tape scans, one per parameter set on demand */
-   struct { rt_bulk *bulk; rt_scan_cfg cfg; int valid; } bulk[MAXPARMSETS];
+   struct { rt_bulk *bulk; rt_scan_cfg cfg; int valid; uint32_t ci; int shared; } bulk[MAXPARMSETS];   /* ci: configuration index inside `bulk` */
    int use_bulk;
    /* statistics */
    long long n_bulk_hits, n_bulk_miss, n_exact_spans, n_events, n_restarts;
@@ -83,20 +85,16 @@ static struct {
    int said_config;
    /* one reel split between worker processes (RT_WORKERS, see run_workers) */
    int par_checked, nworkers, worker;   /* worker: 0 .. nworkers-1, or -1 for the classic single process */
-   uint64_t file_rows;                  /* rows in the file, counted from the position of the first readblock() */
-   uint64_t nominal_lo, nominal_hi;     /* this worker's share of the reel, file rows (cut points are moved to inter-block gaps) */
-   uint64_t row_off;                    /* file row of tape row 0 (the worker only holds its share plus a margin) */
-   uint64_t stop_row;                   /* tape row of the unit boundary where the next worker starts; UINT64_MAX: run to the end */
-   int worker_ready;                    /* the worker's boundaries are known */
+   uint64_t start_row;                  /* worker: the unit boundary this worker starts at */
+   uint64_t stop_row;                   /* the unit boundary where the next worker starts; UINT64_MAX: run to the end */
    int must_seek_start;                 /* worker > 0: the first readblock() call only positions the file at the worker's first row */
-} S = { .worker = -1, .stop_row = UINT64_MAX };
+   int remote_fd; rt_event *remote_buf; /* worker: exact scans are done by the parent (the only process with a CUDA context) */
+} S = { .worker = -1, .stop_row = UINT64_MAX, .remote_fd = -1 };
 
 static double wall(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 #define EXACT_SPAN_ROWS  (1u << 17)
-/* rows a worker holds beyond its nominal share on both sides (the cut moves to the next gap), and the smallest share a reel is split
-   into; the environment overrides exist for tests on the small bundled captures */
-#define WORKER_MARGIN_ROWS  (getenv("RT_WORKER_MARGIN_ROWS") ? strtoull(getenv("RT_WORKER_MARGIN_ROWS"), NULLP, 10) : (uint64_t)(4u << 20))
+/* the smallest share a reel is split into; the environment override exists for tests on the small bundled captures */
 #define WORKER_MIN_ROWS     (getenv("RT_WORKER_MIN_ROWS") ? strtoull(getenv("RT_WORKER_MIN_ROWS"), NULLP, 10) : (uint64_t)(8u << 20))
 #define WORKER_UNPROVEN     98              /* exit code of a worker whose hand-over could not be proven: the reel is decoded unsplit */
 
@@ -152,17 +150,7 @@ static void open_tape(void) {
    assert(fseeko(inf, S.base_pos, SEEK_SET) == 0, "fseek failed");
    uint64_t rowbytes = (uint64_t)nheads * 2;
    uint64_t nrows_file = (uint64_t)(end - S.base_pos) / rowbytes;
-   uint64_t first = 0;                                   /* file rows [first, first + nrows_file) go to the GPU */
-   if (S.worker >= 0) {                                  /* a worker holds its share of the reel plus a margin on both sides */
-      uint64_t lo = S.nominal_lo > WORKER_MARGIN_ROWS ? (S.nominal_lo - WORKER_MARGIN_ROWS) / 2048 * 2048 : 0;
-      uint64_t hi = S.worker == S.nworkers - 1 ? nrows_file : S.nominal_hi + WORKER_MARGIN_ROWS;
-      if (hi > nrows_file) hi = nrows_file;
-      first = lo; nrows_file = hi - lo;
-      S.row_off = first;
-      S.base_pos += (long long)(first * rowbytes);        /* from here on, rows are counted from the worker's first row */
-      S.desc.tstart_ns += first * S.desc.tdelta_ns; }
    int dev = getenv("RT_DEVICE") ? atoi(getenv("RT_DEVICE")) : 0;
-   if (S.worker >= 0 && getenv("RT_DEVICES") && atoi(getenv("RT_DEVICES")) > 1) dev = S.worker % atoi(getenv("RT_DEVICES"));   /* one reel over several GPUs */
    double w1 = wall();
    int rc = rt_open(&S.desc, dev, &S.tape);
    if (rc) rtfatal("rt_open", rc);
@@ -206,7 +194,23 @@ static void ctx_prepare(const rt_scan_cfg *cfg) {
       rc = rt_scan_set_cfg(S.ctx, cfg); if (rc) rtfatal("rt_scan_set_cfg", rc);
       S.ctx_cfg = *cfg; } }
 
+/* worker processes have no CUDA context: their exact scans (misses, continuations) are served by the parent over a socket pair,
+   the events come back through a shared buffer */
+struct wreq { int op; int reset_kind; uint64_t row; rt_scan_cfg cfg; };
+struct wrsp { int rc; uint64_t n, pos, done; char err[160]; };
+enum { WOP_START = 1, WOP_MORE = 2 };
+static void xfer(int fd, void *p, size_t n, int wr) {
+   char *c = p;
+   while (n) { ssize_t k = wr ? write(fd, c, n) : read(fd, c, n); if (k <= 0) fatal("B200 scan: lost the connection to the scanning process"); c += k; n -= (size_t)k; } }
+static void remote_exact(struct evsrc *src, struct wreq *rq) {
+   struct wrsp rs;
+   xfer(S.remote_fd, rq, sizeof *rq, 1); xfer(S.remote_fd, &rs, sizeof rs, 0);
+   if (rs.rc) fatal("B200 scan: exact scan failed in the scanning process (%d): %s", rs.rc, rs.err);
+   src->ev = S.remote_buf; src->n = rs.n; src->at = 0; ++S.n_exact_spans;
+   src->valid_end = rs.done ? rs.pos : UINT64_MAX; }
+
 static void exact_more(struct evsrc *src) {  /* continue the exact scan by one span */
+   if (S.remote_fd >= 0) { struct wreq rq; memset(&rq, 0, sizeof rq); rq.op = WOP_MORE; remote_exact(src, &rq); return; }
    uint64_t done = 0;
    int rc = rt_scan_run(S.ctx, EXACT_SPAN_ROWS, &src->ev, &src->n, &done);
    if (rc) rtfatal("rt_scan_run", rc);
@@ -214,6 +218,11 @@ static void exact_more(struct evsrc *src) {  /* continue the exact scan by one s
    if (done == 0) src->valid_end = UINT64_MAX; /* end of tape: nothing more will ever come */ }
 
 static void exact_start(struct evsrc *src, const rt_scan_cfg *cfg, int reset_kind, uint64_t row) {
+   if (S.remote_fd >= 0) {
+      struct wreq rq; memset(&rq, 0, sizeof rq); rq.op = WOP_START; rq.reset_kind = reset_kind; rq.row = row; rq.cfg = *cfg;
+      memset(src, 0, sizeof *src); src->exact = 1; src->row0 = row; src->cfg = cfg;
+      remote_exact(src, &rq);
+      return; }
    ctx_prepare(cfg);
    int kind = reset_kind & 0xff;
    int rc = rt_scan_reset(S.ctx, kind, row); if (rc) rtfatal("rt_scan_reset", rc);
@@ -258,14 +267,33 @@ static void say_unit(const rt_unit_info *ui, uint64_t row, int all) {
       rlog("       trk %u%s: first event %lld, sync %lld (loud %lld), early sync %lld (loud %lld), need %lld, failed %u, events %u\n", k, late || early ? " ok" : "",
            (long long)ui->first_event_row[k], (long long)ui->sync_row[k], (long long)ui->last_loud_row[k], (long long)ui->sync_early[k],
            (long long)ui->loud_early[k], (long long)ui->need_sync_row[k], ui->failed[k], ui->nevents[k]); } }
-static void say_miss(rt_bulk *bulk, uint64_t row) {
+static void say_miss(rt_bulk *bulk, uint32_t ci, uint64_t row) {
    static rt_unit_info ui, un;
-   if (rt_bulk_unit_info(bulk, 0, row, &ui) != RT_OK) { rlog("  B200 scan: miss at row %llu: no unit\n", (unsigned long long)row); return; }
+   if (rt_bulk_unit_info(bulk, ci, row, &ui) != RT_OK) { rlog("  B200 scan: miss at row %llu: no unit\n", (unsigned long long)row); return; }
    rlog("  B200 scan: miss at row %llu, parmset %d\n", (unsigned long long)row, block.parmset);
    say_unit(&ui, row, 0);
-   if (rt_bulk_unit_at(bulk, 0, ui.unit_index + 1, &un) == RT_OK) {
+   if (rt_bulk_unit_at(bulk, ci, ui.unit_index + 1, &un) == RT_OK) {
       for (uint32_t k = 0; k < un.ntrks; ++k) un.need_sync_row[k] = ui.need_sync_row[k];       /* as seen from `row` */
       say_unit(&un, row, 0); } }
+
+/* BASELINE config 3: every active parameter set scanned by ONE rt_bulk_scan() call (their kernels share the sample planes and run
+   side by side); the reference then picks per block (readtape.c:1755-1795).  Returns 0 if the fan-out does not apply. */
+static int scan_parmsets(void) {
+   static rt_scan_cfg cfgs[MAXPARMSETS]; int which[MAXPARMSETS], n = 0;
+   const int keep = block.parmset;
+   for (int i = 0; i < MAXPARMSETS; ++i) {
+      if (!(i == keep || (multiple_tries && parmsetsptr[i].active))) continue;
+      block.parmset = i; make_cfg(&cfgs[n]); which[n++] = i; }
+   block.parmset = keep;
+   rt_bulk *bulk = NULLP;
+   int rc = rt_bulk_scan(S.tape, cfgs, (uint32_t)n, &bulk);
+   if (rc == RT_ERR_UNSUPPORTED) return 0;
+   if (rc) rtfatal("rt_bulk_scan", rc);
+   for (int k = 0; k < n; ++k) {
+      const int ps = which[k];
+      if (S.bulk[ps].valid && !S.bulk[ps].shared) rt_bulk_free(S.bulk[ps].bulk);
+      S.bulk[ps].bulk = bulk; S.bulk[ps].cfg = cfgs[k]; S.bulk[ps].valid = 1; S.bulk[ps].ci = (uint32_t)k; S.bulk[ps].shared = 1; }
+   return n; }
 
 static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    int ps = block.parmset;
@@ -273,18 +301,23 @@ static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
    /* the density and deskew pre-passes (readtape.c:1656-1717) reset per block like the main pass: the same speculative scan
       serves them, with their own configuration (handlers bypassed and width 8 / skew delays still zero) */
    if (S.bulk[ps].valid && memcmp(&S.bulk[ps].cfg, cfg, sizeof *cfg) != 0) {    /* e.g. the skew changed after the pre-pass */
-      rt_bulk_free(S.bulk[ps].bulk); S.bulk[ps].valid = 0; }
+      if (!S.bulk[ps].shared && S.remote_fd < 0) rt_bulk_free(S.bulk[ps].bulk);
+      S.bulk[ps].valid = 0; }
    if (!S.bulk[ps].valid) {
-      int rc = rt_bulk_scan(S.tape, cfg, 1, &S.bulk[ps].bulk);
-      if (rc == RT_ERR_UNSUPPORTED) { S.use_bulk = 0; return 0; }
-      if (rc) rtfatal("rt_bulk_scan", rc);
-      S.bulk[ps].cfg = *cfg; S.bulk[ps].valid = 1; }
+      if (S.remote_fd >= 0) return 0;                 /* a worker cannot scan: the parent serves this decode with the exact scan */
+      if (getenv("RT_FANOUT") && atoi(getenv("RT_FANOUT")) && !doing_density_detection && !doing_deskew && scan_parmsets()) { /* all at once */ }
+      else {
+         int rc = rt_bulk_scan(S.tape, cfg, 1, &S.bulk[ps].bulk);
+         if (rc == RT_ERR_UNSUPPORTED) { S.use_bulk = 0; return 0; }
+         if (rc) rtfatal("rt_bulk_scan", rc);
+         S.bulk[ps].cfg = *cfg; S.bulk[ps].valid = 1; S.bulk[ps].ci = 0; S.bulk[ps].shared = 0; } }
+   if (!S.bulk[ps].valid) return 0;
    uint64_t valid = 0;
    memset(src, 0, sizeof *src); src->row0 = row; src->cfg = cfg;
-   int rc = rt_bulk_lookup(S.bulk[ps].bulk, 0, row, &src->ev, &src->n, &valid);
+   int rc = rt_bulk_lookup(S.bulk[ps].bulk, S.bulk[ps].ci, row, &src->ev, &src->n, &valid);
    if (rc == RT_MISS) {
       ++S.n_bulk_miss;
-      if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2) say_miss(S.bulk[ps].bulk, row);
+      if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2) say_miss(S.bulk[ps].bulk, S.bulk[ps].ci, row);
       return 0; }
    if (rc) rtfatal("rt_bulk_lookup", rc);
    src->valid_end = row + valid;
@@ -542,18 +575,47 @@ static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, s
  * The replay of the events through the reference's handlers is single-threaded host work (the reference is not re-entrant), and once
  * the scan runs on the GPU it is all that is left: ~150 ns per flux transition.  Every block decode starts from init_trackstate(),
  * so blocks are independent, and the reference's per-block outputs in .tap format simply concatenate.  With RT_WORKERS=P the first
- * readblock() call forks P workers BEFORE anything touches CUDA; worker i opens its own share of the reel (file rows
- * [i*N/P, (i+1)*N/P) plus a margin), scans it on the GPU (RT_DEVICES=n deals the workers over n GPUs) and runs the reference's
- * unchanged process_file() loop on it, writing <out>.partNNN.tap.  Cut points are not the nominal rows but inter-block gaps:
- *   - worker i > 0 starts at the first unit boundary behind its nominal first row (a unit boundary is the start of an all-track
- *     quiet stretch, k_units.cu), i.e. with a fresh init_trackstate() there;
- *   - worker i < P-1 stops at the first block start for which rt_bulk_lookup() PROVES that a fresh reset there is equivalent to a
- *     fresh reset at a unit that starts at or behind that same boundary -- which it computes from its own copy of the same samples.
- *     If the proof fails the worker exits with WORKER_UNPROVEN and the parent decodes the reel unsplit.
- * The parent never initialises CUDA: it waits, concatenates the parts (each without its end-of-medium marker), writes the marker,
- * and reports like readtape's main() does in quiet mode.  Only what is safe to split is split: .tap output, quiet mode (per-block log
- * lines carry running block numbers), no text file, no Whirlwind (state persists), no density / deskew pre-pass pending. */
+ * readblock() call
+ *   1. opens the tape and scans it for every parameter set the run may use (one rt_bulk_scan call), results fetched into memory
+ *      that forked children can read (RT_OPT_SHARED_RESULTS);
+ *   2. cuts the reel into P parts at unit boundaries (a unit boundary is the start of an all-track quiet stretch, k_units.cu) and
+ *      forks P workers.  A worker never touches CUDA (a context does not survive fork(), and creating one costs seconds): it runs
+ *      the reference's unchanged process_file() loop on its part, looking its events up in the shared results and writing
+ *      <out>.partNNN.tap.  The rare decodes the speculative scan cannot serve (misses, units that end inside a block) are scanned by
+ *      the parent, which answers over a socket pair;
+ *   3. worker i > 0 starts with a fresh init_trackstate() at its boundary; worker i < P-1 stops at the first block start for which
+ *      rt_bulk_lookup() PROVES that a fresh reset there is equivalent to a fresh reset at a unit at or behind the next worker's
+ *      boundary.  If that proof fails the worker exits with WORKER_UNPROVEN and the parent decodes the reel unsplit;
+ *   4. the parent concatenates the parts (each without its end-of-medium marker), writes the marker, and reports like readtape's
+ *      main() does in quiet mode.
+ * Only what is safe to split is split: .tap output, quiet mode (per-block log lines carry running block numbers), no text file, no
+ * Whirlwind (state persists), no density / deskew pre-pass pending. */
+#define WORKER_BUF_EVENTS (1u << 19)
+struct chan { int fd; pid_t pid; int alive; rt_event *buf; rt_scan *ctx; rt_scan_cfg cfg; };
+
 static void part_name(char *buf, size_t n, int i, const char *ext) { snprintf(buf, n, "%s.part%03d%s", baseoutfilename, i, ext); }
+static void worker_exit(int status, void *arg) { (void)arg; fflush(NULLP); _exit(status); }   /* no CUDA teardown in a forked child */
+
+static void serve_one(struct chan *ch) {                       /* parent: one exact-scan request of a worker */
+   struct wreq rq; struct wrsp rs;
+   memset(&rs, 0, sizeof rs);
+   size_t got = 0;
+   while (got < sizeof rq) { ssize_t k = read(ch->fd, (char *)&rq + got, sizeof rq - got); if (k <= 0) { ch->alive = 0; return; } got += (size_t)k; }
+   int rc = RT_OK;
+   if (rq.op == WOP_START) {
+      if (!ch->ctx) rc = rt_scan_begin(S.tape, &rq.cfg, &ch->ctx);
+      else if (memcmp(&ch->cfg, &rq.cfg, sizeof rq.cfg) != 0) rc = rt_scan_set_cfg(ch->ctx, &rq.cfg);
+      ch->cfg = rq.cfg;
+      if (!rc) rc = rt_scan_reset(ch->ctx, rq.reset_kind & 0xff, rq.row); }
+   const rt_event *ev = NULLP; uint64_t n = 0, done = 0;
+   for (uint64_t span = EXACT_SPAN_ROWS; !rc; span /= 2) {      /* a span whose events fit the shared buffer */
+      rc = rt_scan_run(ch->ctx, span, &ev, &n, &done);
+      if (rc || n <= WORKER_BUF_EVENTS) break;
+      rc = rt_scan_rewind(ch->ctx, rt_scan_pos(ch->ctx) - done);
+      if (!rc && span <= 1) rc = RT_ERR_OVERFLOW; }
+   if (!rc) { memcpy(ch->buf, ev, (size_t)n * sizeof *ev); rs.n = n; rs.pos = rt_scan_pos(ch->ctx); rs.done = done; }
+   else { rs.rc = rc; strncpy(rs.err, rt_last_error(), sizeof rs.err - 1); }
+   xfer(ch->fd, &rs, sizeof rs, 1); }
 
 static void run_workers(void) {
    const char *env = getenv("RT_WORKERS");
@@ -561,45 +623,81 @@ static void run_workers(void) {
    if (P <= 1) return;
    if (!(tbin_file && tap_format && quiet && !do_txtfile && mode != WW && subsample == 1 && bpi != 0 && !doing_density_detection
          && !doing_deskew && (!deskew || skew_given) && numblks == 0 && numblks_limit == INT_MAX && outf == NULLP)) return;
-   long long pos = ftello(inf);
-   assert(pos >= 0 && fseeko(inf, 0, SEEK_END) == 0, "fseek failed");
-   long long end = ftello(inf);
-   assert(fseeko(inf, pos, SEEK_SET) == 0, "fseek failed");
-   const uint64_t N = (uint64_t)(end - pos) / ((uint64_t)nheads * 2);
-   if (N / (uint64_t)P < WORKER_MIN_ROWS) P = (int)(N / WORKER_MIN_ROWS);
+   double w0 = wall();
+   open_tape();
+   if (!S.use_bulk) return;
+   if (P > 256) P = 256;
+   if (S.nrows / (uint64_t)P < WORKER_MIN_ROWS) P = (int)(S.nrows / WORKER_MIN_ROWS);
    if (P <= 1) return;
+   /* 1. every parameter set the run may use, scanned at once, results where children can read them */
+   rt_set_option(RT_OPT_SHARED_RESULTS, 1);
+   const int ps0 = block.parmset;
+   if (!scan_parmsets()) { rt_set_option(RT_OPT_SHARED_RESULTS, 0); return; }
+   int rc = rt_bulk_fetch(S.bulk[ps0].bulk);
+   rt_set_option(RT_OPT_SHARED_RESULTS, 0);
+   if (rc) rtfatal("rt_bulk_fetch", rc);
+   /* 2. the cut points: the first unit boundary behind each nominal share */
+   static uint64_t cut[257]; static rt_unit_info ui;
+   int parts = 1; cut[0] = 0;
+   for (int i = 1; i < P; ++i) {
+      rc = rt_bulk_unit_info(S.bulk[ps0].bulk, S.bulk[ps0].ci, (uint64_t)i * S.nrows / (uint64_t)P, &ui);
+      if (rc == RT_OK) rc = rt_bulk_unit_at(S.bulk[ps0].bulk, S.bulk[ps0].ci, ui.unit_index + 1, &ui);
+      if (rc != RT_OK) break;                                   /* no boundary behind this row: the last part takes the rest */
+      if (ui.row0 > cut[parts - 1]) cut[parts++] = ui.row0; }
+   P = parts; cut[P] = UINT64_MAX;
+   if (P <= 1) return;
+   S.s_open += wall() - w0;
+   static struct chan ch[256];
    static char base[MAXPATH + 50];
    strcpy(base, baseoutfilename);
-   fflush(NULL);
-   pid_t pids[256]; if (P > 256) P = 256;
+   rt_event *bufs = mmap(NULLP, (size_t)P * WORKER_BUF_EVENTS * sizeof(rt_event), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+   assert(bufs != MAP_FAILED, "cannot map the workers' event buffers");
+   fflush(NULLP);
    for (int i = 0; i < P; ++i) {
+      int sv[2];
+      assert(socketpair(AF_UNIX, SOCK_STREAM, 0, sv) == 0, "socketpair failed");
       pid_t pid = fork();
       assert(pid >= 0, "fork failed");
-      if (pid == 0) {                                        /* the worker: carries on into open_tape() with its share */
+      if (pid == 0) {                                           /* the worker: carries on in readblock() with its part */
          char name[MAXPATH + 80];
-         S.worker = i; S.nworkers = P; S.file_rows = N;
-         S.nominal_lo = (uint64_t)i * N / (uint64_t)P / 2048 * 2048;
-         S.nominal_hi = i == P - 1 ? N : (uint64_t)(i + 1) * N / (uint64_t)P / 2048 * 2048;
-         S.must_seek_start = i > 0;
-         if (i > 0) numblks = 1 << 20;                         /* "wrote block 1" (readtape.c:1271) is the first worker's line */
+         for (int k = 0; k < i; ++k) close(ch[k].fd);
+         close(sv[0]);
+         on_exit(worker_exit, NULLP);
+         setenv("RT_BRIDGE", "0", 1);                           /* lookups must stay on the host: what a bridge would prove, the parent scans */
+         S.worker = i; S.nworkers = P; S.remote_fd = sv[1]; S.remote_buf = bufs + (size_t)i * WORKER_BUF_EVENTS;
+         S.start_row = cut[i]; S.stop_row = cut[i + 1]; S.must_seek_start = i > 0;
+         S.ctx = NULLP; S.ctx_valid = 0;
+         S.n_events = S.n_bulk_hits = S.n_bulk_miss = S.n_restarts = S.n_exact_spans = 0; S.s_scan = S.s_replay = 0;
+         if (i > 0) numblks = 1 << 20;                          /* "wrote block 1" (readtape.c:1271) is the first worker's line */
          part_name(name, sizeof name, i, ".out");
          assert(freopen(name, "w", stdout) != NULLP, "cannot create %s", name);
          part_name(name, sizeof name, i, "");
          assert(strlen(name) < MAXPATH, "output name too long");
-         strcpy(baseoutfilename, name);                      /* create_datafile() -> <out>.partNNN.tap */
+         strcpy(baseoutfilename, name);                         /* create_datafile() -> <out>.partNNN.tap */
          return; }
-      pids[i] = pid; }
-   /* the parent */
+      close(sv[1]);
+      ch[i].fd = sv[0]; ch[i].pid = pid; ch[i].alive = 1; ch[i].buf = bufs + (size_t)i * WORKER_BUF_EVENTS; ch[i].ctx = NULLP; }
+   /* the parent: serve exact scans until every worker has hung up */
+   for (int live = P; live > 0;) {
+      static struct pollfd pf[256];
+      for (int i = 0; i < P; ++i) { pf[i].fd = ch[i].alive ? ch[i].fd : -1; pf[i].events = POLLIN; pf[i].revents = 0; }
+      if (poll(pf, (nfds_t)P, -1) < 0) continue;
+      for (int i = 0; i < P; ++i)
+         if (ch[i].alive && (pf[i].revents & (POLLIN | POLLHUP | POLLERR))) {
+            serve_one(&ch[i]);
+            if (!ch[i].alive) { close(ch[i].fd); --live; } } }
    int worst = 0;
    for (int i = 0; i < P; ++i) {
       int st = 0;
-      assert(waitpid(pids[i], &st, 0) == pids[i], "waitpid failed");
+      assert(waitpid(ch[i].pid, &st, 0) == ch[i].pid, "waitpid failed");
       int code = WIFEXITED(st) ? WEXITSTATUS(st) : 99;
-      if (code != 0 && (worst == 0 || worst == WORKER_UNPROVEN)) worst = code; }
+      if (code != 0 && (worst == 0 || worst == WORKER_UNPROVEN)) worst = code;
+      if (ch[i].ctx) rt_scan_end(ch[i].ctx); }
+   munmap(bufs, (size_t)P * WORKER_BUF_EVENTS * sizeof(rt_event));
    bool all_ok = true;
    char name[MAXPATH + 80], line[MAXLINE];
    if (worst == 0) {
-      for (int i = 0; i < P; ++i) {                          /* the parts, in order, without their end-of-medium markers */
+      for (int i = 0; i < P; ++i) {                             /* the parts, in order, without their end-of-medium markers */
          part_name(name, sizeof name, i, ".tap");
          FILE *f = fopen(name, "rb");
          if (!f) continue;
@@ -617,7 +715,7 @@ static void run_workers(void) {
             left -= (long long)want; }
          numoutbytes += len;
          fclose(f); } }
-   for (int i = 0; i < P; ++i) {                             /* what the workers printed; their verdicts */
+   for (int i = 0; i < P; ++i) {                                /* what the workers printed; their verdicts */
       part_name(name, sizeof name, i, ".out");
       FILE *f = fopen(name, "r");
       if (f) {
@@ -628,54 +726,32 @@ static void run_workers(void) {
          fclose(f); }
       remove(name);
       part_name(name, sizeof name, i, ".tap"); remove(name); }
-   if (worst == WORKER_UNPROVEN) {                           /* decode the reel in one piece after all */
+   if (worst == WORKER_UNPROVEN) {                              /* decode the reel in one piece after all: the tape and its scans are here */
       if (getenv("RT_STATS")) printf("  B200 scan: a worker could not prove its hand-over; decoding the reel unsplit\n");
       return; }
    if (worst != 0) exit(worst);
+   if (getenv("RT_STATS")) printf("  B200 scan: %d workers; parent: %.3f s opening + upload + scan\n", P, S.s_open);
    /* what process_file() does at the end of the file (readtape.c:1862-1867) and main() in quiet mode (:2014) */
    if (tap_format && outf) output_tap_marker(0xffffffffl);
    close_file();
    printf("%s: %s\n", baseinfilename, all_ok ? "ok" : "bad");
-   fflush(NULL);
+   fflush(NULLP);
    exit(0); }
-
-/* worker: the unit boundaries that delimit this worker's part, from the unit table of the current parameter set */
-static void worker_boundaries(const rt_scan_cfg *cfg, uint64_t *start_row) {
-   struct evsrc probe;
-   static rt_unit_info ui;
-   *start_row = 0;
-   /* make sure the whole-tape scan of this parameter set exists (a lookup at the tape's first row creates it) */
-   (void)bulk_start(&probe, cfg, 0);
-   int ps = block.parmset;
-   if (!S.bulk[ps].valid) fatal("B200 scan: RT_WORKERS needs the speculative whole-tape scan");
-   for (int which = 0; which < 2; ++which) {
-      const uint64_t nominal = which == 0 ? S.nominal_lo : S.nominal_hi;
-      if ((which == 0 && S.worker == 0) || (which == 1 && S.worker == S.nworkers - 1)) continue;
-      int rc = rt_bulk_unit_info(S.bulk[ps].bulk, 0, nominal - S.row_off, &ui);
-      if (rc == RT_OK) rc = rt_bulk_unit_at(S.bulk[ps].bulk, 0, ui.unit_index + 1, &ui);
-      if (rc != RT_OK) { fflush(NULL); _exit(WORKER_UNPROVEN); }         /* no inter-block gap within the margin */
-      if (which == 0) *start_row = ui.row0; else S.stop_row = ui.row0; } }
 
 bool readblock(bool retry) {
    double w0 = wall();
    if (!S.par_checked) { S.par_checked = 1; run_workers(); }      /* RT_WORKERS: the parent does not come back from there */
    if (!S.opened) { open_tape(); S.s_open += wall() - w0; w0 = wall(); }
-   if (S.worker >= 0 && !S.worker_ready) {
-      /* a worker's first call: find its boundaries; a worker other than the first only moves to its first row and reports "noise",
-         so that process_file() takes its next block start (blockstart, readtape.c:1722) from there */
-      rt_scan_cfg cfg0; make_cfg(&cfg0);
-      uint64_t start = 0;
-      worker_boundaries(&cfg0, &start);
-      S.worker_ready = 1;
-      if (S.must_seek_start) {
-         S.must_seek_start = 0;
-         timenow_ns = (int64_t)(S.desc.tstart_ns + start * S.desc.tdelta_ns);
-         timenow = rowtime(start);
-         assert(fseeko(inf, S.base_pos + (long long)start * nheads * 2, SEEK_SET) == 0, "fseek failed");
-         block.results[block.parmset].blktype = BS_NOISE;
-         S.pending_reset = RT_RESET_NONE;
-         S.s_scan += wall() - w0;
-         return true; } }
+   if (S.worker > 0 && S.must_seek_start) {
+      /* a worker's first call (other than the first worker's): move to its first row and report "noise", so that process_file()
+         takes its next block start (blockstart, readtape.c:1722) from there */
+      S.must_seek_start = 0;
+      timenow_ns = (int64_t)(S.desc.tstart_ns + S.start_row * S.desc.tdelta_ns);
+      timenow = rowtime(S.start_row);
+      assert(fseeko(inf, S.base_pos + (long long)S.start_row * nheads * 2, SEEK_SET) == 0, "fseek failed");
+      block.results[block.parmset].blktype = BS_NOISE;
+      S.pending_reset = RT_RESET_NONE;
+      return true; }
    long long pos = ftello(inf);
    assert(pos >= S.base_pos && (pos - S.base_pos) % (nheads * 2) == 0, "B200 scan: unexpected file position %lld", pos);
    uint64_t row0 = (uint64_t)(pos - S.base_pos) / (uint64_t)(nheads * 2);
@@ -695,7 +771,7 @@ bool readblock(bool retry) {
    int from_bulk = !persistent && bulk_start(&src, &cfg, row0);
    if (S.stop_row != UINT64_MAX && !retry) {                     /* a worker that is not the last: is this block the next worker's? */
       uint64_t u0 = 0;
-      if (from_bulk && rt_bulk_last_unit(S.bulk[block.parmset].bulk, 0, &u0, NULLP) == RT_OK && u0 >= S.stop_row) {
+      if (from_bulk && rt_bulk_last_unit(S.bulk[block.parmset].bulk, S.bulk[block.parmset].ci, &u0, NULLP) == RT_OK && u0 >= S.stop_row) {
          /* proven: a fresh reset here == a fresh reset at a unit at or behind the boundary; the next worker starts exactly there */
          S.s_scan += wall() - w0;
          if (getenv("RT_STATS")) {
