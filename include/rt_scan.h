@@ -149,6 +149,10 @@ int  rt_open(const rt_tape_desc *desc, int device, rt_tape **out);
  * memory (rt_host_alloc) makes the copy asynchronous.  Replaces the fread()s of
  * readtape.c:1408,1414. */
 int  rt_upload(rt_tape *tape, const int16_t *rows, uint64_t nrows);
+/* Same, but the rows are read from file descriptor `fd` at byte offset `offset` (pread): the library reads the file (page cache)
+ * with a few threads straight into its pinned staging ring, so the caller needs neither a whole-file buffer nor a mapping and the
+ * copy engine is kept busy.  Replaces the fread()s of readtape.c:1408,1414 for a whole capture at once. */
+int  rt_upload_fd(rt_tape *tape, int fd, uint64_t offset, uint64_t nrows);
 /* Same, but `rows_dev` is already a DEVICE pointer (product library only). */
 int  rt_attach_device(rt_tape *tape, const void *rows_dev, uint64_t nrows);
 /* Forget the samples but keep the device buffers (re-use the tape for the next capture of similar size). */

@@ -36,7 +36,10 @@
  * float expressions are evaluated in float, double in double, exactly like the reference
  * build; the float/double type of every sub-expression follows the reference source.
  */
+#define _XOPEN_SOURCE 700
 #include <stdlib.h>
+#include <unistd.h>
+#include <sys/types.h>
 #include <string.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -138,6 +141,15 @@ int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
       t->nrows = r; }
    return RT_OK; }
 
+int rt_upload_fd(rt_tape *t, int fd, uint64_t offset, uint64_t n) {
+   if (!t || fd < 0) return RT_ERR_ARG;
+   int16_t *buf = malloc((size_t)n * t->desc.nheads * 2 + 2);
+   if (!buf) return RT_ERR_NOMEM;
+   size_t want = (size_t)n * t->desc.nheads * 2, got = 0;
+   while (got < want) { ssize_t k = pread(fd, (char *)buf + got, want - got, (off_t)(offset + got)); if (k <= 0) { free(buf); return RT_ERR_ARG; } got += (size_t)k; }
+   int rc = rt_upload(t, buf, n);
+   free(buf);
+   return rc; }
 int rt_attach_device(rt_tape *t, const void *p, uint64_t n) {
    (void)t; (void)p; (void)n; return set_err(RT_ERR_UNSUPPORTED, "oracle has no device memory"); }
 uint64_t rt_nrows(const rt_tape *t) { return t ? t->nrows : 0; }

@@ -6,6 +6,7 @@
  */
 #include <cuda_runtime.h>
 #include <sys/mman.h>
+#include <unistd.h>
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -49,6 +50,7 @@ extern "C" double rt_row_time(const rt_tape_desc *d, uint64_t row) {
 extern "C" int rt_pkww_width(const rt_scan_cfg *cfg, uint64_t tdelta_ns) { return rtcfg::pkww_width(cfg, tdelta_ns); }
 
 /* ---- tape ---------------------------------------------------------------------------------------- */
+#define RT_RING_SLOTS 8
 struct rt_tape {
    rt_tape_desc desc{};
    int device = 0, sms = 148;
@@ -74,7 +76,7 @@ struct rt_tape {
    std::vector<cudaStream_t> s_par;                               /* rt_bulk_scan with several configurations: their kernels run side by side */
    cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[2] = {nullptr, nullptr};
    uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
-   int16_t *h_ring = nullptr; cudaEvent_t ring_done[6] = {};       /* pinned ring for uploads from pageable memory */
+   int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
 };
 
 static int tape_reserve(rt_tape *t, uint64_t rows) {
@@ -187,16 +189,17 @@ static int enqueue_chunk(rt_tape *t, const int16_t *src, uint64_t n, int buf) {
 /* Upload from PAGEABLE host memory (a file mapping, a malloc'd buffer): cudaMemcpyAsync would stage such a copy through the driver's
    own bounce buffer with one thread (~10 GB/s).  Instead a few threads copy chunks into a ring of pinned buffers while the copy
    engine drains them, which keeps PCIe busy (RT_UPLOAD_THREADS, default 4). */
-static int upload_pageable(rt_tape *t, const int16_t *rows, uint64_t nrows, uint64_t stage_rows) {
+static int upload_pageable(rt_tape *t, const int16_t *rows, int fd, uint64_t fd_offset, uint64_t nrows, uint64_t stage_rows) {
    const uint64_t nh = t->desc.nheads;
-   const int NB = 6;
+   const int NB = RT_RING_SLOTS;
    const size_t slot_bytes = (size_t)stage_rows * nh * 2;
    if (!t->h_ring) {
       CU(cudaHostAlloc(&t->h_ring, slot_bytes * NB, cudaHostAllocDefault));
       for (int i = 0; i < NB; ++i) CU(cudaEventCreateWithFlags(&t->ring_done[i], cudaEventDisableTiming)); }
    const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
    const char *env = getenv("RT_UPLOAD_THREADS");
-   int nthreads = env ? atoi(env) : 4;
+   int nthreads = env && atoi(env) > 0 ? atoi(env) : (rows ? 4 : 6);
+   std::atomic<int> io_error{0};
    nthreads = std::max(1, std::min<int>(nthreads, (int)std::min<uint64_t>(nchunks, 16)));
    std::mutex mu; std::condition_variable cv;
    std::vector<char> filled(nchunks, 0);
@@ -208,7 +211,14 @@ static int upload_pageable(rt_tape *t, const int16_t *rows, uint64_t nrows, uint
          if (i >= nchunks) return;
          { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return i < released + NB; }); }
          const uint64_t r0 = i * stage_rows, n = std::min(stage_rows, nrows - r0);
-         memcpy(reinterpret_cast<char *>(t->h_ring) + (size_t)(i % NB) * slot_bytes, rows + r0 * nh, (size_t)n * nh * 2);
+         char *dst = reinterpret_cast<char *>(t->h_ring) + (size_t)(i % NB) * slot_bytes;
+         if (rows) memcpy(dst, rows + r0 * nh, (size_t)n * nh * 2);
+         else {                                                   /* straight from the file (page cache) into pinned memory */
+            size_t got = 0; const size_t want = (size_t)n * nh * 2;
+            while (got < want) {
+               const ssize_t k = pread(fd, dst + got, want - got, (off_t)(fd_offset + r0 * nh * 2 + got));
+               if (k <= 0) { io_error = 1; memset(dst + got, 0, want - got); break; }
+               got += (size_t)k; } }
          { std::lock_guard<std::mutex> lk(mu); filled[i] = 1; }
          cv.notify_all(); } };
    std::vector<std::thread> th;
@@ -228,6 +238,7 @@ static int upload_pageable(rt_tape *t, const int16_t *rows, uint64_t nrows, uint
    { std::lock_guard<std::mutex> lk(mu); released = nchunks; }
    cv.notify_all();
    for (auto &x : th) x.join();
+   if (rc == RT_OK && io_error) rc = set_err(RT_ERR_ARG, "rt_upload_fd: short read");
    return rc; }
 
 extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
@@ -245,7 +256,7 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
       cudaGetLastError();
       const char *env = getenv("RT_UPLOAD_THREADS");
       if (pageable && !(env && atoi(env) == 0)) {
-         rc = upload_pageable(t, rows, nrows, stage_rows);
+         rc = upload_pageable(t, rows, -1, 0, nrows, stage_rows);
          if (rc) { cudaDeviceSynchronize(); return rc; }
          t->h2d_bytes += nrows * nh * 2;
          return tape_drain(t); } }
@@ -258,6 +269,19 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
       if (rc) return rc;
       done += n; buf ^= 1; }
    t->h2d_bytes += nrows * nh * 2;
+   return tape_drain(t); }
+
+extern "C" int rt_upload_fd(rt_tape *t, int fd, uint64_t offset, uint64_t nrows) {
+   if (!t || fd < 0) return set_err(RT_ERR_ARG, "rt_upload_fd: bad argument");
+   if (nrows == 0) return RT_OK;
+   CU(cudaSetDevice(t->device));
+   int rc = tape_reserve(t, t->nrows + nrows);
+   if (rc) return rc;
+   uint64_t stage_rows = 0;
+   rc = stage_prepare(t, nrows, &stage_rows); if (rc) return rc;
+   rc = upload_pageable(t, nullptr, fd, offset, nrows, stage_rows);
+   if (rc) { cudaDeviceSynchronize(); return rc; }
+   t->h2d_bytes += nrows * t->desc.nheads * 2;
    return tape_drain(t); }
 
 extern "C" int rt_attach_device(rt_tape *t, const void *rows_dev, uint64_t nrows) {

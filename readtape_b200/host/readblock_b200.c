@@ -155,17 +155,11 @@ static void open_tape(void) {
    int rc = rt_open(&S.desc, dev, &S.tape);
    if (rc) rtfatal("rt_open", rc);
    double w2 = wall();
-   /* the payload goes to the GPU straight from the page cache: the file is mapped, not read into a (pinned) copy */
+   /* the payload goes to the GPU straight from the page cache: the library reads the file with a few threads into its pinned
+      staging ring (no whole-file buffer, pinned or not) */
    S.rows_bytes = (size_t)(nrows_file * rowbytes);
-   const long pg = sysconf(_SC_PAGESIZE);
-   const off_t map_off = (off_t)(S.base_pos / pg * pg);
-   const size_t map_len = S.rows_bytes + (size_t)(S.base_pos - map_off);
-   void *map = map_len ? mmap(NULLP, map_len, PROT_READ, MAP_PRIVATE, fileno(inf), map_off) : NULLP;
-   assert(map_len == 0 || map != MAP_FAILED, "cannot map the .tbin payload");
-   if (map_len) madvise(map, map_len, MADV_SEQUENTIAL);
-   rc = rt_upload(S.tape, (const int16_t *)((const char *)map + (S.base_pos - map_off)), nrows_file);
-   if (rc) rtfatal("rt_upload", rc);
-   if (map_len) munmap(map, map_len);
+   rc = rt_upload_fd(S.tape, fileno(inf), (uint64_t)S.base_pos, nrows_file);
+   if (rc) rtfatal("rt_upload_fd", rc);
    if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2)
       rlog("  B200 scan: rt_open %.3f s, upload of %.2f GB %.3f s\n", w2 - w1, S.rows_bytes / 1e9, wall() - w2);
    S.nrows = rt_nrows(S.tape);
@@ -632,10 +626,13 @@ static void run_workers(void) {
    /* 1. every parameter set the run may use, scanned at once, results where children can read them */
    rt_set_option(RT_OPT_SHARED_RESULTS, 1);
    const int ps0 = block.parmset;
+   double w1 = wall();
    if (!scan_parmsets()) { rt_set_option(RT_OPT_SHARED_RESULTS, 0); return; }
+   double w2 = wall();
    int rc = rt_bulk_fetch(S.bulk[ps0].bulk);
    rt_set_option(RT_OPT_SHARED_RESULTS, 0);
    if (rc) rtfatal("rt_bulk_fetch", rc);
+   if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2) printf("  B200 scan: whole-tape scan %.3f s, results to the host %.3f s\n", w2 - w1, wall() - w2);
    /* 2. the cut points: the first unit boundary behind each nominal share */
    static uint64_t cut[257]; static rt_unit_info ui;
    int parts = 1; cut[0] = 0;

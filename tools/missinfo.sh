@@ -13,5 +13,5 @@ cap = captures.full_path(name)
 d = tempfile.mkdtemp()
 r = subprocess.run(["readtape_b200/bin/readtape_b200"] + [o for o in e[2].split() if o not in ("-v", "-v3")] + [f"-outf={d}/{name}", cap],
                    capture_output=True, text=True, env=dict(os.environ, RT_STATS="2"))
-print("\n".join(l for l in r.stdout.splitlines() if "B200 scan" in l or l.startswith("     trk")))
+print("\n".join(l for l in r.stdout.splitlines() if "B200 scan" in l or l.lstrip().startswith(("trk", "unit"))))
 PY
