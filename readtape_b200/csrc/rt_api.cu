@@ -1147,7 +1147,7 @@ extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const
    uint64_t br0 = RT_NOROW, br1 = RT_NOROW;
    if (!unit_covers(bc, b->tape->desc, nt, lo, start_row, &br0)) {
       bool bridged = false;
-      if (lo + 1 < bc.units.size() && unit_covers(bc, b->tape->desc, nt, lo + 1, start_row, &br1)) ++lo;
+      if (lo + 1 < bc.units.size() && unit_covers(bc, b->tape->desc, nt, lo + 1, start_row, &br1)) { ++lo; bridged = true; }   /* covered by the next unit */
       else if (br0 != RT_NOROW || br1 != RT_NOROW) {             /* not provably quiet: a short exact scan can still prove the equivalence */
          const char *env = getenv("RT_BRIDGE");
          if (!(env && env[0] == '0')) {
