@@ -198,6 +198,13 @@ int  rt_bulk_scan(rt_tape *tape, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bul
 /* rt_bulk_scan() leaves its results in device memory; rt_bulk_fetch() copies them to the host (pinned
  * memory).  The first rt_bulk_lookup()/rt_bulk_unit_info() call does it implicitly. */
 int  rt_bulk_fetch(rt_bulk *bulk);
+/* rt_bulk_fetch() with the events placed in the CALLER's buffer (RT_ERR_OVERFLOW if it is too small: nothing is fetched then and
+ * rt_bulk_fetch() can still be called).  For a caller that wants the results in memory of its own choosing -- e.g. a MAP_SHARED
+ * mapping prepared in the background that worker processes forked later can read; rt_host_register() pins such memory for the copy
+ * (cudaHostRegister), rt_host_unregister() unpins it. */
+int  rt_bulk_fetch_to(rt_bulk *bulk, void *events_buf, size_t bytes);
+int  rt_host_register(rt_tape *tape, void *p, size_t bytes);
+int  rt_host_unregister(rt_tape *tape, void *p);
 /* rt_clear() + rt_upload(rows) + rt_bulk_scan(cfg) + rt_bulk_fetch() in one call with the three stages overlapped: the tape is
  * scanned segment by segment while it is still being copied (PCIe is the slow stage), and the events of each segment travel
  * back while the next one arrives.  `rows` should be pinned (rt_host_alloc).  Same results as the separate calls. */

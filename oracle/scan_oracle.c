@@ -542,6 +542,9 @@ int rt_bulk_lookup(rt_bulk *b, uint32_t c, uint64_t r, const rt_event **e, uint6
    return set_err(RT_ERR_UNSUPPORTED, "the oracle only implements the exact scan"); }
 int rt_clear(rt_tape *t) { if (!t) return RT_ERR_ARG; t->nrows = 0; t->cap = 0; return RT_OK; }
 int rt_bulk_fetch(rt_bulk *b) { (void)b; return RT_ERR_UNSUPPORTED; }
+int rt_bulk_fetch_to(rt_bulk *b, void *p, size_t n) { (void)b; (void)p; (void)n; return RT_ERR_UNSUPPORTED; }
+int rt_host_register(rt_tape *t, void *p, size_t n) { (void)t; (void)p; (void)n; return RT_OK; }
+int rt_host_unregister(rt_tape *t, void *p) { (void)t; (void)p; return RT_OK; }
 
 /* The two bit planes of the product's two-pass peak scan, by definition (include/rt_scan.h: rt_peak_masks).  The window of
    lookfor_peak (decoder.c:751-775) at row p holds samples p-w+1 .. p of the track; int16 -> volts (readtape.c:1420) is strictly

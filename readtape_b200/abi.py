@@ -69,7 +69,7 @@ assert EVENT_DTYPE.itemsize == 32
 EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
-           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_bulk_tile_digest", "rt_bulk_last_unit", "rt_set_option", "rt_peak_masks", "rt_pkww_width",
+           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_fetch_to", "rt_host_register", "rt_host_unregister", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_bulk_tile_digest", "rt_bulk_last_unit", "rt_set_option", "rt_peak_masks", "rt_pkww_width",
            "rt_row_time"]
 
 

@@ -198,7 +198,8 @@ static int upload_pageable(rt_tape *t, const int16_t *rows, int fd, uint64_t fd_
       for (int i = 0; i < NB; ++i) CU(cudaEventCreateWithFlags(&t->ring_done[i], cudaEventDisableTiming)); }
    const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
    const char *env = getenv("RT_UPLOAD_THREADS");
-   int nthreads = env && atoi(env) > 0 ? atoi(env) : (rows ? 4 : 6);
+   const int hw = (int)std::thread::hardware_concurrency();
+   int nthreads = env && atoi(env) > 0 ? atoi(env) : std::max(4, std::min(12, hw - 2));
    std::atomic<int> io_error{0};
    nthreads = std::max(1, std::min<int>(nthreads, (int)std::min<uint64_t>(nchunks, 16)));
    std::mutex mu; std::condition_variable cv;
@@ -522,6 +523,7 @@ struct rt_bulk {
    rt_event *d_pool = nullptr; uint32_t *d_chunk_next = nullptr; uint32_t pool_chunks = 0, chunks_used = 0;
    bool pool_from_cache = false, pin_from_cache = false;
    rt_event *h_pool = nullptr; size_t h_pool_events = 0;          /* pinned */
+   rt_event *user_pool = nullptr; size_t user_pool_bytes = 0;     /* rt_bulk_fetch_to(): the caller's buffer */
    size_t h_pool_shared_bytes = 0;                                /* != 0: h_pool is an anonymous MAP_SHARED mapping of this size (RT_OPT_SHARED_RESULTS) */
    std::vector<uint32_t> chunk_next;
    std::vector<rt_event> result;
@@ -606,7 +608,8 @@ extern "C" void rt_bulk_free(rt_bulk *b) {
    rt_tape *t = b->tape;
    cudaSetDevice(t->device);
    if (b->bridge) rt_scan_end(b->bridge);
-   if (b->h_pool_shared_bytes) munmap(b->h_pool, b->h_pool_shared_bytes);
+   if (b->user_pool) { /* the caller's memory */ }
+   else if (b->h_pool_shared_bytes) munmap(b->h_pool, b->h_pool_shared_bytes);
    else if (b->pin_from_cache) t->pin_cache_busy = false; else if (b->h_pool) cudaFreeHost(b->h_pool);
    if (b->pool_from_cache) t->pool_cache_busy = false; else { cudaFree(b->d_pool); cudaFree(b->d_chunk_next); }
    for (auto &c : b->cfgs) { if (c.d_units) cudaFreeAsync(c.d_units, t->stream); if (c.d_meta) cudaFreeAsync(c.d_meta, t->stream); }
@@ -781,7 +784,13 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
    if (b->chunks_used) {
       CU(cudaMemcpyAsync(b->chunk_next.data(), b->d_chunk_next, (size_t)b->chunks_used * 4, cudaMemcpyDeviceToHost, t->stream));
       b->h_pool_events = (size_t)b->chunks_used * RT_EVC;
-      if (g_opt_shared_results) {
+      if (b->user_pool) {
+         if (b->h_pool_events * sizeof(rt_event) > b->user_pool_bytes)
+            return set_err(RT_ERR_OVERFLOW, "rt_bulk_fetch_to: the buffer holds %zu bytes, the events need %zu", b->user_pool_bytes, b->h_pool_events * sizeof(rt_event));
+         b->h_pool = b->user_pool;
+         CU(cudaMemcpyAsync(b->h_pool, b->d_pool, b->h_pool_events * sizeof(rt_event), cudaMemcpyDeviceToHost, t->stream));
+         b->stats.d2h_bytes += b->h_pool_events * sizeof(rt_event) + (uint64_t)b->chunks_used * 4; }
+      else if (g_opt_shared_results) {
          /* memory that worker processes forked after this call can read: shared anonymous pages, pinned only while the copy runs */
          const size_t bytes = (b->h_pool_events * sizeof(rt_event) + 4095) / 4096 * 4096;
          void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_POPULATE, -1, 0);
@@ -813,6 +822,25 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
    if (b->pool_from_cache) { t->pool_cache_busy = false; b->pool_from_cache = false; } else { cudaFree(b->d_pool); cudaFree(b->d_chunk_next); }
    b->d_pool = nullptr; b->d_chunk_next = nullptr;
    b->fetched = true;
+   return RT_OK; }
+
+extern "C" int rt_bulk_fetch_to(rt_bulk *b, void *events_buf, size_t bytes) {
+   if (!b || !events_buf) return set_err(RT_ERR_ARG, "rt_bulk_fetch_to: null argument");
+   if (b->fetched) return set_err(RT_ERR_STATE, "rt_bulk_fetch_to: already fetched");
+   b->user_pool = static_cast<rt_event *>(events_buf); b->user_pool_bytes = bytes;
+   int rc = rt_bulk_fetch(b);
+   if (rc) { b->user_pool = nullptr; b->user_pool_bytes = 0; }
+   return rc; }
+
+extern "C" int rt_host_register(rt_tape *t, void *p, size_t bytes) {
+   if (!t || !p) return set_err(RT_ERR_ARG, "rt_host_register: null argument");
+   CU(cudaSetDevice(t->device));
+   CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+   return RT_OK; }
+extern "C" int rt_host_unregister(rt_tape *t, void *p) {
+   if (!t || !p) return set_err(RT_ERR_ARG, "rt_host_unregister: null argument");
+   CU(cudaSetDevice(t->device));
+   CU(cudaHostUnregister(p));
    return RT_OK; }
 
 /* Upload + whole-tape scan + fetch in one call, overlapped.  Replaces  rt_clear(); rt_upload(); rt_bulk_scan(cfg); rt_bulk_fetch().

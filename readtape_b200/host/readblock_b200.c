@@ -41,6 +41,7 @@
 #include <sys/mman.h>
 #include <sys/socket.h>
 #include <poll.h>
+#include <pthread.h>
 
 /* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
 extern FILE *inf;
@@ -611,6 +612,27 @@ static void serve_one(struct chan *ch) {                       /* parent: one ex
    else { rs.rc = rc; strncpy(rs.err, rt_last_error(), sizeof rs.err - 1); }
    xfer(ch->fd, &rs, sizeof rs, 1); }
 
+/* the memory the workers will read the events from is prepared while CUDA starts up and the file travels to the GPU: an anonymous
+   MAP_SHARED mapping, its pages touched by a few threads (4-5 GB of page faults are a second of single-thread work otherwise) */
+static struct { pthread_t th; char *buf; size_t bytes; int started; } PREP;
+struct touch { char *p; size_t n; };
+static void *prep_touch(void *arg) { struct touch *r = arg; for (size_t i = 0; i < r->n; i += 4096) r->p[i] = 0; return NULLP; }
+static void *prep_main(void *arg) {
+   (void)arg;
+   void *p = mmap(NULLP, PREP.bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+   if (p == MAP_FAILED) { PREP.buf = NULLP; return NULLP; }
+   PREP.buf = p;
+   enum { NT = 8 };
+   pthread_t th[NT]; struct touch r[NT];
+   const size_t per = (PREP.bytes / NT + 4095) / 4096 * 4096;
+   for (int k = 0; k < NT; ++k) {
+      size_t lo = (size_t)k * per; if (lo > PREP.bytes) lo = PREP.bytes;
+      r[k].p = PREP.buf + lo; r[k].n = PREP.bytes - lo < per ? PREP.bytes - lo : per;
+      pthread_create(&th[k], NULLP, prep_touch, &r[k]); }
+   for (int k = 0; k < NT; ++k) pthread_join(th[k], NULLP);
+   return NULLP; }
+
+#define WRET do { if (PREP.buf) { munmap(PREP.buf, PREP.bytes); PREP.buf = NULLP; } return; } while (0)
 static void run_workers(void) {
    const char *env = getenv("RT_WORKERS");
    int P = env ? atoi(env) : 1;
@@ -618,18 +640,31 @@ static void run_workers(void) {
    if (!(tbin_file && tap_format && quiet && !do_txtfile && mode != WW && subsample == 1 && bpi != 0 && !doing_density_detection
          && !doing_deskew && (!deskew || skew_given) && numblks == 0 && numblks_limit == INT_MAX && outf == NULLP)) return;
    double w0 = wall();
+   {  /* events to expect: one per ~48 track-samples per parameter set (800 BPI NRZI at 20 samples per bit: one per ~76) */
+      long long pos = ftello(inf); fseeko(inf, 0, SEEK_END); long long end = ftello(inf); fseeko(inf, pos, SEEK_SET);
+      int nps = 0; for (int i = 0; i < MAXPARMSETS; ++i) if (i == block.parmset || (multiple_tries && parmsetsptr[i].active)) ++nps;
+      PREP.bytes = ((size_t)((end - pos) / 2 / 48) * 32 * (size_t)nps + (64u << 20)) / 4096 * 4096;
+      PREP.started = pthread_create(&PREP.th, NULLP, prep_main, NULLP) == 0; }
    open_tape();
-   if (!S.use_bulk) return;
+   if (PREP.started) pthread_join(PREP.th, NULLP);
+   if (!S.use_bulk) WRET;
    if (P > 256) P = 256;
    if (S.nrows / (uint64_t)P < WORKER_MIN_ROWS) P = (int)(S.nrows / WORKER_MIN_ROWS);
-   if (P <= 1) return;
+   if (P <= 1) WRET;
    /* 1. every parameter set the run may use, scanned at once, results where children can read them */
    rt_set_option(RT_OPT_SHARED_RESULTS, 1);
    const int ps0 = block.parmset;
    double w1 = wall();
-   if (!scan_parmsets()) { rt_set_option(RT_OPT_SHARED_RESULTS, 0); return; }
+   if (!scan_parmsets()) { rt_set_option(RT_OPT_SHARED_RESULTS, 0); WRET; }
    double w2 = wall();
-   int rc = rt_bulk_fetch(S.bulk[ps0].bulk);
+   int rc = RT_ERR_OVERFLOW;
+   if (PREP.started && PREP.buf) {                              /* straight into the prepared mapping, pinned for the copy */
+      const int reg = rt_host_register(S.tape, PREP.buf, PREP.bytes) == RT_OK;
+      rc = rt_bulk_fetch_to(S.bulk[ps0].bulk, PREP.buf, PREP.bytes);
+      if (reg) rt_host_unregister(S.tape, PREP.buf);
+      if (rc == RT_ERR_OVERFLOW) { munmap(PREP.buf, PREP.bytes); PREP.buf = NULLP; }
+      else PREP.buf = NULLP; }                                  /* the results live there from now on */
+   if (rc == RT_ERR_OVERFLOW) rc = rt_bulk_fetch(S.bulk[ps0].bulk);   /* more events than expected: the library maps what is needed */
    rt_set_option(RT_OPT_SHARED_RESULTS, 0);
    if (rc) rtfatal("rt_bulk_fetch", rc);
    if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2) printf("  B200 scan: whole-tape scan %.3f s, results to the host %.3f s\n", w2 - w1, wall() - w2);
@@ -642,7 +677,7 @@ static void run_workers(void) {
       if (rc != RT_OK) break;                                   /* no boundary behind this row: the last part takes the rest */
       if (ui.row0 > cut[parts - 1]) cut[parts++] = ui.row0; }
    P = parts; cut[P] = UINT64_MAX;
-   if (P <= 1) return;
+   if (P <= 1) WRET;
    S.s_open += wall() - w0;
    static struct chan ch[256];
    static char base[MAXPATH + 50];

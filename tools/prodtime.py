@@ -17,6 +17,6 @@ for w in workers.split(","):
     dt = time.time() - t0
     print(f"== workers {w}: rc {r.returncode} {dt:.2f} s  {reps*tile.shape[0]*9/dt/1e9:.2f} G ts/s")
     for l in r.stdout.splitlines():
-        if "B200 scan" in l and ("rt_open" in l or "opening" in l):
+        if "B200 scan" in l and ("rt_open" in l or "opening" in l or "whole-tape" in l) and " worker " not in l:
             print("   ", l.strip())
 shutil.rmtree(d)
