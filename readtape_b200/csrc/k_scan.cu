@@ -21,11 +21,14 @@ __global__ void k_ctx_reset(DevCfg c, TrkState *st, SkewState *sk, int kind, uin
    if (kind == RT_RESET_FULL) reset_full(c, t, s, trk, row, time_is_zero != 0);
    else if (kind == RT_RESET_WW_PARTIAL) {          /* decode_ww.c:42: t_lastpeak = t_prevlastpeak = 0 */
       t.t_lastpeak = 0;
-      t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u); }
+      t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u);
+      t.pure_from = RT_NOROW; }                     /* until the re-initialisation row has passed (track_row sets it) */
    else if (kind == RT_RESET_PEAKSTATE) {           /* decoder.c:413-423 */
       for (int i = 0; i < RT_MAXSKEWSAMP; ++i) s.vdelayed[i] = 0;
       s.ndx_next = s.slots_filled = 0;
-      t.left = t.right = 0; t.minv = t.maxv = 0; t.countdown = 0; } }
+      t.left = t.right = 0; t.minv = t.maxv = 0; t.countdown = 0;
+      t.pure_from = row + (uint64_t)(2 * c.width + c.skew[trk] + 2); }
+   else if (kind == RT_RESET_NONE) t.pure_from = row + (uint64_t)(2 * c.width + c.skew[trk] + 2); }   /* repositioned, or the skew changed: the ring and the FIFO refill first */
 
 __global__ void k_ctx_set_avg_height(TrkState *st, int trk, float v) {
    st[trk].avg_height = v; st[trk].avg_height_count = 0; st[trk].avg_height_sum = 0; }
@@ -38,7 +41,22 @@ __global__ void k_ctx_scan(DevCfg c, TrkState *st, SkewState *sk, uint64_t row_f
    const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
    FlatEmit em{evbuf + (size_t)trk * cap, cap, 0, (uint8_t)trk};
    float v;
-   for (uint64_t row = row_from; row < row_to; ++row) track_row(c, t, s, trk, plane, row, em, &v);
+   /* skip-ahead (scan_generic.cuh): jump from candidate row to candidate row where the masks of phase A are at hand */
+   const bool can_skip = c.m_cand && c.m_acan && c.det == RT_DET_PEAK && !c.invert && !c.differentiate && c.T0[trk] > 0;
+   const float inv_lsb = 32767.0f / c.maxvolts;
+   const uint64_t min_jump = (uint64_t)(3 * c.width + c.skew[trk] + 8);
+   for (uint64_t row = row_from; row < row_to; ++row) {
+      if (can_skip && t.init_row == RT_NOROW && t.pure_from != RT_NOROW && row > t.pure_from && row > row_from) {
+         /* the integer bound of required_rise (decoder.c:785) as the two-pass scan derives it (SparseScan::thresholds) */
+         const float rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+         const float q = rise * inv_lsb * 0.999f - 2.0f;
+         if (q > 0 && (q > 70000.0f ? 70000 : (int)q) >= c.T0[trk]) {
+            const uint64_t from = row + (uint64_t)t.countdown;          /* blind until then anyway (decoder.c:778) */
+            const uint64_t nc = next_candidate(c, trk, from < row_to ? from : row_to, row_to);
+            if (nc >= row + min_jump && skip_to(c, t, s, trk, plane, row - 1, nc - 1)) {
+               row = nc;
+               if (row >= row_to) break; } } }
+      track_row(c, t, s, trk, plane, row, em, &v); }
    st[trk] = t; sk[trk] = s;
    counts[trk] = em.n;
    if (t.failed) atomicMax(failed, (uint32_t)t.failed); }

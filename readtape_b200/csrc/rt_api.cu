@@ -373,6 +373,8 @@ struct rt_scan {
    rt_event *d_ev = nullptr; uint32_t cap = 0; uint32_t *d_counts = nullptr, *d_failed = nullptr;
    rt_event *h_ev = nullptr; size_t h_ev_cap = 0;       /* pinned staging */
    std::vector<rt_event> merged;
+   /* skip-ahead (scan_generic.cuh): candidate / canonical bit planes of the whole tape for this configuration's window width */
+   uint32_t *d_mc = nullptr, *d_md = nullptr, *d_ma = nullptr; uint64_t mask_rows = 0, mask_stride = 0; int mask_width = 0;
 };
 
 static int scan_alloc_events(rt_scan *s, uint32_t cap) {
@@ -411,6 +413,10 @@ extern "C" int rt_scan_set_cfg(rt_scan *s, const rt_scan_cfg *cfg) {
    if (cfg->mode != s->cfg.mode) return set_err(RT_ERR_ARG, "rt_scan_set_cfg: the mode cannot change");
    int rc = cfg_check(s->tape, cfg); if (rc) return rc;
    s->cfg = *cfg; cfg_to_dev(s->tape, cfg, &s->dc); s->have_ckpt = false;
+   if (s->positioned) {                                          /* e.g. new skew delays: the deskew FIFO refills before rows are skipped again */
+      CU(cudaSetDevice(s->tape->device));
+      launch_ctx_reset(s->dc, s->d_st, s->d_sk, RT_RESET_NONE, s->pos, 0, s->tape->stream);
+      CU(cudaGetLastError()); ++s->tape->launches; }
    return RT_OK; }
 
 extern "C" int rt_scan_reset(rt_scan *s, int kind, uint64_t row) {
@@ -420,15 +426,41 @@ extern "C" int rt_scan_reset(rt_scan *s, int kind, uint64_t row) {
    CU(cudaSetDevice(t->device));
    int rc = tape_sync_valid(t); if (rc) return rc;
    s->dc.planes = t->planes; s->dc.plane_stride = t->plane_stride; s->dc.nrows = t->nrows_valid;
-   if (kind != RT_RESET_NONE) {
+   if (kind != RT_RESET_NONE || (s->positioned && row != s->pos)) {
       int tz = rt_row_time(&t->desc, row) == 0.0;
       launch_ctx_reset(s->dc, s->d_st, s->d_sk, kind, row, tz, t->stream);
       CU(cudaGetLastError()); ++t->launches; }
    s->pos = row; s->positioned = true; s->have_ckpt = false;
    return RT_OK; }
 
+/* the bit planes the exact scan's skip-ahead reads: built once per (tape contents, window width), thresholds = a quarter of the
+   default-state bound (the scan only trusts them while its own bound is above that; never a result depends on them) */
+static int scan_prepare_masks(rt_scan *s) {
+   rt_tape *t = s->tape; DevCfg &dc = s->dc;
+   const char *env = getenv("RT_EXACT_SKIP");
+   const bool want = !(env && env[0] == '0') && dc.det == RT_DET_PEAK && !dc.invert && !dc.differentiate && dc.width >= 3
+                     && dc.width <= RT_PKWW_MAX_WIDTH && peak_mask_T0(dc, 0.25f) > 0 && t->nrows_valid > 4096;
+   dc.m_cand = dc.m_cand2 = dc.m_acan = nullptr; dc.mask_stride = 0;
+   for (int k = 0; k < RT_MAXTRKS; ++k) dc.T0[k] = dc.T1[k] = 0;
+   if (!want) return RT_OK;
+   const uint32_t nt = t->desc.ntrks;
+   const uint64_t ms = peak_mask_stride(t->plane_stride);
+   if (ms != s->mask_stride) {
+      cudaFree(s->d_mc); cudaFree(s->d_md); cudaFree(s->d_ma); s->d_mc = s->d_md = s->d_ma = nullptr; s->mask_stride = 0; s->mask_rows = 0;
+      CU(cudaMalloc(&s->d_mc, (size_t)ms * nt * 4)); CU(cudaMalloc(&s->d_md, (size_t)ms * nt * 4)); CU(cudaMalloc(&s->d_ma, (size_t)ms * nt * 4));
+      s->mask_stride = ms; }
+   const int T0 = peak_mask_T0(dc, 0.25f);
+   for (uint32_t k = 0; k < nt; ++k) dc.T0[k] = T0;
+   dc.m_cand = s->d_mc; dc.m_cand2 = s->d_md; dc.m_acan = s->d_ma; dc.mask_stride = ms;
+   if (s->mask_rows != t->nrows_valid || s->mask_width != dc.width) {
+      cudaError_t e = launch_peak_masks(dc, 0, t->nrows_valid, t->stream); ++t->launches;
+      if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "mask kernel launch failed: %s", cudaGetErrorString(e));
+      s->mask_rows = t->nrows_valid; s->mask_width = dc.width; }
+   return RT_OK; }
+
 static int scan_span(rt_scan *s, uint64_t from, uint64_t to, bool want_events) {
    rt_tape *t = s->tape; const uint32_t nt = t->desc.ntrks;
+   { int rc = scan_prepare_masks(s); if (rc) return rc; }
    for (;;) {
       uint32_t zero = 0;
       CU(cudaMemcpyAsync(s->d_failed, &zero, sizeof zero, cudaMemcpyHostToDevice, t->stream));
@@ -504,6 +536,7 @@ extern "C" void rt_scan_end(rt_scan *s) {
    cudaSetDevice(s->tape->device);
    cudaStreamSynchronize(s->tape->stream);
    cudaFree(s->d_st); cudaFree(s->d_ckst); cudaFree(s->d_sk); cudaFree(s->d_cksk); cudaFree(s->d_counts); cudaFree(s->d_ev);
+   cudaFree(s->d_mc); cudaFree(s->d_md); cudaFree(s->d_ma);
    if (s->h_ev) cudaFreeHost(s->h_ev);
    delete s; }
 

@@ -80,6 +80,9 @@ struct TrkState {
    /* replaces the `t_lastpeak == 0` test + `break` of decoder.c:855-861 (quirk Q2): the row at which
       this track (re)initialises after a reset; rows before it are skipped; RT_NOROW = done */
    uint64_t init_row;
+   /* the exact stateful scan may jump over rows that cannot fire (k_scan.cu: skip-ahead) once the window and the deskew FIFO hold
+      nothing but the last consecutive samples of the plane: true from this row on (set by every reset / re-initialisation) */
+   uint64_t pure_from;
    /* times */
    double   t_top, t_bot, t_lastpeak, t_firstzero, t_lastzero;
    /* voltages */

@@ -224,7 +224,8 @@ __device__ inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, in
    t.avg_height = RT_PKWW_PEAKHEIGHT;
    if (!c.density) { t.clk_avg = c.clk_init; for (int i = 0; i < RT_CLKRATE_WINDOW; ++i) t.clk_spacing[i] = c.clk_init; }
    t.t_clkwindow = t.clk_avg / 2 * c.p.clk_factor;
-   t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u); }
+   t.init_row = row + (uint64_t)trk + (time_is_zero ? 1u : 0u);
+   t.pure_from = t.init_row + (uint64_t)(c.width + c.skew[trk] + 2); }
 
 /* ---- quiet tracking: the proof data of the speculative scan (DESIGN.md "unit equivalence") ---------
  * raw_at(j) is the sample of row j as it ENTERS the deskew FIFO.  Any detector window a scan can hold at
@@ -274,6 +275,85 @@ struct QuietTracker {
          if (c.differentiate) { float u = volts_at(c, plane, j); loud = loud || u >= RT_DIFF_THRESHOLD || u <= -RT_DIFF_THRESHOLD; }
          if (loud) last_loud = j + (uint64_t)(L - 1); } } };   /* it stays inside every span for L rows */
 
+/* ---- skip-ahead of the exact stateful scan (k_ctx_scan) ----------------------------------------------------------------------
+ * The moving-window peak detector does per-row work on every sample, but it can only FIRE at rows whose window passes the shape
+ * tests, and phase A of the two-pass scan (scan_masks.cuh) has marked those rows for every threshold >= T0 (`cand`).  Between two
+ * candidate rows the detector state evolves as a pure function of the samples: the ring and the deskew FIFO hold the last samples,
+ * the running maximum is the exact window maximum, the blind countdown counts down, and the lazily refreshed minimum (quirk Q1,
+ * decoder.c:765) follows from its last value by hopping from refresh to refresh (at an `acan` row the minimum is the window's; after
+ * a refresh the next one comes when the leftmost sample carrying the minimum leaves).  So instead of walking those rows, the state
+ * at the row in front of the next candidate is rebuilt from the plane -- bit-identical to having walked there.  Only for the plain
+ * peak detector (no -invert / -differentiate), only while the threshold bound covers T0, and only once the window and the FIFO are
+ * free of the perturbations a reset leaves behind (TrkState::pure_from). */
+__device__ __forceinline__ float gvolts(const DevCfg &c, int x) { return (float)x / 32767 * c.maxvolts; }
+
+/* the lazy minimum (int16 domain) at plane row pr, exact value m at plane row pr0 < pr; see SparseScan::lazy_min (scan_sparse.cuh) */
+__device__ inline int lazy_min_hop(const int16_t *plane, const uint32_t *acan, int w, int64_t pr0, int64_t pr, int m) {
+   int64_t a = pr0; bool have = false;
+   {  int64_t wi = pr >> 5;                                       /* last acan row in (pr0, pr] */
+      uint32_t bits = acan[wi] & (0xffffffffu >> (31 - (int)(pr & 31)));
+      for (;;) {
+         const int64_t base = wi << 5;
+         if (base + 31 <= pr0) break;
+         if (base <= pr0) bits &= (pr0 - base) >= 31 ? 0u : (0xffffffffu << ((int)(pr0 - base) + 1));
+         if (bits) { a = base + 31 - __clz((int)bits); have = true; break; }
+         if (base <= pr0 || wi == 0) break;
+         --wi; bits = acan[wi]; } }
+   int64_t r = have ? a : pr0;
+   bool keep = !have;
+   for (;;) {
+      const int64_t ws = r - w + 1;
+      int mn = 32767, pmn = 0, peq = -1;
+      for (int i = 0; i < w; ++i) { const int v = plane[ws + i]; if (v < mn) { mn = v; pmn = i; } if (peq < 0 && v == m) peq = i; }
+      int64_t at;
+      if (keep && peq >= 0) at = ws + peq; else { m = mn; at = ws + pmn; }
+      keep = false;
+      if (at + w > pr) break;
+      r = at + w; }
+   return m; }
+
+/* Rebuild the state as it is after row `r` has been processed, coming from the state after row `cur` (cur < r), given that no row in
+   (cur, r] can fire.  Window full and pure on entry.  Returns false (state untouched) if the lazy minimum's carrier cannot be found. */
+__device__ inline bool skip_to(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane, uint64_t cur, uint64_t r) {
+   const int w = c.width, delay = c.skew[trk];
+   const int64_t pr0 = (int64_t)cur - delay, pr = (int64_t)r - delay;
+   /* the int16 sample that carries the lazy minimum now */
+   int m = 32768;
+   for (int i = 0; i < w; ++i) { const int x = plane[pr0 - w + 1 + i]; if (gvolts(c, x) == t.minv) { m = x; break; } }
+   if (m == 32768) return false;
+   m = lazy_min_hop(plane, c.m_acan + (size_t)trk * c.mask_stride, w, pr0, pr, m);
+   const uint64_t n = r - cur;
+   t.right = (int)(((uint64_t)t.right + n) % (uint64_t)w);
+   t.left = t.right + 1 >= w ? 0 : t.right + 1;
+   float mx = -100;
+   for (int i = 0; i < w; ++i) {
+      const float v = gvolts(c, plane[pr - w + 1 + i]);
+      int ndx = t.left + i; if (ndx >= w) ndx -= w;
+      t.win[ndx] = v;
+      if (v > mx) mx = v; }
+   t.maxv = mx; t.minv = gvolts(c, m);
+   t.countdown = (uint64_t)t.countdown > n ? t.countdown - (int)n : 0;
+   if (delay) {                                                  /* the FIFO holds the last `delay` raw samples */
+      s.ndx_next = (int)(((uint64_t)s.ndx_next + n) % (uint64_t)delay);
+      for (int i = 0; i < delay; ++i) {
+         int ndx = s.ndx_next + i; if (ndx >= delay) ndx -= delay;
+         s.vdelayed[ndx] = gvolts(c, plane[(int64_t)r - delay + 1 + i]); }
+      s.slots_filled = delay; }
+   return true; }
+
+/* first stream row >= `from` (and < `to`) whose candidate bit is set; `to` if there is none */
+__device__ inline uint64_t next_candidate(const DevCfg &c, int trk, uint64_t from, uint64_t to) {
+   const int delay = c.skew[trk];
+   const uint32_t *mc = c.m_cand + (size_t)trk * c.mask_stride;
+   uint64_t p = from - (uint64_t)delay; const uint64_t pend = to - (uint64_t)delay;
+   uint64_t wi = p >> 5;
+   uint32_t bits = mc[wi] & (0xffffffffu << (int)(p & 31));
+   for (;;) {
+      if (bits) { const uint64_t q = (wi << 5) + (uint64_t)(__ffs((int)bits) - 1); return q < pend ? q + (uint64_t)delay : to; }
+      ++wi;
+      if ((wi << 5) >= pend) return to;
+      bits = mc[wi]; } }
+
 /* ---- one row of one track ------------------------------------------------------------------- */
 /* returns the probe bits of peak_step (0 for the other detectors / skipped rows);
    *v_out = the sample before the deskew FIFO (after invert/differentiate) */
@@ -306,6 +386,7 @@ __device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s,
          t.maxv = t.minv = v_now;
          t.t_lastpeak = row_time(c, row);
          t.init_row = RT_NOROW;
+         t.pure_from = row + (uint64_t)(c.width + c.skew[trk] + 2);   /* slot 0 of the ring was overwritten, this row's sample not pushed */
          return 0; } }
    RowClock clk(c, row);
    unsigned probe = 0;
