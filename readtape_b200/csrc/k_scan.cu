@@ -44,7 +44,7 @@ __global__ void k_ctx_scan(DevCfg c, TrkState *st, SkewState *sk, uint64_t row_f
    /* skip-ahead (scan_generic.cuh): jump from candidate row to candidate row where the masks of phase A are at hand */
    const bool can_skip = c.m_cand && c.m_acan && c.det == RT_DET_PEAK && !c.invert && !c.differentiate && c.T0[trk] > 0;
    const float inv_lsb = 32767.0f / c.maxvolts;
-   const uint64_t min_jump = (uint64_t)(3 * c.width + c.skew[trk] + 8);
+   const uint64_t min_jump = 4;                      /* rebuilding the state costs about as much as walking three rows */
    for (uint64_t row = row_from; row < row_to; ++row) {
       if (can_skip && t.init_row == RT_NOROW && t.pure_from != RT_NOROW && row > t.pure_from && row > row_from) {
          /* the integer bound of required_rise (decoder.c:785) as the two-pass scan derives it (SparseScan::thresholds) */

@@ -94,6 +94,9 @@ static struct {
 
 static double wall(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
+/* the exact scan runs in spans: the first one of a block decode is short (Whirlwind blocks are a few thousand rows, and what was
+   scanned beyond the block's end is scanned again after the next reset), the following ones double */
+#define EXACT_SPAN_FIRST (1u << 12)
 #define EXACT_SPAN_ROWS  (1u << 17)
 /* the smallest share a reel is split into; the environment override exists for tests on the small bundled captures */
 #define WORKER_MIN_ROWS     (getenv("RT_WORKER_MIN_ROWS") ? strtoull(getenv("RT_WORKER_MIN_ROWS"), NULLP, 10) : (uint64_t)(8u << 20))
@@ -159,7 +162,15 @@ static void open_tape(void) {
    /* the payload goes to the GPU straight from the page cache: the library reads the file with a few threads into its pinned
       staging ring (no whole-file buffer, pinned or not) */
    S.rows_bytes = (size_t)(nrows_file * rowbytes);
-   rc = rt_upload_fd(S.tape, fileno(inf), (uint64_t)S.base_pos, nrows_file);
+   if (getenv("RT_UPLOAD_MMAP") && atoi(getenv("RT_UPLOAD_MMAP"))) {   /* experiment: hand the library a mapping of the file instead */
+      const long pg = sysconf(_SC_PAGESIZE);
+      const off_t map_off = (off_t)(S.base_pos / pg * pg);
+      const size_t map_len = S.rows_bytes + (size_t)(S.base_pos - map_off);
+      void *map = mmap(NULLP, map_len, PROT_READ, MAP_SHARED, fileno(inf), map_off);
+      assert(map != MAP_FAILED, "cannot map the .tbin payload");
+      rc = rt_upload(S.tape, (const int16_t *)((const char *)map + (S.base_pos - map_off)), nrows_file);
+      munmap(map, map_len); }
+   else rc = rt_upload_fd(S.tape, fileno(inf), (uint64_t)S.base_pos, nrows_file);
    if (rc) rtfatal("rt_upload_fd", rc);
    if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2)
       rlog("  B200 scan: rt_open %.3f s, upload of %.2f GB %.3f s\n", w2 - w1, S.rows_bytes / 1e9, wall() - w2);
@@ -177,6 +188,7 @@ struct evsrc {
    /* what is needed to carry on with the exact scan when a speculative unit ends inside the block */
    uint64_t row0; const rt_scan_cfg *cfg;
    uint64_t taken; uint64_t last_row; int last_trk;   /* events handed out so far, and the last of them */
+   uint64_t span;                                     /* rows of the next exact span */
 };
 #define TAKE(src) do { (src)->last_row = (src)->ev[(src)->at].row; (src)->last_trk = (src)->ev[(src)->at].trk; ++(src)->at; ++(src)->taken; } while (0)
 
@@ -207,7 +219,9 @@ static void remote_exact(struct evsrc *src, struct wreq *rq) {
 static void exact_more(struct evsrc *src) {  /* continue the exact scan by one span */
    if (S.remote_fd >= 0) { struct wreq rq; memset(&rq, 0, sizeof rq); rq.op = WOP_MORE; remote_exact(src, &rq); return; }
    uint64_t done = 0;
-   int rc = rt_scan_run(S.ctx, EXACT_SPAN_ROWS, &src->ev, &src->n, &done);
+   if (!src->span) src->span = EXACT_SPAN_FIRST;
+   int rc = rt_scan_run(S.ctx, src->span, &src->ev, &src->n, &done);
+   if (src->span < EXACT_SPAN_ROWS) src->span *= 2;
    if (rc) rtfatal("rt_scan_run", rc);
    src->at = 0; src->valid_end = rt_scan_pos(S.ctx); ++S.n_exact_spans;
    if (done == 0) src->valid_end = UINT64_MAX; /* end of tape: nothing more will ever come */ }
@@ -586,7 +600,7 @@ static void decode_from(uint64_t row0, int reset_kind, const rt_scan_cfg *cfg, s
  * Only what is safe to split is split: .tap output, quiet mode (per-block log lines carry running block numbers), no text file, no
  * Whirlwind (state persists), no density / deskew pre-pass pending. */
 #define WORKER_BUF_EVENTS (1u << 19)
-struct chan { int fd; pid_t pid; int alive; rt_event *buf; rt_scan *ctx; rt_scan_cfg cfg; };
+struct chan { int fd; pid_t pid; int alive; rt_event *buf; rt_scan *ctx; rt_scan_cfg cfg; uint64_t span; };
 
 static void part_name(char *buf, size_t n, int i, const char *ext) { snprintf(buf, n, "%s.part%03d%s", baseoutfilename, i, ext); }
 static void worker_exit(int status, void *arg) { (void)arg; fflush(NULLP); _exit(status); }   /* no CUDA teardown in a forked child */
@@ -601,9 +615,12 @@ static void serve_one(struct chan *ch) {                       /* parent: one ex
       if (!ch->ctx) rc = rt_scan_begin(S.tape, &rq.cfg, &ch->ctx);
       else if (memcmp(&ch->cfg, &rq.cfg, sizeof rq.cfg) != 0) rc = rt_scan_set_cfg(ch->ctx, &rq.cfg);
       ch->cfg = rq.cfg;
-      if (!rc) rc = rt_scan_reset(ch->ctx, rq.reset_kind & 0xff, rq.row); }
+      if (!rc) rc = rt_scan_reset(ch->ctx, rq.reset_kind & 0xff, rq.row);
+      ch->span = EXACT_SPAN_FIRST; }
    const rt_event *ev = NULLP; uint64_t n = 0, done = 0;
-   for (uint64_t span = EXACT_SPAN_ROWS; !rc; span /= 2) {      /* a span whose events fit the shared buffer */
+   uint64_t span0 = ch->span ? ch->span : EXACT_SPAN_FIRST;
+   if (ch->span < EXACT_SPAN_ROWS) ch->span = span0 * 2;
+   for (uint64_t span = span0; !rc; span /= 2) {                /* a span whose events fit the shared buffer */
       rc = rt_scan_run(ch->ctx, span, &ev, &n, &done);
       if (rc || n <= WORKER_BUF_EVENTS) break;
       rc = rt_scan_rewind(ch->ctx, rt_scan_pos(ch->ctx) - done);
