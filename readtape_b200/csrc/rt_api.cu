@@ -258,32 +258,29 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
       const char *env = getenv("RT_UPLOAD_THREADS");
       const char *reg = getenv("RT_UPLOAD_REGISTER");
       if (pageable && reg && atoi(reg)) {
-         /* pin the caller's pages in place (e.g. a mapping of a file in the page cache) and let the copy engine read them directly:
-            no CPU copy at all; done piecewise so that pinning the next piece overlaps the copy of the current one */
-         const uint64_t piece = (uint64_t)atoi(reg) > 1 ? (uint64_t)atoi(reg) << 20 : (uint64_t)256 << 20;      /* bytes */
-         const char *base = reinterpret_cast<const char *>(rows);
-         const uint64_t total = nrows * nh * 2;
-         const uintptr_t pg = 4096;
-         bool ok = true; uint64_t done_rows = 0; int buf = 0;
-         uintptr_t reg_lo = reinterpret_cast<uintptr_t>(base) / pg * pg, prev_lo = 0, prev_len = 0;
-         while (ok && done_rows < nrows) {
-            const uintptr_t want_hi = std::min<uintptr_t>(reinterpret_cast<uintptr_t>(base) + total, reg_lo + piece);
-            const uintptr_t hi = (want_hi + pg - 1) / pg * pg;
-            if (cudaHostRegister(reinterpret_cast<void *>(reg_lo), hi - reg_lo, cudaHostRegisterReadOnly) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
-            /* rows wholly inside the pinned pieces so far */
-            const uint64_t rows_hi = std::min<uint64_t>(nrows, (want_hi - reinterpret_cast<uintptr_t>(base)) / (nh * 2));
-            while (done_rows < rows_hi) {
-               const uint64_t n = std::min(stage_rows, rows_hi - done_rows);
-               rc = enqueue_chunk(t, rows + done_rows * nh, n, buf);
+         /* experiment (RT_UPLOAD_REGISTER=1): pin the caller's pages in place (e.g. a mapping of a file in the page cache) and let
+            the copy engine read them directly -- no CPU copy at all */
+         const uintptr_t pg = 4096, lo = reinterpret_cast<uintptr_t>(rows) / pg * pg;
+         const uintptr_t hi = (reinterpret_cast<uintptr_t>(rows) + nrows * nh * 2 + pg - 1) / pg * pg;
+         auto w0 = std::chrono::steady_clock::now();
+         if (cudaHostRegister(reinterpret_cast<void *>(lo), hi - lo, cudaHostRegisterReadOnly) == cudaSuccess) {
+            auto w1 = std::chrono::steady_clock::now();
+            uint64_t done = 0; int buf = 0;
+            while (done < nrows) {
+               const uint64_t n = std::min(stage_rows, nrows - done);
+               rc = enqueue_chunk(t, rows + done * nh, n, buf);
                if (rc) { cudaDeviceSynchronize(); return rc; }
-               done_rows += n; buf ^= 1; }
-            if (prev_len) { cudaStreamSynchronize(t->s_copy); cudaHostUnregister(reinterpret_cast<void *>(prev_lo)); }
-            prev_lo = reg_lo; prev_len = hi - reg_lo;
-            reg_lo = want_hi / pg * pg;                            /* a row may straddle two pieces: the boundary page is pinned twice in turn */
-            if (reg_lo < prev_lo + prev_len) { cudaStreamSynchronize(t->s_copy); cudaHostUnregister(reinterpret_cast<void *>(prev_lo)); prev_len = 0; } }
-         if (prev_len) { cudaStreamSynchronize(t->s_copy); cudaHostUnregister(reinterpret_cast<void *>(prev_lo)); }
-         if (ok) { t->h2d_bytes += nrows * nh * 2; return tape_drain(t); }
-         if (done_rows) return set_err(RT_ERR_CUDA, "rt_upload: cudaHostRegister failed part-way"); }
+               done += n; buf ^= 1; }
+            rc = tape_drain(t);
+            auto w2 = std::chrono::steady_clock::now();
+            cudaHostUnregister(reinterpret_cast<void *>(lo));
+            auto w3 = std::chrono::steady_clock::now();
+            if (getenv("RT_TRACE")) fprintf(stderr, "[rt_upload] register %.3f s, copy+ingest %.3f s, unregister %.3f s\n", std::chrono::duration<double>(w1 - w0).count(),
+                                            std::chrono::duration<double>(w2 - w1).count(), std::chrono::duration<double>(w3 - w2).count());
+            t->h2d_bytes += nrows * nh * 2;
+            return rc; }
+         cudaGetLastError();
+         if (getenv("RT_TRACE")) fprintf(stderr, "[rt_upload] cudaHostRegister of the caller's memory failed: staging instead\n"); }
       if (pageable && !(env && atoi(env) == 0)) {
          rc = upload_pageable(t, rows, -1, 0, nrows, stage_rows);
          if (rc) { cudaDeviceSynchronize(); return rc; }
