@@ -297,13 +297,118 @@ def bench_capture(args, K, W):
     tape.close()
 
 
-def bench_gcr(args, rank, world, local_rank, W, K):
-    """BASELINE config 4: 9-track GCR 6250 density at 6.25 MHz with the zero-crossing detector (-zeros, as all reference GCR
-    examples), the 5 built-in GCR parameter sets (parmsets.c:106-110) x time shards dealt over the ranks (shard.assign_units).
-    Full size = 50e9 track-samples = 5.56e9 rows (100 GB) over 8 GPUs; per GPU `--rows` (default 1/8 of that).  Every
-    (parameter set, shard) unit is one whole-tape scan pass; track-samples are counted once per pass."""
+def bench_one_tape(args, rank, world, local_rank, W, K):
+    """--split one-tape: ONE reel of the config-2 size, time-sharded over the N GPUs of the job: the cuts lie at the
+    centres of inter-block gaps (shard.plan), every rank scans its own shard (plus the pre-roll rows a detector and the deskew FIFO
+    need), and the results -- unit tables, proof data and events -- are gathered on rank 0 over NCCL.  STRONG scaling: the work is
+    fixed, `value` = the reel's track-samples / the slowest rank's time including the gather."""
     import torch
+    import torch.distributed as dist
     from readtape_b200 import shard
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    lib = abi.load_product()
+    tile = synth.nrzi_tile()
+    T = tile.shape[0]
+    rows_total = args.rows
+    hdr = synth.nrzi_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
+    # the reel's quiet gaps: those of the super-tile, repeated (what shard.quiet_gaps finds on any stretch of it)
+    lsb = hdr.maxvolts / 32767.0
+    gaps_tile = shard.quiet_gaps(tile, thr_lsb=int(0.15 / lsb), min_gap_rows=2000)
+    ntiles = (rows_total + T - 1) // T
+    gaps = [(s + k * T, e + k * T) for k in range(ntiles) for s, e in gaps_tile if e + k * T <= rows_total]
+    shards = shard.plan(rows_total, gaps, world)
+    a, b = shards[rank]
+    PRE = 50 + 50 + 9 + 3                                           # MAXSKEWSAMP + PKWW_MAX_WIDTH + ntrks rows in front of the cut
+    lo = max(0, a - PRE) // 2048 * 2048                              # whole ingest tiles
+    n = b - lo
+    dev = torch.empty((n, 9), dtype=torch.int16, device="cuda")
+    tile_t = torch.from_numpy(tile).cuda()
+    at = 0
+    while at < n:                                                   # rows [lo, b) of the periodic reel
+        ph = (lo + at) % T
+        m = min(T - ph, n - at)
+        dev[at:at + m] = tile_t[ph:ph + m]
+        at += m
+    torch.cuda.synchronize()
+    tape = lib.open(shard.sub_desc(desc, lo), device=local_rank)
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    recv = None
+
+    def step():
+        nonlocal recv
+        tape.clear()
+        tape.attach_device(dev.data_ptr(), n)
+        bulk = tape.bulk_scan([cfg])
+        st = bulk.stats()
+        nbytes = bulk.results_size()
+        img = torch.empty((nbytes + 7) // 8 * 8, dtype=torch.uint8, device="cuda")
+        bulk.results_to_device(img.data_ptr(), img.numel())
+        bulk.free()
+        if world > 1:                                               # the result gather: sizes, then the images
+            mine = torch.tensor([img.numel()], dtype=torch.int64, device="cuda")
+            dist.all_gather(sizes, mine)
+            mx = int(max(int(s.item()) for s in sizes))
+            pad = torch.zeros(mx, dtype=torch.uint8, device="cuda"); pad[:img.numel()] = img
+            if rank == 0:
+                if recv is None or recv[0].numel() != mx:
+                    recv = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)]
+                dist.gather(pad, recv, dst=0)
+            else:
+                dist.gather(pad, None, dst=0)
+        return st, img.numel()
+
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(local_rank); sampler.start()
+    time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(K):
+        st, nbytes = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    clocks = sampler.stop()
+    elapsed = t1 - t0
+    ev = torch.tensor([int(st.events)], dtype=torch.int64, device="cuda")
+    by = torch.tensor([int(nbytes)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        tt = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); elapsed = float(tt.item())
+        dist.all_reduce(ev); dist.all_reduce(by)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        tsamp = rows_total * 9
+        alg = 2.0 * tsamp + 32.0 * int(ev.item())
+        line = {"metric": METRIC, "value": tsamp * K / elapsed, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(rows_total).replace(", per GPU", "") + f", ONE reel time-sharded over {world} GPU(s) at inter-block gaps",
+                           "split": "one-tape", "shards": [[int(x), int(y)] for x, y in shards], "pre_roll_rows": PRE,
+                           "l2": "inputs far larger than the 126 MB L2", "events_on_the_reel": int(ev.item())},
+                "roofline": {"bound": "hbm", "kernel": "whole step (ingest + unit finder + both scan passes + result gather)", "achieved": (alg + 2.0 * tsamp) / (elapsed / K) / 1e9 / world,
+                             "peak": peak, "unit": "GB/s", "frac": (alg + 2.0 * tsamp) / (elapsed / K) / 1e9 / world / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "per GPU: (4 B per track-sample for the ingest + 2 B per track-sample + 32 B per event for the scan) / step time"},
+                "e2e": None, "gpu_launches": (int(st.launches) + 2) * K, "clocks": clocks, "cpu_baseline": None,
+                "result_gather": {"bytes_to_rank0_per_step": int(by.item()), "collective": "all_gather(sizes) + gather(images) over NCCL" if world > 1 else "none (1 GPU)"}}
+        print(json.dumps(line))
+    tape.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_gcr(args, rank, world, local_rank, W, K):
+    """BASELINE config 4: synthetic 9-track GCR 6250 (9042 flux cells per inch, 50 IPS, 6.25 MHz) of DECODABLE blocks (synth.gcr_tile:
+    preamble, marks, 7+1-byte groups with valid ECC and parity, resync bursts; the reference decodes them error-free), zero-crossing
+    detector (-zeros, as all reference GCR examples), the 5 built-in GCR parameter sets (parmsets.c:106-110).  Full size = 50e9
+    track-samples = 5.56e9 rows (100 GB) time-sharded over 8 GPUs; every GPU scans its shard for all 5 parameter sets in ONE
+    rt_bulk_scan call ((parameter set x track x unit) jobs side by side).  Track-samples are counted once per parameter set.
+    Weak scaling: `--rows` rows per GPU (default 1/8 of the full reel)."""
+    import torch
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -311,19 +416,18 @@ def bench_gcr(args, rank, world, local_rank, W, K):
     torch.cuda.set_device(local_rank)
     lib = abi.load_product()
     rows = args.rows if args.rows != FULL_ROWS else 5_555_555_556 // 8
-    tile = synth.gcr_like_tile()
+    tile = synth.gcr_tile()
     T = tile.shape[0]
     hdr = synth.gcr_header()
     cfgs = [abi.make_cfg(tbin.MODE_GCR, p, hdr.bpi, hdr.ips, flags=abi.RT_F_FIND_ZEROS) for p in parmsets.GCR]
-    mine = shard.assign_units(len(cfgs), world, world)[rank]                  # [(parmset, shard)]
-    shards = sorted({s for _, s in mine})
-    dev = torch.empty((rows, 9), dtype=torch.int16, device="cuda")            # every shard of the synthetic reel is this tile sequence
+    dev = torch.empty((rows, 9), dtype=torch.int16, device="cuda")            # this rank's time shard of the reel: the tile sequence
     tile_t = torch.from_numpy(tile).cuda()
     for at in range(0, rows, T):
         n = min(T, rows - at)
         dev[at:at + n] = tile_t[:n]
     torch.cuda.synchronize()
-    tapes = {s: lib.open(abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns + s * rows * hdr.tdelta_ns), device=local_rank) for s in shards}
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns + rank * (rows // T * T) * hdr.tdelta_ns)
+    tape = lib.open(desc, device=local_rank)
 
     def barrier():
         if dist is not None:
@@ -331,14 +435,12 @@ def bench_gcr(args, rank, world, local_rank, W, K):
         torch.cuda.synchronize()
 
     def step():
-        out = []
-        for s in shards:
-            tapes[s].clear()
-            tapes[s].attach_device(dev.data_ptr(), rows)
-            bulk = tapes[s].bulk_scan([cfgs[p] for p, ss in mine if ss == s])
-            out.append(bulk.stats())
-            bulk.free()
-        return out
+        tape.clear()
+        tape.attach_device(dev.data_ptr(), rows)
+        bulk = tape.bulk_scan(cfgs)
+        st = bulk.stats()
+        bulk.free()
+        return st
 
     for _ in range(W):
         step()
@@ -346,37 +448,49 @@ def bench_gcr(args, rank, world, local_rank, W, K):
     time.sleep(0.25)
     barrier(); t0 = time.perf_counter()
     for _ in range(K):
-        sts = step()
+        st = step()
     barrier(); t1 = time.perf_counter()
     clocks = sampler.stop()
     elapsed = t1 - t0
-    passes = torch.tensor([len(mine)], dtype=torch.int64, device="cuda")
-    events = torch.tensor([sum(int(s.events) for s in sts)], dtype=torch.int64, device="cuda")
+    # full-scale check of parameter set 0 (outside the timed region): every tile the same events, one tile equal to the oracle's
+    verified = None
+    if not args.no_verify:
+        tape.clear(); tape.attach_device(dev.data_ptr(), rows)
+        bulk = tape.bulk_scan(cfgs[:1])
+        verified = verify.verify_periodic(abi.load_oracle(), bulk, desc, cfgs[0], tile, rows)
+        bulk.free()
+    events = torch.tensor([int(st.events)], dtype=torch.int64, device="cuda")
+    okt = torch.tensor([1 if (verified is None or verified["ok"]) else 0], dtype=torch.int64, device="cuda")
     if dist is not None:
         tt = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); elapsed = float(tt.item())
-        dist.all_reduce(passes); dist.all_reduce(events)                       # the result gather: counts only
+        dist.all_reduce(events); dist.all_reduce(okt, op=dist.ReduceOp.MIN)    # the result gather: counts only
     if rank == 0:
         peak, peak_src = measured_peak()
-        npass = int(passes.item())
+        npass = len(cfgs) * world
         value = npass * rows * 9 * K / elapsed
-        ms_scan = sum(s.ms_scan for s in sts); my_events = sum(int(s.events) for s in sts)
-        alg = 2.0 * rows * 9 * len(mine) + 32.0 * my_events
-        line = {"metric": "track-samples/s, 9-track 6.25 MHz GCR-density TBIN scan (zero-crossing detector), 5 parameter sets", "value": value, "unit": UNIT,
+        ms_scan = float(st.ms_scan)
+        alg = 2.0 * rows * 9 * len(cfgs) + 32.0 * int(st.events)
+        if verified is not None:
+            verified["ok_all_ranks"] = bool(okt.item())
+        line = {"metric": "track-samples/s, 9-track 6.25 MHz GCR 6250 TBIN scan (zero-crossing detector), 5 parameter sets", "value": value, "unit": UNIT,
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"synthetic 9-track GCR-density (9042 fci, 50 IPS, 6.25 MHz) TBIN, {rows} rows ({rows * 18 / 1e9:.1f} GB) per time shard, "
-                                       f"{world} shard(s) x {len(cfgs)} parameter sets = {npass} scan passes dealt over {world} GPU(s), -zeros",
-                           "l2": "inputs far larger than the 126 MB L2", "units_of_rank0": mine},
-                "roofline": {"bound": "hbm", "kernel": "k_units_zc (zero-crossing fast path, one lane per (unit, track))", "achieved": alg / (ms_scan * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": alg / (ms_scan * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_scan / max(1, len(mine))},
-                "e2e": None, "gpu_launches": sum(int(s.launches) for s in sts) * K + 2 * K * len(shards), "clocks": clocks, "cpu_baseline": None,
+                "config": {"workload": f"synthetic 9-track GCR 6250 (9042 fci, 50 IPS, 6.25 MHz) TBIN of decodable 4095-byte blocks, {rows} rows ({rows * 18 / 1e9:.1f} GB) "
+                                       f"per GPU (time shard), x {len(cfgs)} parameter sets = {npass} scan passes over {world} GPU(s), -zeros",
+                           "l2": "inputs far larger than the 126 MB L2", "units_per_shard": int(st.units), "events_per_gpu_step": int(st.events),
+                           "tile_sha256": synth.tile_sha256(tile)[:16], "verified": verified},
+                "roofline": {"bound": "hbm", "kernel": "k_units_zc (zero-crossing fast path, one lane per (parameter set, unit, track))", "achieved": alg / (ms_scan * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": alg / (ms_scan * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_scan,
+                             "note": "the 5 parameter sets' kernels run side by side; ms is the span from the first launch to the last completion"},
+                "e2e": None, "gpu_launches": int(st.launches) * K + 2 * K, "clocks": clocks, "cpu_baseline": None,
                 "result_gather": {"passes": npass, "events": int(events.item())}}
         print(json.dumps(line))
-    for t in tapes.values():
-        t.close()
+    tape.close()
     if dist is not None:
         dist.destroy_process_group()
+    if not bool(okt.item()):
+        sys.exit(1)
 
 
 def main():
@@ -390,6 +504,9 @@ def main():
     ap.add_argument("--workload", default="nrzi", choices=["nrzi", "gcr", "pe", "ww"],
                     help="nrzi: BASELINE config 2 (the headline line); gcr: config 4, GCR-density tape x 5 parameter sets sharded over the GPUs; "
                          "pe: config 3, examples/9trk_PE with 8 parameter sets fanned out on one GPU; ww: config 5, the Whirlwind reel on the exact stateful scan")
+    ap.add_argument("--split", default="replicas", choices=["replicas", "one-tape"],
+                    help="N > 1: replicas = every GPU its own reel of the config-2 size (weak scaling, the default); one-tape = ONE reel "
+                         "time-sharded over the GPUs at inter-block gaps, results gathered on rank 0 over NCCL (strong scaling)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-product", action="store_true", help="skip the whole-program run (TBIN file -> .tap through readtape_b200)")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-scale check of the scan's events against the oracle (outside the timed regions)")
@@ -401,6 +518,8 @@ def main():
 
     if args.workload == "gcr":
         return bench_gcr(args, rank, world, local_rank, W, K)
+    if args.split == "one-tape" and args.impl == "b200":
+        return bench_one_tape(args, rank, world, local_rank, W, K)
     if args.workload in ("pe", "ww"):
         if rank == 0:
             bench_capture(args, K, W)

@@ -198,6 +198,12 @@ int  rt_bulk_scan(rt_tape *tape, const rt_scan_cfg *cfgs, uint32_t ncfgs, rt_bul
 /* rt_bulk_scan() leaves its results in device memory; rt_bulk_fetch() copies them to the host (pinned
  * memory).  The first rt_bulk_lookup()/rt_bulk_unit_info() call does it implicitly. */
 int  rt_bulk_fetch(rt_bulk *bulk);
+/* The results of rt_bulk_scan() as one relocatable image, copied DEVICE to DEVICE (before rt_bulk_fetch): for a caller that moves
+ * results between GPUs itself -- the result gather of a reel sharded over several GPUs (NCCL), SURVEY 8(e).  Image layout, all
+ * configurations in turn: { u64 nunits, u64 ntrks, UnitDesc[nunits], TrkMeta[nunits*ntrks] } ..., then u64 chunks, u32 chunk_next[chunks]
+ * (padded to 8 bytes), rt_event pool[chunks*32].  rt_bulk_results_size() gives its size in bytes. */
+int  rt_bulk_results_size(const rt_bulk *bulk, uint64_t *bytes);
+int  rt_bulk_results_to_device(const rt_bulk *bulk, void *dst_dev, uint64_t bytes);
 /* rt_bulk_fetch() with the events placed in the CALLER's buffer (RT_ERR_OVERFLOW if it is too small: nothing is fetched then and
  * rt_bulk_fetch() can still be called).  For a caller that wants the results in memory of its own choosing -- e.g. a MAP_SHARED
  * mapping prepared in the background that worker processes forked later can read; rt_host_register() pins such memory for the copy

@@ -542,6 +542,8 @@ int rt_bulk_lookup(rt_bulk *b, uint32_t c, uint64_t r, const rt_event **e, uint6
    return set_err(RT_ERR_UNSUPPORTED, "the oracle only implements the exact scan"); }
 int rt_clear(rt_tape *t) { if (!t) return RT_ERR_ARG; t->nrows = 0; t->cap = 0; return RT_OK; }
 int rt_bulk_fetch(rt_bulk *b) { (void)b; return RT_ERR_UNSUPPORTED; }
+int rt_bulk_results_size(const rt_bulk *b, uint64_t *n) { (void)b; (void)n; return RT_ERR_UNSUPPORTED; }
+int rt_bulk_results_to_device(const rt_bulk *b, void *d, uint64_t n) { (void)b; (void)d; (void)n; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_fetch_to(rt_bulk *b, void *p, size_t n) { (void)b; (void)p; (void)n; return RT_ERR_UNSUPPORTED; }
 int rt_host_register(rt_tape *t, void *p, size_t n) { (void)t; (void)p; (void)n; return RT_OK; }
 int rt_host_unregister(rt_tape *t, void *p) { (void)t; (void)p; return RT_OK; }

@@ -69,7 +69,7 @@ assert EVENT_DTYPE.itemsize == 32
 EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
-           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_fetch_to", "rt_host_register", "rt_host_unregister", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_bulk_tile_digest", "rt_bulk_last_unit", "rt_set_option", "rt_peak_masks", "rt_pkww_width",
+           "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_results_size", "rt_bulk_results_to_device", "rt_bulk_fetch_to", "rt_host_register", "rt_host_unregister", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_bulk_tile_digest", "rt_bulk_last_unit", "rt_set_option", "rt_peak_masks", "rt_pkww_width",
            "rt_row_time"]
 
 
@@ -118,6 +118,8 @@ class Lib:
         L.rt_bulk_unit_info.argtypes = [vp, u32, u64, P(UnitInfo)]
         L.rt_bulk_unit_at.argtypes = [vp, u32, u64, P(UnitInfo)]
         L.rt_bulk_free.argtypes = [vp]; L.rt_bulk_free.restype = None
+        L.rt_bulk_results_size.argtypes = [vp, P(u64)]; L.rt_bulk_results_size.restype = i32
+        L.rt_bulk_results_to_device.argtypes = [vp, vp, u64]; L.rt_bulk_results_to_device.restype = i32
         L.rt_bulk_tile_digest.argtypes = [vp, u32, u64, u64, vp, vp, P(u64)]; L.rt_bulk_tile_digest.restype = i32
         L.rt_peak_masks.argtypes = [vp, P(ScanCfg), C.c_float, vp, vp, u64, P(C.c_int32)]
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
@@ -273,6 +275,15 @@ class Bulk:
         ui = UnitInfo()
         rc = self.lib.check(self.lib.L.rt_bulk_unit_at(self.h, cfg_index, unit_index, C.byref(ui)))
         return None if rc == RT_MISS else self._unit_dict(ui)
+
+    def results_size(self) -> int:
+        n = C.c_uint64(0)
+        self.lib.check(self.lib.L.rt_bulk_results_size(self.h, C.byref(n)))
+        return int(n.value)
+
+    def results_to_device(self, dst_dev_ptr: int, nbytes: int) -> None:
+        """the scan's results (unit tables, proof data, chunk links, events) as one image, device to device (rt_bulk_results_to_device)"""
+        self.lib.check(self.lib.L.rt_bulk_results_to_device(self.h, dst_dev_ptr, nbytes))
 
     def tile_digest(self, cfg_index: int, period_rows: int, ntiles: int):
         """(events[ntiles], digest[ntiles], bad_times): per-tile event counts and order-independent digests, computed on the

@@ -882,6 +882,36 @@ extern "C" int rt_bulk_fetch(rt_bulk *b) {
    b->fetched = true;
    return RT_OK; }
 
+extern "C" int rt_bulk_results_size(const rt_bulk *b, uint64_t *bytes) {
+   if (!b || !bytes) return set_err(RT_ERR_ARG, "rt_bulk_results_size: null argument");
+   const uint32_t nt = b->tape->desc.ntrks;
+   uint64_t n = 0;
+   for (const BulkCfg &bc : b->cfgs) n += 16 + (uint64_t)bc.nunits * (sizeof(UnitDesc) + nt * sizeof(TrkMeta));
+   n += 8 + ((uint64_t)b->chunks_used * 4 + 7) / 8 * 8 + (uint64_t)b->chunks_used * RT_EVC * sizeof(rt_event);
+   *bytes = n; return RT_OK; }
+
+extern "C" int rt_bulk_results_to_device(const rt_bulk *b, void *dst_dev, uint64_t bytes) {
+   uint64_t need = 0;
+   int rc = rt_bulk_results_size(b, &need); if (rc) return rc;
+   if (!dst_dev || bytes < need) return set_err(RT_ERR_ARG, "rt_bulk_results_to_device: buffer too small (%llu < %llu)", (unsigned long long)bytes, (unsigned long long)need);
+   if (b->fetched || (b->chunks_used && !b->d_pool)) return set_err(RT_ERR_STATE, "rt_bulk_results_to_device: the results have left the device");
+   rt_tape *t = b->tape; const uint32_t nt = t->desc.ntrks;
+   CU(cudaSetDevice(t->device));
+   char *p = static_cast<char *>(dst_dev);
+   for (const BulkCfg &bc : b->cfgs) {
+      const uint64_t hdr[2] = {bc.nunits, nt};
+      CU(cudaMemcpyAsync(p, hdr, 16, cudaMemcpyHostToDevice, t->stream)); p += 16;
+      if (bc.nunits) {
+         CU(cudaMemcpyAsync(p, bc.d_units, (size_t)bc.nunits * sizeof(UnitDesc), cudaMemcpyDeviceToDevice, t->stream)); p += (size_t)bc.nunits * sizeof(UnitDesc);
+         CU(cudaMemcpyAsync(p, bc.d_meta, (size_t)bc.nunits * nt * sizeof(TrkMeta), cudaMemcpyDeviceToDevice, t->stream)); p += (size_t)bc.nunits * nt * sizeof(TrkMeta); } }
+   const uint64_t chunks = b->chunks_used;
+   CU(cudaMemcpyAsync(p, &chunks, 8, cudaMemcpyHostToDevice, t->stream)); p += 8;
+   if (chunks) {
+      CU(cudaMemcpyAsync(p, b->d_chunk_next, (size_t)chunks * 4, cudaMemcpyDeviceToDevice, t->stream)); p += ((size_t)chunks * 4 + 7) / 8 * 8;
+      CU(cudaMemcpyAsync(p, b->d_pool, (size_t)chunks * RT_EVC * sizeof(rt_event), cudaMemcpyDeviceToDevice, t->stream)); }
+   CU(cudaStreamSynchronize(t->stream));
+   return RT_OK; }
+
 extern "C" int rt_bulk_fetch_to(rt_bulk *b, void *events_buf, size_t bytes) {
    if (!b || !events_buf) return set_err(RT_ERR_ARG, "rt_bulk_fetch_to: null argument");
    if (b->fetched) return set_err(RT_ERR_STATE, "rt_bulk_fetch_to: already fetched");

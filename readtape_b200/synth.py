@@ -192,3 +192,105 @@ def gcr_header(tstart_ns: int = 1_000_000_000) -> TbinHeader:
     from .tbin import MODE_GCR
     return TbinHeader(descr="synthetic GCR-density flux pattern (readtape_b200.synth)", flags=0, ntrks=9, tdelta_ns=GCR_TDELTA_NS,
                       maxvolts=3.2, mode=MODE_GCR, bpi=9042.0, ips=50.0, tstart_ns=tstart_ns)
+
+
+# ---- decodable 6250 BPI GCR blocks (BASELINE config 4) ---------------------------------------------------------------
+# Block format: reference A_documentation.txt:300-328; what the reference checks: gcr_postprocess (decode_gcr.c:503-674): the
+# 5-bit storage codes (gcr_datamap :428), odd parity of every 9-bit character (:472-480) and the ECC character of every group
+# of 7 data bytes (gcr_compute_ecc :127-144).
+GCR_MARK1, GCR_MARK2, GCR_SYNC = 0b00111, 0b11100, 0b11111
+_GCR_DECODE = [16 + 10, 16 + 9, 16 + 2, 16 + 3, 16 + 5, 16 + 5, 16 + 6, 16 + 7, 16 + 10, 9, 10, 11, 16 + 13, 13, 14, 15,
+               16 + 2, 16 + 5, 2, 3, 16 + 5, 5, 6, 7, 16 + 0, 0, 8, 1, 16 + 12, 4, 12, 16 + 15]          # gcr_datamap, decode_gcr.c:428
+GCR_ENCODE = {v: code for code, v in enumerate(_GCR_DECODE) if v < 16}                                   # 4-bit value -> 5-bit code
+_GCR_ECC_A = [0x0f6a71994c5230, 0x70110840108004, 0x5a701108401080, 0x372be95d5a7011,
+              0xe95d5a70110840, 0x4c523001884412, 0x2be95d5a701108, 0x5d5a7011084010]                  # decode_gcr.c:128-136
+
+
+def gcr_ecc(seven: bytes) -> int:
+    """the ECC character of 7 data bytes: bit i = <dblock, A[i]> mod 2 over the 56-bit big-endian block (decode_gcr.c:137-144)"""
+    d = int.from_bytes(bytes(seven), "big")
+    return sum((bin(d & a).count("1") & 1) << i for i, a in enumerate(_GCR_ECC_A))
+
+
+def _word9(b: int) -> int:
+    """9-bit character (data bits msb..lsb, parity last) with odd parity"""
+    return (b << 1) | ((bin(b).count("1") & 1) ^ 1)
+
+
+def _subgroup_codes(words4) -> list:
+    """the 5-bit storage codes of the 9 tracks for 4 characters (track t carries bit 8-t of every character, decode_gcr.c:454-470)"""
+    out = []
+    for t in range(9):
+        nib = 0
+        for w in words4:
+            nib = (nib << 1) | ((w >> (8 - t)) & 1)
+        out.append(GCR_ENCODE[nib])
+    return out
+
+
+def gcr_block_cells(data: bytes) -> np.ndarray:
+    """flux cells of one block, bool (ncells, 9): preamble, Mark 1, data groups (7 bytes + ECC -> two 5-bit subgroups per track)
+    with a resync burst after every 158 storage groups, End Mark, residual and CRC groups (no residual bytes), Mark 2, postamble.
+    len(data) must be a multiple of 7."""
+    assert len(data) % 7 == 0
+    same = lambda code: [code] * 9
+    sg = [same(0b10101), same(0b01111)] + [same(GCR_SYNC)] * 14 + [same(GCR_MARK1)]
+    ngroups = 0
+    for at in range(0, len(data), 7):
+        seven = data[at:at + 7]
+        words = [_word9(b) for b in seven] + [_word9(gcr_ecc(seven))]
+        sg.append(_subgroup_codes(words[:4])); sg.append(_subgroup_codes(words[4:]))
+        ngroups += 1
+        if ngroups % 158 == 0 and at + 7 < len(data):
+            sg += [same(GCR_MARK2), same(GCR_SYNC), same(GCR_SYNC), same(GCR_MARK1)]
+    zero4 = _subgroup_codes([_word9(0)] * 4)
+    sg += [same(GCR_SYNC), zero4, zero4, zero4, zero4, same(GCR_MARK2)]
+    sg += [same(GCR_SYNC)] * 14 + [same(0b11110), same(0b10101)]
+    codes = np.array(sg, dtype=np.uint8)                                   # (nsubgroups, 9)
+    cells = ((codes[:, None, :] >> np.arange(4, -1, -1)[None, :, None]) & 1).astype(bool)
+    return cells.reshape(-1, 9)
+
+
+def gcr_tile(seed: int = 0xC0FFEE, nblocks: int = 8, data_bytes: int = 4095, gap_rows: int = 37_500, noise_mv: float = 4.0,
+             amplitude: float = 1.9) -> np.ndarray:
+    """A tape tile of decodable 6250 BPI GCR blocks (9042 flux cells per inch, 50 IPS, 6.25 MHz sampling, maxvolts 3.2): NRZI flux,
+    i.e. the read signal of the reference's GCR captures (decoded with -zeros) -- a level that changes sign at every 1 cell,
+    band-limited to about a cell -- so that zero crossings mark the 1 cells.  `data_bytes` random bytes per block (a multiple of 7),
+    0.3-inch gaps; the tile is a whole number of ingest tiles long and can be repeated seamlessly."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    per_block = None
+    blocks = []
+    for _ in range(nblocks):
+        cells = gcr_block_cells(rng.integers(0, 256, size=data_bytes, dtype=np.uint8).tobytes())
+        blocks.append(cells)
+        per_block = cells.shape[0]
+    period = int(per_block * GCR_ROWS_PER_BIT) + gap_rows
+    period = (period + 2047) // 2048 * 2048
+    nrows = period * nblocks
+    volts = np.zeros((9, nrows), dtype=np.float64)
+    kern_half = int(GCR_ROWS_PER_BIT)                                      # raised-cosine smoothing over ~2 cells
+    k = np.arange(-kern_half, kern_half + 1)
+    kern = 0.5 * (1.0 + np.cos(np.pi * k / (kern_half + 1))); kern /= kern.sum()
+    for b, cells in enumerate(blocks):
+        start = b * period + gap_rows // 2
+        n = cells.shape[0]
+        edges = start + np.arange(n + 1) * GCR_ROWS_PER_BIT
+        for trk in range(9):
+            level = np.zeros(period, dtype=np.float64)
+            ones = np.flatnonzero(cells[:, trk])
+            t = edges[ones] + 0.5 * GCR_ROWS_PER_BIT + 0.37 * trk - b * period          # the flux reversal sits in the middle of its cell
+            sign = 1.0
+            # the level is 0 in the gap, rises with the first reversal and returns to 0 behind the last one
+            pos = np.round(t).astype(np.int64)
+            for i in range(len(pos)):
+                hi = pos[i + 1] if i + 1 < len(pos) else min(period, pos[i] + int(1.5 * GCR_ROWS_PER_BIT))
+                level[pos[i]:hi] = sign
+                sign = -sign
+            first = pos[0]
+            level[max(0, first - int(1.5 * GCR_ROWS_PER_BIT)):first] = -1.0                # so that the first reversal is a crossing
+            smooth = np.convolve(level, kern, mode="same") * (amplitude + 0.03 * trk)
+            volts[trk, b * period:(b + 1) * period] += smooth
+    volts += rng.normal(0.0, noise_mv * 1e-3, size=volts.shape)
+    q = np.rint(volts / 3.2 * 32767.0)
+    np.clip(q, -32767, 32767, out=q)
+    return np.ascontiguousarray(q.T.astype("<i2"))

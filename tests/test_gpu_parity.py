@@ -393,3 +393,40 @@ def test_tile_digest_at_scale_equals_oracle(cuda_lib, oracle_lib):
     rep2 = verify.verify_periodic(oracle_lib, bulk, desc, cfg, tile, nrows)
     bulk.free(); tape.close()
     assert not rep2["ok"] and rep2["first_differing_tile"] == 3, rep2
+
+
+def test_decodable_gcr_tape_cuda_equals_oracle_and_digest(cuda_lib, oracle_lib):
+    """BASELINE config 4's generator (synth.gcr_tile: decodable 6250 BPI GCR blocks, zero-crossing detector): the whole-tape scan of all 5
+    GCR parameter sets in one call; every unit equals the oracle's exact scan for two of them, and the tile digest check holds"""
+    from readtape_b200 import parmsets, synth, tbin, verify
+    tile = synth.gcr_tile(nblocks=3)
+    hdr = synth.gcr_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfgs = [abi.make_cfg(tbin.MODE_GCR, p, hdr.bpi, hdr.ips, flags=abi.RT_F_FIND_ZEROS) for p in parmsets.GCR]
+    tg, to = cuda_lib.open(desc), oracle_lib.open(desc)
+    rows = np.concatenate([tile] * 3)
+    tg.upload(rows); to.upload(rows)
+    bulk = tg.bulk_scan(cfgs)
+    st = bulk.stats()
+    assert st.track_samples == tg.nrows * 9 * 5 and st.events > 5 * 9 * 9 * 5000
+    for ci in (0, 3):
+        sc = to.scan(cfgs[ci])
+        i = 0
+        while True:
+            ui = bulk.unit_at(ci, i)
+            if ui is None:
+                break
+            r = bulk.lookup(ci, ui["row0"])
+            assert r is not None
+            ev, valid = r
+            sc.reset(abi.RT_RESET_FULL, ui["row0"])
+            want, _ = sc.run(valid)
+            assert evlog.to_canon(ev).tobytes() == evlog.to_canon(want).tobytes(), f"parameter set {ci} unit {i}"
+            i += 1
+        sc.end()
+        assert i >= 9
+    bulk.free()
+    bulk = tg.bulk_scan(cfgs[:1])
+    rep = verify.verify_periodic(oracle_lib, bulk, desc, cfgs[0], tile, tg.nrows)
+    bulk.free(); tg.close(); to.close()
+    assert rep["ok"], rep

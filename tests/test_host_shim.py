@@ -243,3 +243,59 @@ def test_readtape_b200_split_between_worker_processes_equals_reference(tmp_path)
                 assert workers == nw and not unsplit, r.stdout[-1500:]
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def _gcr_reel(d, nblocks=6):
+    from readtape_b200 import synth, tbin
+    path = os.path.join(d, "gcr.tbin")
+    tbin.write_tbin(path, synth.gcr_header(), synth.gcr_tile(nblocks=nblocks))
+    return path
+
+
+def test_reference_decodes_the_synthetic_gcr_blocks(tmp_path):
+    """BASELINE config 4 asks for synthetic GCR blocks the reference's gcr_postprocess validates: the unmodified reference must decode
+    synth.gcr_tile() without errors or warnings and return exactly the generated bytes"""
+    import numpy as np
+    ref = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+    if not os.path.exists(ref):
+        pytest.skip("reference binary not built")
+    path = _gcr_reel(str(tmp_path))
+    r = subprocess.run([ref, "-v", "-nm", "-gcr", "-ips=50", "-zeros", "-tap", "-nolabels", f"-outf={tmp_path}/ref", path], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 blocks had errors, 0 had warnings" in r.stdout, r.stdout[-1500:]
+    tap = open(f"{tmp_path}/ref.tap", "rb").read()
+    rng = np.random.Generator(np.random.PCG64(0xC0FFEE))
+    off = 0
+    for _ in range(6):
+        want = rng.integers(0, 256, size=4095, dtype=np.uint8).tobytes()
+        n = int.from_bytes(tap[off:off + 4], "little")
+        assert n == 4095 and tap[off + 4:off + 4 + n] == want
+        off += 4 + n + (n & 1) + 4
+    assert tap[off:] == b"\xff" * 4
+
+
+def test_shim_on_oracle_backend_decodes_the_synthetic_gcr_blocks(tmp_path):
+    ref = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+    if not (os.path.exists(ref) and os.path.exists(ORACLE_SHIM)):
+        pytest.skip("binaries not built")
+    path = _gcr_reel(str(tmp_path), nblocks=3)
+    for exe, tag in ((ref, "ref"), (ORACLE_SHIM, "new")):
+        r = subprocess.run([exe, "-q", "-m", "-gcr", "-ips=50", "-zeros", "-tap", "-nolabels", "-nolog", f"-outf={tmp_path}/{tag}", path], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:]
+    assert open(f"{tmp_path}/new.tap", "rb").read() == open(f"{tmp_path}/ref.tap", "rb").read()
+
+
+@pytest.mark.gpu
+def test_readtape_b200_decodes_the_synthetic_gcr_blocks(tmp_path):
+    ref = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+    if not (os.path.exists(ref) and os.path.exists(CUDA_SHIM)):
+        pytest.skip("binaries not built")
+    path = _gcr_reel(str(tmp_path), nblocks=8)
+    for exe, tag in ((ref, "ref"), (CUDA_SHIM, "new")):
+        r = subprocess.run([exe, "-q", "-m", "-gcr", "-ips=50", "-zeros", "-tap", "-nolabels", "-nolog", f"-outf={tmp_path}/{tag}", path], capture_output=True, text=True,
+                           env=dict(os.environ, RT_STATS="1"))
+        assert r.returncode == 0, r.stdout[-1500:]
+        if tag == "new":
+            st = shim_stats(r.stdout)
+            record_stats("synthetic_gcr_8_blocks", st)
+            assert st["misses"] == 0 and st["hits"] >= 8, st
+    assert open(f"{tmp_path}/new.tap", "rb").read() == open(f"{tmp_path}/ref.tap", "rb").read()
