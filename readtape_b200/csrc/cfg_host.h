@@ -40,10 +40,9 @@ inline void to_dev(const rt_tape_desc &desc, const int16_t *planes, uint64_t pla
    d->width = pkww_width(cfg, desc.tdelta_ns);
    volatile float bid = bi * sd;
    d->samples_per_bit = cfg->bpi > 0 ? (int)(1 / bid) : 20;                  /* readtape.c:1402 */
-   {  double rpb = cfg->bpi > 0 && cfg->ips > 0 ? 1.0 / ((double)cfg->bpi * cfg->ips * (double)sd) : 20.0;
-      double want = 200e-6 / (double)sd + 24.0 * rpb;                       /* *_IBG_SECS (decoder.h:105,113,116) + 24 bit times */
-      int pr = want > RT_PRESCAN_MAX ? RT_PRESCAN_MAX : (int)want;
-      d->prescan_rows = (pr < RT_PRESCAN_MIN ? RT_PRESCAN_MIN : pr) / 32 * 32; }
+   /* rows in front of a unit examined for quietness.  Measured: a longer pre-scan (an inter-block-gap time) costs every job of the
+      whole-tape scan ~5 % and serves a handful of block starts per reel; those are proven by a bridge scan instead (rt_api.cu) */
+   d->prescan_rows = RT_PRESCAN_MIN;
    d->p = cfg->parms;
    for (int k = 0; k < RT_MAXTRKS; ++k) d->skew[k] = cfg->skew_delaycnt[k]; }
 
