@@ -702,6 +702,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_masks = float(np.mean([s.ms_masks for s in stats]))
+        ms_records = float(np.mean([s.ms_records for s in stats]))
         force = os.environ.get("RT_SCAN")
         two_pass = ms_masks > 0
         alg_bytes = 2.0 * tsamp + 32.0 * events                # 2 B read per track-sample + event bytes
@@ -711,7 +712,13 @@ def main():
         kernels = {"k_ingest_tma": (ms_ingest, ingest_bytes)}
         if two_pass:
             kernels["k_peak_masks"] = (ms_masks, 2.375 * tsamp)
-            kernels["k_units_sparse"] = (ms_scan - ms_masks, 0.375 * tsamp + 32.0 * events)
+            if ms_records > 0:
+                # phase B1 reads the candidate plane and, per candidate, its window, and writes a 24-byte record; phase B2 reads the
+                # records and writes the events (the candidate count is ~2 per event; counted as 2 here)
+                kernels["k_cand_records"] = (ms_records, 0.125 * tsamp + 2 * events * (26.0 + 24.0))
+                kernels["k_units_sparse"] = (ms_scan - ms_masks - ms_records, 2 * events * 24.0 + 32.0 * events)
+            else:
+                kernels["k_units_sparse"] = (ms_scan - ms_masks, 0.375 * tsamp + 32.0 * events)
         else:
             kernels["k_units_scan (generic)" if force == "generic" else "k_units_fast"] = (ms_scan, alg_bytes)
         scan_kernel = max((k for k in kernels if k != "k_ingest_tma"), key=lambda k: kernels[k][0])

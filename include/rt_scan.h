@@ -258,6 +258,7 @@ typedef struct rt_bulk_stats {
    uint32_t pad;             /* rt_bulk_scan_host: number of segments streamed, 0 = plain sequence    */
    uint64_t d2h_bytes;       /* bytes rt_bulk_fetch() copied to the host                     */
    double   ms_masks;        /* device time: candidate-mask pass of the two-pass peak scan (a part of ms_scan; 0 if not used) */
+   double   ms_records;      /* device time: candidate-record pass (phase B1) of the two-pass peak scan (a part of ms_scan; 0 if not used) */
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);
 

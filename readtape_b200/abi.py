@@ -49,7 +49,8 @@ class BulkStats(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("units", C.c_uint64), ("events", C.c_uint64),
                 ("rows_scanned", C.c_uint64), ("track_samples", C.c_uint64),
                 ("ms_preprocess", C.c_double), ("ms_units", C.c_double), ("ms_scan", C.c_double),
-                ("launches", C.c_uint32), ("pad", C.c_uint32), ("d2h_bytes", C.c_uint64), ("ms_masks", C.c_double)]
+                ("launches", C.c_uint32), ("pad", C.c_uint32), ("d2h_bytes", C.c_uint64), ("ms_masks", C.c_double),
+                ("ms_records", C.c_double)]
 
 
 class UnitInfo(C.Structure):

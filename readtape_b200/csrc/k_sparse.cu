@@ -76,6 +76,60 @@ int peak_mask_T0(const DevCfg &c, float frac) {
    const int T0 = (int)((float)T * frac);
    return T0 < 16 ? 0 : (T0 > 65535 ? 65535 : T0); }
 
+/* ---- phase B1: the candidate records (scan_records.cuh) ---------------------------------------------------------------------
+ * One warp per (track, 2048-row tile): lane l owns mask words 2l and 2l+1 of the tile.  The tile's records are placed in the pool
+ * by ONE atomic add (their order across tiles does not matter, rec_tile_base finds them); inside the tile a warp prefix sum over
+ * the lanes' candidate counts keeps them in row order.  Each lane then builds the records of its own candidates. */
+#define REC_WARPS 4
+__global__ void __launch_bounds__(32 * REC_WARPS)
+k_cand_records(const int16_t *planes, uint64_t plane_stride, const uint32_t *cand, const uint32_t *acan, uint64_t mask_stride, int w,
+               const __grid_constant__ TrackT0 t0s, uint32_t tile_lo, uint32_t ntiles, uint64_t rec_tiles, uint64_t nrows, CandRec *recs, uint32_t rec_cap,
+               uint32_t *tile_base, uint32_t *tile_cnt, unsigned int *cursor) {
+   const uint32_t tl = blockIdx.x * REC_WARPS + (threadIdx.x >> 5);
+   if (tl >= ntiles) return;
+   const uint32_t tile = tile_lo + tl;
+   const int trk = blockIdx.y, lane = threadIdx.x & 31;
+   const int16_t *plane = planes + (size_t)trk * plane_stride;
+   const uint32_t *mc = cand + (size_t)trk * mask_stride, *ma = acan + (size_t)trk * mask_stride;
+   const uint64_t w0 = (uint64_t)tile * (RT_REC_TILE / 32) + 2u * (uint32_t)lane;
+   const uint64_t nwords = (nrows + 31) / 32;
+   uint32_t c0 = w0 < nwords ? mc[w0] : 0u, c1 = w0 + 1 < nwords ? mc[w0 + 1] : 0u;
+   if (w0 * 32 + 31 >= nrows) c0 &= w0 * 32 < nrows ? (0xffffffffu >> (31 - (int)((nrows - 1) & 31))) : 0u;       /* rows past the data */
+   if ((w0 + 1) * 32 + 31 >= nrows) c1 &= (w0 + 1) * 32 < nrows ? (0xffffffffu >> (31 - (int)((nrows - 1) & 31))) : 0u;
+   const uint32_t n = (uint32_t)__popc(c0) + (uint32_t)__popc(c1);
+   uint32_t incl = n;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+   uint32_t base = 0;
+   if (lane == 0 && total) base = atomicAdd(cursor, total);
+   base = __shfl_sync(0xffffffffu, base, 0);
+   if (lane == 0) {
+      const bool fits = (uint64_t)base + total <= rec_cap;
+      tile_base[(size_t)trk * rec_tiles + tile] = base;
+      tile_cnt[(size_t)trk * rec_tiles + tile] = fits ? total : 0u; }     /* on overflow the host regrows the pool and reruns */
+   if ((uint64_t)base + total > rec_cap) return;
+   uint32_t at = base + incl - n;
+   const int T0 = t0s.v[trk];
+   for (int half = 0; half < 2; ++half) {
+      uint32_t bits = half ? c1 : c0;
+      while (bits) {
+         const int b = __ffs((int)bits) - 1; bits &= bits - 1;
+         recs[at++] = rtrec::make_record(plane, ma, w, T0, (w0 + (uint64_t)half) * 32 + (uint64_t)b); } } }
+
+cudaError_t launch_cand_records(const DevCfg &c, uint64_t row_lo, uint64_t row_hi, CandRec *recs, uint32_t rec_cap, uint32_t *tile_base, uint32_t *tile_cnt,
+                                unsigned int *cursor, cudaStream_t s) {
+   if (row_hi <= row_lo) return cudaSuccess;
+   const uint32_t tile_lo = (uint32_t)(row_lo / RT_REC_TILE), tile_hi = (uint32_t)((row_hi + RT_REC_TILE - 1) / RT_REC_TILE);
+   const uint32_t ntiles = tile_hi - tile_lo;
+   TrackT0 t0s;
+   for (int k = 0; k < RT_MAXTRKS; ++k) t0s.v[k] = c.T0[k] > 0 ? c.T0[k] : 65535;
+   dim3 grid((ntiles + REC_WARPS - 1) / REC_WARPS, (unsigned)c.ntrks);
+   k_cand_records<<<grid, 32 * REC_WARPS, 0, s>>>(c.planes, c.plane_stride, c.m_cand, c.m_acan, c.mask_stride, c.width, t0s, tile_lo, ntiles, c.rec_tiles, row_hi,
+                                                  recs, rec_cap, tile_base, tile_cnt, cursor);
+   return cudaGetLastError(); }
+uint64_t cand_rec_tiles(uint64_t plane_stride) { return plane_stride / RT_REC_TILE + 2; }
+
 struct SparseJobs {
    const DevCfg &c; const UnitDesc *units; TrkMeta *meta; rt_event *pool; uint32_t *chunk_next; unsigned int *cursor; uint32_t cap_chunks;
    int quiet_thr_lsb; unsigned long long *counters /* [0] rows, [1] events, [2] next job group */; uint64_t total; uint64_t cur; bool exhausted;
@@ -110,7 +164,7 @@ struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0x
 
 /* MINB = CTAs per SM the register allocation aims at (the lane state is large: 4 -> 128 registers, 6 -> 80 with some cold
    state spilled); which one is faster is a latency-hiding question, decided by measurement (RT_SPARSE_OCC) */
-template <int MINB>
+template <int MINB, bool REC>
 __global__ void __launch_bounds__(SPARSE_THREADS, MINB)
 k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
                rt_event *pool, uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks,
@@ -118,7 +172,7 @@ k_units_sparse(DevCfg c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta,
    __shared__ uint32_t heights[RT_AGC_MAX_WINDOW * SPARSE_THREADS];      /* v_heights[] of every lane, [entry][thread] */
    const uint64_t total = (uint64_t)nunits * (uint64_t)c.ntrks;
    SparseJobs jobs{c, units, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters, total, 0, false};
-   SparseScan<SPARSE_THREADS, PoolEmit> us(c, heights + threadIdx.x);
+   SparseScan<SPARSE_THREADS, PoolEmit, REC> us(c, heights + threadIdx.x);
    drive_sparse(us, jobs, WarpAny()); }
 
 bool sparse_scan_eligible(const DevCfg &c) {
@@ -196,19 +250,13 @@ bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist) {
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s) {
-   int occ = 0, per_sm_cached = 0;                                  /* per launch: the occupancy belongs to the device of the launch */
+   int per_sm = 0;                                                  /* per launch: the occupancy belongs to the device of the launch */
    cudaError_t e;
-   {
-      const char *env = getenv("RT_SPARSE_OCC");
-      occ = env ? atoi(env) : 4;
-      if (occ != 5 && occ != 6 && occ != 8) occ = 4;
-      e = occ == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<4>, SPARSE_THREADS, 0)
-        : occ == 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<5>, SPARSE_THREADS, 0)
-        : occ == 6 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<6>, SPARSE_THREADS, 0)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_units_sparse<8>, SPARSE_THREADS, 0);
-      if (e != cudaSuccess) { occ = 0; return e; }
-      if (per_sm_cached < 1) per_sm_cached = 1; }
-   int per_sm = per_sm_cached;
+   const bool rec = c.recs != nullptr;
+   e = rec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_units_sparse<4, true>, SPARSE_THREADS, 0)
+           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_units_sparse<4, false>, SPARSE_THREADS, 0);
+   if (e != cudaSuccess) return e;
+   if (per_sm < 1) per_sm = 1;
    if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
    const uint64_t jobs = (uint64_t)nunits * (uint64_t)c.ntrks;
    uint64_t grid = (jobs + SPARSE_THREADS - 1) / SPARSE_THREADS;
@@ -216,8 +264,6 @@ cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t
    if (grid < 1) grid = 1;
    e = cudaMemsetAsync(counters + 2, 0, sizeof(unsigned long long), s);
    if (e != cudaSuccess) return e;
-   if (occ == 4) k_units_sparse<4><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
-   else if (occ == 5) k_units_sparse<5><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
-   else if (occ == 6) k_units_sparse<6><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
-   else k_units_sparse<8><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   if (rec) k_units_sparse<4, true><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
+   else k_units_sparse<4, false><<<(unsigned)grid, SPARSE_THREADS, 0, s>>>(c, units, nunits, meta, pool, chunk_next, cursor, cap_chunks, quiet_thr_lsb, counters);
    return cudaGetLastError(); }

@@ -47,6 +47,11 @@ uint32_t span_hist_words(int ntrks);
 cudaError_t launch_span_hist(const uint32_t *gmm, uint64_t ngran_cap, uint64_t nrows, int ntrks, uint32_t *d_hist, cudaStream_t s);
 bool peak_mask_auto_T0(DevCfg &c, const uint32_t *hist);
 cudaError_t launch_peak_masks(const DevCfg &c, uint64_t row_lo, uint64_t row_hi, cudaStream_t s);
+/* phase B1 (scan_records.cuh): the candidate records of plane rows [row_lo, row_hi) (whole 2048-row tiles) */
+struct CandRec;
+uint64_t cand_rec_tiles(uint64_t plane_stride);
+cudaError_t launch_cand_records(const DevCfg &c, uint64_t row_lo, uint64_t row_hi, CandRec *recs, uint32_t rec_cap, uint32_t *tile_base, uint32_t *tile_cnt,
+                                unsigned int *cursor, cudaStream_t s);
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s);

@@ -20,6 +20,7 @@
 #include <vector>
 #include <chrono>
 #include "scan_generic.cuh"
+#include "scan_records.cuh"
 #include "kernels.h"
 #include "cfg_host.h"
 
@@ -76,6 +77,8 @@ struct rt_tape {
    std::vector<cudaStream_t> s_par;                               /* rt_bulk_scan with several configurations: their kernels run side by side */
    cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[2] = {nullptr, nullptr};
    uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
+   /* phase B1: candidate records (scan_records.cuh), grow-only like the event pool; one pool shared by the mask sets of a scan */
+   CandRec *rec_cache = nullptr; uint32_t rec_cache_cap = 0; uint32_t rec_hist = 0;
    int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
 };
 
@@ -350,6 +353,7 @@ extern "C" void rt_close(rt_tape *t) {
    if (t->stream) cudaStreamSynchronize(t->stream);
    cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
    cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
+   cudaFree(t->rec_cache);
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
    if (t->h_ring) { cudaFreeHost(t->h_ring); for (auto e : t->ring_done) if (e) cudaEventDestroy(e); }
    if (t->s_copy) cudaStreamDestroy(t->s_copy);
@@ -700,17 +704,25 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    uint32_t *d_bitmap = nullptr, *d_flags = nullptr, *d_blockcount = nullptr, *d_nunits = nullptr; UnitDesc *d_units_tmp = nullptr;
    unsigned long long *d_counters = nullptr; unsigned int *d_cursor = nullptr;
    cudaEvent_t ev[5]; for (auto &e : ev) cudaEventCreate(&e);
+   cudaEvent_t ev_rec = nullptr; cudaEventCreate(&ev_rec);
    std::vector<cudaEvent_t> done_ev(ncfgs, nullptr);
    /* K3c: candidate / canonical bit planes, one set per distinct (window width, T0) -- parameter sets that only differ in
       clock / AGC constants share them */
-   struct MaskSet { int width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; uint32_t *mc, *md, *ma; uint32_t first_cfg; };
+   struct MaskSet { int width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; uint32_t *mc, *md, *ma; uint32_t first_cfg; uint32_t *tb, *tc; };
+   unsigned int *d_rec_cursor = nullptr;                            /* phase B1: records of all mask sets share one pool and one cursor */
+   const char *recenv = getenv("RT_SPARSE_RECORDS");
+   bool use_records = !(recenv && recenv[0] == '0');
+   const uint64_t rec_tiles = cand_rec_tiles(t->plane_stride);
    uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have_hist = false;
    std::vector<MaskSet> msets;
    auto cleanup = [&]() {
       void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_hist};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
-      for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.md) cudaFreeAsync(m.md, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream); }
+      for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.md) cudaFreeAsync(m.md, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream);
+                              if (m.tb) cudaFreeAsync(m.tb, t->stream); if (m.tc) cudaFreeAsync(m.tc, t->stream); }
+      if (d_rec_cursor) cudaFreeAsync(d_rec_cursor, t->stream);
       for (auto &e : ev) cudaEventDestroy(e);
+      if (ev_rec) cudaEventDestroy(ev_rec);
       for (auto e : done_ev) if (e) cudaEventDestroy(e); };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); rt_bulk_free(b); \
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
@@ -761,7 +773,10 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
             msets.push_back(m);
             CUB(cudaMallocAsync(&msets[k].mc, (size_t)mstride * nt * 4, t->stream));
             CUB(cudaMallocAsync(&msets[k].md, (size_t)mstride * nt * 4, t->stream));
-            CUB(cudaMallocAsync(&msets[k].ma, (size_t)mstride * nt * 4, t->stream)); }
+            CUB(cudaMallocAsync(&msets[k].ma, (size_t)mstride * nt * 4, t->stream));
+            if (use_records) {
+               CUB(cudaMallocAsync(&msets[k].tb, (size_t)rec_tiles * nt * 4, t->stream));
+               CUB(cudaMallocAsync(&msets[k].tc, (size_t)rec_tiles * nt * 4, t->stream)); } }
          pl.dc.m_cand = msets[k].mc; pl.dc.m_cand2 = msets[k].md; pl.dc.m_acan = msets[k].ma; pl.dc.mask_stride = mstride; } }
    lap("mask thresholds");
 
@@ -771,7 +786,19 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          per ~40, half of a reel is gap) plus one partly filled chunk per (unit, track); an overflow costs one regrowth + rescan, after
          which the tape's cached pool fits */
       uint64_t want_chunks = std::max<uint64_t>(4096, (uint64_t)ncfgs * (nrows * nt / 64 / RT_EVC) + total_units * nt);
+      /* phase B1's record pool: what the last scan of this tape needed, else one record per 28 track-samples per mask set */
+      uint64_t want_recs = 0;
+      if (use_records && !msets.empty()) {
+         want_recs = t->rec_hist ? (uint64_t)t->rec_hist + t->rec_hist / 16 + 4096 : (uint64_t)msets.size() * (nrows * nt / 28) + 65536;
+         if (!d_rec_cursor) CUB(cudaMallocAsync(&d_rec_cursor, 4, t->stream)); }
+      bool recs_stale = true;
       for (int attempt = 0; attempt < 3; ++attempt) {
+         if (use_records && !msets.empty() && want_recs > t->rec_cache_cap) {
+            if (want_recs > 0xfffffff0ull) use_records = false;
+            else {
+               cudaFree(t->rec_cache); t->rec_cache = nullptr; t->rec_cache_cap = 0;
+               if (cudaMalloc(&t->rec_cache, (size_t)want_recs * sizeof(CandRec)) != cudaSuccess) { cudaGetLastError(); use_records = false; }
+               else { t->rec_cache_cap = (uint32_t)want_recs; recs_stale = true; } } }
          if (want_chunks > b->pool_chunks) {
             if (want_chunks > 0xfffffff0ull) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool too large"); }
             if (b->pool_from_cache || (!b->d_pool && !t->pool_cache_busy)) {          /* use / grow the tape's cached pool */
@@ -793,6 +820,19 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          if (attempt == 0) {                                      /* phase A of the two-pass scan: once per mask set */
             for (auto &m : msets) { CUB(launch_peak_masks(plans[m.first_cfg].dc, 0, nrows, t->stream)); ++t->launches; } }
          CUB(cudaEventRecord(ev[4], t->stream));
+         if (use_records && !msets.empty() && recs_stale) {       /* phase B1: the candidate records of every mask set */
+            CUB(cudaMemsetAsync(d_rec_cursor, 0, 4, t->stream));
+            for (auto &m : msets) {
+               DevCfg dcm = plans[m.first_cfg].dc; dcm.rec_tiles = rec_tiles;
+               CUB(launch_cand_records(dcm, 0, nrows, t->rec_cache, t->rec_cache_cap, m.tb, m.tc, d_rec_cursor, t->stream)); ++t->launches; }
+            recs_stale = false; }
+         for (uint32_t ci = 0; ci < ncfgs; ++ci) {                 /* hand the records to the configurations of each mask set */
+            ScanPlan &pl = plans[ci];
+            pl.dc.recs = nullptr;
+            if (!use_records || !pl.use_sparse) continue;
+            for (auto &m : msets)
+               if (m.mc == pl.dc.m_cand) { pl.dc.recs = t->rec_cache; pl.dc.rec_tile_base = m.tb; pl.dc.rec_tile_cnt = m.tc; pl.dc.rec_tiles = rec_tiles; } }
+         CUB(cudaEventRecord(ev_rec, t->stream));
          for (uint32_t ci = 0; ci < ncfgs; ++ci) {
             BulkCfg &bc = b->cfgs[ci];
             if (!bc.nunits) continue;
@@ -804,14 +844,20 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
                if (!done_ev[ci]) CUB(cudaEventCreateWithFlags(&done_ev[ci], cudaEventDisableTiming));
                CUB(cudaEventRecord(done_ev[ci], st)); CUB(cudaStreamWaitEvent(t->stream, done_ev[ci], 0)); } }
          CUB(cudaEventRecord(ev[3], t->stream));
-         unsigned int used = 0;
+         unsigned int used = 0, used_recs = 0;
          CUB(cudaMemcpyAsync(&used, d_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
+         if (use_records && !msets.empty()) CUB(cudaMemcpyAsync(&used_recs, d_rec_cursor, 4, cudaMemcpyDeviceToHost, t->stream));
          CUB(cudaStreamSynchronize(t->stream));
          float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); b->stats.ms_scan = attempt == 0 ? ms : b->stats.ms_scan + ms;
-         if (attempt == 0 && !msets.empty()) { cudaEventElapsedTime(&ms, ev[2], ev[4]); b->stats.ms_masks = ms; }
+         if (attempt == 0 && !msets.empty()) { cudaEventElapsedTime(&ms, ev[2], ev[4]); b->stats.ms_masks = ms;
+                                               cudaEventElapsedTime(&ms, ev[4], ev_rec); b->stats.ms_records = ms; }
          lap("scan kernel(s) + sync");
-         if (used <= b->pool_chunks) { b->chunks_used = used; break; }
-         want_chunks = (uint64_t)used + used / 8 + 1024;
+         bool again = false;
+         if (use_records && !msets.empty()) {
+            t->rec_hist = used_recs;
+            if (used_recs > t->rec_cache_cap) { want_recs = (uint64_t)used_recs + used_recs / 16 + 4096; again = true; } }   /* some tiles had no room: redo */
+         if (used > b->pool_chunks) { want_chunks = (uint64_t)used + used / 8 + 1024; again = true; }
+         if (!again) { b->chunks_used = used; break; }
          if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
       std::vector<unsigned long long> counters(4 * (size_t)ncfgs, 0);
       CUB(cudaMemcpy(counters.data(), d_counters, 32 * (size_t)ncfgs, cudaMemcpyDeviceToHost));

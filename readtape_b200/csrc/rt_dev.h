@@ -72,6 +72,11 @@ struct DevCfg {
       where the previous one ended plus its inter-block skip, which on real tapes lies up to an inter-block-gap time in front of
       the first all-quiet granule the unit finder cuts at (decaying noise behind a block) */
    int32_t  prescan_rows;
+   /* K3c phase B1 (scan_records.cuh): one record per candidate row of the T0 plane; records of track k, tile t (2048 plane rows) are
+      recs[rec_tile_base[k * rec_tiles + t] ...], rec_tile_cnt[...] of them, in row order.  Null: the sparse scan reads the planes. */
+   const struct CandRec *recs;
+   const uint32_t *rec_tile_base, *rec_tile_cnt;
+   uint64_t rec_tiles;
 };
 
 /* Per-track detector + feedback state: the device mirror of the parts of struct trkstate_t

@@ -31,6 +31,7 @@
 #pragma once
 #include "scan_fast.cuh"
 #include "scan_masks.cuh"
+#include "scan_records.cuh"
 
 namespace rtsparse {
 
@@ -80,7 +81,8 @@ RT_FHD int clz32(uint32_t v) {
 #endif
 }
 
-template <int STRIDE, class Emit>
+/* REC: the candidate rows come as records (scan_records.cuh, phase B1) instead of being derived from the bit planes and the samples */
+template <int STRIDE, class Emit, bool REC = false>
 struct SparseScan {
    const DevCfg &c; const int16_t *plane; const uint32_t *mc, *mc_lo, *mc_hi, *ma; const uint32_t *gm;
    uint64_t row0; uint32_t end; int trk, w, delay; uint32_t io, o_pure;
@@ -90,6 +92,8 @@ struct SparseScan {
    uint32_t o, resume, mq; int m, T, T0t, T1t, st; float inv_lsb, rise, reqmin;
    uint32_t ndense;                                             /* rows walked in dense mode (diagnostics) */
    uint64_t cb; uint32_t cb_o;                                  /* the 64 candidate bits of rows [cb_o, cb_o + 64) (cb_o = NO_ROW32: none held) */
+   /* record mode: the cursor -- tile, index inside it, the tile's place in the record pool */
+   const CandRec *recs; const uint32_t *tbase, *tcnt; uint32_t rt_tile, rt_idx, rt_cnt, rt_base, rt_last;
    /* proof data (offsets relative to row0; OFF_NONE = none), as in UnitScan */
    bool pre; uint32_t pre_pos, pre_end;                         /* pre_end: the row of the first event once it is known */
    int qmin, qmax, qthr, qL; int32_t ll, last_canon;
@@ -108,8 +112,9 @@ struct SparseScan {
       float q = rise * inv_lsb * 0.999f - 2.0f;
       T = !(q > 0) ? 0 : (q > 70000.0f ? 70000 : (int)q);
       /* follow the candidate plane with the highest threshold that T still covers */
-      const uint32_t *want = T1t > 0 && T >= T1t ? mc_hi : mc_lo;
-      if (want != mc) { mc = want; cb_o = NO_ROW32; } }
+      if (!REC) {
+         const uint32_t *want = T1t > 0 && T >= T1t ? mc_hi : mc_lo;
+         if (want != mc) { mc = want; cb_o = NO_ROW32; } } }
 
    /* ---- proof data: identical bookkeeping to UnitScan (scan_fast.cuh) ---- */
    RT_FHD void commit() {
@@ -249,6 +254,10 @@ struct SparseScan {
       mc_lo = c.m_cand + (size_t)trk_ * c.mask_stride; mc_hi = c.m_cand2 + (size_t)trk_ * c.mask_stride; mc = mc_lo;
       ma = c.m_acan + (size_t)trk_ * c.mask_stride; T1t = c.T1[trk_]; cb = 0; cb_o = NO_ROW32;
       gm = c.gmm ? c.gmm + (size_t)trk_ * c.ngran_cap : nullptr; T0t = c.T0[trk_];
+      if (REC) {
+         recs = c.recs; tbase = c.rec_tile_base + (size_t)trk_ * c.rec_tiles; tcnt = c.rec_tile_cnt + (size_t)trk_ * c.rec_tiles;
+         rt_tile = NO_ROW32; rt_idx = rt_cnt = rt_base = 0;
+         rt_last = (uint32_t)((row_end - 1) / RT_REC_TILE); }
       const bool tz = row_time(c, row0) == 0.0;
       io = (uint32_t)trk + (tz ? 1u : 0u);
       o_pure = ((uint32_t)delay > io ? (uint32_t)delay : io) + (uint32_t)w;
@@ -461,7 +470,55 @@ struct SparseScan {
          if (T < T0t) { lazy_min(oc); st = SP_DENSE; } }           /* the masks no longer cover the threshold: walk rows */
       if (o >= end) st = SP_DONE; }
 
-   RT_FHD void step() { if (st == SP_DENSE) dense_step(); else if (st == SP_SPARSE) sparse_step(); }
+   /* ---- sparse mode on records ---- */
+   RT_FHD void rec_tile(uint32_t tile) { rt_tile = tile; rt_base = tbase[tile]; rt_cnt = tcnt[tile]; rt_idx = 0; }
+   /* the cursor at the first record with plane row >= p; false: none before the end of the unit */
+   RT_FHD bool rec_at(uint64_t p) {
+      const uint32_t tile = (uint32_t)(p / RT_REC_TILE);
+      if (rt_tile == NO_ROW32 || tile != rt_tile) { if (tile > rt_last) return false; rec_tile(tile); }
+      for (;;) {
+         while (rt_idx < rt_cnt && (uint64_t)recs[rt_base + rt_idx].row < p) ++rt_idx;
+         if (rt_idx < rt_cnt) return true;
+         if (rt_tile >= rt_last) return false;
+         rec_tile(rt_tile + 1); } }
+
+   RT_FHD void sparse_step_rec() {
+      const uint32_t from = o > resume ? o : resume;
+      if (from >= end) { o = end; st = SP_DONE; return; }
+      const uint64_t pend = prow(end);
+      if (!rec_at(prow(from))) { o = end; st = SP_DONE; return; }
+      const CandRec r = recs[rt_base + rt_idx];
+      if ((uint64_t)r.row >= pend) { o = end; st = SP_DONE; return; }
+      ++rt_idx;
+      const uint32_t oc = (uint32_t)((uint64_t)r.row - row0) + (uint32_t)delay;
+      o = oc + 1;
+      SP_STAT(cands, 1);
+      const int xl = r.xl, xr = r.xr, S = r.S;
+      const bool tcand = S - (xl > xr ? xl : xr) >= T;
+      bool bcand = (xl < xr ? xl : xr) - (int)r.m >= T;
+      if (r.posm != RT_REC_NOPOS) { m = r.m; mq = oc; }          /* the lazy minimum is known exactly here */
+      if (tcand || bcand) {
+         SP_STAT(evals, 1);
+         const float vl = volts(c, xl), vr = volts(c, xr), maxv = volts(c, S);
+         const bool top = tcand && maxv > vl + rise && maxv > vr + rise && (reqmin == 0 || maxv > reqmin);
+         bool bot = false; float minv = 0; int posb = -1, bprev = 0, bnext = 0;
+         if (!top && bcand) {
+            if (r.posm != RT_REC_NOPOS) { posb = r.posm; bprev = r.mprev; bnext = r.mnext; }
+            else {                                                 /* no canonical row within the record's reach: walk from the last known value */
+               const uint64_t m_at = lazy_min(oc);
+               const uint64_t ws = (uint64_t)r.row - (uint32_t)w + 1u;
+               if (m_at != ~0ull && m_at >= ws && m_at <= (uint64_t)r.row) posb = (int)(m_at - ws);
+               else { const int16_t *win = plane + ws; for (int i = w; i-- > 0;) if ((int)win[i] == m) posb = i; }
+               if (posb >= 0) { const int16_t *win = plane + ws; bprev = posb > 0 ? win[posb - 1] : 0; bnext = posb < w - 1 ? win[posb + 1] : 0; }
+               bcand = (xl < xr ? xl : xr) - m >= T; }
+            minv = volts(c, m);
+            bot = bcand && minv < vl - rise && minv < vr - rise && (reqmin == 0 || minv < -reqmin); }
+         if (top) fire(true, maxv, (int)r.posS + 1, true, r.sprev, r.snext, oc);
+         else if (bot) fire(false, minv, posb + 1, posb >= 0, bprev, bnext, oc);
+         if ((top || bot) && T < T0t) { if (mq != oc) lazy_min(oc); st = SP_DENSE; } }   /* the records no longer cover the threshold: walk rows */
+      if (o >= end) st = SP_DONE; }
+
+   RT_FHD void step() { if (st == SP_DENSE) dense_step(); else if (st == SP_SPARSE) { if (REC) sparse_step_rec(); else sparse_step(); } }
 
    RT_FHD void finish(TrkMeta &meta) {
       /* rows before the first event (or the whole unit) that the sparse mode has not tracked yet: done here, for all lanes of

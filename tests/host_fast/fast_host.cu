@@ -64,8 +64,8 @@ extern "C" int fast_host_scan_unit(const int16_t *planes, uint64_t plane_stride,
       rtfast::ZcScan<1, HostEmit> zus(dc, zm);
       rtfast::drive(zus, zjobs, HostCount());
       return RT_OK; }
-   const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE) && !dc.invert && !dc.differentiate
-                         && !dc.density && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
+   const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE || dc.density) && !dc.invert && !dc.differentiate
+                         && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
    if (!eligible) return RT_ERR_UNSUPPORTED;
    std::vector<uint32_t> scratch(rtfast::scratch_words(dc.width), 0x7fff8000u);   /* poison: the largest sample and the smallest complement */
    rtfast::LaneMem<1> mem = rtfast::lane_mem<1>(scratch.data(), dc.width);
@@ -118,18 +118,19 @@ struct HostAny { bool operator()(bool p) const { return p; } };
    The masks and the granule map of a capture are cached between calls (keyed by plane pointer, width, T0, rows). */
 extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_stride, uint64_t nrows, const rt_tape_desc *desc,
                                      const rt_scan_cfg *cfg, uint64_t row0, uint64_t row_end, rt_event *out, uint32_t cap,
-                                     uint32_t *counts, TrkMeta *meta, float t0_frac, int use_gmm) {
+                                     uint32_t *counts, TrkMeta *meta, float t0_frac, int use_gmm, int use_records) {
    DevCfg dc;
    rtcfg::to_dev(*desc, planes, plane_stride, nrows, cfg, &dc);
-   const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE) && !dc.invert && !dc.differentiate
-                         && !dc.density && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
+   const bool eligible = dc.det == RT_DET_PEAK && (dc.mode == RT_MODE_NRZI || dc.mode == RT_MODE_PE || dc.density) && !dc.invert && !dc.differentiate
+                         && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH;
    if (!eligible) return RT_ERR_UNSUPPORTED;
    const float inv_lsb = 32767.0f / dc.maxvolts;
    const float q = dc.p.pkww_rise * inv_lsb * 0.999f - 2.0f;
    int T0 = q > 0 ? (int)((q > 70000.0f ? 70000.0f : (float)(int)q) * t0_frac) : 0;
    if (T0 > 65535) T0 = 65535;
    if (T0 < 1) return RT_ERR_UNSUPPORTED;
-   struct Cache { std::vector<uint32_t> cand, cand2, acan, gmm; uint64_t mask_stride, ngran; };
+   struct Cache { std::vector<uint32_t> cand, cand2, acan, gmm; uint64_t mask_stride, ngran;
+                  std::vector<CandRec> recs; std::vector<uint32_t> tbase, tcnt; uint64_t rec_tiles; };
    const int T1 = T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 65535;      /* a second plane at 1.6 x T0, as the library does for a fixed RT_SPARSE_T0 */
    static std::map<std::tuple<const int16_t *, uint64_t, int, int, int>, Cache> cache;
    auto key = std::make_tuple(planes, nrows, dc.ntrks, dc.width, T0);
@@ -149,6 +150,18 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
             int mn = 32767, mx = -32768;
             for (uint64_t r = g * RT_GRAN; r < (g + 1) * RT_GRAN && r < nrows; ++r) { int v = planes[(size_t)k * plane_stride + r]; if (v < mn) mn = v; if (v > mx) mx = v; }
             cc.gmm[(size_t)k * cc.ngran + g] = ((uint32_t)mn & 0xffffu) | ((uint32_t)mx << 16); }
+      /* phase B1 on the host: the records of every candidate row, tile by tile (the device places the tiles in arbitrary order) */
+      cc.rec_tiles = plane_stride / RT_REC_TILE + 2;
+      cc.tbase.assign((size_t)cc.rec_tiles * dc.ntrks, 0); cc.tcnt.assign((size_t)cc.rec_tiles * dc.ntrks, 0);
+      for (int k = 0; k < dc.ntrks; ++k) {
+         const int16_t *plane = planes + (size_t)k * plane_stride;
+         const uint32_t *mc = cc.cand.data() + (size_t)k * cc.mask_stride, *ma = cc.acan.data() + (size_t)k * cc.mask_stride;
+         for (uint64_t tile = 0; tile * RT_REC_TILE < nrows; ++tile) {
+            cc.tbase[(size_t)k * cc.rec_tiles + tile] = (uint32_t)cc.recs.size();
+            uint32_t n = 0;
+            for (uint64_t p = tile * RT_REC_TILE; p < (tile + 1) * RT_REC_TILE && p < nrows; ++p)
+               if ((mc[p >> 5] >> (p & 31)) & 1u) { cc.recs.push_back(rtrec::make_record(plane, ma, dc.width, T0, p)); ++n; }
+            cc.tcnt[(size_t)k * cc.rec_tiles + tile] = n; } }
       it = cache.emplace(key, std::move(cc)).first; }
    Cache &cc = it->second;
    dc.m_cand = cc.cand.data(); dc.m_cand2 = cc.cand2.data(); dc.m_acan = cc.acan.data(); dc.mask_stride = cc.mask_stride;
@@ -156,8 +169,13 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
    if (use_gmm) { dc.gmm = cc.gmm.data(); dc.ngran_cap = cc.ngran; }
    uint32_t heights[RT_AGC_MAX_WINDOW];
    HostSparseJobs jobs{dc, planes, plane_stride, row0, row_end, out, cap, counts, meta, rtcfg::quiet_thr_lsb(dc), 0, false};
-   rtsparse::SparseScan<1, HostEmit> us(dc, heights);
-   rtsparse::drive_sparse(us, jobs, HostAny());
+   if (use_records) {
+      dc.recs = cc.recs.data(); dc.rec_tile_base = cc.tbase.data(); dc.rec_tile_cnt = cc.tcnt.data(); dc.rec_tiles = cc.rec_tiles;
+      rtsparse::SparseScan<1, HostEmit, true> us(dc, heights);
+      rtsparse::drive_sparse(us, jobs, HostAny()); }
+   else {
+      rtsparse::SparseScan<1, HostEmit> us(dc, heights);
+      rtsparse::drive_sparse(us, jobs, HostAny()); }
    return RT_OK; }
 
 #ifdef RT_SPARSE_STATS

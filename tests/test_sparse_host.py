@@ -31,25 +31,33 @@ def host_lib():
                                       C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
     L.sparse_host_scan_unit.restype = C.c_int
     L.sparse_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg),
-                                        C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+                                        C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
     L.masks_host_build.restype = C.c_int
     L.masks_host_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     return L
 
 
 def sparse_scan(L, planes, stride, nrows, desc, cfg, row0, row_end, frac=0.25, gmm=1, cap=1 << 16):
+    """the two-pass scan on the host, in BOTH forms of its sequential phase -- candidate rows derived from the bit planes and the
+    samples inside the walk, and candidate records built beforehand (phase B1, scan_records.cuh) -- which must agree in everything"""
     nt = desc.ntrks
-    out = np.zeros((nt, cap), dtype=abi.EVENT_DTYPE)
-    counts = np.zeros(nt, dtype=np.uint32)
-    meta = np.zeros((nt, L.fast_host_meta_size()), dtype=np.uint8)
-    rc = L.sparse_host_scan_unit(planes.ctypes.data, stride, nrows, C.byref(desc), C.byref(cfg), row0, row_end,
-                                 out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, frac, gmm)
-    if rc != 0:
-        return None, None
-    assert counts.max(initial=0) <= cap
-    ev = np.concatenate([out[k, :counts[k]] for k in range(nt)])
-    order = np.lexsort((ev["trk"], ev["row"]))
-    return ev[order], meta.view("<u4")
+    res = []
+    for records in (0, 1):
+        out = np.zeros((nt, cap), dtype=abi.EVENT_DTYPE)
+        counts = np.zeros(nt, dtype=np.uint32)
+        meta = np.zeros((nt, L.fast_host_meta_size()), dtype=np.uint8)
+        rc = L.sparse_host_scan_unit(planes.ctypes.data, stride, nrows, C.byref(desc), C.byref(cfg), row0, row_end,
+                                     out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, frac, gmm, records)
+        if rc != 0:
+            return None, None
+        assert counts.max(initial=0) <= cap
+        ev = np.concatenate([out[k, :counts[k]] for k in range(nt)])
+        order = np.lexsort((ev["trk"], ev["row"]))
+        res.append((ev[order], meta.view("<u4").copy()))
+    (e0, m0), (e1, m1) = res
+    assert e0.tobytes() == e1.tobytes(), f"record mode differs from plane mode: {len(e0)} vs {len(e1)} events (unit at row {row0})"
+    assert np.array_equal(m0, m1), f"record mode: proof data differ (unit at row {row0})"
+    return e1, m1
 
 
 def fast_meta(L, planes, stride, nrows, desc, cfg, row0, row_end, cap=1 << 16):
