@@ -55,6 +55,26 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_memory_near_gpu(index):
+    """Prefer host memory on the NUMA node the GPU hangs off for everything this process allocates from now on (the pinned tape and
+    event buffers of the e2e run): with all ranks' buffers on one node, the GPUs of the other socket copy across the inter-socket
+    link.  set_mempolicy(MPOL_PREFERRED) through libc; returns what was done, for the bench line.  Never fatal."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"gpu_pci": bus, "numa_node": node, "policy": "none (no NUMA information)"}
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238                   # x86-64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        return {"gpu_pci": bus, "numa_node": node, "policy": "MPOL_PREFERRED" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})"}
+    except Exception as exc:
+        return {"policy": f"unavailable ({exc!r})"}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -552,6 +572,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    numa = bind_memory_near_gpu(local_rank)
     lib = abi.load_product()                      # raises if the CUDA library is missing: no fallback
     rows = args.rows
     T = tile.shape[0]
@@ -637,6 +658,7 @@ def main():
         barrier(); t0 = time.perf_counter()
         for _ in range(ke):
             ste = step_e2e()
+        torch.cuda.synchronize(); el_local = time.perf_counter() - t0
         barrier(); t1 = time.perf_counter()
         el = t1 - t0
         if dist is not None:
@@ -645,6 +667,7 @@ def main():
             el = float(tt.item())
         e2e = {"value": world * rows * 9 * ke / el, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "rows_per_gpu": int(rows),
                "d2h_bytes_per_step": int(ste.d2h_bytes), "ms_per_step": 1e3 * el / ke, "segments_streamed": int(ste.pad),
+               "h2d_GBps_this_rank": nbytes * ke / el_local / 1e9, "host_memory": numa,
                "api": "rt_bulk_scan_host (pinned host rows -> events + proof data in pinned host memory) + rt_bulk_lookup"}
         lib.L.rt_host_free(hptr)
         rows = rows_full

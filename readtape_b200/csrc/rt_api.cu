@@ -710,8 +710,10 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       clock / AGC constants share them */
    struct MaskSet { int width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; uint32_t *mc, *md, *ma; uint32_t first_cfg; uint32_t *tb, *tc; };
    unsigned int *d_rec_cursor = nullptr;                            /* phase B1: records of all mask sets share one pool and one cursor */
+   /* phase B1 records are opt-in (RT_SPARSE_RECORDS=1): bit-exact, but measured slower than deriving the candidates inside the walk
+      (B200, config 2: records 69 ms + walk 46 ms against 19 ms) */
    const char *recenv = getenv("RT_SPARSE_RECORDS");
-   bool use_records = !(recenv && recenv[0] == '0');
+   bool use_records = recenv && recenv[0] == '1';
    const uint64_t rec_tiles = cand_rec_tiles(t->plane_stride);
    uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have_hist = false;
    std::vector<MaskSet> msets;
