@@ -588,6 +588,8 @@ def main():
         dev[at:at + n] = tile_t[:n]
     torch.cuda.synchronize()
     tape = lib.open(desc, device=local_rank)
+    if not os.environ.get("RT_BENCH_NO_PREPARE"):
+        tape.prepare(cfg)                         # the scan's configuration is known before the samples arrive: masks are built by the ingest kernel
 
     def barrier():
         if dist is not None:

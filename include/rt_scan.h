@@ -155,6 +155,13 @@ int  rt_upload(rt_tape *tape, const int16_t *rows, uint64_t nrows);
 int  rt_upload_fd(rt_tape *tape, int fd, uint64_t offset, uint64_t nrows);
 /* Same, but `rows_dev` is already a DEVICE pointer (product library only). */
 int  rt_attach_device(rt_tape *tape, const void *rows_dev, uint64_t nrows);
+/* Optional, speed only.  Announce the configuration the next whole-tape scan (rt_bulk_scan) will use: rows uploaded / attached from
+ * now on get the candidate / canonical bit planes of that configuration's peak-detector window (phase A of the two-pass scan)
+ * computed by the ingest kernel itself, while their tile is on chip, instead of by a separate pass that re-reads the planes.
+ * The per-track mask thresholds are chosen from the first rows of the tape (or kept from the previous tape of this object).
+ * Only plain NRZI / PE peak detection on 9-head captures with a window of 6..20 samples is fused; anything else is ignored.
+ * cfg == NULL cancels.  Results never depend on it. */
+int  rt_prepare(rt_tape *tape, const rt_scan_cfg *cfg);
 /* Forget the samples but keep the device buffers (re-use the tape for the next capture of similar size). */
 int  rt_clear(rt_tape *tape);
 uint64_t rt_nrows(const rt_tape *tape);

@@ -584,6 +584,7 @@ int rt_bulk_scan_host(rt_tape *t, const int16_t *r, uint64_t n, const rt_scan_cf
 int rt_bulk_unit_at(const rt_bulk *b, uint32_t c, uint64_t r, rt_unit_info *o) { (void)b; (void)c; (void)r; (void)o; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_get_stats(const rt_bulk *b, rt_bulk_stats *o) { (void)b; (void)o; return RT_ERR_UNSUPPORTED; }
 void rt_bulk_free(rt_bulk *b) { (void)b; }
+int rt_prepare(rt_tape *t, const rt_scan_cfg *c) { (void)t; (void)c; return RT_OK; }
 int rt_set_option(int o, int v) { (void)o; (void)v; return RT_OK; }
 int rt_bulk_last_unit(const rt_bulk *b, uint32_t c, uint64_t *r0, uint64_t *r1) { (void)b; (void)c; (void)r0; (void)r1; return RT_ERR_UNSUPPORTED; }
 int rt_bulk_tile_digest(rt_bulk *b, uint32_t c, uint64_t p, uint64_t n, uint64_t *e, uint64_t *d, uint64_t *bt) {

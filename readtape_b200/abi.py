@@ -67,7 +67,7 @@ EVENT_DTYPE = np.dtype([("row", "<u8"), ("t_event", "<f8"), ("v_top", "<f4"), ("
                         ("agc_gain", "<f4"), ("trk", "u1"), ("kind", "u1"), ("pad", "u1", (2,))])
 assert EVENT_DTYPE.itemsize == 32
 
-EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_clear",
+EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_prepare", "rt_clear",
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
            "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_results_size", "rt_bulk_results_to_device", "rt_bulk_fetch_to", "rt_host_register", "rt_host_unregister", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_bulk_tile_digest", "rt_bulk_last_unit", "rt_set_option", "rt_peak_masks", "rt_pkww_width",
@@ -99,6 +99,7 @@ class Lib:
         L.rt_upload.argtypes = [vp, vp, u64]
         L.rt_attach_device.argtypes = [vp, vp, u64]
         L.rt_clear.argtypes = [vp]
+        L.rt_prepare.argtypes = [vp, P(ScanCfg)]; L.rt_prepare.restype = i32
         L.rt_bulk_fetch.argtypes = [vp]
         L.rt_nrows.argtypes = [vp]; L.rt_nrows.restype = u64
         L.rt_close.argtypes = [vp]; L.rt_close.restype = None
@@ -125,7 +126,7 @@ class Lib:
         L.rt_peak_masks.argtypes = [vp, P(ScanCfg), C.c_float, vp, vp, u64, P(C.c_int32)]
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
         L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
-        for fn in ("rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
+        for fn in ("rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_prepare", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
                    "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_lookup",
                    "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_pkww_width", "rt_peak_masks"):
             getattr(L, fn).restype = i32
@@ -170,6 +171,10 @@ class Tape:
 
     def clear(self) -> None:
         self.lib.check(self.lib.L.rt_clear(self.h))
+
+    def prepare(self, cfg) -> None:
+        """announce the configuration of the next whole-tape scan (rt_prepare): uploads then also build its mask planes"""
+        self.lib.check(self.lib.L.rt_prepare(self.h, C.byref(cfg) if cfg is not None else None))
 
     @property
     def nrows(self) -> int:

@@ -8,9 +8,13 @@ namespace rtgen { struct SkewState; }
 struct TrkState;
 
 /* k_ingest.cu */
+/* the bit planes of K3c phase A, to be written by the ingest kernel itself (fused) for the tiles it handles */
+struct IngestMasks { uint32_t *cand, *cand2, *acan; uint64_t mask_stride; int ntrks, width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; };
+bool ingest_masks_supported(int nheads, int ntrks, int width);
 cudaError_t launch_ingest(const int16_t *src, uint64_t nrows, uint64_t row_base, int nheads, const int32_t *trk_of_head,
                           int16_t *planes, uint64_t plane_stride, int16_t *gmm, uint64_t ngran_cap,
-                          unsigned long long *first_end_row, int sms, int force_simple, cudaStream_t st, int *launches);
+                          unsigned long long *first_end_row, int sms, int force_simple, cudaStream_t st, int *launches,
+                          const IngestMasks *mask = nullptr, uint64_t *masked_rows = nullptr);
 
 /* k_units.cu */
 struct UnitParams {

@@ -79,6 +79,14 @@ struct rt_tape {
    uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
    /* phase B1: candidate records (scan_records.cuh), grow-only like the event pool; one pool shared by the mask sets of a scan */
    CandRec *rec_cache = nullptr; uint32_t rec_cache_cap = 0; uint32_t rec_hist = 0;
+   /* rt_prepare(): the bit planes of K3c phase A written by the ingest kernel itself for an announced configuration */
+   struct PreMask {
+      bool active = false, have_thr = false; rt_scan_cfg cfg{}; int width = 0; float rise = 0;
+      int32_t T0[RT_MAXTRKS] = {}, T1[RT_MAXTRKS] = {};
+      uint32_t *mc = nullptr, *md = nullptr, *ma = nullptr; uint64_t stride = 0;
+      uint64_t rows = 0;                                             /* the planes are complete for tape rows [0, rows) */
+      uint64_t fused_rows = 0;                                       /* of which written by the fused kernel (diagnostics) */
+   } pm;
    int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
 };
 
@@ -142,16 +150,60 @@ extern "C" int rt_open(const rt_tape_desc *desc, int device, rt_tape **out) {
    *out = t; return RT_OK; }
 
 /* enqueue the ingest of `nrows` rows at d_src (device) on the tape's stream; does not wait */
+static void cfg_to_dev(const rt_tape *t, const rt_scan_cfg *cfg, DevCfg *d);
+static cudaError_t plan_thresholds_from_rows(rt_tape *t, uint64_t rows_avail);
+
+/* the mask planes of an announced configuration (rt_prepare) follow the sample planes' capacity */
+static int premask_reserve(rt_tape *t) {
+   rt_tape::PreMask &pm = t->pm;
+   const uint64_t ms = peak_mask_stride(t->plane_stride);
+   if (pm.stride == ms && pm.mc) return RT_OK;
+   cudaFree(pm.mc); cudaFree(pm.md); cudaFree(pm.ma); pm.mc = pm.md = pm.ma = nullptr; pm.stride = 0; pm.rows = 0;
+   const size_t bytes = (size_t)ms * t->desc.ntrks * 4;
+   CU(cudaMalloc(&pm.mc, bytes)); CU(cudaMalloc(&pm.md, bytes)); CU(cudaMalloc(&pm.ma, bytes));
+   CU(cudaMemsetAsync(pm.mc, 0, bytes, t->stream)); CU(cudaMemsetAsync(pm.md, 0, bytes, t->stream)); CU(cudaMemsetAsync(pm.ma, 0, bytes, t->stream));
+   pm.stride = ms;
+   return RT_OK; }
+
+static void premask_devcfg(const rt_tape *t, DevCfg *dc) {
+   const rt_tape::PreMask &pm = t->pm;
+   cfg_to_dev(t, &pm.cfg, dc);
+   dc->m_cand = pm.mc; dc->m_cand2 = pm.md; dc->m_acan = pm.ma; dc->mask_stride = pm.stride;
+   for (int k = 0; k < RT_MAXTRKS; ++k) { dc->T0[k] = pm.T0[k]; dc->T1[k] = pm.T1[k]; } }
+
 static int tape_ingest(rt_tape *t, const int16_t *d_src, uint64_t nrows) {
    cudaEvent_t e0, e1;
    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+   rt_tape::PreMask &pm = t->pm;
+   IngestMasks im{}; const IngestMasks *imp = nullptr;
+   if (pm.active) { int rc = premask_reserve(t); if (rc) return rc; }
+   if (pm.active && pm.have_thr && pm.rows == t->nrows) {           /* the planes are complete so far: this chunk's tiles are done on chip */
+      im.cand = pm.mc; im.cand2 = pm.md; im.acan = pm.ma; im.mask_stride = pm.stride; im.ntrks = (int)t->desc.ntrks; im.width = pm.width;
+      memcpy(im.T0, pm.T0, sizeof im.T0); memcpy(im.T1, pm.T1, sizeof im.T1);
+      imp = &im; }
    CU(cudaEventRecord(e0, t->stream));
+   uint64_t masked = 0;
    cudaError_t e = launch_ingest(d_src, nrows, t->nrows, (int)t->desc.nheads, t->trk_of_head, t->planes, t->plane_stride,
-                                 t->gmm, t->ngran_cap, t->d_first_end, t->sms, t->force_simple_ingest, t->stream, &t->launches);
+                                 t->gmm, t->ngran_cap, t->d_first_end, t->sms, t->force_simple_ingest, t->stream, &t->launches, imp, &masked);
    if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "ingest kernel launch failed: %s", cudaGetErrorString(e));
+   if (imp) {                                                     /* what the fused kernel left: the tail behind the last whole tile (or everything) */
+      if (masked < nrows) {
+         DevCfg dc; premask_devcfg(t, &dc);
+         e = launch_peak_masks(dc, t->nrows + masked, t->nrows + nrows, t->stream); ++t->launches;
+         if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "mask kernel launch failed: %s", cudaGetErrorString(e)); }
+      pm.rows = t->nrows + nrows; pm.fused_rows += masked; }
    CU(cudaEventRecord(e1, t->stream));
    t->ingest_events.push_back(e0); t->ingest_events.push_back(e1);
    t->nrows += nrows; t->valid_known = false;
+   if (pm.active && !pm.have_thr && t->nrows >= (1u << 20)) {      /* enough rows to choose the thresholds from: the rest of the tape is fused */
+      CU(cudaStreamSynchronize(t->stream));
+      e = plan_thresholds_from_rows(t, t->nrows);
+      if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "threshold selection failed: %s", cudaGetErrorString(e));
+      if (pm.have_thr) {
+         DevCfg dc; premask_devcfg(t, &dc);
+         e = launch_peak_masks(dc, 0, t->nrows, t->stream); ++t->launches;
+         if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "mask kernel launch failed: %s", cudaGetErrorString(e));
+         pm.rows = t->nrows; } }
    return RT_OK; }
 
 /* wait for everything enqueued on the tape's stream; fold the ingest kernel times into ms_ingest */
@@ -319,7 +371,12 @@ extern "C" int rt_attach_device(rt_tape *t, const void *rows_dev, uint64_t nrows
    CU(cudaSetDevice(t->device));
    int rc = tape_reserve(t, t->nrows + nrows);
    if (rc) return rc;
-   rc = tape_ingest(t, static_cast<const int16_t *>(rows_dev), nrows);
+   const int16_t *src = static_cast<const int16_t *>(rows_dev);
+   if (t->pm.active && !t->pm.have_thr && t->nrows == 0 && nrows > (8u << 20)) {   /* thresholds from the first 4 Mi rows, the rest fused */
+      const uint64_t head = 4u << 20;
+      rc = tape_ingest(t, src, head); if (rc) return rc;
+      src += head * t->desc.nheads; nrows -= head; }
+   rc = tape_ingest(t, src, nrows);
    if (rc) return rc;
    return tape_drain(t); }
 
@@ -330,6 +387,7 @@ extern "C" int rt_clear(rt_tape *t) {
    unsigned long long none = ~0ull;
    CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
    t->nrows = 0; t->nrows_valid = 0; t->valid_known = false; t->ms_ingest = 0; t->h2d_bytes = 0;
+   t->pm.rows = 0; t->pm.fused_rows = 0;
    return RT_OK; }
 
 static int tape_sync_valid(rt_tape *t) {
@@ -353,7 +411,7 @@ extern "C" void rt_close(rt_tape *t) {
    if (t->stream) cudaStreamSynchronize(t->stream);
    cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
    cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
-   cudaFree(t->rec_cache);
+   cudaFree(t->rec_cache); cudaFree(t->pm.mc); cudaFree(t->pm.md); cudaFree(t->pm.ma);
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
    if (t->h_ring) { cudaFreeHost(t->h_ring); for (auto e : t->ring_done) if (e) cudaEventDestroy(e); }
    if (t->s_copy) cudaStreamDestroy(t->s_copy);
@@ -665,6 +723,40 @@ static cudaError_t plan_auto_t0(const rt_tape *t, ScanPlan *pl, uint64_t rows_av
    if (getenv("RT_TRACE")) { fprintf(stderr, "[two-pass scan] T0/T1 per track:"); for (int k = 0; k < nt; ++k) fprintf(stderr, " %d/%d", pl->dc.T0[k], pl->dc.T1[k]); fprintf(stderr, "\n"); }
    return cudaSuccess; }
 
+/* rt_prepare(): the per-track mask thresholds of the announced configuration from the rows ingested so far */
+static cudaError_t plan_thresholds_from_rows(rt_tape *t, uint64_t rows_avail) {
+   rt_tape::PreMask &pm = t->pm;
+   ScanPlan pl; make_plan(t, &pm.cfg, &pl);
+   if (!pl.use_sparse) { pm.active = false; return cudaSuccess; }
+   if (pl.t0_auto) {
+      uint32_t *d_hist = nullptr; std::vector<uint32_t> h_hist; bool have = false;
+      cudaError_t e = cudaMalloc(&d_hist, (size_t)span_hist_words((int)t->desc.ntrks) * 4);
+      if (e != cudaSuccess) return e;
+      e = plan_auto_t0(t, &pl, rows_avail, d_hist, h_hist, have, t->stream);
+      cudaFree(d_hist);
+      if (e != cudaSuccess) return e;
+      if (!pl.use_sparse) { pm.active = false; return cudaSuccess; } }
+   memcpy(pm.T0, pl.dc.T0, sizeof pm.T0); memcpy(pm.T1, pl.dc.T1, sizeof pm.T1);
+   pm.have_thr = true;
+   return cudaSuccess; }
+
+extern "C" int rt_prepare(rt_tape *t, const rt_scan_cfg *cfg) {
+   if (!t) return set_err(RT_ERR_ARG, "rt_prepare: null");
+   rt_tape::PreMask &pm = t->pm;
+   if (!cfg) { pm.active = false; return RT_OK; }
+   int rc = cfg_check(t, cfg); if (rc) return rc;
+   DevCfg dc; cfg_to_dev(t, cfg, &dc);
+   const char *env = getenv("RT_FUSED_MASKS");
+   const bool ok = !(env && env[0] == '0') && dc.det == RT_DET_PEAK && !dc.invert && !dc.differentiate && !dc.density
+                   && (cfg->mode == RT_MODE_NRZI || cfg->mode == RT_MODE_PE)
+                   && ingest_masks_supported((int)t->desc.nheads, (int)t->desc.ntrks, dc.width) && !t->force_simple_ingest;
+   if (!ok) { pm.active = false; return RT_OK; }
+   if (pm.active && pm.width == dc.width && pm.rise == cfg->parms.pkww_rise && memcmp(&pm.cfg, cfg, sizeof *cfg) == 0) return RT_OK;   /* unchanged: thresholds and planes stay */
+   const bool same_masks = pm.width == dc.width && pm.rise == cfg->parms.pkww_rise && pm.cfg.bpi == cfg->bpi && pm.cfg.ips == cfg->ips && pm.cfg.mode == cfg->mode;
+   pm.active = true; pm.cfg = *cfg; pm.width = dc.width; pm.rise = cfg->parms.pkww_rise;
+   if (!same_masks) { pm.have_thr = false; pm.rows = 0; }
+   return RT_OK; }
+
 extern "C" void rt_bulk_free(rt_bulk *b) {
    if (!b) return;
    rt_tape *t = b->tape;
@@ -708,7 +800,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    std::vector<cudaEvent_t> done_ev(ncfgs, nullptr);
    /* K3c: candidate / canonical bit planes, one set per distinct (window width, T0) -- parameter sets that only differ in
       clock / AGC constants share them */
-   struct MaskSet { int width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; uint32_t *mc, *md, *ma; uint32_t first_cfg; uint32_t *tb, *tc; };
+   struct MaskSet { int width; int32_t T0[RT_MAXTRKS], T1[RT_MAXTRKS]; uint32_t *mc, *md, *ma; uint32_t first_cfg; uint32_t *tb, *tc; bool borrowed; };
    unsigned int *d_rec_cursor = nullptr;                            /* phase B1: records of all mask sets share one pool and one cursor */
    /* phase B1 records are opt-in (RT_SPARSE_RECORDS=1): bit-exact, but measured slower than deriving the candidates inside the walk
       (B200, config 2: records 69 ms + walk 46 ms against 19 ms) */
@@ -720,7 +812,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    auto cleanup = [&]() {
       void *scr[] = {d_bitmap, d_flags, d_blockcount, d_nunits, d_units_tmp, d_counters, d_cursor, d_hist};
       for (void *p : scr) if (p) cudaFreeAsync(p, t->stream);
-      for (auto &m : msets) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.md) cudaFreeAsync(m.md, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream);
+      for (auto &m : msets) { if (!m.borrowed) { if (m.mc) cudaFreeAsync(m.mc, t->stream); if (m.md) cudaFreeAsync(m.md, t->stream); if (m.ma) cudaFreeAsync(m.ma, t->stream); }
                               if (m.tb) cudaFreeAsync(m.tb, t->stream); if (m.tc) cudaFreeAsync(m.tc, t->stream); }
       if (d_rec_cursor) cudaFreeAsync(d_rec_cursor, t->stream);
       for (auto &e : ev) cudaEventDestroy(e);
@@ -763,6 +855,38 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
       for (uint32_t ci = 0; ci < ncfgs; ++ci) {
          ScanPlan &pl = plans[ci];
          if (!pl.use_sparse || !b->cfgs[ci].nunits) continue;
+         const rt_tape::PreMask &pm = t->pm;
+         const bool adopt = pm.active && pm.have_thr && pm.mc && pm.stride == mstride && pm.rows >= nrows && pm.width == pl.dc.width
+                            && pm.rise == pl.dc.p.pkww_rise && pm.cfg.bpi == cfgs[ci].bpi && pm.cfg.ips == cfgs[ci].ips && pm.cfg.mode == cfgs[ci].mode;
+         if (adopt) {                                              /* the ingest kernel has already written these planes (rt_prepare) */
+            memcpy(pl.dc.T0, pm.T0, sizeof pl.dc.T0); memcpy(pl.dc.T1, pm.T1, sizeof pl.dc.T1);
+            size_t k = 0;
+            while (k < msets.size() && msets[k].mc != pm.mc) ++k;
+            if (k == msets.size()) {
+               MaskSet m{}; m.width = pl.dc.width; memcpy(m.T0, pl.dc.T0, sizeof m.T0); memcpy(m.T1, pl.dc.T1, sizeof m.T1); m.first_cfg = ci;
+               m.mc = pm.mc; m.md = pm.md; m.ma = pm.ma; m.borrowed = true;
+               msets.push_back(m);
+               if (use_records) {
+                  CUB(cudaMallocAsync(&msets[k].tb, (size_t)rec_tiles * nt * 4, t->stream));
+                  CUB(cudaMallocAsync(&msets[k].tc, (size_t)rec_tiles * nt * 4, t->stream)); } }
+            pl.dc.m_cand = pm.mc; pl.dc.m_cand2 = pm.md; pl.dc.m_acan = pm.ma; pl.dc.mask_stride = mstride;
+            if (getenv("RT_PREMASK_CHECK")) {                       /* tests: the fused planes against the separate mask pass, word for word */
+               uint32_t *tc_ = nullptr, *td_ = nullptr, *ta_ = nullptr;
+               const size_t bytes = (size_t)mstride * nt * 4;
+               CUB(cudaMalloc(&tc_, bytes)); CUB(cudaMalloc(&td_, bytes)); CUB(cudaMalloc(&ta_, bytes));
+               DevCfg dchk = pl.dc; dchk.m_cand = tc_; dchk.m_cand2 = td_; dchk.m_acan = ta_;
+               CUB(launch_peak_masks(dchk, 0, nrows, t->stream));
+               std::vector<uint32_t> h0(mstride * nt), h1(mstride * nt);
+               const uint32_t *pairs[3][2] = {{pm.mc, tc_}, {pm.md, td_}, {pm.ma, ta_}};
+               uint64_t bad = 0; const uint64_t nw = nrows / 32;       /* whole words of valid rows */
+               for (auto &pr : pairs) {
+                  CUB(cudaMemcpyAsync(h0.data(), pr[0], bytes, cudaMemcpyDeviceToHost, t->stream)); CUB(cudaMemcpyAsync(h1.data(), pr[1], bytes, cudaMemcpyDeviceToHost, t->stream));
+                  CUB(cudaStreamSynchronize(t->stream));
+                  for (uint32_t k2 = 0; k2 < nt; ++k2) for (uint64_t wi = 0; wi < nw; ++wi) if (h0[k2 * mstride + wi] != h1[k2 * mstride + wi]) ++bad; }
+               cudaFree(tc_); cudaFree(td_); cudaFree(ta_);
+               if (bad) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_STATE, "fused mask planes differ from the separate pass in %llu words", (unsigned long long)bad); }
+               fprintf(stderr, "[rt_bulk_scan] fused mask planes identical to the separate pass (%llu rows, %llu fused)\n", (unsigned long long)nrows, (unsigned long long)pm.fused_rows); }
+            continue; }
          if (pl.t0_auto) {
             if (!d_hist) { CUB(cudaMallocAsync(&d_hist, (size_t)span_hist_words((int)nt) * 4, t->stream)); ++t->launches; }
             CUB(plan_auto_t0(t, &pl, nrows, d_hist, h_hist, have_hist, t->stream));
@@ -798,7 +922,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          if (use_records && !msets.empty() && want_recs > t->rec_cache_cap) {
             if (want_recs > 0xfffffff0ull) use_records = false;
             else {
-               cudaFree(t->rec_cache); t->rec_cache = nullptr; t->rec_cache_cap = 0;
+               cudaFree(t->rec_cache); cudaFree(t->pm.mc); cudaFree(t->pm.md); cudaFree(t->pm.ma); t->rec_cache = nullptr; t->rec_cache_cap = 0;
                if (cudaMalloc(&t->rec_cache, (size_t)want_recs * sizeof(CandRec)) != cudaSuccess) { cudaGetLastError(); use_records = false; }
                else { t->rec_cache_cap = (uint32_t)want_recs; recs_stale = true; } } }
          if (want_chunks > b->pool_chunks) {
@@ -820,7 +944,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          CUB(cudaMemsetAsync(d_counters, 0, 32 * (size_t)ncfgs, t->stream));
          CUB(cudaEventRecord(ev[2], t->stream));
          if (attempt == 0) {                                      /* phase A of the two-pass scan: once per mask set */
-            for (auto &m : msets) { CUB(launch_peak_masks(plans[m.first_cfg].dc, 0, nrows, t->stream)); ++t->launches; } }
+            for (auto &m : msets) if (!m.borrowed) { CUB(launch_peak_masks(plans[m.first_cfg].dc, 0, nrows, t->stream)); ++t->launches; } }
          CUB(cudaEventRecord(ev[4], t->stream));
          if (use_records && !msets.empty() && recs_stale) {       /* phase B1: the candidate records of every mask set */
             CUB(cudaMemsetAsync(d_rec_cursor, 0, 4, t->stream));
@@ -1061,6 +1185,15 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
             seg_ev.push_back(e); seg_rows_done.push_back(done); next_mark = done + seg_target; } }
       t->h2d_bytes += nrows * nh * 2; }
 
+   /* the ingest kernels enqueued above may already be writing the mask planes of this configuration (rt_prepare) */
+   bool masks_fused = false;
+   {  const rt_tape::PreMask &pm = t->pm;
+      if (pl.use_sparse && pm.active && pm.have_thr && pm.mc && pm.stride == peak_mask_stride(t->plane_stride) && pm.rows >= nrows && pm.width == pl.dc.width
+          && pm.rise == pl.dc.p.pkww_rise && pm.cfg.bpi == cfg->bpi && pm.cfg.ips == cfg->ips && pm.cfg.mode == cfg->mode) {
+         memcpy(pl.dc.T0, pm.T0, sizeof pl.dc.T0); memcpy(pl.dc.T1, pm.T1, sizeof pl.dc.T1);
+         pl.dc.m_cand = pm.mc; pl.dc.m_cand2 = pm.md; pl.dc.m_acan = pm.ma; pl.t0_auto = false; have_hist = true;
+         bc.dc = pl.dc; masks_fused = true; } }
+
    /* 2. per segment: units of the prefix, scan the complete ones, send their results home */
    uint32_t u_done = 0, c_done = 0, nun = 0; double ms_scan = 0, ms_units = 0;
    for (size_t k = 0; k < seg_ev.size() && !failed; ++k) {
@@ -1089,7 +1222,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
       else while (u_final + 1 < nun && bc.units[u_final + 1].row0 + pl.up.tail_rows + 4096 <= R) ++u_final;    /* row_end can no longer change */
       if (u_final == u_done) continue;
       CUS(cudaEventRecord(ev_a, t->s_scan));
-      if (pl.use_sparse) {                                       /* phase A for the rows that arrived since the last segment */
+      if (pl.use_sparse && !masks_fused) {                       /* phase A for the rows that arrived since the last segment */
          if (!ev_m) CUS(cudaEventCreate(&ev_m));
          CUS(launch_peak_masks(pl.dc, masks_done, R, t->s_scan)); ++t->launches;
          masks_done = R / 64 * 64;                               /* the run that holds row R is redone when it is complete */

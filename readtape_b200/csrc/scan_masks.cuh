@@ -112,7 +112,7 @@ struct RunMasks {
       return n0 | (n1 << 16); }
 
    static RT_FHD void run(const int16_t *plane, int64_t p0, uint32_t T0, uint32_t T1, uint32_t (&cand)[2], uint32_t (&cand2)[2], uint32_t (&acan)[2]) {
-      uint32_t x[NW], P[NW], Dt[MASK_RUN / 2];
+      uint32_t x[NW];
       const int16_t *src = plane + (p0 - HALO);                /* 16-byte aligned: p0 % 32 == 0, HALO % 8 == 0, planes 16-byte aligned */
 #pragma unroll
       for (int cch = 0; cch < NW / 4; ++cch) {
@@ -124,6 +124,12 @@ struct RunMasks {
          for (int k = 0; k < 4; ++k) x[4 * cch + k] ^= BIAS2;
 #endif
       }
+      core(x, T0, T1, cand, cand2, acan); }
+
+   /* the same from packed samples already held: x[i] = rows (p0 - HALO + 2i, p0 - HALO + 2i + 1), biased (^ BIAS2).  Used by the
+      ingest kernel, which has the de-interleaved tile in shared memory (k_ingest.cu) */
+   static RT_FHD void core(const uint32_t (&x)[NW], uint32_t T0, uint32_t T1, uint32_t (&cand)[2], uint32_t (&cand2)[2], uint32_t (&acan)[2]) {
+      uint32_t P[NW], Dt[MASK_RUN / 2];
       const uint32_t one2 = 0x00010001u, t0m1 = (T0 - 1u) | ((T0 - 1u) << 16), t1m1 = (T1 - 1u) | ((T1 - 1u) << 16);
       uint32_t gc[4] = {0, 0, 0, 0}, gd[4] = {0, 0, 0, 0}, gn[4] = {0, 0, 0, 0};
       /* pass 1: window maximum -> top-side margin S - max(l, r), and "the leaving sample is below the maximum" (not acan) */

@@ -631,7 +631,7 @@ static void serve_one(struct chan *ch) {                       /* parent: one ex
 
 /* the memory the workers will read the events from is prepared while CUDA starts up and the file travels to the GPU: an anonymous
    MAP_SHARED mapping, its pages touched by a few threads (4-5 GB of page faults are a second of single-thread work otherwise) */
-static struct { pthread_t th; char *buf; size_t bytes; int started; } PREP;
+static struct { pthread_t th; char *buf; size_t bytes; int started; volatile int stop; int registered; } PREP;
 struct touch { char *p; size_t n; };
 static void *prep_touch(void *arg) { struct touch *r = arg; for (size_t i = 0; i < r->n; i += 4096) r->p[i] = 0; return NULLP; }
 static void *prep_main(void *arg) {
@@ -647,9 +647,12 @@ static void *prep_main(void *arg) {
       r[k].p = PREP.buf + lo; r[k].n = PREP.bytes - lo < per ? PREP.bytes - lo : per;
       pthread_create(&th[k], NULLP, prep_touch, &r[k]); }
    for (int k = 0; k < NT; ++k) pthread_join(th[k], NULLP);
+   /* pin it for the device-to-host copy as soon as there is a CUDA context (rt_open done), while the main thread uploads the file */
+   while (!S.tape && !PREP.stop) usleep(2000);
+   if (S.tape && !PREP.stop) PREP.registered = rt_host_register(S.tape, PREP.buf, PREP.bytes) == RT_OK;
    return NULLP; }
 
-#define WRET do { if (PREP.buf) { munmap(PREP.buf, PREP.bytes); PREP.buf = NULLP; } return; } while (0)
+#define WRET do { if (PREP.buf) { if (PREP.registered) rt_host_unregister(S.tape, PREP.buf); munmap(PREP.buf, PREP.bytes); PREP.buf = NULLP; } return; } while (0)
 static void run_workers(void) {
    const char *env = getenv("RT_WORKERS");
    int P = env ? atoi(env) : 1;
@@ -663,6 +666,7 @@ static void run_workers(void) {
       PREP.bytes = ((size_t)((end - pos) / 2 / 48) * 32 * (size_t)nps + (64u << 20)) / 4096 * 4096;
       PREP.started = pthread_create(&PREP.th, NULLP, prep_main, NULLP) == 0; }
    open_tape();
+   PREP.stop = 1;
    if (PREP.started) pthread_join(PREP.th, NULLP);
    if (!S.use_bulk) WRET;
    if (P > 256) P = 256;
@@ -676,10 +680,9 @@ static void run_workers(void) {
    double w2 = wall();
    int rc = RT_ERR_OVERFLOW;
    if (PREP.started && PREP.buf) {                              /* straight into the prepared mapping, pinned for the copy */
-      const int reg = rt_host_register(S.tape, PREP.buf, PREP.bytes) == RT_OK;
+      if (!PREP.registered) PREP.registered = rt_host_register(S.tape, PREP.buf, PREP.bytes) == RT_OK;
       rc = rt_bulk_fetch_to(S.bulk[ps0].bulk, PREP.buf, PREP.bytes);
-      if (reg) rt_host_unregister(S.tape, PREP.buf);
-      if (rc == RT_ERR_OVERFLOW) { munmap(PREP.buf, PREP.bytes); PREP.buf = NULLP; }
+      if (rc == RT_ERR_OVERFLOW) { if (PREP.registered) rt_host_unregister(S.tape, PREP.buf); munmap(PREP.buf, PREP.bytes); PREP.buf = NULLP; }
       else PREP.buf = NULLP; }                                  /* the results live there from now on */
    if (rc == RT_ERR_OVERFLOW) rc = rt_bulk_fetch(S.bulk[ps0].bulk);   /* more events than expected: the library maps what is needed */
    rt_set_option(RT_OPT_SHARED_RESULTS, 0);

@@ -430,3 +430,61 @@ def test_decodable_gcr_tape_cuda_equals_oracle_and_digest(cuda_lib, oracle_lib):
     rep = verify.verify_periodic(oracle_lib, bulk, desc, cfgs[0], tile, tg.nrows)
     bulk.free(); tg.close(); to.close()
     assert rep["ok"], rep
+
+
+def test_fused_ingest_masks_equal_the_separate_pass(cuda_lib, capfd):
+    """rt_prepare(): the ingest kernel writes the candidate / canonical bit planes while a tile is on chip.  The planes must equal the
+    separate mask pass word for word (RT_PREMASK_CHECK compares them on every adopting scan) and the scan results must not change:
+    synthetic tape attached in one piece and uploaded in odd chunks, and the 9-track NRZI captures."""
+    from readtape_b200 import parmsets, synth, tbin
+    import torch
+    tile = synth.nrzi_tile()
+    hdr = synth.nrzi_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
+    rows = np.concatenate([tile] * 8)[:9_700_123]                    # not a whole number of ingest tiles
+    os.environ["RT_PREMASK_CHECK"] = "1"
+    try:
+        def snapshot(tape):
+            bulk = tape.bulk_scan([cfg]); st = bulk.stats()
+            units = _all_units(bulk)
+            evs = [bulk.lookup(0, u["row0"]) for u in units[::7]]
+            bulk.free()
+            return st.events, st.units, units, [(e[0].tobytes(), e[1]) for e in evs]
+        plain = cuda_lib.open(desc); plain.upload(rows); want = snapshot(plain); plain.close()
+        # (a) device-resident rows attached in one call, twice (the second attach has the thresholds from the start)
+        t1 = cuda_lib.open(desc); t1.prepare(cfg)
+        dev = torch.from_numpy(rows).cuda()
+        for _ in range(2):
+            t1.clear(); t1.attach_device(dev.data_ptr(), rows.shape[0])
+            assert snapshot(t1) == want
+        t1.close()
+        # (b) host rows in chunks of odd sizes
+        t2 = cuda_lib.open(desc); t2.prepare(cfg)
+        at = 0
+        for n in (3_000_000, 2048 * 700, 1_234_567, 10**9):
+            t2.upload(rows[at:at + n]); at += n
+        assert snapshot(t2) == want
+        t2.close()
+        err = capfd.readouterr().err
+        assert err.count("fused mask planes identical") >= 3, err[-800:]
+        fused = [int(x.split(",")[1].split()[0]) for x in err.split("identical to the separate pass (")[1:]]
+        assert max(fused) > 4_000_000, fused
+        # (c) real captures (NRZI 800 BPI, window 13)
+        for name in ("Microdata_20blks.nm_tap", "PLAGO_beginning.nm_tap"):
+            doc, segs, heads, crow = load_capture(name)
+            d2 = evlog.desc_from_heads(heads)
+            seg = [s for s in segs if s.reset_kind == abi.RT_RESET_FULL and not (s.flags & abi.RT_F_DENSITY_DETECT)][0]
+            c2 = evlog.cfg_for(seg)
+            res = []
+            for prep in (False, True):
+                tp = cuda_lib.open(d2)
+                if prep:
+                    tp.prepare(c2)
+                tp.upload(crow)
+                bulk = tp.bulk_scan([c2]); st = bulk.stats(); units = _all_units(bulk)
+                res.append((st.events, units, [bulk.lookup(0, u["row0"])[0].tobytes() for u in units]))
+                bulk.free(); tp.close()
+            assert res[0] == res[1], name
+    finally:
+        os.environ.pop("RT_PREMASK_CHECK", None)
