@@ -729,14 +729,18 @@ def main():
         ms_masks = float(np.mean([s.ms_masks for s in stats]))
         ms_records = float(np.mean([s.ms_records for s in stats]))
         force = os.environ.get("RT_SCAN")
-        two_pass = ms_masks > 0
+        two_pass = ms_masks > 0 or bool(stats[-1].two_pass)
+        fused = bool(stats[-1].masks_fused)
         alg_bytes = 2.0 * tsamp + 32.0 * events                # 2 B read per track-sample + event bytes
         ingest_bytes = 4.0 * tsamp                              # K1: 2 B read + 2 B written per track-sample
         # per-kernel algorithmic bytes: phase A reads every sample once and writes 3 bits per track-sample;
         # phase B reads those 3 bits and writes the events
         kernels = {"k_ingest_tma": (ms_ingest, ingest_bytes)}
-        if two_pass:
+        if fused:                                               # phase A runs inside the ingest kernel: 2 B read + 2 B planes + 0.375 B bit planes written per track-sample
+            kernels = {"k_ingest_masks_tma": (ms_ingest, 4.375 * tsamp)}
+        if two_pass and not fused:
             kernels["k_peak_masks"] = (ms_masks, 2.375 * tsamp)
+        if two_pass:
             if ms_records > 0:
                 # phase B1 reads the candidate plane and, per candidate, its window, and writes a 24-byte record; phase B2 reads the
                 # records and writes the events (the candidate count is ~2 per event; counted as 2 here)
@@ -746,9 +750,10 @@ def main():
                 kernels["k_units_sparse"] = (ms_scan - ms_masks, 0.375 * tsamp + 32.0 * events)
         else:
             kernels["k_units_scan (generic)" if force == "generic" else "k_units_fast"] = (ms_scan, alg_bytes)
-        scan_kernel = max((k for k in kernels if k != "k_ingest_tma"), key=lambda k: kernels[k][0])
-        if kernels["k_ingest_tma"][0] > kernels[scan_kernel][0]:
-            scan_kernel = "k_ingest_tma"
+        ingest_name = "k_ingest_masks_tma" if fused else "k_ingest_tma"
+        scan_kernel = max((k for k in kernels if k != ingest_name), key=lambda k: kernels[k][0])
+        if kernels[ingest_name][0] > kernels[scan_kernel][0]:
+            scan_kernel = ingest_name
         dom_ms, dom_bytes = kernels[scan_kernel]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         traffic = None                                            # DRAM bytes of that kernel per launch, from the committed ncu capture

@@ -266,6 +266,8 @@ typedef struct rt_bulk_stats {
    uint64_t d2h_bytes;       /* bytes rt_bulk_fetch() copied to the host                     */
    double   ms_masks;        /* device time: candidate-mask pass of the two-pass peak scan (a part of ms_scan; 0 if not used) */
    double   ms_records;      /* device time: candidate-record pass (phase B1) of the two-pass peak scan (a part of ms_scan; 0 if not used) */
+   uint32_t masks_fused;     /* 1: the mask planes came from the ingest kernel (rt_prepare), ms_masks is 0 and their time is in ms_preprocess */
+   uint32_t two_pass;        /* 1: the two-pass peak scan (K3c) was used */
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);
 

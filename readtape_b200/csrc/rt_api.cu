@@ -991,6 +991,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    lap("counters");
    b->stats.track_samples = nrows * nt * ncfgs;
    b->stats.launches = (uint32_t)(t->launches - launches0);
+   for (auto &m : msets) { b->stats.two_pass = 1; if (m.borrowed) b->stats.masks_fused = 1; }
    if (ncfgs == 1) { t->hist_rows = nrows; t->hist_units = b->cfgs[0].nunits; t->hist_chunks = b->chunks_used; }   /* sizes the streamed scan */
    cleanup();
 #undef CUB
@@ -1264,6 +1265,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    b->stats.track_samples = nrows * nt; b->stats.ms_preprocess = t->ms_ingest; b->stats.ms_units = ms_units; b->stats.ms_scan = ms_scan; b->stats.ms_masks = ms_masks;
    b->stats.launches = (uint32_t)(t->launches - launches0);
    b->stats.pad = (uint32_t)seg_ev.size();                        /* segments streamed (0: the plain sequence was used) */
+   b->stats.two_pass = pl.use_sparse; b->stats.masks_fused = masks_fused;
    t->hist_rows = nrows; t->hist_units = nun; t->hist_chunks = c_done;
    release();
 #undef CUS
