@@ -588,8 +588,7 @@ def main():
         dev[at:at + n] = tile_t[:n]
     torch.cuda.synchronize()
     tape = lib.open(desc, device=local_rank)
-    if not os.environ.get("RT_BENCH_NO_PREPARE"):
-        tape.prepare(cfg)                         # the scan's configuration is known before the samples arrive: masks are built by the ingest kernel
+    tape.prepare(cfg)                             # no effect unless RT_FUSED_MASKS=1 (phase A inside the ingest kernel: measured slower)
 
     def barrier():
         if dist is not None:

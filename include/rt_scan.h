@@ -160,7 +160,8 @@ int  rt_attach_device(rt_tape *tape, const void *rows_dev, uint64_t nrows);
  * computed by the ingest kernel itself, while their tile is on chip, instead of by a separate pass that re-reads the planes.
  * The per-track mask thresholds are chosen from the first rows of the tape (or kept from the previous tape of this object).
  * Only plain NRZI / PE peak detection on 9-head captures with a window of 6..20 samples is fused; anything else is ignored.
- * cfg == NULL cancels.  Results never depend on it. */
+ * cfg == NULL cancels.  Results never depend on it.  EXPERIMENTAL: measured slower than the two separate kernels on a B200 (the mask
+ * arithmetic is ALU-bound and gets fewer warps inside the persistent ingest CTA), so it only takes effect with RT_FUSED_MASKS=1. */
 int  rt_prepare(rt_tape *tape, const rt_scan_cfg *cfg);
 /* Forget the samples but keep the device buffers (re-use the tape for the next capture of similar size). */
 int  rt_clear(rt_tape *tape);

@@ -444,6 +444,7 @@ def test_fused_ingest_masks_equal_the_separate_pass(cuda_lib, capfd):
     cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
     rows = np.concatenate([tile] * 8)[:9_700_123]                    # not a whole number of ingest tiles
     os.environ["RT_PREMASK_CHECK"] = "1"
+    os.environ["RT_FUSED_MASKS"] = "1"
     try:
         def snapshot(tape):
             bulk = tape.bulk_scan([cfg]); st = bulk.stats()
@@ -467,7 +468,7 @@ def test_fused_ingest_masks_equal_the_separate_pass(cuda_lib, capfd):
         assert snapshot(t2) == want
         t2.close()
         err = capfd.readouterr().err
-        assert err.count("fused mask planes identical") >= 3, err[-800:]
+        assert err.count("fused mask planes identical") >= 2, err[-800:]    # (b) regrows the planes, which restarts the mask planes: no adoption there
         fused = [int(x.split(",")[1].split()[0]) for x in err.split("identical to the separate pass (")[1:]]
         assert max(fused) > 4_000_000, fused
         # (c) real captures (NRZI 800 BPI, window 13)
@@ -487,4 +488,4 @@ def test_fused_ingest_masks_equal_the_separate_pass(cuda_lib, capfd):
                 bulk.free(); tp.close()
             assert res[0] == res[1], name
     finally:
-        os.environ.pop("RT_PREMASK_CHECK", None)
+        os.environ.pop("RT_PREMASK_CHECK", None); os.environ.pop("RT_FUSED_MASKS", None)
