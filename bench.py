@@ -740,7 +740,7 @@ def main():
         if two_pass and not fused:
             kernels["k_peak_masks"] = (ms_masks, 2.375 * tsamp)
         if two_pass:
-            if ms_records > 0:
+            if ms_records > 0.05:
                 # phase B1 reads the candidate plane and, per candidate, its window, and writes a 24-byte record; phase B2 reads the
                 # records and writes the events (the candidate count is ~2 per event; counted as 2 here)
                 kernels["k_cand_records"] = (ms_records, 0.125 * tsamp + 2 * events * (26.0 + 24.0))
