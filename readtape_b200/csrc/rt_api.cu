@@ -51,7 +51,7 @@ extern "C" double rt_row_time(const rt_tape_desc *d, uint64_t row) {
 extern "C" int rt_pkww_width(const rt_scan_cfg *cfg, uint64_t tdelta_ns) { return rtcfg::pkww_width(cfg, tdelta_ns); }
 
 /* ---- tape ---------------------------------------------------------------------------------------- */
-#define RT_RING_SLOTS 8
+#define RT_RING_SLOTS 16      /* one reader thread fills a slot at ~2 GB/s from the page cache: the slots in flight set the file -> GPU rate */
 struct rt_tape {
    rt_tape_desc desc{};
    int device = 0, sms = 148;
@@ -254,7 +254,7 @@ static int upload_pageable(rt_tape *t, const int16_t *rows, int fd, uint64_t fd_
    const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
    const char *env = getenv("RT_UPLOAD_THREADS");
    const int hw = (int)std::thread::hardware_concurrency();
-   int nthreads = env && atoi(env) > 0 ? atoi(env) : std::max(4, std::min(12, hw - 2));
+   int nthreads = env && atoi(env) > 0 ? atoi(env) : std::max(4, std::min(RT_RING_SLOTS - 2, hw - 2));
    std::atomic<int> io_error{0};
    nthreads = std::max(1, std::min<int>(nthreads, (int)std::min<uint64_t>(nchunks, 16)));
    std::mutex mu; std::condition_variable cv;
