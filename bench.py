@@ -757,7 +757,7 @@ def main():
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         traffic = None                                            # DRAM bytes of that kernel per launch, from the committed ncu capture
         try:
-            with open(os.path.join(ROOT, "profiles", "summary_r01.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "summary_r02.json")) as fh:
                 prof = json.load(fh).get(scan_kernel)
             if prof and prof["rows"] == rows:
                 traffic = prof["dram_read_bytes"] + prof["dram_write_bytes"]
