@@ -219,13 +219,19 @@ static int tape_drain(rt_tape *t) {
 static int stage_prepare(rt_tape *t, uint64_t nrows, uint64_t *stage_rows) {
    const uint64_t nh = t->desc.nheads;
    const uint64_t chunk_rows = (uint64_t)2048 * 1024;                       /* 2 Mi rows: 36 MiB for 9 heads */
+   const size_t need = std::max((size_t)std::min(chunk_rows, nrows + 2048) * nh * 2 + 256, (size_t)1 << 20);
+   if (t->d_stage[0] && need > t->stage_bytes) {
+      /* a small first upload sized the staging buffers: regrow them for this one (a 1.1 G-row tape went through in 57 k-row
+         chunks otherwise); the pinned ring of the pageable path follows */
+      CU(cudaStreamSynchronize(t->stream)); CU(cudaStreamSynchronize(t->s_copy));
+      for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); t->d_stage[i] = nullptr; }
+      if (t->h_ring) { cudaFreeHost(t->h_ring); t->h_ring = nullptr; } }
    if (!t->d_stage[0]) {
-      size_t need = (size_t)std::min(chunk_rows, nrows + 2048) * nh * 2 + 256;
-      t->stage_bytes = std::max(need, (size_t)1 << 20);
-      CU(cudaStreamCreateWithFlags(&t->s_copy, cudaStreamNonBlocking));
+      t->stage_bytes = need;
+      if (!t->s_copy) CU(cudaStreamCreateWithFlags(&t->s_copy, cudaStreamNonBlocking));
       for (int i = 0; i < 2; ++i) {
          CU(cudaMalloc(&t->d_stage[i], t->stage_bytes));
-         CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming)); } }
+         if (!t->stage_done[i]) { CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming)); } } }
    *stage_rows = (t->stage_bytes - 256) / (nh * 2) / 2048 * 2048;
    return RT_OK; }
 
@@ -250,7 +256,7 @@ static int upload_pageable(rt_tape *t, const int16_t *rows, int fd, uint64_t fd_
    const size_t slot_bytes = (size_t)stage_rows * nh * 2;
    if (!t->h_ring) {
       CU(cudaHostAlloc(&t->h_ring, slot_bytes * NB, cudaHostAllocDefault));
-      for (int i = 0; i < NB; ++i) CU(cudaEventCreateWithFlags(&t->ring_done[i], cudaEventDisableTiming)); }
+      for (int i = 0; i < NB; ++i) if (!t->ring_done[i]) CU(cudaEventCreateWithFlags(&t->ring_done[i], cudaEventDisableTiming)); }
    const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
    const char *env = getenv("RT_UPLOAD_THREADS");
    const int hw = (int)std::thread::hardware_concurrency();
