@@ -513,6 +513,99 @@ def bench_gcr(args, rank, world, local_rank, W, K):
         sys.exit(1)
 
 
+def bench_csv(args, K, W):
+    """the CSV ingest.  The reference's csvtbin (src/csvtbin.c) turns the logic analyser's text export into the TBIN
+    readtape reads, one fgets + ntrks scanfast_float per line on one core.  Workload: the text of the synthetic 9-track NRZI tape
+    (bench tile, "%12.8f, " + 9 x "%9.5f, " per line = 114 bytes per sample, the layout csvtbin's own TBIN -> CSV direction writes),
+    `--rows` lines (default 16 Mi = 1.9 GB of text).  value: conversion with the text resident on the device (k_csv_parse, timed by
+    the library's CUDA events on its stream); e2e: host text -> rt_csv_open (upload + line index) -> csv_preread's maximum ->
+    rt_csv_convert -> int16 rows back in pinned host memory.  cpu_baseline: the unmodified csvtbin_ref on a file of the first 2 Mi
+    lines (its preread pass + conversion + .tbin written to /dev/shm)."""
+    import torch
+    from readtape_b200 import csvtbin
+    lib = abi.load_product()
+    nlines = args.rows if args.rows != FULL_ROWS else 16 << 20
+    tile = synth.nrzi_tile()
+    maxvolts = synth.nrzi_header().maxvolts
+    ttext = synth.csv_from_rows(tile, maxvolts, 0, 1280)
+    head_len = int(np.flatnonzero(ttext == 10)[1]) + 1
+    body = ttext[head_len:]
+    per = tile.shape[0]
+    reps = (nlines + per - 1) // per
+    text = np.concatenate([ttext[:head_len]] + [body] * reps)[:head_len + nlines * (len(body) // per)]
+    line_bytes = len(body) // per
+    ntrks = 9
+    out = torch.empty((nlines, ntrks), dtype=torch.int16).pin_memory()
+
+    def e2e_step():
+        with lib.csv_open(text) as c:
+            pre = csvtbin.preread(c, ntrks)
+            cfg = abi.make_csv_cfg(ntrks, float(pre.maxvolts))
+            st = abi.CsvStats()
+            lib.check(lib.L.rt_csv_convert(c.h, ctypes.byref(cfg), 2, nlines, out.data_ptr(), None, ctypes.byref(st)))
+        return pre, st
+
+    pre, st = e2e_step()
+    # parity at full size: every line of the text is a line of the tile, whose conversion the CPU oracle gives
+    ora = abi.load_oracle()
+    with ora.csv_open(ttext) as c:
+        tile_rows, _ = c.convert(abi.make_csv_cfg(ntrks, float(pre.maxvolts)), 2, per)
+    got = out.numpy()
+    ok = all(np.array_equal(got[a:a + per], tile_rows[:min(per, nlines - a)]) for a in range(0, nlines, per))
+    for _ in range(W):
+        e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / K
+    # resident: the text stays on the device, the rows stay on the device
+    sampler = ClockSampler(0)
+    with lib.csv_open(text) as c:
+        cfg = abi.make_csv_cfg(ntrks, float(pre.maxvolts))
+        ms = []
+        for _ in range(W):
+            c.convert(cfg, 2, nlines, want_rows=False)
+        sampler.start(); time.sleep(0.25)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(K):
+            _, s = c.convert(cfg, 2, nlines, want_rows=False)
+            ms.append(float(s.ms_convert))
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / K
+    clocks = sampler.stop()
+    ms_k = float(np.mean(ms))
+    peak, peak_src = measured_peak()
+    alg = float(nlines) * (line_bytes + 2 * ntrks)
+    cpu = None
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "csvtbin_ref")
+    if not args.no_cpu and os.path.exists(ref_tool):
+        wd = tempfile.mkdtemp(prefix="rtcsv_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            n_ref = min(nlines, 2 << 20)
+            text[:head_len + n_ref * line_bytes].tofile(os.path.join(wd, "sample.csv"))
+            t0 = time.perf_counter()
+            subprocess.run([ref_tool, "-ntrks=9", "-nrzi", "sample"], cwd=wd, check=True, capture_output=True)
+            ref_s = time.perf_counter() - t0
+            cpu = {"value": n_ref * ntrks / ref_s, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"csvtbin_ref (unmodified csvtbin 1.12) on the first {n_ref} lines ({n_ref * line_bytes / 1e6:.0f} MB of text in /dev/shm): preread + conversion + .tbin written, {ref_s:.2f} s"}
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+    line = {"metric": "track-samples/s, CSV text -> TBIN int16 rows (csvtbin's conversion), 9-track capture export", "value": nlines * ntrks / (ms_k * 1e-3), "unit": UNIT,
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"text export of the synthetic 9-track NRZI tape: {nlines} lines x {line_bytes} bytes = {nlines * line_bytes / 1e9:.2f} GB of CSV -> {nlines * ntrks * 2 / 1e9:.2f} GB of int16 rows",
+                       "l2": "inputs far larger than the 126 MB L2", "verified": {"ok": bool(ok), "how": "every tile of the output equals the CPU oracle's conversion of the tile's text (oracle/csv_oracle.c)"},
+                       "wall_ms_per_resident_step": 1e3 * dt, "too_big": int(st.too_big), "too_small": int(st.too_small)},
+            "roofline": {"bound": "hbm", "kernel": "k_csv_parse (one thread per line)", "achieved": alg / (ms_k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms_k * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_k,
+                         "algorithmic_bytes": f"{line_bytes} text bytes read + {2 * ntrks} row bytes written per line"},
+            "e2e": {"value": nlines * ntrks / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(text.size), "d2h_bytes_per_step": int(nlines * ntrks * 2), "ms_per_step": 1e3 * e2e_s,
+                    "what": "rt_csv_open (pageable host text -> device, line index) + rt_csv_max_abs over the first 999,999 lines + rt_csv_convert + rows to pinned host memory"},
+            "gpu_launches": K, "clocks": clocks, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if not ok:
+        sys.exit(1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -521,7 +614,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=int(os.environ.get("RT_BENCH_ROWS", FULL_ROWS)))
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="nrzi", choices=["nrzi", "gcr", "pe", "ww"],
+    ap.add_argument("--workload", default="nrzi", choices=["nrzi", "gcr", "pe", "ww", "csv"],
                     help="nrzi: BASELINE config 2 (the headline line); gcr: config 4, GCR-density tape x 5 parameter sets sharded over the GPUs; "
                          "pe: config 3, examples/9trk_PE with 8 parameter sets fanned out on one GPU; ww: config 5, the Whirlwind reel on the exact stateful scan")
     ap.add_argument("--split", default="replicas", choices=["replicas", "one-tape"],
@@ -543,6 +636,10 @@ def main():
     if args.workload in ("pe", "ww"):
         if rank == 0:
             bench_capture(args, K, W)
+        return
+    if args.workload == "csv":
+        if rank == 0:
+            bench_csv(args, K, W)
         return
     tile = synth.nrzi_tile()
     nproc = os.cpu_count() or 1

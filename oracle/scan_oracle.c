@@ -65,6 +65,9 @@ static int set_err(int code, const char *fmt, ...) {
    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
    return code; }
 const char *rt_last_error(void) { return g_err; }
+__attribute__((visibility("hidden"))) int oracle_fail(int code, const char *fmt, ...) {      /* for csv_oracle.c */
+   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+   return code; }
 int rt_abi_version(void) { return RT_ABI_VERSION; }
 const char *rt_backend(void) { return "oracle-cpu"; }
 

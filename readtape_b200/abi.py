@@ -71,7 +71,20 @@ EXPORTS = ["rt_last_error", "rt_abi_version", "rt_backend", "rt_open", "rt_uploa
            "rt_nrows", "rt_close", "rt_host_alloc", "rt_host_free", "rt_scan_begin", "rt_scan_reset",
            "rt_scan_run", "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_scan_pos", "rt_scan_end",
            "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_fetch", "rt_bulk_results_size", "rt_bulk_results_to_device", "rt_bulk_fetch_to", "rt_host_register", "rt_host_unregister", "rt_bulk_lookup", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_bulk_get_stats", "rt_bulk_free", "rt_bulk_tile_digest", "rt_bulk_last_unit", "rt_set_option", "rt_peak_masks", "rt_pkww_width",
-           "rt_row_time"]
+           "rt_row_time",
+           "rt_csv_open", "rt_csv_close", "rt_csv_nlines", "rt_csv_line", "rt_csv_max_abs", "rt_csv_convert"]       # include/rt_csv.h
+
+
+class CsvCfg(C.Structure):
+    """rt_csv_cfg (include/rt_csv.h)"""
+    _fields_ = [("ntrks", C.c_uint32), ("track_permutation", C.c_uint32 * RT_MAXTRKS), ("maxvolts", C.c_float),
+                ("scalefactor", C.c_float), ("invert", C.c_uint32), ("subsample", C.c_uint32)]
+
+
+class CsvStats(C.Structure):
+    """rt_csv_stats (include/rt_csv.h)"""
+    _fields_ = [("rows", C.c_uint64), ("too_big", C.c_uint64), ("too_small", C.c_uint64), ("minvolts", C.c_float),
+                ("maxvolts", C.c_float), ("ms_convert", C.c_double)]
 
 
 class RtError(RuntimeError):
@@ -126,6 +139,12 @@ class Lib:
         L.rt_peak_masks.argtypes = [vp, P(ScanCfg), C.c_float, vp, vp, u64, P(C.c_int32)]
         L.rt_pkww_width.argtypes = [P(ScanCfg), u64]
         L.rt_row_time.argtypes = [P(TapeDesc), u64]; L.rt_row_time.restype = C.c_double
+        L.rt_csv_open.argtypes = [i32, vp, u64, P(vp)]; L.rt_csv_open.restype = i32
+        L.rt_csv_close.argtypes = [vp]; L.rt_csv_close.restype = None
+        L.rt_csv_nlines.argtypes = [vp]; L.rt_csv_nlines.restype = u64
+        L.rt_csv_line.argtypes = [vp, u64, P(u64), P(u64)]; L.rt_csv_line.restype = i32
+        L.rt_csv_max_abs.argtypes = [vp, u64, u64, u32, C.c_float, P(C.c_float)]; L.rt_csv_max_abs.restype = i32
+        L.rt_csv_convert.argtypes = [vp, P(CsvCfg), u64, u64, vp, vp, P(CsvStats)]; L.rt_csv_convert.restype = i32
         for fn in ("rt_open", "rt_upload", "rt_upload_fd", "rt_attach_device", "rt_prepare", "rt_clear", "rt_bulk_fetch", "rt_scan_begin", "rt_scan_reset", "rt_scan_run",
                    "rt_scan_rewind", "rt_scan_set_avg_height", "rt_scan_set_cfg", "rt_bulk_scan", "rt_bulk_scan_host", "rt_bulk_lookup",
                    "rt_bulk_get_stats", "rt_bulk_unit_info", "rt_bulk_unit_at", "rt_pkww_width", "rt_peak_masks"):
@@ -144,6 +163,58 @@ class Lib:
         h = C.c_void_p()
         self.check(self.L.rt_open(C.byref(desc), device, C.byref(h)))
         return Tape(self, h, desc)
+
+
+    def csv_open(self, text, device: int = 0) -> "Csv":
+        """CSV text (bytes / bytearray / uint8 array / mmap) onto the device, lines indexed (rt_csv_open)"""
+        buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+        h = C.c_void_p()
+        self.check(self.L.rt_csv_open(device, buf.ctypes.data, buf.size, C.byref(h)))
+        return Csv(self, h, buf)
+
+
+class Csv:
+    """A CSV capture on the device (include/rt_csv.h).  `text` keeps the host copy alive for line()."""
+
+    def __init__(self, lib: "Lib", handle, text: np.ndarray):
+        self.lib, self.h, self.text = lib, handle, text
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.L.rt_csv_close(self.h); self.h = None
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+
+    @property
+    def nlines(self) -> int:
+        return int(self.lib.L.rt_csv_nlines(self.h))
+
+    def line(self, i: int) -> bytes:
+        off, ln = C.c_uint64(), C.c_uint64()
+        self.lib.check(self.lib.L.rt_csv_line(self.h, i, C.byref(off), C.byref(ln)))
+        return bytes(self.text[off.value:off.value + ln.value])
+
+    def max_abs(self, first_line: int, nlines: int, ntrks: int, scalefactor: float = 1.0) -> np.float32:
+        out = C.c_float()
+        self.lib.check(self.lib.L.rt_csv_max_abs(self.h, first_line, nlines, ntrks, scalefactor, C.byref(out)))
+        return np.float32(out.value)
+
+    def convert(self, cfg: CsvCfg, first_line: int, nrows: int, tape: "Tape | None" = None, want_rows: bool = True):
+        """(rows int16 [nrows, ntrks] or None, CsvStats): the conversion loop of write_tbin (rt_csv_convert)"""
+        rows = np.empty((nrows, cfg.ntrks), dtype="<i2") if want_rows else None
+        st = CsvStats()
+        self.lib.check(self.lib.L.rt_csv_convert(self.h, C.byref(cfg), first_line, nrows, rows.ctypes.data if want_rows and nrows else None,
+                                                 tape.h if tape is not None else None, C.byref(st)))
+        return rows, st
+
+
+def make_csv_cfg(ntrks: int, maxvolts: float, order=None, scalefactor: float = 1.0, invert: bool = False, subsample: int = 1) -> CsvCfg:
+    c = CsvCfg()
+    c.ntrks = ntrks; c.maxvolts = maxvolts; c.scalefactor = scalefactor; c.invert = int(invert); c.subsample = subsample
+    for i in range(ntrks):
+        c.track_permutation[i] = i if order is None else order[i]
+    return c
 
 
 def _events_from(ptr: C.c_void_p, n: int) -> np.ndarray:

@@ -59,6 +59,15 @@ cudaError_t launch_cand_records(const DevCfg &c, uint64_t row_lo, uint64_t row_h
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s);
+/* k_csv.cu: CSV ingest (line index, csv_preread's maximum, parse + quantise) */
+uint32_t csv_index_warps(uint64_t nbytes);      /* scratch entries launch_csv_count / launch_csv_index need: round up to a multiple of 8 */
+cudaError_t launch_csv_count(const char *txt, uint64_t n, uint32_t *warp_counts, uint64_t *warp_offsets, uint64_t *total, cudaStream_t s);
+cudaError_t launch_csv_index(const char *txt, uint64_t n, const uint64_t *warp_offsets, uint64_t *line_start, uint64_t cap, cudaStream_t s);
+cudaError_t launch_csv_maxabs(const char *txt, uint64_t n, const uint64_t *line_start, uint64_t nlines_total, uint64_t first_line, uint64_t nlines,
+                              int ntrks, float scalefactor, float *out, cudaStream_t s);
+cudaError_t launch_csv_parse(const char *txt, uint64_t n, const uint64_t *line_start, uint64_t nlines_total, int ntrks, const uint32_t *perm,
+                             float maxvolts, float scalefactor, int invert, uint32_t subsample, uint64_t first_line, uint64_t nrows,
+                             int16_t *rows, unsigned long long *stats, float *fstats, cudaStream_t s);
 /* k_digest.cu: per-tile event counts and order-independent digests of a finished whole-tape scan (verification at scale) */
 cudaError_t launch_tile_digest(const DevCfg &c, const UnitDesc *units, uint32_t nunits, const TrkMeta *meta, const rt_event *pool,
                                const uint32_t *chunk_next, uint64_t period, uint64_t ntiles, unsigned long long *counts,

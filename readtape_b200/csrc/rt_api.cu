@@ -23,6 +23,7 @@
 #include "scan_records.cuh"
 #include "kernels.h"
 #include "cfg_host.h"
+#include "rt_internal.h"
 
 using rtgen::SkewState;
 
@@ -35,6 +36,9 @@ static int set_err(int code, const char *fmt, ...) {
       return set_err(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 extern "C" const char *rt_last_error(void) { return g_err; }
+int rt_fail(int code, const char *fmt, ...) {                     /* rt_internal.h: set_err for the other translation units */
+   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+   return code; }
 
 /* process-wide options (rt_set_option) */
 static int g_opt_shared_results = 0;

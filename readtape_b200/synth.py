@@ -294,3 +294,42 @@ def gcr_tile(seed: int = 0xC0FFEE, nblocks: int = 8, data_bytes: int = 4095, gap
     q = np.rint(volts / 3.2 * 32767.0)
     np.clip(q, -32767, 32767, out=q)
     return np.ascontiguousarray(q.T.astype("<i2"))
+
+
+def csv_from_rows(rows: np.ndarray, maxvolts: float, tstart_ns: int = 0, tdelta_ns: int = 1280, decimals: int = 5,
+                  title: str = "'synthetic capture") -> np.ndarray:
+    """The text a logic analyser would export for these int16 rows (uint8 array): two title lines, then per sample
+    "%12.8f, " of the time and "%9.5f, " per track of row/32767*maxvolts -- the layout the reference's own TBIN -> CSV
+    direction writes (csvtbin.c:579-590), produced with integer arithmetic on whole arrays.  Used as INPUT of the CSV ingest
+    (tests, bench); what matters is that it is realistic text, not that it round-trips."""
+    rows = np.asarray(rows)
+    n, nt = rows.shape
+    head = (title + "\n" + "Time, " + ", ".join(f"Track {i}" for i in range(nt)) + "\n").encode()
+    tw, vw = 12 + 2, 9 + 2                                   # field widths with the ", " separator
+    line = np.full((n, tw + nt * vw + 1), ord(" "), dtype=np.uint8)
+    line[:, -1] = ord("\n")
+    # time: seconds with 8 decimals, right-aligned in 12
+    t = (tstart_ns + tdelta_ns * np.arange(n, dtype=np.int64) + 5) // 10          # units of 1e-8 s
+    for k in range(8):
+        line[:, 11 - k] = ord("0") + (t % 10); t //= 10
+    line[:, 3] = ord(".")
+    for k in range(3):                                        # up to 999 s
+        d = t % 10; t //= 10
+        line[:, 2 - k] = np.where((d > 0) | (t > 0) | (k == 0), ord("0") + d, ord(" "))
+    line[:, 12] = ord(",")
+    scale = 10 ** decimals
+    v = np.rint(rows.astype(np.float64) / 32767.0 * maxvolts * scale).astype(np.int64)
+    neg = v < 0
+    a = np.abs(v)
+    base = tw
+    for c in range(nt):
+        col = a[:, c].copy()
+        o = base + c * vw
+        for k in range(decimals):
+            line[:, o + 8 - k] = ord("0") + (col % 10); col //= 10
+        line[:, o + 8 - decimals] = ord(".")
+        line[:, o + 7 - decimals] = ord("0") + (col % 10); col //= 10
+        line[:, o + 6 - decimals] = np.where(col > 0, ord("0") + (col % 10), np.where(neg[:, c], ord("-"), ord(" ")))
+        line[:, o + 5 - decimals] = np.where((col > 0) & neg[:, c], ord("-"), ord(" "))
+        line[:, o + 9] = ord(",")
+    return np.concatenate([np.frombuffer(head, dtype=np.uint8), line.reshape(-1)])

@@ -1,4 +1,4 @@
-"""The C-ABI boundary: both libraries export every symbol include/rt_scan.h declares."""
+"""The C-ABI boundary: both libraries export every symbol include/*.h declare."""
 import ctypes
 import os
 import re
@@ -10,7 +10,7 @@ from readtape_b200 import abi
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "rt_scan.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))) if h.endswith(".h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", text)))
 
