@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "kernels.h"
+#include "tma_1d.cuh"
 
 #define CSV_THREADS 256
 #define CSV_WARP_BYTES (128u << 10)                         /* text per warp in the indexing kernels: 256 coalesced 512-byte reads */
@@ -184,40 +185,129 @@ __device__ __forceinline__ int16_t quantise(float fsample, const CsvParseArgs &a
    if (sample >= 32767) { sample = 32767; ++big; }
    return (int16_t)sample; }
 
-/* stats: [0] too big, [1] too small (u64); fstats: [0] max volts (>= 0), [1] -min volts (>= 0) */
-template <bool IDENTITY>
-__global__ void __launch_bounds__(CSV_THREADS)
+/* ---- the conversion kernel ------------------------------------------------------------------------------------------------------
+ * One block = CSV_PB consecutive rows = (without -subsample) one contiguous piece of text, ~14 KB for a 9-track export.  The bulk
+ * copy engine brings that piece into shared memory in one cp.async.bulk (coalesced, no L1 thrash from 128 threads walking 128
+ * different cache lines a byte at a time); each thread then reads ITS line through a 4-byte window: one aligned 32-bit shared-memory
+ * load per 4 characters, issued a whole word ahead of its use, so the scanner's character-by-character dependency chain is register
+ * shifts, not memory latency.  The finished rows go to shared memory and leave as one coalesced store per block.
+ * A block whose text does not fit the stage (long lines, -subsample) falls back to the scanner that reads global memory. */
+#define CSV_PB 128
+#define CSV_STAGE_BYTES (CSV_PB * 160)                      /* 20 KB: lines of up to 160 characters on average */
+
+/* One line through the reference's scanner, written as a state machine that takes one character per turn so that the threads of a
+ * warp stay together: the calls  scanfast_double(&p); scanfast_float(&p) x ntrks  (csvtbin.c:691-693) see the line as
+ *      field := [ ,]* -? digit* ( . digit* )?
+ * repeated, each field starting at the character that ended the one before.  State 0 = in the leading blanks / commas of a field,
+ * 1 = after the sign or in the integer digits, 2 = in the fraction digits.  A character that can start nothing ('\n', a letter)
+ * leaves this field and every later one 0, as the reference's scanner returns 0 without advancing.
+ * The characters come four at a time: `cur` = the next 4 characters of the line whatever its alignment (funnel shift of two aligned
+ * shared-memory words, the following word already loaded), consumed by four unrolled copies of the step; a digit -- three
+ * characters in four -- takes the short branch.  vals[f * CSV_PB] receives field f (the time stamp, field -1, is dropped). */
+struct LineScan {
+   int field, state, k, ntrks;
+   float n;
+   bool negative;
+   float *vals;
+   const float *frac;
+
+   /* a character that is not a digit; false = the line is finished (all fields done, or nothing more can be scanned) */
+   __device__ __forceinline__ bool other(unsigned c) {
+      if (state == 1 && c == '.') { state = 2; return true; }
+      if (state != 0) {                                       /* the field ends here; c is looked at again as the start of the next */
+         if (field >= 0) vals[field * CSV_PB] = negative ? -n : n;
+         if (++field == ntrks) return false;
+         n = 0; negative = false; k = 0; state = 0; }
+      if (c == ' ' || c == ',') return true;
+      if (c == '-') { negative = true; state = 1; return true; }
+      if (c == '.') { state = 2; return true; }
+      return false; }
+
+   __device__ __forceinline__ bool step(unsigned c) {
+      const unsigned d = c - '0';
+      if (d < 10u) {
+         if (state == 2) { n += frac[k + d]; k = min(k + 10, 10 * (CSV_FRAC_ROWS - 1)); }
+         else { n = n * 10 + digit_value(d); state = 1; }
+         return true; }
+      return other(c); }
+
+   __device__ __forceinline__ void run(const unsigned char *stage, uint32_t off) {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(stage) + (off >> 2);
+      const uint32_t sh = 8 * (off & 3u);
+      uint32_t w0 = w[0], last = w[1]; w += 2;
+      uint32_t cur = __funnelshift_r(w0, last, sh);
+      field = -1; state = 0; k = 0; n = 0; negative = false;
+      for (;;) {
+         const uint32_t v = *w++;                             /* the word after next: its latency hides behind four characters */
+         const uint32_t nxt = __funnelshift_r(last, v, sh);
+         last = v;
+         if (!step(cur & 0xffu)) break;
+         if (!step(cur >> 8 & 0xffu)) break;
+         if (!step(cur >> 16 & 0xffu)) break;
+         if (!step(cur >> 24)) break;
+         cur = nxt; }
+      for (int f = field < 0 ? 0 : field; f < ntrks; ++f) vals[f * CSV_PB] = 0.0f; } };
+
+/* stats: [0] too big, [1] too small (u64); fstats: [0] max volts (>= 0), [1] -min volts (>= 0)
+   dynamic shared memory: stage[CSV_STAGE_BYTES + 32] | frac[CSV_FRAC_ROWS * 10] | mbarrier | vals[ntrks][CSV_PB] floats;
+   the finished rows reuse the stage */
+static size_t csv_parse_smem(int ntrks) { return CSV_STAGE_BYTES + 32 + (size_t)ntrks * CSV_PB * 4 + CSV_FRAC_ROWS * 10 * 4 + 16; }
+
+__global__ void __launch_bounds__(CSV_PB, 8)
 k_csv_parse(const char *txt, uint64_t n, const uint64_t *line_start, uint64_t nlines_total, const __grid_constant__ CsvParseArgs a, uint64_t nrows,
             int16_t *rows, unsigned long long *stats, float *fstats) {
-   __shared__ float frac[CSV_FRAC_ROWS * 10];
-   fill_frac_table(frac);
-   const uint64_t r = (uint64_t)blockIdx.x * CSV_THREADS + threadIdx.x;
-   unsigned big = 0, small_ = 0; float vmax = 0, vmin = 0;
-   if (r < nrows) {
-      /* csvtbin.c:686: of every `subsample` lines the LAST one is used */
-      const uint64_t line = a.first_line + (r + 1) * a.subsample - 1;
-      int16_t *out = rows + r * (uint64_t)a.ntrks;
+   extern __shared__ __align__(128) unsigned char smem[];
+   unsigned char *stage = smem;
+   float *frac = reinterpret_cast<float *>(smem + CSV_STAGE_BYTES + 32);
+   uint64_t *bar = reinterpret_cast<uint64_t *>(frac + CSV_FRAC_ROWS * 10);
+   float *vals = reinterpret_cast<float *>(bar + 2);
+   int16_t *srows = reinterpret_cast<int16_t *>(stage);
+   const uint64_t r0 = (uint64_t)blockIdx.x * CSV_PB;
+   const uint32_t nr = (uint32_t)(nrows - r0 < CSV_PB ? nrows - r0 : CSV_PB);
+   /* the text of this block's rows: from the first character of its first line to the '\n' of its last (csvtbin.c:686: of every
+      `subsample` lines the LAST one is used) */
+   const uint64_t g_lo = line_start[a.first_line + (r0 + 1) * a.subsample - 1];
+   const uint64_t g_hi = line_start[a.first_line + (r0 + nr) * a.subsample];
+   const uint64_t base = g_lo & ~15ull;
+   const uint64_t bytes = (g_hi - base + 15) & ~15ull;      /* the text buffer is padded: reading up to 31 bytes past its end is fine */
+   const bool staged = bytes <= CSV_STAGE_BYTES;
+   if (threadIdx.x == 0 && staged) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, (uint32_t)bytes);
+      tma_load_1d(stage, txt + base, (uint32_t)bytes, bar); }
+   fill_frac_table(frac);                                    /* ends with __syncthreads(): the barrier is initialised for everybody */
+   const uint32_t t = threadIdx.x;
+   float *my = vals + t;
+   if (staged) mbar_wait(bar, 0);
+   if (t < nr) {
+      const uint64_t line = a.first_line + (r0 + t + 1) * a.subsample - 1;
       uint64_t lo;
-      if (line_is_plain(line_start, line, &lo)) {
+      const bool plain = line_is_plain(line_start, line, &lo);
+      if (staged && plain) { LineScan s; s.ntrks = a.ntrks; s.vals = my; s.frac = frac; s.run(stage, (uint32_t)(lo - base)); }
+      else if (plain) {
          const unsigned char *p = reinterpret_cast<const unsigned char *>(txt) + lo;
          skip_number_fast(p);
-         if (IDENTITY) {                                        /* no -order: column k is position k, nothing to hold back */
 #pragma unroll 1
-            for (int k = 0; k < a.ntrks; ++k) out[k] = quantise(scan_float_fast(p, frac) * a.scalefactor, a, big, small_, vmin, vmax); }
-         else {
-            float samples[RT_MAXTRKS];
-#pragma unroll 1
-            for (int k = 0; k < a.ntrks; ++k) samples[a.perm[k]] = scan_float_fast(p, frac) * a.scalefactor;
-#pragma unroll 1
-            for (int k = 0; k < a.ntrks; ++k) out[k] = quantise(samples[k], a, big, small_, vmin, vmax); } }
+         for (int k = 0; k < a.ntrks; ++k) my[k * CSV_PB] = scan_float_fast(p, frac); }
       else {
          Cursor c = line_cursor(txt, n, line_start, nlines_total, line);
          skip_number(c);
-         float samples[RT_MAXTRKS];
 #pragma unroll 1
-         for (int k = 0; k < a.ntrks; ++k) samples[a.perm[k]] = scan_float(c) * a.scalefactor;
+         for (int k = 0; k < a.ntrks; ++k) my[k * CSV_PB] = scan_float(c); } }
+   __syncthreads();                                          /* everybody is done with the text: the stage becomes the rows */
+   unsigned big = 0, small_ = 0; float vmax = 0, vmin = 0;
+   if (t < nr) {
 #pragma unroll 1
-         for (int k = 0; k < a.ntrks; ++k) out[k] = quantise(samples[k], a, big, small_, vmin, vmax); } }
+      for (int k = 0; k < a.ntrks; ++k)                       /* csvtbin.c:693: column k goes to position track_permutation[k] */
+         srows[t * a.ntrks + a.perm[k]] = quantise(my[k * CSV_PB] * a.scalefactor, a, big, small_, vmin, vmax); }
+   __syncthreads();
+   {  /* the block's rows are contiguous in the output and start 16-byte aligned (128 rows x ntrks x 2 bytes per block) */
+      const uint32_t nbytes = nr * (uint32_t)a.ntrks * 2u;
+      unsigned char *dst = reinterpret_cast<unsigned char *>(rows + r0 * (uint64_t)a.ntrks);
+      const uint32_t n16 = nbytes / 16;
+      for (uint32_t i = t; i < n16; i += CSV_PB) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(srows)[i];
+      for (uint32_t i = n16 * 8 + t; i < nbytes / 2; i += CSV_PB) reinterpret_cast<int16_t *>(dst)[i] = srows[i]; }
    for (int d = 16; d > 0; d >>= 1) {
       big += __shfl_xor_sync(0xffffffffu, big, d); small_ += __shfl_xor_sync(0xffffffffu, small_, d);
       vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d)); vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d)); }
@@ -257,9 +347,9 @@ cudaError_t launch_csv_parse(const char *txt, uint64_t n, const uint64_t *line_s
    if (!nrows) return cudaSuccess;
    CsvParseArgs a; a.ntrks = ntrks; a.maxvolts = maxvolts; a.scalefactor = scalefactor; a.invert = invert; a.subsample = subsample; a.first_line = first_line;
    for (int k = 0; k < RT_MAXTRKS; ++k) a.perm[k] = k < ntrks ? perm[k] : 0;
-   bool identity = true;
-   for (int k = 0; k < ntrks; ++k) identity = identity && perm[k] == (uint32_t)k;
-   const unsigned nb = (unsigned)((nrows + CSV_THREADS - 1) / CSV_THREADS);
-   if (identity) k_csv_parse<true><<<nb, CSV_THREADS, 0, s>>>(txt, n, line_start, nlines_total, a, nrows, rows, stats, fstats);
-   else k_csv_parse<false><<<nb, CSV_THREADS, 0, s>>>(txt, n, line_start, nlines_total, a, nrows, rows, stats, fstats);
+   const unsigned nb = (unsigned)((nrows + CSV_PB - 1) / CSV_PB);
+   const size_t smem = csv_parse_smem(ntrks);
+   cudaError_t e = cudaFuncSetAttribute(k_csv_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csv_parse_smem(RT_MAXTRKS));
+   if (e != cudaSuccess) return e;
+   k_csv_parse<<<nb, CSV_PB, smem, s>>>(txt, n, line_start, nlines_total, a, nrows, rows, stats, fstats);
    return cudaGetLastError(); }

@@ -28,12 +28,16 @@ struct rt_csv {
       if (d_line_start) cudaFree(d_line_start);
       if (stream) cudaStreamDestroy(stream); } };
 
-/* pageable host memory -> device through a ring of pinned slots filled by a few threads (the same scheme as rt_upload) */
+/* pageable host memory -> device through a ring of pinned slots filled by a few threads (the same scheme as rt_upload).  Pinning
+   192 MB costs tens of milliseconds, so the ring is allocated once per process and kept (one upload at a time uses it). */
+static std::mutex g_ring_mu;
+static char *g_ring = nullptr;
 static int upload_text(rt_csv *c, const char *text, uint64_t nbytes) {
    const size_t slot = 16u << 20; const int NB = 12;
    if (nbytes <= slot) { CU(cudaMemcpyAsync(c->d_text, text, nbytes, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return RT_OK; }
-   char *ring = nullptr; cudaEvent_t done[NB];
-   CU(cudaHostAlloc(&ring, slot * NB, cudaHostAllocDefault));
+   std::lock_guard<std::mutex> ring_lock(g_ring_mu);
+   if (!g_ring) CU(cudaHostAlloc(&g_ring, slot * NB, cudaHostAllocPortable));
+   char *ring = g_ring; cudaEvent_t done[NB];
    for (int i = 0; i < NB; ++i) cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
    const uint64_t nchunks = (nbytes + slot - 1) / slot;
    const int hw = (int)std::thread::hardware_concurrency();
@@ -66,7 +70,6 @@ static int upload_text(rt_csv *c, const char *text, uint64_t nbytes) {
    for (auto &x : th) x.join();
    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
    for (int i = 0; i < NB; ++i) cudaEventDestroy(done[i]);
-   cudaFreeHost(ring);
    if (e != cudaSuccess) return rt_fail(RT_ERR_CUDA, "rt_csv_open: text upload failed: %s", cudaGetErrorString(e));
    return RT_OK; }
 
