@@ -575,6 +575,13 @@ def bench_csv(args, K, W):
     ms_k = float(np.mean(ms))
     peak, peak_src = measured_peak()
     alg = float(nlines) * (line_bytes + 2 * ntrks)
+    traffic = None
+    try:                                                    # dram bytes per line from the committed ncu capture of this kernel
+        with open(os.path.join(ROOT, "profiles", "summary_r02.json")) as fh:
+            k = json.load(fh)["k_csv_parse"]
+        traffic = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["lines"] * nlines
+    except Exception:
+        pass
     cpu = None
     ref_tool = os.path.join(ROOT, "oracle", "_ref", "csvtbin_ref")
     if not args.no_cpu and os.path.exists(ref_tool):
@@ -595,9 +602,10 @@ def bench_csv(args, K, W):
             "config": {"workload": f"text export of the synthetic 9-track NRZI tape: {nlines} lines x {line_bytes} bytes = {nlines * line_bytes / 1e9:.2f} GB of CSV -> {nlines * ntrks * 2 / 1e9:.2f} GB of int16 rows",
                        "l2": "inputs far larger than the 126 MB L2", "verified": {"ok": bool(ok), "how": "every tile of the output equals the CPU oracle's conversion of the tile's text (oracle/csv_oracle.c)"},
                        "wall_ms_per_resident_step": 1e3 * dt, "too_big": int(st.too_big), "too_small": int(st.too_small)},
-            "roofline": {"bound": "hbm", "kernel": "k_csv_parse (one thread per line)", "achieved": alg / (ms_k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms_k * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_k,
-                         "algorithmic_bytes": f"{line_bytes} text bytes read + {2 * ntrks} row bytes written per line"},
+            "roofline": {"bound": "hbm", "kernel": "k_csv_parse (one thread per line, text staged in shared memory by cp.async.bulk)", "achieved": alg / (ms_k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms_k * 1e-3) / 1e9 / peak, "traffic": traffic, "algorithmic": alg, "peak_source": peak_src, "ms_per_launch": ms_k,
+                         "algorithmic_bytes": f"{line_bytes} text bytes read + {2 * ntrks} row bytes written per line",
+                         "note": "issue-bound, not memory-bound: ~36 instructions per character at 88% issue-slot use (profiles/k_csv_parse_r02_raw.csv)"},
             "e2e": {"value": nlines * ntrks / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(text.size), "d2h_bytes_per_step": int(nlines * ntrks * 2), "ms_per_step": 1e3 * e2e_s,
                     "what": "rt_csv_open (pageable host text -> device, line index) + rt_csv_max_abs over the first 999,999 lines + rt_csv_convert + rows to pinned host memory"},
             "gpu_launches": K, "clocks": clocks, "cpu_baseline": cpu}
