@@ -73,6 +73,8 @@ static struct {
    long long base_pos;              /* file offset of row 0 */
    uint64_t nrows;                  /* rows before the end marker */
    size_t rows_bytes;               /* payload bytes uploaded */
+   long long group_bytes;           /* file bytes per row of the tape: nheads * 2 * subsample (readtape.c:1407: of every `subsample` rows the last is used) */
+   long long endfile_extra;         /* file bytes the reference has read past the last whole group when it meets the end marker */
    /* the pending reset, noted by the wrapped reset functions */
    int pending_reset;               /* RT_RESET_*; RT_RESET_NONE if none since the last readblock() */
    /* stateful exact context (Whirlwind, and the fallback for everything else) */
@@ -139,7 +141,6 @@ static void make_cfg(rt_scan_cfg *c) {
 
 static void open_tape(void) {
    assert(tbin_file, "the B200 scan reads .tbin captures only (convert CSV with csvtbin first)");
-   assert(subsample == 1, "the B200 scan does not support -subsample");
    assert(sizeof(int16_t) == 2 && nheads >= ntrks && nheads <= MAXTRKS, "bad head count %d", nheads);
    memset(&S.desc, 0, sizeof S.desc);
    S.desc.ntrks = (uint32_t)ntrks; S.desc.nheads = (uint32_t)nheads;
@@ -154,6 +155,7 @@ static void open_tape(void) {
    assert(fseeko(inf, S.base_pos, SEEK_SET) == 0, "fseek failed");
    uint64_t rowbytes = (uint64_t)nheads * 2;
    uint64_t nrows_file = (uint64_t)(end - S.base_pos) / rowbytes;
+   S.group_bytes = (long long)rowbytes * subsample; S.endfile_extra = 2;
    int dev = getenv("RT_DEVICE") ? atoi(getenv("RT_DEVICE")) : 0;
    double w1 = wall();
    int rc = rt_open(&S.desc, dev, &S.tape);
@@ -162,7 +164,23 @@ static void open_tape(void) {
    /* the payload goes to the GPU straight from the page cache: the library reads the file with a few threads into its pinned
       staging ring (no whole-file buffer, pinned or not) */
    S.rows_bytes = (size_t)(nrows_file * rowbytes);
-   if (getenv("RT_UPLOAD_MMAP") && atoi(getenv("RT_UPLOAD_MMAP"))) {   /* experiment: hand the library a mapping of the file instead */
+   if (subsample > 1) {
+      /* -subsample=n (readtape.c:1407-1413): the reference reads n rows per sample and uses the last; the end marker ends the file
+         at whichever of them carries it.  The rows are thinned on the host (a rarely used option), an end-marker row is appended, and
+         the tape the GPU sees is the thinned one; file positions map to its rows in groups of n. */
+      int16_t *raw = malloc(S.rows_bytes + rowbytes);
+      assert(raw != NULLP, "no memory for the .tbin payload");
+      size_t got = 0;
+      while (got < S.rows_bytes) { ssize_t k = pread(fileno(inf), (char *)raw + got, S.rows_bytes - got, (off_t)(S.base_pos + (long long)got)); assert(k > 0, "can't read .tbin data"); got += (size_t)k; }
+      uint64_t m = 0;
+      while (m < nrows_file && raw[m * nheads] != -32768) ++m;
+      uint64_t kept = m / (uint64_t)subsample;
+      for (uint64_t r = 0; r < kept; ++r) memmove(raw + r * nheads, raw + ((r + 1) * subsample - 1) * nheads, rowbytes);
+      int have_marker = m < nrows_file;
+      if (have_marker) { raw[kept * nheads] = -32768; S.endfile_extra = (long long)((m - kept * subsample) * rowbytes) + 2; }
+      rc = rt_upload(S.tape, raw, kept + (uint64_t)have_marker);
+      free(raw); }
+   else if (getenv("RT_UPLOAD_MMAP") && atoi(getenv("RT_UPLOAD_MMAP"))) {   /* experiment: hand the library a mapping of the file instead */
       const long pg = sysconf(_SC_PAGESIZE);
       const off_t map_off = (off_t)(S.base_pos / pg * pg);
       const size_t map_len = S.rows_bytes + (size_t)(S.base_pos - map_off);
@@ -800,13 +818,13 @@ bool readblock(bool retry) {
       S.must_seek_start = 0;
       timenow_ns = (int64_t)(S.desc.tstart_ns + S.start_row * S.desc.tdelta_ns);
       timenow = rowtime(S.start_row);
-      assert(fseeko(inf, S.base_pos + (long long)S.start_row * nheads * 2, SEEK_SET) == 0, "fseek failed");
+      assert(fseeko(inf, S.base_pos + (long long)S.start_row * S.group_bytes, SEEK_SET) == 0, "fseek failed");
       block.results[block.parmset].blktype = BS_NOISE;
       S.pending_reset = RT_RESET_NONE;
       return true; }
    long long pos = ftello(inf);
-   assert(pos >= S.base_pos && (pos - S.base_pos) % (nheads * 2) == 0, "B200 scan: unexpected file position %lld", pos);
-   uint64_t row0 = (uint64_t)(pos - S.base_pos) / (uint64_t)(nheads * 2);
+   assert(pos >= S.base_pos && (pos - S.base_pos) % S.group_bytes == 0, "B200 scan: unexpected file position %lld", pos);
+   uint64_t row0 = (uint64_t)((pos - S.base_pos) / S.group_bytes);
    int reset_kind = S.pending_reset; S.pending_reset = RT_RESET_NONE;
    samples_per_bit = bpi > 0 ? (int)(1 / (bpi * ips * sample_deltat)) : 20;     /* readtape.c:1402 */
    rt_scan_cfg cfg; make_cfg(&cfg);
@@ -843,7 +861,7 @@ bool readblock(bool retry) {
    numsamples += (long long)consumed;
    if (!retry) lines_in += (long long)consumed + (endfile ? 1 : 0);
    timenow_ns = (int64_t)(S.desc.tstart_ns + last_row * S.desc.tdelta_ns);
-   assert(fseeko(inf, S.base_pos + (long long)last_row * nheads * 2 + (endfile ? 2 : 0), SEEK_SET) == 0, "fseek failed");
+   assert(fseeko(inf, S.base_pos + (long long)last_row * S.group_bytes + (endfile ? S.endfile_extra : 0), SEEK_SET) == 0, "fseek failed");
 
    struct results_t *result = &block.results[block.parmset];                 /* readtape.c:1509-1515 */
    result->errcount = result->track_mismatch + result->vparity_errs + result->ecc_errs + result->crc_errs + result->lrc_errs

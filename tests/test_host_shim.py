@@ -299,3 +299,41 @@ def test_readtape_b200_decodes_the_synthetic_gcr_blocks(tmp_path):
             record_stats("synthetic_gcr_8_blocks", st)
             assert st["misses"] == 0 and st["hits"] >= 8, st
     assert open(f"{tmp_path}/new.tap", "rb").read() == open(f"{tmp_path}/ref.tap", "rb").read()
+
+
+# ---- -subsample=n (readtape.c:1407-1413): of every n rows the last is used, the sample period is NOT rescaled -------------
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+SUBSAMPLE_CASES = ["-nrzi -bpi=1600 -ips=50 -subsample=2 -tap", "-nrzi -bpi=2400 -ips=50 -subsample=3 -tap -nm"]
+
+
+def _subsample_case(exe, opts, tmp_path):
+    """the unmodified reference runs beside the shim (it travels with the repo): same .tap, same log"""
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/readtape_ref not built")
+    capture = capture_path("Microdata_20blks")
+    got = {}
+    for tag, binary in (("ref", REF_EXE), ("new", exe)):
+        d = tmp_path / tag
+        d.mkdir()
+        if not os.path.exists(binary):
+            pytest.skip(f"{binary} not built")
+        env = {k: v for k, v in os.environ.items() if k != "RT_STATS"}
+        r = subprocess.run([binary] + opts.split() + ["-outf=m", capture], capture_output=True, text=True, cwd=str(d), env=env, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        log = [ln for ln in open(d / "m.log", errors="replace").read().splitlines()
+               if not re.search(r"^this is readtape version|command line:|samples were processed in", ln)]
+        got[tag] = (open(d / "m.tap", "rb").read(), log)
+    assert len(got["ref"][0]) > 5000
+    assert got["new"][0] == got["ref"][0], ".tap differs from the reference's"
+    assert got["new"][1] == got["ref"][1], "log differs from the reference's"
+
+
+@pytest.mark.parametrize("opts", SUBSAMPLE_CASES)
+def test_shim_on_oracle_backend_subsample(opts, tmp_path):
+    _subsample_case(ORACLE_SHIM, opts, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", SUBSAMPLE_CASES)
+def test_readtape_b200_subsample(opts, tmp_path):
+    _subsample_case(CUDA_SHIM, opts, tmp_path)
