@@ -85,6 +85,7 @@ static struct {
    /* statistics */
    long long n_bulk_hits, n_bulk_miss, n_exact_spans, n_events, n_restarts;
    double s_scan, s_replay, s_open;  /* wall seconds: inside the rt_scan library / replaying events into the handlers / opening */
+   double s_exact;                   /* of s_replay: inside exact-scan spans asked for in the middle of a block decode */
    int said_config;
    /* one reel split between worker processes (RT_WORKERS, see run_workers) */
    int par_checked, nworkers, worker;   /* worker: 0 .. nworkers-1, or -1 for the classic single process */
@@ -238,7 +239,9 @@ static void exact_more(struct evsrc *src) {  /* continue the exact scan by one s
    if (S.remote_fd >= 0) { struct wreq rq; memset(&rq, 0, sizeof rq); rq.op = WOP_MORE; remote_exact(src, &rq); return; }
    uint64_t done = 0;
    if (!src->span) src->span = EXACT_SPAN_FIRST;
+   const double x0 = wall();
    int rc = rt_scan_run(S.ctx, src->span, &src->ev, &src->n, &done);
+   S.s_exact += wall() - x0;
    if (src->span < EXACT_SPAN_ROWS) src->span *= 2;
    if (rc) rtfatal("rt_scan_run", rc);
    src->at = 0; src->valid_end = rt_scan_pos(S.ctx); ++S.n_exact_spans;
@@ -872,5 +875,6 @@ bool readblock(bool retry) {
    if (endfile && getenv("RT_STATS")) {
       rlog("  B200 scan: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n",
            S.n_events, S.n_bulk_hits, S.n_bulk_miss, S.n_restarts, S.n_exact_spans);
-      rlog("  B200 scan: %.3f s opening + upload, %.3f s in the scan library, %.3f s replaying events into the handlers\n", S.s_open, S.s_scan, S.s_replay); }
+      rlog("  B200 scan: %.3f s opening + upload, %.3f s in the scan library, %.3f s replaying events into the handlers\n", S.s_open, S.s_scan, S.s_replay);
+      if (S.s_exact > 0) rlog("  B200 scan: %.3f s of the replay time were exact-scan spans continued inside block decodes\n", S.s_exact); }
    return !endfile; }
