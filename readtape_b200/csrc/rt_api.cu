@@ -92,6 +92,7 @@ struct rt_tape {
       uint64_t fused_rows = 0;                                       /* of which written by the fused kernel (diagnostics) */
    } pm;
    int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
+   int ring_slots = 0;            /* slots h_ring holds (pinning costs ~0.4 ms per MB: a small capture gets a small ring) */
 };
 
 static int tape_reserve(rt_tape *t, uint64_t rows) {
@@ -222,7 +223,9 @@ static int tape_drain(rt_tape *t) {
 /* two device staging buffers for the chunked host->device copy; *stage_rows = rows per chunk */
 static int stage_prepare(rt_tape *t, uint64_t nrows, uint64_t *stage_rows) {
    const uint64_t nh = t->desc.nheads;
-   const uint64_t chunk_rows = (uint64_t)2048 * 1024;                       /* 2 Mi rows: 36 MiB for 9 heads */
+   /* 2 Mi rows per chunk (36 MiB for 9 heads); a small upload is cut into ~8 chunks so that reading, copying and ingesting overlap
+      and the pinned ring stays small (pinning costs ~0.4 ms per MB) */
+   const uint64_t chunk_rows = std::min<uint64_t>((uint64_t)2048 * 1024, std::max<uint64_t>(128 * 1024, (nrows / 8 + 2047) / 2048 * 2048));
    const size_t need = std::max((size_t)std::min(chunk_rows, nrows + 2048) * nh * 2 + 256, (size_t)1 << 20);
    if (t->d_stage[0] && need > t->stage_bytes) {
       /* a small first upload sized the staging buffers: regrow them for this one (a 1.1 G-row tape went through in 57 k-row
@@ -256,12 +259,16 @@ static int enqueue_chunk(rt_tape *t, const int16_t *src, uint64_t n, int buf) {
    engine drains them, which keeps PCIe busy (RT_UPLOAD_THREADS, default 4). */
 static int upload_pageable(rt_tape *t, const int16_t *rows, int fd, uint64_t fd_offset, uint64_t nrows, uint64_t stage_rows) {
    const uint64_t nh = t->desc.nheads;
-   const int NB = RT_RING_SLOTS;
    const size_t slot_bytes = (size_t)stage_rows * nh * 2;
+   const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
+   const int NB = (int)std::min<uint64_t>(RT_RING_SLOTS, std::max<uint64_t>(3, nchunks));   /* >= 3: the loop below keeps NB - 2 copies in flight */
+   if (t->h_ring && t->ring_slots < NB) {                          /* a later, larger upload: grow the ring */
+      CU(cudaStreamSynchronize(t->stream)); if (t->s_copy) CU(cudaStreamSynchronize(t->s_copy));
+      cudaFreeHost(t->h_ring); t->h_ring = nullptr; }
    if (!t->h_ring) {
       CU(cudaHostAlloc(&t->h_ring, slot_bytes * NB, cudaHostAllocDefault));
+      t->ring_slots = NB;
       for (int i = 0; i < NB; ++i) if (!t->ring_done[i]) CU(cudaEventCreateWithFlags(&t->ring_done[i], cudaEventDisableTiming)); }
-   const uint64_t nchunks = (nrows + stage_rows - 1) / stage_rows;
    const char *env = getenv("RT_UPLOAD_THREADS");
    const int hw = (int)std::thread::hardware_concurrency();
    int nthreads = env && atoi(env) > 0 ? atoi(env) : std::max(4, std::min(RT_RING_SLOTS - 2, hw - 2));
