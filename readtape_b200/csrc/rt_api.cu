@@ -92,6 +92,7 @@ struct rt_tape {
       uint64_t fused_rows = 0;                                       /* of which written by the fused kernel (diagnostics) */
    } pm;
    int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
+   uint32_t chunks_hist = 0;      /* event chunks per configuration the last whole-tape scan of this tape used (first guess of the next) */
    int ring_slots = 0;            /* slots h_ring holds (pinning costs ~0.4 ms per MB: a small capture gets a small ring) */
 };
 
@@ -932,6 +933,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
          per ~40, half of a reel is gap) plus one partly filled chunk per (unit, track); an overflow costs one regrowth + rescan, after
          which the tape's cached pool fits */
       uint64_t want_chunks = std::max<uint64_t>(4096, (uint64_t)ncfgs * (nrows * nt / 64 / RT_EVC) + total_units * nt);
+      if (t->chunks_hist) want_chunks = std::max<uint64_t>(want_chunks, (uint64_t)ncfgs * ((uint64_t)t->chunks_hist + t->chunks_hist / 8 + 64));
       /* phase B1's record pool: what the last scan of this tape needed, else one record per 28 track-samples per mask set */
       uint64_t want_recs = 0;
       if (use_records && !msets.empty()) {
@@ -1003,7 +1005,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
             t->rec_hist = used_recs;
             if (used_recs > t->rec_cache_cap) { want_recs = (uint64_t)used_recs + used_recs / 16 + 4096; again = true; } }   /* some tiles had no room: redo */
          if (used > b->pool_chunks) { want_chunks = (uint64_t)used + used / 8 + 1024; again = true; }
-         if (!again) { b->chunks_used = used; break; }
+         if (!again) { b->chunks_used = used; t->chunks_hist = (uint32_t)((used + ncfgs - 1) / ncfgs); break; }
          if (attempt == 2) { cleanup(); rt_bulk_free(b); return set_err(RT_ERR_OVERFLOW, "event pool overflow after regrowth"); } }
       std::vector<unsigned long long> counters(4 * (size_t)ncfgs, 0);
       CUB(cudaMemcpy(counters.data(), d_counters, 32 * (size_t)ncfgs, cudaMemcpyDeviceToHost));

@@ -313,7 +313,9 @@ static int scan_parmsets(void) {
    const int keep = block.parmset;
    for (int i = 0; i < MAXPARMSETS; ++i) {
       if (!(i == keep || (multiple_tries && parmsetsptr[i].active))) continue;
-      block.parmset = i; make_cfg(&cfgs[n]); which[n++] = i; }
+      block.parmset = i; make_cfg(&cfgs[n]);
+      if (i != keep && S.bulk[i].valid && memcmp(&S.bulk[i].cfg, &cfgs[n], sizeof cfgs[n]) == 0) continue;   /* already scanned */
+      which[n++] = i; }
    block.parmset = keep;
    rt_bulk *bulk = NULLP;
    int rc = rt_bulk_scan(S.tape, cfgs, (uint32_t)n, &bulk);
@@ -335,7 +337,14 @@ static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
       S.bulk[ps].valid = 0; }
    if (!S.bulk[ps].valid) {
       if (S.remote_fd >= 0) return 0;                 /* a worker cannot scan: the parent serves this decode with the exact scan */
-      if (getenv("RT_FANOUT") && atoi(getenv("RT_FANOUT")) && !doing_density_detection && !doing_deskew && scan_parmsets()) { /* all at once */ }
+      /* Most blocks decode with the first parameter set, so that one is scanned alone.  The first block that needs another try
+         usually is not the last: on a tape of moderate size all remaining active sets are then scanned by ONE call, side by side,
+         instead of one whole-tape scan per set (RT_FANOUT=1: all of them from the start; RT_FANOUT=0: never). */
+      const char *fo = getenv("RT_FANOUT");
+      int any_valid = 0;
+      for (int i = 0; i < MAXPARMSETS; ++i) any_valid |= S.bulk[i].valid;
+      const int fan = fo ? (atoi(fo) != 0) : (any_valid && multiple_tries && (double)S.nrows * ntrks < 2e9);
+      if (fan && !doing_density_detection && !doing_deskew && scan_parmsets()) { /* all at once */ }
       else {
          int rc = rt_bulk_scan(S.tape, cfg, 1, &S.bulk[ps].bulk);
          if (rc == RT_ERR_UNSUPPORTED) { S.use_bulk = 0; return 0; }
