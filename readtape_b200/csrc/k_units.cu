@@ -118,3 +118,39 @@ cudaError_t launch_find_units(const int16_t *gmm, uint64_t ngran_cap, int ntrks,
    k_close_units<<<64, 256, 0, st>>>(d_units, d_nunits, units_cap, nrows, up.tail_rows);
    *launches += 5;
    return cudaGetLastError(); }
+
+
+/* ---- -invert (readtape.c:1421): a negated copy of the planes and of the granule map ------------------------------------------------
+ * The reference negates every sample as it is read.  volts(-x) == -volts(x) exactly (rounding is symmetric, -32768 never occurs:
+ * it is the end marker), so a scan of the negated planes with the invert flag cleared IS the inverted scan, and every fast kernel
+ * serves it unchanged.  One thread per 8 samples; granule (min, max) becomes (-max, -min). */
+__global__ void __launch_bounds__(256)
+k_negate_planes(const int16_t *src, int16_t *dst, uint64_t plane_stride, uint64_t row_lo, uint64_t row_hi, int ntrks) {
+   const uint64_t per = (row_hi - row_lo + 7) / 8;                 /* row_lo is a multiple of 8 */
+   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= per * (uint64_t)ntrks) return;
+   const uint64_t k = i / per, r = row_lo + (i - k * per) * 8;
+   const uint4 v = *reinterpret_cast<const uint4 *>(src + k * plane_stride + r);     /* the planes are padded beyond the last row */
+   uint4 o; o.x = __vneg2(v.x); o.y = __vneg2(v.y); o.z = __vneg2(v.z); o.w = __vneg2(v.w);
+   *reinterpret_cast<uint4 *>(dst + k * plane_stride + r) = o; }
+
+__global__ void __launch_bounds__(256)
+k_negate_gmm(const uint32_t *src, uint32_t *dst, uint64_t ngran_cap, uint64_t g_lo, uint64_t g_hi, int ntrks) {
+   const uint64_t per = g_hi - g_lo;
+   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= per * (uint64_t)ntrks) return;
+   const uint64_t k = i / per, g = g_lo + (i - k * per);
+   const uint32_t w = src[k * ngran_cap + g];
+   const int mn = (int)(int16_t)(uint16_t)(w & 0xffffu), mx = (int)(int16_t)(uint16_t)(w >> 16);
+   dst[k * ngran_cap + g] = ((uint32_t)(-mx) & 0xffffu) | ((uint32_t)(-mn) << 16); }
+
+cudaError_t launch_negate(const int16_t *planes, int16_t *planes_inv, uint64_t plane_stride, const int16_t *gmm, int16_t *gmm_inv, uint64_t ngran_cap,
+                          uint64_t row_lo, uint64_t row_hi, int ntrks, cudaStream_t s) {
+   row_lo = row_lo / RT_GRAN * RT_GRAN;                              /* whole granules (and 16-byte aligned vectors) */
+   if (row_hi <= row_lo) return cudaSuccess;
+   const uint64_t n = (row_hi - row_lo + 7) / 8 * (uint64_t)ntrks;
+   k_negate_planes<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(planes, planes_inv, plane_stride, row_lo, row_hi, ntrks);
+   const uint64_t g_lo = row_lo / RT_GRAN, g_hi = (row_hi + RT_GRAN - 1) / RT_GRAN;
+   const uint64_t m = (g_hi - g_lo) * (uint64_t)ntrks;
+   k_negate_gmm<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t *>(gmm), reinterpret_cast<uint32_t *>(gmm_inv), ngran_cap, g_lo, g_hi, ntrks);
+   return cudaGetLastError(); }

@@ -59,6 +59,9 @@ cudaError_t launch_cand_records(const DevCfg &c, uint64_t row_lo, uint64_t row_h
 cudaError_t launch_units_sparse(const DevCfg &c, const UnitDesc *units, uint32_t nunits, TrkMeta *meta, rt_event *pool,
                                 uint32_t *chunk_next, unsigned int *cursor, uint32_t cap_chunks, int quiet_thr_lsb,
                                 unsigned long long *counters, int sms, int max_ctas_per_sm, cudaStream_t s);
+/* k_units.cu: negated copy of the planes / granule map for -invert */
+cudaError_t launch_negate(const int16_t *planes, int16_t *planes_inv, uint64_t plane_stride, const int16_t *gmm, int16_t *gmm_inv, uint64_t ngran_cap,
+                          uint64_t row_lo, uint64_t row_hi, int ntrks, cudaStream_t s);
 /* k_csv.cu: CSV ingest (line index, csv_preread's maximum, parse + quantise) */
 uint32_t csv_index_warps(uint64_t nbytes);      /* scratch entries launch_csv_count / launch_csv_index need: round up to a multiple of 8 */
 cudaError_t launch_csv_count(const char *txt, uint64_t n, uint32_t *warp_counts, uint64_t *warp_offsets, uint64_t *total, cudaStream_t s);

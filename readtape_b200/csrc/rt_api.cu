@@ -65,6 +65,8 @@ struct rt_tape {
    uint64_t cap_rows = 0;         /* capacity of the planes, rows */
    int16_t *planes = nullptr; uint64_t plane_stride = 0;
    int16_t *gmm = nullptr; uint64_t ngran_cap = 0;
+   /* -invert: negated copies (same strides), made on demand by rt_bulk_scan for rows [0, inv_rows) */
+   int16_t *planes_inv = nullptr, *gmm_inv = nullptr; uint64_t inv_rows = 0;
    unsigned long long *d_first_end = nullptr;
    uint64_t nrows_valid = 0; bool valid_known = false;
    int16_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t stage_done[2] = {nullptr, nullptr};
@@ -114,6 +116,7 @@ static int tape_reserve(rt_tape *t, uint64_t rows) {
                             (size_t)((t->nrows + RT_GRAN - 1) / RT_GRAN) * 4, cudaMemcpyDeviceToDevice, t->stream)); }
       CU(cudaStreamSynchronize(t->stream));
       cudaFree(t->planes); cudaFree(t->gmm); }
+   cudaFree(t->planes_inv); cudaFree(t->gmm_inv); t->planes_inv = t->gmm_inv = nullptr; t->inv_rows = 0;   /* other strides now: rebuilt on demand */
    t->planes = np; t->plane_stride = newcap; t->gmm = ng; t->ngran_cap = ngran; t->cap_rows = newcap;
    return RT_OK; }
 
@@ -405,7 +408,7 @@ extern "C" int rt_clear(rt_tape *t) {
    unsigned long long none = ~0ull;
    CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
    t->nrows = 0; t->nrows_valid = 0; t->valid_known = false; t->ms_ingest = 0; t->h2d_bytes = 0;
-   t->pm.rows = 0; t->pm.fused_rows = 0;
+   t->pm.rows = 0; t->pm.fused_rows = 0; t->inv_rows = 0;
    return RT_OK; }
 
 static int tape_sync_valid(rt_tape *t) {
@@ -427,7 +430,7 @@ extern "C" void rt_close(rt_tape *t) {
    if (!t) return;
    cudaSetDevice(t->device);
    if (t->stream) cudaStreamSynchronize(t->stream);
-   cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end);
+   cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end); cudaFree(t->planes_inv); cudaFree(t->gmm_inv);
    cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
    cudaFree(t->rec_cache); cudaFree(t->pm.mc); cudaFree(t->pm.md); cudaFree(t->pm.ma);
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
@@ -675,8 +678,24 @@ static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
 
 /* Everything derived from one configuration that the unit finder and the scan kernels need. */
 struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; bool use_sparse; bool t0_auto; };
-static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl) {
+/* -invert with the fast kernels: negated planes (rows [0, nrows)), made once per tape and extended as it grows */
+static int tape_ensure_inverted(rt_tape *t, uint64_t nrows) {
+   if (t->inv_rows >= nrows) return RT_OK;
+   const uint32_t nt = t->desc.ntrks;
+   if (!t->planes_inv) {
+      CU(cudaMalloc(&t->planes_inv, (size_t)t->plane_stride * nt * sizeof(int16_t)));
+      cudaError_t e = cudaMalloc(&t->gmm_inv, (size_t)t->ngran_cap * nt * 4);
+      if (e != cudaSuccess) { cudaFree(t->planes_inv); t->planes_inv = nullptr; return set_err(RT_ERR_CUDA, "cudaMalloc(inverted granule map) failed: %s", cudaGetErrorString(e)); }
+      t->inv_rows = 0; }
+   CU(launch_negate(t->planes, t->planes_inv, t->plane_stride, t->gmm, t->gmm_inv, t->ngran_cap, t->inv_rows, nrows, (int)nt, t->stream));
+   t->launches += 2; t->inv_rows = nrows;
+   return RT_OK; }
+
+static void make_plan(const rt_tape *t, const rt_scan_cfg *cfg, ScanPlan *pl, bool use_inverted = false) {
    cfg_to_dev(t, cfg, &pl->dc);
+   if (use_inverted && pl->dc.invert && !pl->dc.differentiate && t->planes_inv) {   /* scan the negated planes, flag cleared (k_units.cu) */
+      pl->dc.planes = t->planes_inv; pl->dc.invert = 0;
+      if (pl->dc.gmm) pl->dc.gmm = reinterpret_cast<const uint32_t *>(t->gmm_inv); }
    const DevCfg &dc = pl->dc;
    /* proposal thresholds (heuristic) and the exact quiet threshold the scan kernel applies */
    const double lsb = (double)t->desc.maxvolts / 32767.0;
@@ -855,7 +874,8 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    uint64_t total_units = 0;
    for (uint32_t ci = 0; ci < ncfgs; ++ci) {
       BulkCfg &bc = b->cfgs[ci];
-      ScanPlan &pl = plans[ci]; make_plan(t, &cfgs[ci], &pl);
+      if ((cfgs[ci].flags & RT_F_INVERT) && !(cfgs[ci].flags & RT_F_DIFFERENTIATE)) { int rc_ = tape_ensure_inverted(t, nrows); if (rc_) { cleanup(); rt_bulk_free(b); return rc_; } }
+      ScanPlan &pl = plans[ci]; make_plan(t, &cfgs[ci], &pl, true);
       bc.cfg = cfgs[ci]; bc.dc = pl.dc; bc.fast = pl.use_fast;
       CUB(cudaEventRecord(ev[0], t->stream));
       CUB(launch_find_units(t->gmm, t->ngran_cap, (int)nt, nrows, pl.up, d_bitmap, d_flags, d_blockcount, d_units_tmp, units_cap, d_nunits, t->stream, &t->launches));

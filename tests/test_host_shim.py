@@ -303,7 +303,9 @@ def test_readtape_b200_decodes_the_synthetic_gcr_blocks(tmp_path):
 
 # ---- -subsample=n (readtape.c:1407-1413): of every n rows the last is used, the sample period is NOT rescaled -------------
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
-SUBSAMPLE_CASES = ["-nrzi -bpi=1600 -ips=50 -subsample=2 -tap", "-nrzi -bpi=2400 -ips=50 -subsample=3 -tap -nm"]
+SUBSAMPLE_CASES = ["-nrzi -bpi=1600 -ips=50 -subsample=2 -tap", "-nrzi -bpi=2400 -ips=50 -subsample=3 -tap -nm",
+                   # -invert (readtape.c:1421): served by the fast kernels on a negated copy of the planes
+                   "-nrzi -bpi=800 -ips=50 -invert -tap"]
 
 
 def _subsample_case(exe, opts, tmp_path):
