@@ -92,7 +92,9 @@ struct rt_tape {
       uint32_t *mc = nullptr, *md = nullptr, *ma = nullptr; uint64_t stride = 0;
       uint64_t rows = 0;                                             /* the planes are complete for tape rows [0, rows) */
       uint64_t fused_rows = 0;                                       /* of which written by the fused kernel (diagnostics) */
+      bool overlap = false;                                          /* RT_FUSED_MASKS=2: separate mask kernel, one chunk behind the ingest kernel, on its own stream */
    } pm;
+   cudaStream_t s_mask = nullptr; std::vector<cudaEvent_t> mask_events;
    int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
    uint32_t chunks_hist = 0;      /* event chunks per configuration the last whole-tape scan of this tape used (first guess of the next) */
    int ring_slots = 0;            /* slots h_ring holds (pinning costs ~0.4 ms per MB: a small capture gets a small ring) */
@@ -186,6 +188,35 @@ static int tape_ingest(rt_tape *t, const int16_t *d_src, uint64_t nrows) {
    rt_tape::PreMask &pm = t->pm;
    IngestMasks im{}; const IngestMasks *imp = nullptr;
    if (pm.active) { int rc = premask_reserve(t); if (rc) return rc; }
+   if (pm.active && pm.have_thr && pm.rows == t->nrows && pm.overlap) {
+      /* The ingest kernel is bound by HBM (86 % of the peak, 1 CTA per SM), the mask kernel by the integer pipe (93 %, half the
+         bandwidth): they are run side by side -- the rows go through in chunks, the mask kernel of chunk i on a second stream while
+         the ingest kernel of chunk i+1 runs (the window only looks back, so a chunk needs nothing from the next one). */
+      if (!t->s_mask) CU(cudaStreamCreateWithFlags(&t->s_mask, cudaStreamNonBlocking));
+      const char *ce = getenv("RT_OVERLAP_CHUNK");
+      const uint64_t chunk = (ce && atoll(ce) > 0 ? (uint64_t)atoll(ce) : (uint64_t)16 << 20) / 2048 * 2048;   /* 4 Mi .. 128 Mi rows measured alike */
+      DevCfg dc; premask_devcfg(t, &dc);
+      CU(cudaEventRecord(e0, t->stream));
+      size_t nev = 0;
+      for (uint64_t at = 0; at < nrows; at += chunk) {
+         const uint64_t n = std::min(chunk, nrows - at);
+         uint64_t masked = 0;
+         cudaError_t e = launch_ingest(d_src + at * t->desc.nheads, n, t->nrows + at, (int)t->desc.nheads, t->trk_of_head, t->planes, t->plane_stride,
+                                       t->gmm, t->ngran_cap, t->d_first_end, t->sms, t->force_simple_ingest, t->stream, &t->launches, nullptr, &masked);
+         if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "ingest kernel launch failed: %s", cudaGetErrorString(e));
+         if (nev == t->mask_events.size()) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); t->mask_events.push_back(ev); }
+         CU(cudaEventRecord(t->mask_events[nev], t->stream));
+         CU(cudaStreamWaitEvent(t->s_mask, t->mask_events[nev], 0)); ++nev;
+         e = launch_peak_masks(dc, t->nrows + at, t->nrows + at + n, t->s_mask); ++t->launches;
+         if (e != cudaSuccess) return set_err(RT_ERR_CUDA, "mask kernel launch failed: %s", cudaGetErrorString(e)); }
+      if (nev == t->mask_events.size()) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); t->mask_events.push_back(ev); }
+      CU(cudaEventRecord(t->mask_events[nev], t->s_mask));
+      CU(cudaStreamWaitEvent(t->stream, t->mask_events[nev], 0));   /* whatever follows on the tape's stream sees complete planes */
+      CU(cudaEventRecord(e1, t->stream));
+      t->ingest_events.push_back(e0); t->ingest_events.push_back(e1);
+      pm.rows = t->nrows + nrows;
+      t->nrows += nrows; t->valid_known = false;
+      return RT_OK; }
    if (pm.active && pm.have_thr && pm.rows == t->nrows) {           /* the planes are complete so far: this chunk's tiles are done on chip */
       im.cand = pm.mc; im.cand2 = pm.md; im.acan = pm.ma; im.mask_stride = pm.stride; im.ntrks = (int)t->desc.ntrks; im.width = pm.width;
       memcpy(im.T0, pm.T0, sizeof im.T0); memcpy(im.T1, pm.T1, sizeof im.T1);
@@ -436,6 +467,8 @@ extern "C" void rt_close(rt_tape *t) {
    for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
    if (t->h_ring) { cudaFreeHost(t->h_ring); for (auto e : t->ring_done) if (e) cudaEventDestroy(e); }
    if (t->s_copy) cudaStreamDestroy(t->s_copy);
+   if (t->s_mask) cudaStreamDestroy(t->s_mask);
+   for (auto e : t->mask_events) cudaEventDestroy(e);
    if (t->stream) cudaStreamDestroy(t->stream);
    for (auto st : t->s_par) cudaStreamDestroy(st);
    if (t->s_scan) cudaStreamDestroy(t->s_scan);
@@ -786,14 +819,18 @@ extern "C" int rt_prepare(rt_tape *t, const rt_scan_cfg *cfg) {
    /* Measured on a B200 (config 2): the fused kernel takes 17.4 ms where the TMA ingest (7.2 ms) and the separate mask pass (7.2 ms)
       take 14.4 ms together -- the mask arithmetic is ALU-bound and gets 9 warps per SM inside the persistent ingest CTA instead of ~21 --
       so the fusion saves the 20 GB re-read but loses time.  It stays available for experiments (RT_FUSED_MASKS=1); DESIGN.md 6b. */
+   /* What does pay is running the two kernels side by side (mode 2, the default): the ingest kernel is bound by HBM, the mask kernel by
+      the integer pipe; chunk by chunk on two streams they take 12.0 ms together instead of 14.3 ms one after the other.
+      RT_FUSED_MASKS=0: rt_prepare has no effect (the mask pass runs inside rt_bulk_scan); =1: the fused kernel; =2: side by side. */
    const char *env = getenv("RT_FUSED_MASKS");
-   const bool ok = env && env[0] == '1' && dc.det == RT_DET_PEAK && !dc.invert && !dc.differentiate && !dc.density
+   if (!env) env = "2";
+   const bool ok = (env[0] == '1' || env[0] == '2') && dc.det == RT_DET_PEAK && !dc.invert && !dc.differentiate && !dc.density
                    && (cfg->mode == RT_MODE_NRZI || cfg->mode == RT_MODE_PE)
-                   && ingest_masks_supported((int)t->desc.nheads, (int)t->desc.ntrks, dc.width) && !t->force_simple_ingest;
+                   && (env[0] == '2' || (ingest_masks_supported((int)t->desc.nheads, (int)t->desc.ntrks, dc.width) && !t->force_simple_ingest));
    if (!ok) { pm.active = false; return RT_OK; }
    if (pm.active && pm.width == dc.width && pm.rise == cfg->parms.pkww_rise && memcmp(&pm.cfg, cfg, sizeof *cfg) == 0) return RT_OK;   /* unchanged: thresholds and planes stay */
    const bool same_masks = pm.width == dc.width && pm.rise == cfg->parms.pkww_rise && pm.cfg.bpi == cfg->bpi && pm.cfg.ips == cfg->ips && pm.cfg.mode == cfg->mode;
-   pm.active = true; pm.cfg = *cfg; pm.width = dc.width; pm.rise = cfg->parms.pkww_rise;
+   pm.active = true; pm.cfg = *cfg; pm.width = dc.width; pm.rise = cfg->parms.pkww_rise; pm.overlap = env[0] == '2';
    if (!same_masks) { pm.have_thr = false; pm.rows = 0; }
    return RT_OK; }
 

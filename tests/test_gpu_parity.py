@@ -529,3 +529,39 @@ def test_invert_is_served_by_the_fast_kernels_and_is_exact(name, cuda_lib, oracl
         hits += 1
     assert hits >= 1
     osc.end(); otape.close(); bulk.free(); bulk_neg.free(); tape.close(); neg.close()
+
+
+def test_ingest_and_mask_kernels_side_by_side_give_the_same_planes(cuda_lib, capfd):
+    """RT_FUSED_MASKS=2 (rt_prepare): the mask kernel of chunk i runs on a second stream while the ingest kernel of chunk i+1 runs.
+    The planes must equal the separate pass word for word (RT_PREMASK_CHECK) and the scan results must not change."""
+    from readtape_b200 import parmsets, synth, tbin
+    import torch
+    tile = synth.nrzi_tile()
+    hdr = synth.nrzi_header()
+    desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns)
+    cfg = abi.make_cfg(tbin.MODE_NRZI, parmsets.NRZI[0], hdr.bpi, hdr.ips)
+    rows = np.concatenate([tile] * 8)[:9_700_123]
+    os.environ["RT_PREMASK_CHECK"] = "1"
+    os.environ["RT_FUSED_MASKS"] = "2"
+    os.environ["RT_OVERLAP_CHUNK"] = str(1 << 20)                  # 1 Mi-row chunks: several hand-overs between the two streams
+    try:
+        def snapshot(tape):
+            bulk = tape.bulk_scan([cfg]); st = bulk.stats()
+            units = _all_units(bulk)
+            evs = [bulk.lookup(0, u["row0"]) for u in units[::7]]
+            fusedflag = st.masks_fused
+            bulk.free()
+            return (st.events, st.units, units, [(e[0].tobytes(), e[1]) for e in evs]), fusedflag
+        plain = cuda_lib.open(desc); plain.upload(rows); want, _ = snapshot(plain); plain.close()
+        t1 = cuda_lib.open(desc); t1.prepare(cfg)
+        dev = torch.from_numpy(rows).cuda()
+        for _ in range(2):
+            t1.clear(); t1.attach_device(dev.data_ptr(), rows.shape[0])
+            got, fusedflag = snapshot(t1)
+            assert got == want and fusedflag == 1
+        t1.close()
+        err = capfd.readouterr().err
+        assert err.count("fused mask planes identical") >= 2, err[-800:]
+    finally:
+        for k in ("RT_PREMASK_CHECK", "RT_FUSED_MASKS", "RT_OVERLAP_CHUNK"):
+            os.environ.pop(k, None)
