@@ -728,7 +728,7 @@ def main():
     ms_scan = float(np.mean([s.ms_scan for s in stats])); ms_units = float(np.mean([s.ms_units for s in stats]))
     ms_ingest = float(np.mean([s.ms_preprocess for s in stats]))
     events = int(stats[-1].events); units = int(stats[-1].units)
-    launches_per_step = int(stats[-1].launches) + 2   # + the ingest kernels (TMA tiles + plain tail)
+    launches_per_step = int(stats[-1].launches) + int(stats[-1].launches_ingest)   # the scan's kernels + the ingest (and mask) kernels enqueued since rt_clear
 
     # ---- e2e: host buffers through the C-ABI ----
     e2e = None

@@ -269,6 +269,9 @@ typedef struct rt_bulk_stats {
    double   ms_records;      /* device time: candidate-record pass (phase B1) of the two-pass peak scan (a part of ms_scan; 0 if not used) */
    uint32_t masks_fused;     /* 1: the mask planes came from the ingest kernel (rt_prepare), ms_masks is 0 and their time is in ms_preprocess */
    uint32_t two_pass;        /* 1: the two-pass peak scan (K3c) was used */
+   uint32_t launches_ingest; /* kernels launched on this tape between rt_clear() / rt_open() and this scan: the ingest kernels, and the
+                                mask kernels that run beside them after rt_prepare() */
+   uint32_t pad2;
 } rt_bulk_stats;
 int  rt_bulk_get_stats(const rt_bulk *bulk, rt_bulk_stats *out);
 

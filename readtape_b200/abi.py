@@ -50,7 +50,8 @@ class BulkStats(C.Structure):
                 ("rows_scanned", C.c_uint64), ("track_samples", C.c_uint64),
                 ("ms_preprocess", C.c_double), ("ms_units", C.c_double), ("ms_scan", C.c_double),
                 ("launches", C.c_uint32), ("pad", C.c_uint32), ("d2h_bytes", C.c_uint64), ("ms_masks", C.c_double),
-                ("ms_records", C.c_double), ("masks_fused", C.c_uint32), ("two_pass", C.c_uint32)]
+                ("ms_records", C.c_double), ("masks_fused", C.c_uint32), ("two_pass", C.c_uint32),
+                ("launches_ingest", C.c_uint32), ("pad2", C.c_uint32)]
 
 
 class UnitInfo(C.Structure):

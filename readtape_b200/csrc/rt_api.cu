@@ -96,6 +96,7 @@ struct rt_tape {
    } pm;
    cudaStream_t s_mask = nullptr; std::vector<cudaEvent_t> mask_events;
    int16_t *h_ring = nullptr; cudaEvent_t ring_done[RT_RING_SLOTS] = {};   /* pinned ring for uploads from pageable memory / files */
+   int launches_at_clear = 0;     /* value of `launches` at the last rt_clear() */
    uint32_t chunks_hist = 0;      /* event chunks per configuration the last whole-tape scan of this tape used (first guess of the next) */
    int ring_slots = 0;            /* slots h_ring holds (pinning costs ~0.4 ms per MB: a small capture gets a small ring) */
 };
@@ -439,7 +440,7 @@ extern "C" int rt_clear(rt_tape *t) {
    unsigned long long none = ~0ull;
    CU(cudaMemcpy(t->d_first_end, &none, sizeof none, cudaMemcpyHostToDevice));
    t->nrows = 0; t->nrows_valid = 0; t->valid_known = false; t->ms_ingest = 0; t->h2d_bytes = 0;
-   t->pm.rows = 0; t->pm.fused_rows = 0; t->inv_rows = 0;
+   t->pm.rows = 0; t->pm.fused_rows = 0; t->inv_rows = 0; t->launches_at_clear = t->launches;
    return RT_OK; }
 
 static int tape_sync_valid(rt_tape *t) {
@@ -1070,6 +1071,7 @@ extern "C" int rt_bulk_scan(rt_tape *t, const rt_scan_cfg *cfgs, uint32_t ncfgs,
    lap("counters");
    b->stats.track_samples = nrows * nt * ncfgs;
    b->stats.launches = (uint32_t)(t->launches - launches0);
+   b->stats.launches_ingest = (uint32_t)(launches0 - t->launches_at_clear);
    for (auto &m : msets) { b->stats.two_pass = 1; if (m.borrowed) b->stats.masks_fused = 1; }
    if (ncfgs == 1) { t->hist_rows = nrows; t->hist_units = b->cfgs[0].nunits; t->hist_chunks = b->chunks_used; }   /* sizes the streamed scan */
    cleanup();
@@ -1343,6 +1345,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
    b->stats.rows = nrows; b->stats.units = nun; b->stats.events = counters[1]; b->stats.rows_scanned = counters[0];
    b->stats.track_samples = nrows * nt; b->stats.ms_preprocess = t->ms_ingest; b->stats.ms_units = ms_units; b->stats.ms_scan = ms_scan; b->stats.ms_masks = ms_masks;
    b->stats.launches = (uint32_t)(t->launches - launches0);
+   b->stats.launches_ingest = (uint32_t)(launches0 - t->launches_at_clear);
    b->stats.pad = (uint32_t)seg_ev.size();                        /* segments streamed (0: the plain sequence was used) */
    b->stats.two_pass = pl.use_sparse; b->stats.masks_fused = masks_fused;
    t->hist_rows = nrows; t->hist_units = nun; t->hist_chunks = c_done;

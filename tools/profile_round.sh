@@ -7,7 +7,8 @@ O=gpurun_out/prof
 python bench.py > $O/bench_full.json 2> $O/bench_full.err                       # value / e2e / roofline / cpu_baseline / product / verified
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2>/dev/null
 # launch list of the same command (per-launch times are cold-cache and serialised: compare SHARES with the live timing)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
+# (since rt_prepare runs the ingest and mask kernels chunk by chunk there are ~140 launches per step: -c 1200 covers 2 + 3 steps)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-product --no-verify > /dev/null 2>&1
 # one full capture of each kernel of a step, with source correlation
 ncu --set full --import-source on --clock-control none -k regex:"k_peak_masks|k_units_sparse|k_ingest_tma" -c 3 -o $O/prof_full -f \
