@@ -55,6 +55,7 @@ extern "C" double rt_row_time(const rt_tape_desc *d, uint64_t row) {
 extern "C" int rt_pkww_width(const rt_scan_cfg *cfg, uint64_t tdelta_ns) { return rtcfg::pkww_width(cfg, tdelta_ns); }
 
 /* ---- tape ---------------------------------------------------------------------------------------- */
+#define RT_STAGE_BUFS 6
 #define RT_RING_SLOTS 16      /* one reader thread fills a slot at ~2 GB/s from the page cache: the slots in flight set the file -> GPU rate */
 struct rt_tape {
    rt_tape_desc desc{};
@@ -69,7 +70,11 @@ struct rt_tape {
    int16_t *planes_inv = nullptr, *gmm_inv = nullptr; uint64_t inv_rows = 0;
    unsigned long long *d_first_end = nullptr;
    uint64_t nrows_valid = 0; bool valid_known = false;
-   int16_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t stage_done[2] = {nullptr, nullptr};
+   /* device staging buffers of the chunked host->device copy: two by default.  RT_STAGE=n (up to 6) lets the copy engine run further
+      ahead of the ingest kernel when scan kernels of earlier segments hold the SMs (rt_bulk_scan_host); measured on a B200: no
+      difference (460 / 482 / 556 / 516 / 572 ms end to end for n = 2 / 6 / 2 / 6 / 4 on one box -- the spread is the host's) */
+   int nstage = 2;                /* buffers in use (RT_STAGE=n, 2..RT_STAGE_BUFS) */
+   int16_t *d_stage[RT_STAGE_BUFS] = {}; size_t stage_bytes = 0; cudaEvent_t stage_done[RT_STAGE_BUFS] = {};
    int force_simple_ingest = 0;
    int launches = 0;
    float ms_ingest = 0;
@@ -81,7 +86,7 @@ struct rt_tape {
    rt_event *pin_cache = nullptr; size_t pin_cache_events = 0; bool pin_cache_busy = false;
    /* rt_bulk_scan_host(): extra streams, and the sizes the last whole-tape scan needed (capacity planning of the streamed scan) */
    std::vector<cudaStream_t> s_par;                               /* rt_bulk_scan with several configurations: their kernels run side by side */
-   cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[2] = {nullptr, nullptr};
+   cudaStream_t s_scan = nullptr, s_out = nullptr, s_copy = nullptr; cudaEvent_t stage_copied[RT_STAGE_BUFS] = {};
    uint64_t hist_rows = 0; uint32_t hist_units = 0, hist_chunks = 0;
    /* phase B1: candidate records (scan_records.cuh), grow-only like the event pool; one pool shared by the mask sets of a scan */
    CandRec *rec_cache = nullptr; uint32_t rec_cache_cap = 0; uint32_t rec_hist = 0;
@@ -267,12 +272,13 @@ static int stage_prepare(rt_tape *t, uint64_t nrows, uint64_t *stage_rows) {
       /* a small first upload sized the staging buffers: regrow them for this one (a 1.1 G-row tape went through in 57 k-row
          chunks otherwise); the pinned ring of the pageable path follows */
       CU(cudaStreamSynchronize(t->stream)); CU(cudaStreamSynchronize(t->s_copy));
-      for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); t->d_stage[i] = nullptr; }
+      for (int i = 0; i < RT_STAGE_BUFS; ++i) { cudaFree(t->d_stage[i]); t->d_stage[i] = nullptr; }
       if (t->h_ring) { cudaFreeHost(t->h_ring); t->h_ring = nullptr; } }
    if (!t->d_stage[0]) {
       t->stage_bytes = need;
       if (!t->s_copy) CU(cudaStreamCreateWithFlags(&t->s_copy, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; ++i) {
+      { const char *se = getenv("RT_STAGE"); const int want = se ? atoi(se) : 2; t->nstage = want < 2 ? 2 : want > RT_STAGE_BUFS ? RT_STAGE_BUFS : want; }
+      for (int i = 0; i < t->nstage; ++i) {
          CU(cudaMalloc(&t->d_stage[i], t->stage_bytes));
          if (!t->stage_done[i]) { CU(cudaEventCreateWithFlags(&t->stage_done[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t->stage_copied[i], cudaEventDisableTiming)); } } }
    *stage_rows = (t->stage_bytes - 256) / (nh * 2) / 2048 * 2048;
@@ -337,7 +343,7 @@ static int upload_pageable(rt_tape *t, const int16_t *rows, int fd, uint64_t fd_
       { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return filled[i] != 0; }); }
       const uint64_t r0 = i * stage_rows, n = std::min(stage_rows, nrows - r0);
       if (rc == RT_OK) {
-         rc = enqueue_chunk(t, reinterpret_cast<const int16_t *>(reinterpret_cast<char *>(t->h_ring) + (size_t)(i % NB) * slot_bytes), n, (int)(i & 1));
+         rc = enqueue_chunk(t, reinterpret_cast<const int16_t *>(reinterpret_cast<char *>(t->h_ring) + (size_t)(i % NB) * slot_bytes), n, (int)(i % (uint64_t)t->nstage));
          if (rc == RT_OK && cudaEventRecord(t->ring_done[i % NB], t->s_copy) != cudaSuccess) rc = set_err(RT_ERR_CUDA, "cudaEventRecord failed"); }
       if (i + 2 >= (uint64_t)NB) {                                /* keep NB - 2 copies in flight, then free the oldest slot */
          const uint64_t k = i + 2 - NB;
@@ -378,7 +384,7 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
                const uint64_t n = std::min(stage_rows, nrows - done);
                rc = enqueue_chunk(t, rows + done * nh, n, buf);
                if (rc) { cudaDeviceSynchronize(); return rc; }
-               done += n; buf ^= 1; }
+               done += n; buf = (buf + 1) % t->nstage; }
             rc = tape_drain(t);
             auto w2 = std::chrono::steady_clock::now();
             cudaHostUnregister(reinterpret_cast<void *>(lo));
@@ -401,7 +407,7 @@ extern "C" int rt_upload(rt_tape *t, const int16_t *rows, uint64_t nrows) {
       uint64_t n = std::min(stage_rows ? stage_rows : nrows - done, nrows - done);
       rc = enqueue_chunk(t, rows + done * nh, n, buf);
       if (rc) return rc;
-      done += n; buf ^= 1; }
+      done += n; buf = (buf + 1) % t->nstage; }
    t->h2d_bytes += nrows * nh * 2;
    return tape_drain(t); }
 
@@ -465,7 +471,7 @@ extern "C" void rt_close(rt_tape *t) {
    cudaFree(t->planes); cudaFree(t->gmm); cudaFree(t->d_first_end); cudaFree(t->planes_inv); cudaFree(t->gmm_inv);
    cudaFree(t->pool_cache); cudaFree(t->next_cache); if (t->pin_cache) cudaFreeHost(t->pin_cache);
    cudaFree(t->rec_cache); cudaFree(t->pm.mc); cudaFree(t->pm.md); cudaFree(t->pm.ma);
-   for (int i = 0; i < 2; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
+   for (int i = 0; i < RT_STAGE_BUFS; ++i) { cudaFree(t->d_stage[i]); if (t->stage_done[i]) cudaEventDestroy(t->stage_done[i]); if (t->stage_copied[i]) cudaEventDestroy(t->stage_copied[i]); }
    if (t->h_ring) { cudaFreeHost(t->h_ring); for (auto e : t->ring_done) if (e) cudaEventDestroy(e); }
    if (t->s_copy) cudaStreamDestroy(t->s_copy);
    if (t->s_mask) cudaStreamDestroy(t->s_mask);
@@ -1261,7 +1267,7 @@ extern "C" int rt_bulk_scan_host(rt_tape *t, const int16_t *rows, uint64_t nrows
          const uint64_t n = std::min(stage_rows, nrows - done);
          rc = enqueue_chunk(t, rows + done * nh, n, buf);
          if (rc) { cudaDeviceSynchronize(); release(); t->pool_cache_busy = t->pin_cache_busy = false; delete b; return rc; }
-         done += n; buf ^= 1;
+         done += n; buf = (buf + 1) % t->nstage;
          if (done >= next_mark || done == nrows) {
             cudaEvent_t e; CUS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); CUS(cudaEventRecord(e, t->stream));
             seg_ev.push_back(e); seg_rows_done.push_back(done); next_mark = done + seg_target; } }
