@@ -608,6 +608,10 @@ static int scan_prepare_masks(rt_scan *s) {
 
 static int scan_span(rt_scan *s, uint64_t from, uint64_t to, bool want_events) {
    rt_tape *t = s->tape; const uint32_t nt = t->desc.ntrks;
+   static const bool trace = getenv("RT_TRACE") != nullptr;
+   const auto w0 = std::chrono::steady_clock::now();
+   struct Lap { const std::chrono::steady_clock::time_point w0; uint64_t from, to; bool ev, on; ~Lap() { if (on) fprintf(stderr, "[scan_span] rows [%llu, %llu) = %llu, %s: %.3f ms\n",
+      (unsigned long long)from, (unsigned long long)to, (unsigned long long)(to - from), ev ? "events" : "rewind", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count()); } } lap{w0, from, to, want_events, trace};
    { int rc = scan_prepare_masks(s); if (rc) return rc; }
    for (;;) {
       uint32_t zero = 0;
