@@ -11,5 +11,5 @@ with tempfile.TemporaryDirectory() as d:
         r = subprocess.run(['readtape_b200/bin/readtape_b200'] + doc['options'].split() + [f'-outf={d}/o', cap], capture_output=True, text=True,
                            env=dict(os.environ, RT_STATS='2', RT_TRACE='1'))
     print(r.stderr[-6000:])
-    print('\n'.join(l for l in r.stdout.splitlines() if 'B200 scan' in l))
+    print('\n'.join(l for l in r.stdout.splitlines() if 'B200 scan' in l or l.startswith('[')))
 PY
