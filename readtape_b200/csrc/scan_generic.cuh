@@ -285,7 +285,14 @@ struct QuietTracker {
  * at the row in front of the next candidate is rebuilt from the plane -- bit-identical to having walked there.  Only for the plain
  * peak detector (no -invert / -differentiate), only while the threshold bound covers T0, and only once the window and the FIFO are
  * free of the perturbations a reset leaves behind (TrkState::pure_from). */
-__device__ __forceinline__ float gvolts(const DevCfg &c, int x) { return (float)x / 32767 * c.maxvolts; }
+/* x / 32767.0f without the division subroutine: q0 = x*r, e = fma(-32767, q0, x), q = fma(e, r, q0) with r = RN(1/32767) is
+   bit-identical to the IEEE quotient for every int16 x (exhaustive check in tests/test_sparse_host.py, the same routine as
+   rtfast::div32767 in scan_fast.cuh) */
+__device__ __forceinline__ float exact_div32767(float xf) {
+   const float r = 1.0f / 32767.0f;
+   const float q0 = __fmul_rn(xf, r);
+   return __fmaf_rn(__fmaf_rn(-32767.0f, q0, xf), r, q0); }
+__device__ __forceinline__ float gvolts(const DevCfg &c, int x) { return exact_div32767((float)x) * c.maxvolts; }
 
 /* the lazy minimum (int16 domain) at plane row pr, exact value m at plane row pr0 < pr; see SparseScan::lazy_min (scan_sparse.cuh) */
 __device__ inline int lazy_min_hop(const int16_t *plane, const uint32_t *acan, int w, int64_t pr0, int64_t pr, int m) {
@@ -319,7 +326,12 @@ __device__ inline bool skip_to(const DevCfg &c, TrkState &t, SkewState &s, int t
    const int64_t pr0 = (int64_t)cur - delay, pr = (int64_t)r - delay;
    /* the int16 sample that carries the lazy minimum now */
    int m = 32768;
-   for (int i = 0; i < w; ++i) { const int x = plane[pr0 - w + 1 + i]; if (gvolts(c, x) == t.minv) { m = x; break; } }
+   {  /* gvolts is strictly monotone, so the int16 value whose voltage is minv is found by inverting once and checking the neighbours;
+         the window is then searched with integer compares (first occurrence, as before) */
+      int guess = (int)rintf(t.minv / c.maxvolts * 32767.0f), mi = 32768;
+      for (int d = -2; d <= 2; ++d) { const int x = guess + d; if (x >= -32768 && x <= 32767 && gvolts(c, x) == t.minv) { mi = x; break; } }
+      if (mi == 32768) return false;
+      for (int i = 0; i < w; ++i) if ((int)plane[pr0 - w + 1 + i] == mi) { m = mi; break; } }
    if (m == 32768) return false;
    m = lazy_min_hop(plane, c.m_acan + (size_t)trk * c.mask_stride, w, pr0, pr, m);
    const uint64_t n = r - cur;
@@ -361,7 +373,7 @@ template <class Emit>
 __device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane,
                                      uint64_t row, Emit &em, float *v_out) {
    /* int16 -> volts, invert, differentiate */
-   float v = (float)plane[row] / 32767 * c.maxvolts;
+   float v = gvolts(c, (int)plane[row]);
    if (c.invert) v = -v;
    if (c.differentiate) {
       float delta = v - s.v_last_raw;
