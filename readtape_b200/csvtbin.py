@@ -71,8 +71,8 @@ def preread(csv: "abi.Csv", ntrks: int, scalefactor: float = 1.0, subsample: int
     m = np.float32(csv.max_abs(HEADER_LINES, n, ntrks, scalefactor))
     mv = np.float32(np.float32(int(np.float32(np.float32(m + np.float32(0.55)) * np.float32(10.0)))) / np.float32(10.0))
     if subsample > 1:
-        tstart += (subsample - 1) * tdelta
-        tdelta *= subsample
+        tstart += ((subsample - 1) * tdelta) & 0xFFFFFFFF          # csvtbin.c:653-654: unsigned 32-bit products, wrap included
+        tdelta = (tdelta * subsample) & 0xFFFFFFFF
     given = np.float32(maxvolts_given)
     if given == 0 or given < mv:
         given = mv

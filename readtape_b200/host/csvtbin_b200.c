@@ -162,7 +162,7 @@ int main(int argc, char **argv) {
    say("after %s samples, the sample delta is %.2lf usec (%u nsec), samples start at %.6lf seconds, and the rounded-up maximum voltage is %.1fV\n",
        commas(npre), (double)tdelta / 1e3, tdelta, (double)tstart / 1e9, pre_maxvolts);
    if (subsample > 1) {
-      tstart += (uint64_t)(subsample - 1) * tdelta; tdelta *= subsample;
+      tstart += (uint32_t)((subsample - 1) * tdelta); tdelta *= subsample;   /* csvtbin.c:653-654: unsigned 32-bit products, wrap included */
       say("for subsampling every %d samples, we adjusted the delta to %.2lf usec (%u nsec), and the sample start to %.6lf seconds\n", subsample, (double)tdelta / 1e3, tdelta, (double)tstart / 1e9); }
    float hdr_maxvolts = maxvolts_opt;
    if (hdr_maxvolts == 0) hdr_maxvolts = pre_maxvolts;

@@ -257,3 +257,61 @@ def test_csv_straight_into_the_tape_scans_like_the_tbin(cuda_lib):
         seen.append((int(ev[0]), int(dg[0]), bad))
         b.free()
     assert seen[0][0] > 10000 and seen[0] == seen[1] and seen[0][2] == 0
+
+
+def _hostile_number(rng):
+    k = int(rng.integers(0, 12))
+    v = rng.normal(0, 3) * (10.0 ** rng.integers(-4, 3))
+    return ["", "-", ".", f"{int(v)}", f"{v:.0f}.", ("%.3f" % v).replace("0.", "."), f"{v:.3e}", f"{v:.25f}", "--1.5", "1.2.3",
+            f"{v:.{int(rng.integers(0, 9))}f}", f"{v:.{int(rng.integers(0, 9))}f}"][k]
+
+
+def _hostile_case(rng):
+    ntrks = int(rng.integers(5, 13)); nl = int(rng.integers(3, 300))
+    lines = ["title", "Time" + "".join(f", c{i}" for i in range(ntrks))]
+    t = 0.0
+    for _ in range(nl):
+        t += 1e-6
+        sep = [", ", ",", " ", " , ", ",,"][int(rng.integers(0, 5))]
+        cols = [f"{t:.8f}"] + [_hostile_number(rng) for _ in range(ntrks if rng.random() > 0.05 else int(rng.integers(0, ntrks + 3)))]
+        ln = sep.join(cols)
+        if rng.random() < 0.03: ln = ""
+        if rng.random() < 0.03: ln += "\r"
+        if rng.random() < 0.02: ln = "x" + ln                  # a time stamp that does not scan: wild header values, still identical
+        lines.append(ln)
+    text = "\n".join(lines) + ("\n" if rng.random() > 0.3 else "")
+    opts = [f"-ntrks={ntrks}"]
+    for p, o in ((0.3, "-invert"), (0.3, f"-scale={rng.uniform(0.5, 2):.3f}"), (0.3, f"-subsample={int(rng.integers(1, 4))}"),
+                 (0.3, f"-skip={int(rng.integers(0, 5))}"), (0.3, "-redo"), (0.3, f"-maxvolts={rng.uniform(0.5, 14):.1f}")):
+        if rng.random() < p:
+            opts.append(o)
+    return text, opts
+
+
+def _fuzz_tool(tool, tmp_path, seed, ncases):
+    """hostile text (garbage, exponents, doubled signs and points, blank lines, CR, missing and surplus columns, every separator the
+    scanner skips) and random options through the unmodified reference tool and ours: the .tbin files must be identical"""
+    if not (os.path.exists(REF_TOOL) and os.path.exists(tool)):
+        pytest.skip("csvtbin_ref / the tool under test not built")
+    rng = np.random.default_rng(seed)
+    for it in range(ncases):
+        text, opts = _hostile_case(rng)
+        got = []
+        for exe, nm in ((REF_TOOL, "a"), (tool, "b")):
+            with open(tmp_path / f"{nm}.csv", "w", newline="") as fh:
+                fh.write(text)
+            out = tmp_path / f"{nm}.tbin"
+            if out.exists():
+                out.unlink()
+            r = subprocess.run([exe] + opts + [nm], capture_output=True, text=True, cwd=str(tmp_path), timeout=120)
+            got.append((r.returncode, masked(out.read_bytes()) if out.exists() and r.returncode == 0 else b""))
+        assert got[0] == got[1], f"case {it} of seed {seed}: options {opts}, {len(got[0][1])} vs {len(got[1][1])} bytes"
+
+
+def test_fuzz_host_tool_on_oracle_backend_against_reference(tmp_path):
+    _fuzz_tool(ORACLE_TOOL, tmp_path, 11, 40)
+
+
+@pytest.mark.gpu
+def test_fuzz_csvtbin_b200_against_reference(tmp_path):
+    _fuzz_tool(CUDA_TOOL, tmp_path, 12, 25)
