@@ -75,6 +75,9 @@ RT_FHD CandRec make_record(const int16_t *plane, const uint32_t *acan, int w, in
                const uint64_t at = rr - (uint64_t)w + 1u + (km & 63u);
                if (at + (uint64_t)w > p) { posm = (int)(at - ws); break; }
                rr = at + (uint64_t)w; } } } }
+   else posm = RT_REC_NOPOS;     /* m is the window's minimum here, a lower bound of the lazily kept one (decoder.c:765 never lowers the running
+                                    minimum when a sample enters): enough to rule the bottom test out, but NOT the detector's state -- the walk
+                                    must not adopt it (found by the host-build fuzz: a later dense-mode stretch started from a wrong minimum) */
    r.m = (int16_t)m; r.posm = (uint8_t)posm;
    if (posm != RT_REC_NOPOS) { r.mprev = posm > 0 ? win[posm - 1] : (int16_t)0; r.mnext = posm < w - 1 ? win[posm + 1] : (int16_t)0; }
    else r.mprev = r.mnext = 0;

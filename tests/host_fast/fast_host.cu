@@ -187,3 +187,22 @@ extern "C" void volts_host_all(float maxvolts, float *out /* [65536], index x + 
    for (int x = -32768; x <= 32767; ++x) out[x + 32768] = rtfast::volts(dc, x); }
 
 extern "C" int fast_host_meta_size(void) { return (int)sizeof(TrkMeta); }
+
+/* debugging aid for tests: the candidate record of plane row p of track trk, with the masks built as sparse_host_scan_unit does */
+extern "C" int rec_host_debug(const int16_t *planes, uint64_t plane_stride, uint64_t nrows, const rt_tape_desc *desc, const rt_scan_cfg *cfg,
+                              float t0_frac, int trk, uint64_t p, CandRec *out, uint32_t *acan_bits /* 64 rows ending at p */, int *T0_out) {
+   DevCfg dc;
+   rtcfg::to_dev(*desc, planes, plane_stride, nrows, cfg, &dc);
+   const float inv_lsb = 32767.0f / dc.maxvolts;
+   const float q = dc.p.pkww_rise * inv_lsb * 0.999f - 2.0f;
+   int T0 = q > 0 ? (int)((q > 70000.0f ? 70000.0f : (float)(int)q) * t0_frac) : 0;
+   const int T1 = T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 65535;
+   const uint64_t nruns = (nrows + rtmask::MASK_RUN - 1) / rtmask::MASK_RUN;
+   const uint64_t ms = 2 * nruns + 4;
+   std::vector<uint32_t> cand(ms * dc.ntrks), cand2(ms * dc.ntrks), acan(ms * dc.ntrks);
+   masks_host_build(planes, plane_stride, dc.ntrks, nruns, dc.width, T0, T1, cand.data(), cand2.data(), acan.data(), ms, 1);
+   const uint32_t *ma = acan.data() + (size_t)trk * ms;
+   *out = rtrec::make_record(planes + (size_t)trk * plane_stride, ma, dc.width, T0, p);
+   for (int i = 0; i < 64; ++i) { const uint64_t r = p - 63 + i; acan_bits[i] = (ma[r >> 5] >> (r & 31)) & 1u; }
+   *T0_out = T0;
+   return (int)((cand[(size_t)trk * ms + (p >> 5)] >> (p & 31)) & 1u); }

@@ -228,7 +228,7 @@ def test_volts_without_division_is_exact(host_lib):
         assert want.dtype == np.float32 and np.array_equal(out.view(np.uint32), want.view(np.uint32)), mv
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 61])       # 61: found by a 400-seed run -- the record mode adopted a window minimum as the lazy one
 def test_sparse_scan_on_adversarial_signals(seed, host_lib, oracle_lib):
     """signals built to stress what real captures rarely do: coarsely quantised levels (long runs of EQUAL samples: every
     leftmost-position and equality rule of lookfor_peak / refine_peak / the lazy minimum is hit), clipping at +-full scale,
