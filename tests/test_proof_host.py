@@ -1,0 +1,122 @@
+"""Soundness of the unit-equivalence proof on the HOST build of the scan kernels.
+
+rt_bulk_lookup() (readtape_b200/csrc/rt_api.cu: unit_covers, unit_tail_covers) decides from the per-track proof data a scan
+kernel leaves behind (TrkMeta: canonical rows, last loud rows, quiet tail) whether the events of a unit scanned from row0 may stand
+in for a fresh reset at ANOTHER row.  The rule is re-stated here in Python and attacked: units cut ANYWHERE (also inside blocks --
+the unit finder is only a heuristic, soundness must not depend on it), reset rows in front of, inside and at the tail of the unit,
+synthetic NRZI tapes with noise and adversarial burst signals for the peak detector (two-pass scan) and the GCR zero-crossing
+path, random parameter sets and skews.  Whenever the rule ACCEPTS, the unit's events must equal the oracle's fresh-reset scan from
+that row, event for event.  (The CUDA kernels instantiate the same __host__ __device__ code; the bridge scans are not modelled.)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from readtape_b200 import abi, evlog, parmsets, synth, tbin
+from test_fast_host import fast_host, make_planes  # noqa: F401  (fixture)
+
+NOROW = 2**64 - 1
+PRESCAN = 256                     # RT_PRESCAN_MIN (rt_dev.h)
+
+
+def _bind(L):
+    L.sparse_host_scan_unit.restype = C.c_int
+    L.sparse_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg), C.c_uint64, C.c_uint64,
+                                        C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    L.fast_host_meta_size.restype = C.c_int
+    return L
+
+
+def scan_unit(L, kind, planes, stride, n, desc, cfg, row0, row_end, frac):
+    nt = desc.ntrks; cap = 1 << 17
+    out = np.zeros((nt, cap), dtype=abi.EVENT_DTYPE); counts = np.zeros(nt, dtype=np.uint32); ms = L.fast_host_meta_size(); meta = np.zeros((nt, ms), dtype=np.uint8)
+    if kind == 'sparse': rc = L.sparse_host_scan_unit(planes.ctypes.data, stride, n, C.byref(desc), C.byref(cfg), row0, row_end, out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, frac, 1, 0)
+    else: rc = L.fast_host_scan_unit(planes.ctypes.data, stride, n, C.byref(desc), C.byref(cfg), row0, row_end, out.ctypes.data, cap, counts.ctypes.data, meta.ctypes.data, 1)
+    if rc != 0: return None, None
+    ev = np.concatenate([out[k, :counts[k]] for k in range(nt)]); ev = ev[np.lexsort((ev['trk'], ev['row']))]
+    m64 = meta[:, :72].copy().view('<u8'); m32 = meta[:, 72:88].copy().view('<u4')
+    metas = [dict(first_event_row=int(r[0]), sync_row=int(r[1]), last_loud_row=int(r[2]), sync_early=int(r[3]), loud_early=int(r[4]), sync_first=int(r[5]),
+                  quiet_from=int(r[6]), last_event_row=int(r[7]), quiet_tail_from=int(r[8]), nevents=int(w[1]), failed=int(w[2])) for r, w in zip(m64, m32)]
+    return ev, metas
+
+
+def covers(metas, det_peak, width, skew, row0, row_end, start_row, tz):
+    if start_row >= row_end: return False
+    if any(m['failed'] for m in metas): return False
+    if start_row == row0: return True
+    pre0 = row0 - PRESCAN if row0 > PRESCAN else 0
+    examined = start_row >= pre0
+    for k, m in enumerate(metas):
+        lead = max(k + (1 if tz else 0), skew[k]); need = start_row + (lead + width + 1 if det_peak else lead + 2)
+        late = examined and m['sync_row'] != NOROW and m['sync_row'] >= need and (m['last_loud_row'] == NOROW or m['last_loud_row'] < start_row)
+        early = examined and m['sync_early'] != NOROW and m['sync_early'] >= need and (m['loud_early'] == NOROW or m['loud_early'] < start_row)
+        if not late and not early: return False
+    return True
+
+
+def tail_covers(metas, row0, row_end, start_row):
+    if start_row < row0 or start_row >= row_end: return False
+    for m in metas:
+        if m['failed']: return False
+        if m['nevents'] and m['last_event_row'] >= start_row: return False
+        if m['quiet_tail_from'] == NOROW or m['quiet_tail_from'] > start_row: return False
+    return True
+
+
+@pytest.mark.parametrize("seeds", [range(1, 5), range(5, 9), range(9, 13)])
+def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
+    L, ora = _bind(fast_host), oracle_lib
+    failures = []; checked = accepted = 0
+    for seed in seeds:
+        rng = np.random.default_rng(seed)
+        style = seed % 3
+        if style == 0:
+            hdr, rows = synth.nrzi_tape(nblocks=int(rng.integers(2, 5)), seed=seed, data_bytes=int(rng.integers(8, 120)), noise_mv=float(rng.choice([2.0, 5.0, 40.0, 150.0])), wobble=0.01)
+            rows = rows.copy(); n = len(rows)
+            desc = abi.make_desc(9, hdr.maxvolts, hdr.tdelta_ns, hdr.tstart_ns if rng.random() < 0.8 else 0)
+            mode, ps = (tbin.MODE_NRZI, parmsets.NRZI); bpi = 800.0
+        else:
+            n = 64 * int(rng.integers(150, 500)); t = np.arange(n); rows = np.zeros((n, 9), dtype=np.int64)
+            for k in range(9):
+                period = rng.uniform(14, 60)
+                amp = rng.uniform(1500, 30000) * (1 + 0.8 * np.sign(np.sin(2 * np.pi * t / rng.uniform(3000, 9000))))
+                gate = (rng.random(n).cumsum() % 2000 > rng.uniform(300, 1500))
+                sig = amp * np.sin(2 * np.pi * t / period + rng.uniform(0, 6)) * gate + rng.uniform(0, 800) * np.sin(2 * np.pi * t / 5000.0) + rng.normal(0, rng.uniform(3, 60), n)
+                q = int(rng.choice([1, 1, 64, 512])); rows[:, k] = np.clip(np.round(sig / q) * q, -32767, 32767)
+            rows = rows.astype('<i2')
+            desc = abi.make_desc(9, 4.4 if style == 1 else 1.5, 1280 if style == 1 else 160, 1_000_000_000)
+            mode, ps = ((tbin.MODE_NRZI, parmsets.NRZI) if rng.random() < 0.5 else (tbin.MODE_PE, parmsets.PE)) if style == 1 else (tbin.MODE_GCR, parmsets.GCR)
+            bpi = float(rng.choice([556, 800, 1600])) if style == 1 else 9042.0
+        skew = [0] * 9 if rng.random() < 0.5 else [int(x) for x in rng.integers(0, 12, 9)]
+        flags = abi.RT_F_FIND_ZEROS if mode == tbin.MODE_GCR else 0
+        cfg = abi.make_cfg(mode, ps[int(rng.integers(0, len(ps)))], bpi, 50.0, flags=flags, skew=skew)
+        det_peak = mode != tbin.MODE_GCR
+        width = ora.L.rt_pkww_width(C.byref(cfg), desc.tdelta_ns) if det_peak else 0
+        planes, stride = make_planes(rows, desc)
+        tape = ora.open(desc); tape.upload(rows)
+        try:
+            sc = tape.scan(cfg)
+        except abi.RtError:
+            tape.close(); continue
+        for _ in range(4):
+            row0 = int(rng.integers(0, n - 3000)); row_end = min(n, row0 + int(rng.integers(2000, 40000)))
+            ev, metas = scan_unit(L, 'sparse' if det_peak else 'zc', planes, stride, n, desc, cfg, row0, row_end, float(rng.choice([0.25, 0.7, 0.06])))
+            if ev is None: continue
+            cands = sorted(set([row0] + [max(0, row0 - int(d)) for d in rng.integers(1, 400, 12)] + [row0 + int(d) for d in rng.integers(1, 3000, 12)] + [row_end - int(d) for d in rng.integers(1, 3000, 8)]))
+            for s in cands:
+                if s >= row_end: continue
+                tz = (desc.tstart_ns + s * desc.tdelta_ns) == 0
+                c = covers(metas, det_peak, width, skew, row0, row_end, s, tz); tl = (not c) and tail_covers(metas, row0, row_end, s)
+                checked += 1
+                if not (c or tl): continue
+                accepted += 1
+                sc.reset(abi.RT_RESET_FULL, s); want, _ = sc.run(row_end - s)
+                a = evlog.to_canon(ev if c else ev[:0]); b = evlog.to_canon(want)
+                if a.tobytes() != b.tobytes():
+                    k = evlog._first_diff(a, b)
+                    failures.append(f"seed {seed} style {style}: unit [{row0}, {row_end}) accepted for a reset at row {s} by the {'covers' if c else 'tail'} rule, "
+                                    f"but event #{k} differs: unit {a[k] if k < len(a) else None} / fresh scan {b[k] if k < len(b) else None} ({len(a)} vs {len(b)} events)")
+        sc.end(); tape.close()
+    assert not failures, "\n".join(failures[:5])
+    assert accepted >= 10, (checked, accepted)
