@@ -6,7 +6,9 @@ in for a fresh reset at ANOTHER row.  The rule is re-stated here in Python and a
 the unit finder is only a heuristic, soundness must not depend on it), reset rows in front of, inside and at the tail of the unit,
 synthetic NRZI tapes with noise and adversarial burst signals for the peak detector (two-pass scan) and the GCR zero-crossing
 path, random parameter sets and skews.  Whenever the rule ACCEPTS, the unit's events must equal the oracle's fresh-reset scan from
-that row, event for event.  (The CUDA kernels instantiate the same __host__ __device__ code; the bridge scans are not modelled.)
+that row, event for event.  Modelled: the quiet rule (late / early pair), the tail rule, the bridge scan (bridge_holds) and the
+chaining of event-free units (units overlap: a unit is scanned past the start of the next).  The CUDA kernels instantiate the same
+__host__ __device__ code.
 """
 import ctypes as C
 
@@ -67,7 +69,7 @@ def tail_covers(metas, row0, row_end, start_row):
 @pytest.mark.parametrize("seeds", [range(1, 5), range(5, 9), range(9, 13)])
 def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
     L, ora = _bind(fast_host), oracle_lib
-    failures = []; checked = accepted = 0
+    failures = []; checked = accepted = bridged = chained = 0
     for seed in seeds:
         rng = np.random.default_rng(seed)
         style = seed % 3
@@ -108,6 +110,20 @@ def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
                 if s >= row_end: continue
                 tz = (desc.tstart_ns + s * desc.tdelta_ns) == 0
                 c = covers(metas, det_peak, width, skew, row0, row_end, s, tz); tl = (not c) and tail_covers(metas, row0, row_end, s)
+                if not c and not tl and det_peak and s < row_end and not any(m['failed'] for m in metas) and s != row0:
+                    # the bridge (bridge_holds): every track that the quiet rule does not prove has a canonical row far enough behind s
+                    pre0 = row0 - PRESCAN if row0 > PRESCAN else 0; examined = s >= pre0; upto = 0; ok = True
+                    for k, m in enumerate(metas):
+                        lead = max(k + (1 if tz else 0), skew[k]); need = s + lead + width + 1
+                        late = examined and m['sync_row'] != NOROW and m['sync_row'] >= need and (m['last_loud_row'] == NOROW or m['last_loud_row'] < s)
+                        early = examined and m['sync_early'] != NOROW and m['sync_early'] >= need and (m['loud_early'] == NOROW or m['loud_early'] < s)
+                        if not late and not early:
+                            if m['sync_row'] != NOROW and m['sync_row'] >= need: upto = max(upto, m['sync_row'])
+                            else: ok = False
+                    if ok and upto and upto - s <= 65536 and upto < row_end:
+                        sc.reset(abi.RT_RESET_FULL, s); evb, done_ = sc.run(upto - s + 1)
+                        if done_ == upto - s + 1 and not any(int(e['row']) <= metas[int(e['trk'])]['sync_row'] for e in evb):
+                            c = True; bridged += 1
                 checked += 1
                 if not (c or tl): continue
                 accepted += 1
@@ -115,8 +131,33 @@ def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
                 a = evlog.to_canon(ev if c else ev[:0]); b = evlog.to_canon(want)
                 if a.tobytes() != b.tobytes():
                     k = evlog._first_diff(a, b)
-                    failures.append(f"seed {seed} style {style}: unit [{row0}, {row_end}) accepted for a reset at row {s} by the {'covers' if c else 'tail'} rule, "
+                    failures.append(f"seed {seed} style {style}: unit [{row0}, {row_end}) accepted for a reset at row {s} ({'covers / bridge' if c else 'tail'} rule), "
                                     f"but event #{k} differs: unit {a[k] if k < len(a) else None} / fresh scan {b[k] if k < len(b) else None} ({len(a)} vs {len(b)} events)")
+        for _ in range(6):
+            # aim at a quiet stretch: A = an event-free unit inside it, B = the unit behind it (reaching into the signal)
+            amp = np.abs(rows.astype(np.int32)).max(axis=1); blk = amp[: n // 256 * 256].reshape(-1, 256).max(axis=1)
+            quiet = np.flatnonzero(blk < 400)
+            if len(quiet) == 0: break
+            r0 = int(quiet[int(rng.integers(0, len(quiet)))]) * 256 + int(rng.integers(0, 200))
+            if r0 > n - 3000: continue
+            r1 = r0 + int(rng.integers(150, 1500)); r2 = min(n, r1 + int(rng.integers(1500, 20000)))
+            frac = float(rng.choice([0.25, 0.7, 0.06]))
+            r1e = min(r2, r1 + int(rng.integers(40, 700)))          # units overlap: A is scanned past the start of B
+            evA, mA = scan_unit(L, 'sparse' if det_peak else 'zc', planes, stride, n, desc, cfg, r0, r1e, frac)
+            evB, mB = scan_unit(L, 'sparse' if det_peak else 'zc', planes, stride, n, desc, cfg, r1, r2, frac)
+            if evA is None or evB is None or len(evA): continue
+            if not all((not m['failed']) and m['sync_first'] != NOROW and m['sync_first'] < r1e for m in mB): continue
+            for s_ in sorted(set([r0] + [max(0, r0 - int(d)) for d in rng.integers(1, 300, 6)] + [r0 + int(d) for d in rng.integers(1, 200, 4)])):
+                if s_ >= r1: continue
+                tz = (desc.tstart_ns + s_ * desc.tdelta_ns) == 0
+                if not covers(mA, det_peak, width, skew, r0, r1e, s_, tz): continue
+                chained += 1
+                sc.reset(abi.RT_RESET_FULL, s_); want, _ = sc.run(r2 - s_)
+                a = evlog.to_canon(evB); b = evlog.to_canon(want)
+                if a.tobytes() != b.tobytes():
+                    k = evlog._first_diff(a, b)
+                    failures.append(f"seed {seed} style {style}: chain [{r0}, {r1e}) -> [{r1}, {r2}) accepted for a reset at row {s_}, but event #{k} differs: "
+                                    f"unit {a[k] if k < len(a) else None} / fresh scan {b[k] if k < len(b) else None} ({len(a)} vs {len(b)} events)")
         sc.end(); tape.close()
     assert not failures, "\n".join(failures[:5])
-    assert accepted >= 10, (checked, accepted)
+    assert accepted >= 10 and bridged + chained >= 1, (checked, accepted, bridged, chained)
