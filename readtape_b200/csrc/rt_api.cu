@@ -1480,12 +1480,18 @@ static bool unit_covers(const BulkCfg &bc, const rt_tape_desc &desc, uint32_t nt
    const bool examined = start_row >= pre0;                     /* quietness before pre0 was never examined */
    const bool tz = rt_row_time(&desc, start_row) == 0.0;
    bool all = true, bridgeable = bc.dc.det == RT_DET_PEAK; uint64_t upto = 0;
+   /* The zero-crossing detectors keep their extremes and their armed flags through quiet rows (decoder.c:617-683: v_top / v_bot and
+      zerocross_*_pending only change at crossings), so "not loud since start_row" is not enough there: a loud excursion of the UNIT's
+      own scan in [row0, start_row) leaves it armed where the fresh scan is not.  For them the unit itself must have been quiet from its
+      first row up to the canonical row (found by the proof-soundness fuzz of tests/test_proof_host.py, end of round 2). */
+   const bool zc = bc.dc.det != RT_DET_PEAK;
+   auto quiet_since = [&](uint64_t loud) { return loud == RT_NOROW || (loud < start_row && (!zc || loud < u.row0)); };
    for (uint32_t k = 0; k < nt; ++k) {
       const uint64_t need = start_row + (uint64_t)fill_of(bc.dc, k, tz);
       /* two recorded (canonical row, last loud row before it) pairs: the end of the unit's first quiet stretch,
          and the last one before its first event; either proves the equivalence */
-      const bool late = examined && m[k].sync_row != RT_NOROW && m[k].sync_row >= need && (m[k].last_loud_row == RT_NOROW || m[k].last_loud_row < start_row);
-      const bool early = examined && m[k].sync_early != RT_NOROW && m[k].sync_early >= need && (m[k].loud_early == RT_NOROW || m[k].loud_early < start_row);
+      const bool late = examined && m[k].sync_row != RT_NOROW && m[k].sync_row >= need && quiet_since(m[k].last_loud_row);
+      const bool early = examined && m[k].sync_early != RT_NOROW && m[k].sync_early >= need && quiet_since(m[k].loud_early);
       if (!late && !early) {
          all = false;
          if (m[k].sync_row != RT_NOROW && m[k].sync_row >= need) upto = std::max(upto, m[k].sync_row); else bridgeable = false; } }

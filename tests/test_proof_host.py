@@ -49,10 +49,12 @@ def covers(metas, det_peak, width, skew, row0, row_end, start_row, tz):
     if start_row == row0: return True
     pre0 = row0 - PRESCAN if row0 > PRESCAN else 0
     examined = start_row >= pre0
+    # zero-crossing detectors keep extremes and armed flags through quiet rows: the unit must have been quiet since ITS first row
+    quiet_since = lambda loud: loud == NOROW or (loud < start_row and (det_peak or loud < row0))      # noqa: E731
     for k, m in enumerate(metas):
         lead = max(k + (1 if tz else 0), skew[k]); need = start_row + (lead + width + 1 if det_peak else lead + 2)
-        late = examined and m['sync_row'] != NOROW and m['sync_row'] >= need and (m['last_loud_row'] == NOROW or m['last_loud_row'] < start_row)
-        early = examined and m['sync_early'] != NOROW and m['sync_early'] >= need and (m['loud_early'] == NOROW or m['loud_early'] < start_row)
+        late = examined and m['sync_row'] != NOROW and m['sync_row'] >= need and quiet_since(m['last_loud_row'])
+        early = examined and m['sync_early'] != NOROW and m['sync_early'] >= need and quiet_since(m['loud_early'])
         if not late and not early: return False
     return True
 
