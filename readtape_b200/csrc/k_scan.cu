@@ -45,30 +45,10 @@ __global__ void k_ctx_scan(DevCfg c, TrkState *st, SkewState *sk, uint64_t row_f
    const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
    TrkState t = st[trk]; SkewState s = sk[trk];
    FlatEmit em{evbuf + (size_t)trk * cap, cap, 0, (uint8_t)trk};
-   float v;
-   /* skip-ahead (scan_generic.cuh): jump from candidate row to candidate row where the masks of phase A are at hand */
-   const bool can_skip = c.m_cand && c.m_acan && c.det == RT_DET_PEAK && !c.invert && !c.differentiate && c.T0[trk] > 0;
-   const float inv_lsb = 32767.0f / c.maxvolts;
-   const uint64_t min_jump = 4;                      /* rebuilding the state costs about as much as walking three rows */
-   unsigned long long n_walk = 0, n_jump = 0, n_jumped = 0, n_nothr = 0, n_short = 0;
-   for (uint64_t row = row_from; row < row_to; ++row) {
-      if (can_skip && t.init_row == RT_NOROW && t.pure_from != RT_NOROW && row > t.pure_from && row > row_from) {
-         /* the integer bound of required_rise (decoder.c:785) as the two-pass scan derives it (SparseScan::thresholds) */
-         const float rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
-         const float q = rise * inv_lsb * 0.999f - 2.0f;
-         if (q > 0 && (q > 70000.0f ? 70000 : (int)q) >= c.T0[trk]) {
-            const uint64_t from = row + (uint64_t)t.countdown;          /* blind until then anyway (decoder.c:778) */
-            const uint64_t nc = next_candidate(c, trk, from < row_to ? from : row_to, row_to);
-            if (nc >= row + min_jump && skip_to(c, t, s, trk, plane, row - 1, nc - 1)) {
-               ++n_jump; n_jumped += nc - row;
-               row = nc;
-               if (row >= row_to) break; }
-            else ++n_short; }
-         else ++n_nothr; }
-      ++n_walk;
-      track_row(c, t, s, trk, plane, row, em, &v); }
+   CtxStats cs{0, 0, 0, 0, 0};
+   ctx_scan_rows(c, t, s, trk, plane, row_from, row_to, em, cs);
    if (trace) printf("[k_ctx_scan] trk %d rows %llu: walked %llu, %llu jumps over %llu rows, threshold below the mask's at %llu rows, next candidate too near at %llu, T0 %d gain %.3f avg_height %.3f\n",
-                     trk, (unsigned long long)(row_to - row_from), n_walk, n_jump, n_jumped, n_nothr, n_short, c.T0[trk], t.agc_gain, t.avg_height);
+                     trk, (unsigned long long)(row_to - row_from), cs.walked, cs.jumps, cs.jumped, cs.nothr, cs.near, c.T0[trk], t.agc_gain, t.avg_height);
    st[trk] = t; sk[trk] = s;
    counts[trk] = em.n;
    if (t.failed) atomicMax(failed, (uint32_t)t.failed); }

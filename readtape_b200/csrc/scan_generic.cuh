@@ -27,20 +27,38 @@
 #include "feedback.cuh"
 #include "quiet.cuh"
 
+/* host + device: tests/host_fast builds this file for the CPU too (the exact scan and its skip-ahead are fuzzed there against the oracle) */
+#define RT_GEN __host__ __device__
+
 namespace rtgen {
 
-__device__ __forceinline__ double row_time(const DevCfg &c, uint64_t row) {
+RT_GEN __forceinline__ int gen_clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+   return __clz((int)v);
+#else
+   return v ? __builtin_clz(v) : 32;
+#endif
+}
+RT_GEN __forceinline__ int gen_ffs32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+   return __ffs((int)v);
+#else
+   return __builtin_ffs((int)v);
+#endif
+}
+
+RT_GEN __forceinline__ double row_time(const DevCfg &c, uint64_t row) {
    long long ns = (long long)(c.tstart_ns + row * c.tdelta_ns);
    return (double)ns / 1e9; }
 
 /* lazily evaluated timenow of the current row */
 struct RowClock {
    const DevCfg &c; uint64_t row; double t; bool have;
-   __device__ RowClock(const DevCfg &c_, uint64_t r) : c(c_), row(r), t(0), have(false) {}
-   __device__ __forceinline__ double now() { if (!have) { t = row_time(c, row); have = true; } return t; } };
+   RT_GEN RowClock(const DevCfg &c_, uint64_t r) : c(c_), row(r), t(0), have(false) {}
+   RT_GEN __forceinline__ double now() { if (!have) { t = row_time(c, row); have = true; } return t; } };
 
 /* ---- clock averaging, decoder.c:533-558 ---------------------------------------------------- */
-__device__ inline void clk_adjust(const DevCfg &c, TrkState &t, float delta) {
+RT_GEN inline void clk_adjust(const DevCfg &c, TrkState &t, float delta) {
    int win = c.p.clk_window; float alpha = c.p.clk_alpha;
    if (win > 0) {
       float old = t.clk_spacing[t.clk_ndx];
@@ -50,7 +68,7 @@ __device__ inline void clk_adjust(const DevCfg &c, TrkState &t, float delta) {
    else if (alpha > 0) t.clk_avg = alpha * delta + (1 - alpha) * t.clk_avg;
    else t.clk_avg = (c.mode & (RT_MODE_PE + RT_MODE_WW)) ? 1 / (c.bpi * c.ips) : 0.0f; }
 
-__device__ inline void clk_force(TrkState &t, float v) {
+RT_GEN inline void clk_force(TrkState &t, float v) {
    for (int i = 0; i < RT_CLKRATE_WINDOW; ++i) t.clk_spacing[i] = v;
    t.clk_avg = v; }
 
@@ -60,7 +78,7 @@ using rtfb::baseline_accumulate;
 using rtfb::nrzi_feedback;
 using rtfb::pe_feedback;
 
-__device__ inline void gcr_addbit(TrkState &t, int bit) {
+RT_GEN inline void gcr_addbit(TrkState &t, int bit) {
    t.datablock = 1;
    if (t.datacount < RT_MAXBLOCK) { t.bit_m2 = t.bit_m1; t.bit_m1 = (uint8_t)bit; ++t.datacount; }
    t.lastbits = (uint8_t)((t.lastbits << 1) | bit);
@@ -71,7 +89,7 @@ __device__ inline void gcr_addbit(TrkState &t, int bit) {
       if (t.resync_bitcount == 5) clk_force(t, t.t_peakdelta);
       ++t.resync_bitcount; } }
 
-__device__ inline void gcr_feedback(const DevCfg &c, TrkState &t, bool top, double t_ev) {
+RT_GEN inline void gcr_feedback(const DevCfg &c, TrkState &t, bool top, double t_ev) {
    float delta = (float)(t_ev - t.t_lastpeak);
    int numbits = 1;
    if (t.datablock) {
@@ -87,7 +105,7 @@ __device__ inline void gcr_feedback(const DevCfg &c, TrkState &t, bool top, doub
 
 /* ---- per-event glue, decoder.c:560-609 ------------------------------------------------------ */
 template <class Emit>
-__device__ inline void transition(const DevCfg &c, TrkState &t, bool top, uint64_t row, Emit &em) {
+RT_GEN inline void transition(const DevCfg &c, TrkState &t, bool top, uint64_t row, Emit &em) {
    double t_ev = top ? t.t_top : t.t_bot;
    float v_top_seen = t.v_top, v_bot_seen = t.v_bot;
    ++t.peakcount;
@@ -101,7 +119,7 @@ __device__ inline void transition(const DevCfg &c, TrkState &t, bool top, uint64
    em.emit(row, t_ev, v_top_seen, v_bot_seen, t.agc_gain, top); }
 
 /* ---- moving-window peak detector, decoder.c:700-810 ------------------------------------------ */
-__device__ inline double refine(const DevCfg &c, TrkState &t, float val, bool top, double timenow) {
+RT_GEN inline double refine(const DevCfg &c, TrkState &t, float val, bool top, double timenow) {
    const int w = c.width;
    int left_distance = 1, prev = -1;
    float adj = 0;
@@ -131,7 +149,7 @@ __device__ inline double refine(const DevCfg &c, TrkState &t, float val, bool to
  * the running maximum leaving a full window -- the state-independent event at which two scans of
  * the same samples that were reset at different rows provably become identical. */
 template <class Emit>
-__device__ inline void peak_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em, unsigned &probe) {
+RT_GEN inline void peak_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em, unsigned &probe) {
    const int w = c.width;
    float leaving = 0;
    probe = 0;
@@ -167,7 +185,7 @@ __device__ inline void peak_step(const DevCfg &c, TrkState &t, float v_now, RowC
 
 /* ---- zero-crossing detectors, decoder.c:617-683 ---------------------------------------------- */
 template <class Emit>
-__device__ inline void zc_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em) {
+RT_GEN inline void zc_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em) {
    if (v_now > 0) {
       t.dn_pending = 0;
       if (t.v_top < v_now) {
@@ -191,7 +209,7 @@ __device__ inline void zc_step(const DevCfg &c, TrkState &t, float v_now, RowClo
    t.v_prev = v_now; }
 
 template <class Emit>
-__device__ inline void dzc_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em) {
+RT_GEN inline void dzc_step(const DevCfg &c, TrkState &t, float v_now, RowClock &clk, Emit &em) {
    if (v_now > 0) {
       if (t.v_top < v_now) t.v_top = v_now;
       if (t.up_pending) {
@@ -216,7 +234,7 @@ __device__ inline void dzc_step(const DevCfg &c, TrkState &t, float v_now, RowCl
 /* The skew FIFO / differentiator state of the generic path. */
 struct SkewState { float vdelayed[RT_MAXSKEWSAMP]; int32_t ndx_next, slots_filled; float v_last_raw; int32_t pad; };
 
-__device__ inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, int trk, uint64_t row, bool time_is_zero) {
+RT_GEN inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, int trk, uint64_t row, bool time_is_zero) {
    /* memset(trkstate,0) + the non-zero members, decoder.c:437-449 */
    char *p = (char *)&t; for (unsigned i = 0; i < sizeof(TrkState); ++i) p[i] = 0;
    p = (char *)&s; for (unsigned i = 0; i < sizeof(SkewState); ++i) p[i] = 0;
@@ -237,11 +255,11 @@ __device__ inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, in
  *                   undifferentiated |v| >= DIFFERENTIATE_THRESHOLD (a reset zeroes v_last_raw, so the
  *                   first delta after it is the sample itself)
  * Conservative: "not loud" is a proof, "loud" may be a false alarm. */
-__device__ __forceinline__ float volts_at(const DevCfg &c, const int16_t *plane, uint64_t j) {
+RT_GEN __forceinline__ float volts_at(const DevCfg &c, const int16_t *plane, uint64_t j) {
    float v = (float)plane[j] / 32767 * c.maxvolts;
    return c.invert ? -v : v; }
 
-__device__ inline float raw_at(const DevCfg &c, const int16_t *plane, uint64_t j) {
+RT_GEN inline float raw_at(const DevCfg &c, const int16_t *plane, uint64_t j) {
    float v = volts_at(c, plane, j);
    if (c.differentiate) {
       float prev = j ? volts_at(c, plane, j - 1) : 0.0f;
@@ -252,13 +270,13 @@ __device__ inline float raw_at(const DevCfg &c, const int16_t *plane, uint64_t j
 
 struct QuietTracker {
    float runmin, runmax, thr; int L; uint64_t last_loud; bool primed, use_int; QuietInt qi;
-   __device__ void init(const DevCfg &c, int trk, float quiet_thr, int quiet_thr_lsb) {
+   RT_GEN void init(const DevCfg &c, int trk, float quiet_thr, int quiet_thr_lsb) {
       L = (c.det == RT_DET_PEAK ? c.width : 1) + c.skew[trk];
       thr = quiet_thr; last_loud = RT_NOROW; primed = false; runmin = runmax = 0;
       use_int = c.det == RT_DET_PEAK && !c.differentiate;          /* quiet.cuh: the int16-domain test both scan kernels share */
       qi.init(L, quiet_thr_lsb); }
    /* feed row j (rows must be fed consecutively); v = raw_at(j) */
-   __device__ void feed(const DevCfg &c, const int16_t *plane, uint64_t j, float v) {
+   RT_GEN void feed(const DevCfg &c, const int16_t *plane, uint64_t j, float v) {
       if (use_int) { qi.feed(plane, j, (int)plane[j]); last_loud = qi.last_loud; return; }
       if (c.det == RT_DET_PEAK) {
          if (!primed) { runmin = runmax = v; primed = true; }
@@ -288,14 +306,20 @@ struct QuietTracker {
 /* x / 32767.0f without the division subroutine: q0 = x*r, e = fma(-32767, q0, x), q = fma(e, r, q0) with r = RN(1/32767) is
    bit-identical to the IEEE quotient for every int16 x (exhaustive check in tests/test_sparse_host.py, the same routine as
    rtfast::div32767 in scan_fast.cuh) */
-__device__ __forceinline__ float exact_div32767(float xf) {
+RT_GEN __forceinline__ float exact_div32767(float xf) {
    const float r = 1.0f / 32767.0f;
+#ifdef __CUDA_ARCH__
    const float q0 = __fmul_rn(xf, r);
-   return __fmaf_rn(__fmaf_rn(-32767.0f, q0, xf), r, q0); }
-__device__ __forceinline__ float gvolts(const DevCfg &c, int x) { return exact_div32767((float)x) * c.maxvolts; }
+   return __fmaf_rn(__fmaf_rn(-32767.0f, q0, xf), r, q0);
+#else
+   const float q0 = xf * r;
+   return fmaf(fmaf(-32767.0f, q0, xf), r, q0);
+#endif
+}
+RT_GEN __forceinline__ float gvolts(const DevCfg &c, int x) { return exact_div32767((float)x) * c.maxvolts; }
 
 /* the lazy minimum (int16 domain) at plane row pr, exact value m at plane row pr0 < pr; see SparseScan::lazy_min (scan_sparse.cuh) */
-__device__ inline int lazy_min_hop(const int16_t *plane, const uint32_t *acan, int w, int64_t pr0, int64_t pr, int m) {
+RT_GEN inline int lazy_min_hop(const int16_t *plane, const uint32_t *acan, int w, int64_t pr0, int64_t pr, int m) {
    int64_t a = pr0; bool have = false;
    {  int64_t wi = pr >> 5;                                       /* last acan row in (pr0, pr] */
       uint32_t bits = acan[wi] & (0xffffffffu >> (31 - (int)(pr & 31)));
@@ -303,7 +327,7 @@ __device__ inline int lazy_min_hop(const int16_t *plane, const uint32_t *acan, i
          const int64_t base = wi << 5;
          if (base + 31 <= pr0) break;
          if (base <= pr0) bits &= (pr0 - base) >= 31 ? 0u : (0xffffffffu << ((int)(pr0 - base) + 1));
-         if (bits) { a = base + 31 - __clz((int)bits); have = true; break; }
+         if (bits) { a = base + 31 - gen_clz32(bits); have = true; break; }
          if (base <= pr0 || wi == 0) break;
          --wi; bits = acan[wi]; } }
    int64_t r = have ? a : pr0;
@@ -321,7 +345,7 @@ __device__ inline int lazy_min_hop(const int16_t *plane, const uint32_t *acan, i
 
 /* Rebuild the state as it is after row `r` has been processed, coming from the state after row `cur` (cur < r), given that no row in
    (cur, r] can fire.  Window full and pure on entry.  Returns false (state untouched) if the lazy minimum's carrier cannot be found. */
-__device__ inline bool skip_to(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane, uint64_t cur, uint64_t r) {
+RT_GEN inline bool skip_to(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane, uint64_t cur, uint64_t r) {
    const int w = c.width, delay = c.skew[trk];
    const int64_t pr0 = (int64_t)cur - delay, pr = (int64_t)r - delay;
    /* the int16 sample that carries the lazy minimum now */
@@ -354,14 +378,14 @@ __device__ inline bool skip_to(const DevCfg &c, TrkState &t, SkewState &s, int t
    return true; }
 
 /* first stream row >= `from` (and < `to`) whose candidate bit is set; `to` if there is none */
-__device__ inline uint64_t next_candidate(const DevCfg &c, int trk, uint64_t from, uint64_t to) {
+RT_GEN inline uint64_t next_candidate(const DevCfg &c, int trk, uint64_t from, uint64_t to) {
    const int delay = c.skew[trk];
    const uint32_t *mc = c.m_cand + (size_t)trk * c.mask_stride;
    uint64_t p = from - (uint64_t)delay; const uint64_t pend = to - (uint64_t)delay;
    uint64_t wi = p >> 5;
    uint32_t bits = mc[wi] & (0xffffffffu << (int)(p & 31));
    for (;;) {
-      if (bits) { const uint64_t q = (wi << 5) + (uint64_t)(__ffs((int)bits) - 1); return q < pend ? q + (uint64_t)delay : to; }
+      if (bits) { const uint64_t q = (wi << 5) + (uint64_t)(gen_ffs32(bits) - 1); return q < pend ? q + (uint64_t)delay : to; }
       ++wi;
       if ((wi << 5) >= pend) return to;
       bits = mc[wi]; } }
@@ -370,7 +394,7 @@ __device__ inline uint64_t next_candidate(const DevCfg &c, int trk, uint64_t fro
 /* returns the probe bits of peak_step (0 for the other detectors / skipped rows);
    *v_out = the sample before the deskew FIFO (after invert/differentiate) */
 template <class Emit>
-__device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane,
+RT_GEN inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane,
                                      uint64_t row, Emit &em, float *v_out) {
    /* int16 -> volts, invert, differentiate */
    float v = gvolts(c, (int)plane[row]);
@@ -409,5 +433,33 @@ __device__ inline unsigned track_row(const DevCfg &c, TrkState &t, SkewState &s,
          && clk.now() > t.t_lastpeak + RT_GCR_IDLE_THRESH * (double)t.clk_avg)
       t.datablock = 0;
    return probe; }
+
+/* ---- a span of rows of one track of the stateful exact scan (k_ctx_scan), with the skip-ahead ---------------------------------- */
+struct CtxStats { unsigned long long walked, jumps, jumped, nothr, near; };
+
+template <class Emit>
+RT_GEN inline void ctx_scan_rows(const DevCfg &c, TrkState &t, SkewState &s, int trk, const int16_t *plane, uint64_t row_from, uint64_t row_to,
+                                 Emit &em, CtxStats &cs) {
+   float v;
+   /* skip-ahead: jump from candidate row to candidate row where the masks of phase A are at hand */
+   const bool can_skip = c.m_cand && c.m_acan && c.det == RT_DET_PEAK && !c.invert && !c.differentiate && c.T0[trk] > 0;
+   const float inv_lsb = 32767.0f / c.maxvolts;
+   const uint64_t min_jump = 4;                      /* rebuilding the state costs about as much as walking three rows */
+   for (uint64_t row = row_from; row < row_to; ++row) {
+      if (can_skip && t.init_row == RT_NOROW && t.pure_from != RT_NOROW && row > t.pure_from && row > row_from) {
+         /* the integer bound of required_rise (decoder.c:785) as the two-pass scan derives it (SparseScan::thresholds) */
+         const float rise = c.p.pkww_rise * (t.avg_height / RT_PKWW_PEAKHEIGHT) / t.agc_gain;
+         const float q = rise * inv_lsb * 0.999f - 2.0f;
+         if (q > 0 && (q > 70000.0f ? 70000 : (int)q) >= c.T0[trk]) {
+            const uint64_t from = row + (uint64_t)t.countdown;          /* blind until then anyway (decoder.c:778) */
+            const uint64_t nc = next_candidate(c, trk, from < row_to ? from : row_to, row_to);
+            if (nc >= row + min_jump && skip_to(c, t, s, trk, plane, row - 1, nc - 1)) {
+               ++cs.jumps; cs.jumped += nc - row;
+               row = nc;
+               if (row >= row_to) break; }
+            else ++cs.near; }
+         else ++cs.nothr; }
+      ++cs.walked;
+      track_row(c, t, s, trk, plane, row, em, &v); } }
 
 }  // namespace rtgen

@@ -206,3 +206,55 @@ extern "C" int rec_host_debug(const int16_t *planes, uint64_t plane_stride, uint
    for (int i = 0; i < 64; ++i) { const uint64_t r = p - 63 + i; acan_bits[i] = (ma[r >> 5] >> (r & 31)) & 1u; }
    *T0_out = T0;
    return (int)((cand[(size_t)trk * ms + (p >> 5)] >> (p & 31)) & 1u); }
+
+/* ---- the exact stateful scan (scan_generic.cuh: what k_ctx_scan runs per track) on the host -----------------------------------------
+ * Fresh RT_RESET_FULL at reset_row, then rows [reset_row, row_to) in spans of span_rows (one span = one kernel launch of the
+ * library), with the skip-ahead over the mask planes (use_masks; T0 = t0_frac of the default-state bound, as scan_prepare_masks
+ * chooses it) or walking every row.  stats[5]: rows walked, jumps, rows jumped over, rows with the threshold below the masks',
+ * candidates too near.  The events must equal the oracle's whatever the spans and the masks. */
+#include "scan_generic.cuh"
+struct GenEmit {
+   rt_event *buf; uint32_t cap, n; uint8_t trk;
+   void emit(uint64_t row, double t_ev, float v_top, float v_bot, float agc, bool top) {
+      if (n < cap) {
+         rt_event e;
+         e.row = row; e.t_event = t_ev; e.v_top = v_top; e.v_bot = v_bot; e.agc_gain = agc;
+         e.trk = trk; e.kind = top ? RT_EV_TOP : RT_EV_BOT; e.pad[0] = e.pad[1] = 0;
+         buf[n] = e; }
+      ++n; } };
+
+extern "C" int generic_host_ctx_scan(const int16_t *planes, uint64_t plane_stride, uint64_t nrows, const rt_tape_desc *desc, const rt_scan_cfg *cfg,
+                                     uint64_t reset_row, uint64_t row_to, uint64_t span_rows, int use_masks, float t0_frac,
+                                     rt_event *out, uint32_t cap, uint32_t *counts, unsigned long long *stats) {
+   DevCfg dc;
+   rtcfg::to_dev(*desc, planes, plane_stride, nrows, cfg, &dc);
+   if (row_to > nrows) row_to = nrows;
+   std::vector<uint32_t> cand, cand2, acan;
+   if (use_masks && dc.det == RT_DET_PEAK && !dc.invert && !dc.differentiate && dc.width >= 3 && dc.width <= RT_PKWW_MAX_WIDTH) {
+      const float inv_lsb = 32767.0f / dc.maxvolts;
+      const float q = dc.p.pkww_rise * inv_lsb * 0.999f - 2.0f;
+      int T0 = q > 0 ? (int)((float)(q > 70000.0f ? 70000 : (int)q) * t0_frac) : 0;
+      if (T0 > 65535) T0 = 65535;
+      if (T0 >= 16) {
+         const int T1 = T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 65535;
+         const uint64_t nruns = (nrows + rtmask::MASK_RUN - 1) / rtmask::MASK_RUN;
+         if (nruns * rtmask::MASK_RUN > plane_stride) return RT_ERR_ARG;
+         const uint64_t ms = 2 * nruns + 4;
+         cand.assign((size_t)ms * dc.ntrks, 0); cand2.assign((size_t)ms * dc.ntrks, 0); acan.assign((size_t)ms * dc.ntrks, 0);
+         masks_host_build(planes, plane_stride, dc.ntrks, nruns, dc.width, T0, T1, cand.data(), cand2.data(), acan.data(), ms, 1);
+         dc.m_cand = cand.data(); dc.m_cand2 = cand2.data(); dc.m_acan = acan.data(); dc.mask_stride = ms;
+         for (int k = 0; k < RT_MAXTRKS; ++k) { dc.T0[k] = T0; dc.T1[k] = T1; } } }
+   rtgen::CtxStats cs{0, 0, 0, 0, 0};
+   const bool tz = rtgen::row_time(dc, reset_row) == 0.0;
+   int failed = 0;
+   for (int k = 0; k < dc.ntrks; ++k) {
+      TrkState t; rtgen::SkewState s;
+      rtgen::reset_full(dc, t, s, k, reset_row, tz);
+      GenEmit em{out + (size_t)k * cap, cap, 0, (uint8_t)k};
+      const int16_t *plane = planes + (size_t)k * plane_stride;
+      for (uint64_t from = reset_row; from < row_to; from += span_rows)
+         rtgen::ctx_scan_rows(dc, t, s, k, plane, from, from + span_rows < row_to ? from + span_rows : row_to, em, cs);
+      counts[k] = em.n;
+      if (t.failed) failed = t.failed; }
+   if (stats) { stats[0] = cs.walked; stats[1] = cs.jumps; stats[2] = cs.jumped; stats[3] = cs.nothr; stats[4] = cs.near; }
+   return failed ? -100 - failed : RT_OK; }
