@@ -132,8 +132,13 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
    struct Cache { std::vector<uint32_t> cand, cand2, acan, gmm; uint64_t mask_stride, ngran;
                   std::vector<CandRec> recs; std::vector<uint32_t> tbase, tcnt; uint64_t rec_tiles; };
    const int T1 = T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 65535;      /* a second plane at 1.6 x T0, as the library does for a fixed RT_SPARSE_T0 */
-   static std::map<std::tuple<const int16_t *, uint64_t, int, int, int>, Cache> cache;
-   auto key = std::make_tuple(planes, nrows, dc.ntrks, dc.width, T0);
+   /* keyed by the CONTENT of the planes too: a test's next array may well land at the address of the last one */
+   uint64_t fp = 1469598103934665603ull;
+   for (int k = 0; k < dc.ntrks; ++k) {
+      const int16_t *pl = planes + (size_t)k * plane_stride;
+      for (uint64_t r = 0; r < nrows; ++r) fp = (fp ^ (uint16_t)pl[r]) * 1099511628211ull; }
+   static std::map<std::tuple<const int16_t *, uint64_t, int, int, int, uint64_t>, Cache> cache;
+   auto key = std::make_tuple(planes, nrows, dc.ntrks, dc.width, T0, fp);
    auto it = cache.find(key);
    if (it == cache.end()) {
       if (cache.size() > 8) cache.clear();
