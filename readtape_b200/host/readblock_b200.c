@@ -287,12 +287,15 @@ static void continue_exact(struct evsrc *src) {
    src->taken = taken; src->last_row = last_row; src->last_trk = last_trk; }
 
 /* diagnostics (RT_STATS=2): why no speculative unit could be proven equivalent to a fresh reset at `row` */
+/* the rule of unit_covers (rt_api.cu): no loud row since the reset row -- and, for the zero-crossing detectors, none since the unit's own first row */
+static int quiet_since(const rt_unit_info *ui, uint64_t loud, uint64_t row) {
+   return loud == UINT64_MAX || (loud < row && (!find_zeros || loud < ui->row0)); }
 static void say_unit(const rt_unit_info *ui, uint64_t row, int all) {
    rlog("     unit %llu of %llu [%llu, %llu)\n", (unsigned long long)ui->unit_index, (unsigned long long)ui->nunits,
         (unsigned long long)ui->row0, (unsigned long long)ui->row_end);
    for (uint32_t k = 0; k < ui->ntrks; ++k) {
-      const int late = ui->sync_row[k] != UINT64_MAX && ui->sync_row[k] >= ui->need_sync_row[k] && (ui->last_loud_row[k] == UINT64_MAX || ui->last_loud_row[k] < row);
-      const int early = ui->sync_early[k] != UINT64_MAX && ui->sync_early[k] >= ui->need_sync_row[k] && (ui->loud_early[k] == UINT64_MAX || ui->loud_early[k] < row);
+      const int late = ui->sync_row[k] != UINT64_MAX && ui->sync_row[k] >= ui->need_sync_row[k] && quiet_since(ui, ui->last_loud_row[k], row);
+      const int early = ui->sync_early[k] != UINT64_MAX && ui->sync_early[k] >= ui->need_sync_row[k] && quiet_since(ui, ui->loud_early[k], row);
       if ((late || early) && !all) continue;
       rlog("       trk %u%s: first event %lld, sync %lld (loud %lld), early sync %lld (loud %lld), need %lld, failed %u, events %u\n", k, late || early ? " ok" : "",
            (long long)ui->first_event_row[k], (long long)ui->sync_row[k], (long long)ui->last_loud_row[k], (long long)ui->sync_early[k],
