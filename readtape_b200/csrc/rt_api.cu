@@ -23,6 +23,7 @@
 #include "scan_records.cuh"
 #include "kernels.h"
 #include "cfg_host.h"
+#include "lookup_rules.h"
 #include "rt_internal.h"
 
 using rtgen::SkewState;
@@ -716,9 +717,7 @@ struct rt_bulk {
    uint64_t n_bridged = 0;
 };
 
-static int fill_of(const DevCfg &dc, uint32_t k, bool tz) {
-   int lead = std::max<int>((int)k + (tz ? 1 : 0), dc.skew[k]);
-   return dc.det == RT_DET_PEAK ? lead + dc.width + 1 : lead + 2; }
+using rtlookup::fill_of;                                      /* lookup_rules.h */
 
 /* Everything derived from one configuration that the unit finder and the scan kernels need. */
 struct ScanPlan { DevCfg dc; UnitParams up; float quiet_thr; int quiet_thr_lsb; bool use_fast; bool use_sparse; bool t0_auto; };
@@ -1465,38 +1464,10 @@ extern "C" int rt_bulk_unit_at(const rt_bulk *b, uint32_t ci, uint64_t unit_inde
    fill_unit_info(b, bc, (size_t)unit_index, bc.units[unit_index].row0, out);
    return RT_OK; }
 
-/* Can unit `ui` stand in for a fresh RT_RESET_FULL at `start_row`?  (DESIGN.md "unit equivalence")
-   *bridge_to (if given) is set when the only thing missing is the quietness of the rows between start_row and the unit's canonical
-   rows: the row up to which an exact scan from start_row has to stay event-free for the equivalence to hold all the same (see
-   bridge_holds); RT_NOROW if that cannot help. */
+/* Can unit `ui` stand in for a fresh RT_RESET_FULL at `start_row`?  The rules live in lookup_rules.h (DESIGN.md "unit equivalence"),
+   which the CPU test harness compiles too. */
 static bool unit_covers(const BulkCfg &bc, const rt_tape_desc &desc, uint32_t nt, size_t ui, uint64_t start_row, uint64_t *bridge_to = nullptr) {
-   if (bridge_to) *bridge_to = RT_NOROW;
-   const UnitDesc &u = bc.units[ui];
-   const TrkMeta *m = &bc.meta[ui * nt];
-   if (start_row >= u.row_end) return false;
-   for (uint32_t k = 0; k < nt; ++k) if (m[k].failed) return false;
-   if (start_row == u.row0) return true;                        /* the very same reset: trivially identical */
-   const uint64_t pre0 = u.row0 > (uint64_t)bc.dc.prescan_rows ? u.row0 - (uint64_t)bc.dc.prescan_rows : 0;
-   const bool examined = start_row >= pre0;                     /* quietness before pre0 was never examined */
-   const bool tz = rt_row_time(&desc, start_row) == 0.0;
-   bool all = true, bridgeable = bc.dc.det == RT_DET_PEAK; uint64_t upto = 0;
-   /* The zero-crossing detectors keep their extremes and their armed flags through quiet rows (decoder.c:617-683: v_top / v_bot and
-      zerocross_*_pending only change at crossings), so "not loud since start_row" is not enough there: a loud excursion of the UNIT's
-      own scan in [row0, start_row) leaves it armed where the fresh scan is not.  For them the unit itself must have been quiet from its
-      first row up to the canonical row (found by the proof-soundness fuzz of tests/test_proof_host.py, end of round 2). */
-   const bool zc = bc.dc.det != RT_DET_PEAK;
-   auto quiet_since = [&](uint64_t loud) { return loud == RT_NOROW || (loud < start_row && (!zc || loud < u.row0)); };
-   for (uint32_t k = 0; k < nt; ++k) {
-      const uint64_t need = start_row + (uint64_t)fill_of(bc.dc, k, tz);
-      /* two recorded (canonical row, last loud row before it) pairs: the end of the unit's first quiet stretch,
-         and the last one before its first event; either proves the equivalence */
-      const bool late = examined && m[k].sync_row != RT_NOROW && m[k].sync_row >= need && quiet_since(m[k].last_loud_row);
-      const bool early = examined && m[k].sync_early != RT_NOROW && m[k].sync_early >= need && quiet_since(m[k].loud_early);
-      if (!late && !early) {
-         all = false;
-         if (m[k].sync_row != RT_NOROW && m[k].sync_row >= need) upto = std::max(upto, m[k].sync_row); else bridgeable = false; } }
-   if (!all && bridgeable && bridge_to && upto - start_row <= 65536) *bridge_to = upto;
-   return all; }
+   return rtlookup::unit_covers(bc.dc, bc.units[ui], &bc.meta[ui * nt], nt, start_row, rt_row_time(&desc, start_row) == 0.0, bridge_to); }
 
 /* The bridge: unit `ui` has, on every track, a canonical row c_k (TrkMeta::sync_row: the window maximum has just left a full window,
    so the detector state is a pure function of the samples there) in front of its first event and far enough behind start_row for a
@@ -1519,17 +1490,8 @@ static int bridge_holds(rt_bulk *b, uint32_t ci, size_t ui, uint64_t start_row, 
    *ok = true; ++b->n_bridged;
    return RT_OK; }
 
-/* The tail rule: start_row lies behind every event of unit `ui`, and no row of [start_row, row_end) is loud on any track: a fresh
-   scan from start_row stays in default state (no event, so no feedback) and cannot fire before row_end either. */
-static bool unit_tail_covers(const BulkCfg &bc, uint32_t nt, size_t ui, uint64_t start_row) {
-   const UnitDesc &u = bc.units[ui];
-   const TrkMeta *m = &bc.meta[ui * nt];
-   if (start_row < u.row0 || start_row >= u.row_end) return false;
-   for (uint32_t k = 0; k < nt; ++k) {
-      if (m[k].failed) return false;
-      if (m[k].nevents && m[k].last_event_row >= start_row) return false;
-      if (m[k].quiet_tail_from == RT_NOROW || m[k].quiet_tail_from > start_row) return false; }
-   return true; }
+static bool unit_tail_covers(const BulkCfg &bc, uint32_t nt, size_t ui, uint64_t start_row) {      /* the tail rule, lookup_rules.h */
+   return rtlookup::unit_tail_covers(bc.units[ui], &bc.meta[ui * nt], nt, start_row); }
 
 extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event **events, uint64_t *nevents, uint64_t *valid_rows) {
    if (!b || ci >= b->cfgs.size()) return set_err(RT_ERR_ARG, "rt_bulk_lookup: bad argument");
@@ -1563,17 +1525,8 @@ extern "C" int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const
    /* Chaining: while the unit holds no event at all, the reference's scan passes through it unchanged; it is
       then identical to the NEXT unit's fresh scan from that unit's first canonical row on, provided that row
       lies inside the stretch where this unit has already shown the scan to be event-free (the overlap). */
-   while (lo + 1 < bc.units.size()) {
-      bool empty = true;
-      for (uint32_t k = 0; k < nt; ++k) if (m[k].nevents) { empty = false; break; }
-      if (!empty) break;
-      const TrkMeta *mn = &bc.meta[(lo + 1) * nt];
-      const uint64_t known_quiet_end = bc.units[lo].row_end;
-      bool ok = true;
-      for (uint32_t k = 0; k < nt && ok; ++k)
-         ok = !mn[k].failed && mn[k].sync_first != RT_NOROW && mn[k].sync_first < known_quiet_end;
-      if (!ok) break;
-      ++lo; m = mn; }
+   for (uint64_t from = start_row; lo + 1 < bc.units.size() && rtlookup::chains_into_next(bc.dc, bc.units[lo], m, &bc.meta[(lo + 1) * nt], nt, from); ) {
+      ++lo; m = &bc.meta[lo * nt]; from = bc.units[lo].row0; }      /* the passing scan equals this unit's fresh scan from its first canonical row on */
    const UnitDesc &ue = bc.units[lo];
    /* merge the per-track chunk chains into (row, trk) order */
    struct CC { uint32_t chunk, left, slot; } cc[RT_MAXTRKS];

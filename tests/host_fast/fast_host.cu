@@ -13,6 +13,7 @@
 #include <map>
 #include <tuple>
 #include "cfg_host.h"
+#include "lookup_rules.h"
 
 struct HostEmit {
    rt_event *buf; uint32_t cap, n; uint64_t first_row; uint32_t first_chunk; uint8_t trk; uint64_t last_row;
@@ -263,3 +264,20 @@ extern "C" int generic_host_ctx_scan(const int16_t *planes, uint64_t plane_strid
       if (t.failed) failed = t.failed; }
    if (stats) { stats[0] = cs.walked; stats[1] = cs.jumps; stats[2] = cs.jumped; stats[3] = cs.nothr; stats[4] = cs.near; }
    return failed ? -100 - failed : RT_OK; }
+
+/* ---- the unit-equivalence rules of rt_bulk_lookup (lookup_rules.h: the product's own code) ------------------------------------------
+ * meta = the TrkMeta[ntrks] a *_host_scan_unit call returned for the unit [row0, row_end).  lookup_host_covers: 1 = a fresh reset at
+ * start_row is covered (quiet rule), 0 = not; *bridge_to as unit_covers sets it.  lookup_host_tail / lookup_host_chain: the tail rule
+ * and the chaining of an event-free unit into the next one. */
+extern "C" int lookup_host_covers(const rt_tape_desc *desc, const rt_scan_cfg *cfg, uint64_t row0, uint64_t row_end, const TrkMeta *meta, uint64_t start_row, uint64_t *bridge_to) {
+   DevCfg dc; rtcfg::to_dev(*desc, nullptr, 0, 0, cfg, &dc);
+   const UnitDesc u{row0, row_end};
+   const bool tz = (long long)(dc.tstart_ns + start_row * dc.tdelta_ns) == 0;
+   return rtlookup::unit_covers(dc, u, meta, (uint32_t)dc.ntrks, start_row, tz, bridge_to) ? 1 : 0; }
+extern "C" int lookup_host_tail(const rt_tape_desc *desc, uint64_t row0, uint64_t row_end, const TrkMeta *meta, uint64_t start_row) {
+   const UnitDesc u{row0, row_end};
+   return rtlookup::unit_tail_covers(u, meta, desc->ntrks, start_row) ? 1 : 0; }
+extern "C" int lookup_host_chain(const rt_tape_desc *desc, const rt_scan_cfg *cfg, uint64_t row0, uint64_t row_end, const TrkMeta *meta, const TrkMeta *meta_next, uint64_t start_row) {
+   DevCfg dc; rtcfg::to_dev(*desc, nullptr, 0, 0, cfg, &dc);
+   const UnitDesc u{row0, row_end};
+   return rtlookup::chains_into_next(dc, u, meta, meta_next, desc->ntrks, start_row) ? 1 : 0; }

@@ -1,8 +1,9 @@
 """Soundness of the unit-equivalence proof on the HOST build of the scan kernels.
 
-rt_bulk_lookup() (readtape_b200/csrc/rt_api.cu: unit_covers, unit_tail_covers) decides from the per-track proof data a scan
-kernel leaves behind (TrkMeta: canonical rows, last loud rows, quiet tail) whether the events of a unit scanned from row0 may stand
-in for a fresh reset at ANOTHER row.  The rule is re-stated here in Python and attacked: units cut ANYWHERE (also inside blocks --
+rt_bulk_lookup() (readtape_b200/csrc/lookup_rules.h: unit_covers, unit_tail_covers, chains_into_next) decides from the per-track
+proof data a scan kernel leaves behind (TrkMeta: canonical rows, last loud rows, quiet tail) whether the events of a unit scanned
+from row0 may stand in for a fresh reset at ANOTHER row.  The product's own rule code (the header is compiled into the host build,
+lookup_host_* in tests/host_fast/fast_host.cu) is attacked: units cut ANYWHERE (also inside blocks --
 the unit finder is only a heuristic, soundness must not depend on it), reset rows in front of, inside and at the tail of the unit,
 synthetic NRZI tapes with noise and adversarial burst signals for the peak detector (two-pass scan) and the GCR zero-crossing
 path, random parameter sets and skews.  Whenever the rule ACCEPTS, the unit's events must equal the oracle's fresh-reset scan from
@@ -27,7 +28,18 @@ def _bind(L):
     L.sparse_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg), C.c_uint64, C.c_uint64,
                                         C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
     L.fast_host_meta_size.restype = C.c_int
+    L.lookup_host_covers.restype = C.c_int
+    L.lookup_host_covers.argtypes = [C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.lookup_host_tail.restype = C.c_int
+    L.lookup_host_tail.argtypes = [C.POINTER(abi.TapeDesc), C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.lookup_host_chain.restype = C.c_int
+    L.lookup_host_chain.argtypes = [C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
     return L
+
+
+class Metas(list):
+    """the proof data of one unit: parsed per track (for messages and the test's own bookkeeping) + the raw TrkMeta[] the rules take"""
+    raw = None
 
 
 def scan_unit(L, kind, planes, stride, n, desc, cfg, row0, row_end, frac):
@@ -38,37 +50,28 @@ def scan_unit(L, kind, planes, stride, n, desc, cfg, row0, row_end, frac):
     if rc != 0: return None, None
     ev = np.concatenate([out[k, :counts[k]] for k in range(nt)]); ev = ev[np.lexsort((ev['trk'], ev['row']))]
     m64 = meta[:, :72].copy().view('<u8'); m32 = meta[:, 72:88].copy().view('<u4')
-    metas = [dict(first_event_row=int(r[0]), sync_row=int(r[1]), last_loud_row=int(r[2]), sync_early=int(r[3]), loud_early=int(r[4]), sync_first=int(r[5]),
-                  quiet_from=int(r[6]), last_event_row=int(r[7]), quiet_tail_from=int(r[8]), nevents=int(w[1]), failed=int(w[2])) for r, w in zip(m64, m32)]
+    metas = Metas(dict(first_event_row=int(r[0]), sync_row=int(r[1]), last_loud_row=int(r[2]), sync_early=int(r[3]), loud_early=int(r[4]), sync_first=int(r[5]),
+                  quiet_from=int(r[6]), last_event_row=int(r[7]), quiet_tail_from=int(r[8]), nevents=int(w[1]), failed=int(w[2])) for r, w in zip(m64, m32))
+    metas.raw = np.ascontiguousarray(meta)
     return ev, metas
 
 
-def covers(metas, det_peak, width, skew, row0, row_end, start_row, tz):
-    if start_row >= row_end: return False
-    if any(m['failed'] for m in metas): return False
-    if start_row == row0: return True
-    pre0 = row0 - PRESCAN if row0 > PRESCAN else 0
-    examined = start_row >= pre0
-    # zero-crossing detectors keep extremes and armed flags through quiet rows: the unit must have been quiet since ITS first row
-    quiet_since = lambda loud: loud == NOROW or (loud < start_row and (det_peak or loud < row0))      # noqa: E731
-    for k, m in enumerate(metas):
-        lead = max(k + (1 if tz else 0), skew[k]); need = start_row + (lead + width + 1 if det_peak else lead + 2)
-        late = examined and m['sync_row'] != NOROW and m['sync_row'] >= need and quiet_since(m['last_loud_row'])
-        early = examined and m['sync_early'] != NOROW and m['sync_early'] >= need and quiet_since(m['loud_early'])
-        if not late and not early: return False
-    return True
+def covers(L, desc, cfg, metas, row0, row_end, start_row):
+    """rtlookup::unit_covers -> (covered, bridge_to or None)"""
+    br = C.c_uint64(NOROW)
+    ok = L.lookup_host_covers(C.byref(desc), C.byref(cfg), row0, row_end, metas.raw.ctypes.data, start_row, C.byref(br))
+    return bool(ok), (None if br.value == NOROW else int(br.value))
 
 
-def tail_covers(metas, row0, row_end, start_row):
-    if start_row < row0 or start_row >= row_end: return False
-    for m in metas:
-        if m['failed']: return False
-        if m['nevents'] and m['last_event_row'] >= start_row: return False
-        if m['quiet_tail_from'] == NOROW or m['quiet_tail_from'] > start_row: return False
-    return True
+def tail_covers(L, desc, metas, row0, row_end, start_row):
+    return bool(L.lookup_host_tail(C.byref(desc), row0, row_end, metas.raw.ctypes.data, start_row))
 
 
-@pytest.mark.parametrize("seeds", [range(1, 5), range(5, 9), range(9, 13)])
+def chains(L, desc, cfg, metas, row0, row_end, metas_next, start_row):
+    return bool(L.lookup_host_chain(C.byref(desc), C.byref(cfg), row0, row_end, metas.raw.ctypes.data, metas_next.raw.ctypes.data, start_row))
+
+
+@pytest.mark.parametrize("seeds", [range(1, 5), range(5, 9), range(9, 13), [188, 4, 7]])     # 188: an event-free but LOUD zero-crossing unit was chained into the next one
 def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
     L, ora = _bind(fast_host), oracle_lib
     failures = []; checked = accepted = bridged = chained = 0
@@ -110,22 +113,12 @@ def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
             cands = sorted(set([row0] + [max(0, row0 - int(d)) for d in rng.integers(1, 400, 12)] + [row0 + int(d) for d in rng.integers(1, 3000, 12)] + [row_end - int(d) for d in rng.integers(1, 3000, 8)]))
             for s in cands:
                 if s >= row_end: continue
-                tz = (desc.tstart_ns + s * desc.tdelta_ns) == 0
-                c = covers(metas, det_peak, width, skew, row0, row_end, s, tz); tl = (not c) and tail_covers(metas, row0, row_end, s)
-                if not c and not tl and det_peak and s < row_end and not any(m['failed'] for m in metas) and s != row0:
-                    # the bridge (bridge_holds): every track that the quiet rule does not prove has a canonical row far enough behind s
-                    pre0 = row0 - PRESCAN if row0 > PRESCAN else 0; examined = s >= pre0; upto = 0; ok = True
-                    for k, m in enumerate(metas):
-                        lead = max(k + (1 if tz else 0), skew[k]); need = s + lead + width + 1
-                        late = examined and m['sync_row'] != NOROW and m['sync_row'] >= need and (m['last_loud_row'] == NOROW or m['last_loud_row'] < s)
-                        early = examined and m['sync_early'] != NOROW and m['sync_early'] >= need and (m['loud_early'] == NOROW or m['loud_early'] < s)
-                        if not late and not early:
-                            if m['sync_row'] != NOROW and m['sync_row'] >= need: upto = max(upto, m['sync_row'])
-                            else: ok = False
-                    if ok and upto and upto - s <= 65536 and upto < row_end:
-                        sc.reset(abi.RT_RESET_FULL, s); evb, done_ = sc.run(upto - s + 1)
-                        if done_ == upto - s + 1 and not any(int(e['row']) <= metas[int(e['trk'])]['sync_row'] for e in evb):
-                            c = True; bridged += 1
+                c, upto = covers(L, desc, cfg, metas, row0, row_end, s); tl = (not c) and tail_covers(L, desc, metas, row0, row_end, s)
+                if not c and not tl and upto is not None and upto < row_end:
+                    # the bridge (rt_api.cu: bridge_holds): an exact scan from s must stay event-free up to every track's canonical row
+                    sc.reset(abi.RT_RESET_FULL, s); evb, done_ = sc.run(upto - s + 1)
+                    if done_ == upto - s + 1 and not any(int(e['row']) <= metas[int(e['trk'])]['sync_row'] for e in evb):
+                        c = True; bridged += 1
                 checked += 1
                 if not (c or tl): continue
                 accepted += 1
@@ -148,11 +141,9 @@ def test_accepted_resets_reproduce_the_fresh_scan(seeds, fast_host, oracle_lib):
             evA, mA = scan_unit(L, 'sparse' if det_peak else 'zc', planes, stride, n, desc, cfg, r0, r1e, frac)
             evB, mB = scan_unit(L, 'sparse' if det_peak else 'zc', planes, stride, n, desc, cfg, r1, r2, frac)
             if evA is None or evB is None or len(evA): continue
-            if not all((not m['failed']) and m['sync_first'] != NOROW and m['sync_first'] < r1e for m in mB): continue
             for s_ in sorted(set([r0] + [max(0, r0 - int(d)) for d in rng.integers(1, 300, 6)] + [r0 + int(d) for d in rng.integers(1, 200, 4)])):
                 if s_ >= r1: continue
-                tz = (desc.tstart_ns + s_ * desc.tdelta_ns) == 0
-                if not covers(mA, det_peak, width, skew, r0, r1e, s_, tz): continue
+                if not covers(L, desc, cfg, mA, r0, r1e, s_)[0] or not chains(L, desc, cfg, mA, r0, r1e, mB, s_): continue
                 chained += 1
                 sc.reset(abi.RT_RESET_FULL, s_); want, _ = sc.run(r2 - s_)
                 a = evlog.to_canon(evB); b = evlog.to_canon(want)

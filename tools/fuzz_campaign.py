@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""tools/fuzz_campaign.py -- run the seeded CPU fuzz tests of tests/ over seed ranges far beyond what the suite runs.
+
+    python tools/fuzz_campaign.py proof 100 400        # tests/test_proof_host.py, seeds 100..399
+    python tools/fuzz_campaign.py ctx 100 400          # tests/test_ctx_host.py (exact scan with skip-ahead)
+    python tools/fuzz_campaign.py sparse 100 400       # tests/test_sparse_host.py adversarial signals (one seed per call)
+    python tools/fuzz_campaign.py oracle 100 200       # tests/test_oracle_fuzz.py (the instrumented unmodified reference)
+
+Each seed runs in its own pytest-free call of the test function; a failing seed is printed and the campaign goes on.  TEST
+INFRASTRUCTURE: everything here runs the host builds and the oracle, never the product path.
+"""
+import os, sys, tempfile, pathlib, traceback
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ctypes as C
+import subprocess
+
+
+def main():
+    which, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    from readtape_b200 import abi
+    import test_fast_host as tfh
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "host_fast")], stdout=subprocess.DEVNULL)
+    oracle = abi.load_oracle()
+    bad = []
+    def host_lib():
+        import test_sparse_host as tsh
+        return tsh.host_lib.__wrapped__() if hasattr(tsh.host_lib, "__wrapped__") else None
+    L = C.CDLL(tfh.HOST_LIB)
+    L.fast_host_scan_unit.restype = C.c_int
+    L.fast_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    L.sparse_host_scan_unit.restype = C.c_int
+    L.sparse_host_scan_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(abi.TapeDesc), C.POINTER(abi.ScanCfg), C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    L.masks_host_build.restype = C.c_int
+    L.masks_host_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    for seed in range(lo, hi):
+        try:
+            if which == "proof":
+                import test_proof_host as m
+                try: m.test_accepted_resets_reproduce_the_fresh_scan.__wrapped__
+                except AttributeError: pass
+                m.test_accepted_resets_reproduce_the_fresh_scan(range(seed, seed + 1), L, oracle)
+            elif which == "ctx":
+                import test_ctx_host as m
+                m.test_exact_scan_with_skip_ahead_equals_oracle(range(seed, seed + 1), L, oracle)
+            elif which == "sparse":
+                import test_sparse_host as m
+                m.test_sparse_scan_on_adversarial_signals(seed, L, oracle)
+            elif which == "oracle":
+                import test_oracle_fuzz as m
+                with tempfile.TemporaryDirectory() as d:
+                    m.test_oracle_reproduces_the_reference_events_on_adversarial_captures(range(seed, seed + 1), oracle, pathlib.Path(d))
+            else:
+                raise SystemExit("unknown campaign " + which)
+        except AssertionError as e:
+            msg = str(e)
+            # the sanity floors of the tests (enough accepted / bridged / jumped cases in a RANGE of seeds: the message is the tuple
+            # of counts) do not apply to a single seed
+            if msg.startswith("(") and msg.rstrip().endswith(")") and "\n" not in msg: continue
+            bad.append(seed); print(f"[{which}] seed {seed} FAILED: {msg[:600]}", flush=True)
+        except BaseException as e:                                  # pytest.fail raises Failed (a BaseException)
+            if isinstance(e, (KeyboardInterrupt, SystemExit)): raise
+            bad.append(seed); print(f"[{which}] seed {seed} FAILED: {type(e).__name__}: {str(e)[:600]}", flush=True)
+        if (seed - lo) % 20 == 19: print(f"[{which}] .. seed {seed}, {len(bad)} failures so far", flush=True)
+    print(f"[{which}] seeds {lo}..{hi - 1}: {len(bad)} failing seeds {bad}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
