@@ -22,6 +22,9 @@ nvidia-smi --query-gpu=name --format=csv,noheader
 if [ "${QUICK_SET:-a}" = a ]; then
 check Microdata_20blks Microdata_20blks.001.bin 21af9d8842f39722fcd15452662f1709cf1c35b7450810f21470ae2605ce9260 -m -nrzi -hex -ascii -v
 check 132_pt1 132_pt1.tap d861b6751eef576400d546d0e7a97428621197fc1b915ef75b1a6dd6781a4e89 -whirlwind -fluxdir=auto -tap -deskew -octal2 -flexo -v
+elif [ "$QUICK_SET" = c ]; then   # host-side lookup rules after a rebuild: one peak-detector capture, one zero-crossing capture
+check Microdata_20blks Microdata_20blks.001.bin 21af9d8842f39722fcd15452662f1709cf1c35b7450810f21470ae2605ce9260 -m -nrzi -hex -ascii -v
+check 1kblks_43blks 1kblks_43blks.tap 25c703cb5dab51110e8b37091233f98a328e67414497174ca1d8233be04738bd -m -gcr -ips=50 -order=76543210p -zeros -correct -tap -ascii -linefeed -v
 else   # the two GCR -zeros captures: the zero-crossing fast path and its (tightened) unit-equivalence rule
 check sf93_8blks sf93_8blks.tap 452a3e2496df04846539524ae1d5a1a80d6cdcd5d1150c7c19b4efa580c575cf -m -gcr -ips=50 -zeros -correct -tap -ascii -linefeed -v
 check 1kblks_43blks 1kblks_43blks.tap 25c703cb5dab51110e8b37091233f98a328e67414497174ca1d8233be04738bd -m -gcr -ips=50 -order=76543210p -zeros -correct -tap -ascii -linefeed -v
