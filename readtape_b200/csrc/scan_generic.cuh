@@ -250,7 +250,8 @@ RT_GEN inline void reset_full(const DevCfg &c, TrkState &t, SkewState &s, int tr
  * row j -- whatever row it was reset at, full or still filling, delayed or not -- only contains raw
  * samples of rows [j-L+1, j] with L = width + skew delay (peak detector) or 1 + skew delay (zero
  * crossing).  Row j is "loud" if that span could make ANY such scan in default state fire or arm:
- *   peak detector : max - min over the span >= 0.999 * pkww_rise   (required_rise at AGC 1, height 4)
+ *   peak detector : max - min over the span >= 0.999 * pkww_rise   (required_rise at AGC 1, height 4); differentiated: additionally
+ *                   an undifferentiated |v| >= DIFFERENTIATE_THRESHOLD at row j itself (see below)
  *   zero crossing : some |v| > ZEROCROSS_PEAK in the span; differentiated: additionally some
  *                   undifferentiated |v| >= DIFFERENTIATE_THRESHOLD (a reset zeroes v_last_raw, so the
  *                   first delta after it is the sample itself)
@@ -287,7 +288,11 @@ struct QuietTracker {
             uint64_t from = j + 1 >= (uint64_t)L ? j + 1 - L : 0;
             for (uint64_t i = from; i < j; ++i) { float x = raw_at(c, plane, i); if (x > mx) mx = x; if (x < mn) mn = x; }
             runmin = mn; runmax = mx;
-            if (mx - mn >= thr) last_loud = j; } }
+            if (mx - mn >= thr) last_loud = j; }
+         /* -differentiate: a scan reset AT row j sees the sample itself as its first delta (v_last_raw is zeroed, readtape.c:1383-1394,
+            decoder.c:437), a spike no other scan has, unless the dead-band swallows it -- so no reset row may carry |v| beyond it
+            (found by the fuzz of tests/test_proof_generic_host.py, end of round 2) */
+         if (c.differentiate) { const float u = volts_at(c, plane, j); if (u >= RT_DIFF_THRESHOLD || u <= -RT_DIFF_THRESHOLD) last_loud = j; } }
       else {
          bool loud = v > RT_ZEROCROSS_PEAK || v < -RT_ZEROCROSS_PEAK;
          if (c.differentiate) { float u = volts_at(c, plane, j); loud = loud || u >= RT_DIFF_THRESHOLD || u <= -RT_DIFF_THRESHOLD; }

@@ -281,3 +281,50 @@ extern "C" int lookup_host_chain(const rt_tape_desc *desc, const rt_scan_cfg *cf
    DevCfg dc; rtcfg::to_dev(*desc, nullptr, 0, 0, cfg, &dc);
    const UnitDesc u{row0, row_end};
    return rtlookup::chains_into_next(dc, u, meta, meta_next, desc->ntrks, start_row) ? 1 : 0; }
+
+/* ---- the speculative unit scan on the exact generic detector code (k_units_scan, k_scan.cu) on the host ------------------------------
+ * k_units_scan serves what the fast kernels do not: -differentiate (zero-crossing of the differentiated signal, and the peak detector
+ * on it), widths outside the fast path.  Its per-(unit, track) body -- track_row() + QuietTracker + the proof-data bookkeeping -- is
+ * MIRRORED here statement for statement (k_scan.cu:61-100; the detector and the tracker themselves are the shared __host__ __device__
+ * code of scan_generic.cuh), so that the unit-equivalence rules can be attacked for those detectors too (tests/test_proof_host.py).
+ * Keep the two in step; the kernel's body becomes a call of a shared function the next time it can be re-verified on hardware. */
+extern "C" int generic_host_scan_unit(const int16_t *planes, uint64_t plane_stride, uint64_t nrows, const rt_tape_desc *desc, const rt_scan_cfg *cfg,
+                                      uint64_t row0, uint64_t row_end, rt_event *out, uint32_t cap, uint32_t *counts, TrkMeta *meta) {
+   using namespace rtgen;
+   DevCfg c;
+   rtcfg::to_dev(*desc, planes, plane_stride, nrows, cfg, &c);
+   if (row_end > nrows) row_end = nrows;
+   float quiet_thr = 0;                                           /* make_plan (rt_api.cu) */
+   if (c.det == RT_DET_PEAK) { quiet_thr = c.p.pkww_rise * 0.999f; if (c.p.pkww_rise < 1e-3f) quiet_thr = 0; }
+   const int quiet_thr_lsb = rtcfg::quiet_thr_lsb(c);
+   const UnitDesc ud{row0, row_end};
+   for (int trk = 0; trk < c.ntrks; ++trk) {
+      TrkState t; SkewState s;
+      reset_full(c, t, s, trk, ud.row0, row_time(c, ud.row0) == 0.0);
+      const int16_t *plane = c.planes + (size_t)trk * c.plane_stride;
+      HostEmit em{out + (size_t)trk * cap, cap, 0, RT_NOROW, RT_NOCHUNK, (uint8_t)trk, RT_NOROW};
+      QuietTracker qt; qt.init(c, trk, quiet_thr, quiet_thr_lsb);
+      const uint64_t pre0 = ud.row0 > (uint64_t)c.prescan_rows ? ud.row0 - (uint64_t)c.prescan_rows : 0;
+      for (uint64_t j = pre0; j < ud.row0; ++j) qt.feed(c, plane, j, raw_at(c, plane, j));
+      const uint64_t quiet_from = qt.last_loud == RT_NOROW ? pre0 : qt.last_loud + 1;
+      uint64_t sync_row = RT_NOROW, loud_at_sync = RT_NOROW, sync_first = RT_NOROW, sync_early = RT_NOROW, loud_early = RT_NOROW;
+      bool early_frozen = false;
+      const int lead = std::max(trk + (row_time(c, ud.row0) == 0.0 ? 1 : 0), c.skew[trk]);
+      const uint64_t own_fill = ud.row0 + (uint64_t)(c.det == RT_DET_PEAK ? lead + c.width + 1 : lead + 2);
+      for (uint64_t row = ud.row0; row < ud.row_end; ++row) {
+         float v_raw;
+         unsigned probe = track_row(c, t, s, trk, plane, row, em, &v_raw);
+         if (em.n == 0) {
+            qt.feed(c, plane, row, v_raw);
+            const bool canonical = c.det == RT_DET_PEAK ? (probe & 2) != 0 : row >= own_fill;
+            if (sync_early != RT_NOROW && qt.last_loud != loud_early) early_frozen = true;
+            if (canonical && (qt.last_loud == RT_NOROW || qt.last_loud < row)) {
+               sync_row = row; loud_at_sync = qt.last_loud;
+               if (!early_frozen) { sync_early = row; loud_early = qt.last_loud; }
+               if (sync_first == RT_NOROW && row >= own_fill && (qt.last_loud == RT_NOROW || qt.last_loud < ud.row0)) sync_first = row; } } }
+      TrkMeta m;
+      m.first_event_row = em.first_row; m.sync_row = sync_row; m.last_loud_row = loud_at_sync; m.sync_first = sync_first; m.quiet_from = quiet_from; m.sync_early = sync_early; m.loud_early = loud_early;
+      m.first_chunk = em.first_chunk; m.nevents = em.n; m.failed = t.failed; m.pad = 0;
+      m.last_event_row = em.last_row; m.quiet_tail_from = RT_NOROW;
+      meta[trk] = m; counts[trk] = em.n; }
+   return RT_OK; }

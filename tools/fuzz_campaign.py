@@ -4,6 +4,7 @@
     python tools/fuzz_campaign.py proof 100 400        # tests/test_proof_host.py, seeds 100..399
     python tools/fuzz_campaign.py ctx 100 400          # tests/test_ctx_host.py (exact scan with skip-ahead)
     python tools/fuzz_campaign.py sparse 100 400       # tests/test_sparse_host.py adversarial signals (one seed per call)
+    python tools/fuzz_campaign.py generic 100 400      # tests/test_proof_generic_host.py (k_units_scan's detectors and proof data)
     python tools/fuzz_campaign.py oracle 100 200       # tests/test_oracle_fuzz.py (the instrumented unmodified reference)
 
 Each seed runs in its own pytest-free call of the test function; a failing seed is printed and the campaign goes on.  TEST
@@ -46,6 +47,9 @@ def main():
             elif which == "sparse":
                 import test_sparse_host as m
                 m.test_sparse_scan_on_adversarial_signals(seed, L, oracle)
+            elif which == "generic":
+                import test_proof_generic_host as m
+                m.test_generic_unit_scan_and_its_proof_data(range(seed, seed + 1), L, oracle)
             elif which == "oracle":
                 import test_oracle_fuzz as m
                 with tempfile.TemporaryDirectory() as d:
