@@ -117,6 +117,7 @@ struct HostAny { bool operator()(bool p) const { return p; } };
 /* Same contract as fast_host_scan_unit, through the two-pass scan.  t0_frac: T0 as a fraction of the default-state threshold bound
    (1.0 exercises the dense fall-back whenever the AGC lowers the threshold; tiny values make every row a candidate).
    The masks and the granule map of a capture are cached between calls (keyed by plane pointer, width, T0, rows). */
+static uint64_t g_planes_id = 0;
 extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_stride, uint64_t nrows, const rt_tape_desc *desc,
                                      const rt_scan_cfg *cfg, uint64_t row0, uint64_t row_end, rt_event *out, uint32_t cap,
                                      uint32_t *counts, TrkMeta *meta, float t0_frac, int use_gmm, int use_records) {
@@ -135,7 +136,8 @@ extern "C" int sparse_host_scan_unit(const int16_t *planes, uint64_t plane_strid
    const int T1 = T0 * 8 / 5 <= 65535 ? T0 * 8 / 5 : 65535;      /* a second plane at 1.6 x T0, as the library does for a fixed RT_SPARSE_T0 */
    /* keyed by the CONTENT of the planes too: a test's next array may well land at the address of the last one */
    uint64_t fp = 1469598103934665603ull;
-   for (int k = 0; k < dc.ntrks; ++k) {
+   if (g_planes_id) fp = g_planes_id;                             /* hostsim.cu: the caller vouches for the content (one id per build of the planes) */
+   else for (int k = 0; k < dc.ntrks; ++k) {
       const int16_t *pl = planes + (size_t)k * plane_stride;
       for (uint64_t r = 0; r < nrows; ++r) fp = (fp ^ (uint16_t)pl[r]) * 1099511628211ull; }
    static std::map<std::tuple<const int16_t *, uint64_t, int, int, int, uint64_t>, Cache> cache;

@@ -1,0 +1,111 @@
+"""The host shim's SPECULATIVE paths without a GPU: readblock_b200.c on the CPU simulation of the whole C-ABI.
+
+The CPU oracle implements only the exact scan, so `readtape_shim_oracle` never takes the paths the product lives on: speculative
+hits, units that end inside a block (the exact scan continues the replay), bridge scans, chained units, the parameter-set fan-out,
+the hand-over proofs between worker processes.  tests/host_fast/hostsim.cu implements rt_bulk_scan / rt_bulk_lookup on the CPU from
+the HOST BUILD of the product's scan code (the same __host__ __device__ templates the kernels instantiate, the same proof data), the
+product's own lookup rules (readtape_b200/csrc/lookup_rules.h) and a re-statement of the unit finder; `readtape_shim_hostsim` is
+the reference's host code + readblock_b200.c linked against it.  Everything below runs that binary beside the unmodified reference:
+
+  * the WHOLE bundled captures against the reference-held goldens, with the hit / miss / restart counts the GPU run recorded
+    (profiles/hitrates_r02.json: the simulation reproduces them number for number);
+  * units cut every n rows, INSIDE blocks (HOSTSIM_UNIT_ROWS): outputs must not depend on the unit finder;
+  * one reel split between worker processes (RT_WORKERS), the parameter-set fan-out (RT_FANOUT=1);
+  * the randomised runs of tests/test_fuzz_shim.py (synthetic tapes, capture windows, random options), with random unit cuts.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, capture_path
+import test_fuzz_shim as fz
+import test_host_shim as hs
+
+SIM = os.path.join(ROOT, "oracle", "_ref", "readtape_shim_hostsim")
+REF = os.path.join(ROOT, "oracle", "_ref", "readtape_ref")
+
+
+@pytest.fixture(scope="session")
+def sim():
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "readtape_b200", "host"), "hostsim"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if not (os.path.exists(SIM) and os.path.exists(REF)):
+        pytest.skip("readtape_shim_hostsim / readtape_ref not built (make -C readtape_b200/host hostsim in the build container)")
+    return SIM
+
+
+@pytest.mark.parametrize("label", sorted(hs.FULL))
+def test_hostsim_whole_capture_matches_reference_golden(label, sim, tmp_path):
+    out = hs.run_full(sim, label, tmp_path)
+    assert "hostsim-cpu" in out
+    st = hs.shim_stats(out)
+    assert st is not None, out[-1500:]
+    print(f"[hostsim] {label}: {st}")
+    doc = hs.FULL[label]
+    if "-whirlwind" in doc["options"] or "-differentiate" in doc["options"]:
+        return
+    decodes = st["hits"] + st["misses"]
+    assert decodes > 0 and st["hits"] - st["restarts"] >= hs.MIN_HIT_RATE * decodes, f"{label}: {st}"
+
+
+@pytest.mark.parametrize("name,cut", [("Microdata_20blks.nm_tap", 4096), ("Microdata_20blks", 20000), ("LJS009_part1_39blks", 9000), ("sf93_8blks", 30000),
+                                      ("1600bpi_ukn_6s", 2048), ("SRI_SDS_102715028_4secs", 5000)])
+def test_hostsim_units_cut_inside_blocks(name, cut, sim, tmp_path):
+    """the unit finder is a heuristic: with units cut every `cut` rows (in the middle of blocks) the proof has to reject what it cannot
+    prove and the exact scan has to carry the replay on -- same outputs, many more misses / restarts"""
+    out = hs.run_shim(sim, name, tmp_path, {"HOSTSIM_UNIT_ROWS": str(cut)})
+    st = hs.shim_stats(out)
+    print(f"[hostsim] {name}, units of {cut} rows: {st}")
+    assert st["misses"] + st["restarts"] > 0, st
+
+
+def test_hostsim_parameter_set_fanout(sim, tmp_path):
+    """all active parameter sets scanned by ONE rt_bulk_scan call from the start (RT_FANOUT=1), BASELINE config 3"""
+    out = hs.run_shim(sim, "LJS009_part1_39blks", tmp_path, {"RT_FANOUT": "1"})
+    assert hs.shim_stats(out)["hits"] > 0
+
+
+def test_hostsim_worker_processes(sim, tmp_path):
+    """RT_WORKERS: one reel split between worker processes, the hand-overs proven by rt_bulk_lookup / rt_bulk_last_unit"""
+    d = str(tmp_path)
+    path, nrows = hs._reel(d, 6)
+    jobs = [("synthetic_6_tiles_3_workers", path, "-q -nm -nrzi -bpi=800 -ips=50 -tap -nolog -nolabels", {"RT_WORKERS": "3", "RT_WORKER_MIN_ROWS": "100000", "RT_WORKER_MARGIN_ROWS": "100000"}, 3)]
+    for name, opts in (("LJS009_part1_39blks", "-q -m -ntrks=9 -pe -bpi=1600 -ips=50 -tap -nolog"),
+                       ("1kblks_43blks", "-q -m -gcr -ips=50 -order=76543210p -zeros -correct -tap -nolog"),
+                       ("tss_4secs", "-q -m -nrzi -ntrks=7 -tap -nolog")):
+        jobs.append((name + "_3_workers", capture_path(name, full=True), opts, {"RT_WORKERS": "3", "RT_WORKER_MIN_ROWS": "300000", "RT_WORKER_MARGIN_ROWS": "700000"}, 3))
+    for label, cap, opts, env, nw in jobs:
+        r0 = subprocess.run([REF] + opts.split() + [f"-outf={d}/ref_{label}", cap], capture_output=True, text=True, timeout=900)
+        assert r0.returncode == 0, r0.stdout[-1500:]
+        r = subprocess.run([sim] + opts.split() + [f"-outf={d}/new_{label}", cap], capture_output=True, text=True, env=dict(os.environ, RT_STATS="1", **env), timeout=900)
+        assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
+        a = open(f"{d}/new_{label}.tap", "rb").read(); b = open(f"{d}/ref_{label}.tap", "rb").read()
+        workers = len([l for l in r.stdout.splitlines() if "B200 scan: worker" in l and "speculative hits" in l]) + 1
+        unsplit = "decoding the reel unsplit" in r.stdout
+        print(f"[hostsim] {label}: {workers} workers reported, unsplit fallback {unsplit}")
+        assert a == b, f"{label}: .tap differs ({len(a)} vs {len(b)} bytes)\n" + r.stdout[-1500:]
+        assert r.stdout.strip().splitlines()[-1] == r0.stdout.strip().splitlines()[-1], (r.stdout[-300:], r0.stdout[-300:])
+        assert not [f for f in os.listdir(d) if ".part" in f], "part files left behind"
+        if label.startswith("synthetic"):
+            assert workers == nw and not unsplit, r.stdout[-1500:]
+
+
+def _with_random_cuts(make_case):
+    def f(rng, wd):
+        opts, what = make_case(rng, wd)
+        if rng.random() < 0.5: os.environ["HOSTSIM_UNIT_ROWS"] = str(int(rng.choice([1024, 4096, 20000, 100000])))
+        else: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+        return opts, what + f", unit cuts {os.environ.get('HOSTSIM_UNIT_ROWS')}"
+    return f
+
+
+def test_hostsim_random_synthetic_tapes(sim, tmp_path):
+    try: fz.fuzz(sim, _with_random_cuts(fz.synthetic_case), 301, 12, tmp_path)
+    finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+
+
+def test_hostsim_random_capture_windows(sim, tmp_path):
+    try: fz.fuzz(sim, _with_random_cuts(fz.capture_case), 302, 10, tmp_path)
+    finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)

@@ -5,6 +5,10 @@
     python tools/fuzz_campaign.py ctx 100 400          # tests/test_ctx_host.py (exact scan with skip-ahead)
     python tools/fuzz_campaign.py sparse 100 400       # tests/test_sparse_host.py adversarial signals (one seed per call)
     python tools/fuzz_campaign.py generic 100 400      # tests/test_proof_generic_host.py (k_units_scan's detectors and proof data)
+    python tools/fuzz_campaign.py shim-synth 0 200     # tests/test_fuzz_shim.py: the event-driven readblock() on the oracle backend beside the
+    python tools/fuzz_campaign.py shim-capture 0 200   #   unmodified reference binary (4 random cases per seed): rc, outputs and logs identical
+    python tools/fuzz_campaign.py sim-synth 0 200      # the same on the CPU simulation of the whole C-ABI (tests/host_fast/hostsim.cu): speculative
+    python tools/fuzz_campaign.py sim-capture 0 200    #   hits, restarts, bridge scans, with units cut at random
     python tools/fuzz_campaign.py oracle 100 200       # tests/test_oracle_fuzz.py (the instrumented unmodified reference)
 
 Each seed runs in its own pytest-free call of the test function; a failing seed is printed and the campaign goes on.  TEST
@@ -50,6 +54,16 @@ def main():
             elif which == "generic":
                 import test_proof_generic_host as m
                 m.test_generic_unit_scan_and_its_proof_data(range(seed, seed + 1), L, oracle)
+            elif which in ("shim-synth", "shim-capture"):
+                import test_fuzz_shim as m
+                with tempfile.TemporaryDirectory() as d:
+                    m.fuzz(m.ORACLE_SHIM, m.synthetic_case if which == "shim-synth" else m.capture_case, 100000 + seed, 4, pathlib.Path(d))
+            elif which in ("sim-synth", "sim-capture"):
+                import test_fuzz_shim as m, test_hostsim as hsim
+                case = hsim._with_random_cuts(m.synthetic_case if which == "sim-synth" else m.capture_case)
+                with tempfile.TemporaryDirectory() as d:
+                    try: m.fuzz(hsim.SIM, case, 200000 + seed, 4, pathlib.Path(d))
+                    finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
             elif which == "oracle":
                 import test_oracle_fuzz as m
                 with tempfile.TemporaryDirectory() as d:
