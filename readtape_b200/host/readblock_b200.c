@@ -203,6 +203,7 @@ static void open_tape(void) {
 struct evsrc {
    const rt_event *ev; uint64_t n, at;      /* current batch */
    uint64_t valid_end;                      /* rows < valid_end are covered by what we hold */
+   uint64_t unit_end;                       /* speculative source: the end row of the unit the lookup arrived at (after chaining) */
    int exact;                               /* 1: S.ctx is running and can be continued */
    /* what is needed to carry on with the exact scan when a speculative unit ends inside the block */
    uint64_t row0; const rt_scan_cfg *cfg;
@@ -362,7 +363,7 @@ static int bulk_start(struct evsrc *src, const rt_scan_cfg *cfg, uint64_t row) {
       if (getenv("RT_STATS") && atoi(getenv("RT_STATS")) >= 2) say_miss(S.bulk[ps].bulk, S.bulk[ps].ci, row);
       return 0; }
    if (rc) rtfatal("rt_bulk_lookup", rc);
-   src->valid_end = row + valid;
+   src->valid_end = src->unit_end = row + valid;
    if (src->valid_end >= S.nrows) src->valid_end = UINT64_MAX;
    ++S.n_bulk_hits;
    return 1; }
@@ -853,19 +854,37 @@ bool readblock(bool retry) {
    struct evsrc src;
    uint64_t last_row = row0; bool endfile = false;
    int persistent = mode == WW || reset_kind != RT_RESET_FULL;   /* Whirlwind: the scan state carries over from block to block */
-   int from_bulk = !persistent && bulk_start(&src, &cfg, row0);
+   int from_bulk = !persistent && bulk_start(&src, &cfg, row0), exact_started = 0;
    if (S.stop_row != UINT64_MAX && !retry) {                     /* a worker that is not the last: is this block the next worker's? */
-      uint64_t u0 = 0;
-      if (from_bulk && rt_bulk_last_unit(S.bulk[block.parmset].bulk, S.bulk[block.parmset].ci, &u0, NULLP) == RT_OK && u0 >= S.stop_row) {
-         /* proven: a fresh reset here == a fresh reset at a unit at or behind the boundary; the next worker starts exactly there */
-         S.s_scan += wall() - w0;
-         if (getenv("RT_STATS")) {
-            rlog("  B200 scan: worker %d of %d: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n", S.worker, S.nworkers,
-                 S.n_events, S.n_bulk_hits, S.n_bulk_miss, S.n_restarts, S.n_exact_spans);
-            rlog("  B200 scan: worker %d: %.3f s opening + upload, %.3f s in the scan library, %.3f s replaying events into the handlers\n", S.worker, S.s_open, S.s_scan, S.s_replay); }
-         return false; }                                          /* end of this worker's part: block type BS_NONE, "end of file" */
-      if (row0 >= S.stop_row) { fflush(NULL); _exit(WORKER_UNPROVEN); } }
-   if (!from_bulk) exact_start(&src, &cfg, reset_kind, row0);
+      /* The next worker starts with a fresh reset at S.stop_row, the first row of a unit.  This worker may stop in front of a block
+         only if that reset PROVABLY sees what a fresh reset here sees: both lookups arrive at the same unit (same end row), so both
+         get the same events.  The block in front of us must not be decoded unless it begins on this side of the boundary, or it
+         would come out twice -- the lookup may have been served by a unit BEHIND the boundary (directly, or by chaining through
+         event-free units), and a miss leaves us with an exact scan that runs on as far as it needs.  Whatever cannot be decided
+         ends the split: WORKER_UNPROVEN, the parent decodes the reel in one piece.  (Before the end of round 2 the test was "the
+         lookup resolved to a unit at or behind the boundary", which let a block that STRADDLES the boundary -- units can begin
+         inside blocks, at all-track drop-outs -- be followed by a worker starting in the middle of it, and a block served through
+         a chain across the boundary be decoded by both workers: found by the worker fuzz on the CPU simulation, tests/test_hostsim.py.) */
+      if (from_bulk && src.unit_end > S.stop_row) {
+         const rt_event *e2 = NULLP; uint64_t n2 = 0, valid2 = 0;
+         int rc2 = rt_bulk_lookup(S.bulk[block.parmset].bulk, S.bulk[block.parmset].ci, S.stop_row, &e2, &n2, &valid2);
+         if (rc2 != RT_OK && rc2 != RT_MISS) rtfatal("rt_bulk_lookup", rc2);
+         if (rc2 == RT_OK && S.stop_row + valid2 == src.unit_end) {
+            S.s_scan += wall() - w0;
+            if (getenv("RT_STATS")) {
+               rlog("  B200 scan: worker %d of %d: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n", S.worker, S.nworkers,
+                    S.n_events, S.n_bulk_hits, S.n_bulk_miss, S.n_restarts, S.n_exact_spans);
+               rlog("  B200 scan: worker %d: %.3f s opening + upload, %.3f s in the scan library, %.3f s replaying events into the handlers\n", S.worker, S.s_open, S.s_scan, S.s_replay); }
+            return false; }                                       /* end of this worker's part: block type BS_NONE, "end of file" */
+         /* not the next worker's view: the lookup above has overwritten the library's result buffer, fetch ours again */
+         uint64_t valid = 0;
+         int rc1 = rt_bulk_lookup(S.bulk[block.parmset].bulk, S.bulk[block.parmset].ci, row0, &src.ev, &src.n, &valid);
+         if (rc1 != RT_OK || row0 + valid != src.unit_end) fatal("B200 scan: a repeated lookup at row %llu gave another answer", (unsigned long long)row0); }
+      if (row0 >= S.stop_row) { fflush(NULL); _exit(WORKER_UNPROVEN); }
+      if (!from_bulk) { exact_start(&src, &cfg, reset_kind, row0); exact_started = 1; }
+      /* the block must begin on this side of the boundary */
+      if (peek_event(&src, S.stop_row) == NULLP) { fflush(NULL); _exit(WORKER_UNPROVEN); } }
+   if (!from_bulk && !exact_started) exact_start(&src, &cfg, reset_kind, row0);
    S.s_scan += wall() - w0; w0 = wall();
    decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile);
    if (src.exact && persistent && !endfile) {   /* Whirlwind continues from here: leave the scan state exactly where the host stopped */

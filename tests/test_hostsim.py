@@ -109,3 +109,49 @@ def test_hostsim_random_synthetic_tapes(sim, tmp_path):
 def test_hostsim_random_capture_windows(sim, tmp_path):
     try: fz.fuzz(sim, _with_random_cuts(fz.capture_case), 302, 10, tmp_path)
     finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+
+
+def worker_case(rng, wd):
+    """a noisy synthetic reel with dropouts (blocks the first parameter set fails on), decoded by 2..5 worker processes with small
+    shares and margins, units cut at random: the .tap and the summary line must be the reference's"""
+    from readtape_b200 import synth, tbin
+    nb = int(rng.integers(6, 24)); noise = float(rng.choice([2.0, 5.0, 40.0, 150.0])); wob = float(rng.choice([0.0, 0.01, 0.04]))
+    hdr, rows = synth.nrzi_tape(nblocks=nb, seed=int(rng.integers(1, 1 << 30)), data_bytes=int(rng.integers(8, 300)), noise_mv=noise, wobble=wob)
+    rows = rows.copy()
+    for _ in range(int(rng.integers(0, 5))):
+        a = int(rng.integers(0, len(rows) - 10)); b = a + int(rng.integers(10, 6000)); k = int(rng.integers(0, 9))
+        rows[a:b, k] = (rows[a:b, k] * float(rng.choice([0.0, 0.1, 0.3]))).astype(np.int16)
+    if rng.random() < 0.2: rows = rows[: int(rng.integers(len(rows) // 2, len(rows)))]
+    with open(os.path.join(wd, "t.tbin"), "wb") as fh:
+        fh.write(tbin.build_header(hdr)); rows.tofile(fh); fh.write(np.array([tbin.END_MARK], dtype="<i2").tobytes())
+    opts = ["-q", "-tap", "-nolog", "-nrzi", "-bpi=800", "-ips=50", str(rng.choice(["-nm", "-m"]))]
+    if rng.random() < 0.3: opts.append("-nolabels")
+    env = {"RT_WORKERS": str(int(rng.integers(2, 6))), "RT_WORKER_MIN_ROWS": str(int(rng.choice([2000, 20000, 60000]))),
+           "RT_WORKER_MARGIN_ROWS": str(int(rng.choice([1000, 30000, 200000])))}
+    if rng.random() < 0.5: env["HOSTSIM_UNIT_ROWS"] = str(int(rng.choice([1024, 4096, 20000, 100000])))
+    return opts, env, f"synthetic NRZI, {nb} blocks, noise {noise} mV, {len(rows)} rows, {env}"
+
+
+def worker_fuzz(sim, seed, ncases, tmp_path):
+    rng = np.random.default_rng(seed); wd = str(tmp_path); failures = []; split = 0
+    for it in range(ncases):
+        opts, env, what = worker_case(rng, wd)
+        res = []
+        for exe, tag, e in ((REF, "ref", {}), (sim, "new", dict(env, RT_STATS="1"))):
+            for f in os.listdir(wd):
+                if f.startswith(tag): os.remove(os.path.join(wd, f))
+            p = subprocess.run([exe] + opts + [f"-outf={wd}/{tag}", f"{wd}/t.tbin"], capture_output=True, text=True, errors="replace", timeout=900, env=dict(os.environ, **e))
+            tapf = f"{wd}/{tag}.tap"
+            lines = [l for l in p.stdout.strip().splitlines() if "B200 scan" not in l]
+            res.append((p.returncode, open(tapf, "rb").read() if os.path.exists(tapf) else None, lines[-1:] ))
+            if tag == "new" and "B200 scan: worker" in p.stdout: split += 1
+        if res[0] != res[1]:
+            why = "return code" if res[0][0] != res[1][0] else ".tap" if res[0][1] != res[1][1] else "summary line"
+            failures.append(f"case {it} of seed {seed}: {what}: {why} differs ({res[0][2]} / {res[1][2]})")
+        if [f for f in os.listdir(wd) if ".part" in f]: failures.append(f"case {it} of seed {seed}: {what}: part files left behind")
+    assert not failures, "\n".join(failures)
+    return split
+
+
+def test_hostsim_random_worker_splits(sim, tmp_path):
+    assert worker_fuzz(sim, 303, 10, tmp_path) >= 3

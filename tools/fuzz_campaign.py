@@ -9,6 +9,7 @@
     python tools/fuzz_campaign.py shim-capture 0 200   #   unmodified reference binary (4 random cases per seed): rc, outputs and logs identical
     python tools/fuzz_campaign.py sim-synth 0 200      # the same on the CPU simulation of the whole C-ABI (tests/host_fast/hostsim.cu): speculative
     python tools/fuzz_campaign.py sim-capture 0 200    #   hits, restarts, bridge scans, with units cut at random
+    python tools/fuzz_campaign.py sim-workers 0 200    #   one reel split between worker processes (RT_WORKERS) with small shares and random unit cuts
     python tools/fuzz_campaign.py oracle 100 200       # tests/test_oracle_fuzz.py (the instrumented unmodified reference)
 
 Each seed runs in its own pytest-free call of the test function; a failing seed is printed and the campaign goes on.  TEST
@@ -64,6 +65,10 @@ def main():
                 with tempfile.TemporaryDirectory() as d:
                     try: m.fuzz(hsim.SIM, case, 200000 + seed, 4, pathlib.Path(d))
                     finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+            elif which == "sim-workers":
+                import test_hostsim as hsim
+                with tempfile.TemporaryDirectory() as d:
+                    hsim.worker_fuzz(hsim.SIM, 300000 + seed, 4, pathlib.Path(d))
             elif which == "oracle":
                 import test_oracle_fuzz as m
                 with tempfile.TemporaryDirectory() as d:
