@@ -230,8 +230,9 @@ int  rt_bulk_lookup(rt_bulk *bulk, uint32_t cfg_index, uint64_t start_row,
                     const rt_event **events, uint64_t *nevents, uint64_t *valid_rows);
 
 /* The unit the last successful rt_bulk_lookup() of configuration `cfg_index` resolved to (before chaining through event-free
- * units): its first row and end.  Lets a caller that splits one tape between workers prove a hand-over: "a fresh reset at my
- * current row is equivalent to a fresh reset at a unit that starts at or behind the row where the next worker starts". */
+ * units): its first row and end.  Diagnostics.  (A caller that splits one tape between workers proves a hand-over with two
+ * lookups instead: start_row + *valid_rows is the end row of the unit a lookup ARRIVED at, after chaining; two rows whose lookups
+ * arrive at the same unit see the same events -- readblock_b200.c.) */
 int  rt_bulk_last_unit(const rt_bulk *bulk, uint32_t cfg_index, uint64_t *row0, uint64_t *row_end);
 
 /* Diagnostics: the unit rt_bulk_lookup() would consult for `start_row` and the per-track proof data
