@@ -92,23 +92,32 @@ def test_hostsim_worker_processes(sim, tmp_path):
             assert workers == nw and not unsplit, r.stdout[-1500:]
 
 
+SIM_KNOBS = ("HOSTSIM_UNIT_ROWS", "RT_FANOUT", "RT_BRIDGE")
+
+
 def _with_random_cuts(make_case):
+    """the case generator of test_fuzz_shim + the knobs of the speculative paths: units cut at random, all parameter sets scanned
+    at once or one by one, bridge scans off"""
     def f(rng, wd):
         opts, what = make_case(rng, wd)
+        for k in SIM_KNOBS: os.environ.pop(k, None)
         if rng.random() < 0.5: os.environ["HOSTSIM_UNIT_ROWS"] = str(int(rng.choice([1024, 4096, 20000, 100000])))
-        else: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
-        return opts, what + f", unit cuts {os.environ.get('HOSTSIM_UNIT_ROWS')}"
+        r = rng.random()
+        if r < 0.25: os.environ["RT_FANOUT"] = "1"
+        elif r < 0.35: os.environ["RT_FANOUT"] = "0"
+        if rng.random() < 0.2: os.environ["RT_BRIDGE"] = "0"
+        return opts, (what or "") + ", " + " ".join(f"{k}={os.environ[k]}" for k in SIM_KNOBS if k in os.environ)
     return f
 
 
 def test_hostsim_random_synthetic_tapes(sim, tmp_path):
     try: fz.fuzz(sim, _with_random_cuts(fz.synthetic_case), 301, 12, tmp_path)
-    finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+    finally: [os.environ.pop(k, None) for k in SIM_KNOBS]
 
 
 def test_hostsim_random_capture_windows(sim, tmp_path):
     try: fz.fuzz(sim, _with_random_cuts(fz.capture_case), 302, 10, tmp_path)
-    finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+    finally: [os.environ.pop(k, None) for k in SIM_KNOBS]
 
 
 def worker_case(rng, wd):

@@ -64,7 +64,7 @@ def main():
                 case = hsim._with_random_cuts(m.synthetic_case if which == "sim-synth" else m.capture_case)
                 with tempfile.TemporaryDirectory() as d:
                     try: m.fuzz(hsim.SIM, case, 200000 + seed, 4, pathlib.Path(d))
-                    finally: os.environ.pop("HOSTSIM_UNIT_ROWS", None)
+                    finally: [os.environ.pop(k, None) for k in hsim.SIM_KNOBS]
             elif which == "sim-workers":
                 import test_hostsim as hsim
                 with tempfile.TemporaryDirectory() as d:
