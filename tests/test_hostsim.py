@@ -152,11 +152,13 @@ def worker_fuzz(sim, seed, ncases, tmp_path):
             p = subprocess.run([exe] + opts + [f"-outf={wd}/{tag}", f"{wd}/t.tbin"], capture_output=True, text=True, errors="replace", timeout=900, env=dict(os.environ, **e))
             tapf = f"{wd}/{tag}.tap"
             lines = [l for l in p.stdout.strip().splitlines() if "B200 scan" not in l]
-            res.append((p.returncode, open(tapf, "rb").read() if os.path.exists(tapf) else None, lines[-1:] ))
-            if tag == "new" and "B200 scan: worker" in p.stdout: split += 1
+            res.append((p.returncode, open(tapf, "rb").read() if os.path.exists(tapf) else None, lines[-1:]))
+            if tag == "new":
+                tail = (p.stdout[-700:] + p.stderr[-300:]).replace("\n", " | ")
+                if "B200 scan: worker" in p.stdout: split += 1
         if res[0] != res[1]:
             why = "return code" if res[0][0] != res[1][0] else ".tap" if res[0][1] != res[1][1] else "summary line"
-            failures.append(f"case {it} of seed {seed}: {what}: {why} differs ({res[0][2]} / {res[1][2]})")
+            failures.append(f"case {it} of seed {seed}: {what}: {why} differs ({res[0][2]} / {res[1][2]}); rc {res[0][0]} / {res[1][0]}; output of the run under test: {tail}")
         if [f for f in os.listdir(wd) if ".part" in f]: failures.append(f"case {it} of seed {seed}: {what}: part files left behind")
     assert not failures, "\n".join(failures)
     return split
