@@ -110,6 +110,31 @@ def _with_random_cuts(make_case):
     return f
 
 
+def _punch_all_track_dropouts(rng, wd):
+    """all tracks attenuated for 40..600 rows at 1..4 places of t.tbin: the REAL unit finder then cuts units inside blocks (a quiet
+    stretch of all tracks is what it looks for), whatever the reference makes of the damaged block"""
+    path = os.path.join(wd, "t.tbin")
+    raw = np.fromfile(path, dtype="<i2", offset=256)
+    rows = raw[:-1].reshape(-1, 9).copy()
+    for _ in range(int(rng.integers(1, 5))):
+        a = int(rng.integers(0, max(1, len(rows) - 700))); b = a + int(rng.integers(40, 600))
+        rows[a:b] = (rows[a:b] * float(rng.choice([0.0, 0.01, 0.03]))).astype(np.int16)
+    head = open(path, "rb").read(256)
+    with open(path, "wb") as fh:
+        fh.write(head); rows.tofile(fh); fh.write(raw[-1:].tobytes())
+
+
+def dropout_case(rng, wd):
+    opts, what = fz.synthetic_case(rng, wd)
+    _punch_all_track_dropouts(rng, wd)
+    return opts, what + ", all-track drop-outs"
+
+
+def test_hostsim_random_tapes_with_all_track_dropouts(sim, tmp_path):
+    try: fz.fuzz(sim, _with_random_cuts(dropout_case), 304, 10, tmp_path)
+    finally: [os.environ.pop(k, None) for k in SIM_KNOBS]
+
+
 def test_hostsim_random_synthetic_tapes(sim, tmp_path):
     try: fz.fuzz(sim, _with_random_cuts(fz.synthetic_case), 301, 12, tmp_path)
     finally: [os.environ.pop(k, None) for k in SIM_KNOBS]
@@ -124,7 +149,8 @@ def worker_case(rng, wd):
     """a noisy synthetic reel with dropouts (blocks the first parameter set fails on), decoded by 2..5 worker processes with small
     shares and margins, units cut at random: the .tap and the summary line must be the reference's"""
     from readtape_b200 import synth, tbin
-    nb = int(rng.integers(6, 24)); noise = float(rng.choice([2.0, 5.0, 40.0, 150.0])); wob = float(rng.choice([0.0, 0.01, 0.04]))
+    clean = rng.random() < 0.4            # a reel the split should succeed on: quiet gaps, units cut where the unit finder cuts them
+    nb = int(rng.integers(6, 24)); noise = float(rng.choice([2.0, 5.0] if clean else [2.0, 5.0, 40.0, 150.0])); wob = float(rng.choice([0.0, 0.01, 0.04]))
     hdr, rows = synth.nrzi_tape(nblocks=nb, seed=int(rng.integers(1, 1 << 30)), data_bytes=int(rng.integers(8, 300)), noise_mv=noise, wobble=wob)
     rows = rows.copy()
     for _ in range(int(rng.integers(0, 5))):
@@ -133,11 +159,12 @@ def worker_case(rng, wd):
     if rng.random() < 0.2: rows = rows[: int(rng.integers(len(rows) // 2, len(rows)))]
     with open(os.path.join(wd, "t.tbin"), "wb") as fh:
         fh.write(tbin.build_header(hdr)); rows.tofile(fh); fh.write(np.array([tbin.END_MARK], dtype="<i2").tobytes())
+    if not clean and rng.random() < 0.5: _punch_all_track_dropouts(rng, wd)
     opts = ["-q", "-tap", "-nolog", "-nrzi", "-bpi=800", "-ips=50", str(rng.choice(["-nm", "-m"]))]
     if rng.random() < 0.3: opts.append("-nolabels")
     env = {"RT_WORKERS": str(int(rng.integers(2, 6))), "RT_WORKER_MIN_ROWS": str(int(rng.choice([2000, 20000, 60000]))),
            "RT_WORKER_MARGIN_ROWS": str(int(rng.choice([1000, 30000, 200000])))}
-    if rng.random() < 0.5: env["HOSTSIM_UNIT_ROWS"] = str(int(rng.choice([1024, 4096, 20000, 100000])))
+    if not clean and rng.random() < 0.5: env["HOSTSIM_UNIT_ROWS"] = str(int(rng.choice([1024, 4096, 20000, 100000])))
     return opts, env, f"synthetic NRZI, {nb} blocks, noise {noise} mV, {len(rows)} rows, {env}"
 
 

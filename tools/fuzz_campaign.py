@@ -9,6 +9,7 @@
     python tools/fuzz_campaign.py shim-capture 0 200   #   unmodified reference binary (4 random cases per seed): rc, outputs and logs identical
     python tools/fuzz_campaign.py sim-synth 0 200      # the same on the CPU simulation of the whole C-ABI (tests/host_fast/hostsim.cu): speculative
     python tools/fuzz_campaign.py sim-capture 0 200    #   hits, restarts, bridge scans, with units cut at random
+    python tools/fuzz_campaign.py sim-dropout 0 200    #   synthetic tapes with all-track drop-outs (the real unit finder cuts inside blocks)
     python tools/fuzz_campaign.py sim-workers 0 200    #   one reel split between worker processes (RT_WORKERS) with small shares and random unit cuts
     python tools/fuzz_campaign.py oracle 100 200       # tests/test_oracle_fuzz.py (the instrumented unmodified reference)
 
@@ -59,9 +60,9 @@ def main():
                 import test_fuzz_shim as m
                 with tempfile.TemporaryDirectory() as d:
                     m.fuzz(m.ORACLE_SHIM, m.synthetic_case if which == "shim-synth" else m.capture_case, 100000 + seed, 4, pathlib.Path(d))
-            elif which in ("sim-synth", "sim-capture"):
+            elif which in ("sim-synth", "sim-capture", "sim-dropout"):
                 import test_fuzz_shim as m, test_hostsim as hsim
-                case = hsim._with_random_cuts(m.synthetic_case if which == "sim-synth" else m.capture_case)
+                case = hsim._with_random_cuts({"sim-synth": m.synthetic_case, "sim-capture": m.capture_case, "sim-dropout": hsim.dropout_case}[which])
                 with tempfile.TemporaryDirectory() as d:
                     try: m.fuzz(hsim.SIM, case, 200000 + seed, 4, pathlib.Path(d))
                     finally: [os.environ.pop(k, None) for k in hsim.SIM_KNOBS]
