@@ -887,6 +887,10 @@ bool readblock(bool retry) {
    if (!from_bulk && !exact_started) exact_start(&src, &cfg, reset_kind, row0);
    S.s_scan += wall() - w0; w0 = wall();
    decode_from(row0, reset_kind, &cfg, &src, &last_row, &endfile);
+   if (endfile && S.stop_row != UINT64_MAX) {
+      /* a worker that is not the last has run into the end of the tape: its block began on its side of the boundary and never
+         ended, so the next worker started in the middle of it.  No hand-over was proven: the reel is decoded in one piece. */
+      fflush(NULL); _exit(WORKER_UNPROVEN); }
    if (src.exact && persistent && !endfile) {   /* Whirlwind continues from here: leave the scan state exactly where the host stopped */
       int rc = rt_scan_rewind(S.ctx, last_row); if (rc) rtfatal("rt_scan_rewind", rc); }
 

@@ -168,10 +168,24 @@ def worker_case(rng, wd):
     return opts, env, f"synthetic NRZI, {nb} blocks, noise {noise} mV, {len(rows)} rows, {env}"
 
 
-def worker_fuzz(sim, seed, ncases, tmp_path):
+def worker_capture_case(rng, wd):
+    """a random window of a bundled capture (PE, GCR, NRZI; noise and drop-outs added) with a command line the worker split accepts"""
+    opts, what = fz.capture_case(rng, wd)
+    if opts is None: return None, None, None
+    keep = [o for o in opts if o.split("=")[0] in ("-ntrks", "-order", "-pe", "-nrzi", "-gcr", "-bpi", "-ips", "-zeros", "-correct", "-nm", "-m", "-whirlwind", "-differentiate")]
+    if "-nrzi" in keep and not any(o.startswith("-bpi") for o in keep): keep.append(str(rng.choice(["-bpi=800", "-bpi=556", "-bpi=200"])))
+    opts = ["-q", "-tap", "-nolog"] + keep
+    env = {"RT_WORKERS": str(int(rng.integers(2, 6))), "RT_WORKER_MIN_ROWS": str(int(rng.choice([5000, 20000, 60000]))),
+           "RT_WORKER_MARGIN_ROWS": str(int(rng.choice([1000, 30000, 200000])))}
+    if rng.random() < 0.3: env["HOSTSIM_UNIT_ROWS"] = str(int(rng.choice([4096, 20000, 100000])))
+    return opts, env, what + f", {env}"
+
+
+def worker_fuzz(sim, seed, ncases, tmp_path, make_case=None):
     rng = np.random.default_rng(seed); wd = str(tmp_path); failures = []; split = 0
     for it in range(ncases):
-        opts, env, what = worker_case(rng, wd)
+        opts, env, what = (make_case or worker_case)(rng, wd)
+        if opts is None: continue
         res = []
         for exe, tag, e in ((REF, "ref", {}), (sim, "new", dict(env, RT_STATS="1"))):
             for f in os.listdir(wd):
@@ -193,3 +207,7 @@ def worker_fuzz(sim, seed, ncases, tmp_path):
 
 def test_hostsim_random_worker_splits(sim, tmp_path):
     assert worker_fuzz(sim, 303, 10, tmp_path) >= 3
+
+
+def test_hostsim_random_worker_splits_of_capture_windows(sim, tmp_path):
+    worker_fuzz(sim, 305, 8, tmp_path, worker_capture_case)

@@ -66,10 +66,10 @@ def main():
                 with tempfile.TemporaryDirectory() as d:
                     try: m.fuzz(hsim.SIM, case, 200000 + seed, 4, pathlib.Path(d))
                     finally: [os.environ.pop(k, None) for k in hsim.SIM_KNOBS]
-            elif which == "sim-workers":
+            elif which in ("sim-workers", "sim-workers-capture"):
                 import test_hostsim as hsim
                 with tempfile.TemporaryDirectory() as d:
-                    hsim.worker_fuzz(hsim.SIM, 300000 + seed, 4, pathlib.Path(d))
+                    hsim.worker_fuzz(hsim.SIM, 300000 + seed, 4, pathlib.Path(d), hsim.worker_capture_case if which.endswith("capture") else None)
             elif which == "oracle":
                 import test_oracle_fuzz as m
                 with tempfile.TemporaryDirectory() as d:
