@@ -40,7 +40,9 @@ Ora &ora() {
          Dl_info di; dladdr((void *)&ora, &di);
          std::string me = di.dli_fname; me = me.substr(0, me.rfind('/'));
          path = me + "/../../../oracle/_ref/libscan_oracle.so"; }
-      o.h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);
+      /* RTLD_DEEPBIND keeps the oracle's internal calls of its own rt_* functions its own (this library exports the same names).  The
+         sanitizer runtimes refuse that flag: HOSTSIM_NO_DEEPBIND=1 drops it, for an oracle built with -Wl,-Bsymbolic (HOSTSIM_ORACLE) */
+      o.h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL | (getenv("HOSTSIM_NO_DEEPBIND") ? 0 : RTLD_DEEPBIND));
       if (!o.h) { fprintf(stderr, "hostsim: cannot load the oracle (%s): %s\n", path.c_str(), dlerror()); abort(); }
 #define ORA_FN(name) o.name = (decltype(o.name))dlsym(o.h, #name); if (!o.name) { fprintf(stderr, "hostsim: oracle lacks %s\n", #name); abort(); }
       ORA_FN(rt_last_error) ORA_FN(rt_open) ORA_FN(rt_upload) ORA_FN(rt_upload_fd) ORA_FN(rt_clear) ORA_FN(rt_nrows) ORA_FN(rt_close) ORA_FN(rt_host_alloc) ORA_FN(rt_host_free)
