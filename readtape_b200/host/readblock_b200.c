@@ -659,7 +659,7 @@ static void serve_one(struct chan *ch) {                       /* parent: one ex
       if (rc || n <= WORKER_BUF_EVENTS) break;
       rc = rt_scan_rewind(ch->ctx, rt_scan_pos(ch->ctx) - done);
       if (!rc && span <= 1) rc = RT_ERR_OVERFLOW; }
-   if (!rc) { memcpy(ch->buf, ev, (size_t)n * sizeof *ev); rs.n = n; rs.pos = rt_scan_pos(ch->ctx); rs.done = done; }
+   if (!rc) { if (n) memcpy(ch->buf, ev, (size_t)n * sizeof *ev); rs.n = n; rs.pos = rt_scan_pos(ch->ctx); rs.done = done; }
    else { rs.rc = rc; strncpy(rs.err, rt_last_error(), sizeof rs.err - 1); }
    xfer(ch->fd, &rs, sizeof rs, 1); }
 
