@@ -45,6 +45,7 @@
 
 /* ---- reference globals we read (all non-static in readtape.c / decoder.c) ------------------------ */
 extern FILE *inf;
+extern char indatafilename[];
 extern bool tbin_file, invert_data, do_differentiate, find_zeros, doing_density_detection, doing_deskew;
 extern struct tbin_hdr_t tbin_hdr;
 extern struct tbin_dat_t tbin_dat;
@@ -739,6 +740,7 @@ static void run_workers(void) {
    rt_event *bufs = mmap(NULLP, (size_t)P * WORKER_BUF_EVENTS * sizeof(rt_event), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
    assert(bufs != MAP_FAILED, "cannot map the workers' event buffers");
    fflush(NULLP);
+   const long long inf_pos0 = ftello(inf);                      /* where process_file() is in the input file */
    for (int i = 0; i < P; ++i) {
       int sv[2];
       assert(socketpair(AF_UNIX, SOCK_STREAM, 0, sv) == 0, "socketpair failed");
@@ -749,6 +751,16 @@ static void run_workers(void) {
          for (int k = 0; k < i; ++k) close(ch[k].fd);
          close(sv[0]);
          on_exit(worker_exit, NULLP);
+         {  /* An input stream of its own.  fork() leaves all processes on ONE open file description, hence on one file offset: the
+               reference keeps its place in the capture with ftello / fseeko on `inf` (save_file_position, readtape.c:1127-1140),
+               and a seek of one worker moved the others (rare, timing dependent: "unexpected file position", or a block decoded
+               from the wrong row; found by the worker fuzz on the CPU simulation at the end of round 2). */
+            char pth[64]; snprintf(pth, sizeof pth, "/proc/self/fd/%d", fileno(inf));
+            FILE *own = fopen(pth, "rb");
+            if (!own) own = fopen(indatafilename, "rb");
+            assert(own != NULLP, "a worker cannot reopen the input file");
+            assert(fseeko(own, inf_pos0, SEEK_SET) == 0, "fseek failed");
+            inf = own; }                                        /* the inherited stream is left alone (closing it would seek the shared offset) */
          setenv("RT_BRIDGE", "0", 1);                           /* lookups must stay on the host: what a bridge would prove, the parent scans */
          S.worker = i; S.nworkers = P; S.remote_fd = sv[1]; S.remote_buf = bufs + (size_t)i * WORKER_BUF_EVENTS;
          S.start_row = cut[i]; S.stop_row = cut[i + 1]; S.must_seek_start = i > 0;
@@ -814,6 +826,7 @@ static void run_workers(void) {
       part_name(name, sizeof name, i, ".tap"); remove(name); }
    if (worst == WORKER_UNPROVEN) {                              /* decode the reel in one piece after all: the tape and its scans are here */
       if (getenv("RT_STATS")) printf("  B200 scan: a worker could not prove its hand-over; decoding the reel unsplit\n");
+      assert(fseeko(inf, inf_pos0, SEEK_SET) == 0, "fseek failed");
       return; }
    if (worst != 0) exit(worst);
    if (getenv("RT_STATS")) printf("  B200 scan: %d workers; parent: %.3f s opening + upload + scan\n", P, S.s_open);
@@ -902,6 +915,17 @@ bool readblock(bool retry) {
    assert(fseeko(inf, S.base_pos + (long long)last_row * S.group_bytes + (endfile ? S.endfile_extra : 0), SEEK_SET) == 0, "fseek failed");
 
    struct results_t *result = &block.results[block.parmset];                 /* readtape.c:1509-1515 */
+   if (S.worker > 0 && (mode == GCR || mode == PE) && (result->blktype == BS_BLOCK || result->blktype == BS_BADBLOCK)) {
+      /* The reference's bit arrays (data[], data_faked[], data_time[]) are never cleared between blocks: where a track of this block
+         ended short of the longest one, the post-processing reads what EARLIER blocks left there (decode_gcr.c:503-674 tolerates two
+         bits of mismatch, decode_pe.c / decode_nrzi.c pad likewise).  A worker other than the first does not have that history --
+         its arrays hold only its own blocks -- so a PE or GCR block whose tracks differ in length cannot be proven to come out as in
+         one piece: the split ends.  (NRZI tracks differ by the trailing bit in every block, and nrzi_postprocess only reads below
+         the shortest track, decode_nrzi.c:35-75.)  (Found by the worker fuzz on windows of the GCR captures: the last byte of a block cut off by the
+         end of the tape.) */
+      int lo = INT_MAX, hi = 0;
+      for (int k = 0; k < ntrks; ++k) { if (trkstate[k].datacount < lo) lo = trkstate[k].datacount; if (trkstate[k].datacount > hi) hi = trkstate[k].datacount; }
+      if (lo != hi) { fflush(NULL); _exit(WORKER_UNPROVEN); } }
    result->errcount = result->track_mismatch + result->vparity_errs + result->ecc_errs + result->crc_errs + result->lrc_errs
                       + result->gcr_bad_sequence + result->ww_bad_length + result->ww_speed_err;
    result->warncount = result->missed_midbits + result->corrected_bits + result->gcr_bad_dgroups
