@@ -94,6 +94,7 @@ static struct {
    uint64_t stop_row;                   /* the unit boundary where the next worker starts; UINT64_MAX: run to the end */
    int must_seek_start;                 /* worker > 0: the first readblock() call only positions the file at the worker's first row */
    int remote_fd; rt_event *remote_buf; /* worker: exact scans are done by the parent (the only process with a CUDA context) */
+   volatile int *handover_ps;           /* worker: shared slot for the parameter set its NEXT block would have been tried with first */
 } S = { .worker = -1, .stop_row = UINT64_MAX, .remote_fd = -1 };
 
 static double wall(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
@@ -739,6 +740,11 @@ static void run_workers(void) {
    strcpy(base, baseoutfilename);
    rt_event *bufs = mmap(NULLP, (size_t)P * WORKER_BUF_EVENTS * sizeof(rt_event), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
    assert(bufs != MAP_FAILED, "cannot map the workers' event buffers");
+   /* the parameter set each worker hands over with (see the hand-over in readblock): -1 = none reported */
+   volatile int *final_ps = mmap(NULLP, 4096 + (size_t)P * sizeof(int), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+   assert(final_ps != MAP_FAILED, "cannot map the workers' hand-over slots");
+   for (int i = 0; i < P; ++i) final_ps[i] = -1;
+   const int ps_start = block.parmset;                          /* what every worker starts trying with */
    fflush(NULLP);
    const long long inf_pos0 = ftello(inf);                      /* where process_file() is in the input file */
    for (int i = 0; i < P; ++i) {
@@ -762,7 +768,7 @@ static void run_workers(void) {
             assert(fseeko(own, inf_pos0, SEEK_SET) == 0, "fseek failed");
             inf = own; }                                        /* the inherited stream is left alone (closing it would seek the shared offset) */
          setenv("RT_BRIDGE", "0", 1);                           /* lookups must stay on the host: what a bridge would prove, the parent scans */
-         S.worker = i; S.nworkers = P; S.remote_fd = sv[1]; S.remote_buf = bufs + (size_t)i * WORKER_BUF_EVENTS;
+         S.worker = i; S.nworkers = P; S.remote_fd = sv[1]; S.remote_buf = bufs + (size_t)i * WORKER_BUF_EVENTS; S.handover_ps = &final_ps[i];
          S.start_row = cut[i]; S.stop_row = cut[i + 1]; S.must_seek_start = i > 0;
          S.ctx = NULLP; S.ctx_valid = 0;
          S.n_events = S.n_bulk_hits = S.n_bulk_miss = S.n_restarts = S.n_exact_spans = 0; S.s_scan = S.s_replay = 0;
@@ -792,6 +798,13 @@ static void run_workers(void) {
       if (code != 0 && (worst == 0 || worst == WORKER_UNPROVEN)) worst = code;
       if (ch[i].ctx) rt_scan_end(ch[i].ctx); }
    munmap(bufs, (size_t)P * WORKER_BUF_EVENTS * sizeof(rt_event));
+   /* The reference tries the parameter sets of a block starting with the one that decoded the PREVIOUS block and stops at the first
+      clean decoding (readtape.c:1755-1795); a worker starts with the set the run started with.  Unless its neighbour in front ended
+      on exactly that set, the first block behind the boundary could be tried in another order -- and stop at another clean decoding
+      -- than in one piece: no split then. */
+   if (worst == 0 && multiple_tries)
+      for (int i = 0; i + 1 < P; ++i) if (final_ps[i] != ps_start) worst = WORKER_UNPROVEN;
+   munmap((void *)final_ps, 4096 + (size_t)P * sizeof(int));
    bool all_ok = true;
    char name[MAXPATH + 80], line[MAXLINE];
    if (worst == 0) {
@@ -883,6 +896,7 @@ bool readblock(bool retry) {
          int rc2 = rt_bulk_lookup(S.bulk[block.parmset].bulk, S.bulk[block.parmset].ci, S.stop_row, &e2, &n2, &valid2);
          if (rc2 != RT_OK && rc2 != RT_MISS) rtfatal("rt_bulk_lookup", rc2);
          if (rc2 == RT_OK && S.stop_row + valid2 == src.unit_end) {
+            if (S.handover_ps) *S.handover_ps = block.parmset;   /* the set the block in front of us would be tried with first */
             S.s_scan += wall() - w0;
             if (getenv("RT_STATS")) {
                rlog("  B200 scan: worker %d of %d: %lld events, %lld speculative hits, %lld misses, %lld restarts, %lld exact spans\n", S.worker, S.nworkers,
