@@ -929,14 +929,13 @@ bool readblock(bool retry) {
    assert(fseeko(inf, S.base_pos + (long long)last_row * S.group_bytes + (endfile ? S.endfile_extra : 0), SEEK_SET) == 0, "fseek failed");
 
    struct results_t *result = &block.results[block.parmset];                 /* readtape.c:1509-1515 */
-   if (S.worker > 0 && (mode == GCR || mode == PE) && (result->blktype == BS_BLOCK || result->blktype == BS_BADBLOCK)) {
-      /* The reference's bit arrays (data[], data_faked[], data_time[]) are never cleared between blocks: where a track of this block
-         ended short of the longest one, the post-processing reads what EARLIER blocks left there (decode_gcr.c:503-674 tolerates two
-         bits of mismatch; PE counts its parity errors up to the shortest track but writes the block at full length, decode_pe.c:57-101).  A worker other than the first does not have that history --
-         its arrays hold only its own blocks -- so a PE or GCR block whose tracks differ in length cannot be proven to come out as in
-         one piece: the split ends.  (NRZI tracks differ by the trailing bit in every block, and nrzi_postprocess only reads below
-         the shortest track, decode_nrzi.c:35-75.)  Found by the worker fuzz on windows of the GCR captures: the last byte of a block
-         cut off by the end of the tape. */
+   if (S.worker > 0 && mode == GCR && (result->blktype == BS_BLOCK || result->blktype == BS_BADBLOCK)) {
+      /* The reference's bit arrays (data[], data_time[]) are never cleared between blocks, and gcr_end_of_block lets a block whose
+         tracks differ by up to two bits through to gcr_postprocess (decode_gcr.c:684-729), which then reads what EARLIER blocks
+         left behind the end of a short track.  A worker other than the first does not have that history -- its arrays hold only
+         its own blocks -- so such a block cannot be proven to come out as in one piece: the split ends.  (NRZI and PE write and
+         check a block only up to its shortest track: decode_nrzi.c:35-75, decode_pe.c:96-102, readtape.c:1183,1214.)  Found by the
+         worker fuzz on windows of the GCR captures: the last byte of a block cut off by the end of the tape. */
       int lo = INT_MAX, hi = 0;
       for (int k = 0; k < ntrks; ++k) { if (trkstate[k].datacount < lo) lo = trkstate[k].datacount; if (trkstate[k].datacount > hi) hi = trkstate[k].datacount; }
       if (lo != hi) { fflush(NULL); _exit(WORKER_UNPROVEN); } }
