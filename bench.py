@@ -145,7 +145,7 @@ def reference_run(tile, ntiles_per_proc, nproc, steps, warmup, workdir):
 # ---- the product, end to end: TBIN file -> .tap through readtape with the B200 scan -------------------------------------------
 def product_run(tile, workdir, gpus, nproc, reps=889, ref_tiles=56, runs=2):
     """readtape_b200 (the reference's own host code with readblock() replaced, readtape_b200/host) on a reel of `reps` super-tiles
-    in the page cache, split between `nproc` worker processes (RT_WORKERS) dealt over `gpus` GPUs (RT_DEVICES), wall clock from
+    in the page cache, split between `nproc` worker processes (RT_WORKERS; one scanning parent on one GPU), wall clock from
     exec to exit; beside it the unmodified reference doing the same work with all host cores (`nproc` processes x `ref_tiles`
     super-tiles each, >= the same number of rows); the product's .tap must be the reference's."""
     exe = os.path.join(ROOT, "readtape_b200", "bin", "readtape_b200")
