@@ -892,10 +892,16 @@ bool readblock(bool retry) {
          inside blocks, at all-track drop-outs -- be followed by a worker starting in the middle of it, and a block served through
          a chain across the boundary be decoded by both workers: found by the worker fuzz on the CPU simulation, tests/test_hostsim.py.) */
       if (from_bulk && src.unit_end > S.stop_row) {
+         /* "the same unit": the same end row AND the same events (count, first, last) -- the end row alone does not identify a unit
+            near the end of the tape, where every unit is clamped to the last row */
+         const uint64_t n1 = src.n;
+         const uint64_t f1 = n1 ? src.ev[0].row : 0, l1 = n1 ? src.ev[n1 - 1].row : 0;
+         const int ft1 = n1 ? src.ev[0].trk : 0, lt1 = n1 ? src.ev[n1 - 1].trk : 0;
          const rt_event *e2 = NULLP; uint64_t n2 = 0, valid2 = 0;
          int rc2 = rt_bulk_lookup(S.bulk[block.parmset].bulk, S.bulk[block.parmset].ci, S.stop_row, &e2, &n2, &valid2);
          if (rc2 != RT_OK && rc2 != RT_MISS) rtfatal("rt_bulk_lookup", rc2);
-         if (rc2 == RT_OK && S.stop_row + valid2 == src.unit_end) {
+         if (rc2 == RT_OK && S.stop_row + valid2 == src.unit_end && n2 == n1
+             && (n1 == 0 || (e2[0].row == f1 && e2[0].trk == ft1 && e2[n1 - 1].row == l1 && e2[n1 - 1].trk == lt1))) {
             if (S.handover_ps) *S.handover_ps = block.parmset;   /* the set the block in front of us would be tried with first */
             S.s_scan += wall() - w0;
             if (getenv("RT_STATS")) {

@@ -324,6 +324,9 @@ int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event *
       int best = -1; uint64_t brow = ~0ull;
       for (uint32_t k = 0; k < nt; ++k) { const auto &v = sc.ev[lo * nt + k]; if (at[k] < v.size() && v[at[k]].row < brow) { brow = v[at[k]].row; best = (int)k; } }
       b->result.push_back(sc.ev[lo * nt + best][at[best]++]); }
+   if (getenv("HOSTSIM_TRACE")) fprintf(stderr, "[hostsim] lookup(%llu): first unit %zu [%llu, %llu), arrived at unit %zu [%llu, %llu), %zu events, first at row %lld\n", (unsigned long long)start_row,
+                                        sc.last_unit, (unsigned long long)sc.units[sc.last_unit].row0, (unsigned long long)sc.units[sc.last_unit].row_end, lo, (unsigned long long)sc.units[lo].row0,
+                                        (unsigned long long)sc.units[lo].row_end, b->result.size(), b->result.empty() ? -1ll : (long long)b->result[0].row);
    if (events) *events = b->result.data();
    if (nevents) *nevents = b->result.size();
    if (valid_rows) *valid_rows = sc.units[lo].row_end - start_row;
