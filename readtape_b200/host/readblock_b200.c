@@ -798,10 +798,10 @@ static void run_workers(void) {
       if (code != 0 && (worst == 0 || worst == WORKER_UNPROVEN)) worst = code;
       if (ch[i].ctx) rt_scan_end(ch[i].ctx); }
    munmap(bufs, (size_t)P * WORKER_BUF_EVENTS * sizeof(rt_event));
-   /* The reference tries the parameter sets of a block starting with the one that decoded the PREVIOUS block and stops at the first
-      clean decoding (readtape.c:1755-1795); a worker starts with the set the run started with.  Unless its neighbour in front ended
-      on exactly that set, the first block behind the boundary could be tried in another order -- and stop at another clean decoding
-      -- than in one piece: no split then. */
+   /* Every block is tried with `starting_parmset` first (readtape.c:1722), which stays 0 unless the reference is compiled with
+      USE_ALL_PARMSETS (then it rotates from block to block, readtape.c:1875-1878, and the try order -- hence which clean decoding a
+      block stops at -- would depend on how many blocks came before).  A cheap guard for that build: every worker must have ended on
+      the set its neighbour started trying with, else no split. */
    if (worst == 0 && multiple_tries)
       for (int i = 0; i + 1 < P; ++i) if (final_ps[i] != ps_start) worst = WORKER_UNPROVEN;
    munmap((void *)final_ps, 4096 + (size_t)P * sizeof(int));
