@@ -15,6 +15,7 @@
  * HOSTSIM_UNIT_ROWS=n additionally cuts every unit after n rows (a cut INSIDE blocks: restarts and continued exact scans).
  */
 #include "fast_host.cu"
+#include "rt_csv.h"
 #include <dlfcn.h>
 #include <unistd.h>
 #include <cstdarg>
@@ -331,5 +332,18 @@ int rt_bulk_lookup(rt_bulk *b, uint32_t ci, uint64_t start_row, const rt_event *
    if (nevents) *nevents = b->result.size();
    if (valid_rows) *valid_rows = sc.units[lo].row_end - start_row;
    return RT_OK; }
+
+/* ---- include/rt_csv.h: forwarded to the oracle (so that the Python mirror of the ABI, readtape_b200/abi.py, can load this library) ---- */
+#define CSV_FN(name) static decltype(&::name) f = (decltype(&::name))dlsym(ora().h, #name)
+int rt_csv_open(int device, const char *text, uint64_t nbytes, rt_csv **out) { CSV_FN(rt_csv_open); return f ? f(device, text, nbytes, out) : RT_ERR_UNSUPPORTED; }
+void rt_csv_close(rt_csv *csv) { CSV_FN(rt_csv_close); if (f) f(csv); }
+uint64_t rt_csv_nlines(const rt_csv *csv) { CSV_FN(rt_csv_nlines); return f ? f(csv) : 0; }
+int rt_csv_line(const rt_csv *csv, uint64_t line, uint64_t *offset, uint64_t *length) { CSV_FN(rt_csv_line); return f ? f(csv, line, offset, length) : RT_ERR_UNSUPPORTED; }
+int rt_csv_max_abs(rt_csv *csv, uint64_t first_line, uint64_t nlines, uint32_t ntrks, float scalefactor, float *max_abs) {
+   CSV_FN(rt_csv_max_abs); return f ? f(csv, first_line, nlines, ntrks, scalefactor, max_abs) : RT_ERR_UNSUPPORTED; }
+int rt_csv_convert(rt_csv *csv, const rt_csv_cfg *cfg, uint64_t first_line, uint64_t nrows, int16_t *rows_out, rt_tape *tape, rt_csv_stats *stats) {
+   if (tape) return sim_err(RT_ERR_UNSUPPORTED, "hostsim: rt_csv_convert into a tape");
+   CSV_FN(rt_csv_convert); return f ? f(csv, cfg, first_line, nrows, rows_out, nullptr, stats) : RT_ERR_UNSUPPORTED; }
+#undef CSV_FN
 
 }  /* extern "C" */
